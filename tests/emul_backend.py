@@ -1,0 +1,244 @@
+"""TEST INFRASTRUCTURE: torch (CPU) emulation of the C-ABI kernel set of libxfr_b200.so.
+
+Every method has the name, argument order and semantics of the kernel wrapper of
+the same name in xfr_b200/kernels.py (include/xfrb.h documents each).  It exists so
+that (1) the host-side schedule in xfr_b200/engine.py can be checked against the
+oracle on a machine without a GPU, and (2) each CUDA kernel can be checked on the
+GPU against a readable statement of what it must compute.  The product never
+imports this module; xfr_b200.kernels raises if the CUDA library is missing.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from xfr_b200.packing import unpack_dual_cols
+
+MODE_AWP, MODE_ALL, MODE_AFFINEONLY = 0, 1, 2
+EPS = 1e-16
+
+
+def relu(t):
+    return torch.clamp_min(t, 0)
+
+
+def hook(affine, a, x, z, mode, eps=EPS):
+    """One _backward_ebp firing without a prior (reference whitebox.py:381-430)."""
+    zh = relu(z)
+    p = a * zh
+    if mode == MODE_AWP:
+        return p / (x + eps) if affine else zh
+    if mode == MODE_ALL:
+        return p / (x + eps)
+    if mode == MODE_AFFINEONLY:
+        return p / (x + eps) if affine else z
+    raise ValueError(mode)
+
+
+def _rows(t, J):
+    """Saved tensors hold N samples; gradient tensors hold J = G*N rows (sample = j % N)."""
+    n = t.shape[0]
+    if n == J:
+        return t
+    assert J % n == 0
+    return t.repeat((J // n,) + (1,) * (t.dim() - 1))
+
+
+def im2col_nhwc(x, R, S, pad):
+    """[N,H,W,C] -> [N*H*W, R*S*C], K ordered (r, s, c); stride 1."""
+    N, H, W, C = x.shape
+    if R == 1 and S == 1:
+        return x.reshape(N * H * W, C)
+    xp = F.pad(x, (0, 0, pad, pad, pad, pad))
+    cols = [xp[:, r:r + H, s:s + W, :] for r in range(R) for s in range(S)]
+    return torch.stack(cols, dim=3).reshape(N * H * W, R * S * C)
+
+
+class EmulBackend(object):
+    name = 'emul'
+
+    def __init__(self, eps=EPS):
+        self.eps = eps
+
+    # ------------------------------------------------------------ forward
+    def stem_fwd(self, x, stem, o, mp):
+        """x [N,224,224,3]; o = conv7x7/2(x)+b [N,112,112,64]; mp = maxpool3x3/2(relu(bn(o)))."""
+        w = stem.W.view(7, 7, 3, stem.cout).permute(3, 2, 0, 1)
+        oo = F.conv2d(x.permute(0, 3, 1, 2), w, stem.b, 2, 3)
+        r1 = relu(oo * stem.bn[0].view(1, -1, 1, 1) + stem.bn[1].view(1, -1, 1, 1))
+        o.copy_(oo.permute(0, 2, 3, 1))
+        mp.copy_(F.max_pool2d(r1, 3, 2, 1).permute(0, 2, 3, 1))
+
+    def subsample2(self, u, out):
+        out.copy_(u[:, ::2, ::2, :])
+
+    def avgpool2(self, u, out):
+        out.copy_(F.avg_pool2d(u.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1))
+
+    def conv_dual(self, inp, L, o, xr, act, res=None):
+        """o = conv(inp)+b ; xr = relu(conv_{W+}(inp)+b') ; act = relu(o*alpha+beta [+ res, zero-padded channels])."""
+        A = im2col_nhwc(inp, L.R, L.S, L.R // 2)
+        D = A @ L.Bf.t() + L.bias
+        t, p = unpack_dual_cols(D, L.tn)
+        o.view(-1, L.cout).copy_(t)
+        xr.view(-1, L.cout).copy_(relu(p))
+        a = t * L.bn[0] + L.bn[1]
+        if res is not None:
+            rc = res.shape[-1]
+            a[:, :rc] += res.reshape(-1, rc)
+        act.view(-1, L.cout).copy_(relu(a))
+
+    def head_fwd(self, u, head, v, f1, xn, nrm):
+        vv = u.mean(dim=(1, 2)) if False else F.avg_pool2d(u.permute(0, 3, 1, 2), 7, 7).flatten(1)
+        ff = F.linear(vv, head.W1, head.b1)
+        nn_ = ff.norm(dim=1).clamp_min(1e-12)
+        v.copy_(vv)
+        f1.copy_(ff)
+        nrm.copy_(nn_)
+        xn.copy_(ff / nn_.unsqueeze(1))
+
+    # ------------------------------------------------------------ backward
+    def head_bwd(self, Pn, W2, head, v, xn, nrm, mode, g_out, hooked_fc2=False):
+        """Pn [J,C]; W2 [N,C,512] per-sample un-hooked classifier rows (signed) or, when
+        hooked_fc2, the network's own [C,512] fc2 (W+ and a Linear hook).
+        g_out [J,7,7,2048] = gradient w.r.t. the last block output (after AvgPool backward)."""
+        J = Pn.shape[0]
+        xn_, v_, nrm_ = _rows(xn, J), _rows(v, J), _rows(nrm, J)
+        if hooked_fc2:
+            gr = Pn @ relu(W2)
+            gr = hook(True, relu(xn_ * head.scale), relu(head.scale * relu(xn_)), gr, mode, self.eps)
+        else:
+            gr = torch.einsum('jc,jcd->jd', Pn, _rows(W2, J))
+        gr = gr * head.scale
+        f1p = F.linear(relu(v_), head.W1p, head.b1p)
+        Xmul = relu(F.normalize(f1p, p=2, dim=1))
+        gr = hook(False, relu(xn_), Xmul, gr, mode, self.eps)
+        gr = (gr - xn_ * (xn_ * gr).sum(1, keepdim=True)) / nrm_.unsqueeze(1)
+        gr = gr @ head.W1p
+        gr = hook(True, relu(v_), relu(v_), gr, mode, self.eps)     # X = relu(avgpool(relu(u))) = v since u >= 0
+        g_out.copy_((gr / 49.0).view(J, 1, 1, -1).expand(-1, 7, 7, -1))
+
+    def _mid_chain(self, z, o, xr, bn, mode):
+        alpha, beta, sp, tp = bn[0], bn[1], bn[2], bn[3]
+        a = relu(o * alpha + beta)
+        xrelu = relu(relu(o) * sp + tp)
+        z = hook(False, a, xrelu, z, mode, self.eps)     # ReLU module hook
+        z = hook(True, a, a, z, mode, self.eps)          # consumer Conv2d hook
+        z = z * (a > 0)                                  # ReLU backward
+        z = z * sp                                       # BatchNorm backward with gamma+
+        return hook(True, relu(o), xr, z, mode, self.eps)  # BatchNorm hook
+
+    def _dgrad(self, y, Bd, R):
+        """y [J,H,W,Cout] -> [J*H*W, Cin]"""
+        return im2col_nhwc(y, R, R, R // 2) @ Bd.t()
+
+    def dgrad_mid(self, y, L, o, xr, bn, mode, y_out):
+        """z = W+^T y (conv L), then the hook chain at the activation a = relu(bn(o)) that fed conv L."""
+        J = y.shape[0]
+        z = self._dgrad(y, L.Bd, L.R)
+        y_out.view(-1, L.cin).copy_(self._mid_chain(z, _rows(o, J).reshape(-1, L.cin),
+                                                     _rows(xr, J).reshape(-1, L.cin), bn, mode))
+
+    def dgrad_plain(self, y, L, z_out, signed=False):
+        z_out.view(-1, L.cin).copy_(self._dgrad(y, L.signed_dgrad() if signed else L.Bd, L.R))
+
+    def _join_chain(self, z, out, o3, xr3, bn3, res, hooks, mode):
+        """Hook chain on a block output `out` (hooks: 1 = [affine], 2 = [affine, non-affine Add],
+        3 = [affine, affine]) followed by the start of that block's main path.
+        res = the block's residual input zero-padded to C channels (only read in MODE_ALL)."""
+        alpha, beta, sp = bn3[0], bn3[1], bn3[2]
+        if mode != MODE_ALL:      # non-affine hooks ignore (a, x) in these modes
+            xblk = out
+            rres = out
+        else:
+            rres = relu(res)
+            xblk = relu(relu(o3 * alpha + beta) + rres)
+        z = hook(False, out, xblk, z, mode, self.eps)
+        z = hook(True, out, out, z, mode, self.eps)
+        if hooks == 2:
+            z = hook(False, out, out, z, mode, self.eps)
+        elif hooks == 3:
+            z = hook(True, out, out, z, mode, self.eps)
+        g = z * (out > 0)
+        zz = hook(False, rres, rres, g, mode, self.eps)      # Add slot 0 with the residual's (A, X)
+        zz = zz * sp
+        y3 = hook(True, relu(o3), xr3, zz, mode, self.eps)
+        return g, y3
+
+    def dgrad_join(self, y1, L, g_res, out, o3, xr3, bn3, res, hooks, mode, g_out, y3_out):
+        """z = W+^T y1 (1x1 conv L, stride 1) + g_res, then the join chain."""
+        J = y1.shape[0]
+        C = L.cin
+        z = self._dgrad(y1, L.Bd, 1) + g_res.reshape(-1, C)
+        r = None if res is None else _rows(res, J)
+        if r is not None:
+            r = (F.pad(r, (0, C - r.shape[-1])) if r.shape[-1] < C else r).reshape(-1, C)
+        g, y3 = self._join_chain(z, _rows(out, J).reshape(-1, C), _rows(o3, J).reshape(-1, C),
+                                 _rows(xr3, J).reshape(-1, C), bn3, r, hooks, mode)
+        g_out.view(-1, C).copy_(g)
+        y3_out.view(-1, C).copy_(y3)
+
+    def join(self, zmain, up, gres_lo, k, out, o3, xr3, bn3, res, hooks, mode, g_out, y3_out):
+        """Unfused block boundary: z[j,h,w,c] = zmain (at stride `up`: even pixels only) +
+        avgpool_k backward of gres_lo (first Cr channels), then the join chain."""
+        J, H, W, C = g_out.shape
+        z = torch.zeros(J, H, W, C)
+        z[:, ::up, ::up, :] += zmain
+        if gres_lo is not None:
+            cr = gres_lo.shape[-1]
+            z[..., :cr] += gres_lo.repeat_interleave(k, 1).repeat_interleave(k, 2) / float(k * k)
+        r = None if res is None else _rows(res, J)
+        if r is not None and r.shape[-1] < C:
+            r = F.pad(r, (0, C - r.shape[-1]))
+        g, y3 = self._join_chain(z.view(-1, C), _rows(out, J).reshape(-1, C), _rows(o3, J).reshape(-1, C),
+                                 _rows(xr3, J).reshape(-1, C), bn3, None if r is None else r.reshape(-1, C),
+                                 hooks, mode)
+        g_out.view(-1, C).copy_(g)
+        y3_out.view(-1, C).copy_(y3)
+
+    def ds_res(self, g, ap, mode, gres_lo):
+        """Residual branch of a downsample block, up to (not including) AvgPool backward:
+        Add slot-1 hook -> channel slice -> ConcatChannels hook (both non-affine, a = x = relu(ap))."""
+        J = g.shape[0]
+        cr = ap.shape[-1]
+        a = relu(_rows(ap, J))
+        z = hook(False, a, a, g[..., :cr], mode, self.eps)
+        gres_lo.copy_(hook(False, a, a, z, mode, self.eps))
+
+    def stem_bwd(self, zmain, gres, o, mp, bn, mode, P2, chansum, sums):
+        """Chain at the max-pool output (Conv2d + AvgPool2d(k=1) hooks, both affine), MaxPool
+        backward, ReLU / MaxPool2d hooks, ReLU + BN backward, BN hook -> P[-2] = relu(o)*relu(z)."""
+        J = zmain.shape[0]
+        alpha, beta, sp, tp = bn[0], bn[1], bn[2], bn[3]
+        mp_ = _rows(mp, J)
+        o_ = _rows(o, J)
+        z = zmain + gres
+        z = hook(True, mp_, mp_, z, mode, self.eps)
+        z = hook(True, mp_, mp_, z, mode, self.eps)
+        r1 = relu(o_ * alpha + beta).permute(0, 3, 1, 2)
+        _, idx = F.max_pool2d(r1, 3, 2, 1, return_indices=True)
+        zz = torch.zeros_like(r1).flatten(2).scatter_add_(2, idx.flatten(2), z.permute(0, 3, 1, 2).flatten(2))
+        zz = zz.view_as(r1).permute(0, 2, 3, 1)
+        r1 = r1.permute(0, 2, 3, 1)
+        xrelu = relu(relu(o_) * sp + tp)
+        zz = hook(False, r1, xrelu, zz, mode, self.eps)
+        zz = hook(False, r1, r1, zz, mode, self.eps)
+        zz = zz * (r1 > 0) * sp
+        p = relu(o_) * relu(zz)
+        P2.copy_(p)
+        chansum.copy_(p.sum(-1))
+        sums.copy_(p.double().sum(dim=(1, 2, 3)).float())
+
+    def contrast(self, P2, sums, N, out):
+        """out[n] = sum_c relu(P2[n]/sums[n] - P2[N+n]/sums[N+n])  (reference whitebox.py:524-526)."""
+        pm = P2[:N] / sums[:N].view(N, 1, 1, 1)
+        pn = P2[N:2 * N] / sums[N:2 * N].view(N, 1, 1, 1)
+        out.copy_(relu(pm - pn).sum(-1))
+
+    def saliency_post(self, mwp, out):
+        """gaussian(sigma=2, nearest, truncate 4) -> max(0,.) -> / max(sum, eps)  (whitebox.py:455-460)."""
+        import scipy.ndimage as ndi
+        for i in range(mwp.shape[0]):
+            img = ndi.gaussian_filter(mwp[i].numpy(), 2, mode='nearest', truncate=4.0)
+            img = np.maximum(0, img)
+            img = img / max(img.sum(), self.eps)
+            out[i].copy_(torch.from_numpy(img))

@@ -1,0 +1,223 @@
+"""Host-side schedule of the batched forward + excitation-backprop sweep for the
+STR-Janus ResNet (reference resnet.py:168-265, whitebox.py:482-527).
+
+The engine owns the packed weights and a workspace of NHWC fp32 buffers and issues
+one kernel per fused stage through a backend object:
+
+  xfr_b200.kernels.CudaBackend  - the product path: ctypes calls into libxfr_b200.so
+                                  (hand-written sm_100a kernels), launched on torch's
+                                  current CUDA stream;
+  tests/emul_backend.EmulBackend - test double used only by tests/ to check this
+                                  schedule against the oracle on a CPU-only machine.
+
+What is stored by the forward sweep, per conv c:
+  o_c  = conv_c(a_in) + b                (true pre-BN output)
+  xr_c = relu(conv_{W+}(a_in) + b)       (the X of the BatchNorm hook, whitebox.py:327)
+and per block its output `out` (needed for the hooks chained on it and as the
+residual of the next block).  Everything else (a = relu(bn(o)), the gamma+ forward,
+ReLU masks) is recomputed inside the backward epilogues from o_c.
+
+Backward rows: the gradient batch holds J = G*N rows (G seed groups, e.g. mate and
+non-mate, over the same N probes); row j reads the saved tensors of sample j % N, so
+the two contrastive sweeps share one forward and run as one batch.
+"""
+import torch
+
+from . import packing
+
+MODE_IDS = {'affineonly_with_prior': 0, 'all': 1, 'norelu': 1, 'affineonly': 2}
+STRESNET101 = (3, 4, 23, 3)
+
+
+class _Block(object):
+    pass
+
+
+class StResnetEngine(object):
+    """Batched whitebox engine for the STR ResNet topology [3,4,23,3] (or any `layers`)."""
+
+    def __init__(self, state_dict, backend, layers=STRESNET101, device='cpu', with_bias=False, tn=128,
+                 eps=1e-16):
+        self.be = backend
+        self.layers = tuple(layers)
+        self.device = torch.device(device)
+        self.with_bias = with_bias
+        self.eps = eps
+        sd = {k: v.detach().cpu() for k, v in state_dict.items()}
+        self.stem = packing.Stem(sd, with_bias=with_bias).to(self.device)
+        self.head = packing.Head(sd, with_bias=with_bias).to(self.device)
+        self.blocks = []
+        inplanes, hw = 64, 56
+        for li, (planes, n) in enumerate(zip((64, 128, 256, 512), self.layers), start=1):
+            for bi in range(n):
+                b = _Block()
+                b.name = 'layer%d.%d' % (li, bi)
+                b.stride = 2 if (bi == 0 and li > 1) else 1
+                b.has_ds = bi == 0
+                b.cin, b.planes, b.cout = inplanes, planes, planes * 4
+                b.hw_in = hw
+                hw = hw // b.stride
+                b.hw = hw
+                b.c1 = packing.ConvBN(sd, b.name + '.conv1', b.name + '.bn1', tn, with_bias).to(self.device)
+                b.c2 = packing.ConvBN(sd, b.name + '.conv2', b.name + '.bn2', tn, with_bias).to(self.device)
+                b.c3 = packing.ConvBN(sd, b.name + '.conv3', b.name + '.bn3', tn, with_bias).to(self.device)
+                self.blocks.append(b)
+                inplanes = planes * 4
+        self._ws = {}
+        self.enc_dim = 512
+
+    # ------------------------------------------------------------ workspace
+    def buf(self, name, *shape):
+        """Named fp32 buffer, allocated once per (name, shape): static addresses for graph capture."""
+        key = (name,) + tuple(shape)
+        t = self._ws.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=torch.float32, device=self.device)
+            self._ws[key] = t
+        return t
+
+    def workspace_bytes(self):
+        return sum(t.numel() * 4 for t in self._ws.values())
+
+    # ------------------------------------------------------------ forward
+    def forward(self, x_nhwc):
+        """x_nhwc [N,224,224,3] (mean-subtracted, reference whitebox.py:108-110).  Fills the saved
+        tensors and returns xn [N,512] (the unit-norm encoding; encode() = 50*xn)."""
+        be = self.be
+        N = x_nhwc.shape[0]
+        S = {'N': N}
+        S['o_s'] = self.buf('o_s', N, 112, 112, 64)
+        S['mp'] = self.buf('mp', N, 56, 56, 64)
+        be.stem_fwd(x_nhwc, self.stem, S['o_s'], S['mp'])
+        u = S['mp']
+        for i, b in enumerate(self.blocks):
+            h = b.hw
+            t = {}
+            if b.has_ds:
+                if b.stride == 2:
+                    t['ap'] = self.buf('ap%d' % i, N, h, h, b.cin)
+                    be.avgpool2(u, t['ap'])
+                    t['us'] = self.buf('us%d' % i, N, h, h, b.cin)
+                    be.subsample2(u, t['us'])
+                    cin1 = t['us']
+                else:
+                    t['ap'] = u
+                    cin1 = u
+                res = t['ap']
+            else:
+                cin1 = u
+                res = u
+            for k, c in (('1', b.planes), ('2', b.planes), ('3', b.cout)):
+                t['o' + k] = self.buf('o%s_%d' % (k, i), N, h, h, c)
+                t['xr' + k] = self.buf('xr%s_%d' % (k, i), N, h, h, c)
+            a1 = self.buf('a1', N, h, h, b.planes)
+            a2 = self.buf('a2', N, h, h, b.planes)
+            t['out'] = self.buf('out%d' % i, N, h, h, b.cout)
+            t['u'] = u
+            t['res'] = res
+            be.conv_dual(cin1, b.c1, t['o1'], t['xr1'], a1)
+            be.conv_dual(a1, b.c2, t['o2'], t['xr2'], a2)
+            be.conv_dual(a2, b.c3, t['o3'], t['xr3'], t['out'], res)
+            S[i] = t
+            u = t['out']
+        S['v'] = self.buf('v', N, 2048)
+        S['f1'] = self.buf('f1', N, 512)
+        S['xn'] = self.buf('xn', N, 512)
+        S['nrm'] = self.buf('nrm', N)
+        be.head_fwd(u, self.head, S['v'], S['f1'], S['xn'], S['nrm'])
+        self.saved = S
+        return S['xn']
+
+    # ------------------------------------------------------------ backward
+    def ebp_backward(self, Pn, W2, mode='affineonly_with_prior', hooked_fc2=False):
+        """One excitation-backprop sweep over J = Pn.shape[0] gradient rows (J % N == 0).
+        Pn [J,C] class priors; W2 [N,C,512] per-sample classifier rows (set_triplet_classifier,
+        un-hooked, signed) or the network's hooked fc2 [C,512].
+        Returns (P2 [J,112,112,64] = P[-2], chansum [J,112,112], sums [J])."""
+        be, S = self.be, self.saved
+        N = S['N']
+        J = Pn.shape[0]
+        assert J % N == 0
+        m = MODE_IDS[mode]
+        nb = len(self.blocks)
+        last = self.blocks[-1]
+        g = self.buf('g_head', J, 7, 7, last.cout)
+        be.head_bwd(Pn, W2, self.head, S['v'], S['xn'], S['nrm'], m, g, hooked_fc2)
+        # chain on the last block output (ReLU + AvgPool2d hooks) and the start of its main path
+        t = S[nb - 1]
+        gb = self.buf('g%d' % ((nb - 1) % 2), J, last.hw, last.hw, last.cout)
+        y3 = self.buf('y3', J, last.hw, last.hw, last.cout)
+        be.join(g, 1, None, 1, t['out'], t['o3'], t['xr3'], last.c3.bn, t['res'], 1, m, gb, y3)
+        for i in range(nb - 1, -1, -1):
+            b, t = self.blocks[i], S[i]
+            h = b.hw
+            y2 = self.buf('y2', J, h, h, b.planes)
+            y1 = self.buf('y1', J, h, h, b.planes)
+            be.dgrad_mid(y3, b.c3, t['o2'], t['xr2'], b.c2.bn, m, y2)
+            be.dgrad_mid(y2, b.c2, t['o1'], t['xr1'], b.c1.bn, m, y1)
+            if not b.has_ds:
+                p, tp = self.blocks[i - 1], S[i - 1]
+                gp = self.buf('g%d' % ((i - 1) % 2), J, h, h, b.cin)
+                y3 = self.buf('y3', J, h, h, b.cin)
+                be.dgrad_join(y1, b.c1, gb, tp['out'], tp['o3'], tp['xr3'], p.c3.bn, tp['res'], 2, m, gp, y3)
+                gb = gp
+                continue
+            zlo = self.buf('zlo', J, h, h, b.cin)
+            be.dgrad_plain(y1, b.c1, zlo)
+            gres = self.buf('gres', J, h, h, b.cin)
+            be.ds_res(gb, t['ap'], m, gres)
+            if i == 0:
+                P2 = self.buf('P2', J, 112, 112, 64)
+                chansum = self.buf('chansum', J, 112, 112)
+                sums = self.buf('sums', J)
+                be.stem_bwd(zlo, gres, S['o_s'], S['mp'], self.stem.bn, m, P2, chansum, sums)
+                return P2, chansum, sums
+            p, tp = self.blocks[i - 1], S[i - 1]
+            hp = b.hw_in
+            gp = self.buf('g%d' % ((i - 1) % 2), J, hp, hp, b.cin)
+            y3 = self.buf('y3', J, hp, hp, b.cin)
+            be.join(zlo, b.stride, gres, b.stride, tp['out'], tp['o3'], tp['xr3'], p.c3.bn, tp['res'], 3, m,
+                    gp, y3)
+            gb = gp
+
+    # ------------------------------------------------------------ composed operators
+    def _onehot(self, J, C, cols):
+        P = torch.zeros(J, C, dtype=torch.float32)
+        for (lo, hi), c in cols:
+            P[lo:hi, c] = 1.0
+        return P.to(self.device)
+
+    def ebp(self, x_nhwc, Pn, W2, mode='affineonly_with_prior', hooked_fc2=False, saliency=True):
+        """Whitebox.ebp over a batch (reference whitebox.py:482-504) -> [N,112,112] device tensor."""
+        self.forward(x_nhwc)
+        _, chansum, _ = self.ebp_backward(Pn, W2, mode, hooked_fc2)
+        if not saliency:
+            return chansum
+        out = self.buf('sal', chansum.shape[0], 112, 112)
+        self.be.saliency_post(chansum, out)
+        return out
+
+    def contrastive(self, x_nhwc, W2, k_pos=0, k_neg=1, mode='affineonly_with_prior', hooked_fc2=False,
+                    saliency=True, num_classes=None):
+        """Whitebox.contrastive_ebp over a batch (reference whitebox.py:506-527): one shared
+        forward, mate and non-mate sweeps as one gradient batch of 2N rows."""
+        N = x_nhwc.shape[0]
+        C = num_classes if num_classes is not None else W2.shape[-2]
+        self.forward(x_nhwc)
+        Pn = self.priors_contrastive(N, C, k_pos, k_neg)
+        P2, _, sums = self.ebp_backward(Pn, W2, mode, hooked_fc2)
+        mwp = self.buf('cmwp', N, 112, 112)
+        self.be.contrast(P2, sums, N, mwp)
+        if not saliency:
+            return mwp
+        out = self.buf('sal', N, 112, 112)
+        self.be.saliency_post(mwp, out)
+        return out
+
+    def priors_contrastive(self, N, C, k_pos, k_neg):
+        key = ('prior', N, C, k_pos, k_neg)
+        P = self._ws.get(key)
+        if P is None:
+            P = self._onehot(2 * N, C, (((0, N), k_pos), ((N, 2 * N), k_neg)))
+            self._ws[key] = P
+        return P

@@ -1,0 +1,142 @@
+"""Weight packing for the sm_100a kernels (host side, pure torch, runs once per handle).
+
+Activations live in HBM as NHWC fp32; every convolution is an implicit GEMM
+    D[m, n] = sum_k A[m, k] * B[n, k]
+with m = (image, y, x) pixel, k = (tap, input channel) and B stored K-major
+("[N][K]", the layout both the tcgen05 shared-memory descriptors and the SIMT
+kernel read).
+
+Forward "dual" pack (one GEMM gives the true and the positive pre-activation,
+reference whitebox.py:317-330 'positive_activation' pass): the N dimension holds
+W and relu(W) side by side, arranged per N-tile of width `tn` as
+    [tn/2 rows of W | the same tn/2 rows of relu(W)]
+so that one thread of the epilogue owns conv(x) and conv+(x) of the same channel.
+
+Dgrad pack: Z = W+^T Y (reference whitebox.py:371-374) is the same implicit GEMM
+with the roles of Cin/Cout swapped and the taps mirrored:
+    Bd[ci, (r', s', co)] = relu(W)[co, ci, R-1-r', S-1-s'].
+"""
+import torch
+
+BN_EPS = 1e-5
+
+
+def fold_bn(sd, name, with_bias=False):
+    """Eval-mode BatchNorm as y = x*alpha + beta (what torch's CPU kernel computes),
+    plus the positive-pass / backward constants of excitation backprop:
+      sp = relu(gamma)/sqrt(var+eps)   (BN backward with gamma+, and the gamma+ forward scale)
+      tp = beta' - mu*sp               (gamma+ forward shift; beta' = relu(beta) iff with_bias)
+    Returns a [4, C] tensor (alpha, beta, sp, tp)."""
+    g, b = sd[name + '.weight'].float(), sd[name + '.bias'].float()
+    mu, var = sd[name + '.running_mean'].float(), sd[name + '.running_var'].float()
+    inv = 1.0 / torch.sqrt(var + BN_EPS)
+    alpha = g * inv
+    beta = b - mu * alpha
+    sp = torch.clamp_min(g, 0) * inv
+    bb = torch.clamp_min(b, 0) if with_bias else b
+    tp = bb - mu * sp
+    return torch.stack((alpha, beta, sp, tp)).contiguous()
+
+
+def pack_dual_fwd(w, b, tn, with_bias=False):
+    """w [Cout,Cin,R,S], b [Cout] or None -> (Bf [2*Cout, R*S*Cin], bias [2*Cout]) in tile order."""
+    cout, cin, R, S = w.shape
+    half = tn // 2
+    assert cout % half == 0, (cout, tn)
+    wk = w.permute(0, 2, 3, 1).reshape(cout, R * S * cin).float()   # [Cout][(r,s,ci)]
+    wp = torch.clamp_min(wk, 0)
+    if b is None:
+        b = torch.zeros(cout)
+    b = b.float()
+    bp = torch.clamp_min(b, 0) if with_bias else b
+    nt = cout // half
+    Bf = torch.stack((wk.view(nt, half, -1), wp.view(nt, half, -1)), dim=1).reshape(2 * cout, -1)
+    bias = torch.stack((b.view(nt, half), bp.view(nt, half)), dim=1).reshape(2 * cout)
+    return Bf.contiguous(), bias.contiguous()
+
+
+def pack_dgrad(w, positive=True):
+    """w [Cout,Cin,R,S] -> Bd [Cin, R*S*Cout] (taps mirrored), relu'd when positive."""
+    cout, cin, R, S = w.shape
+    wf = torch.flip(w.float(), dims=(2, 3))
+    if positive:
+        wf = torch.clamp_min(wf, 0)
+    return wf.permute(1, 2, 3, 0).reshape(cin, R * S * cout).contiguous()
+
+
+def unpack_dual_cols(D, tn):
+    """[M, 2*Cout] tile-ordered GEMM result -> (true [M,Cout], pos [M,Cout])."""
+    M, n2 = D.shape
+    half = tn // 2
+    nt = n2 // tn
+    D = D.view(M, nt, 2, half)
+    return D[:, :, 0].reshape(M, nt * half), D[:, :, 1].reshape(M, nt * half)
+
+
+class ConvBN(object):
+    """One conv + its BatchNorm, packed.  Tensors move with .to(device)."""
+
+    def __init__(self, sd, conv, bn, tn, with_bias=False):
+        w = sd[conv + '.weight']
+        b = sd.get(conv + '.bias')
+        self.name = conv
+        self.cout, self.cin, self.R, self.S = w.shape
+        self.tn = tn
+        self.Bf, self.bias = pack_dual_fwd(w, b, tn, with_bias)
+        self.Bd = pack_dgrad(w, positive=True)
+        self.Bd_signed = None       # true-gradient passes (weighted subtree) pack this lazily
+        self.bn = fold_bn(sd, bn, with_bias)
+        self._w = w                 # kept for lazy packs only
+
+    def signed_dgrad(self):
+        if self.Bd_signed is None:
+            self.Bd_signed = pack_dgrad(self._w, positive=False).to(self.Bd.device)
+        return self.Bd_signed
+
+    def to(self, device):
+        for k in ('Bf', 'bias', 'Bd', 'bn'):
+            setattr(self, k, getattr(self, k).to(device))
+        if self.Bd_signed is not None:
+            self.Bd_signed = self.Bd_signed.to(device)
+        return self
+
+
+class Stem(object):
+    """7x7/2 conv, Cin=3 (reference resnet.py:177-181).  K = 147 is padded to 148."""
+
+    def __init__(self, sd, conv='conv1', bn='bn1', with_bias=False):
+        w = sd[conv + '.weight'].float()            # [64,3,7,7]
+        b = sd.get(conv + '.bias')
+        b = torch.zeros(w.shape[0]) if b is None else b.float()
+        self.cout = w.shape[0]
+        wk = w.permute(2, 3, 1, 0).reshape(147, self.cout)   # [(r,s,ci)][co]
+        self.W = wk.contiguous()
+        self.Wp = torch.clamp_min(wk, 0).contiguous()
+        self.b = b.contiguous()
+        self.bp = (torch.clamp_min(b, 0) if with_bias else b).contiguous()
+        self.bn = fold_bn(sd, bn, with_bias)
+
+    def to(self, device):
+        for k in ('W', 'Wp', 'b', 'bp', 'bn'):
+            setattr(self, k, getattr(self, k).to(device))
+        return self
+
+
+class Head(object):
+    """avgpool7 -> fc1 -> L2 normalise -> x50 -> fc2 (reference resnet.py:235-258)."""
+
+    def __init__(self, sd, with_bias=False):
+        self.W1 = sd['fc1.weight'].float().contiguous()              # [512, 2048]
+        self.b1 = sd['fc1.bias'].float().contiguous()
+        self.W1p = torch.clamp_min(self.W1, 0).contiguous()
+        self.b1p = (torch.clamp_min(self.b1, 0) if with_bias else self.b1).contiguous()
+        self.W1pT = self.W1p.t().contiguous()                        # [2048, 512]
+        self.W2 = sd['fc2.weight'].float().contiguous() if 'fc2.weight' in sd else None
+        self.scale = 50.0
+
+    def to(self, device):
+        for k in ('W1', 'b1', 'W1p', 'b1p', 'W1pT', 'W2'):
+            v = getattr(self, k)
+            if v is not None:
+                setattr(self, k, v.to(device))
+        return self
