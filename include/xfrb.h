@@ -1,0 +1,135 @@
+/* libxfr_b200.so — C ABI of the B200 (sm_100a) whitebox saliency kernels.
+ *
+ * Drop-in boundary for the excitation-backprop hot path of stresearch/xfr
+ * (python/xfr/models/whitebox.py).  The reference has no FFI of its own: its hot
+ * path is torch autograd + Python hooks.  Each entry point below replaces one
+ * fused stage of that path and cites the reference lines it stands for.  The
+ * Python host (xfr_b200/kernels.py, ctypes) is the only caller; INTEGRATION.md
+ * shows the binding.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to contiguous fp32 (double where stated),
+ *    activations are NHWC, caller-owned; nothing is allocated or freed here;
+ *  - `stream` is a cudaStream_t (as void*); all work is enqueued on it, nothing
+ *    synchronises;
+ *  - return value 0 = ok, otherwise an error code; xfrb_last_error() gives text;
+ *  - "gradient rows": a backward tensor holds J = G*N images (G seed groups over
+ *    the same N probes); row j reads the forward tensors of sample j % N;
+ *  - `mode`: 0 = affineonly_with_prior, 1 = all (== norelu without a prior),
+ *    2 = affineonly   (reference whitebox.py:397-430, no prior set);
+ *  - `impl`: 0 = fp32 CUDA-core implicit GEMM, 1 = tcgen05 3xTF32 (fp32-equivalent),
+ *    2 = tcgen05 single-pass TF32;
+ *  - `bn` is [4][C]: alpha, beta (eval BatchNorm y = x*alpha+beta), sp = relu(gamma)/sigma,
+ *    tp = beta' - mu*sp (the gamma+ forward of the 'positive_activation' pass).
+ */
+#ifndef XFRB_H_
+#define XFRB_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XFRB_MODE_AWP 0
+#define XFRB_MODE_ALL 1
+#define XFRB_MODE_AFFINEONLY 2
+
+#define XFRB_IMPL_FP32 0
+#define XFRB_IMPL_TF32X3 1
+#define XFRB_IMPL_TF32 2
+
+int xfrb_version(void);
+const char* xfrb_last_error(void);
+/* 1 when the device under the current context is compute capability 10.x */
+int xfrb_device_ok(void);
+/* 1 when GEMM implementation `impl` (XFRB_IMPL_*) is compiled into this library */
+int xfrb_impl_available(int impl);
+
+/* ---- forward ("activation" + "positive_activation" passes, whitebox.py:490-493) ---- */
+
+/* STR ResNet stem: o = conv7x7/2(x)+b  [N,112,112,64];  mp = maxpool3x3/2(relu(bn(o))) [N,56,56,64]
+ * (reference resnet.py:225-228).  W is [147][64] ((r,s,ci) major), x is [N,224,224,3]. */
+int xfrb_stem_fwd(const float* x, const float* W, const float* b, const float* bn,
+                  float* o, float* mp, int N, void* stream);
+
+/* u[N,H,W,C] -> out[N,H/2,W/2,C]: even pixels (input of a stride-2 1x1 conv, resnet.py:116) */
+int xfrb_subsample2(const float* u, float* out, int N, int H, int W, int C, void* stream);
+/* u[N,H,W,C] -> out[N,H/2,W/2,C]: AvgPool2d(2,2) of the shortcut (resnet.py:211) */
+int xfrb_avgpool2(const float* u, float* out, int N, int H, int W, int C, void* stream);
+
+/* One conv of a Bottleneck in both passes at once (resnet.py:132-149; whitebox.py:317-330):
+ *   o   = conv_W(inp) + b                     [N,H,W,Cout]   (true pre-BN output)
+ *   xr  = relu(conv_relu(W)(inp) + b')        [N,H,W,Cout]   (X of the BatchNorm hook)
+ *   act = relu(o*alpha + beta + res)          [N,H,W,Cout]   (res: [N,H,W,res_c], zero beyond res_c; may be NULL)
+ * Bf/bias: dual pack of xfr_b200/packing.py (tile width tn).  R = 1 or 3, stride 1, pad R/2. */
+int xfrb_conv_dual(const float* inp, const float* Bf, const float* bias, const float* bn,
+                   const float* res, int res_c, float* o, float* xr, float* act,
+                   int N, int H, int W, int Cin, int Cout, int R, int tn, int impl, void* stream);
+
+/* avgpool7 -> fc1 (+ the W+ twin) -> L2 normalise (resnet.py:235-252).
+ * B1 = dual pack of fc1 [1024][2048], bias1 [1024] (tile width tn); scratch [N,1024].
+ * v [N,2048], f1 [N,512], f1p [N,512] (fc1 with relu(W) on relu(v)), xn [N,512], nrm [N]. */
+int xfrb_head_fwd(const float* u, const float* B1, const float* bias1, int tn, float* scratch,
+                  float* v, float* f1, float* f1p, float* xn, float* nrm, int N, int impl, void* stream);
+
+/* ---- backward (the 'ebp' pass + Xn.backward(Pn), whitebox.py:496-498) ---- */
+
+/* Head: seed = Pn @ W2 (un-hooked per-sample triplet classifier, whitebox.py:93-96), x50,
+ * Multiply hook, Jacobian of F.normalize, fc1 with relu(W) (W1pT [2048][512]), Linear hook,
+ * AvgPool2d(7) backward.  Pn [J,C], W2 [N,C,512]; scratch [J,2560]; g_out [J,7,7,2048]. */
+int xfrb_head_bwd(const float* Pn, const float* W2, int C, const float* W1pT,
+                  const float* v, const float* f1p, const float* xn, const float* nrm,
+                  float* scratch, float* g_out, int J, int N, int mode, float eps, int impl, void* stream);
+
+/* z = relu(W)^T y through conv (R = 1|3), then the hook chain at the activation
+ * a = relu(bn(o)) feeding that conv: ReLU hook, Conv2d hook, ReLU backward, BatchNorm
+ * backward with gamma+, BatchNorm hook (whitebox.py:381-430).  y [J,H,W,Cout] -> y_out [J,H,W,Cin];
+ * o, xr [N,H,W,Cin] are the saved tensors of the conv that PRODUCED a; bn is its BatchNorm. */
+int xfrb_dgrad_mid(const float* y, const float* Bd, const float* o, const float* xr, const float* bn,
+                   float* y_out, int J, int N, int H, int W, int Cin, int Cout, int R,
+                   int mode, float eps, int impl, void* stream);
+
+/* z_out = B^T y only (downsample blocks' conv1; true-gradient passes of weighted_subtree_ebp). */
+int xfrb_dgrad_plain(const float* y, const float* Bd, float* z_out,
+                     int J, int H, int W, int Cin, int Cout, int R, int impl, void* stream);
+
+/* Identity-block boundary: z = relu(W1)^T y1 + g_res, hooks chained on the previous block's
+ * output `out` (ReLU; Conv2d; then `hooks`: 1 none, 2 Add(non-affine), 3 AvgPool2d(affine)),
+ * ReLU backward -> g_out; then Add slot-0 hook (residual's (A,X): the late-binding closure of
+ * whitebox.py:379-432), BatchNorm backward, BatchNorm hook -> y3_out.  All [.,H,W,C], C = Cin. */
+int xfrb_dgrad_join(const float* y1, const float* Bd, const float* g_res,
+                    const float* out, const float* o3, const float* xr3, const float* bn3,
+                    const float* res, int res_c, float* g_out, float* y3_out,
+                    int J, int N, int H, int W, int Cin, int Cout,
+                    int hooks, int mode, float eps, int impl, void* stream);
+
+/* Same boundary without the GEMM (head -> last block, and below a downsample block):
+ * z[j,h,w,c] = zmain[j,h/up,w/up,c] on pixels divisible by `up` (else 0)
+ *            + gres_lo[j,h/k,w/k,c]/(k*k) for c < gres_c   (AvgPool2d(k) backward). */
+int xfrb_join(const float* zmain, int up, const float* gres_lo, int gres_c, int k,
+              const float* out, const float* o3, const float* xr3, const float* bn3,
+              const float* res, int res_c, float* g_out, float* y3_out,
+              int J, int N, int H, int W, int C, int hooks, int mode, float eps, void* stream);
+
+/* Shortcut branch of a downsample block up to AvgPool backward: Add slot-1 hook, channel
+ * slice, ConcatChannels hook (resnet.py:152-157).  g [J,H,W,C], ap [N,H,W,Cr] -> gres_lo [J,H,W,Cr]. */
+int xfrb_ds_res(const float* g, const float* ap, float* gres_lo,
+                int J, int N, int H, int W, int C, int Cr, int mode, float eps, void* stream);
+
+/* Stem: hooks on the max-pool output, MaxPool backward (first maximum wins, as torch),
+ * ReLU / MaxPool2d hooks, ReLU + BatchNorm backward, BatchNorm hook:
+ *   P2 = P[-2] = relu(o)*relu(z) [J,112,112,64]; chansum [J,112,112]; sums [J] (double).
+ * zc is scratch [J,56,56,64]. */
+int xfrb_stem_bwd(const float* zmain, const float* gres, const float* o, const float* mp, const float* bn,
+                  float* zc, float* P2, float* chansum, double* sums,
+                  int J, int N, int mode, float eps, void* stream);
+
+/* out[n] = sum_c relu(P2[n]/sums[n] - P2[N+n]/sums[N+n])  (whitebox.py:524-526) */
+int xfrb_contrast(const float* P2, const double* sums, float* out, int N, int HW, int C, void* stream);
+
+/* skimage.filters.gaussian(sigma=2) -> max(0,.) -> /max(sum,eps)  (whitebox.py:455-460); [B,H,W], H,W <= 128 */
+int xfrb_saliency_post(const float* mwp, float* out, int B, int H, int W, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XFRB_H_ */

@@ -87,17 +87,19 @@ class EmulBackend(object):
             a[:, :rc] += res.reshape(-1, rc)
         act.view(-1, L.cout).copy_(relu(a))
 
-    def head_fwd(self, u, head, v, f1, xn, nrm):
-        vv = u.mean(dim=(1, 2)) if False else F.avg_pool2d(u.permute(0, 3, 1, 2), 7, 7).flatten(1)
-        ff = F.linear(vv, head.W1, head.b1)
+    def head_fwd(self, u, head, v, f1, f1p, xn, nrm):
+        """v = avgpool7(u); (f1 | f1p) = one dual GEMM v @ [W1 ; relu(W1)]^T + (b | b'); xn = f1/|f1|."""
+        vv = F.avg_pool2d(u.permute(0, 3, 1, 2), 7, 7).flatten(1)
+        ff, fp = unpack_dual_cols(vv @ head.B1.t() + head.bias1, head.tn)
         nn_ = ff.norm(dim=1).clamp_min(1e-12)
         v.copy_(vv)
         f1.copy_(ff)
+        f1p.copy_(fp)
         nrm.copy_(nn_)
         xn.copy_(ff / nn_.unsqueeze(1))
 
     # ------------------------------------------------------------ backward
-    def head_bwd(self, Pn, W2, head, v, xn, nrm, mode, g_out, hooked_fc2=False):
+    def head_bwd(self, Pn, W2, head, v, f1p, xn, nrm, mode, g_out, hooked_fc2=False):
         """Pn [J,C]; W2 [N,C,512] per-sample un-hooked classifier rows (signed) or, when
         hooked_fc2, the network's own [C,512] fc2 (W+ and a Linear hook).
         g_out [J,7,7,2048] = gradient w.r.t. the last block output (after AvgPool backward)."""
@@ -109,11 +111,10 @@ class EmulBackend(object):
         else:
             gr = torch.einsum('jc,jcd->jd', Pn, _rows(W2, J))
         gr = gr * head.scale
-        f1p = F.linear(relu(v_), head.W1p, head.b1p)
-        Xmul = relu(F.normalize(f1p, p=2, dim=1))
+        Xmul = relu(F.normalize(_rows(f1p, J), p=2, dim=1))
         gr = hook(False, relu(xn_), Xmul, gr, mode, self.eps)
         gr = (gr - xn_ * (xn_ * gr).sum(1, keepdim=True)) / nrm_.unsqueeze(1)
-        gr = gr @ head.W1p
+        gr = gr @ head.W1pT.t()
         gr = hook(True, relu(v_), relu(v_), gr, mode, self.eps)     # X = relu(avgpool(relu(u))) = v since u >= 0
         g_out.copy_((gr / 49.0).view(J, 1, 1, -1).expand(-1, 7, 7, -1))
 
@@ -226,12 +227,13 @@ class EmulBackend(object):
         p = relu(o_) * relu(zz)
         P2.copy_(p)
         chansum.copy_(p.sum(-1))
-        sums.copy_(p.double().sum(dim=(1, 2, 3)).float())
+        sums.copy_(p.double().sum(dim=(1, 2, 3)))
 
     def contrast(self, P2, sums, N, out):
         """out[n] = sum_c relu(P2[n]/sums[n] - P2[N+n]/sums[N+n])  (reference whitebox.py:524-526)."""
-        pm = P2[:N] / sums[:N].view(N, 1, 1, 1)
-        pn = P2[N:2 * N] / sums[N:2 * N].view(N, 1, 1, 1)
+        sf = sums.float()
+        pm = P2[:N] / sf[:N].view(N, 1, 1, 1)
+        pn = P2[N:2 * N] / sf[N:2 * N].view(N, 1, 1, 1)
         out.copy_(relu(pm - pn).sum(-1))
 
     def saliency_post(self, mwp, out):

@@ -1,0 +1,206 @@
+// extern "C" surface of libxfr_b200.so (see include/xfrb.h for the contract of every call).
+#include "../../include/xfrb.h"
+#include "common.cuh"
+#include <stdio.h>
+#include <string.h>
+
+namespace xfrb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* what, cudaError_t e) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, e == cudaSuccess ? "invalid argument" : cudaGetErrorString(e));
+}
+
+// forward declarations of the stage launchers (stages.cu)
+cudaError_t launch_stem_fwd(const float*, const float*, const float*, const float*, float*, float*, int, cudaStream_t);
+cudaError_t launch_subsample2(const float*, float*, int, int, int, int, cudaStream_t);
+cudaError_t launch_avgpool2(const float*, float*, int, int, int, int, cudaStream_t);
+cudaError_t launch_avgpool7(const float*, float*, int, int, cudaStream_t);
+cudaError_t launch_head_norm(const float*, int, float*, float*, float*, float*, int, cudaStream_t);
+cudaError_t launch_head_bwd_a(const float*, const float*, int, const float*, const float*, const float*, float*, int, int,
+                              int, float, cudaStream_t);
+cudaError_t launch_head_bwd_b(const float*, const float*, float*, int, int, int, int, float, cudaStream_t);
+cudaError_t launch_join(const JoinArgs&, cudaStream_t);
+cudaError_t launch_ds_res(const float*, const float*, float*, int, int, int, int, int, int, int, float, cudaStream_t);
+cudaError_t launch_stem_bwd(const float*, const float*, const float*, const float*, const float*, float*, float*, float*,
+                            double*, int, int, int, float, cudaStream_t);
+cudaError_t launch_contrast(const float*, const double*, float*, int, int, int, cudaStream_t);
+cudaError_t launch_saliency_post(const float*, float*, int, int, int, float, cudaStream_t);
+
+static int finish(const char* what, cudaError_t e) {
+    if (e != cudaSuccess) {
+        set_error(what, e);
+        return (int)e;
+    }
+    return 0;
+}
+
+static cudaError_t run_gemm(const float* A, const float* B, const ConvGeom& g, const EpiParams& ep, int impl, cudaStream_t st) {
+    if (impl == XFRB_IMPL_FP32) return launch_conv_simt(A, B, g, ep, st);
+    if (impl == XFRB_IMPL_TF32X3 || impl == XFRB_IMPL_TF32) return launch_conv_tc(A, B, g, ep, impl == XFRB_IMPL_TF32X3, st);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace xfrb
+
+using namespace xfrb;
+
+extern "C" {
+
+int xfrb_version(void) { return 1; }
+const char* xfrb_last_error(void) { return g_err; }
+
+int xfrb_device_ok(void) {
+    int dev = 0;
+    cudaDeviceProp p;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
+    return p.major == 10 ? 1 : 0;
+}
+
+int xfrb_impl_available(int impl) {
+    if (impl == XFRB_IMPL_FP32) return 1;
+    if (impl == XFRB_IMPL_TF32X3 || impl == XFRB_IMPL_TF32) return conv_tc_available() ? 1 : 0;
+    return 0;
+}
+
+int xfrb_stem_fwd(const float* x, const float* W, const float* b, const float* bn, float* o, float* mp, int N, void* stream) {
+    return finish("xfrb_stem_fwd", launch_stem_fwd(x, W, b, bn, o, mp, N, (cudaStream_t)stream));
+}
+
+int xfrb_subsample2(const float* u, float* out, int N, int H, int W, int C, void* stream) {
+    if ((H | W) & 1 || C % 4) return finish("xfrb_subsample2", cudaErrorInvalidValue);
+    return finish("xfrb_subsample2", launch_subsample2(u, out, N, H, W, C, (cudaStream_t)stream));
+}
+
+int xfrb_avgpool2(const float* u, float* out, int N, int H, int W, int C, void* stream) {
+    if ((H | W) & 1 || C % 4) return finish("xfrb_avgpool2", cudaErrorInvalidValue);
+    return finish("xfrb_avgpool2", launch_avgpool2(u, out, N, H, W, C, (cudaStream_t)stream));
+}
+
+int xfrb_conv_dual(const float* inp, const float* Bf, const float* bias, const float* bn, const float* res, int res_c,
+                   float* o, float* xr, float* act, int N, int H, int W, int Cin, int Cout, int R, int tn, int impl,
+                   void* stream) {
+    if ((R != 1 && R != 3) || tn != 128 || Cout % 64 || (res && res_c % 4)) return finish("xfrb_conv_dual", cudaErrorInvalidValue);
+    ConvGeom g{H, W, Cin, R, R * R * Cin, 2 * Cout};
+    EpiParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.kind = EPI_FWD_DUAL;
+    ep.M = ep.Ms = N * H * W;
+    ep.C = Cout;
+    ep.bias = bias; ep.bn = bn; ep.res = res; ep.res_c = res_c;
+    ep.out0 = o; ep.out1 = xr; ep.out2 = act;
+    return finish("xfrb_conv_dual", run_gemm(inp, Bf, g, ep, impl, (cudaStream_t)stream));
+}
+
+int xfrb_head_fwd(const float* u, const float* B1, const float* bias1, int tn, float* scratch, float* v, float* f1, float* f1p,
+                  float* xn, float* nrm, int N, int impl, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = launch_avgpool7(u, v, N, 2048, st);
+    if (e != cudaSuccess) return finish("xfrb_head_fwd/avgpool", e);
+    ConvGeom g{1, 1, 2048, 1, 2048, 1024};
+    EpiParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.kind = EPI_PLAIN;
+    ep.M = ep.Ms = N;
+    ep.C = 1024;
+    ep.bias = bias1;
+    ep.out0 = scratch;
+    e = run_gemm(v, B1, g, ep, impl, st);
+    if (e != cudaSuccess) return finish("xfrb_head_fwd/fc1", e);
+    return finish("xfrb_head_fwd/norm", launch_head_norm(scratch, tn, f1, f1p, xn, nrm, N, st));
+}
+
+int xfrb_head_bwd(const float* Pn, const float* W2, int C, const float* W1pT, const float* v, const float* f1p, const float* xn,
+                  const float* nrm, float* scratch, float* g_out, int J, int N, int mode, float eps, int impl, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = launch_head_bwd_a(Pn, W2, C, f1p, xn, nrm, scratch, J, N, mode, eps, st);
+    if (e != cudaSuccess) return finish("xfrb_head_bwd/a", e);
+    // z [J,2048] = scratch [J,512] @ relu(W1) ; staged in the tail of g_out, then expanded in place order-safely:
+    // g_out is [J,49,2048]; z is written to a separate region at the END of g_out (last J*2048 floats) only if J*2048
+    // <= room; to stay simple and race-free we use a dedicated slice: scratch + J*512 must hold J*2048 floats.
+    float* z = scratch + (size_t)J * 512;
+    ConvGeom g{1, 1, 512, 1, 512, 2048};
+    EpiParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.kind = EPI_PLAIN;
+    ep.M = ep.Ms = J;
+    ep.C = 2048;
+    ep.out0 = z;
+    e = run_gemm(scratch, W1pT, g, ep, impl, st);
+    if (e != cudaSuccess) return finish("xfrb_head_bwd/fc1", e);
+    return finish("xfrb_head_bwd/b", launch_head_bwd_b(z, v, g_out, J, N, 2048, mode, eps, st));
+}
+
+int xfrb_dgrad_mid(const float* y, const float* Bd, const float* o, const float* xr, const float* bn, float* y_out, int J, int N,
+                   int H, int W, int Cin, int Cout, int R, int mode, float eps, int impl, void* stream) {
+    if (R != 1 && R != 3) return finish("xfrb_dgrad_mid", cudaErrorInvalidValue);
+    ConvGeom g{H, W, Cout, R, R * R * Cout, Cin};
+    EpiParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.kind = EPI_MID;
+    ep.M = J * H * W; ep.Ms = N * H * W;
+    ep.C = Cin;
+    ep.mode = mode; ep.eps = eps;
+    ep.bn = bn; ep.o = o; ep.xr = xr;
+    ep.out0 = y_out;
+    return finish("xfrb_dgrad_mid", run_gemm(y, Bd, g, ep, impl, (cudaStream_t)stream));
+}
+
+int xfrb_dgrad_plain(const float* y, const float* Bd, float* z_out, int J, int H, int W, int Cin, int Cout, int R, int impl,
+                     void* stream) {
+    if (R != 1 && R != 3) return finish("xfrb_dgrad_plain", cudaErrorInvalidValue);
+    ConvGeom g{H, W, Cout, R, R * R * Cout, Cin};
+    EpiParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.kind = EPI_PLAIN;
+    ep.M = ep.Ms = J * H * W;
+    ep.C = Cin;
+    ep.out0 = z_out;
+    return finish("xfrb_dgrad_plain", run_gemm(y, Bd, g, ep, impl, (cudaStream_t)stream));
+}
+
+int xfrb_dgrad_join(const float* y1, const float* Bd, const float* g_res, const float* out, const float* o3, const float* xr3,
+                    const float* bn3, const float* res, int res_c, float* g_out, float* y3_out, int J, int N, int H, int W,
+                    int Cin, int Cout, int hooks, int mode, float eps, int impl, void* stream) {
+    ConvGeom g{H, W, Cout, 1, Cout, Cin};
+    EpiParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.kind = EPI_JOIN;
+    ep.M = J * H * W; ep.Ms = N * H * W;
+    ep.C = Cin;
+    ep.mode = mode; ep.hooks = hooks; ep.eps = eps;
+    ep.bn = bn3; ep.o = o3; ep.xr = xr3; ep.outp = out; ep.g_res = g_res; ep.res = res; ep.res_c = res_c;
+    ep.out0 = g_out; ep.out1 = y3_out;
+    return finish("xfrb_dgrad_join", run_gemm(y1, Bd, g, ep, impl, (cudaStream_t)stream));
+}
+
+int xfrb_join(const float* zmain, int up, const float* gres_lo, int gres_c, int k, const float* out, const float* o3,
+              const float* xr3, const float* bn3, const float* res, int res_c, float* g_out, float* y3_out, int J, int N, int H,
+              int W, int C, int hooks, int mode, float eps, void* stream) {
+    if (C % 4 || (gres_lo && gres_c % 4) || (res && res_c % 4) || up < 1 || k < 1) return finish("xfrb_join", cudaErrorInvalidValue);
+    JoinArgs a{zmain, up, gres_lo, gres_c, k, out, o3, xr3, bn3, res, res_c, g_out, y3_out, J, N, H, W, C, hooks, mode, eps};
+    return finish("xfrb_join", launch_join(a, (cudaStream_t)stream));
+}
+
+int xfrb_ds_res(const float* g, const float* ap, float* gres_lo, int J, int N, int H, int W, int C, int Cr, int mode, float eps,
+                void* stream) {
+    if (C % 4 || Cr % 4) return finish("xfrb_ds_res", cudaErrorInvalidValue);
+    return finish("xfrb_ds_res", launch_ds_res(g, ap, gres_lo, J, N, H, W, C, Cr, mode, eps, (cudaStream_t)stream));
+}
+
+int xfrb_stem_bwd(const float* zmain, const float* gres, const float* o, const float* mp, const float* bn, float* zc, float* P2,
+                  float* chansum, double* sums, int J, int N, int mode, float eps, void* stream) {
+    return finish("xfrb_stem_bwd", launch_stem_bwd(zmain, gres, o, mp, bn, zc, P2, chansum, sums, J, N, mode, eps, (cudaStream_t)stream));
+}
+
+int xfrb_contrast(const float* P2, const double* sums, float* out, int N, int HW, int C, void* stream) {
+    return finish("xfrb_contrast", launch_contrast(P2, sums, out, N, HW, C, (cudaStream_t)stream));
+}
+
+int xfrb_saliency_post(const float* mwp, float* out, int B, int H, int W, float eps, void* stream) {
+    if (H > 128 || W > 128) return finish("xfrb_saliency_post", cudaErrorInvalidValue);
+    return finish("xfrb_saliency_post", launch_saliency_post(mwp, out, B, H, W, eps, (cudaStream_t)stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,172 @@
+// Shared device helpers: the excitation-backprop hook algebra used by every epilogue.
+// Mirrors reference python/xfr/models/whitebox.py:381-430 (_backward_ebp, no prior set).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define XFRB_MODE_AWP 0
+#define XFRB_MODE_ALL 1
+#define XFRB_MODE_AFFINEONLY 2
+
+namespace xfrb {
+
+void set_error(const char* what, cudaError_t e);
+int check_launch(const char* what);
+
+__device__ __forceinline__ float relu(float v) { return fmaxf(v, 0.f); }
+
+// One hook firing: zh = relu(z); p = a*zh; return p/(x+eps) | zh | z  depending on mode/kind.
+template <bool AFFINE>
+__device__ __forceinline__ float hook(float a, float x, float z, int mode, float eps) {
+    float zh = fmaxf(z, 0.f);
+    if (AFFINE || mode == XFRB_MODE_ALL) return __fdiv_rn(__fmul_rn(a, zh), __fadd_rn(x, eps));
+    return mode == XFRB_MODE_AWP ? zh : z;
+}
+
+struct BnC {  // per-channel BatchNorm constants (see include/xfrb.h)
+    float alpha, beta, sp, tp;
+};
+
+__device__ __forceinline__ float bn_act(float o, const BnC& b) {  // a = relu(bn(o))
+    return fmaxf(__fadd_rn(__fmul_rn(o, b.alpha), b.beta), 0.f);
+}
+
+// Chain at an inner activation a = relu(bn(o)) (ReLU hook, Conv2d hook, ReLU bwd, BN bwd, BN hook).
+__device__ __forceinline__ float mid_chain(float z, float o, float xr, const BnC& b, int mode, float eps) {
+    float a = bn_act(o, b);
+    float ro = fmaxf(o, 0.f);
+    float xrelu = fmaxf(__fadd_rn(__fmul_rn(ro, b.sp), b.tp), 0.f);
+    z = hook<false>(a, xrelu, z, mode, eps);
+    z = hook<true>(a, a, z, mode, eps);
+    z = a > 0.f ? z : 0.f;
+    z = __fmul_rn(z, b.sp);
+    return hook<true>(ro, xr, z, mode, eps);
+}
+
+// Chain on a block output `out` + start of that block's main path.
+// hooks: 1 = [affine], 2 = [affine, non-affine], 3 = [affine, affine].
+__device__ __forceinline__ void join_chain(float z, float out, float o3, float xr3, float res, const BnC& b,
+                                           int hooks, int mode, float eps, float& g, float& y3) {
+    float rres = fmaxf(res, 0.f);
+    float xblk = out;
+    if (mode == XFRB_MODE_ALL) xblk = fmaxf(__fadd_rn(fmaxf(__fadd_rn(__fmul_rn(o3, b.alpha), b.beta), 0.f), rres), 0.f);
+    z = hook<false>(out, xblk, z, mode, eps);
+    z = hook<true>(out, out, z, mode, eps);
+    if (hooks == 2) z = hook<false>(out, out, z, mode, eps);
+    else if (hooks == 3) z = hook<true>(out, out, z, mode, eps);
+    g = out > 0.f ? z : 0.f;
+    float zz = hook<false>(rres, rres, g, mode, eps);
+    zz = __fmul_rn(zz, b.sp);
+    y3 = hook<true>(fmaxf(o3, 0.f), xr3, zz, mode, eps);
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// ---------------- epilogue parameter block shared by the SIMT and tcgen05 GEMMs ----------------
+enum EpiKind { EPI_PLAIN = 0, EPI_FWD_DUAL = 1, EPI_MID = 2, EPI_JOIN = 3 };
+
+struct EpiParams {
+    int kind;
+    int M;        // rows of the GEMM (J*H*W or N*H*W)
+    int Ms;       // rows of the saved tensors (N*H*W); row m reads m % Ms
+    int C;        // channels of the output tensors (Cout for FWD_DUAL, GEMM N otherwise)
+    int mode, hooks;
+    float eps;
+    const float* bias;   // FWD_DUAL: [2C] tile order ; PLAIN: optional [N] bias
+    const float* bn;     // [4][C]
+    const float* res;    // FWD_DUAL: residual [Ms, res_c] ; JOIN: block residual (MODE_ALL only)
+    int res_c;
+    const float* o;      // MID: o ; JOIN: o3
+    const float* xr;     // MID: xr ; JOIN: xr3
+    const float* outp;   // JOIN: previous block output
+    const float* g_res;  // JOIN: residual-path gradient [M, C]
+    float* out0;         // PLAIN: z ; FWD_DUAL: o ; MID: y_out ; JOIN: g_out
+    float* out1;         // FWD_DUAL: xr ; JOIN: y3_out
+    float* out2;         // FWD_DUAL: act
+};
+
+// 4 consecutive channels (c..c+3) of one row.  acc = true/only accumulator, accp = positive twin (FWD_DUAL).
+__device__ __forceinline__ void epilogue4(const EpiParams& P, int m, int c, float4 acc, float4 accp,
+                                          float4 bias_t, float4 bias_p) {
+    const size_t off = (size_t)m * P.C + c;
+    if (P.kind == EPI_PLAIN) {
+        st4(P.out0 + off, acc);
+        return;
+    }
+    const float* bnp = P.bn + c;
+    float4 al = ld4(bnp), be = ld4(bnp + P.C), sp = ld4(bnp + 2 * P.C), tp = ld4(bnp + 3 * P.C);
+    BnC b[4] = {{al.x, be.x, sp.x, tp.x}, {al.y, be.y, sp.y, tp.y}, {al.z, be.z, sp.z, tp.z}, {al.w, be.w, sp.w, tp.w}};
+    float a[4] = {acc.x, acc.y, acc.z, acc.w};
+    if (P.kind == EPI_FWD_DUAL) {
+        float ap[4] = {accp.x, accp.y, accp.z, accp.w};
+        float bt[4] = {bias_t.x, bias_t.y, bias_t.z, bias_t.w};
+        float bp[4] = {bias_p.x, bias_p.y, bias_p.z, bias_p.w};
+        float r[4] = {0.f, 0.f, 0.f, 0.f};
+        if (P.res != nullptr && c < P.res_c) {
+            float4 rv = ld4(P.res + (size_t)m * P.res_c + c);
+            r[0] = rv.x; r[1] = rv.y; r[2] = rv.z; r[3] = rv.w;
+        }
+        float o[4], x[4], act[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            o[i] = __fadd_rn(a[i], bt[i]);
+            x[i] = fmaxf(__fadd_rn(ap[i], bp[i]), 0.f);
+            act[i] = fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(o[i], b[i].alpha), b[i].beta), r[i]), 0.f);
+        }
+        st4(P.out0 + off, make_float4(o[0], o[1], o[2], o[3]));
+        st4(P.out1 + off, make_float4(x[0], x[1], x[2], x[3]));
+        st4(P.out2 + off, make_float4(act[0], act[1], act[2], act[3]));
+        return;
+    }
+    const int ms = m % P.Ms;
+    const size_t offs = (size_t)ms * P.C + c;
+    float4 ov = ld4(P.o + offs), xv = ld4(P.xr + offs);
+    float o[4] = {ov.x, ov.y, ov.z, ov.w}, x[4] = {xv.x, xv.y, xv.z, xv.w};
+    if (P.kind == EPI_MID) {
+        float y[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = mid_chain(a[i], o[i], x[i], b[i], P.mode, P.eps);
+        st4(P.out0 + off, make_float4(y[0], y[1], y[2], y[3]));
+        return;
+    }
+    // EPI_JOIN
+    float4 gv = ld4(P.g_res + off), uv = ld4(P.outp + offs);
+    float gr[4] = {gv.x, gv.y, gv.z, gv.w}, u[4] = {uv.x, uv.y, uv.z, uv.w};
+    float r[4] = {0.f, 0.f, 0.f, 0.f};
+    if (P.mode == XFRB_MODE_ALL && P.res != nullptr && c < P.res_c) {
+        float4 rv = ld4(P.res + (size_t)ms * P.res_c + c);
+        r[0] = rv.x; r[1] = rv.y; r[2] = rv.z; r[3] = rv.w;
+    }
+    float g[4], y3[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        join_chain(__fadd_rn(a[i], gr[i]), u[i], o[i], x[i], r[i], b[i], P.hooks, P.mode, P.eps, g[i], y3[i]);
+    st4(P.out0 + off, make_float4(g[0], g[1], g[2], g[3]));
+    st4(P.out1 + off, make_float4(y3[0], y3[1], y3[2], y3[3]));
+}
+
+// geometry of the implicit GEMM:  A[m, (r,s,ci)] = in[n, h+r-pad, w+s-pad, ci]
+struct ConvGeom {
+    int H, W, Cin;   // spatial size (stride 1, same in/out) and channels of the A operand
+    int R;           // 1 or 3
+    int K;           // R*R*Cin
+    int Nn;          // GEMM N (rows of B)
+};
+
+// arguments of the unfused block-boundary kernel (xfrb_join)
+struct JoinArgs {
+    const float* zmain; int up;
+    const float* gres_lo; int gres_c, k;
+    const float* out; const float* o3; const float* xr3; const float* bn3;
+    const float* res; int res_c;
+    float* g_out; float* y3_out;
+    int J, N, H, W, C, hooks, mode; float eps;
+};
+
+cudaError_t launch_conv_simt(const float* A, const float* B, const ConvGeom& g, const EpiParams& ep, cudaStream_t st);
+bool conv_tc_available();
+cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& g, const EpiParams& ep, int split3,
+                           cudaStream_t st);
+
+}  // namespace xfrb

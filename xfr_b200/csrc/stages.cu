@@ -1,0 +1,543 @@
+// HBM-bound stages of the whitebox path that are not GEMMs: stem, pooling, head glue, block
+// boundaries of downsample blocks, MaxPool backward, contrastive combine, saliency post-filter.
+// All tensors NHWC fp32, 128-bit accesses along channels.
+#include "common.cuh"
+#include <math.h>
+
+namespace xfrb {
+
+// ------------------------------------------------------------------ stem forward
+// o[n,oh,ow,co] = sum_{r,s,ci} x[n,2oh+r-3,2ow+s-3,ci] * W[(r,s,ci),co] + b[co]      (resnet.py:177,225)
+// block = 8x8 output pixels x 64 channels; 256 threads = 64 pixels x 4 channel groups of 16.
+constexpr int ST_T = 8;                   // output tile edge
+constexpr int ST_P = ST_T * 2 + 5;        // input patch edge (21)
+__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                        const float* __restrict__ b, float* __restrict__ o, int N) {
+    extern __shared__ __align__(16) float sm[];
+    float* sW = sm;                       // [147][64]
+    float* sx = sm + 147 * 64;            // [21][21][3]
+    const int tid = threadIdx.x;
+    const int n = blockIdx.z, oh0 = blockIdx.y * ST_T, ow0 = blockIdx.x * ST_T;
+    for (int i = tid; i < 147 * 64 / 4; i += 256) reinterpret_cast<float4*>(sW)[i] = __ldg(reinterpret_cast<const float4*>(W) + i);
+    const int ih0 = oh0 * 2 - 3, iw0 = ow0 * 2 - 3;
+    for (int i = tid; i < ST_P * ST_P * 3; i += 256) {
+        int ci = i % 3, p = i / 3;
+        int pw = p % ST_P, ph = p / ST_P;
+        int ih = ih0 + ph, iw = iw0 + pw;
+        float v = 0.f;
+        if (ih >= 0 && ih < 224 && iw >= 0 && iw < 224) v = __ldg(x + (((size_t)n * 224 + ih) * 224 + iw) * 3 + ci);
+        sx[i] = v;
+    }
+    __syncthreads();
+    const int pix = tid >> 2, cg = tid & 3;
+    const int py = pix >> 3, px = pix & 7;
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int r = 0; r < 7; ++r) {
+        const float* xr = sx + ((py * 2 + r) * ST_P + px * 2) * 3;
+        const float* wr = sW + (r * 21) * 64 + cg * 16;
+#pragma unroll
+        for (int sc = 0; sc < 21; ++sc) {
+            float xv = xr[sc];
+            const float4* w4 = reinterpret_cast<const float4*>(wr + sc * 64);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 w = w4[q];
+                acc[q * 4 + 0] = fmaf(xv, w.x, acc[q * 4 + 0]);
+                acc[q * 4 + 1] = fmaf(xv, w.y, acc[q * 4 + 1]);
+                acc[q * 4 + 2] = fmaf(xv, w.z, acc[q * 4 + 2]);
+                acc[q * 4 + 3] = fmaf(xv, w.w, acc[q * 4 + 3]);
+            }
+        }
+    }
+    float* op = o + (((size_t)n * 112 + oh0 + py) * 112 + ow0 + px) * 64 + cg * 16;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float4 bb = __ldg(reinterpret_cast<const float4*>(b + cg * 16) + q);
+        st4(op + q * 4, make_float4(acc[q * 4] + bb.x, acc[q * 4 + 1] + bb.y, acc[q * 4 + 2] + bb.z, acc[q * 4 + 3] + bb.w));
+    }
+}
+
+// mp = maxpool3x3/2 pad 1 of relu(bn(o))   (resnet.py:226-228)
+__global__ void stem_pool_kernel(const float* __restrict__ o, const float* __restrict__ bn, float* __restrict__ mp, int total4) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    int c = (i & 15) * 4;
+    int p = i >> 4;
+    int pw = p % 56; p /= 56;
+    int ph = p % 56;
+    int n = p / 56;
+    float4 al = ld4(bn + c), be = ld4(bn + 64 + c);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int r = 0; r < 3; ++r) {
+        int h = ph * 2 - 1 + r;
+        if (h < 0 || h >= 112) continue;
+        for (int s = 0; s < 3; ++s) {
+            int w = pw * 2 - 1 + s;
+            if (w < 0 || w >= 112) continue;
+            float4 v = ld4(o + (((size_t)n * 112 + h) * 112 + w) * 64 + c);
+            m.x = fmaxf(m.x, fmaxf(__fadd_rn(__fmul_rn(v.x, al.x), be.x), 0.f));
+            m.y = fmaxf(m.y, fmaxf(__fadd_rn(__fmul_rn(v.y, al.y), be.y), 0.f));
+            m.z = fmaxf(m.z, fmaxf(__fadd_rn(__fmul_rn(v.z, al.z), be.z), 0.f));
+            m.w = fmaxf(m.w, fmaxf(__fadd_rn(__fmul_rn(v.w, al.w), be.w), 0.f));
+        }
+    }
+    st4(mp + (size_t)i * 4, m);
+}
+
+cudaError_t launch_stem_fwd(const float* x, const float* W, const float* b, const float* bn, float* o, float* mp, int N,
+                            cudaStream_t st) {
+    size_t smem = (147 * 64 + ST_P * ST_P * 3) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    stem_conv_kernel<<<dim3(112 / ST_T, 112 / ST_T, N), 256, smem, st>>>(x, W, b, o, N);
+    int total4 = N * 56 * 56 * 16;
+    stem_pool_kernel<<<(total4 + 255) / 256, 256, 0, st>>>(o, bn, mp, total4);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ shortcut helpers
+__global__ void subsample2_kernel(const float* __restrict__ u, float* __restrict__ out, int H, int W, int C4, size_t total4) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    int c = i % C4;
+    size_t p = i / C4;
+    int w = p % (W / 2); p /= (W / 2);
+    int h = p % (H / 2);
+    size_t n = p / (H / 2);
+    reinterpret_cast<float4*>(out)[i] = __ldg(reinterpret_cast<const float4*>(u) + ((n * H + 2 * h) * W + 2 * w) * C4 + c);
+}
+
+__global__ void avgpool2_kernel(const float* __restrict__ u, float* __restrict__ out, int H, int W, int C4, size_t total4) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    int c = i % C4;
+    size_t p = i / C4;
+    int w = p % (W / 2); p /= (W / 2);
+    int h = p % (H / 2);
+    size_t n = p / (H / 2);
+    const float4* b = reinterpret_cast<const float4*>(u) + ((n * H + 2 * h) * W + 2 * w) * C4 + c;
+    float4 a = __ldg(b), b1 = __ldg(b + C4), c0 = __ldg(b + (size_t)W * C4), c1 = __ldg(b + (size_t)W * C4 + C4);
+    // torch avg_pool2d: sum in window order, then divide by the pool size
+    float4 r;
+    r.x = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.x, b1.x), c0.x), c1.x), 4.f);
+    r.y = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.y, b1.y), c0.y), c1.y), 4.f);
+    r.z = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.z, b1.z), c0.z), c1.z), 4.f);
+    r.w = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.w, b1.w), c0.w), c1.w), 4.f);
+    reinterpret_cast<float4*>(out)[i] = r;
+}
+
+cudaError_t launch_subsample2(const float* u, float* out, int N, int H, int W, int C, cudaStream_t st) {
+    size_t total4 = (size_t)N * (H / 2) * (W / 2) * (C / 4);
+    subsample2_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(u, out, H, W, C / 4, total4);
+    return cudaGetLastError();
+}
+cudaError_t launch_avgpool2(const float* u, float* out, int N, int H, int W, int C, cudaStream_t st) {
+    size_t total4 = (size_t)N * (H / 2) * (W / 2) * (C / 4);
+    avgpool2_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(u, out, H, W, C / 4, total4);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ head forward glue
+// v[n,c] = mean over 7x7 of u[n,:,:,c]   (resnet.py:235)
+__global__ void avgpool7_kernel(const float* __restrict__ u, float* __restrict__ v, int C4, int total4) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    int c = i % C4, n = i / C4;
+    const float4* b = reinterpret_cast<const float4*>(u) + (size_t)n * 49 * C4 + c;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < 49; ++p) {
+        float4 t = __ldg(b + (size_t)p * C4);
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    reinterpret_cast<float4*>(v)[i] = make_float4(s.x / 49.f, s.y / 49.f, s.z / 49.f, s.w / 49.f);
+}
+
+// scratch [N, 1024] (dual tile order, bias already added) -> f1, f1p, nrm, xn.   512 threads per row.
+__global__ void __launch_bounds__(512) head_norm_kernel(const float* __restrict__ scratch, int tn, float* __restrict__ f1,
+                                                        float* __restrict__ f1p, float* __restrict__ xn, float* __restrict__ nrm) {
+    __shared__ float red[16];
+    const int n = blockIdx.x, c = threadIdx.x;
+    const int half = tn / 2;
+    const int t = c / half, j = c % half;
+    float a = scratch[(size_t)n * 1024 + t * tn + j];
+    float p = scratch[(size_t)n * 1024 + t * tn + half + j];
+    f1[(size_t)n * 512 + c] = a;
+    f1p[(size_t)n * 512 + c] = p;
+    float s = a * a;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((c & 31) == 0) red[c >> 5] = s;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < 16; ++i) tot += red[i];
+    float nn = fmaxf(sqrtf(tot), 1e-12f);      // F.normalize eps (resnet.py:250)
+    if (c == 0) nrm[n] = nn;
+    xn[(size_t)n * 512 + c] = __fdiv_rn(a, nn);
+}
+
+cudaError_t launch_avgpool7(const float* u, float* v, int N, int C, cudaStream_t st) {
+    int total4 = N * C / 4;
+    avgpool7_kernel<<<(total4 + 255) / 256, 256, 0, st>>>(u, v, C / 4, total4);
+    return cudaGetLastError();
+}
+cudaError_t launch_head_norm(const float* scratch, int tn, float* f1, float* f1p, float* xn, float* nrm, int N, cudaStream_t st) {
+    head_norm_kernel<<<N, 512, 0, st>>>(scratch, tn, f1, f1p, xn, nrm);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ head backward glue
+// row j: seed = Pn[j,:] @ W2[j%N] ; x50 ; Multiply hook ; Jacobian of normalize -> scratch[j, 512]
+__global__ void __launch_bounds__(512) head_bwd_a_kernel(const float* __restrict__ Pn, const float* __restrict__ W2, int C,
+                                                         const float* __restrict__ f1p, const float* __restrict__ xn,
+                                                         const float* __restrict__ nrm, float* __restrict__ scratch,
+                                                         int N, int mode, float eps) {
+    __shared__ float red[16];
+    __shared__ float bc;
+    const int j = blockIdx.x, n = j % N, d = threadIdx.x;
+    auto block_sum = [&](float s) {
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        __syncthreads();
+        if ((d & 31) == 0) red[d >> 5] = s;
+        __syncthreads();
+        if (d == 0) {
+            float t = 0.f;
+            for (int i = 0; i < 16; ++i) t += red[i];
+            bc = t;
+        }
+        __syncthreads();
+        return bc;
+    };
+    float g = 0.f;
+    for (int c = 0; c < C; ++c) g = fmaf(Pn[(size_t)j * C + c], W2[((size_t)n * C + c) * 512 + d], g);
+    g = g * 50.f;                                                 // Multiply backward (resnet.py:160-165)
+    float x = xn[(size_t)n * 512 + d];
+    float xmul = 0.f;
+    if (mode == XFRB_MODE_ALL) {
+        float fp = f1p[(size_t)n * 512 + d];
+        float nn = fmaxf(sqrtf(block_sum(fp * fp)), 1e-12f);
+        xmul = fmaxf(__fdiv_rn(fp, nn), 0.f);
+    }
+    g = hook<false>(fmaxf(x, 0.f), xmul, g, mode, eps);
+    float dot = block_sum(x * g);
+    scratch[(size_t)j * 512 + d] = __fdiv_rn(g - x * dot, nrm[n]);
+}
+
+// z [J,2048] (fc1 dgrad) -> Linear hook with a = x = v, /49, broadcast over 7x7
+__global__ void head_bwd_b_kernel(const float* __restrict__ z, const float* __restrict__ v, float* __restrict__ g_out,
+                                  int N, int C4, int total4, int mode, float eps) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    int c = i % C4, j = i / C4, n = j % N;
+    float4 zz = reinterpret_cast<const float4*>(z)[i];
+    float4 vv = __ldg(reinterpret_cast<const float4*>(v) + (size_t)n * C4 + c);
+    float4 r;
+    r.x = hook<true>(fmaxf(vv.x, 0.f), fmaxf(vv.x, 0.f), zz.x, mode, eps) / 49.f;
+    r.y = hook<true>(fmaxf(vv.y, 0.f), fmaxf(vv.y, 0.f), zz.y, mode, eps) / 49.f;
+    r.z = hook<true>(fmaxf(vv.z, 0.f), fmaxf(vv.z, 0.f), zz.z, mode, eps) / 49.f;
+    r.w = hook<true>(fmaxf(vv.w, 0.f), fmaxf(vv.w, 0.f), zz.w, mode, eps) / 49.f;
+    float4* o = reinterpret_cast<float4*>(g_out) + (size_t)j * 49 * C4 + c;
+    for (int p = 0; p < 49; ++p) o[(size_t)p * C4] = r;
+}
+
+cudaError_t launch_head_bwd_a(const float* Pn, const float* W2, int C, const float* f1p, const float* xn, const float* nrm,
+                              float* scratch, int J, int N, int mode, float eps, cudaStream_t st) {
+    head_bwd_a_kernel<<<J, 512, 0, st>>>(Pn, W2, C, f1p, xn, nrm, scratch, N, mode, eps);
+    return cudaGetLastError();
+}
+cudaError_t launch_head_bwd_b(const float* z, const float* v, float* g_out, int J, int N, int C, int mode, float eps,
+                              cudaStream_t st) {
+    int total4 = J * C / 4;
+    head_bwd_b_kernel<<<(total4 + 255) / 256, 256, 0, st>>>(z, v, g_out, N, C / 4, total4, mode, eps);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ unfused block boundary
+
+__global__ void join_kernel(JoinArgs a, size_t total4) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int C4 = a.C / 4;
+    int c = (int)(i % C4) * 4;
+    size_t p = i / C4;
+    int w = p % a.W; p /= a.W;
+    int h = p % a.H;
+    int j = (int)(p / a.H);
+    int n = j % a.N;
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    if (h % a.up == 0 && w % a.up == 0) {
+        int Hm = a.H / a.up, Wm = a.W / a.up;
+        float4 t = ld4(a.zmain + (((size_t)j * Hm + h / a.up) * Wm + w / a.up) * a.C + c);
+        z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
+    }
+    if (a.gres_lo != nullptr && c < a.gres_c) {
+        int Hr = a.H / a.k, Wr = a.W / a.k;
+        float4 t = ld4(a.gres_lo + (((size_t)j * Hr + h / a.k) * Wr + w / a.k) * a.gres_c + c);
+        float kk = (float)(a.k * a.k);
+        z[0] = __fadd_rn(z[0], __fdiv_rn(t.x, kk)); z[1] = __fadd_rn(z[1], __fdiv_rn(t.y, kk));
+        z[2] = __fadd_rn(z[2], __fdiv_rn(t.z, kk)); z[3] = __fadd_rn(z[3], __fdiv_rn(t.w, kk));
+    }
+    size_t ms = ((size_t)n * a.H + h) * a.W + w;
+    float4 uv = ld4(a.out + ms * a.C + c), ov = ld4(a.o3 + ms * a.C + c), xv = ld4(a.xr3 + ms * a.C + c);
+    float u[4] = {uv.x, uv.y, uv.z, uv.w}, o[4] = {ov.x, ov.y, ov.z, ov.w}, x[4] = {xv.x, xv.y, xv.z, xv.w};
+    float r[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a.mode == XFRB_MODE_ALL && a.res != nullptr && c < a.res_c) {
+        float4 rv = ld4(a.res + ms * a.res_c + c);
+        r[0] = rv.x; r[1] = rv.y; r[2] = rv.z; r[3] = rv.w;
+    }
+    float4 al = ld4(a.bn3 + c), be = ld4(a.bn3 + a.C + c), sp = ld4(a.bn3 + 2 * a.C + c), tp = ld4(a.bn3 + 3 * a.C + c);
+    BnC b[4] = {{al.x, be.x, sp.x, tp.x}, {al.y, be.y, sp.y, tp.y}, {al.z, be.z, sp.z, tp.z}, {al.w, be.w, sp.w, tp.w}};
+    float g[4], y3[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) join_chain(z[q], u[q], o[q], x[q], r[q], b[q], a.hooks, a.mode, a.eps, g[q], y3[q]);
+    reinterpret_cast<float4*>(a.g_out)[i] = make_float4(g[0], g[1], g[2], g[3]);
+    reinterpret_cast<float4*>(a.y3_out)[i] = make_float4(y3[0], y3[1], y3[2], y3[3]);
+}
+
+cudaError_t launch_join(const JoinArgs& a, cudaStream_t st) {
+    size_t total4 = (size_t)a.J * a.H * a.W * (a.C / 4);
+    join_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(a, total4);
+    return cudaGetLastError();
+}
+
+__global__ void ds_res_kernel(const float* __restrict__ g, const float* __restrict__ ap, float* __restrict__ gres_lo,
+                              int N, size_t HW, int C, int Cr, int mode, float eps, size_t total4) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int C4 = Cr / 4;
+    int c = (int)(i % C4) * 4;
+    size_t p = i / C4;              // j*HW + pixel
+    size_t j = p / HW, pix = p % HW;
+    size_t n = j % N;
+    float4 gv = ld4(g + p * C + c);
+    float4 av = ld4(ap + (n * HW + pix) * Cr + c);
+    float gg[4] = {gv.x, gv.y, gv.z, gv.w}, aa[4] = {av.x, av.y, av.z, av.w};
+    float r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float a = fmaxf(aa[q], 0.f);
+        float z = hook<false>(a, a, gg[q], mode, eps);     // Add, slot 1
+        r[q] = hook<false>(a, a, z, mode, eps);            // ConcatChannels
+    }
+    reinterpret_cast<float4*>(gres_lo)[i] = make_float4(r[0], r[1], r[2], r[3]);
+}
+
+cudaError_t launch_ds_res(const float* g, const float* ap, float* gres_lo, int J, int N, int H, int W, int C, int Cr,
+                          int mode, float eps, cudaStream_t st) {
+    size_t total4 = (size_t)J * H * W * (Cr / 4);
+    ds_res_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(g, ap, gres_lo, N, (size_t)H * W, C, Cr, mode, eps, total4);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ stem backward
+// zc = two affine hooks (Conv2d of layer1.0.conv1, AvgPool2d(k=1) of its shortcut) on z = zmain + gres, a = x = mp
+__global__ void stem_bwd_a_kernel(const float* __restrict__ zmain, const float* __restrict__ gres, const float* __restrict__ mp,
+                                  float* __restrict__ zc, size_t per_sample4, int N, int mode, float eps, size_t total4) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    size_t j = i / per_sample4, r = i % per_sample4;
+    size_t n = j % N;
+    float4 a = reinterpret_cast<const float4*>(zmain)[i], b = reinterpret_cast<const float4*>(gres)[i];
+    float4 m = __ldg(reinterpret_cast<const float4*>(mp) + n * per_sample4 + r);
+    float z[4] = {__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w)};
+    float mm[4] = {fmaxf(m.x, 0.f), fmaxf(m.y, 0.f), fmaxf(m.z, 0.f), fmaxf(m.w, 0.f)};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        z[q] = hook<true>(mm[q], mm[q], z[q], mode, eps);
+        z[q] = hook<true>(mm[q], mm[q], z[q], mode, eps);
+    }
+    reinterpret_cast<float4*>(zc)[i] = make_float4(z[0], z[1], z[2], z[3]);
+}
+
+// one thread = one (j, h, w, 4 channels) element of the 112x112x64 stem activation
+__global__ void __launch_bounds__(256) stem_bwd_b_kernel(const float* __restrict__ zc, const float* __restrict__ o,
+                                                         const float* __restrict__ bn, float* __restrict__ P2,
+                                                         float* __restrict__ chansum, double* __restrict__ sums,
+                                                         int N, int mode, float eps) {
+    // grid: (112*112*16/256, J)
+    __shared__ double red[8];
+    const int j = blockIdx.y, n = j % N;
+    const int i = blockIdx.x * 256 + threadIdx.x;      // < 112*112*16
+    const int c = (i & 15) * 4;
+    const int pix = i >> 4;
+    const int h = pix / 112, w = pix % 112;
+    float4 al = ld4(bn + c), be = ld4(bn + 64 + c), sp = ld4(bn + 128 + c), tp = ld4(bn + 192 + c);
+    const float alv[4] = {al.x, al.y, al.z, al.w}, bev[4] = {be.x, be.y, be.z, be.w};
+    const float spv[4] = {sp.x, sp.y, sp.z, sp.w}, tpv[4] = {tp.x, tp.y, tp.z, tp.w};
+    const float* ob = o + (size_t)n * 112 * 112 * 64 + c;
+    float ov[4], me[4];
+    {
+        float4 v = ld4(ob + ((size_t)h * 112 + w) * 64);
+        ov[0] = v.x; ov[1] = v.y; ov[2] = v.z; ov[3] = v.w;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) me[q] = fmaxf(__fadd_rn(__fmul_rn(ov[q], alv[q]), bev[q]), 0.f);
+    }
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    // MaxPool2d(3,2,1) backward as a gather: pooled row ph covers input rows 2ph-1..2ph+1; (h,w) receives the
+    // gradient of every window whose FIRST maximum (row-major scan, as torch's CPU kernel) it is.
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        int ph = (h + 1) / 2 - a;
+        if (ph < 0 || ph >= 56 || 2 * ph - 1 > h || h > 2 * ph + 1) continue;
+#pragma unroll
+        for (int b2 = 0; b2 < 2; ++b2) {
+            int pw = (w + 1) / 2 - b2;
+            if (pw < 0 || pw >= 56 || 2 * pw - 1 > w || w > 2 * pw + 1) continue;
+            bool win[4] = {true, true, true, true};
+            const int my = h - (2 * ph - 1), mx = w - (2 * pw - 1);     // my position inside the window
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int s2 = 0; s2 < 3; ++s2) {
+                    int hh = 2 * ph - 1 + r, ww = 2 * pw - 1 + s2;
+                    if ((r == my && s2 == mx) || hh < 0 || hh >= 112 || ww < 0 || ww >= 112) continue;
+                    float4 v = ld4(ob + ((size_t)hh * 112 + ww) * 64);
+                    const float vv[4] = {v.x, v.y, v.z, v.w};
+                    const bool before = (r < my) || (r == my && s2 < mx);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float rv = fmaxf(__fadd_rn(__fmul_rn(vv[q], alv[q]), bev[q]), 0.f);
+                        win[q] = win[q] && (before ? (rv < me[q]) : (rv <= me[q]));
+                    }
+                }
+            float4 gz = ld4(zc + (((size_t)j * 56 + ph) * 56 + pw) * 64 + c);
+            const float gzv[4] = {gz.x, gz.y, gz.z, gz.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (win[q]) z[q] = __fadd_rn(z[q], gzv[q]);
+        }
+    }
+    float p[4];
+    float csum = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float r = me[q];
+        float ro = fmaxf(ov[q], 0.f);
+        float xrelu = fmaxf(__fadd_rn(__fmul_rn(ro, spv[q]), tpv[q]), 0.f);
+        float zz = hook<false>(r, xrelu, z[q], mode, eps);   // ReLU hook
+        zz = hook<false>(r, r, zz, mode, eps);               // MaxPool2d hook
+        zz = r > 0.f ? zz : 0.f;
+        zz = __fmul_rn(zz, spv[q]);
+        p[q] = __fmul_rn(ro, fmaxf(zz, 0.f));                // BatchNorm hook records P[-2]
+        csum += p[q];
+    }
+    st4(P2 + ((size_t)j * 112 * 112 + pix) * 64 + c, make_float4(p[0], p[1], p[2], p[3]));
+    // channel sum across the 16 lanes that share a pixel
+    for (int o2 = 8; o2 > 0; o2 >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o2);
+    if ((threadIdx.x & 15) == 0) chansum[(size_t)j * 112 * 112 + pix] = csum;
+    double ds = (threadIdx.x & 15) == 0 ? (double)csum : 0.0;
+    for (int o2 = 16; o2 > 0; o2 >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o2);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ds;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += red[k];
+        atomicAdd(sums + j, t);
+    }
+}
+
+cudaError_t launch_stem_bwd(const float* zmain, const float* gres, const float* o, const float* mp, const float* bn,
+                            float* zc, float* P2, float* chansum, double* sums, int J, int N, int mode, float eps,
+                            cudaStream_t st) {
+    size_t per4 = (size_t)56 * 56 * 16, total4 = per4 * J;
+    cudaMemsetAsync(sums, 0, sizeof(double) * J, st);
+    stem_bwd_a_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(zmain, gres, mp, zc, per4, N, mode, eps, total4);
+    stem_bwd_b_kernel<<<dim3(112 * 112 * 16 / 256, J), 256, 0, st>>>(zc, o, bn, P2, chansum, sums, N, mode, eps);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ contrastive combine
+// out[n,pix] = sum_c relu(P2[n,pix,c]/S[n] - P2[N+n,pix,c]/S[N+n])     (whitebox.py:524-526)
+__global__ void contrast_kernel(const float* __restrict__ P2, const double* __restrict__ sums, float* __restrict__ out,
+                                int N, int HW, int C4) {
+    // 16 lanes per pixel (C = 64) generalised: C4 lanes per pixel, C4 a power of two <= 32
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)N * HW * C4;
+    float s = 0.f;
+    size_t pixg = i / C4;
+    if (i < total) {
+        size_t n = pixg / HW;
+        float sm = (float)sums[n], sn = (float)sums[N + n];
+        float4 a = reinterpret_cast<const float4*>(P2)[i];
+        float4 b = reinterpret_cast<const float4*>(P2)[i + (size_t)N * HW * C4];
+        s = fmaxf(__fsub_rn(__fdiv_rn(a.x, sm), __fdiv_rn(b.x, sn)), 0.f) + fmaxf(__fsub_rn(__fdiv_rn(a.y, sm), __fdiv_rn(b.y, sn)), 0.f) +
+            fmaxf(__fsub_rn(__fdiv_rn(a.z, sm), __fdiv_rn(b.z, sn)), 0.f) + fmaxf(__fsub_rn(__fdiv_rn(a.w, sm), __fdiv_rn(b.w, sn)), 0.f);
+    }
+    for (int o = C4 / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (i < total && (threadIdx.x % C4) == 0) out[pixg] = s;
+}
+
+cudaError_t launch_contrast(const float* P2, const double* sums, float* out, int N, int HW, int C, cudaStream_t st) {
+    int C4 = C / 4;
+    if (C4 > 32 || (C4 & (C4 - 1))) return cudaErrorInvalidValue;
+    size_t total = (size_t)N * HW * C4;
+    contrast_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P2, sums, out, N, HW, C4);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ saliency post-filter
+// scipy.ndimage.gaussian_filter(sigma=2, mode='nearest', truncate=4): 17 taps, axis 0 then axis 1, each pass
+// accumulated in double and stored as float32; then max(0,.) and division by max(sum, eps)  (whitebox.py:455-460)
+__global__ void __launch_bounds__(512) saliency_post_kernel(const float* __restrict__ mwp, float* __restrict__ out, int H, int W,
+                                                            float eps) {
+    extern __shared__ float sm[];
+    float* a = sm;             // [H*W]
+    float* b = sm + H * W;     // [H*W]
+    __shared__ double wts[17];
+    __shared__ double red[16];
+    const int tid = threadIdx.x;
+    const float* src = mwp + (size_t)blockIdx.x * H * W;
+    if (tid == 0) {
+        double s = 0.0;
+        for (int i = -8; i <= 8; ++i) { wts[i + 8] = exp(-0.5 / 4.0 * (double)(i * i)); s += wts[i + 8]; }
+        for (int i = 0; i < 17; ++i) wts[i] /= s;
+    }
+    for (int i = tid; i < H * W; i += blockDim.x) a[i] = src[i];
+    __syncthreads();
+    for (int i = tid; i < H * W; i += blockDim.x) {        // axis 0 (rows)
+        int h = i / W, w = i % W;
+        double s = 0.0;
+        for (int t = -8; t <= 8; ++t) {
+            int hh = min(max(h + t, 0), H - 1);
+            s += wts[t + 8] * (double)a[hh * W + w];
+        }
+        b[i] = (float)s;
+    }
+    __syncthreads();
+    double part = 0.0;
+    for (int i = tid; i < H * W; i += blockDim.x) {        // axis 1 (columns)
+        int h = i / W, w = i % W;
+        double s = 0.0;
+        for (int t = -8; t <= 8; ++t) {
+            int ww = min(max(w + t, 0), W - 1);
+            s += wts[t + 8] * (double)b[h * W + ww];
+        }
+        float v = fmaxf((float)s, 0.f);
+        a[i] = v;
+        part += (double)v;
+    }
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((tid & 31) == 0) red[tid >> 5] = part;
+    __syncthreads();
+    double tot = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+    float denom = fmaxf((float)tot, eps);
+    float* dst = out + (size_t)blockIdx.x * H * W;
+    for (int i = tid; i < H * W; i += blockDim.x) dst[i] = __fdiv_rn(a[i], denom);
+}
+
+cudaError_t launch_saliency_post(const float* mwp, float* out, int B, int H, int W, float eps, cudaStream_t st) {
+    size_t smem = (size_t)2 * H * W * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(saliency_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 128 * 4);
+        attr = true;
+    }
+    saliency_post_kernel<<<B, 512, smem, st>>>(mwp, out, H, W, eps);
+    return cudaGetLastError();
+}
+
+}  // namespace xfrb

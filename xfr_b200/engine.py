@@ -45,7 +45,7 @@ class StResnetEngine(object):
         self.eps = eps
         sd = {k: v.detach().cpu() for k, v in state_dict.items()}
         self.stem = packing.Stem(sd, with_bias=with_bias).to(self.device)
-        self.head = packing.Head(sd, with_bias=with_bias).to(self.device)
+        self.head = packing.Head(sd, tn, with_bias=with_bias).to(self.device)
         self.blocks = []
         inplanes, hw = 64, 56
         for li, (planes, n) in enumerate(zip((64, 128, 256, 512), self.layers), start=1):
@@ -67,17 +67,17 @@ class StResnetEngine(object):
         self.enc_dim = 512
 
     # ------------------------------------------------------------ workspace
-    def buf(self, name, *shape):
-        """Named fp32 buffer, allocated once per (name, shape): static addresses for graph capture."""
+    def buf(self, name, *shape, **kw):
+        """Named buffer, allocated once per (name, shape): static addresses for graph capture."""
         key = (name,) + tuple(shape)
         t = self._ws.get(key)
         if t is None:
-            t = torch.empty(shape, dtype=torch.float32, device=self.device)
+            t = torch.empty(shape, dtype=kw.get('dtype', torch.float32), device=self.device)
             self._ws[key] = t
         return t
 
     def workspace_bytes(self):
-        return sum(t.numel() * 4 for t in self._ws.values())
+        return sum(t.numel() * t.element_size() for t in self._ws.values())
 
     # ------------------------------------------------------------ forward
     def forward(self, x_nhwc):
@@ -122,9 +122,10 @@ class StResnetEngine(object):
             u = t['out']
         S['v'] = self.buf('v', N, 2048)
         S['f1'] = self.buf('f1', N, 512)
+        S['f1p'] = self.buf('f1p', N, 512)
         S['xn'] = self.buf('xn', N, 512)
         S['nrm'] = self.buf('nrm', N)
-        be.head_fwd(u, self.head, S['v'], S['f1'], S['xn'], S['nrm'])
+        be.head_fwd(u, self.head, S['v'], S['f1'], S['f1p'], S['xn'], S['nrm'])
         self.saved = S
         return S['xn']
 
@@ -142,7 +143,7 @@ class StResnetEngine(object):
         nb = len(self.blocks)
         last = self.blocks[-1]
         g = self.buf('g_head', J, 7, 7, last.cout)
-        be.head_bwd(Pn, W2, self.head, S['v'], S['xn'], S['nrm'], m, g, hooked_fc2)
+        be.head_bwd(Pn, W2, self.head, S['v'], S['f1p'], S['xn'], S['nrm'], m, g, hooked_fc2)
         # chain on the last block output (ReLU + AvgPool2d hooks) and the start of its main path
         t = S[nb - 1]
         gb = self.buf('g%d' % ((nb - 1) % 2), J, last.hw, last.hw, last.cout)
@@ -169,7 +170,7 @@ class StResnetEngine(object):
             if i == 0:
                 P2 = self.buf('P2', J, 112, 112, 64)
                 chansum = self.buf('chansum', J, 112, 112)
-                sums = self.buf('sums', J)
+                sums = self.buf('sums', J, dtype=torch.float64)
                 be.stem_bwd(zlo, gres, S['o_s'], S['mp'], self.stem.bn, m, P2, chansum, sums)
                 return P2, chansum, sums
             p, tp = self.blocks[i - 1], S[i - 1]

@@ -1,0 +1,185 @@
+"""ctypes binding of libxfr_b200.so (include/xfrb.h) — the only compute backend of the product.
+
+There is deliberately no CPU or torch fallback: if the library is missing, cannot be
+loaded, or the device is not a compute-capability-10.x GPU, construction raises.
+Kernels are enqueued on torch's current CUDA stream; torch only provides device
+memory and streams.
+"""
+import ctypes
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libxfr_b200.so')
+
+IMPL_FP32, IMPL_TF32X3, IMPL_TF32 = 0, 1, 2
+IMPLS = {'fp32': IMPL_FP32, 'tf32x3': IMPL_TF32X3, 'tf32': IMPL_TF32}
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_F = ctypes.c_float
+
+# name -> argtypes, in the order of include/xfrb.h
+_SIGNATURES = {
+    'xfrb_stem_fwd': [_P, _P, _P, _P, _P, _P, _I, _P],
+    'xfrb_subsample2': [_P, _P, _I, _I, _I, _I, _P],
+    'xfrb_avgpool2': [_P, _P, _I, _I, _I, _I, _P],
+    'xfrb_conv_dual': [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'xfrb_head_fwd': [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    'xfrb_head_bwd': [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
+    'xfrb_dgrad_mid': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    'xfrb_dgrad_plain': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    'xfrb_dgrad_join': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    'xfrb_join': [_P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
+    'xfrb_ds_res': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
+    'xfrb_stem_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
+    'xfrb_contrast': [_P, _P, _P, _I, _I, _I, _P],
+    'xfrb_saliency_post': [_P, _P, _I, _I, _I, _F, _P],
+}
+EXPORTS = ['xfrb_version', 'xfrb_last_error', 'xfrb_device_ok', 'xfrb_impl_available'] + sorted(_SIGNATURES)
+
+_lib = None
+
+
+def load_library(path=LIB_PATH):
+    """dlopen the in-tree library and declare every prototype.  Raises if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise RuntimeError('xfr_b200: %s not found - build it with `python -m xfr_b200.build` '
+                           '(there is no CPU fallback)' % path)
+    lib = ctypes.CDLL(path)
+    lib.xfrb_version.restype = _I
+    lib.xfrb_last_error.restype = ctypes.c_char_p
+    lib.xfrb_device_ok.restype = _I
+    lib.xfrb_impl_available.restype = _I
+    lib.xfrb_impl_available.argtypes = [_I]
+    for name, args in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = _I
+    _lib = lib
+    return lib
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class CudaBackend(object):
+    """Kernel set of the engine on one B200.  Method names/arguments mirror tests/emul_backend.py."""
+    name = 'cuda'
+
+    def __init__(self, device, impl='fp32', eps=1e-16):
+        self.lib = load_library()
+        self.device = torch.device(device)
+        if self.device.type != 'cuda' or not torch.cuda.is_available():
+            raise RuntimeError('xfr_b200: a CUDA device is required (no CPU fallback)')
+        with torch.cuda.device(self.device):
+            if not self.lib.xfrb_device_ok():
+                raise RuntimeError('xfr_b200: kernels are built for sm_100a only; device is %s'
+                                   % torch.cuda.get_device_name(self.device))
+        self.impl = IMPLS[impl] if isinstance(impl, str) else int(impl)
+        if not self.lib.xfrb_impl_available(self.impl):
+            raise NotImplementedError('xfr_b200: GEMM implementation %r is not compiled into %s' % (impl, LIB_PATH))
+        self.eps = float(eps)
+        self._scratch = {}
+        self.launches = 0
+
+    # -------------------------------------------------------------- helpers
+    def _st(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _check(self, rc):
+        self.launches += 1
+        if rc != 0:
+            raise RuntimeError('xfr_b200 kernel failed: %s' % self.lib.xfrb_last_error().decode())
+
+    def _tmp(self, name, n):
+        t = self._scratch.get(name)
+        if t is None or t.numel() < n:
+            t = torch.empty(n, dtype=torch.float32, device=self.device)
+            self._scratch[name] = t
+        return t
+
+    # -------------------------------------------------------------- forward
+    def stem_fwd(self, x, stem, o, mp):
+        self._check(self.lib.xfrb_stem_fwd(_ptr(x), _ptr(stem.W), _ptr(stem.b), _ptr(stem.bn), _ptr(o), _ptr(mp),
+                                           x.shape[0], self._st()))
+
+    def subsample2(self, u, out):
+        N, H, W, C = u.shape
+        self._check(self.lib.xfrb_subsample2(_ptr(u), _ptr(out), N, H, W, C, self._st()))
+
+    def avgpool2(self, u, out):
+        N, H, W, C = u.shape
+        self._check(self.lib.xfrb_avgpool2(_ptr(u), _ptr(out), N, H, W, C, self._st()))
+
+    def conv_dual(self, inp, L, o, xr, act, res=None):
+        N, H, W, Cin = inp.shape
+        self._check(self.lib.xfrb_conv_dual(_ptr(inp), _ptr(L.Bf), _ptr(L.bias), _ptr(L.bn), _ptr(res),
+                                            0 if res is None else res.shape[-1], _ptr(o), _ptr(xr), _ptr(act),
+                                            N, H, W, Cin, L.cout, L.R, L.tn, self.impl, self._st()))
+
+    def head_fwd(self, u, head, v, f1, f1p, xn, nrm):
+        N = u.shape[0]
+        scratch = self._tmp('head_fwd', N * 1024)
+        self._check(self.lib.xfrb_head_fwd(_ptr(u), _ptr(head.B1), _ptr(head.bias1), head.tn, _ptr(scratch), _ptr(v),
+                                           _ptr(f1), _ptr(f1p), _ptr(xn), _ptr(nrm), N, self.impl, self._st()))
+
+    # -------------------------------------------------------------- backward
+    def head_bwd(self, Pn, W2, head, v, f1p, xn, nrm, mode, g_out, hooked_fc2=False):
+        if hooked_fc2:
+            raise NotImplementedError('hooked fc2 head (non-triplet classifier) is not on the CUDA path yet')
+        J, C = Pn.shape
+        N = v.shape[0]
+        scratch = self._tmp('head_bwd', J * 2560)
+        self._check(self.lib.xfrb_head_bwd(_ptr(Pn), _ptr(W2), C, _ptr(head.W1pT), _ptr(v), _ptr(f1p), _ptr(xn),
+                                           _ptr(nrm), _ptr(scratch), _ptr(g_out), J, N, mode, self.eps, self.impl,
+                                           self._st()))
+
+    def dgrad_mid(self, y, L, o, xr, bn, mode, y_out):
+        J, H, W, Cout = y.shape
+        self._check(self.lib.xfrb_dgrad_mid(_ptr(y), _ptr(L.Bd), _ptr(o), _ptr(xr), _ptr(bn), _ptr(y_out), J,
+                                            o.shape[0], H, W, L.cin, Cout, L.R, mode, self.eps, self.impl, self._st()))
+
+    def dgrad_plain(self, y, L, z_out, signed=False):
+        J, H, W, Cout = y.shape
+        B = L.signed_dgrad() if signed else L.Bd
+        self._check(self.lib.xfrb_dgrad_plain(_ptr(y), _ptr(B), _ptr(z_out), J, H, W, L.cin, Cout, L.R, self.impl,
+                                              self._st()))
+
+    def dgrad_join(self, y1, L, g_res, out, o3, xr3, bn3, res, hooks, mode, g_out, y3_out):
+        J, H, W, Cout = y1.shape
+        self._check(self.lib.xfrb_dgrad_join(_ptr(y1), _ptr(L.Bd), _ptr(g_res), _ptr(out), _ptr(o3), _ptr(xr3),
+                                             _ptr(bn3), _ptr(res), 0 if res is None else res.shape[-1], _ptr(g_out),
+                                             _ptr(y3_out), J, out.shape[0], H, W, L.cin, Cout, hooks, mode, self.eps,
+                                             self.impl, self._st()))
+
+    def join(self, zmain, up, gres_lo, k, out, o3, xr3, bn3, res, hooks, mode, g_out, y3_out):
+        J, H, W, C = g_out.shape
+        self._check(self.lib.xfrb_join(_ptr(zmain), up, _ptr(gres_lo), 0 if gres_lo is None else gres_lo.shape[-1], k,
+                                       _ptr(out), _ptr(o3), _ptr(xr3), _ptr(bn3), _ptr(res),
+                                       0 if res is None else res.shape[-1], _ptr(g_out), _ptr(y3_out), J, out.shape[0],
+                                       H, W, C, hooks, mode, self.eps, self._st()))
+
+    def ds_res(self, g, ap, mode, gres_lo):
+        J, H, W, C = g.shape
+        self._check(self.lib.xfrb_ds_res(_ptr(g), _ptr(ap), _ptr(gres_lo), J, ap.shape[0], H, W, C, ap.shape[-1], mode,
+                                         self.eps, self._st()))
+
+    def stem_bwd(self, zmain, gres, o, mp, bn, mode, P2, chansum, sums):
+        J = zmain.shape[0]
+        zc = self._tmp('stem_zc', J * 56 * 56 * 64)
+        self._check(self.lib.xfrb_stem_bwd(_ptr(zmain), _ptr(gres), _ptr(o), _ptr(mp), _ptr(bn), _ptr(zc), _ptr(P2),
+                                           _ptr(chansum), _ptr(sums), J, o.shape[0], mode, self.eps, self._st()))
+
+    def contrast(self, P2, sums, N, out):
+        HW = P2.shape[1] * P2.shape[2]
+        self._check(self.lib.xfrb_contrast(_ptr(P2), _ptr(sums), _ptr(out), N, HW, P2.shape[3], self._st()))
+
+    def saliency_post(self, mwp, out):
+        B, H, W = mwp.shape
+        self._check(self.lib.xfrb_saliency_post(_ptr(mwp), _ptr(out), B, H, W, self.eps, self._st()))

@@ -125,17 +125,19 @@ class Stem(object):
 class Head(object):
     """avgpool7 -> fc1 -> L2 normalise -> x50 -> fc2 (reference resnet.py:235-258)."""
 
-    def __init__(self, sd, with_bias=False):
+    def __init__(self, sd, tn=128, with_bias=False):
+        self.tn = tn
         self.W1 = sd['fc1.weight'].float().contiguous()              # [512, 2048]
         self.b1 = sd['fc1.bias'].float().contiguous()
         self.W1p = torch.clamp_min(self.W1, 0).contiguous()
         self.b1p = (torch.clamp_min(self.b1, 0) if with_bias else self.b1).contiguous()
-        self.W1pT = self.W1p.t().contiguous()                        # [2048, 512]
+        self.W1pT = self.W1p.t().contiguous()                        # [2048, 512]: B operand of the fc1 dgrad
+        self.B1, self.bias1 = pack_dual_fwd(self.W1.view(512, -1, 1, 1), self.b1, tn, with_bias)
         self.W2 = sd['fc2.weight'].float().contiguous() if 'fc2.weight' in sd else None
         self.scale = 50.0
 
     def to(self, device):
-        for k in ('W1', 'b1', 'W1p', 'b1p', 'W1pT', 'W2'):
+        for k in ('W1', 'b1', 'W1p', 'b1p', 'W1pT', 'W2', 'B1', 'bias1'):
             v = getattr(self, k)
             if v is not None:
                 setattr(self, k, v.to(device))
