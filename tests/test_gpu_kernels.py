@@ -36,3 +36,43 @@ def test_each_kernel_against_emulation(impl, mode):
     bad = {k: v for k, v in sh.errors.items() if v > TOL[impl]}
     print('\n'.join('%-18s %.3g' % kv for kv in sorted(sh.errors.items())))
     assert not bad, bad
+
+
+def _conv_case(be, J, H, C_in, C_out, R, seed=0):
+    """dgrad_plain == plain implicit GEMM: y [J,H,H,C_out-as-K] x Bd [C_in, R*R*K] -> [J,H,H,C_in]."""
+    from emul_backend import im2col_nhwc
+    g = torch.Generator().manual_seed(seed)
+    y = torch.randn(J, H, H, C_out, generator=g)
+    Bd = torch.randn(C_in, R * R * C_out, generator=g) / (R * (C_out ** 0.5))
+
+    class L(object):
+        pass
+    L.Bd, L.cin, L.R = Bd.cuda(), C_in, R
+    out = torch.full((J, H, H, C_in), float('nan'), device='cuda')
+    be.dgrad_plain(y.cuda(), L, out)
+    torch.cuda.synchronize()
+    want = (im2col_nhwc(y.double(), R, R, R // 2) @ Bd.double().t()).view(J, H, H, C_in)
+    got = out.cpu().double()
+    assert torch.isfinite(got).all()
+    return float((got - want).abs().max() / want.abs().max())
+
+
+@pytest.mark.parametrize('impl,tol', [('fp32', 1e-5), ('tf32x3', 1e-4), ('tf32', 3e-3)])
+def test_gemm_shapes(impl, tol):
+    """Every (spatial size, tap count, N width) family the ResNet-101 schedule launches, incl. ragged M tails."""
+    from xfr_b200.kernels import CudaBackend
+    try:
+        be = CudaBackend('cuda:0', impl=impl)
+    except NotImplementedError:
+        pytest.skip('impl %s not built' % impl)
+    cases = [  # J, H, C_in (GEMM N), C_out (A channels), R
+        (3, 56, 64, 64, 1), (3, 56, 64, 64, 3), (2, 56, 256, 64, 1), (3, 28, 128, 128, 3), (3, 28, 512, 128, 1),
+        (5, 14, 256, 256, 3), (5, 14, 1024, 256, 1), (5, 7, 512, 512, 3), (3, 7, 2048, 512, 1), (7, 1, 2048, 512, 1),
+        (1, 7, 512, 2048, 1), (300, 1, 128, 64, 1),
+    ]
+    errs = {}
+    for c in cases:
+        errs[c] = _conv_case(be, *c)
+    print('\n'.join('%-28s %.3g' % (str(k), v) for k, v in errs.items()))
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, bad

@@ -1,8 +1,472 @@
-// tcgen05 implicit-GEMM convolution (impl 1 = 3xTF32, impl 2 = TF32) -- placeholder until the kernel lands.
+// tcgen05 implicit-GEMM convolution for sm_100a (impl 1 = 3xTF32 "fp32-equivalent", impl 2 = single TF32).
+//
+//   D[m, n] = sum_k A[m, k] * B[n, k]      A: NHWC activations (R x R taps, stride 1, zero pad), B: K-major weights
+//
+// One persistent CTA per SM, 320 threads, warp-specialised:
+//   warp 0      TMA producer   - cp.async.bulk.tensor loads of the A tile (128 pixel rows x 32 channels; for 3x3 convs a
+//                                4-D box (32ch, W, bh rows, bn images) shifted by the tap, out-of-bounds rows/columns
+//                                zero-filled by the TMA unit = the conv padding) and of the B tile (BN x 32), both
+//                                landing in 128B-swizzled shared memory, signalled through an mbarrier (complete_tx)
+//   warp 1      MMA issuer     - one lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) with the
+//                                accumulator in TMEM (two accumulator stages so the epilogue of tile i overlaps the
+//                                main loop of tile i+1); tcgen05.commit releases smem stages / publishes accumulators
+//   warps 2-5   operand split  - (3xTF32 only) rewrite each landed stage as hi = rna_tf32(x) in place and lo = x - hi in
+//                                a twin buffer; the issuer then runs hi*hi + lo*hi + hi*lo into the same accumulator
+//   warps 6-9   epilogue       - tcgen05.ld the accumulator (lane = pixel row), apply the fused EBP epilogue of
+//                                common.cuh against the saved tensors, store NHWC fp32 with 128-bit accesses
 #include "common.cuh"
+#include <cuda.h>
+#include <stdio.h>
+
 namespace xfrb {
-bool conv_tc_available() { return false; }
-cudaError_t launch_conv_tc(const float*, const float*, const ConvGeom&, const EpiParams&, int, cudaStream_t) {
-    return cudaErrorNotSupported;
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                       // 32 fp32 = one 128-byte swizzle row
+constexpr int TC_THREADS = 320;
+constexpr uint32_t A_TILE_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+
+struct TcGeom {
+    int a4d;            // 0: A is a 2-D [M, C] matrix (1x1 conv / linear); 1: 4-D NHWC box loads (3x3)
+    int R, Cin, kchunks, num_k;
+    int H, W, bh, bimg, tiles_per_img, Nimg;
+    int n_m_tiles, n_n_tiles;
+    uint32_t a_bytes;   // bytes one A load deposits (box volume * 4)
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+        "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major operand tile in 128B-swizzled smem: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address
+    d |= (uint64_t)1 << 16;                            // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// wait for outstanding tcgen05.ld; the registers are tied to the asm so no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(float* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
+                   "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+                 :
+                 : "memory");
+}
+
+// ------------------------------------------------------------------ kernel
+template <int BN, bool SPLIT3>
+struct TcCfg {
+    static constexpr uint32_t B_TILE_BYTES = BN * TC_BK * 4;
+    static constexpr uint32_t STAGE_BYTES = (A_TILE_BYTES + B_TILE_BYTES) * (SPLIT3 ? 2 : 1);
+    static constexpr int STAGES = SPLIT3 ? (BN == 128 ? 3 : 4) : (BN == 128 ? 6 : 8);
+    static constexpr uint32_t TMEM_COLS = 2 * BN;          // two accumulator stages (128 or 256: powers of two)
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool SPLIT3>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGeom g, const EpiParams ep) {
+    using Cfg = TcCfg<BN, SPLIT3>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    // barrier block lives after the stages
+    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto split_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + 2 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8 * (3 * STAGES + 4));
+
+    auto a_hi = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
+    auto b_hi = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + A_TILE_BYTES; };
+    auto a_lo = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + A_TILE_BYTES + Cfg::B_TILE_BYTES; };
+    auto b_lo = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = g.n_m_tiles * g.n_n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+            mbar_init(split_bar(s), 4);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile -> coordinates
+    auto tile_coords = [&](int tile, int& m0, int& mvalid, int& n_img0, int& h0, int& ncol0) {
+        int mt = tile / g.n_n_tiles, nt = tile - mt * g.n_n_tiles;
+        ncol0 = nt * BN;
+        if (!g.a4d) {
+            m0 = mt * TC_BM;
+            mvalid = min(TC_BM, ep.M - m0);
+            n_img0 = 0;
+            h0 = 0;
+        } else if (g.bimg > 1) {
+            n_img0 = mt * g.bimg;
+            h0 = 0;
+            m0 = n_img0 * g.H * g.W;
+            mvalid = min(g.bimg, g.Nimg - n_img0) * g.H * g.W;
+        } else {
+            n_img0 = mt / g.tiles_per_img;
+            h0 = (mt - n_img0 * g.tiles_per_img) * g.bh;
+            m0 = (n_img0 * g.H + h0) * g.W;
+            mvalid = min(g.bh, g.H - h0) * g.W;
+        }
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int m0, mvalid, n_img0, h0, ncol0;
+                tile_coords(tile, m0, mvalid, n_img0, h0, ncol0);
+                for (int kb = 0; kb < g.num_k; ++kb) {
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_expect_tx(full_bar(s), g.a_bytes + Cfg::B_TILE_BYTES);
+                    int tap = kb / g.kchunks;
+                    int c0 = (kb - tap * g.kchunks) * TC_BK;
+                    if (g.a4d) {
+                        int dr = tap / g.R - (g.R >> 1), ds = tap % g.R - (g.R >> 1);
+                        tma_load_4d(a_hi(s), &tmA, c0, ds, h0 + dr, n_img0, full_bar(s));
+                    } else {
+                        tma_load_2d(a_hi(s), &tmA, c0, m0, full_bar(s));
+                    }
+                    tma_load_2d(b_hi(s), &tmB, kb * TC_BK, ncol0, full_bar(s));
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        int s = 0;
+        uint32_t ph = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int a = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            if (lane == 0) mbar_wait(tempty_bar(a), aph ^ 1u);
+            __syncwarp();
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + (uint32_t)(a * BN);
+            for (int kb = 0; kb < g.num_k; ++kb) {
+                if (lane == 0) {
+                    mbar_wait(SPLIT3 ? split_bar(s) : full_bar(s), ph);
+                    tc_fence_after();
+                    const uint64_t dah = make_desc(a_hi(s)), dbh = make_desc(b_hi(s));
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        const uint64_t koff = (uint64_t)((k * 32) >> 4);
+                        tc_mma_tf32(tacc, dah + koff, dbh + koff, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    if (SPLIT3) {
+                        const uint64_t dal = make_desc(a_lo(s)), dbl = make_desc(b_lo(s));
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 8; ++k) {
+                            const uint64_t koff = (uint64_t)((k * 32) >> 4);
+                            tc_mma_tf32(tacc, dal + koff, dbh + koff, idesc, 1u);
+                            tc_mma_tf32(tacc, dah + koff, dbl + koff, idesc, 1u);
+                        }
+                    }
+                    tc_commit(empty_bar(s));                 // smem stage reusable once these MMAs retire
+                    if (kb == g.num_k - 1) tc_commit(tfull_bar(a));
+                }
+                __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp < 6) {
+        // ===================== operand split (3xTF32) =====================
+        if (SPLIT3) {
+            const int t = threadIdx.x - 64;    // 0..127
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < g.num_k; ++kb) {
+                    mbar_wait(full_bar(s), ph);
+                    // A and B tiles are contiguous: [A_hi | B_hi] -> twins [A_lo | B_lo] at +A+B bytes
+                    float4* hi = reinterpret_cast<float4*>(smem_gen + s * Cfg::STAGE_BYTES);
+                    float4* lo = reinterpret_cast<float4*>(smem_gen + s * Cfg::STAGE_BYTES + A_TILE_BYTES + Cfg::B_TILE_BYTES);
+                    constexpr int NV = (A_TILE_BYTES + Cfg::B_TILE_BYTES) / 16;
+#pragma unroll 4
+                    for (int i = t; i < NV; i += 128) {
+                        float4 v = hi[i];
+                        float4 h, l;
+                        uint32_t u;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u); l.x = v.x - h.x;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y)); h.y = __uint_as_float(u); l.y = v.y - h.y;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u); l.z = v.z - h.z;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u); l.w = v.w - h.w;
+                        hi[i] = h;
+                        lo[i] = l;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(split_bar(s));
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int q = warp & 3;                        // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int a = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            int m0, mvalid, n_img0, h0, ncol0;
+            tile_coords(tile, m0, mvalid, n_img0, h0, ncol0);
+            mbar_wait(tfull_bar(a), aph);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
+            const bool valid = row < mvalid;
+            const int m = m0 + row;
+            if (ep.kind == EPI_FWD_DUAL) {
+                // BN == 128: columns [0,64) true channels, [64,128) relu(W) twins of the same channels
+                const int cbase = (ncol0 / BN) * (BN / 2);
+#pragma unroll 1
+                for (int j = 0; j < BN / 2; j += 16) {
+                    float vt[16], vp[16];
+                    tmem_ld16(tacc + j, vt);
+                    tmem_ld16(tacc + BN / 2 + j, vp);
+                    tmem_ld_wait(vt);
+                    tmem_ld_wait(vp);
+                    if (valid) {
+#pragma unroll
+                        for (int e = 0; e < 16; e += 4) {
+                            float4 bt = ld4(ep.bias + ncol0 + j + e), bp = ld4(ep.bias + ncol0 + BN / 2 + j + e);
+                            epilogue4(ep, m, cbase + j + e, make_float4(vt[e], vt[e + 1], vt[e + 2], vt[e + 3]),
+                                      make_float4(vp[e], vp[e + 1], vp[e + 2], vp[e + 3]), bt, bp);
+                        }
+                    }
+                }
+            } else {
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+                for (int j = 0; j < BN; j += 16) {
+                    float vt[16];
+                    tmem_ld16(tacc + j, vt);
+                    tmem_ld_wait(vt);
+                    if (valid) {
+#pragma unroll
+                        for (int e = 0; e < 16; e += 4) {
+                            const int c = ncol0 + j + e;
+                            float4 acc = make_float4(vt[e], vt[e + 1], vt[e + 2], vt[e + 3]);
+                            if (ep.kind == EPI_PLAIN && ep.bias != nullptr) {
+                                float4 bt = ld4(ep.bias + c);
+                                acc.x += bt.x; acc.y += bt.y; acc.z += bt.z; acc.w += bt.w;
+                            }
+                            epilogue4(ep, m, c, acc, z4, z4, z4);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(a));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS));
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static bool encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                   const cuuint32_t* box) {
+    EncodeTiledFn fn = get_encode();
+    if (!fn) return false;
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+bool conv_tc_available() { return true; }
+
+template <int BN, bool SPLIT3>
+static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGeom& g, const EpiParams& ep, cudaStream_t st) {
+    using Cfg = TcCfg<BN, SPLIT3>;
+    static bool attr = false;
+    static int sms = 0;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        attr = true;
+    }
+    int total = g.n_m_tiles * g.n_n_tiles;
+    int grid = total < sms ? total : sms;
+    conv_tc_kernel<BN, SPLIT3><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, g, ep);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, const EpiParams& ep, int split3, cudaStream_t st) {
+    if (cg.Cin % TC_BK != 0) return cudaErrorInvalidValue;
+    int BN;
+    if (ep.kind == EPI_FWD_DUAL) {
+        if (cg.Nn % 128) return cudaErrorInvalidValue;
+        BN = 128;
+    } else if (cg.Nn % 128 == 0) BN = 128;
+    else if (cg.Nn % 64 == 0) BN = 64;
+    else return cudaErrorInvalidValue;
+
+    TcGeom g;
+    g.R = cg.R;
+    g.Cin = cg.Cin;
+    g.kchunks = cg.Cin / TC_BK;
+    g.num_k = cg.R * cg.R * g.kchunks;
+    g.H = cg.H;
+    g.W = cg.W;
+    g.n_n_tiles = cg.Nn / BN;
+    const int HW = cg.H * cg.W;
+    g.Nimg = ep.M / HW;
+    CUtensorMap tmA, tmB;
+    if (cg.R == 1) {
+        g.a4d = 0;
+        g.bh = g.bimg = g.tiles_per_img = 1;
+        g.n_m_tiles = (ep.M + TC_BM - 1) / TC_BM;
+        g.a_bytes = A_TILE_BYTES;
+        cuuint64_t dims[2] = {(cuuint64_t)cg.Cin, (cuuint64_t)ep.M};
+        cuuint64_t strides[1] = {(cuuint64_t)cg.Cin * 4};
+        cuuint32_t box[2] = {TC_BK, TC_BM};
+        if (!encode(&tmA, A, 2, dims, strides, box)) return cudaErrorInvalidValue;
+    } else {
+        g.a4d = 1;
+        if (cg.W > 128) return cudaErrorInvalidValue;
+        if (HW <= 64) {                         // several whole images per tile (7x7 maps)
+            g.bimg = TC_BM / HW;
+            g.bh = cg.H;
+            g.tiles_per_img = 1;
+            g.n_m_tiles = (g.Nimg + g.bimg - 1) / g.bimg;
+        } else {
+            g.bimg = 1;
+            g.bh = TC_BM / cg.W;
+            if (g.bh > cg.H) g.bh = cg.H;
+            // prefer a row count that divides H (no ragged last tile) when it costs nothing
+            for (int b = g.bh; b >= 1; --b)
+                if (cg.H % b == 0 && (cg.H / b) == (cg.H + g.bh - 1) / g.bh) { g.bh = b; break; }
+            g.tiles_per_img = (cg.H + g.bh - 1) / g.bh;
+            g.n_m_tiles = g.Nimg * g.tiles_per_img;
+        }
+        g.a_bytes = (uint32_t)(TC_BK * cg.W * g.bh * g.bimg * 4);
+        cuuint64_t dims[4] = {(cuuint64_t)cg.Cin, (cuuint64_t)cg.W, (cuuint64_t)cg.H, (cuuint64_t)g.Nimg};
+        cuuint64_t strides[3] = {(cuuint64_t)cg.Cin * 4, (cuuint64_t)cg.W * cg.Cin * 4, (cuuint64_t)HW * cg.Cin * 4};
+        cuuint32_t box[4] = {TC_BK, (cuuint32_t)cg.W, (cuuint32_t)g.bh, (cuuint32_t)g.bimg};
+        if (!encode(&tmA, A, 4, dims, strides, box)) return cudaErrorInvalidValue;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)cg.K, (cuuint64_t)cg.Nn};
+        cuuint64_t strides[1] = {(cuuint64_t)cg.K * 4};
+        cuuint32_t box[2] = {TC_BK, (cuuint32_t)BN};
+        if (!encode(&tmB, B, 2, dims, strides, box)) return cudaErrorInvalidValue;
+    }
+    if (BN == 128) return split3 ? launch_cfg<128, true>(tmA, tmB, g, ep, st) : launch_cfg<128, false>(tmA, tmB, g, ep, st);
+    return split3 ? launch_cfg<64, true>(tmA, tmB, g, ep, st) : launch_cfg<64, false>(tmA, tmB, g, ep, st);
+}
+
 }  // namespace xfrb
