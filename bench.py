@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""Benchmark of the whitebox hot path: contrastive-EBP saliency maps/sec, STR ResNet-101, 224x224 probes.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 256] [--gemm tf32x3|tf32|fp32]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...      the reference algorithm on the host cores (oracle port)
+
+One step = one pass of forward + mate/non-mate excitation backprop + contrastive combine + saliency
+post-filter over `batch` synthetic (probe, mate, non-mate) triplets per GPU (BASELINE.json configs[1]).
+Prints ONE JSON line (rank 0).  See DESIGN.md "measurement" for what each key means.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+# algorithmic work per ResNet-101 contrastive map: fp32, mate + non-mate
+EBP_BWD_BYTES_PER_MAP = 336e6     # 4*[2*S_o + 2*(S_o+S_i)],  S_i = 13.65 M, S_o = 14.20 M
+FLOP_PER_MAP = 57.2e9             # 28.8 forward (true + positive) + 28.4 two W+ dgrad sweeps
+METRIC = 'contrastive-EBP saliency maps/sec (ResNet-101, 224x224)'
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super(ClockSampler, self).__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.rows[0][1]), 'reasons': reasons, 'samples': len(sm)}
+
+
+def cpu_port(n_triplets, threads):
+    """The reference algorithm restated on the CPU (oracle port, torch CPU fp32), batch 1 like the reference."""
+    from oracle import stresnet_oracle as O      # cpu_baseline leg only
+    from xfr_b200 import synth
+    torch.set_num_threads(threads)
+    sd = synth.stresnet_state_dict(0)
+    x = synth.synthetic_probes(n_triplets + 1, seed=1)
+    g = torch.Generator().manual_seed(5)
+    W2 = torch.randn(n_triplets + 1, 2, 512, generator=g) * 0.02
+    O.contrastive_ebp(sd, x[:1], W2[:1])                     # warm-up
+    t0 = time.time()
+    for i in range(1, n_triplets + 1):
+        O.contrastive_ebp(sd, x[i:i + 1], W2[i:i + 1])
+    return n_triplets / (time.time() - t0)
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores.  The reference is
+    pure Python on torch and cannot travel to the GPU box, so this is the oracle port (oracle/stresnet_oracle.py, pinned to
+    the reference's outputs by tests/golden) with every host thread."""
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    per_step = 2
+    vals = []
+    from oracle import stresnet_oracle as O
+    from xfr_b200 import synth
+    torch.set_num_threads(cores)
+    sd = synth.stresnet_state_dict(0)
+    n = per_step * (args.steps + args.warmup)
+    x = synth.synthetic_probes(n, seed=1)
+    g = torch.Generator().manual_seed(5)
+    W2 = torch.randn(n, 2, 512, generator=g) * 0.02
+    k = 0
+    t_steps = []
+    for s in range(args.warmup + args.steps):
+        t0 = time.time()
+        for _ in range(per_step):
+            O.contrastive_ebp(sd, x[k:k + 1], W2[k:k + 1])
+            k += 1
+        if s >= args.warmup:
+            t_steps.append(time.time() - t0)
+    tot = sum(t_steps)
+    v = per_step * args.steps / tot
+    sample = '%d triplets per step, batch 1, torch CPU fp32, %d threads' % (per_step, cores)
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'maps/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * tot / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'contrastive triplet EBP, ResNet-101, synthetic 224x224 (bounded sample of configs[1])',
+                   'mode': 'affineonly_with_prior', 'sample': sample},
+        'cpu_baseline': {'value': v, 'unit': 'maps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': 'maps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--batch', type=int, default=256, help='triplets per GPU per step')
+    ap.add_argument('--chunk', type=int, default=64, help='probes per engine sweep')
+    ap.add_argument('--gemm', default='tf32x3', choices=['tf32x3', 'tf32', 'fp32'])
+    ap.add_argument('--mode', default='affineonly_with_prior')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        return run_reference(args, rank)
+
+    import torch.distributed as dist
+    from xfr_b200 import synth, whitebox
+    from xfr_b200.engine import StResnetEngine  # noqa: F401
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    # ---------------- setup (untimed): weights, probes, classifier rows from encodings of 2*B further images
+    B = args.batch
+    sd = {k: v.to(dev) for k, v in synth.stresnet_state_dict(0).items()}
+    net = whitebox.WhiteboxSTResnet(sd, impl=args.gemm)
+    wb = whitebox.Whitebox(net, ebp_subtree_mode=args.mode)
+    whitebox._CHUNK = args.chunk
+    x_host = synth.synthetic_probes(B, seed=100 + rank).pin_memory()            # [B,3,224,224] fp32, 154 MB at B=256
+    with torch.no_grad():
+        enc = torch.cat([net.encode(synth.synthetic_probes(64, seed=1000 + 16 * rank + i).to(dev)) for i in range(2 * B // 64)]) \
+            if B >= 64 else net.encode(synth.synthetic_probes(2 * B, seed=1000 + rank).to(dev))
+    net.set_triplet_classifiers(enc[:B] / 2500.0, enc[B:2 * B] / 2500.0)       # generate_whitebox_saliency.py:103
+    eng = net.engine()
+    W2 = net.triplet_rows(B)
+    x_dev = x_host.to(dev).permute(0, 2, 3, 1).contiguous()                    # resident NHWC copy for the kernel-side number
+    maps_dev = torch.empty(B, 112, 112, device=dev)
+    maps_host = torch.empty(B, 112, 112).pin_memory()
+    gathered = torch.empty(world * B, 112, 112, device=dev) if world > 1 and rank == 0 else None
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    bwd_events = []
+
+    def step_resident(record):
+        for i in range(0, B, args.chunk):
+            xs, ws = x_dev[i:i + args.chunk], W2[i:i + args.chunk].contiguous()
+            n = xs.shape[0]
+            eng.forward(xs)
+            if record:
+                e0, e1 = ev(), ev()
+                e0.record()
+            P2, _, sums = eng.ebp_backward(eng.priors_contrastive(n, 2, 0, 1), ws, args.mode)
+            if record:
+                e1.record()
+                bwd_events.append((e0, e1))
+            mwp = eng.buf('cmwp', n, 112, 112)
+            eng.be.contrast(P2, sums, n, mwp)
+            eng.be.saliency_post(mwp, maps_dev[i:i + n])
+        if world > 1:
+            dist.gather(maps_dev, list(gathered.split(B)) if rank == 0 else None, dst=0)
+
+    def step_e2e():
+        wb.contrastive_ebp_batch(x_host, 0, 1, out=maps_host)                  # H2D probes, sweep, D2H maps
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn, steps, **kw):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = ev(), ev()
+        s.record()
+        for _ in range(steps):
+            fn(**kw)
+        e.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_resident(False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = eng.be.launches
+    ms = timed(step_resident, args.steps, record=True)
+    launches = eng.be.launches - l0
+    torch.cuda.synchronize()
+    bwd_ms = sum(a.elapsed_time(b) for a, b in bwd_events)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.summary()
+
+    if world > 1:
+        lt = torch.tensor([float(launches), bwd_ms], device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.MAX)
+        bwd_ms = float(lt[1].item())
+    total_maps = world * B * args.steps
+    value = total_maps / (ms / 1e3)
+    e2e = total_maps / (ms_e2e / 1e3)
+    peak, peak_src = measured_peaks()
+    # EBP-backward stage of ONE GPU: algorithmic bytes of the maps it swept / device time of its backward sweeps
+    ach = EBP_BWD_BYTES_PER_MAP * B * args.steps / (bwd_ms / 1e3) / 1e9
+    out = {
+        'metric': METRIC, 'value': value, 'unit': 'maps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': {'tf32x3': 'f32 (3xTF32 tcgen05, fp32 accumulate)', 'tf32': 'tf32', 'fp32': 'f32'}[args.gemm], 'data': 'synthetic',
+        'config': {'workload': 'contrastive triplet EBP, ResNet-101, batch %d synthetic 224x224 per GPU (BASELINE configs[1])' % B,
+                   'mode': args.mode, 'ebp_version': 6, 'chunk': args.chunk, 'gemm': args.gemm,
+                   'l2': 'inputs larger than L2 (%.0f MB probes, %.1f GB workspace per sweep)' % (x_dev.numel() * 4 / 1e6, eng.workspace_bytes() / 1e9),
+                   'weights': 'seeded synthetic (real STR weights are git-LFS pointers)'},
+        'e2e': {'value': e2e, 'unit': 'maps/s', 'h2d_bytes_per_step': int(x_host.numel() * 4), 'd2h_bytes_per_step': int(maps_host.numel() * 4),
+                'ms_per_step': ms_e2e / args.steps},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
+                     'kernel': 'EBP backward sweep (conv_tc_kernel dgrad + fused hook epilogues, join/stem kernels)',
+                     'peak_source': peak_src, 'bwd_ms_per_step': bwd_ms / args.steps,
+                     'tensor_tflops_whole_step': FLOP_PER_MAP * B * args.steps / (ms / 1e3) / 1e12 / 1.0},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count()
+        n = 4
+        out['cpu_baseline'] = {'value': cpu_port(n, cores), 'unit': 'maps/s', 'cores': cores, 'kind': 'port',
+                               'sample': '%d triplets of the same workload, batch 1, torch CPU fp32 restatement (oracle/)' % n}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

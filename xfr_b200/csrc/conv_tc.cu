@@ -2,7 +2,7 @@
 //
 //   D[m, n] = sum_k A[m, k] * B[n, k]      A: NHWC activations (R x R taps, stride 1, zero pad), B: K-major weights
 //
-// One persistent CTA per SM, 320 threads, warp-specialised:
+// One persistent CTA per SM, 448 threads, warp-specialised:
 //   warp 0      TMA producer   - cp.async.bulk.tensor loads of the A tile (128 pixel rows x 32 channels; for 3x3 convs a
 //                                4-D box (32ch, W, bh rows, bn images) shifted by the tap, out-of-bounds rows/columns
 //                                zero-filled by the TMA unit = the conv padding) and of the B tile (BN x 32), both
@@ -12,7 +12,7 @@
 //                                main loop of tile i+1); tcgen05.commit releases smem stages / publishes accumulators
 //   warps 2-5   operand split  - (3xTF32 only) rewrite each landed stage as hi = rna_tf32(x) in place and lo = x - hi in
 //                                a twin buffer; the issuer then runs hi*hi + lo*hi + hi*lo into the same accumulator
-//   warps 6-9   epilogue       - tcgen05.ld the accumulator (lane = pixel row), apply the fused EBP epilogue of
+//   warps 6-13  epilogue       - tcgen05.ld the accumulator (lane = pixel row), apply the fused EBP epilogue of
 //                                common.cuh against the saved tensors, store NHWC fp32 with 128-bit accesses
 #include "common.cuh"
 #include <cuda.h>
@@ -22,7 +22,8 @@ namespace xfrb {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                       // 32 fp32 = one 128-byte swizzle row
-constexpr int TC_THREADS = 320;
+constexpr int TC_EPI_WARPS = 8;                  // two warps per TMEM lane quarter, alternating 16-column chunks
+constexpr int TC_THREADS = (6 + TC_EPI_WARPS) * 32;   // 448
 constexpr uint32_t A_TILE_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 
 struct TcGeom {
@@ -119,10 +120,11 @@ struct TcCfg {
     static constexpr uint32_t STAGE_BYTES = (A_TILE_BYTES + B_TILE_BYTES) * (SPLIT3 ? 2 : 1);
     static constexpr int STAGES = SPLIT3 ? (BN == 128 ? 3 : 4) : (BN == 128 ? 6 : 8);
     static constexpr uint32_t TMEM_COLS = 2 * BN;          // two accumulator stages (128 or 256: powers of two)
-    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr uint32_t PRM_BYTES = 2 * 6 * BN * 4;   // per accumulator stage: bn[4][BN] + bias_t[BN] + bias_p[BN]
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + PRM_BYTES;
 };
 
-template <int BN, bool SPLIT3>
+template <int BN, bool SPLIT3, int KIND>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGeom g, const EpiParams ep) {
     using Cfg = TcCfg<BN, SPLIT3>;
@@ -138,6 +140,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + 2 + a); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8 * (3 * STAGES + 4));
+    float* prm_s = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 256);   // [2][6][BN]
 
     auto a_hi = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
     auto b_hi = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + A_TILE_BYTES; };
@@ -157,7 +160,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 4);
+            mbar_init(tempty_bar(a), TC_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -289,56 +292,123 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ===================== epilogue =====================
+        // Thread = one pixel row of the tile (TMEM lane); the two warps of a lane quarter alternate 16-column
+        // chunks.  Every global load of a chunk (saved tensors, read-only path) is issued before the first use so
+        // that ~16 128-bit requests per thread are in flight; per-channel constants come from shared memory.
+        const int ew = warp - 6;                       // 0..7
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
+        const int half = ew >> 2;                      // which chunks of the tile this warp owns
         const int row = q * 32 + lane;
+        const int et = threadIdx.x - 6 * 32;           // 0..255
+        constexpr int CH = (KIND == EPI_FWD_DUAL) ? BN / 2 : BN;      // channels per tile
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int a = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             int m0, mvalid, n_img0, h0, ncol0;
             tile_coords(tile, m0, mvalid, n_img0, h0, ncol0);
+            const int cbase = (KIND == EPI_FWD_DUAL) ? (ncol0 / BN) * (BN / 2) : ncol0;
+            float* prm = prm_s + a * 6 * BN;
+            // stage the per-channel constants of this tile: rows 0-3 bn (alpha, beta, sp, tp), 4 bias_t, 5 bias_p
+            if (KIND != EPI_PLAIN) {
+                for (int i = et; i < 4 * CH; i += TC_EPI_WARPS * 32) {
+                    int r = i / CH, j = i - r * CH;
+                    prm[r * BN + j] = __ldg(ep.bn + (size_t)r * ep.C + cbase + j);
+                }
+            }
+            if (KIND == EPI_FWD_DUAL) {
+                for (int i = et; i < BN; i += TC_EPI_WARPS * 32) {
+                    int r = i / CH, j = i - r * CH;            // r = 0: true bias, 1: positive twin
+                    prm[(4 + r) * BN + j] = __ldg(ep.bias + ncol0 + r * CH + j);
+                }
+            } else if (KIND == EPI_PLAIN) {
+                for (int i = et; i < BN; i += TC_EPI_WARPS * 32) prm[4 * BN + i] = ep.bias ? __ldg(ep.bias + ncol0 + i) : 0.f;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
             mbar_wait(tfull_bar(a), aph);
             tc_fence_after();
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
             const bool valid = row < mvalid;
             const int m = m0 + row;
-            if (ep.kind == EPI_FWD_DUAL) {
-                // BN == 128: columns [0,64) true channels, [64,128) relu(W) twins of the same channels
-                const int cbase = (ncol0 / BN) * (BN / 2);
+            const int ms = (KIND == EPI_MID || KIND == EPI_JOIN) ? m % ep.Ms : m;
 #pragma unroll 1
-                for (int j = 0; j < BN / 2; j += 16) {
-                    float vt[16], vp[16];
-                    tmem_ld16(tacc + j, vt);
-                    tmem_ld16(tacc + BN / 2 + j, vp);
-                    tmem_ld_wait(vt);
-                    tmem_ld_wait(vp);
-                    if (valid) {
+            for (int j = half * 16; j < CH; j += 32) {
+                const int c = cbase + j;
+                float vt[16], vp[16];
+                tmem_ld16(tacc + j, vt);
+                if (KIND == EPI_FWD_DUAL) tmem_ld16(tacc + CH + j, vp);
+                // ---- issue every global load of this chunk before touching the accumulator
+                float4 l0[4], l1[4], l2[4], l3[4];
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                        for (int e = 0; e < 16; e += 4) {
-                            float4 bt = ld4(ep.bias + ncol0 + j + e), bp = ld4(ep.bias + ncol0 + BN / 2 + j + e);
-                            epilogue4(ep, m, cbase + j + e, make_float4(vt[e], vt[e + 1], vt[e + 2], vt[e + 3]),
-                                      make_float4(vp[e], vp[e + 1], vp[e + 2], vp[e + 3]), bt, bp);
+                for (int e = 0; e < 4; ++e) l0[e] = l1[e] = l2[e] = l3[e] = z4;
+                if (valid) {
+                    if (KIND == EPI_FWD_DUAL) {
+                        if (ep.res != nullptr && c < ep.res_c) {
+                            const float4* rp = reinterpret_cast<const float4*>(ep.res + (size_t)m * ep.res_c + c);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) l0[e] = __ldg(rp + e);
+                        }
+                    } else if (KIND == EPI_MID || KIND == EPI_JOIN) {
+                        const size_t offs = (size_t)ms * ep.C + c;
+                        const float4* op = reinterpret_cast<const float4*>(ep.o + offs);
+                        const float4* xp = reinterpret_cast<const float4*>(ep.xr + offs);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { l0[e] = __ldg(op + e); l1[e] = __ldg(xp + e); }
+                        if (KIND == EPI_JOIN) {
+                            const float4* up = reinterpret_cast<const float4*>(ep.outp + offs);
+                            const float4* gp = reinterpret_cast<const float4*>(ep.g_res + (size_t)m * ep.C + c);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) { l2[e] = __ldg(up + e); l3[e] = __ldg(gp + e); }
                         }
                     }
                 }
-            } else {
-                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-                for (int j = 0; j < BN; j += 16) {
-                    float vt[16];
-                    tmem_ld16(tacc + j, vt);
-                    tmem_ld_wait(vt);
-                    if (valid) {
+                float rr[16];
 #pragma unroll
-                        for (int e = 0; e < 16; e += 4) {
-                            const int c = ncol0 + j + e;
-                            float4 acc = make_float4(vt[e], vt[e + 1], vt[e + 2], vt[e + 3]);
-                            if (ep.kind == EPI_PLAIN && ep.bias != nullptr) {
-                                float4 bt = ld4(ep.bias + c);
-                                acc.x += bt.x; acc.y += bt.y; acc.z += bt.z; acc.w += bt.w;
-                            }
-                            epilogue4(ep, m, c, acc, z4, z4, z4);
+                for (int e = 0; e < 16; ++e) rr[e] = 0.f;
+                if (KIND == EPI_JOIN && valid && ep.mode == XFRB_MODE_ALL && ep.res != nullptr && c < ep.res_c) {
+                    const float4* rp = reinterpret_cast<const float4*>(ep.res + (size_t)ms * ep.res_c + c);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { float4 t = __ldg(rp + e); rr[4 * e] = t.x; rr[4 * e + 1] = t.y; rr[4 * e + 2] = t.z; rr[4 * e + 3] = t.w; }
+                }
+                tmem_ld_wait(vt);
+                if (KIND == EPI_FWD_DUAL) tmem_ld_wait(vp);
+                if (valid) {
+                    const size_t off = (size_t)m * ep.C + c;
+                    const float* la = reinterpret_cast<const float*>(l0);
+                    const float* lb = reinterpret_cast<const float*>(l1);
+                    const float* lc = reinterpret_cast<const float*>(l2);
+                    const float* ld = reinterpret_cast<const float*>(l3);
+                    float r0[16], r1[16], r2[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        BnC b;
+                        if (KIND != EPI_PLAIN) { b.alpha = prm[j + e]; b.beta = prm[BN + j + e]; b.sp = prm[2 * BN + j + e]; b.tp = prm[3 * BN + j + e]; }
+                        if (KIND == EPI_PLAIN) {
+                            r0[e] = vt[e] + prm[4 * BN + j + e];
+                        } else if (KIND == EPI_FWD_DUAL) {
+                            float o = __fadd_rn(vt[e], prm[4 * BN + j + e]);
+                            r0[e] = o;
+                            r1[e] = fmaxf(__fadd_rn(vp[e], prm[5 * BN + j + e]), 0.f);
+                            r2[e] = fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(o, b.alpha), b.beta), la[e]), 0.f);
+                        } else if (KIND == EPI_MID) {
+                            r0[e] = mid_chain(vt[e], la[e], lb[e], b, ep.mode, ep.eps);
+                        } else {
+                            join_chain(__fadd_rn(vt[e], ld[e]), lc[e], la[e], lb[e], rr[e], b, ep.hooks, ep.mode, ep.eps, r0[e], r1[e]);
                         }
+                    }
+                    float4* p0 = reinterpret_cast<float4*>(ep.out0 + off);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) p0[e] = make_float4(r0[4 * e], r0[4 * e + 1], r0[4 * e + 2], r0[4 * e + 3]);
+                    if (KIND == EPI_FWD_DUAL || KIND == EPI_JOIN) {
+                        float4* p1 = reinterpret_cast<float4*>(ep.out1 + off);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) p1[e] = make_float4(r1[4 * e], r1[4 * e + 1], r1[4 * e + 2], r1[4 * e + 3]);
+                    }
+                    if (KIND == EPI_FWD_DUAL) {
+                        float4* p2 = reinterpret_cast<float4*>(ep.out2 + off);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) p2[e] = make_float4(r2[4 * e], r2[4 * e + 1], r2[4 * e + 2], r2[4 * e + 3]);
                     }
                 }
             }
@@ -386,13 +456,13 @@ static bool encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t
 
 bool conv_tc_available() { return true; }
 
-template <int BN, bool SPLIT3>
+template <int BN, bool SPLIT3, int KIND>
 static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGeom& g, const EpiParams& ep, cudaStream_t st) {
     using Cfg = TcCfg<BN, SPLIT3>;
     static bool attr = false;
     static int sms = 0;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT3, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -401,7 +471,7 @@ static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, co
     }
     int total = g.n_m_tiles * g.n_n_tiles;
     int grid = total < sms ? total : sms;
-    conv_tc_kernel<BN, SPLIT3><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, g, ep);
+    conv_tc_kernel<BN, SPLIT3, KIND><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, g, ep);
     return cudaGetLastError();
 }
 
@@ -465,8 +535,20 @@ cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, c
         cuuint32_t box[2] = {TC_BK, (cuuint32_t)BN};
         if (!encode(&tmB, B, 2, dims, strides, box)) return cudaErrorInvalidValue;
     }
-    if (BN == 128) return split3 ? launch_cfg<128, true>(tmA, tmB, g, ep, st) : launch_cfg<128, false>(tmA, tmB, g, ep, st);
-    return split3 ? launch_cfg<64, true>(tmA, tmB, g, ep, st) : launch_cfg<64, false>(tmA, tmB, g, ep, st);
+#define XFRB_TC_DISPATCH(BN_, SP_)                                                                       \
+    switch (ep.kind) {                                                                                   \
+        case EPI_PLAIN: return launch_cfg<BN_, SP_, EPI_PLAIN>(tmA, tmB, g, ep, st);                      \
+        case EPI_FWD_DUAL: return launch_cfg<BN_, SP_, EPI_FWD_DUAL>(tmA, tmB, g, ep, st);                \
+        case EPI_MID: return launch_cfg<BN_, SP_, EPI_MID>(tmA, tmB, g, ep, st);                          \
+        case EPI_JOIN: return launch_cfg<BN_, SP_, EPI_JOIN>(tmA, tmB, g, ep, st);                        \
+        default: return cudaErrorInvalidValue;                                                           \
+    }
+    if (BN == 128) {
+        if (split3) { XFRB_TC_DISPATCH(128, true) } else { XFRB_TC_DISPATCH(128, false) }
+    } else {
+        if (split3) { XFRB_TC_DISPATCH(64, true) } else { XFRB_TC_DISPATCH(64, false) }
+    }
+#undef XFRB_TC_DISPATCH
 }
 
 }  // namespace xfrb

@@ -92,8 +92,8 @@ class CudaBackend(object):
     def _st(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def _check(self, rc):
-        self.launches += 1
+    def _check(self, rc, kernels=1):
+        self.launches += kernels        # kernels this call enqueued (stem_fwd/stem_bwd: 2, head_fwd/head_bwd: 3)
         if rc != 0:
             raise RuntimeError('xfr_b200 kernel failed: %s' % self.lib.xfrb_last_error().decode())
 
@@ -107,7 +107,7 @@ class CudaBackend(object):
     # -------------------------------------------------------------- forward
     def stem_fwd(self, x, stem, o, mp):
         self._check(self.lib.xfrb_stem_fwd(_ptr(x), _ptr(stem.W), _ptr(stem.b), _ptr(stem.bn), _ptr(o), _ptr(mp),
-                                           x.shape[0], self._st()))
+                                           x.shape[0], self._st()), 2)
 
     def subsample2(self, u, out):
         N, H, W, C = u.shape
@@ -127,7 +127,7 @@ class CudaBackend(object):
         N = u.shape[0]
         scratch = self._tmp('head_fwd', N * 1024)
         self._check(self.lib.xfrb_head_fwd(_ptr(u), _ptr(head.B1), _ptr(head.bias1), head.tn, _ptr(scratch), _ptr(v),
-                                           _ptr(f1), _ptr(f1p), _ptr(xn), _ptr(nrm), N, self.impl, self._st()))
+                                           _ptr(f1), _ptr(f1p), _ptr(xn), _ptr(nrm), N, self.impl, self._st()), 3)
 
     # -------------------------------------------------------------- backward
     def head_bwd(self, Pn, W2, head, v, f1p, xn, nrm, mode, g_out, hooked_fc2=False):
@@ -138,7 +138,7 @@ class CudaBackend(object):
         scratch = self._tmp('head_bwd', J * 2560)
         self._check(self.lib.xfrb_head_bwd(_ptr(Pn), _ptr(W2), C, _ptr(head.W1pT), _ptr(v), _ptr(f1p), _ptr(xn),
                                            _ptr(nrm), _ptr(scratch), _ptr(g_out), J, N, mode, self.eps, self.impl,
-                                           self._st()))
+                                           self._st()), 3)
 
     def dgrad_mid(self, y, L, o, xr, bn, mode, y_out):
         J, H, W, Cout = y.shape
@@ -174,7 +174,7 @@ class CudaBackend(object):
         J = zmain.shape[0]
         zc = self._tmp('stem_zc', J * 56 * 56 * 64)
         self._check(self.lib.xfrb_stem_bwd(_ptr(zmain), _ptr(gres), _ptr(o), _ptr(mp), _ptr(bn), _ptr(zc), _ptr(P2),
-                                           _ptr(chansum), _ptr(sums), J, o.shape[0], mode, self.eps, self._st()))
+                                           _ptr(chansum), _ptr(sums), J, o.shape[0], mode, self.eps, self._st()), 2)
 
     def contrast(self, P2, sums, N, out):
         HW = P2.shape[1] * P2.shape[2]
