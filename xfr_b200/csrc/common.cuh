@@ -19,7 +19,9 @@ __device__ __forceinline__ float relu(float v) { return fmaxf(v, 0.f); }
 template <bool AFFINE>
 __device__ __forceinline__ float hook(float a, float x, float z, int mode, float eps) {
     float zh = fmaxf(z, 0.f);
-    if (AFFINE || mode == XFRB_MODE_ALL) return __fdiv_rn(__fmul_rn(a, zh), __fadd_rn(x, eps));
+    // p/(x+eps): x + eps >= 1e-16 is a normal positive float, so the 2-ulp reciprocal path (MUFU.RCP + FMUL) is safe;
+    // an IEEE division costs ~10 issue slots per hook and the epilogues are issue-bound (profiles/r1_notes.md).
+    if (AFFINE || mode == XFRB_MODE_ALL) return __fdividef(__fmul_rn(a, zh), __fadd_rn(x, eps));
     return mode == XFRB_MODE_AWP ? zh : z;
 }
 

@@ -121,7 +121,8 @@ struct TcCfg {
     static constexpr int STAGES = SPLIT3 ? (BN == 128 ? 3 : 4) : (BN == 128 ? 6 : 8);
     static constexpr uint32_t TMEM_COLS = 2 * BN;          // two accumulator stages (128 or 256: powers of two)
     static constexpr uint32_t PRM_BYTES = 2 * 6 * BN * 4;   // per accumulator stage: bn[4][BN] + bias_t[BN] + bias_p[BN]
-    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + PRM_BYTES;
+    static constexpr uint32_t TR_BYTES = TC_EPI_WARPS * 2048;   // per epilogue warp: 32 rows x 16 columns transpose slab
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + PRM_BYTES + TR_BYTES;
 };
 
 template <int BN, bool SPLIT3, int KIND>
@@ -141,6 +142,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + 2 + a); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8 * (3 * STAGES + 4));
     float* prm_s = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 256);   // [2][6][BN]
+    float4* tr_s = reinterpret_cast<float4*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 256 + Cfg::PRM_BYTES);
 
     auto a_hi = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
     auto b_hi = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + A_TILE_BYTES; };
@@ -292,14 +294,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ===================== epilogue =====================
-        // Thread = one pixel row of the tile (TMEM lane); the two warps of a lane quarter alternate 16-column
-        // chunks.  Every global load of a chunk (saved tensors, read-only path) is issued before the first use so
-        // that ~16 128-bit requests per thread are in flight; per-channel constants come from shared memory.
+        // TMEM hands each thread one pixel ROW of the accumulator, but NHWC tensors want consecutive lanes on
+        // consecutive CHANNELS: a 32-row x 16-column slab is therefore transposed through a 2 KB XOR-swizzled smem
+        // buffer per warp, after which lane l owns channels 4*(l%4)..+3 of rows 8i + l/4 (i = 0..3).  Every global
+        // access of the epilogue is then a 64-byte row segment per 4 lanes (8 rows per request instead of 32), and all
+        // loads of a slab are issued before the accumulator is waited for.  The two warps of a TMEM lane quarter
+        // alternate slabs; per-channel constants are staged in smem once per tile.
         const int ew = warp - 6;                       // 0..7
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
-        const int half = ew >> 2;                      // which chunks of the tile this warp owns
-        const int row = q * 32 + lane;
+        const int half = ew >> 2;                      // which slabs of the tile this warp owns
         const int et = threadIdx.x - 6 * 32;           // 0..255
+        const int cgl = lane & 3;                      // my 4-channel group inside the slab
+        const int rsub = lane >> 2;                    // my row inside each group of 8 rows
+        float4* tbuf = tr_s + ew * 128;
         constexpr int CH = (KIND == EPI_FWD_DUAL) ? BN / 2 : BN;      // channels per tile
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -328,88 +335,123 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(tfull_bar(a), aph);
             tc_fence_after();
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
-            const bool valid = row < mvalid;
-            const int m = m0 + row;
-            const int ms = (KIND == EPI_MID || KIND == EPI_JOIN) ? m % ep.Ms : m;
+            // rows this thread finishes (coalesced orientation)
+            int mrow[4], msav[4];
+            bool vrow[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = q * 32 + 8 * i + rsub;
+                vrow[i] = r < mvalid;
+                mrow[i] = m0 + r;
+                msav[i] = (KIND == EPI_MID || KIND == EPI_JOIN) ? mrow[i] % ep.Ms : mrow[i];
+            }
 #pragma unroll 1
             for (int j = half * 16; j < CH; j += 32) {
-                const int c = cbase + j;
+                const int c = cbase + j + 4 * cgl;
                 float vt[16], vp[16];
                 tmem_ld16(tacc + j, vt);
                 if (KIND == EPI_FWD_DUAL) tmem_ld16(tacc + CH + j, vp);
-                // ---- issue every global load of this chunk before touching the accumulator
-                float4 l0[4], l1[4], l2[4], l3[4];
+                // ---- issue every global load of this slab before touching the accumulator
                 const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 l0[4], l1[4], l2[4], l3[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) l0[e] = l1[e] = l2[e] = l3[e] = z4;
-                if (valid) {
+                for (int i = 0; i < 4; ++i) {
+                    l0[i] = l1[i] = l2[i] = l3[i] = z4;
+                    if (!vrow[i]) continue;
                     if (KIND == EPI_FWD_DUAL) {
-                        if (ep.res != nullptr && c < ep.res_c) {
-                            const float4* rp = reinterpret_cast<const float4*>(ep.res + (size_t)m * ep.res_c + c);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) l0[e] = __ldg(rp + e);
-                        }
+                        if (ep.res != nullptr && c < ep.res_c) l0[i] = __ldg(reinterpret_cast<const float4*>(ep.res + (size_t)mrow[i] * ep.res_c + c));
                     } else if (KIND == EPI_MID || KIND == EPI_JOIN) {
-                        const size_t offs = (size_t)ms * ep.C + c;
-                        const float4* op = reinterpret_cast<const float4*>(ep.o + offs);
-                        const float4* xp = reinterpret_cast<const float4*>(ep.xr + offs);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) { l0[e] = __ldg(op + e); l1[e] = __ldg(xp + e); }
+                        const size_t offs = (size_t)msav[i] * ep.C + c;
+                        l0[i] = __ldg(reinterpret_cast<const float4*>(ep.o + offs));
+                        l1[i] = __ldg(reinterpret_cast<const float4*>(ep.xr + offs));
                         if (KIND == EPI_JOIN) {
-                            const float4* up = reinterpret_cast<const float4*>(ep.outp + offs);
-                            const float4* gp = reinterpret_cast<const float4*>(ep.g_res + (size_t)m * ep.C + c);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) { l2[e] = __ldg(up + e); l3[e] = __ldg(gp + e); }
+                            l2[i] = __ldg(reinterpret_cast<const float4*>(ep.outp + offs));
+                            l3[i] = __ldg(reinterpret_cast<const float4*>(ep.g_res + (size_t)mrow[i] * ep.C + c));
                         }
                     }
                 }
-                float rr[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) rr[e] = 0.f;
-                if (KIND == EPI_JOIN && valid && ep.mode == XFRB_MODE_ALL && ep.res != nullptr && c < ep.res_c) {
-                    const float4* rp = reinterpret_cast<const float4*>(ep.res + (size_t)ms * ep.res_c + c);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { float4 t = __ldg(rp + e); rr[4 * e] = t.x; rr[4 * e + 1] = t.y; rr[4 * e + 2] = t.z; rr[4 * e + 3] = t.w; }
-                }
+                // ---- transpose the accumulator slab(s): row-per-lane -> channel-group-per-lane
+                float4 at[4], apv[4];
                 tmem_ld_wait(vt);
-                if (KIND == EPI_FWD_DUAL) tmem_ld_wait(vp);
-                if (valid) {
-                    const size_t off = (size_t)m * ep.C + c;
-                    const float* la = reinterpret_cast<const float*>(l0);
-                    const float* lb = reinterpret_cast<const float*>(l1);
-                    const float* lc = reinterpret_cast<const float*>(l2);
-                    const float* ld = reinterpret_cast<const float*>(l3);
-                    float r0[16], r1[16], r2[16];
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        BnC b;
-                        if (KIND != EPI_PLAIN) { b.alpha = prm[j + e]; b.beta = prm[BN + j + e]; b.sp = prm[2 * BN + j + e]; b.tp = prm[3 * BN + j + e]; }
-                        if (KIND == EPI_PLAIN) {
-                            r0[e] = vt[e] + prm[4 * BN + j + e];
-                        } else if (KIND == EPI_FWD_DUAL) {
-                            float o = __fadd_rn(vt[e], prm[4 * BN + j + e]);
-                            r0[e] = o;
-                            r1[e] = fmaxf(__fadd_rn(vp[e], prm[5 * BN + j + e]), 0.f);
-                            r2[e] = fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(o, b.alpha), b.beta), la[e]), 0.f);
-                        } else if (KIND == EPI_MID) {
-                            r0[e] = mid_chain(vt[e], la[e], lb[e], b, ep.mode, ep.eps);
-                        } else {
-                            join_chain(__fadd_rn(vt[e], ld[e]), lc[e], la[e], lb[e], rr[e], b, ep.hooks, ep.mode, ep.eps, r0[e], r1[e]);
+                for (int g4 = 0; g4 < 4; ++g4)
+                    tbuf[lane * 4 + (g4 ^ ((lane >> 1) & 3))] = make_float4(vt[4 * g4], vt[4 * g4 + 1], vt[4 * g4 + 2], vt[4 * g4 + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rl = 8 * i + rsub;
+                    at[i] = tbuf[rl * 4 + (cgl ^ ((rl >> 1) & 3))];
+                }
+                __syncwarp();
+                if (KIND == EPI_FWD_DUAL) {
+                    tmem_ld_wait(vp);
+#pragma unroll
+                    for (int g4 = 0; g4 < 4; ++g4)
+                        tbuf[lane * 4 + (g4 ^ ((lane >> 1) & 3))] = make_float4(vp[4 * g4], vp[4 * g4 + 1], vp[4 * g4 + 2], vp[4 * g4 + 3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rl = 8 * i + rsub;
+                        apv[i] = tbuf[rl * 4 + (cgl ^ ((rl >> 1) & 3))];
+                    }
+                    __syncwarp();
+                }
+                // ---- per-channel constants of my 4 channels
+                const int pj = j + 4 * cgl;
+                BnC b[4];
+                float bt[4] = {0.f, 0.f, 0.f, 0.f}, bp[4] = {0.f, 0.f, 0.f, 0.f};
+                if (KIND != EPI_PLAIN) {
+                    const float4 al = *reinterpret_cast<const float4*>(prm + pj), be = *reinterpret_cast<const float4*>(prm + BN + pj);
+                    const float4 sp = *reinterpret_cast<const float4*>(prm + 2 * BN + pj), tp = *reinterpret_cast<const float4*>(prm + 3 * BN + pj);
+                    b[0] = {al.x, be.x, sp.x, tp.x}; b[1] = {al.y, be.y, sp.y, tp.y}; b[2] = {al.z, be.z, sp.z, tp.z}; b[3] = {al.w, be.w, sp.w, tp.w};
+                }
+                if (KIND == EPI_PLAIN || KIND == EPI_FWD_DUAL) {
+                    const float4 t = *reinterpret_cast<const float4*>(prm + 4 * BN + pj);
+                    bt[0] = t.x; bt[1] = t.y; bt[2] = t.z; bt[3] = t.w;
+                }
+                if (KIND == EPI_FWD_DUAL) {
+                    const float4 t = *reinterpret_cast<const float4*>(prm + 5 * BN + pj);
+                    bp[0] = t.x; bp[1] = t.y; bp[2] = t.z; bp[3] = t.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (!vrow[i]) continue;
+                    const size_t off = (size_t)mrow[i] * ep.C + c;
+                    const float av[4] = {at[i].x, at[i].y, at[i].z, at[i].w};
+                    const float la[4] = {l0[i].x, l0[i].y, l0[i].z, l0[i].w};
+                    const float lb[4] = {l1[i].x, l1[i].y, l1[i].z, l1[i].w};
+                    float r0[4], r1[4], r2[4];
+                    if (KIND == EPI_PLAIN) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) r0[e] = av[e] + bt[e];
+                    } else if (KIND == EPI_FWD_DUAL) {
+                        const float pv[4] = {apv[i].x, apv[i].y, apv[i].z, apv[i].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            r0[e] = __fadd_rn(av[e], bt[e]);
+                            r1[e] = fmaxf(__fadd_rn(pv[e], bp[e]), 0.f);
+                            r2[e] = fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(r0[e], b[e].alpha), b[e].beta), la[e]), 0.f);
                         }
-                    }
-                    float4* p0 = reinterpret_cast<float4*>(ep.out0 + off);
+                    } else if (KIND == EPI_MID) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) p0[e] = make_float4(r0[4 * e], r0[4 * e + 1], r0[4 * e + 2], r0[4 * e + 3]);
-                    if (KIND == EPI_FWD_DUAL || KIND == EPI_JOIN) {
-                        float4* p1 = reinterpret_cast<float4*>(ep.out1 + off);
+                        for (int e = 0; e < 4; ++e) r0[e] = mid_chain(av[e], la[e], lb[e], b[e], ep.mode, ep.eps);
+                    } else {
+                        const float lc[4] = {l2[i].x, l2[i].y, l2[i].z, l2[i].w};
+                        const float ld[4] = {l3[i].x, l3[i].y, l3[i].z, l3[i].w};
+                        float rr[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (ep.mode == XFRB_MODE_ALL && ep.res != nullptr && c < ep.res_c) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(ep.res + (size_t)msav[i] * ep.res_c + c));
+                            rr[0] = t.x; rr[1] = t.y; rr[2] = t.z; rr[3] = t.w;
+                        }
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) p1[e] = make_float4(r1[4 * e], r1[4 * e + 1], r1[4 * e + 2], r1[4 * e + 3]);
+                        for (int e = 0; e < 4; ++e)
+                            join_chain(__fadd_rn(av[e], ld[e]), lc[e], la[e], lb[e], rr[e], b[e], ep.hooks, ep.mode, ep.eps, r0[e], r1[e]);
                     }
-                    if (KIND == EPI_FWD_DUAL) {
-                        float4* p2 = reinterpret_cast<float4*>(ep.out2 + off);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) p2[e] = make_float4(r2[4 * e], r2[4 * e + 1], r2[4 * e + 2], r2[4 * e + 3]);
-                    }
+                    *reinterpret_cast<float4*>(ep.out0 + off) = make_float4(r0[0], r0[1], r0[2], r0[3]);
+                    if (KIND == EPI_FWD_DUAL || KIND == EPI_JOIN)
+                        *reinterpret_cast<float4*>(ep.out1 + off) = make_float4(r1[0], r1[1], r1[2], r1[3]);
+                    if (KIND == EPI_FWD_DUAL)
+                        *reinterpret_cast<float4*>(ep.out2 + off) = make_float4(r2[0], r2[1], r2[2], r2[3]);
                 }
             }
             tc_fence_before();
