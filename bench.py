@@ -167,7 +167,7 @@ def main():
     x_dev = x_host.to(dev).permute(0, 2, 3, 1).contiguous()                    # resident NHWC copy for the kernel-side number
     maps_dev = torch.empty(B, 112, 112, device=dev)
     maps_host = torch.empty(B, 112, 112).pin_memory()
-    gathered = torch.empty(world * B, 112, 112, device=dev) if world > 1 and rank == 0 else None
+    from xfr_b200.shard import gather_maps
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     bwd_events = []
@@ -188,7 +188,7 @@ def main():
             eng.be.contrast(P2, sums, n, mwp)
             eng.be.saliency_post(mwp, maps_dev[i:i + n])
         if world > 1:
-            dist.gather(maps_dev, list(gathered.split(B)) if rank == 0 else None, dst=0)
+            gather_maps(maps_dev, world * B, dst=0)          # the only collective on the data path (NCCL gather)
 
     def step_e2e():
         wb.contrastive_ebp_batch(x_host, 0, 1, out=maps_host)                  # H2D probes, sweep, D2H maps
