@@ -123,8 +123,14 @@ int xfrb_stem_bwd(const float* zmain, const float* gres, const float* o, const f
                   float* zc, float* P2, float* chansum, double* sums,
                   int J, int N, int mode, float eps, void* stream);
 
-/* out[n] = sum_c relu(P2[n]/sums[n] - P2[N+n]/sums[N+n])  (whitebox.py:524-526) */
-int xfrb_contrast(const float* P2, const double* sums, float* out, int N, int HW, int C, void* stream);
+/* out[n] = sum_c relu(k*P2[n]/sums[n] - k*P2[N+n]/sums[N+n])  (whitebox.py:524-526); k = 1, or with thr != NULL the
+ * truncation mask k = (P2[n] >= thr[n]) of whitebox.py:550-556 */
+int xfrb_contrast(const float* P2, const double* sums, const float* thr, float* out, int N, int HW, int C, void* stream);
+
+/* Truncated contrastive EBP (whitebox.py:550-554): thr[n] = the smallest mate-MWP value whose ascending cumulative sum
+ * reaches percentile% of the total, over the first N rows of P2 (per_sample elements each). */
+int xfrb_trunc_threshold(const float* P2, const double* sums, float percentile, float* thr, int N, long long per_sample,
+                         void* stream);
 
 /* skimage.filters.gaussian(sigma=2) -> max(0,.) -> /max(sum,eps)  (whitebox.py:455-460); [B,H,W], H,W <= 128 */
 int xfrb_saliency_post(const float* mwp, float* out, int B, int H, int W, float eps, void* stream);

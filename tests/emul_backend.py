@@ -229,12 +229,25 @@ class EmulBackend(object):
         chansum.copy_(p.sum(-1))
         sums.copy_(p.double().sum(dim=(1, 2, 3)))
 
-    def contrast(self, P2, sums, N, out):
-        """out[n] = sum_c relu(P2[n]/sums[n] - P2[N+n]/sums[N+n])  (reference whitebox.py:524-526)."""
+    def contrast(self, P2, sums, N, out, thr=None):
+        """out[n] = sum_c relu(k*P2[n]/sums[n] - k*P2[N+n]/sums[N+n]), k = (P2[n] >= thr[n]) or 1
+        (reference whitebox.py:524-526, 556)."""
         sf = sums.float()
         pm = P2[:N] / sf[:N].view(N, 1, 1, 1)
         pn = P2[N:2 * N] / sf[N:2 * N].view(N, 1, 1, 1)
-        out.copy_(relu(pm - pn).sum(-1))
+        d = relu(pm - pn)
+        if thr is not None:
+            d = d * (P2[:N] >= thr.view(N, 1, 1, 1))
+        out.copy_(d.sum(-1))
+
+    def trunc_threshold(self, P2, sums, N, percentile, thr):
+        """thr[n] = smallest value of P2[n] whose ascending cumulative sum reaches percentile% of the total
+        (reference whitebox.py:550-554, evaluated in double)."""
+        for n in range(N):
+            srt, _ = torch.sort(P2[n].flatten().double())
+            cs = torch.cumsum(srt, 0)
+            k = int(torch.searchsorted(cs, torch.tensor(percentile / 100.0 * float(sums[n]), dtype=torch.float64)))
+            thr[n] = 0.0 if percentile <= 0 else float(srt[min(k, srt.numel() - 1)])
 
     def saliency_post(self, mwp, out):
         """gaussian(sigma=2, nearest, truncate 4) -> max(0,.) -> / max(sum, eps)  (whitebox.py:455-460)."""

@@ -39,7 +39,7 @@ class ShadowBackend(object):
         'stem_fwd': (2, 3), 'subsample2': (1,), 'avgpool2': (1,), 'conv_dual': (2, 3, 4),
         'head_fwd': (2, 3, 4, 5, 6), 'head_bwd': (8,), 'dgrad_mid': (6,), 'dgrad_plain': (2,),
         'dgrad_join': (10, 11), 'join': (11, 12), 'ds_res': (3,), 'stem_bwd': (6, 7, 8),
-        'contrast': (3,), 'saliency_post': (1,),
+        'contrast': (3,), 'saliency_post': (1,), 'trunc_threshold': (4,),
     }
 
     def __init__(self, cuda_be, emul_be, pack_map):

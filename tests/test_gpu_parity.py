@@ -78,3 +78,55 @@ def test_batch_rows_are_independent():
     for i in (0, 3):
         one = eng.contrastive(x[i:i + 1].contiguous(), W2[i:i + 1].contiguous()).cpu().numpy()
         assert rel_err(one[0], full[i]) < 1e-5
+
+
+def test_whitebox_api_vs_reference():
+    """The drop-in classes (xfr_b200.whitebox) called the way demo/test_whitebox.py calls the reference's."""
+    from xfr_b200 import whitebox
+    G = golden(L101)
+    dev = torch.device('cuda:0')
+    sd = {k: v.to(dev) for k, v in synth.stresnet_state_dict(0, L101, 2).items()}
+    x, W2, imgs = golden_inputs(G)
+    probe = imgs[0:1]                                       # NCHW like net.preprocess() returns
+    for ver, key_c, key_t in ((None, 'cebp_awp_smooth', 'tcebp20_awp_smooth'), (11, 'cebp_v11_u8', None)):
+        wb = whitebox.Whitebox(whitebox.WhiteboxSTResnet(sd), ebp_version=ver)
+        x_mate = wb.net.encode(imgs[1:2])
+        x_non = wb.net.encode(imgs[2:3])
+        assert rel_err(x_mate.cpu().numpy(), G['enc_mate']) < 1e-3
+        wb.net.set_triplet_classifier((1.0 / 2500.0) * x_mate, (1.0 / 2500.0) * x_non)
+        assert wb.net.num_classes() == 2
+        c = wb.contrastive_ebp(probe, k_poschannel=0, k_negchannel=1)
+        assert c.shape == (112, 112)
+        if ver is None:
+            assert c.dtype == np.float32 and np.abs(c - G[key_c]).max() < 1e-4
+            t = wb.truncated_contrastive_ebp(probe, 0, 1, percentile=20)
+            assert np.abs(t - G[key_t]).max() < 1e-4 and rel_err(t, G[key_t]) < 5e-2
+            P = torch.zeros(1, 2)
+            P[0][0] = 1.0
+            e = wb.ebp(probe, P)
+            assert rel_err(e, G['ebp_awp_smooth']) < 5e-3
+            em = wb.ebp(probe, P, mwp=True)
+            assert rel_err(em, G['ebp_mwp_awp_smooth']) < 5e-3
+        else:
+            assert c.dtype == np.uint8                       # ebp_version 11: with_bias + uint8/PIL post-processing
+            assert np.abs(c.astype(np.int32) - G[key_c].astype(np.int32)).max() <= 40   # contrastive noise amplified by min-max stretch
+    with pytest.raises(RuntimeError):
+        whitebox.Whitebox(whitebox.WhiteboxSTResnet(sd), ebp_version=3)
+
+
+def test_full_size_properties():
+    """Size-independent checks at a full 64-probe sweep: maps are non-negative, sum to one, permuting the batch permutes
+    the maps, and swapping mate/non-mate rows equals swapping k_pos/k_neg."""
+    eng, dev = _engine(L101, 'tf32x3')
+    N = 64
+    x = synth.synthetic_probes(N, seed=11).permute(0, 2, 3, 1).contiguous().to(dev)
+    g = torch.Generator().manual_seed(12)
+    W2 = (torch.randn(N, 2, 512, generator=g) * 0.02).to(dev)
+    a = eng.contrastive(x, W2).clone()
+    assert torch.isfinite(a).all() and (a >= 0).all()
+    assert torch.allclose(a.sum(dim=(1, 2)), torch.ones(N, device=dev), atol=1e-4)
+    perm = torch.randperm(N, generator=g).to(dev)
+    b = eng.contrastive(x[perm].contiguous(), W2[perm].contiguous()).clone()
+    assert float((b - a[perm]).abs().max() / a.max()) < 1e-4
+    c = eng.contrastive(x, W2.flip(1).contiguous(), k_pos=1, k_neg=0).clone()
+    assert float((c - a).abs().max() / a.max()) < 1e-4

@@ -67,3 +67,22 @@ def test_resnet101_default_mode():
     # (oracle vs hooks, both CPU fp32) is 2e-3 of the map maximum here; see DESIGN.md "parity".
     assert rel_err(c[0], G['cebp_awp_smooth']) < 2e-2
     assert np.abs(c[0] - G['cebp_awp_smooth']).max() < 1e-4
+
+
+@pytest.mark.parametrize('layers', [L1111, L101])
+def test_truncated_and_with_bias(layers):
+    G = golden(layers)
+    sd = synth.stresnet_state_dict(0, layers, 2)
+    x, W2, _ = golden_inputs(G)
+    eng = StResnetEngine(sd, EmulBackend(), layers)
+    c = eng.contrastive(x, W2, percentile=20).clone().numpy()
+    tol = 5e-4 if layers == L1111 else 2e-2
+    for i, pname in enumerate(('smooth', 'noise')):
+        assert rel_err(c[i], G['tcebp20_awp_%s' % pname]) < tol
+        assert np.abs(c[i] - G['tcebp20_awp_%s' % pname]).max() < 1e-4
+    engb = StResnetEngine(sd, EmulBackend(), layers, with_bias=True)
+    P1 = torch.zeros(1, 2)
+    P1[:, 0] = 1
+    m = engb.ebp(x[:1], P1, W2[:1], saliency=False).clone().numpy()
+    assert rel_err(m[0], G['ebp_mwp_awp_withbias']) < 1e-5
+    assert rel_err(m[0], G['ebp_mwp_awp_smooth']) > 1e-4        # with_bias really changes the map

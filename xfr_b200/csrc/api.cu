@@ -25,7 +25,8 @@ cudaError_t launch_join(const JoinArgs&, cudaStream_t);
 cudaError_t launch_ds_res(const float*, const float*, float*, int, int, int, int, int, int, int, float, cudaStream_t);
 cudaError_t launch_stem_bwd(const float*, const float*, const float*, const float*, const float*, float*, float*, float*,
                             double*, int, int, int, float, cudaStream_t);
-cudaError_t launch_contrast(const float*, const double*, float*, int, int, int, cudaStream_t);
+cudaError_t launch_contrast(const float*, const double*, const float*, float*, int, int, int, cudaStream_t);
+cudaError_t launch_trunc_threshold(const float*, const double*, float, float*, int, size_t, cudaStream_t);
 cudaError_t launch_saliency_post(const float*, float*, int, int, int, float, cudaStream_t);
 
 static int finish(const char* what, cudaError_t e) {
@@ -194,8 +195,13 @@ int xfrb_stem_bwd(const float* zmain, const float* gres, const float* o, const f
     return finish("xfrb_stem_bwd", launch_stem_bwd(zmain, gres, o, mp, bn, zc, P2, chansum, sums, J, N, mode, eps, (cudaStream_t)stream));
 }
 
-int xfrb_contrast(const float* P2, const double* sums, float* out, int N, int HW, int C, void* stream) {
-    return finish("xfrb_contrast", launch_contrast(P2, sums, out, N, HW, C, (cudaStream_t)stream));
+int xfrb_contrast(const float* P2, const double* sums, const float* thr, float* out, int N, int HW, int C, void* stream) {
+    return finish("xfrb_contrast", launch_contrast(P2, sums, thr, out, N, HW, C, (cudaStream_t)stream));
+}
+
+int xfrb_trunc_threshold(const float* P2, const double* sums, float percentile, float* thr, int N, long long per_sample,
+                         void* stream) {
+    return finish("xfrb_trunc_threshold", launch_trunc_threshold(P2, sums, percentile, thr, N, (size_t)per_sample, (cudaStream_t)stream));
 }
 
 int xfrb_saliency_post(const float* mwp, float* out, int B, int H, int W, float eps, void* stream) {

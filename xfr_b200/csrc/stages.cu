@@ -449,11 +449,68 @@ cudaError_t launch_stem_bwd(const float* zmain, const float* gres, const float* 
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ truncation threshold
+// truncated_contrastive_ebp (whitebox.py:550-554): ascending sort of the mate MWP, cumulative sum, keep the elements whose
+// running sum has reached percentile% of the total.  Values are >= 0, so their IEEE bit patterns are ordered like the
+// values and the first kept element v* is found by a 3-level radix descent (11 + 11 + 10 bits) over per-bin VALUE SUMS
+// accumulated in double: thr[n] = v*, mask = (P >= v*).  One block per sample; three streaming passes over 3.2 MB.
+__global__ void __launch_bounds__(1024) trunc_threshold_kernel(const float* __restrict__ P2, const double* __restrict__ sums,
+                                                               float pct, float* __restrict__ thr, size_t per_sample) {
+    __shared__ double hist[2048];
+    __shared__ unsigned int s_prefix;
+    __shared__ double s_below;
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const float* p = P2 + (size_t)n * per_sample;
+    const double target = (double)(pct / 100.0f) * sums[n];
+    if (tid == 0) { s_prefix = 0u; s_below = 0.0; }
+    const int shifts[3] = {21, 10, 0};
+    const int widths[3] = {11, 11, 10};
+    for (int level = 0; level < 3; ++level) {
+        const int nb = 1 << widths[level];
+        for (int i = tid; i < nb; i += 1024) hist[i] = 0.0;
+        __syncthreads();
+        const unsigned int prefix = s_prefix;
+        const int sh = shifts[level];
+        const int hsh = sh + widths[level];            // bits above this level must equal the prefix
+        for (size_t i = tid; i < per_sample / 4; i += 1024) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                unsigned int u = __float_as_uint(vv[e]);
+                if (vv[e] > 0.f && (level == 0 || (u >> hsh) == (prefix >> hsh)))
+                    atomicAdd(&hist[(u >> sh) & (nb - 1)], (double)vv[e]);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double run = s_below;
+            int b = 0;
+            for (; b < nb; ++b) {
+                if (run + hist[b] >= target) break;
+                run += hist[b];
+            }
+            if (b == nb) b = nb - 1;       // rounding: target marginally above the total
+            s_below = run;
+            s_prefix = prefix | ((unsigned int)b << sh);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) thr[n] = (pct <= 0.f) ? 0.f : __uint_as_float(s_prefix);
+}
+
+cudaError_t launch_trunc_threshold(const float* P2, const double* sums, float pct, float* thr, int N, size_t per_sample,
+                                   cudaStream_t st) {
+    if (per_sample % 4) return cudaErrorInvalidValue;
+    trunc_threshold_kernel<<<N, 1024, 0, st>>>(P2, sums, pct, thr, per_sample);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ contrastive combine
-// out[n,pix] = sum_c relu(P2[n,pix,c]/S[n] - P2[N+n,pix,c]/S[N+n])     (whitebox.py:524-526)
-__global__ void contrast_kernel(const float* __restrict__ P2, const double* __restrict__ sums, float* __restrict__ out,
-                                int N, int HW, int C4) {
-    // 16 lanes per pixel (C = 64) generalised: C4 lanes per pixel, C4 a power of two <= 32
+// out[n,pix] = sum_c relu(k*P2[n,pix,c]/S[n] - k*P2[N+n,pix,c]/S[N+n]),  k = (P2[n,pix,c] >= thr[n]) or 1    (whitebox.py:524-526, 556)
+__global__ void contrast_kernel(const float* __restrict__ P2, const double* __restrict__ sums, const float* __restrict__ thr,
+                                float* __restrict__ out, int N, int HW, int C4) {
+    // C4 lanes per pixel (C = 64 -> 16 lanes), C4 a power of two <= 32
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)N * HW * C4;
     float s = 0.f;
@@ -461,20 +518,24 @@ __global__ void contrast_kernel(const float* __restrict__ P2, const double* __re
     if (i < total) {
         size_t n = pixg / HW;
         float sm = (float)sums[n], sn = (float)sums[N + n];
+        float t = thr ? thr[n] : -1.f;
         float4 a = reinterpret_cast<const float4*>(P2)[i];
         float4 b = reinterpret_cast<const float4*>(P2)[i + (size_t)N * HW * C4];
-        s = fmaxf(__fsub_rn(__fdiv_rn(a.x, sm), __fdiv_rn(b.x, sn)), 0.f) + fmaxf(__fsub_rn(__fdiv_rn(a.y, sm), __fdiv_rn(b.y, sn)), 0.f) +
-            fmaxf(__fsub_rn(__fdiv_rn(a.z, sm), __fdiv_rn(b.z, sn)), 0.f) + fmaxf(__fsub_rn(__fdiv_rn(a.w, sm), __fdiv_rn(b.w, sn)), 0.f);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (av[e] >= t) s += fmaxf(__fsub_rn(__fdiv_rn(av[e], sm), __fdiv_rn(bv[e], sn)), 0.f);
     }
     for (int o = C4 / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (i < total && (threadIdx.x % C4) == 0) out[pixg] = s;
 }
 
-cudaError_t launch_contrast(const float* P2, const double* sums, float* out, int N, int HW, int C, cudaStream_t st) {
+cudaError_t launch_contrast(const float* P2, const double* sums, const float* thr, float* out, int N, int HW, int C,
+                            cudaStream_t st) {
     int C4 = C / 4;
     if (C4 > 32 || (C4 & (C4 - 1))) return cudaErrorInvalidValue;
     size_t total = (size_t)N * HW * C4;
-    contrast_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P2, sums, out, N, HW, C4);
+    contrast_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P2, sums, thr, out, N, HW, C4);
     return cudaGetLastError();
 }
 

@@ -199,16 +199,20 @@ class StResnetEngine(object):
         return out
 
     def contrastive(self, x_nhwc, W2, k_pos=0, k_neg=1, mode='affineonly_with_prior', hooked_fc2=False,
-                    saliency=True, num_classes=None):
-        """Whitebox.contrastive_ebp over a batch (reference whitebox.py:506-527): one shared
-        forward, mate and non-mate sweeps as one gradient batch of 2N rows."""
+                    saliency=True, num_classes=None, percentile=None):
+        """Whitebox.contrastive_ebp / truncated_contrastive_ebp over a batch (reference whitebox.py:506-558):
+        one shared forward, mate and non-mate sweeps as one gradient batch of 2N rows."""
         N = x_nhwc.shape[0]
         C = num_classes if num_classes is not None else W2.shape[-2]
         self.forward(x_nhwc)
         Pn = self.priors_contrastive(N, C, k_pos, k_neg)
         P2, _, sums = self.ebp_backward(Pn, W2, mode, hooked_fc2)
         mwp = self.buf('cmwp', N, 112, 112)
-        self.be.contrast(P2, sums, N, mwp)
+        thr = None
+        if percentile is not None:      # truncated_contrastive_ebp (reference whitebox.py:529-558)
+            thr = self.buf('thr', N)
+            self.be.trunc_threshold(P2, sums, N, percentile, thr)
+        self.be.contrast(P2, sums, N, mwp, thr)
         if not saliency:
             return mwp
         out = self.buf('sal', N, 112, 112)

@@ -34,7 +34,8 @@ _SIGNATURES = {
     'xfrb_join': [_P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     'xfrb_ds_res': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     'xfrb_stem_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
-    'xfrb_contrast': [_P, _P, _P, _I, _I, _I, _P],
+    'xfrb_contrast': [_P, _P, _P, _P, _I, _I, _I, _P],
+    'xfrb_trunc_threshold': [_P, _P, _F, _P, _I, ctypes.c_longlong, _P],
     'xfrb_saliency_post': [_P, _P, _I, _I, _I, _F, _P],
 }
 EXPORTS = ['xfrb_version', 'xfrb_last_error', 'xfrb_device_ok', 'xfrb_impl_available'] + sorted(_SIGNATURES)
@@ -176,9 +177,13 @@ class CudaBackend(object):
         self._check(self.lib.xfrb_stem_bwd(_ptr(zmain), _ptr(gres), _ptr(o), _ptr(mp), _ptr(bn), _ptr(zc), _ptr(P2),
                                            _ptr(chansum), _ptr(sums), J, o.shape[0], mode, self.eps, self._st()), 2)
 
-    def contrast(self, P2, sums, N, out):
+    def contrast(self, P2, sums, N, out, thr=None):
         HW = P2.shape[1] * P2.shape[2]
-        self._check(self.lib.xfrb_contrast(_ptr(P2), _ptr(sums), _ptr(out), N, HW, P2.shape[3], self._st()))
+        self._check(self.lib.xfrb_contrast(_ptr(P2), _ptr(sums), _ptr(thr), _ptr(out), N, HW, P2.shape[3], self._st()))
+
+    def trunc_threshold(self, P2, sums, N, percentile, thr):
+        per = P2.shape[1] * P2.shape[2] * P2.shape[3]
+        self._check(self.lib.xfrb_trunc_threshold(_ptr(P2), _ptr(sums), float(percentile), _ptr(thr), N, per, self._st()))
 
     def saliency_post(self, mwp, out):
         B, H, W = mwp.shape

@@ -13,10 +13,10 @@ Additions (not in the reference, which is batch-1 only): `Whitebox.ebp_batch`,
 
 Status of the reference surface in this round:
   done   encode / classify / set_triplet_classifier / num_classes / preprocess / clear,
-         ebp, contrastive_ebp (all four ebp_subtree_mode values, ebp_version 6 post-processing),
-         embeddings, ebp_subtree_mode
-  next   truncated_contrastive_ebp, layerwise_ebp, layerwise_contrastive_ebp, weighted_subtree_ebp,
-         the hooked (non-triplet) fc2 head, ebp_version != 6 uint8 post-processing, with_bias
+         ebp, contrastive_ebp, truncated_contrastive_ebp (all four ebp_subtree_mode values, ebp_version 6 post-processing),
+         embeddings, ebp_subtree_mode, with_bias / ebp_version 11, ebp_version != 6 (uint8 + PIL blur on the host)
+  next   layerwise_ebp, layerwise_contrastive_ebp, weighted_subtree_ebp,
+         the hooked (non-triplet) fc2 head
 """
 import numpy as np
 import torch
@@ -183,11 +183,20 @@ class Whitebox(nn.Module):
     def _engine(self):
         if self.eps != 1E-16 and abs(self.eps - self.net.engine().be.eps) > 0:
             self.net.engine().be.eps = float(self.eps)
-        if self._ebp_with_bias:
-            raise NotImplementedError('xfr_b200: with_bias / ebp_version 11 is not on the CUDA path yet')
-        if self.convert_saliency_uint8:
-            raise NotImplementedError('xfr_b200: ebp_version != 6 (uint8 + PIL blur post-processing) is not on the CUDA path yet')
         return self.net.engine(self._ebp_with_bias)
+
+    def _float32_to_uint8(self, img):
+        """whitebox.py:439-441"""
+        return np.uint8(255 * ((img - np.min(img)) / (self.eps + (np.max(img) - np.min(img)))))
+
+    def _mwp_to_saliency_uint8(self, P, blur_radius=2):
+        """ebp_version != 6 branch of _mwp_to_saliency (whitebox.py:451-454): 8-bit quantise, PIL GaussianBlur,
+        re-quantise.  PIL's filter is the reference's own dependency; it runs on the host on a 112x112 uint8 image."""
+        import PIL.Image
+        import PIL.ImageFilter
+        img = self._float32_to_uint8(P)
+        img = np.array(PIL.Image.fromarray(img).filter(PIL.ImageFilter.GaussianBlur(radius=blur_radius)))
+        return self._float32_to_uint8(img)
 
     # ---------------------------------------------------------------- batched entry points
     def ebp_batch(self, x, Pn, mwp=False):
@@ -201,11 +210,14 @@ class Whitebox(nn.Module):
             Pn = Pn.expand(N, -1)
         for i in range(0, N, _CHUNK):
             m = eng.ebp(self.net._nhwc(x[i:i + _CHUNK]), Pn[i:i + _CHUNK].contiguous(), W2[i:i + _CHUNK].contiguous(),
-                        self._ebp_subtree_mode, saliency=not mwp)
+                        self._ebp_subtree_mode, saliency=not (mwp or self.convert_saliency_uint8))
             outs.append(m.cpu())
-        return torch.cat(outs).numpy()
+        maps = torch.cat(outs).numpy()
+        if self.convert_saliency_uint8 and not mwp:
+            maps = np.stack([self._mwp_to_saliency_uint8(m) for m in maps])
+        return maps
 
-    def contrastive_ebp_batch(self, x, k_poschannel=0, k_negchannel=1, out=None):
+    def contrastive_ebp_batch(self, x, k_poschannel=0, k_negchannel=1, out=None, percentile=None):
         """N probes, each against its own (mate, non-mate) rows -> float32 [N,112,112] (numpy, or `out` pinned tensor)."""
         eng = self._engine()
         N = x.shape[0]
@@ -213,9 +225,11 @@ class Whitebox(nn.Module):
         res = out if out is not None else torch.empty(N, 112, 112)
         for i in range(0, N, _CHUNK):
             m = eng.contrastive(self.net._nhwc(x[i:i + _CHUNK]), W2[i:i + _CHUNK].contiguous(), k_poschannel, k_negchannel,
-                                self._ebp_subtree_mode)
+                                self._ebp_subtree_mode, percentile=percentile, saliency=not self.convert_saliency_uint8)
             res[i:i + m.shape[0]].copy_(m, non_blocking=True)
         torch.cuda.current_stream(W2.device).synchronize()
+        if self.convert_saliency_uint8:
+            return np.stack([self._mwp_to_saliency_uint8(m) for m in res.numpy()])
         return res if out is not None else res.numpy()
 
     # ---------------------------------------------------------------- reference API (batch 1)
@@ -230,7 +244,10 @@ class Whitebox(nn.Module):
         return self.contrastive_ebp_batch(img_probe, k_poschannel, k_negchannel)[0]
 
     def truncated_contrastive_ebp(self, img_probe, k_poschannel, k_negchannel, percentile=20):
-        raise NotImplementedError('xfr_b200: truncated_contrastive_ebp is scheduled next (DESIGN.md)')
+        """whitebox.py:529-558"""
+        assert(k_poschannel >= 0 and k_poschannel < self.net.num_classes())
+        assert(k_negchannel >= 0 and k_negchannel < self.net.num_classes())
+        return self.contrastive_ebp_batch(img_probe, k_poschannel, k_negchannel, percentile=percentile)[0]
 
     def layerwise_ebp(self, img_probe, k_layer, mode='argmax', k_element=None, k_poschannel=0, mwp=True):
         raise NotImplementedError('xfr_b200: layerwise_ebp is scheduled next (DESIGN.md)')
