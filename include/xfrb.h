@@ -19,6 +19,9 @@
  *    2 = affineonly   (reference whitebox.py:397-430, no prior set);
  *  - `impl`: 0 = fp32 CUDA-core implicit GEMM, 1 = tcgen05 3xTF32 (fp32-equivalent),
  *    2 = tcgen05 single-pass TF32;
+ *  - weight operands (`Bf`, `Bd`, `B1`, `W1pT`) are K-major [rows][K] fp32.  For impl 1 they hold TWO planes
+ *    [2][rows][K]: hi = rna_tf32(W) and lo = W - hi (the host does the 3xTF32 split of the static operand once,
+ *    xfr_b200/packing.py); for impl 2 one plane of rna_tf32(W); for impl 0 one plane of W;
  *  - `bn` is [4][C]: alpha, beta (eval BatchNorm y = x*alpha+beta), sp = relu(gamma)/sigma,
  *    tp = beta' - mu*sp (the gamma+ forward of the 'positive_activation' pass).
  */

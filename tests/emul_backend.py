@@ -53,11 +53,17 @@ def im2col_nhwc(x, R, S, pad):
     return torch.stack(cols, dim=3).reshape(N * H * W, R * S * C)
 
 
+def _w(B):
+    """Weight operand -> plain matrix: the 3xTF32 pack is two planes (hi, lo) with hi + lo == W exactly."""
+    return B.sum(0) if B.dim() == 3 else B
+
+
 class EmulBackend(object):
     name = 'emul'
 
-    def __init__(self, eps=EPS):
+    def __init__(self, eps=EPS, impl_name='fp32'):
         self.eps = eps
+        self.impl_name = impl_name      # which weight packing the engine should build (the arithmetic here is fp32)
 
     # ------------------------------------------------------------ forward
     def stem_fwd(self, x, stem, o, mp):
@@ -77,7 +83,7 @@ class EmulBackend(object):
     def conv_dual(self, inp, L, o, xr, act, res=None):
         """o = conv(inp)+b ; xr = relu(conv_{W+}(inp)+b') ; act = relu(o*alpha+beta [+ res, zero-padded channels])."""
         A = im2col_nhwc(inp, L.R, L.S, L.R // 2)
-        D = A @ L.Bf.t() + L.bias
+        D = A @ _w(L.Bf).t() + L.bias
         t, p = unpack_dual_cols(D, L.tn)
         o.view(-1, L.cout).copy_(t)
         xr.view(-1, L.cout).copy_(relu(p))
@@ -90,7 +96,7 @@ class EmulBackend(object):
     def head_fwd(self, u, head, v, f1, f1p, xn, nrm):
         """v = avgpool7(u); (f1 | f1p) = one dual GEMM v @ [W1 ; relu(W1)]^T + (b | b'); xn = f1/|f1|."""
         vv = F.avg_pool2d(u.permute(0, 3, 1, 2), 7, 7).flatten(1)
-        ff, fp = unpack_dual_cols(vv @ head.B1.t() + head.bias1, head.tn)
+        ff, fp = unpack_dual_cols(vv @ _w(head.B1).t() + head.bias1, head.tn)
         nn_ = ff.norm(dim=1).clamp_min(1e-12)
         v.copy_(vv)
         f1.copy_(ff)
@@ -114,7 +120,7 @@ class EmulBackend(object):
         Xmul = relu(F.normalize(_rows(f1p, J), p=2, dim=1))
         gr = hook(False, relu(xn_), Xmul, gr, mode, self.eps)
         gr = (gr - xn_ * (xn_ * gr).sum(1, keepdim=True)) / nrm_.unsqueeze(1)
-        gr = gr @ head.W1pT.t()
+        gr = gr @ _w(head.W1pT).t()
         gr = hook(True, relu(v_), relu(v_), gr, mode, self.eps)     # X = relu(avgpool(relu(u))) = v since u >= 0
         g_out.copy_((gr / 49.0).view(J, 1, 1, -1).expand(-1, 7, 7, -1))
 
@@ -130,7 +136,7 @@ class EmulBackend(object):
 
     def _dgrad(self, y, Bd, R):
         """y [J,H,W,Cout] -> [J*H*W, Cin]"""
-        return im2col_nhwc(y, R, R, R // 2) @ Bd.t()
+        return im2col_nhwc(y, R, R, R // 2) @ _w(Bd).t()
 
     def dgrad_mid(self, y, L, o, xr, bn, mode, y_out):
         """z = W+^T y (conv L), then the hook chain at the activation a = relu(bn(o)) that fed conv L."""

@@ -25,7 +25,7 @@ def test_each_kernel_against_emulation(impl, mode):
         cuda_be = CudaBackend(dev, impl=impl)
     except NotImplementedError:
         pytest.skip('impl %s not built' % impl)
-    eng_cpu = StResnetEngine(sd, EmulBackend(), L1111)
+    eng_cpu = StResnetEngine(sd, EmulBackend(impl_name=impl), L1111)
     eng = StResnetEngine(sd, cuda_be, L1111, device=dev)
     sh = ShadowBackend(cuda_be, EmulBackend(), pack_map(eng, eng_cpu))
     eng.be = sh
@@ -47,7 +47,8 @@ def _conv_case(be, J, H, C_in, C_out, R, seed=0):
 
     class L(object):
         pass
-    L.Bd, L.cin, L.R = Bd.cuda(), C_in, R
+    from xfr_b200.packing import gemm_planes
+    L.Bd, L.cin, L.R = gemm_planes(Bd, be.impl_name).cuda(), C_in, R
     out = torch.full((J, H, H, C_in), float('nan'), device='cuda')
     be.dgrad_plain(y.cuda(), L, out)
     torch.cuda.synchronize()

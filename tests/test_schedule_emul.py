@@ -13,8 +13,8 @@ from xfr_b200.engine import StResnetEngine
 MODES = (('affineonly_with_prior', 'awp'), ('all', 'all'), ('affineonly', 'affineonly'), ('norelu', 'norelu'))
 
 
-def _engine(layers):
-    return StResnetEngine(synth.stresnet_state_dict(0, layers, 2), EmulBackend(), layers)
+def _engine(layers, impl='fp32'):
+    return StResnetEngine(synth.stresnet_state_dict(0, layers, 2), EmulBackend(impl_name=impl), layers)
 
 
 def test_pack_roundtrip():
@@ -35,10 +35,20 @@ def test_pack_roundtrip():
     assert torch.allclose(got.view(1, 5, 5, 64).permute(0, 3, 1, 2), want, atol=1e-4)
 
 
+def test_split_planes_are_exact():
+    g = torch.Generator().manual_seed(9)
+    B = torch.randn(64, 96, generator=g) * torch.logspace(-6, 3, 96)
+    P = packing.gemm_planes(B, 'tf32x3')
+    assert torch.equal(P[0] + P[1], B)                                   # hi + lo reproduces W bit for bit
+    assert torch.equal(P[0].view(torch.int32) & 0x1FFF, torch.zeros(64, 96, dtype=torch.int32))   # hi is a TF32 number
+    assert float((P[1].abs() / B.abs()).max()) <= 2.0 ** -11 + 1e-9      # |lo| <= half a TF32 ulp
+
+
 @pytest.mark.parametrize('mode,tag', MODES)
-def test_small_net(mode, tag):
+@pytest.mark.parametrize('impl', ['fp32', 'tf32x3'])
+def test_small_net(mode, tag, impl):
     G = golden(L1111)
-    eng = _engine(L1111)
+    eng = _engine(L1111, impl)
     x, W2, imgs = golden_inputs(G)
     xn = eng.forward(imgs.permute(0, 2, 3, 1).contiguous())
     assert rel_err(50 * xn[1:2].numpy(), G['enc_mate']) < 1e-5

@@ -37,9 +37,10 @@ static int finish(const char* what, cudaError_t e) {
     return 0;
 }
 
-static cudaError_t run_gemm(const float* A, const float* B, const ConvGeom& g, const EpiParams& ep, int impl, cudaStream_t st) {
+static cudaError_t run_gemm(const float* A, const float* B, const ConvGeom& g, const EpiParams& ep, int impl, cudaStream_t st,
+                            int tn = 0) {
     if (impl == XFRB_IMPL_FP32) return launch_conv_simt(A, B, g, ep, st);
-    if (impl == XFRB_IMPL_TF32X3 || impl == XFRB_IMPL_TF32) return launch_conv_tc(A, B, g, ep, impl == XFRB_IMPL_TF32X3, st);
+    if (impl == XFRB_IMPL_TF32X3 || impl == XFRB_IMPL_TF32) return launch_conv_tc(A, B, g, ep, impl == XFRB_IMPL_TF32X3, tn, st);
     return cudaErrorInvalidValue;
 }
 
@@ -82,7 +83,9 @@ int xfrb_avgpool2(const float* u, float* out, int N, int H, int W, int C, void* 
 int xfrb_conv_dual(const float* inp, const float* Bf, const float* bias, const float* bn, const float* res, int res_c,
                    float* o, float* xr, float* act, int N, int H, int W, int Cin, int Cout, int R, int tn, int impl,
                    void* stream) {
-    if ((R != 1 && R != 3) || tn != 128 || Cout % 64 || (res && res_c % 4)) return finish("xfrb_conv_dual", cudaErrorInvalidValue);
+    if ((R != 1 && R != 3) || (tn != 128 && tn != 256) || (impl == XFRB_IMPL_FP32 && tn != 128) || (2 * Cout) % tn ||
+        (res && res_c % 4))
+        return finish("xfrb_conv_dual", cudaErrorInvalidValue);
     ConvGeom g{H, W, Cin, R, R * R * Cin, 2 * Cout};
     EpiParams ep;
     memset(&ep, 0, sizeof(ep));
@@ -91,7 +94,7 @@ int xfrb_conv_dual(const float* inp, const float* Bf, const float* bias, const f
     ep.C = Cout;
     ep.bias = bias; ep.bn = bn; ep.res = res; ep.res_c = res_c;
     ep.out0 = o; ep.out1 = xr; ep.out2 = act;
-    return finish("xfrb_conv_dual", run_gemm(inp, Bf, g, ep, impl, (cudaStream_t)stream));
+    return finish("xfrb_conv_dual", run_gemm(inp, Bf, g, ep, impl, (cudaStream_t)stream, tn));
 }
 
 int xfrb_head_fwd(const float* u, const float* B1, const float* bias1, int tn, float* scratch, float* v, float* f1, float* f1p,
@@ -107,7 +110,7 @@ int xfrb_head_fwd(const float* u, const float* B1, const float* bias1, int tn, f
     ep.C = 1024;
     ep.bias = bias1;
     ep.out0 = scratch;
-    e = run_gemm(v, B1, g, ep, impl, st);
+    e = run_gemm(v, B1, g, ep, impl, st, tn);
     if (e != cudaSuccess) return finish("xfrb_head_fwd/fc1", e);
     return finish("xfrb_head_fwd/norm", launch_head_norm(scratch, tn, f1, f1p, xn, nrm, N, st));
 }

@@ -168,7 +168,8 @@ struct JoinArgs {
 
 cudaError_t launch_conv_simt(const float* A, const float* B, const ConvGeom& g, const EpiParams& ep, cudaStream_t st);
 bool conv_tc_available();
-cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& g, const EpiParams& ep, int split3,
+// B: [planes][Nn][K] with the 3xTF32 (hi, lo) planes when split3; tn: dual-pack tile width (FWD_DUAL) or a cap on BN
+cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& g, const EpiParams& ep, int split3, int tn,
                            cudaStream_t st);
 
 }  // namespace xfrb

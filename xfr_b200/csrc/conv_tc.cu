@@ -10,8 +10,9 @@
 //   warp 1      MMA issuer     - one lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) with the
 //                                accumulator in TMEM (two accumulator stages so the epilogue of tile i overlaps the
 //                                main loop of tile i+1); tcgen05.commit releases smem stages / publishes accumulators
-//   warps 2-5   operand split  - (3xTF32 only) rewrite each landed stage as hi = rna_tf32(x) in place and lo = x - hi in
-//                                a twin buffer; the issuer then runs hi*hi + lo*hi + hi*lo into the same accumulator
+//   warps 2-5   operand split  - (3xTF32 only) rewrite the landed activation tile as hi = rna_tf32(x) in place and
+//                                lo = x - hi in a twin buffer (weights arrive pre-split from the host as two planes);
+//                                the issuer then runs hi*hi + lo*hi + hi*lo into the same accumulator
 //   warps 6-13  epilogue       - tcgen05.ld the accumulator (lane = pixel row), apply the fused EBP epilogue of
 //                                common.cuh against the saved tensors, store NHWC fp32 with 128-bit accesses
 #include "common.cuh"
@@ -31,6 +32,7 @@ struct TcGeom {
     int R, Cin, kchunks, num_k;
     int H, W, bh, bimg, tiles_per_img, Nimg;
     int n_m_tiles, n_n_tiles;
+    int b_rows;         // rows of one plane of B (the lo plane of the 3xTF32 split starts at row b_rows)
     uint32_t a_bytes;   // bytes one A load deposits (box volume * 4)
 };
 
@@ -118,7 +120,7 @@ template <int BN, bool SPLIT3>
 struct TcCfg {
     static constexpr uint32_t B_TILE_BYTES = BN * TC_BK * 4;
     static constexpr uint32_t STAGE_BYTES = (A_TILE_BYTES + B_TILE_BYTES) * (SPLIT3 ? 2 : 1);
-    static constexpr int STAGES = SPLIT3 ? (BN == 128 ? 3 : 4) : (BN == 128 ? 6 : 8);
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;   // 3xTF32: 2 / 3 / 4 for BN = 256 / 128 / 64; TF32: 4 / 6 / 8
     static constexpr uint32_t TMEM_COLS = 2 * BN;          // two accumulator stages (128 or 256: powers of two)
     static constexpr uint32_t PRM_BYTES = 2 * 6 * BN * 4;   // per accumulator stage: bn[4][BN] + bias_t[BN] + bias_p[BN]
     static constexpr uint32_t TR_BYTES = TC_EPI_WARPS * 2048;   // per epilogue warp: 32 rows x 16 columns transpose slab
@@ -145,9 +147,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float4* tr_s = reinterpret_cast<float4*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 256 + Cfg::PRM_BYTES);
 
     auto a_hi = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
-    auto b_hi = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + A_TILE_BYTES; };
-    auto a_lo = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + A_TILE_BYTES + Cfg::B_TILE_BYTES; };
-    auto b_lo = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES; };
+    auto a_lo = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + A_TILE_BYTES; };                       // split only
+    auto b_hi = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + (SPLIT3 ? 2 : 1) * A_TILE_BYTES; };
+    auto b_lo = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES; };   // split only
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = g.n_m_tiles * g.n_n_tiles;
@@ -207,7 +209,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tile_coords(tile, m0, mvalid, n_img0, h0, ncol0);
                 for (int kb = 0; kb < g.num_k; ++kb) {
                     mbar_wait(empty_bar(s), ph ^ 1u);
-                    mbar_expect_tx(full_bar(s), g.a_bytes + Cfg::B_TILE_BYTES);
+                    mbar_expect_tx(full_bar(s), g.a_bytes + (SPLIT3 ? 2 : 1) * Cfg::B_TILE_BYTES);
                     int tap = kb / g.kchunks;
                     int c0 = (kb - tap * g.kchunks) * TC_BK;
                     if (g.a4d) {
@@ -217,6 +219,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tma_load_2d(a_hi(s), &tmA, c0, m0, full_bar(s));
                     }
                     tma_load_2d(b_hi(s), &tmB, kb * TC_BK, ncol0, full_bar(s));
+                    if (SPLIT3) tma_load_2d(b_lo(s), &tmB, kb * TC_BK, g.b_rows + ncol0, full_bar(s));   // host-split lo plane
                     if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
             }
@@ -269,10 +272,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 for (int kb = 0; kb < g.num_k; ++kb) {
                     mbar_wait(full_bar(s), ph);
-                    // A and B tiles are contiguous: [A_hi | B_hi] -> twins [A_lo | B_lo] at +A+B bytes
+                    // only the activation tile is split here; the weight tile arrives as (hi, lo) planes split on the host
                     float4* hi = reinterpret_cast<float4*>(smem_gen + s * Cfg::STAGE_BYTES);
-                    float4* lo = reinterpret_cast<float4*>(smem_gen + s * Cfg::STAGE_BYTES + A_TILE_BYTES + Cfg::B_TILE_BYTES);
-                    constexpr int NV = (A_TILE_BYTES + Cfg::B_TILE_BYTES) / 16;
+                    float4* lo = reinterpret_cast<float4*>(smem_gen + s * Cfg::STAGE_BYTES + A_TILE_BYTES);
+                    constexpr int NV = A_TILE_BYTES / 16;
 #pragma unroll 4
                     for (int i = t; i < NV; i += 128) {
                         float4 v = hi[i];
@@ -517,13 +520,15 @@ static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, co
     return cudaGetLastError();
 }
 
-cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, const EpiParams& ep, int split3, cudaStream_t st) {
+cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, const EpiParams& ep, int split3, int tn,
+                           cudaStream_t st) {
     if (cg.Cin % TC_BK != 0) return cudaErrorInvalidValue;
     int BN;
     if (ep.kind == EPI_FWD_DUAL) {
-        if (cg.Nn % 128) return cudaErrorInvalidValue;
-        BN = 128;
-    } else if (cg.Nn % 128 == 0) BN = 128;
+        BN = tn;                                  // the dual pack fixes the tile width
+        if ((BN != 128 && BN != 256) || cg.Nn % BN) return cudaErrorInvalidValue;
+    } else if (cg.Nn % 256 == 0 && tn != 128) BN = 256;
+    else if (cg.Nn % 128 == 0) BN = 128;
     else if (cg.Nn % 64 == 0) BN = 64;
     else return cudaErrorInvalidValue;
 
@@ -535,6 +540,7 @@ cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, c
     g.H = cg.H;
     g.W = cg.W;
     g.n_n_tiles = cg.Nn / BN;
+    g.b_rows = cg.Nn;
     const int HW = cg.H * cg.W;
     g.Nimg = ep.M / HW;
     CUtensorMap tmA, tmB;
@@ -572,7 +578,8 @@ cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, c
         if (!encode(&tmA, A, 4, dims, strides, box)) return cudaErrorInvalidValue;
     }
     {
-        cuuint64_t dims[2] = {(cuuint64_t)cg.K, (cuuint64_t)cg.Nn};
+        // B is [planes][Nn][K]: plane 0 = rna_tf32(W) (or W itself for single-pass TF32), plane 1 = W - plane 0
+        cuuint64_t dims[2] = {(cuuint64_t)cg.K, (cuuint64_t)cg.Nn * (split3 ? 2 : 1)};
         cuuint64_t strides[1] = {(cuuint64_t)cg.K * 4};
         cuuint32_t box[2] = {TC_BK, (cuuint32_t)BN};
         if (!encode(&tmB, B, 2, dims, strides, box)) return cudaErrorInvalidValue;
@@ -585,7 +592,9 @@ cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, c
         case EPI_JOIN: return launch_cfg<BN_, SP_, EPI_JOIN>(tmA, tmB, g, ep, st);                        \
         default: return cudaErrorInvalidValue;                                                           \
     }
-    if (BN == 128) {
+    if (BN == 256) {
+        if (split3) { XFRB_TC_DISPATCH(256, true) } else { XFRB_TC_DISPATCH(256, false) }
+    } else if (BN == 128) {
         if (split3) { XFRB_TC_DISPATCH(128, true) } else { XFRB_TC_DISPATCH(128, false) }
     } else {
         if (split3) { XFRB_TC_DISPATCH(64, true) } else { XFRB_TC_DISPATCH(64, false) }

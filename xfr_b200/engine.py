@@ -36,8 +36,7 @@ class _Block(object):
 class StResnetEngine(object):
     """Batched whitebox engine for the STR ResNet topology [3,4,23,3] (or any `layers`)."""
 
-    def __init__(self, state_dict, backend, layers=STRESNET101, device='cpu', with_bias=False, tn=128,
-                 eps=1e-16):
+    def __init__(self, state_dict, backend, layers=STRESNET101, device='cpu', with_bias=False, eps=1e-16):
         self.be = backend
         self.layers = tuple(layers)
         self.device = torch.device(device)
@@ -45,7 +44,8 @@ class StResnetEngine(object):
         self.eps = eps
         sd = {k: v.detach().cpu() for k, v in state_dict.items()}
         self.stem = packing.Stem(sd, with_bias=with_bias).to(self.device)
-        self.head = packing.Head(sd, tn, with_bias=with_bias).to(self.device)
+        impl = getattr(backend, 'impl_name', 'fp32')     # decides the weight planes / tile widths of the packs
+        self.head = packing.Head(sd, impl, with_bias=with_bias).to(self.device)
         self.blocks = []
         inplanes, hw = 64, 56
         for li, (planes, n) in enumerate(zip((64, 128, 256, 512), self.layers), start=1):
@@ -58,9 +58,9 @@ class StResnetEngine(object):
                 b.hw_in = hw
                 hw = hw // b.stride
                 b.hw = hw
-                b.c1 = packing.ConvBN(sd, b.name + '.conv1', b.name + '.bn1', tn, with_bias).to(self.device)
-                b.c2 = packing.ConvBN(sd, b.name + '.conv2', b.name + '.bn2', tn, with_bias).to(self.device)
-                b.c3 = packing.ConvBN(sd, b.name + '.conv3', b.name + '.bn3', tn, with_bias).to(self.device)
+                b.c1 = packing.ConvBN(sd, b.name + '.conv1', b.name + '.bn1', impl, with_bias).to(self.device)
+                b.c2 = packing.ConvBN(sd, b.name + '.conv2', b.name + '.bn2', impl, with_bias).to(self.device)
+                b.c3 = packing.ConvBN(sd, b.name + '.conv3', b.name + '.bn3', impl, with_bias).to(self.device)
                 self.blocks.append(b)
                 inplanes = planes * 4
         self._ws = {}

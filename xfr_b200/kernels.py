@@ -83,6 +83,7 @@ class CudaBackend(object):
                 raise RuntimeError('xfr_b200: kernels are built for sm_100a only; device is %s'
                                    % torch.cuda.get_device_name(self.device))
         self.impl = IMPLS[impl] if isinstance(impl, str) else int(impl)
+        self.impl_name = {v: k for k, v in IMPLS.items()}[self.impl]
         if not self.lib.xfrb_impl_available(self.impl):
             raise NotImplementedError('xfr_b200: GEMM implementation %r is not compiled into %s' % (impl, LIB_PATH))
         self.eps = float(eps)

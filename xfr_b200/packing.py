@@ -21,6 +21,31 @@ import torch
 BN_EPS = 1e-5
 
 
+def rna_tf32(t):
+    """cvt.rna.tf32.f32 on the host: round to nearest (ties away from zero) to a 10-bit mantissa."""
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def gemm_planes(B, impl):
+    """Weight operand as the GEMM implementation wants it (include/xfrb.h):
+    'fp32' -> B ; 'tf32' -> rna_tf32(B) ; 'tf32x3' -> [2, rows, K] = (hi, lo) with hi + lo == B exactly."""
+    B = B.float().contiguous()
+    if impl == 'fp32':
+        return B
+    hi = rna_tf32(B)
+    if impl == 'tf32':
+        return hi.contiguous()
+    if impl == 'tf32x3':
+        return torch.stack((hi, B - hi)).contiguous()
+    raise ValueError(impl)
+
+
+def dual_tile_width(cout, impl):
+    """Tile width of the forward dual pack: the tcgen05 kernel runs N = 256 tiles when the layer is wide enough."""
+    return 256 if (impl != 'fp32' and cout % 128 == 0) else 128
+
+
 def fold_bn(sd, name, with_bias=False):
     """Eval-mode BatchNorm as y = x*alpha + beta (what torch's CPU kernel computes),
     plus the positive-pass / backward constants of excitation backprop:
@@ -76,21 +101,23 @@ def unpack_dual_cols(D, tn):
 class ConvBN(object):
     """One conv + its BatchNorm, packed.  Tensors move with .to(device)."""
 
-    def __init__(self, sd, conv, bn, tn, with_bias=False):
+    def __init__(self, sd, conv, bn, impl='fp32', with_bias=False):
         w = sd[conv + '.weight']
         b = sd.get(conv + '.bias')
         self.name = conv
+        self.impl = impl
         self.cout, self.cin, self.R, self.S = w.shape
-        self.tn = tn
-        self.Bf, self.bias = pack_dual_fwd(w, b, tn, with_bias)
-        self.Bd = pack_dgrad(w, positive=True)
+        self.tn = dual_tile_width(self.cout, impl)
+        Bf, self.bias = pack_dual_fwd(w, b, self.tn, with_bias)
+        self.Bf = gemm_planes(Bf, impl)
+        self.Bd = gemm_planes(pack_dgrad(w, positive=True), impl)
         self.Bd_signed = None       # true-gradient passes (weighted subtree) pack this lazily
         self.bn = fold_bn(sd, bn, with_bias)
         self._w = w                 # kept for lazy packs only
 
     def signed_dgrad(self):
         if self.Bd_signed is None:
-            self.Bd_signed = pack_dgrad(self._w, positive=False).to(self.Bd.device)
+            self.Bd_signed = gemm_planes(pack_dgrad(self._w, positive=False), self.impl).to(self.Bd.device)
         return self.Bd_signed
 
     def to(self, device):
@@ -125,14 +152,15 @@ class Stem(object):
 class Head(object):
     """avgpool7 -> fc1 -> L2 normalise -> x50 -> fc2 (reference resnet.py:235-258)."""
 
-    def __init__(self, sd, tn=128, with_bias=False):
-        self.tn = tn
+    def __init__(self, sd, impl='fp32', with_bias=False):
+        self.tn = tn = 128
         self.W1 = sd['fc1.weight'].float().contiguous()              # [512, 2048]
         self.b1 = sd['fc1.bias'].float().contiguous()
         self.W1p = torch.clamp_min(self.W1, 0).contiguous()
         self.b1p = (torch.clamp_min(self.b1, 0) if with_bias else self.b1).contiguous()
-        self.W1pT = self.W1p.t().contiguous()                        # [2048, 512]: B operand of the fc1 dgrad
-        self.B1, self.bias1 = pack_dual_fwd(self.W1.view(512, -1, 1, 1), self.b1, tn, with_bias)
+        self.W1pT = gemm_planes(self.W1p.t(), impl)                  # [2048, 512]: B operand of the fc1 dgrad
+        B1, self.bias1 = pack_dual_fwd(self.W1.view(512, -1, 1, 1), self.b1, tn, with_bias)
+        self.B1 = gemm_planes(B1, impl)
         self.W2 = sd['fc2.weight'].float().contiguous() if 'fc2.weight' in sd else None
         self.scale = 50.0
 
