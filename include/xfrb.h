@@ -50,9 +50,10 @@ int xfrb_impl_available(int impl);
 /* ---- forward ("activation" + "positive_activation" passes, whitebox.py:490-493) ---- */
 
 /* STR ResNet stem: o = conv7x7/2(x)+b  [N,112,112,64];  mp = maxpool3x3/2(relu(bn(o))) [N,56,56,64]
- * (reference resnet.py:225-228).  W is [147][64] ((r,s,ci) major), x is [N,224,224,3]. */
+ * (reference resnet.py:225-228).  W is [147][64] ((r,s,ci) major), x is [N,224,224,3].  pool_pad = 1 (STR net) or 0
+ * (VGGFace2 ResNet-50: MaxPool2d(3,2,0,ceil_mode=True), resnet50_128.py:16; windows clipped at the border). */
 int xfrb_stem_fwd(const float* x, const float* W, const float* b, const float* bn,
-                  float* o, float* mp, int N, void* stream);
+                  float* o, float* mp, int N, int pool_pad, void* stream);
 
 /* u[N,H,W,C] -> out[N,H/2,W/2,C]: even pixels (input of a stride-2 1x1 conv, resnet.py:116) */
 int xfrb_subsample2(const float* u, float* out, int N, int H, int W, int C, void* stream);
@@ -63,10 +64,11 @@ int xfrb_avgpool2(const float* u, float* out, int N, int H, int W, int C, void* 
  *   o   = conv_W(inp) + b                     [N,H,W,Cout]   (true pre-BN output)
  *   xr  = relu(conv_relu(W)(inp) + b')        [N,H,W,Cout]   (X of the BatchNorm hook)
  *   act = relu(o*alpha + beta + res)          [N,H,W,Cout]   (res: [N,H,W,res_c], zero beyond res_c; may be NULL)
- * Bf/bias: dual pack of xfr_b200/packing.py (tile width tn).  R = 1 or 3, stride 1, pad R/2. */
+ * Bf/bias: dual pack of xfr_b200/packing.py (tile width tn).  R = 1 or 3, stride 1, pad R/2.
+ * relu_act = 0 emits act = o*alpha + beta + res without the ReLU (conv + BN projection shortcut, resnet50_128.py:185-187). */
 int xfrb_conv_dual(const float* inp, const float* Bf, const float* bias, const float* bn,
                    const float* res, int res_c, float* o, float* xr, float* act,
-                   int N, int H, int W, int Cin, int Cout, int R, int tn, int impl, void* stream);
+                   int N, int H, int W, int Cin, int Cout, int R, int tn, int relu_act, int impl, void* stream);
 
 /* avgpool7 -> fc1 (+ the W+ twin) -> L2 normalise (resnet.py:235-252).
  * B1 = dual pack of fc1 [1024][2048], bias1 [1024] (tile width tn); scratch [N,1024].
@@ -91,12 +93,14 @@ int xfrb_dgrad_mid(const float* y, const float* Bd, const float* o, const float*
                    float* y_out, int J, int N, int H, int W, int Cin, int Cout, int R,
                    int mode, float eps, int impl, void* stream);
 
-/* z_out = B^T y only (downsample blocks' conv1; true-gradient passes of weighted_subtree_ebp). */
+/* z_out (+)= B^T y only (downsample / projection blocks; true-gradient passes of weighted_subtree_ebp).
+ * accumulate = 1 adds onto z_out (the second of the two dgrads that meet at a projection block's input). */
 int xfrb_dgrad_plain(const float* y, const float* Bd, float* z_out,
-                     int J, int H, int W, int Cin, int Cout, int R, int impl, void* stream);
+                     int J, int H, int W, int Cin, int Cout, int R, int accumulate, int impl, void* stream);
 
 /* Identity-block boundary: z = relu(W1)^T y1 + g_res, hooks chained on the previous block's
- * output `out` (ReLU; Conv2d; then `hooks`: 1 none, 2 Add(non-affine), 3 AvgPool2d(affine)),
+ * output `out` (ReLU; Conv2d; then `hooks & 3`: 1 none, 2 Add(non-affine), 3 a second affine hook; `hooks & 4`: the
+ * residual sum is torch.add, not a module - no Add hook, other X for the block ReLU: VGGFace2 ResNet-50),
  * ReLU backward -> g_out; then Add slot-0 hook (residual's (A,X): the late-binding closure of
  * whitebox.py:379-432), BatchNorm backward, BatchNorm hook -> y3_out.  All [.,H,W,C], C = Cin. */
 int xfrb_dgrad_join(const float* y1, const float* Bd, const float* g_res,
@@ -124,7 +128,23 @@ int xfrb_ds_res(const float* g, const float* ap, float* gres_lo,
  * zc is scratch [J,56,56,64]. */
 int xfrb_stem_bwd(const float* zmain, const float* gres, const float* o, const float* mp, const float* bn,
                   float* zc, float* P2, float* chansum, double* sums,
-                  int J, int N, int mode, float eps, void* stream);
+                  int J, int N, int mode, float eps, int pool_pad, void* stream);
+
+/* ---- VGGFace2 ResNet-50-128d pieces (reference models/resnet50_128_pytorch/resnet50_128.py, whitebox.py:210-258) ---- */
+
+/* kind 0: y = BatchNorm hook after BatchNorm backward with gamma+, relu(o)*relu(g*sp)/(xr+eps)  (projection shortcut);
+ * kind 1: y = relu(o)*sp + tp, the positive-pass BatchNorm output (X of the shortcut operand, mode 'all').
+ * g, y [J,HW,C] (kind 1: [N,HW,C]); o, xr [N,HW,C]. */
+int xfrb_bn_hook(const float* g, const float* o, const float* xr, const float* bn, float* y,
+                 int J, int N, int HW, int C, int kind, int mode, float eps, void* stream);
+
+/* v = avgpool7(u) [N,C]; enc = v @ Wfe^T [N,D]  (pool5_7x7_s1 + feat_extract, resnet50_128.py:345-347) */
+int xfrb_head_fwd_linear(const float* u, const float* Bfe, float* v, float* enc, int N, int C, int D, int impl, void* stream);
+
+/* seed = Pn @ W2 (un-hooked fc1 of the wrapper, whitebox.py:216-230), z = seed @ relu(Wfe) (BfeT [C][D]), Conv2d hook
+ * with a = x = v, AvgPool backward.  scratch [J,(D+C)]; g_out [J,7,7,C]. */
+int xfrb_head_bwd_linear(const float* Pn, const float* W2, int Ccls, const float* BfeT, const float* v, float* scratch,
+                         float* g_out, int J, int N, int C, int D, int mode, float eps, int impl, void* stream);
 
 /* out[n] = sum_c relu(k*P2[n]/sums[n] - k*P2[N+n]/sums[N+n])  (whitebox.py:524-526); k = 1, or with thr != NULL the
  * truncation mask k = (P2[n] >= thr[n]) of whitebox.py:550-556 */

@@ -72,7 +72,8 @@ class EmulBackend(object):
         oo = F.conv2d(x.permute(0, 3, 1, 2), w, stem.b, 2, 3)
         r1 = relu(oo * stem.bn[0].view(1, -1, 1, 1) + stem.bn[1].view(1, -1, 1, 1))
         o.copy_(oo.permute(0, 2, 3, 1))
-        mp.copy_(F.max_pool2d(r1, 3, 2, 1).permute(0, 2, 3, 1))
+        pad = stem.pool_pad
+        mp.copy_(F.max_pool2d(r1, 3, 2, pad, ceil_mode=(pad == 0)).permute(0, 2, 3, 1))
 
     def subsample2(self, u, out):
         out.copy_(u[:, ::2, ::2, :])
@@ -80,7 +81,7 @@ class EmulBackend(object):
     def avgpool2(self, u, out):
         out.copy_(F.avg_pool2d(u.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1))
 
-    def conv_dual(self, inp, L, o, xr, act, res=None):
+    def conv_dual(self, inp, L, o, xr, act, res=None, relu_act=True):
         """o = conv(inp)+b ; xr = relu(conv_{W+}(inp)+b') ; act = relu(o*alpha+beta [+ res, zero-padded channels])."""
         A = im2col_nhwc(inp, L.R, L.S, L.R // 2)
         D = A @ _w(L.Bf).t() + L.bias
@@ -91,7 +92,7 @@ class EmulBackend(object):
         if res is not None:
             rc = res.shape[-1]
             a[:, :rc] += res.reshape(-1, rc)
-        act.view(-1, L.cout).copy_(relu(a))
+        act.view(-1, L.cout).copy_(relu(a) if relu_act else a)
 
     def head_fwd(self, u, head, v, f1, f1p, xn, nrm):
         """v = avgpool7(u); (f1 | f1p) = one dual GEMM v @ [W1 ; relu(W1)]^T + (b | b'); xn = f1/|f1|."""
@@ -145,28 +146,35 @@ class EmulBackend(object):
         y_out.view(-1, L.cin).copy_(self._mid_chain(z, _rows(o, J).reshape(-1, L.cin),
                                                      _rows(xr, J).reshape(-1, L.cin), bn, mode))
 
-    def dgrad_plain(self, y, L, z_out, signed=False):
-        z_out.view(-1, L.cin).copy_(self._dgrad(y, L.signed_dgrad() if signed else L.Bd, L.R))
+    def dgrad_plain(self, y, L, z_out, signed=False, accumulate=False):
+        z = self._dgrad(y, L.signed_dgrad() if signed else L.Bd, L.R)
+        if accumulate:
+            z = z + z_out.reshape(-1, L.cin)
+        z_out.view(-1, L.cin).copy_(z)
 
     def _join_chain(self, z, out, o3, xr3, bn3, res, hooks, mode):
         """Hook chain on a block output `out` (hooks: 1 = [affine], 2 = [affine, non-affine Add],
         3 = [affine, affine]) followed by the start of that block's main path.
         res = the block's residual input zero-padded to C channels (only read in MODE_ALL)."""
-        alpha, beta, sp = bn3[0], bn3[1], bn3[2]
+        alpha, beta, sp, tp = bn3[0], bn3[1], bn3[2], bn3[3]
+        fn_add, chain = bool(hooks & 4), hooks & 3      # hooks & 4: torch.add instead of an Add module (ResNet-50-128d)
         if mode != MODE_ALL:      # non-affine hooks ignore (a, x) in these modes
             xblk = out
             rres = out
+        elif fn_add:
+            rres = None
+            xblk = relu((relu(o3) * sp + tp) + res)
         else:
             rres = relu(res)
             xblk = relu(relu(o3 * alpha + beta) + rres)
         z = hook(False, out, xblk, z, mode, self.eps)
         z = hook(True, out, out, z, mode, self.eps)
-        if hooks == 2:
+        if chain == 2:
             z = hook(False, out, out, z, mode, self.eps)
-        elif hooks == 3:
+        elif chain == 3:
             z = hook(True, out, out, z, mode, self.eps)
         g = z * (out > 0)
-        zz = hook(False, rres, rres, g, mode, self.eps)      # Add slot 0 with the residual's (A, X)
+        zz = g if fn_add else hook(False, rres, rres, g, mode, self.eps)      # Add slot 0 with the residual's (A, X)
         zz = zz * sp
         y3 = hook(True, relu(o3), xr3, zz, mode, self.eps)
         return g, y3
@@ -211,18 +219,39 @@ class EmulBackend(object):
         z = hook(False, a, a, g[..., :cr], mode, self.eps)
         gres_lo.copy_(hook(False, a, a, z, mode, self.eps))
 
-    def stem_bwd(self, zmain, gres, o, mp, bn, mode, P2, chansum, sums):
+    def bn_hook(self, g, o, xr, bn, y, kind, mode):
+        """kind 0: BatchNorm backward (gamma+) + BatchNorm hook of a conv output; kind 1: relu(o)*sp + tp."""
+        sp, tp = bn[2], bn[3]
+        if kind == 1:
+            y.copy_(relu(o) * sp + tp)
+        else:
+            J = g.shape[0]
+            y.copy_(hook(True, relu(_rows(o, J)), _rows(xr, J), g * sp, mode, self.eps))
+
+    def head_fwd_linear(self, u, head, v, enc):
+        vv = F.avg_pool2d(u.permute(0, 3, 1, 2), 7, 7).flatten(1)
+        v.copy_(vv)
+        enc.copy_(vv @ _w(head.Bfe).t())
+
+    def head_bwd_linear(self, Pn, W2, head, v, mode, g_out):
+        J = Pn.shape[0]
+        v_ = _rows(v, J)
+        gr = torch.einsum('jc,jcd->jd', Pn, _rows(W2, J)) @ _w(head.BfeT).t()
+        gr = hook(True, relu(v_), relu(v_), gr, mode, self.eps)
+        g_out.copy_((gr / 49.0).view(J, 1, 1, -1).expand(-1, 7, 7, -1))
+
+    def stem_bwd(self, zmain, gres, o, mp, bn, mode, P2, chansum, sums, pool_pad=1):
         """Chain at the max-pool output (Conv2d + AvgPool2d(k=1) hooks, both affine), MaxPool
         backward, ReLU / MaxPool2d hooks, ReLU + BN backward, BN hook -> P[-2] = relu(o)*relu(z)."""
         J = zmain.shape[0]
         alpha, beta, sp, tp = bn[0], bn[1], bn[2], bn[3]
         mp_ = _rows(mp, J)
         o_ = _rows(o, J)
-        z = zmain + gres
+        z = zmain if gres is None else zmain + gres
         z = hook(True, mp_, mp_, z, mode, self.eps)
         z = hook(True, mp_, mp_, z, mode, self.eps)
         r1 = relu(o_ * alpha + beta).permute(0, 3, 1, 2)
-        _, idx = F.max_pool2d(r1, 3, 2, 1, return_indices=True)
+        _, idx = F.max_pool2d(r1, 3, 2, pool_pad, ceil_mode=(pool_pad == 0), return_indices=True)
         zz = torch.zeros_like(r1).flatten(2).scatter_add_(2, idx.flatten(2), z.permute(0, 3, 1, 2).flatten(2))
         zz = zz.view_as(r1).permute(0, 2, 3, 1)
         r1 = r1.permute(0, 2, 3, 1)

@@ -39,7 +39,8 @@ class ShadowBackend(object):
         'stem_fwd': (2, 3), 'subsample2': (1,), 'avgpool2': (1,), 'conv_dual': (2, 3, 4),
         'head_fwd': (2, 3, 4, 5, 6), 'head_bwd': (8,), 'dgrad_mid': (6,), 'dgrad_plain': (2,),
         'dgrad_join': (10, 11), 'join': (11, 12), 'ds_res': (3,), 'stem_bwd': (6, 7, 8),
-        'contrast': (3,), 'saliency_post': (1,), 'trunc_threshold': (4,),
+        'contrast': (3,), 'saliency_post': (1,), 'trunc_threshold': (4,), 'bn_hook': (4,), 'head_fwd_linear': (2, 3),
+        'head_bwd_linear': (5,),
     }
 
     def __init__(self, cuda_be, emul_be, pack_map):
@@ -52,18 +53,19 @@ class ShadowBackend(object):
             raise AttributeError(name)
 
         def call(*args, **kw):
-            getattr(self.cuda, name)(*args, **kw)
-            torch.cuda.synchronize()
             outs = self.OUTPUTS[name]
-            cargs = []
+            torch.cuda.synchronize()
+            cargs = []          # host copies taken BEFORE the CUDA call (some outputs are also read: accumulate)
             for i, a in enumerate(args):
                 if torch.is_tensor(a):
-                    cargs.append(torch.empty_like(a, device='cpu') if i in outs else a.detach().cpu().clone())
+                    cargs.append(a.detach().cpu().clone())
                 elif id(a) in self.pack_map:
                     cargs.append(self.pack_map[id(a)])
                 else:
                     cargs.append(a)
             ckw = {k: (v.detach().cpu().clone() if torch.is_tensor(v) else v) for k, v in kw.items()}
+            getattr(self.cuda, name)(*args, **kw)
+            torch.cuda.synchronize()
             getattr(self.emul, name)(*cargs, **ckw)
             for i in outs:
                 got, want = args[i].detach().cpu().double(), cargs[i].double()
@@ -78,6 +80,23 @@ class ShadowBackend(object):
 def pack_map(eng_gpu, eng_cpu):
     m = {id(eng_gpu.stem): eng_cpu.stem, id(eng_gpu.head): eng_cpu.head}
     for bg, bc in zip(eng_gpu.blocks, eng_cpu.blocks):
-        for k in ('c1', 'c2', 'c3'):
-            m[id(getattr(bg, k))] = getattr(bc, k)
+        for k in ('c1', 'c2', 'c3', 'cp'):
+            if getattr(bg, k, None) is not None:
+                m[id(getattr(bg, k))] = getattr(bc, k)
     return m
+
+
+R50_WEIGHTS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_ref', 'resnet50_128.pth')
+R50_MEAN = (131.0912, 103.8827, 91.4953)
+
+
+def r50_inputs():
+    """Real VGGFace2 ResNet-50-128d weights + the bundled real triplet / demo face (crops stored in the golden file).
+    Returns (state_dict, G, X dict of [1,3,224,224] tensors) or None when the 95 MB weight file did not travel."""
+    if not os.path.exists(R50_WEIGHTS):
+        return None
+    G = np.load(os.path.join(GOLD, 'resnet50_128_real.npz'))
+    sd = torch.load(R50_WEIGHTS)
+    X = {k: torch.from_numpy((G['crop_' + k].astype(np.float64) - np.array(R50_MEAN)).transpose(2, 0, 1).astype(np.float32)).unsqueeze(0)
+         for k in ('probe', 'mate', 'nonmate', 'demo')}
+    return sd, G, X

@@ -1,0 +1,104 @@
+"""VGGFace2 ResNet-50-128d with the REAL bundled weights on the REAL bundled triplet (the north star's "bundled demo
+triplets"): oracle and host schedule on the CPU, CUDA kernels on the GPU, all against the reference's own outputs
+(tests/golden/resnet50_128_real.npz, made by oracle/gen_golden_r50.py).  Skipped when oracle/_ref/resnet50_128.pth
+(95 MB, git-ignored, extracted from the reference's tarball by the generator) is not in the working tree."""
+import numpy as np
+import pytest
+import torch
+
+from emul_backend import EmulBackend
+from helpers import ShadowBackend, pack_map, r50_inputs, rel_err
+from xfr_b200.engine import Resnet50_128Engine
+
+MODES = (('affineonly_with_prior', 'awp'), ('all', 'all'), ('affineonly', 'affineonly'), ('norelu', 'norelu'))
+R50 = r50_inputs()
+needs_weights = pytest.mark.skipif(R50 is None, reason='oracle/_ref/resnet50_128.pth not present')
+
+
+@needs_weights
+def test_oracle_matches_reference_fingerprints():
+    from oracle import resnet50_128_oracle as O
+    sd, G, X = R50
+    assert rel_err(O.encode(sd, X['mate']).numpy(), G['enc_mate']) < 1e-6
+    fc1 = torch.from_numpy(np.concatenate((G['enc_mate'], G['enc_nonmate']))).float()
+    P0 = torch.zeros(1, 2)
+    P0[0, 0] = 1
+    P, kinds = O.ebp_mwp(sd, X['probe'], P0, fc1)
+    assert kinds == [str(k) for k in G['P_kinds']] and len(P) == 158
+    sums = np.array([float(p.double().sum()) for p in P])
+    assert np.max(np.abs(sums - G['Psum_awp_probe']) / (np.abs(G['Psum_awp_probe']) + 1e-30)) < 1e-5
+    c = O.contrastive_ebp(sd, X['probe'], fc1)[0]
+    # SURVEY 8c fingerprints of the shimmed reference: max 1.649949e-03 at pixel 5553
+    assert abs(float(G['cebp_awp_probe'].max()) - 1.649949e-03) < 1e-8 and int(G['cebp_awp_probe'].argmax()) == 5553
+    assert int(c.argmax()) == 5553 and rel_err(c, G['cebp_awp_probe']) < 1e-4
+    t = O.contrastive_ebp(sd, X['probe'], fc1, percentile=20)[0]
+    assert rel_err(t, G['tcebp20_awp_probe']) < 1e-4
+
+
+@needs_weights
+@pytest.mark.parametrize('mode,tag', MODES)
+def test_schedule_emulation(mode, tag):
+    sd, G, X = R50
+    eng = Resnet50_128Engine(sd, EmulBackend(impl_name='tf32x3'))
+    x = torch.cat([X['probe'], X['demo']]).permute(0, 2, 3, 1).contiguous()
+    W2 = torch.from_numpy(np.concatenate((G['enc_mate'], G['enc_nonmate']))).float().unsqueeze(0).repeat(2, 1, 1)
+    P1 = torch.zeros(2, 2)
+    P1[:, 0] = 1
+    s = eng.ebp(x, P1, W2, mode).clone().numpy()
+    c = eng.contrastive(x, W2, mode=mode).clone().numpy()
+    t = eng.contrastive(x, W2, mode=mode, percentile=20).clone().numpy()
+    for i, p in enumerate(('probe', 'demo')):
+        assert rel_err(s[i], G['ebp_%s_%s' % (tag, p)]) < 1e-5
+        assert rel_err(c[i], G['cebp_%s_%s' % (tag, p)]) < 1e-4
+        assert rel_err(t[i], G['tcebp20_%s_%s' % (tag, p)]) < 1e-4
+
+
+@needs_weights
+@pytest.mark.gpu
+@pytest.mark.parametrize('impl', ['fp32', 'tf32x3'])
+def test_gpu_kernels_shadow(impl):
+    from xfr_b200.kernels import CudaBackend
+    sd, G, X = R50
+    dev = torch.device('cuda:0')
+    be = CudaBackend(dev, impl=impl)
+    eng_cpu = Resnet50_128Engine(sd, EmulBackend(impl_name=impl))
+    eng = Resnet50_128Engine(sd, be, device=dev)
+    sh = ShadowBackend(be, EmulBackend(), pack_map(eng, eng_cpu))
+    eng.be = sh
+    x = torch.cat([X['probe'], X['demo']]).permute(0, 2, 3, 1).contiguous().to(dev)
+    W2 = torch.from_numpy(np.concatenate((G['enc_mate'], G['enc_nonmate']))).float().unsqueeze(0).repeat(2, 1, 1).to(dev)
+    for mode in ('affineonly_with_prior', 'all'):
+        eng.contrastive(x, W2, mode=mode)
+    tol = 2e-5 if impl == 'fp32' else 2e-4
+    print('\n'.join('%-20s %.3g' % kv for kv in sorted(sh.errors.items())))
+    bad = {k: v for k, v in sh.errors.items() if v > tol}
+    assert not bad, bad
+
+
+@needs_weights
+@pytest.mark.gpu
+@pytest.mark.parametrize('impl', ['fp32', 'tf32x3', 'tf32'])
+def test_gpu_real_weights_real_triplet_vs_reference(impl):
+    """North-star parity: maps of the CUDA path vs the reference's CPU output on the bundled triplet, <= 1e-4 max-abs."""
+    from xfr_b200 import whitebox
+    sd, G, X = R50
+    dev = torch.device('cuda:0')
+    sdd = {k: v.to(dev) for k, v in sd.items()}
+    report = {}
+    for mode, tag in MODES:
+        wb = whitebox.Whitebox(whitebox.Whitebox_resnet50_128(sdd, impl=impl), ebp_subtree_mode=mode)
+        x_mate, x_non = wb.net.encode(X['mate']), wb.net.encode(X['nonmate'])
+        assert rel_err(x_mate.cpu().numpy(), G['enc_mate']) < (1e-4 if impl != 'tf32' else 2e-2)
+        wb.net.set_triplet_classifier(x_mate, x_non)
+        P0 = torch.zeros(1, 2)
+        P0[0][0] = 1.0
+        for p in ('probe', 'demo'):
+            for key, got in (('ebp', wb.ebp(X[p], P0)), ('cebp', wb.contrastive_ebp(X[p], 0, 1)),
+                             ('tcebp20', wb.truncated_contrastive_ebp(X[p], 0, 1, percentile=20))):
+                ref = G['%s_%s_%s' % (key, tag, p)]
+                report['%s_%s_%s' % (key, tag, p)] = (float(np.abs(got - ref).max()), rel_err(got, ref))
+    print('\n'.join('%-26s max-abs %.3g   max-abs/max(ref) %.3g' % (k, v[0], v[1]) for k, v in sorted(report.items())))
+    rel_tol = {'fp32': 1e-3, 'tf32x3': 1e-2, 'tf32': 1.0}[impl]
+    for k, (a, r) in report.items():
+        assert a < 1e-4, (k, a)
+        assert r < rel_tol, (k, r)

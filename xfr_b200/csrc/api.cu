@@ -13,7 +13,10 @@ void set_error(const char* what, cudaError_t e) {
 }
 
 // forward declarations of the stage launchers (stages.cu)
-cudaError_t launch_stem_fwd(const float*, const float*, const float*, const float*, float*, float*, int, cudaStream_t);
+cudaError_t launch_stem_fwd(const float*, const float*, const float*, const float*, float*, float*, int, int, cudaStream_t);
+cudaError_t launch_bn_hook(const float*, const float*, const float*, const float*, float*, size_t, size_t, int, int, int, float,
+                           cudaStream_t);
+cudaError_t launch_head_seed(const float*, const float*, int, int, int, int, float*, cudaStream_t);
 cudaError_t launch_subsample2(const float*, float*, int, int, int, int, cudaStream_t);
 cudaError_t launch_avgpool2(const float*, float*, int, int, int, int, cudaStream_t);
 cudaError_t launch_avgpool7(const float*, float*, int, int, cudaStream_t);
@@ -24,7 +27,7 @@ cudaError_t launch_head_bwd_b(const float*, const float*, float*, int, int, int,
 cudaError_t launch_join(const JoinArgs&, cudaStream_t);
 cudaError_t launch_ds_res(const float*, const float*, float*, int, int, int, int, int, int, int, float, cudaStream_t);
 cudaError_t launch_stem_bwd(const float*, const float*, const float*, const float*, const float*, float*, float*, float*,
-                            double*, int, int, int, float, cudaStream_t);
+                            double*, int, int, int, float, int, cudaStream_t);
 cudaError_t launch_contrast(const float*, const double*, const float*, float*, int, int, int, cudaStream_t);
 cudaError_t launch_trunc_threshold(const float*, const double*, float, float*, int, size_t, cudaStream_t);
 cudaError_t launch_saliency_post(const float*, float*, int, int, int, float, cudaStream_t);
@@ -66,8 +69,10 @@ int xfrb_impl_available(int impl) {
     return 0;
 }
 
-int xfrb_stem_fwd(const float* x, const float* W, const float* b, const float* bn, float* o, float* mp, int N, void* stream) {
-    return finish("xfrb_stem_fwd", launch_stem_fwd(x, W, b, bn, o, mp, N, (cudaStream_t)stream));
+int xfrb_stem_fwd(const float* x, const float* W, const float* b, const float* bn, float* o, float* mp, int N, int pool_pad,
+                  void* stream) {
+    if (pool_pad != 0 && pool_pad != 1) return finish("xfrb_stem_fwd", cudaErrorInvalidValue);
+    return finish("xfrb_stem_fwd", launch_stem_fwd(x, W, b, bn, o, mp, N, pool_pad, (cudaStream_t)stream));
 }
 
 int xfrb_subsample2(const float* u, float* out, int N, int H, int W, int C, void* stream) {
@@ -81,7 +86,7 @@ int xfrb_avgpool2(const float* u, float* out, int N, int H, int W, int C, void* 
 }
 
 int xfrb_conv_dual(const float* inp, const float* Bf, const float* bias, const float* bn, const float* res, int res_c,
-                   float* o, float* xr, float* act, int N, int H, int W, int Cin, int Cout, int R, int tn, int impl,
+                   float* o, float* xr, float* act, int N, int H, int W, int Cin, int Cout, int R, int tn, int relu_act, int impl,
                    void* stream) {
     if ((R != 1 && R != 3) || (tn != 128 && tn != 256) || (impl == XFRB_IMPL_FP32 && tn != 128) || (2 * Cout) % tn ||
         (res && res_c % 4))
@@ -93,6 +98,7 @@ int xfrb_conv_dual(const float* inp, const float* Bf, const float* bias, const f
     ep.M = ep.Ms = N * H * W;
     ep.C = Cout;
     ep.bias = bias; ep.bn = bn; ep.res = res; ep.res_c = res_c;
+    ep.hooks = relu_act ? 0 : 1;
     ep.out0 = o; ep.out1 = xr; ep.out2 = act;
     return finish("xfrb_conv_dual", run_gemm(inp, Bf, g, ep, impl, (cudaStream_t)stream, tn));
 }
@@ -151,8 +157,8 @@ int xfrb_dgrad_mid(const float* y, const float* Bd, const float* o, const float*
     return finish("xfrb_dgrad_mid", run_gemm(y, Bd, g, ep, impl, (cudaStream_t)stream));
 }
 
-int xfrb_dgrad_plain(const float* y, const float* Bd, float* z_out, int J, int H, int W, int Cin, int Cout, int R, int impl,
-                     void* stream) {
+int xfrb_dgrad_plain(const float* y, const float* Bd, float* z_out, int J, int H, int W, int Cin, int Cout, int R, int accumulate,
+                     int impl, void* stream) {
     if (R != 1 && R != 3) return finish("xfrb_dgrad_plain", cudaErrorInvalidValue);
     ConvGeom g{H, W, Cout, R, R * R * Cout, Cin};
     EpiParams ep;
@@ -161,6 +167,7 @@ int xfrb_dgrad_plain(const float* y, const float* Bd, float* z_out, int J, int H
     ep.M = ep.Ms = J * H * W;
     ep.C = Cin;
     ep.out0 = z_out;
+    ep.g_res = accumulate ? z_out : nullptr;
     return finish("xfrb_dgrad_plain", run_gemm(y, Bd, g, ep, impl, (cudaStream_t)stream));
 }
 
@@ -194,8 +201,49 @@ int xfrb_ds_res(const float* g, const float* ap, float* gres_lo, int J, int N, i
 }
 
 int xfrb_stem_bwd(const float* zmain, const float* gres, const float* o, const float* mp, const float* bn, float* zc, float* P2,
-                  float* chansum, double* sums, int J, int N, int mode, float eps, void* stream) {
-    return finish("xfrb_stem_bwd", launch_stem_bwd(zmain, gres, o, mp, bn, zc, P2, chansum, sums, J, N, mode, eps, (cudaStream_t)stream));
+                  float* chansum, double* sums, int J, int N, int mode, float eps, int pool_pad, void* stream) {
+    if (pool_pad != 0 && pool_pad != 1) return finish("xfrb_stem_bwd", cudaErrorInvalidValue);
+    return finish("xfrb_stem_bwd",
+                  launch_stem_bwd(zmain, gres, o, mp, bn, zc, P2, chansum, sums, J, N, mode, eps, pool_pad, (cudaStream_t)stream));
+}
+
+int xfrb_bn_hook(const float* g, const float* o, const float* xr, const float* bn, float* y, int J, int N, int HW, int C, int kind,
+                 int mode, float eps, void* stream) {
+    if (C % 4) return finish("xfrb_bn_hook", cudaErrorInvalidValue);
+    return finish("xfrb_bn_hook", launch_bn_hook(g, o, xr, bn, y, (size_t)(kind == 1 ? N : J) * HW, (size_t)N * HW, C, kind, mode, eps,
+                                                 (cudaStream_t)stream));
+}
+
+int xfrb_head_fwd_linear(const float* u, const float* Bfe, float* v, float* enc, int N, int C, int D, int impl, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = launch_avgpool7(u, v, N, C, st);
+    if (e != cudaSuccess) return finish("xfrb_head_fwd_linear/avgpool", e);
+    ConvGeom g{1, 1, C, 1, C, D};
+    EpiParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.kind = EPI_PLAIN;
+    ep.M = ep.Ms = N;
+    ep.C = D;
+    ep.out0 = enc;
+    return finish("xfrb_head_fwd_linear/gemm", run_gemm(v, Bfe, g, ep, impl, st));
+}
+
+int xfrb_head_bwd_linear(const float* Pn, const float* W2, int Ccls, const float* BfeT, const float* v, float* scratch, float* g_out,
+                         int J, int N, int C, int D, int mode, float eps, int impl, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = launch_head_seed(Pn, W2, Ccls, D, J, N, scratch, st);
+    if (e != cudaSuccess) return finish("xfrb_head_bwd_linear/seed", e);
+    float* z = scratch + (size_t)J * D;
+    ConvGeom g{1, 1, D, 1, D, C};
+    EpiParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.kind = EPI_PLAIN;
+    ep.M = ep.Ms = J;
+    ep.C = C;
+    ep.out0 = z;
+    e = run_gemm(scratch, BfeT, g, ep, impl, st);
+    if (e != cudaSuccess) return finish("xfrb_head_bwd_linear/gemm", e);
+    return finish("xfrb_head_bwd_linear/b", launch_head_bwd_b(z, v, g_out, J, N, C, mode, eps, st));
 }
 
 int xfrb_contrast(const float* P2, const double* sums, const float* thr, float* out, int N, int HW, int C, void* stream) {

@@ -46,18 +46,27 @@ __device__ __forceinline__ float mid_chain(float z, float o, float xr, const BnC
 }
 
 // Chain on a block output `out` + start of that block's main path.
-// hooks: 1 = [affine], 2 = [affine, non-affine], 3 = [affine, affine].
+// hooks & 3: 1 = [affine], 2 = [affine, non-affine], 3 = [affine, affine]   (hooks that follow the block's ReLU hook)
+// hooks & 4: the residual sum is a plain function (VGGFace2 ResNet-50, resnet50_128.py:187): no Add hook, and the X of the
+//            block ReLU sums positive-pass values, relu(BN+(relu(o3)) + res) with res = the positive-pass shortcut;
+//            otherwise (STR ResNet, resnet.py:104-149) the Add module's inputs were overridden by A and its slot-0 hook
+//            carries the residual's (A, X) (late-binding closure, whitebox.py:379-432).
 __device__ __forceinline__ void join_chain(float z, float out, float o3, float xr3, float res, const BnC& b,
                                            int hooks, int mode, float eps, float& g, float& y3) {
+    const bool fn_add = (hooks & 4) != 0;
+    const int chain = hooks & 3;
     float rres = fmaxf(res, 0.f);
     float xblk = out;
-    if (mode == XFRB_MODE_ALL) xblk = fmaxf(__fadd_rn(fmaxf(__fadd_rn(__fmul_rn(o3, b.alpha), b.beta), 0.f), rres), 0.f);
+    if (mode == XFRB_MODE_ALL) {
+        if (fn_add) xblk = fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(fmaxf(o3, 0.f), b.sp), b.tp), res), 0.f);
+        else xblk = fmaxf(__fadd_rn(fmaxf(__fadd_rn(__fmul_rn(o3, b.alpha), b.beta), 0.f), rres), 0.f);
+    }
     z = hook<false>(out, xblk, z, mode, eps);
     z = hook<true>(out, out, z, mode, eps);
-    if (hooks == 2) z = hook<false>(out, out, z, mode, eps);
-    else if (hooks == 3) z = hook<true>(out, out, z, mode, eps);
+    if (chain == 2) z = hook<false>(out, out, z, mode, eps);
+    else if (chain == 3) z = hook<true>(out, out, z, mode, eps);
     g = out > 0.f ? z : 0.f;
-    float zz = hook<false>(rres, rres, g, mode, eps);
+    float zz = fn_add ? g : hook<false>(rres, rres, g, mode, eps);
     zz = __fmul_rn(zz, b.sp);
     y3 = hook<true>(fmaxf(o3, 0.f), xr3, zz, mode, eps);
 }
@@ -82,7 +91,7 @@ struct EpiParams {
     const float* o;      // MID: o ; JOIN: o3
     const float* xr;     // MID: xr ; JOIN: xr3
     const float* outp;   // JOIN: previous block output
-    const float* g_res;  // JOIN: residual-path gradient [M, C]
+    const float* g_res;  // JOIN: residual-path gradient [M, C] ; PLAIN: optional tensor to accumulate onto
     float* out0;         // PLAIN: z ; FWD_DUAL: o ; MID: y_out ; JOIN: g_out
     float* out1;         // FWD_DUAL: xr ; JOIN: y3_out
     float* out2;         // FWD_DUAL: act
@@ -93,6 +102,10 @@ __device__ __forceinline__ void epilogue4(const EpiParams& P, int m, int c, floa
                                           float4 bias_t, float4 bias_p) {
     const size_t off = (size_t)m * P.C + c;
     if (P.kind == EPI_PLAIN) {
+        if (P.g_res != nullptr) {      // accumulate into an existing tensor (second dgrad of a projection block)
+            float4 t = ld4(P.g_res + off);
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
         st4(P.out0 + off, acc);
         return;
     }
@@ -114,7 +127,8 @@ __device__ __forceinline__ void epilogue4(const EpiParams& P, int m, int c, floa
         for (int i = 0; i < 4; ++i) {
             o[i] = __fadd_rn(a[i], bt[i]);
             x[i] = fmaxf(__fadd_rn(ap[i], bp[i]), 0.f);
-            act[i] = fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(o[i], b[i].alpha), b[i].beta), r[i]), 0.f);
+            act[i] = __fadd_rn(__fadd_rn(__fmul_rn(o[i], b[i].alpha), b[i].beta), r[i]);
+            if (!(P.hooks & 1)) act[i] = fmaxf(act[i], 0.f);      // hooks bit 0: emit bn(o) without the ReLU (projection shortcut)
         }
         st4(P.out0 + off, make_float4(o[0], o[1], o[2], o[3]));
         st4(P.out1 + off, make_float4(x[0], x[1], x[2], x[3]));

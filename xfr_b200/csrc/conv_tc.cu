@@ -363,6 +363,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (!vrow[i]) continue;
                     if (KIND == EPI_FWD_DUAL) {
                         if (ep.res != nullptr && c < ep.res_c) l0[i] = __ldg(reinterpret_cast<const float4*>(ep.res + (size_t)mrow[i] * ep.res_c + c));
+                    } else if (KIND == EPI_PLAIN) {
+                        if (ep.g_res != nullptr) l0[i] = *reinterpret_cast<const float4*>(ep.g_res + (size_t)mrow[i] * ep.C + c);
                     } else if (KIND == EPI_MID || KIND == EPI_JOIN) {
                         const size_t offs = (size_t)msav[i] * ep.C + c;
                         l0[i] = __ldg(reinterpret_cast<const float4*>(ep.o + offs));
@@ -426,14 +428,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     float r0[4], r1[4], r2[4];
                     if (KIND == EPI_PLAIN) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) r0[e] = av[e] + bt[e];
+                        for (int e = 0; e < 4; ++e) r0[e] = av[e] + bt[e] + la[e];
                     } else if (KIND == EPI_FWD_DUAL) {
                         const float pv[4] = {apv[i].x, apv[i].y, apv[i].z, apv[i].w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             r0[e] = __fadd_rn(av[e], bt[e]);
                             r1[e] = fmaxf(__fadd_rn(pv[e], bp[e]), 0.f);
-                            r2[e] = fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(r0[e], b[e].alpha), b[e].beta), la[e]), 0.f);
+                            r2[e] = __fadd_rn(__fadd_rn(__fmul_rn(r0[e], b[e].alpha), b[e].beta), la[e]);
+                            if (!(ep.hooks & 1)) r2[e] = fmaxf(r2[e], 0.f);
                         }
                     } else if (KIND == EPI_MID) {
 #pragma unroll

@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
 }
 
 // mp = maxpool3x3/2 pad 1 of relu(bn(o))   (resnet.py:226-228)
-__global__ void stem_pool_kernel(const float* __restrict__ o, const float* __restrict__ bn, float* __restrict__ mp, int total4) {
+__global__ void stem_pool_kernel(const float* __restrict__ o, const float* __restrict__ bn, float* __restrict__ mp, int total4,
+                                 int pad) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
     int c = (i & 15) * 4;
@@ -71,10 +72,10 @@ __global__ void stem_pool_kernel(const float* __restrict__ o, const float* __res
     float4 al = ld4(bn + c), be = ld4(bn + 64 + c);
     float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     for (int r = 0; r < 3; ++r) {
-        int h = ph * 2 - 1 + r;
+        int h = ph * 2 - pad + r;
         if (h < 0 || h >= 112) continue;
         for (int s = 0; s < 3; ++s) {
-            int w = pw * 2 - 1 + s;
+            int w = pw * 2 - pad + s;
             if (w < 0 || w >= 112) continue;
             float4 v = ld4(o + (((size_t)n * 112 + h) * 112 + w) * 64 + c);
             m.x = fmaxf(m.x, fmaxf(__fadd_rn(__fmul_rn(v.x, al.x), be.x), 0.f));
@@ -87,7 +88,7 @@ __global__ void stem_pool_kernel(const float* __restrict__ o, const float* __res
 }
 
 cudaError_t launch_stem_fwd(const float* x, const float* W, const float* b, const float* bn, float* o, float* mp, int N,
-                            cudaStream_t st) {
+                            int pool_pad, cudaStream_t st) {
     size_t smem = (147 * 64 + ST_P * ST_P * 3) * sizeof(float);
     static bool attr = false;
     if (!attr) {
@@ -96,7 +97,7 @@ cudaError_t launch_stem_fwd(const float* x, const float* W, const float* b, cons
     }
     stem_conv_kernel<<<dim3(112 / ST_T, 112 / ST_T, N), 256, smem, st>>>(x, W, b, o, N);
     int total4 = N * 56 * 56 * 16;
-    stem_pool_kernel<<<(total4 + 255) / 256, 256, 0, st>>>(o, bn, mp, total4);
+    stem_pool_kernel<<<(total4 + 255) / 256, 256, 0, st>>>(o, bn, mp, total4, pool_pad);
     return cudaGetLastError();
 }
 
@@ -340,7 +341,8 @@ __global__ void stem_bwd_a_kernel(const float* __restrict__ zmain, const float* 
     if (i >= total4) return;
     size_t j = i / per_sample4, r = i % per_sample4;
     size_t n = j % N;
-    float4 a = reinterpret_cast<const float4*>(zmain)[i], b = reinterpret_cast<const float4*>(gres)[i];
+    float4 a = reinterpret_cast<const float4*>(zmain)[i];
+    float4 b = gres ? reinterpret_cast<const float4*>(gres)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 m = __ldg(reinterpret_cast<const float4*>(mp) + n * per_sample4 + r);
     float z[4] = {__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w)};
     float mm[4] = {fmaxf(m.x, 0.f), fmaxf(m.y, 0.f), fmaxf(m.z, 0.f), fmaxf(m.w, 0.f)};
@@ -356,7 +358,7 @@ __global__ void stem_bwd_a_kernel(const float* __restrict__ zmain, const float* 
 __global__ void __launch_bounds__(256) stem_bwd_b_kernel(const float* __restrict__ zc, const float* __restrict__ o,
                                                          const float* __restrict__ bn, float* __restrict__ P2,
                                                          float* __restrict__ chansum, double* __restrict__ sums,
-                                                         int N, int mode, float eps) {
+                                                         int N, int mode, float eps, int pad) {
     // grid: (112*112*16/256, J)
     __shared__ double red[8];
     const int j = blockIdx.y, n = j % N;
@@ -376,23 +378,24 @@ __global__ void __launch_bounds__(256) stem_bwd_b_kernel(const float* __restrict
         for (int q = 0; q < 4; ++q) me[q] = fmaxf(__fadd_rn(__fmul_rn(ov[q], alv[q]), bev[q]), 0.f);
     }
     float z[4] = {0.f, 0.f, 0.f, 0.f};
-    // MaxPool2d(3,2,1) backward as a gather: pooled row ph covers input rows 2ph-1..2ph+1; (h,w) receives the
-    // gradient of every window whose FIRST maximum (row-major scan, as torch's CPU kernel) it is.
+    // MaxPool2d(3, 2, pad) backward as a gather: pooled row ph covers input rows 2ph-pad..2ph-pad+2 (clipped: pad 1 for
+    // the STR net, pad 0 + ceil_mode for VGGFace2); (h,w) receives the gradient of every window whose FIRST maximum
+    // (row-major scan, as torch's CPU kernel) it is.
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
-        int ph = (h + 1) / 2 - a;
-        if (ph < 0 || ph >= 56 || 2 * ph - 1 > h || h > 2 * ph + 1) continue;
+        int ph = (h + pad) / 2 - a;
+        if (ph < 0 || ph >= 56 || 2 * ph - pad > h || h > 2 * ph - pad + 2) continue;
 #pragma unroll
         for (int b2 = 0; b2 < 2; ++b2) {
-            int pw = (w + 1) / 2 - b2;
-            if (pw < 0 || pw >= 56 || 2 * pw - 1 > w || w > 2 * pw + 1) continue;
+            int pw = (w + pad) / 2 - b2;
+            if (pw < 0 || pw >= 56 || 2 * pw - pad > w || w > 2 * pw - pad + 2) continue;
             bool win[4] = {true, true, true, true};
-            const int my = h - (2 * ph - 1), mx = w - (2 * pw - 1);     // my position inside the window
+            const int my = h - (2 * ph - pad), mx = w - (2 * pw - pad);     // my position inside the window
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
                 for (int s2 = 0; s2 < 3; ++s2) {
-                    int hh = 2 * ph - 1 + r, ww = 2 * pw - 1 + s2;
+                    int hh = 2 * ph - pad + r, ww = 2 * pw - pad + s2;
                     if ((r == my && s2 == mx) || hh < 0 || hh >= 112 || ww < 0 || ww >= 112) continue;
                     float4 v = ld4(ob + ((size_t)hh * 112 + ww) * 64);
                     const float vv[4] = {v.x, v.y, v.z, v.w};
@@ -441,11 +444,62 @@ __global__ void __launch_bounds__(256) stem_bwd_b_kernel(const float* __restrict
 
 cudaError_t launch_stem_bwd(const float* zmain, const float* gres, const float* o, const float* mp, const float* bn,
                             float* zc, float* P2, float* chansum, double* sums, int J, int N, int mode, float eps,
-                            cudaStream_t st) {
+                            int pool_pad, cudaStream_t st) {
     size_t per4 = (size_t)56 * 56 * 16, total4 = per4 * J;
     cudaMemsetAsync(sums, 0, sizeof(double) * J, st);
     stem_bwd_a_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(zmain, gres, mp, zc, per4, N, mode, eps, total4);
-    stem_bwd_b_kernel<<<dim3(112 * 112 * 16 / 256, J), 256, 0, st>>>(zc, o, bn, P2, chansum, sums, N, mode, eps);
+    stem_bwd_b_kernel<<<dim3(112 * 112 * 16 / 256, J), 256, 0, st>>>(zc, o, bn, P2, chansum, sums, N, mode, eps, pool_pad);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ projection-shortcut helpers (VGGFace2 ResNet-50)
+// BatchNorm backward with gamma+ then the BatchNorm hook of a conv output: y = relu(o) * relu(g*sp) / (xr + eps).
+// g [J,HW,C]; o, xr [N,HW,C].  kind 1 instead emits the positive-pass BN, relu(o)*sp + tp (X of the shortcut, MODE_ALL).
+__global__ void bn_hook_kernel(const float* __restrict__ g, const float* __restrict__ o, const float* __restrict__ xr,
+                               const float* __restrict__ bn, float* __restrict__ y, size_t rows_saved, int C, int kind, int mode,
+                               float eps, size_t total4) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int C4 = C / 4;
+    const int c = (int)(i % C4) * 4;
+    const size_t row = i / C4;
+    const size_t rs = row % rows_saved;
+    float4 ov = ld4(o + rs * C + c);
+    float4 sp = ld4(bn + 2 * C + c), tp = ld4(bn + 3 * C + c);
+    const float oo[4] = {ov.x, ov.y, ov.z, ov.w}, spv[4] = {sp.x, sp.y, sp.z, sp.w}, tpv[4] = {tp.x, tp.y, tp.z, tp.w};
+    float r[4];
+    if (kind == 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) r[q] = __fadd_rn(__fmul_rn(fmaxf(oo[q], 0.f), spv[q]), tpv[q]);
+    } else {
+        float4 gv = ld4(g + row * C + c), xv = ld4(xr + rs * C + c);
+        const float gg[4] = {gv.x, gv.y, gv.z, gv.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) r[q] = hook<true>(fmaxf(oo[q], 0.f), xx[q], __fmul_rn(gg[q], spv[q]), mode, eps);
+    }
+    reinterpret_cast<float4*>(y)[i] = make_float4(r[0], r[1], r[2], r[3]);
+}
+
+cudaError_t launch_bn_hook(const float* g, const float* o, const float* xr, const float* bn, float* y, size_t rows, size_t rows_saved,
+                           int C, int kind, int mode, float eps, cudaStream_t st) {
+    size_t total4 = rows * (C / 4);
+    bn_hook_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(g, o, xr, bn, y, rows_saved, C, kind, mode, eps, total4);
+    return cudaGetLastError();
+}
+
+// seed[j,:] = Pn[j,:] @ W2[j % N]   (un-hooked classifier rows, signed)
+__global__ void head_seed_kernel(const float* __restrict__ Pn, const float* __restrict__ W2, int C, int D, int N,
+                                 float* __restrict__ seed) {
+    const int j = blockIdx.x, n = j % N;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float g = 0.f;
+        for (int c = 0; c < C; ++c) g = fmaf(Pn[(size_t)j * C + c], W2[((size_t)n * C + c) * D + d], g);
+        seed[(size_t)j * D + d] = g;
+    }
+}
+
+cudaError_t launch_head_seed(const float* Pn, const float* W2, int C, int D, int J, int N, float* seed, cudaStream_t st) {
+    head_seed_kernel<<<J, 128, 0, st>>>(Pn, W2, C, D, N, seed);
     return cudaGetLastError();
 }
 

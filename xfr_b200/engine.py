@@ -33,18 +33,86 @@ class _Block(object):
     pass
 
 
-class StResnetEngine(object):
-    """Batched whitebox engine for the STR ResNet topology [3,4,23,3] (or any `layers`)."""
+class _Engine(object):
+    """Workspace + the operators composed from forward() / ebp_backward() of a concrete topology."""
+    map_hw = 112
 
-    def __init__(self, state_dict, backend, layers=STRESNET101, device='cpu', with_bias=False, eps=1e-16):
+    def _init_base(self, backend, device, with_bias, eps):
         self.be = backend
-        self.layers = tuple(layers)
         self.device = torch.device(device)
         self.with_bias = with_bias
         self.eps = eps
+        self._ws = {}
+        return getattr(backend, 'impl_name', 'fp32')     # decides the weight planes / tile widths of the packs
+
+    # ------------------------------------------------------------ workspace
+    def buf(self, name, *shape, **kw):
+        """Named buffer, allocated once per (name, shape): static addresses for graph capture."""
+        key = (name,) + tuple(shape)
+        t = self._ws.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=kw.get('dtype', torch.float32), device=self.device)
+            self._ws[key] = t
+        return t
+
+    def workspace_bytes(self):
+        return sum(t.numel() * t.element_size() for t in self._ws.values())
+
+    # ------------------------------------------------------------ composed operators
+    def _onehot(self, J, C, cols):
+        P = torch.zeros(J, C, dtype=torch.float32)
+        for (lo, hi), c in cols:
+            P[lo:hi, c] = 1.0
+        return P.to(self.device)
+
+    def ebp(self, x_nhwc, Pn, W2, mode='affineonly_with_prior', hooked_fc2=False, saliency=True):
+        """Whitebox.ebp over a batch (reference whitebox.py:482-504) -> [N,112,112] device tensor."""
+        self.forward(x_nhwc)
+        _, chansum, _ = self.ebp_backward(Pn, W2, mode, hooked_fc2)
+        if not saliency:
+            return chansum
+        out = self.buf('sal', chansum.shape[0], self.map_hw, self.map_hw)
+        self.be.saliency_post(chansum, out)
+        return out
+
+    def contrastive(self, x_nhwc, W2, k_pos=0, k_neg=1, mode='affineonly_with_prior', hooked_fc2=False,
+                    saliency=True, num_classes=None, percentile=None):
+        """Whitebox.contrastive_ebp / truncated_contrastive_ebp over a batch (reference whitebox.py:506-558):
+        one shared forward, mate and non-mate sweeps as one gradient batch of 2N rows."""
+        N = x_nhwc.shape[0]
+        C = num_classes if num_classes is not None else W2.shape[-2]
+        self.forward(x_nhwc)
+        Pn = self.priors_contrastive(N, C, k_pos, k_neg)
+        P2, _, sums = self.ebp_backward(Pn, W2, mode, hooked_fc2)
+        mwp = self.buf('cmwp', N, self.map_hw, self.map_hw)
+        thr = None
+        if percentile is not None:      # truncated_contrastive_ebp (reference whitebox.py:529-558)
+            thr = self.buf('thr', N)
+            self.be.trunc_threshold(P2, sums, N, percentile, thr)
+        self.be.contrast(P2, sums, N, mwp, thr)
+        if not saliency:
+            return mwp
+        out = self.buf('sal', N, self.map_hw, self.map_hw)
+        self.be.saliency_post(mwp, out)
+        return out
+
+    def priors_contrastive(self, N, C, k_pos, k_neg):
+        key = ('prior', N, C, k_pos, k_neg)
+        P = self._ws.get(key)
+        if P is None:
+            P = self._onehot(2 * N, C, (((0, N), k_pos), ((N, 2 * N), k_neg)))
+            self._ws[key] = P
+        return P
+
+
+class StResnetEngine(_Engine):
+    """Batched whitebox engine for the STR ResNet topology [3,4,23,3] (or any `layers`)."""
+
+    def __init__(self, state_dict, backend, layers=STRESNET101, device='cpu', with_bias=False, eps=1e-16):
+        impl = self._init_base(backend, device, with_bias, eps)
+        self.layers = tuple(layers)
         sd = {k: v.detach().cpu() for k, v in state_dict.items()}
         self.stem = packing.Stem(sd, with_bias=with_bias).to(self.device)
-        impl = getattr(backend, 'impl_name', 'fp32')     # decides the weight planes / tile widths of the packs
         self.head = packing.Head(sd, impl, with_bias=with_bias).to(self.device)
         self.blocks = []
         inplanes, hw = 64, 56
@@ -63,21 +131,7 @@ class StResnetEngine(object):
                 b.c3 = packing.ConvBN(sd, b.name + '.conv3', b.name + '.bn3', impl, with_bias).to(self.device)
                 self.blocks.append(b)
                 inplanes = planes * 4
-        self._ws = {}
         self.enc_dim = 512
-
-    # ------------------------------------------------------------ workspace
-    def buf(self, name, *shape, **kw):
-        """Named buffer, allocated once per (name, shape): static addresses for graph capture."""
-        key = (name,) + tuple(shape)
-        t = self._ws.get(key)
-        if t is None:
-            t = torch.empty(shape, dtype=kw.get('dtype', torch.float32), device=self.device)
-            self._ws[key] = t
-        return t
-
-    def workspace_bytes(self):
-        return sum(t.numel() * t.element_size() for t in self._ws.values())
 
     # ------------------------------------------------------------ forward
     def forward(self, x_nhwc):
@@ -181,48 +235,135 @@ class StResnetEngine(object):
                     gp, y3)
             gb = gp
 
-    # ------------------------------------------------------------ composed operators
-    def _onehot(self, J, C, cols):
-        P = torch.zeros(J, C, dtype=torch.float32)
-        for (lo, hi), c in cols:
-            P[lo:hi, c] = 1.0
-        return P.to(self.device)
 
-    def ebp(self, x_nhwc, Pn, W2, mode='affineonly_with_prior', hooked_fc2=False, saliency=True):
-        """Whitebox.ebp over a batch (reference whitebox.py:482-504) -> [N,112,112] device tensor."""
-        self.forward(x_nhwc)
-        _, chansum, _ = self.ebp_backward(Pn, W2, mode, hooked_fc2)
-        if not saliency:
-            return chansum
-        out = self.buf('sal', chansum.shape[0], 112, 112)
-        self.be.saliency_post(chansum, out)
-        return out
+class Resnet50_128Engine(_Engine):
+    """Batched whitebox engine for the VGGFace2 ResNet-50-128d (reference models/resnet50_128_pytorch/resnet50_128.py,
+    plugin whitebox.py:210-258).  Same kernels as the STR net; differences: conv + BN projection
+    shortcuts, the residual sum is a function (no Add hooks), MaxPool2d(3,2,0,ceil), avgpool7 + 1x1 conv 2048->128 head
+    with the wrapper's un-hooked fc1 (set_triplet_classifier rows [N,2,128])."""
+    STAGES = ((2, 3, 64), (3, 4, 128), (4, 6, 256), (5, 3, 512))
 
-    def contrastive(self, x_nhwc, W2, k_pos=0, k_neg=1, mode='affineonly_with_prior', hooked_fc2=False,
-                    saliency=True, num_classes=None, percentile=None):
-        """Whitebox.contrastive_ebp / truncated_contrastive_ebp over a batch (reference whitebox.py:506-558):
-        one shared forward, mate and non-mate sweeps as one gradient batch of 2N rows."""
+    def __init__(self, state_dict, backend, device='cpu', with_bias=False, eps=1e-16):
+        impl = self._init_base(backend, device, with_bias, eps)
+        sd = {k: v.detach().cpu() for k, v in state_dict.items()}
+        self.stem = packing.Stem(sd, 'conv1_7x7_s2', 'conv1_7x7_s2_bn', with_bias, pool_pad=0).to(self.device)
+        self.head = packing.LinearHead(sd, 'feat_extract', impl).to(self.device)
+        self.blocks = []
+        inplanes, hw = 64, 56
+        for st, n, planes in self.STAGES:
+            for i in range(1, n + 1):
+                b = _Block()
+                b.name = 'conv%d_%d' % (st, i)
+                b.stride = 2 if (i == 1 and st > 2) else 1
+                b.proj = i == 1
+                b.cin, b.planes, b.cout = inplanes, planes, planes * 4
+                b.hw_in = hw
+                hw = hw // b.stride
+                b.hw = hw
+                mk = lambda c: packing.ConvBN(sd, b.name + c, b.name + c + '_bn', impl, with_bias).to(self.device)
+                b.c1, b.c2, b.c3 = mk('_1x1_reduce'), mk('_3x3'), mk('_1x1_increase')
+                b.cp = mk('_1x1_proj') if b.proj else None
+                self.blocks.append(b)
+                inplanes = planes * 4
+        self.enc_dim = self.head.dim
+
+    def forward(self, x_nhwc):
+        """Fills the saved tensors; returns the 128-d encoding [N,128] (Whitebox_resnet50_128.encode, whitebox.py:222-224)."""
+        be = self.be
         N = x_nhwc.shape[0]
-        C = num_classes if num_classes is not None else W2.shape[-2]
-        self.forward(x_nhwc)
-        Pn = self.priors_contrastive(N, C, k_pos, k_neg)
-        P2, _, sums = self.ebp_backward(Pn, W2, mode, hooked_fc2)
-        mwp = self.buf('cmwp', N, 112, 112)
-        thr = None
-        if percentile is not None:      # truncated_contrastive_ebp (reference whitebox.py:529-558)
-            thr = self.buf('thr', N)
-            self.be.trunc_threshold(P2, sums, N, percentile, thr)
-        self.be.contrast(P2, sums, N, mwp, thr)
-        if not saliency:
-            return mwp
-        out = self.buf('sal', N, 112, 112)
-        self.be.saliency_post(mwp, out)
-        return out
+        S = {'N': N}
+        S['o_s'] = self.buf('o_s', N, 112, 112, 64)
+        S['mp'] = self.buf('mp', N, 56, 56, 64)
+        be.stem_fwd(x_nhwc, self.stem, S['o_s'], S['mp'])
+        u = S['mp']
+        for i, b in enumerate(self.blocks):
+            h = b.hw
+            t = {'u': u}
+            cin1 = u
+            if b.stride == 2:
+                cin1 = self.buf('us%d' % i, N, h, h, b.cin)
+                be.subsample2(u, cin1)
+            for k, c in (('1', b.planes), ('2', b.planes), ('3', b.cout)):
+                t['o' + k] = self.buf('o%s_%d' % (k, i), N, h, h, c)
+                t['xr' + k] = self.buf('xr%s_%d' % (k, i), N, h, h, c)
+            a1 = self.buf('a1', N, h, h, b.planes)
+            a2 = self.buf('a2', N, h, h, b.planes)
+            t['out'] = self.buf('out%d' % i, N, h, h, b.cout)
+            be.conv_dual(cin1, b.c1, t['o1'], t['xr1'], a1)
+            be.conv_dual(a1, b.c2, t['o2'], t['xr2'], a2)
+            if b.proj:
+                t['op'] = self.buf('op%d' % i, N, h, h, b.cout)
+                t['xrp'] = self.buf('xrp%d' % i, N, h, h, b.cout)
+                res = self.buf('resp', N, h, h, b.cout)
+                be.conv_dual(cin1, b.cp, t['op'], t['xrp'], res, relu_act=False)     # res = bn_p(conv_p(u)), no ReLU
+            else:
+                res = u
+            t['res'] = res if not b.proj else None          # identity: the X of the shortcut operand is u itself
+            be.conv_dual(a2, b.c3, t['o3'], t['xr3'], t['out'], res)
+            S[i] = t
+            u = t['out']
+        S['v'] = self.buf('v', N, u.shape[-1])
+        S['enc'] = self.buf('enc', N, self.head.dim)
+        be.head_fwd_linear(u, self.head, S['v'], S['enc'])
+        self.saved = S
+        return S['enc']
 
-    def priors_contrastive(self, N, C, k_pos, k_neg):
-        key = ('prior', N, C, k_pos, k_neg)
-        P = self._ws.get(key)
-        if P is None:
-            P = self._onehot(2 * N, C, (((0, N), k_pos), ((N, 2 * N), k_neg)))
-            self._ws[key] = P
-        return P
+    def _xres(self, i, m):
+        """Positive-pass value of block i's shortcut operand (only read in mode 'all'): identity blocks -> the block
+        input; projection blocks -> BN+(relu(op))."""
+        b, t = self.blocks[i], self.saved[i]
+        if m != MODE_IDS['all']:
+            return None
+        if not b.proj:
+            return t['u']
+        x = self.buf('xresp', *t['op'].shape)
+        self.be.bn_hook(None, t['op'], None, b.cp.bn, x, 1, m)
+        return x
+
+    def ebp_backward(self, Pn, W2, mode='affineonly_with_prior', hooked_fc2=False):
+        """W2 [N,2,128]: rows of the wrapper's un-hooked fc1.  Returns (P2 [J,112,112,64], chansum, sums)."""
+        be, S = self.be, self.saved
+        N = S['N']
+        J = Pn.shape[0]
+        assert J % N == 0 and not hooked_fc2
+        m = MODE_IDS[mode]
+        nb = len(self.blocks)
+        last = self.blocks[-1]
+        g = self.buf('g_head', J, 7, 7, last.cout)
+        be.head_bwd_linear(Pn, W2, self.head, S['v'], m, g)
+        t = S[nb - 1]
+        gb = self.buf('g%d' % ((nb - 1) % 2), J, last.hw, last.hw, last.cout)
+        y3 = self.buf('y3', J, last.hw, last.hw, last.cout)
+        be.join(g, 1, None, 1, t['out'], t['o3'], t['xr3'], last.c3.bn, self._xres(nb - 1, m), 1 | 4, m, gb, y3)
+        for i in range(nb - 1, -1, -1):
+            b, t = self.blocks[i], S[i]
+            h = b.hw
+            y2 = self.buf('y2', J, h, h, b.planes)
+            y1 = self.buf('y1', J, h, h, b.planes)
+            be.dgrad_mid(y3, b.c3, t['o2'], t['xr2'], b.c2.bn, m, y2)
+            be.dgrad_mid(y2, b.c2, t['o1'], t['xr1'], b.c1.bn, m, y1)
+            if not b.proj:
+                p, tp = self.blocks[i - 1], S[i - 1]
+                gp = self.buf('g%d' % ((i - 1) % 2), J, h, h, b.cin)
+                y3 = self.buf('y3', J, h, h, b.cin)
+                be.dgrad_join(y1, b.c1, gb, tp['out'], tp['o3'], tp['xr3'], p.c3.bn, self._xres(i - 1, m), 1 | 4, m, gp, y3)
+                gb = gp
+                continue
+            # projection block: both dgrads land on the (sub-sampled) block input
+            zlo = self.buf('zlo', J, h, h, b.cin)
+            be.dgrad_plain(y1, b.c1, zlo)
+            yp = self.buf('yp', J, h, h, b.cout)
+            be.bn_hook(gb, t['op'], t['xrp'], b.cp.bn, yp, 0, m)          # BN backward (gamma+) + BatchNorm hook of proj_bn
+            be.dgrad_plain(yp, b.cp, zlo, accumulate=True)
+            if i == 0:
+                P2 = self.buf('P2', J, 112, 112, 64)
+                chansum = self.buf('chansum', J, 112, 112)
+                sums = self.buf('sums', J, dtype=torch.float64)
+                be.stem_bwd(zlo, None, S['o_s'], S['mp'], self.stem.bn, m, P2, chansum, sums, 0)
+                return P2, chansum, sums
+            p, tp = self.blocks[i - 1], S[i - 1]
+            hp = b.hw_in
+            gp = self.buf('g%d' % ((i - 1) % 2), J, hp, hp, b.cin)
+            y3 = self.buf('y3', J, hp, hp, b.cin)
+            be.join(zlo, b.stride, None, 1, tp['out'], tp['o3'], tp['xr3'], p.c3.bn, self._xres(i - 1, m), 3 | 4, m, gp, y3)
+            gb = gp

@@ -22,18 +22,21 @@ _F = ctypes.c_float
 
 # name -> argtypes, in the order of include/xfrb.h
 _SIGNATURES = {
-    'xfrb_stem_fwd': [_P, _P, _P, _P, _P, _P, _I, _P],
+    'xfrb_stem_fwd': [_P, _P, _P, _P, _P, _P, _I, _I, _P],
     'xfrb_subsample2': [_P, _P, _I, _I, _I, _I, _P],
     'xfrb_avgpool2': [_P, _P, _I, _I, _I, _I, _P],
-    'xfrb_conv_dual': [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'xfrb_conv_dual': [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'xfrb_head_fwd': [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     'xfrb_head_bwd': [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
     'xfrb_dgrad_mid': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
-    'xfrb_dgrad_plain': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    'xfrb_dgrad_plain': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'xfrb_dgrad_join': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     'xfrb_join': [_P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     'xfrb_ds_res': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
-    'xfrb_stem_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
+    'xfrb_stem_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
+    'xfrb_bn_hook': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
+    'xfrb_head_fwd_linear': [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    'xfrb_head_bwd_linear': [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
     'xfrb_contrast': [_P, _P, _P, _P, _I, _I, _I, _P],
     'xfrb_trunc_threshold': [_P, _P, _F, _P, _I, ctypes.c_longlong, _P],
     'xfrb_saliency_post': [_P, _P, _I, _I, _I, _F, _P],
@@ -109,7 +112,7 @@ class CudaBackend(object):
     # -------------------------------------------------------------- forward
     def stem_fwd(self, x, stem, o, mp):
         self._check(self.lib.xfrb_stem_fwd(_ptr(x), _ptr(stem.W), _ptr(stem.b), _ptr(stem.bn), _ptr(o), _ptr(mp),
-                                           x.shape[0], self._st()), 2)
+                                           x.shape[0], stem.pool_pad, self._st()), 2)
 
     def subsample2(self, u, out):
         N, H, W, C = u.shape
@@ -119,11 +122,11 @@ class CudaBackend(object):
         N, H, W, C = u.shape
         self._check(self.lib.xfrb_avgpool2(_ptr(u), _ptr(out), N, H, W, C, self._st()))
 
-    def conv_dual(self, inp, L, o, xr, act, res=None):
+    def conv_dual(self, inp, L, o, xr, act, res=None, relu_act=True):
         N, H, W, Cin = inp.shape
         self._check(self.lib.xfrb_conv_dual(_ptr(inp), _ptr(L.Bf), _ptr(L.bias), _ptr(L.bn), _ptr(res),
                                             0 if res is None else res.shape[-1], _ptr(o), _ptr(xr), _ptr(act),
-                                            N, H, W, Cin, L.cout, L.R, L.tn, self.impl, self._st()))
+                                            N, H, W, Cin, L.cout, L.R, L.tn, 1 if relu_act else 0, self.impl, self._st()))
 
     def head_fwd(self, u, head, v, f1, f1p, xn, nrm):
         N = u.shape[0]
@@ -147,11 +150,11 @@ class CudaBackend(object):
         self._check(self.lib.xfrb_dgrad_mid(_ptr(y), _ptr(L.Bd), _ptr(o), _ptr(xr), _ptr(bn), _ptr(y_out), J,
                                             o.shape[0], H, W, L.cin, Cout, L.R, mode, self.eps, self.impl, self._st()))
 
-    def dgrad_plain(self, y, L, z_out, signed=False):
+    def dgrad_plain(self, y, L, z_out, signed=False, accumulate=False):
         J, H, W, Cout = y.shape
         B = L.signed_dgrad() if signed else L.Bd
-        self._check(self.lib.xfrb_dgrad_plain(_ptr(y), _ptr(B), _ptr(z_out), J, H, W, L.cin, Cout, L.R, self.impl,
-                                              self._st()))
+        self._check(self.lib.xfrb_dgrad_plain(_ptr(y), _ptr(B), _ptr(z_out), J, H, W, L.cin, Cout, L.R,
+                                              1 if accumulate else 0, self.impl, self._st()))
 
     def dgrad_join(self, y1, L, g_res, out, o3, xr3, bn3, res, hooks, mode, g_out, y3_out):
         J, H, W, Cout = y1.shape
@@ -172,11 +175,30 @@ class CudaBackend(object):
         self._check(self.lib.xfrb_ds_res(_ptr(g), _ptr(ap), _ptr(gres_lo), J, ap.shape[0], H, W, C, ap.shape[-1], mode,
                                          self.eps, self._st()))
 
-    def stem_bwd(self, zmain, gres, o, mp, bn, mode, P2, chansum, sums):
+    def stem_bwd(self, zmain, gres, o, mp, bn, mode, P2, chansum, sums, pool_pad=1):
         J = zmain.shape[0]
         zc = self._tmp('stem_zc', J * 56 * 56 * 64)
         self._check(self.lib.xfrb_stem_bwd(_ptr(zmain), _ptr(gres), _ptr(o), _ptr(mp), _ptr(bn), _ptr(zc), _ptr(P2),
-                                           _ptr(chansum), _ptr(sums), J, o.shape[0], mode, self.eps, self._st()), 2)
+                                           _ptr(chansum), _ptr(sums), J, o.shape[0], mode, self.eps, pool_pad, self._st()), 2)
+
+    # -------------------------------------------------------------- VGGFace2 ResNet-50-128d pieces
+    def bn_hook(self, g, o, xr, bn, y, kind, mode):
+        N, H, W, C = o.shape
+        J = N if g is None else g.shape[0]
+        self._check(self.lib.xfrb_bn_hook(_ptr(g), _ptr(o), _ptr(xr), _ptr(bn), _ptr(y), J, N, H * W, C, kind, mode, self.eps,
+                                          self._st()))
+
+    def head_fwd_linear(self, u, head, v, enc):
+        N, C = u.shape[0], u.shape[-1]
+        self._check(self.lib.xfrb_head_fwd_linear(_ptr(u), _ptr(head.Bfe), _ptr(v), _ptr(enc), N, C, head.dim, self.impl,
+                                                  self._st()), 2)
+
+    def head_bwd_linear(self, Pn, W2, head, v, mode, g_out):
+        J, Ccls = Pn.shape
+        N, C = v.shape
+        scratch = self._tmp('head_bwd_lin', J * (head.dim + C))
+        self._check(self.lib.xfrb_head_bwd_linear(_ptr(Pn), _ptr(W2), Ccls, _ptr(head.BfeT), _ptr(v), _ptr(scratch), _ptr(g_out),
+                                                  J, N, C, head.dim, mode, self.eps, self.impl, self._st()), 3)
 
     def contrast(self, P2, sums, N, out, thr=None):
         HW = P2.shape[1] * P2.shape[2]

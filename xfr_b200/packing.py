@@ -131,7 +131,8 @@ class ConvBN(object):
 class Stem(object):
     """7x7/2 conv, Cin=3 (reference resnet.py:177-181).  K = 147 is padded to 148."""
 
-    def __init__(self, sd, conv='conv1', bn='bn1', with_bias=False):
+    def __init__(self, sd, conv='conv1', bn='bn1', with_bias=False, pool_pad=1):
+        self.pool_pad = pool_pad                    # MaxPool2d(3,2,1) for the STR net; (3,2,0,ceil_mode) for VGGFace2
         w = sd[conv + '.weight'].float()            # [64,3,7,7]
         b = sd.get(conv + '.bias')
         b = torch.zeros(w.shape[0]) if b is None else b.float()
@@ -169,4 +170,20 @@ class Head(object):
             v = getattr(self, k)
             if v is not None:
                 setattr(self, k, v.to(device))
+        return self
+
+
+class LinearHead(object):
+    """avgpool7 -> 1x1 conv C->D without bias (VGGFace2 ResNet-50-128d: pool5_7x7_s1 + feat_extract,
+    reference resnet50_128.py:169-170, 345-347)."""
+
+    def __init__(self, sd, name='feat_extract', impl='fp32'):
+        w = sd[name + '.weight'].float()
+        self.dim, self.cin = w.shape[0], w.shape[1]
+        W = w.reshape(self.dim, self.cin)
+        self.Bfe = gemm_planes(W, impl)                                   # [D][C]
+        self.BfeT = gemm_planes(torch.clamp_min(W, 0).t(), impl)          # [C][D]: relu(W)^T, the dgrad operand
+
+    def to(self, device):
+        self.Bfe, self.BfeT = self.Bfe.to(device), self.BfeT.to(device)
         return self

@@ -23,9 +23,9 @@ import torch
 import torch.nn as nn
 
 from . import synth
-from .engine import MODE_IDS, StResnetEngine
+from .engine import MODE_IDS, Resnet50_128Engine, StResnetEngine
 
-_CHUNK = 64     # probes per engine sweep (workspace = ~210 MB per probe)
+_CHUNK = 128    # probes per engine sweep (workspace = ~210 MB per probe)
 
 
 class WhiteboxNetwork(object):
@@ -138,6 +138,58 @@ class WhiteboxSTResnet(WhiteboxNetwork):
         """PIL image -> [1,3,224,224] (whitebox.py:108-110, resnet.py:25-37)."""
         img = np.asarray(im.resize((224, 224)).convert('RGB'), dtype=np.float64) - np.array(synth.MEAN_RGB)
         return torch.from_numpy(np.moveaxis(img, 2, 0)).float().unsqueeze(0)
+
+
+class Whitebox_resnet50_128(WhiteboxSTResnet):
+    """VGGFace2 ResNet-50-128d plugin (reference whitebox.py:210-258): 128-d encoding = feat_extract output, classifier =
+    an un-hooked Linear(128, 2) held by the wrapper (whitebox.py:216-230).  `net` is the reference's
+    resnet50_128.Resnet50_128 module or its state_dict."""
+
+    def __init__(self, net, impl='tf32x3'):
+        if isinstance(net, dict):
+            self._sd = net
+            self.net = _StateDictModule(net)
+        else:
+            self.net = net
+            self.net.eval()
+            self._sd = net.state_dict()
+        self._impl = impl
+        self._engine = None
+        # reference: self.fc1 = nn.Linear(128, 2, bias=False) with default (random) init; here the rows must be set
+        self._W2 = None
+        self._ncls = 2
+
+    def engine(self, with_bias=False):
+        if self._engine is None or self._engine.with_bias != with_bias:
+            from .kernels import CudaBackend
+            dev = self._device()
+            self._engine = Resnet50_128Engine(self._sd, CudaBackend(dev, impl=self._impl), device=dev, with_bias=with_bias)
+        return self._engine
+
+    def encode(self, x):
+        """whitebox.py:222-224: self.net(x)[0], the 128-d feat_extract output (not normalised)."""
+        eng = self.engine()
+        return torch.cat([eng.forward(self._nhwc(x[i:i + _CHUNK])).clone() for i in range(0, x.shape[0], _CHUNK)])
+
+    def classify(self, x):
+        enc = self.encode(x)
+        return torch.einsum('nd,ncd->nc', enc, self.triplet_rows(enc.shape[0]))
+
+    def num_classes(self):
+        return 2
+
+    def preprocess(self, img):
+        """whitebox.py:235-258: shorter side -> 224 (bilinear), centre crop 224, subtract the VGGFace2 mean."""
+        import PIL.Image
+        mean = (131.0912, 103.8827, 91.4953)
+        im_shape = np.array(img.size)
+        img = img.convert('RGB')
+        ratio = 224.0 / np.min(im_shape)
+        img = img.resize(size=(int(np.ceil(im_shape[0] * ratio)), int(np.ceil(im_shape[1] * ratio))), resample=PIL.Image.BILINEAR)
+        x = np.array(img)
+        h0, w0 = (x.shape[0] - 224) // 2, (x.shape[1] - 224) // 2
+        x = x[h0:h0 + 224, w0:w0 + 224] - mean
+        return torch.from_numpy(x.transpose(2, 0, 1).astype(np.float32)).unsqueeze(0)
 
 
 class _StateDictModule(nn.Module):
