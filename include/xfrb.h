@@ -72,9 +72,10 @@ int xfrb_conv_dual(const float* inp, const float* Bf, const float* bias, const f
 
 /* avgpool7 -> fc1 (+ the W+ twin) -> L2 normalise (resnet.py:235-252).
  * B1 = dual pack of fc1 [1024][2048], bias1 [1024] (tile width tn); scratch [N,1024].
- * v [N,2048], f1 [N,512], f1p [N,512] (fc1 with relu(W) on relu(v)), xn [N,512], nrm [N]. */
+ * v [N,2048], f1 [N,512], f1p [N,512] (fc1 with relu(W) on relu(v)), xn [N,512], nrm [N],
+ * xmul [N,512] = relu(normalize(f1p)) (X of the Multiply hook; may be NULL). */
 int xfrb_head_fwd(const float* u, const float* B1, const float* bias1, int tn, float* scratch,
-                  float* v, float* f1, float* f1p, float* xn, float* nrm, int N, int impl, void* stream);
+                  float* v, float* f1, float* f1p, float* xn, float* nrm, float* xmul, int N, int impl, void* stream);
 
 /* ---- backward (the 'ebp' pass + Xn.backward(Pn), whitebox.py:496-498) ---- */
 
@@ -157,6 +158,33 @@ int xfrb_trunc_threshold(const float* P2, const double* sums, float percentile, 
 
 /* skimage.filters.gaussian(sigma=2) -> max(0,.) -> /max(sum,eps)  (whitebox.py:455-460); [B,H,W], H,W <= 128 */
 int xfrb_saliency_post(const float* mwp, float* out, int B, int H, int W, float eps, void* stream);
+
+/* ---- generic single-hook path: priors, P recording, true gradients (whitebox.py:561-737) ---- */
+
+#define XFRB_MODE_NONE 3   /* no hook fires (plain backprop); P_out then records the incoming gradient (self.dA) */
+
+/* One _backward_ebp firing (whitebox.py:381-430) over [J,H,W,C]:
+ *   z = z_in[at stride up, first C of zc channels] + z_in2[/k2, c < c2]/(k2*k2);  z *= pre_scale
+ *   (a, x) from `recipe` over the saved tensors s0 [N,H,W,c0], s1 [N,H,W,C], s2 [N,H,W,c2s] and bn [4][C]
+ *     0: a = x = relu(s0)   1: a = relu(bn(s0)), x = relu(relu(s0)*sp+tp)   2: a = x = relu(bn(s0))
+ *     3: a = relu(s0), x = s1   4: a = relu(s0), x = relu(relu(bn(s1)) + relu(s2))   5: a = relu(s0), x = s1
+ *   p = a*relu(z), replaced for gradient row `prior_row` by the prior (a full tensor `prior` [H*W*C], or the single element
+ *   prior_elem = prior_val); P_out <- p; return value per `mode` (`affine`: Conv/Linear/AvgPool/BatchNorm kinds;
+ *   relu_or_maxpool = 2 marks ReLU/MaxPool kinds for the 'norelu' rule whitebox.py:418-419, passed with mode 1);
+ *   then optionally masked by (a > 0) and scaled by bn[post_scale_row][c] (ReLU / BatchNorm backward); -> z_out. */
+int xfrb_hook(const float* z_in, int up, int zc, const float* z_in2, int k2, int c2, float pre_scale, const float* s0, int c0,
+              const float* s1, const float* s2, int c2s, const float* bn, const float* prior, int prior_row, long long prior_elem,
+              float prior_val, float* P_out, float* z_out, int recipe, int affine, int relu_or_maxpool, int mode, int post_mask,
+              int post_scale_row, int J, int N, int H, int W, int C, float eps, void* stream);
+/* seed[j,:] = Pn[j,:] @ W2[j % N]  (Pn [J,Ccls], W2 [N,Ccls,D]) */
+int xfrb_head_seed(const float* Pn, const float* W2, int Ccls, int D, int J, int N, float* seed, void* stream);
+/* Jacobian of F.normalize (resnet.py:250): gout = (gin - xn*<xn,gin>)/nrm, rows of length D <= 1024 */
+int xfrb_normalize_bwd(const float* gin, const float* xn, const float* nrm, float* gout, int J, int N, int D, void* stream);
+/* MaxPool2d(3,2,pool_pad) backward alone: g [J,56,56,64] -> out [J,112,112,64]; arg-max recomputed from relu(bn(o)) */
+int xfrb_maxpool_bwd(const float* g, const float* o, const float* bn, float* out, int J, int N, int pool_pad, void* stream);
+/* weighted_subtree_ebp layer score (whitebox.py:687-696): max / first argmax over n elements of m*(-gneg),
+ * m = (gate >= 0) if gate_ge0 else (gate < 0) */
+int xfrb_subtree_score(const float* gate, const float* gneg, int gate_ge0, long long n, float* score, long long* arg, void* stream);
 
 #ifdef __cplusplus
 }

@@ -94,7 +94,7 @@ class EmulBackend(object):
             a[:, :rc] += res.reshape(-1, rc)
         act.view(-1, L.cout).copy_(relu(a) if relu_act else a)
 
-    def head_fwd(self, u, head, v, f1, f1p, xn, nrm):
+    def head_fwd(self, u, head, v, f1, f1p, xn, nrm, xmul=None):
         """v = avgpool7(u); (f1 | f1p) = one dual GEMM v @ [W1 ; relu(W1)]^T + (b | b'); xn = f1/|f1|."""
         vv = F.avg_pool2d(u.permute(0, 3, 1, 2), 7, 7).flatten(1)
         ff, fp = unpack_dual_cols(vv @ _w(head.B1).t() + head.bias1, head.tn)
@@ -102,6 +102,8 @@ class EmulBackend(object):
         v.copy_(vv)
         f1.copy_(ff)
         f1p.copy_(fp)
+        if xmul is not None:
+            xmul.copy_(relu(F.normalize(fp, p=2, dim=1)))
         nrm.copy_(nn_)
         xn.copy_(ff / nn_.unsqueeze(1))
 
@@ -218,6 +220,100 @@ class EmulBackend(object):
         a = relu(_rows(ap, J))
         z = hook(False, a, a, g[..., :cr], mode, self.eps)
         gres_lo.copy_(hook(False, a, a, z, mode, self.eps))
+
+    # ------------------------------------------------------------ generic single-hook path
+    def hook(self, z_in, z_out, shape, recipe, affine, mode, s0=None, s1=None, s2=None, bn=None, up=1, zc=None, z_in2=None, k2=1,
+             pre_scale=1.0, prior=None, P_out=None, relu_or_maxpool=0, post_mask=False, post_scale_row=-1, N=None):
+        """One _backward_ebp firing with optional prior / recording (reference whitebox.py:381-430); include/xfrb.h xfrb_hook."""
+        J, H, W, C = shape
+        z = torch.zeros(J, H, W, C)
+        if z_in is not None:
+            z[:, ::up, ::up, :] += z_in.reshape(J, H // up, W // up, -1)[..., :C]
+        if z_in2 is not None:
+            c2 = z_in2.shape[-1]
+            z[..., :c2] += z_in2.reshape(J, H // k2, W // k2, c2).repeat_interleave(k2, 1).repeat_interleave(k2, 2) / float(k2 * k2)
+        z = z * pre_scale
+
+        def src(t, width=C):
+            if t is None:
+                return None
+            t = _rows(t.reshape(t.shape[0], H, W, -1), J)
+            return F.pad(t, (0, width - t.shape[-1])) if t.shape[-1] < width else t
+        v0, v1, v2 = src(s0), src(s1), src(s2)
+        if bn is not None:
+            alpha, beta, sp, tp = bn[0], bn[1], bn[2], bn[3]
+        if recipe == 0:
+            a = x = relu(v0)
+        elif recipe == 1:
+            a = relu(v0 * alpha + beta)
+            x = relu(relu(v0) * sp + tp)
+        elif recipe == 2:
+            a = x = relu(v0 * alpha + beta)
+        elif recipe == 4:
+            a = relu(v0)
+            x = relu(relu(v1 * alpha + beta) + (relu(v2) if v2 is not None else 0))
+        else:
+            a, x = relu(v0), v1
+        if mode == 3:                                    # XFRB_MODE_NONE: true gradient, dA recording
+            if P_out is not None:
+                P_out.copy_(z.view_as(P_out))
+            ret = z
+        else:
+            zh = relu(z)
+            p = a * zh
+            pr = None
+            if prior is not None:
+                row = prior[0]
+                pr = torch.zeros(H * W * C)
+                if len(prior) == 2:
+                    pr = prior[1].reshape(-1).float().clone()
+                else:
+                    pr[prior[1]] = prior[2]
+                pr = pr.view(H, W, C)
+                p = p.clone()
+                p[row] = pr
+            if P_out is not None:
+                P_out.copy_(p.view_as(P_out))
+            quo = p / (x + self.eps)
+            if mode == MODE_ALL:
+                ret = quo
+            elif mode == MODE_AFFINEONLY:
+                ret = quo if affine else z
+            else:
+                ret = quo if affine else zh
+            if pr is not None:
+                ret = ret.clone()
+                if mode == MODE_AWP:
+                    ret[row] = ((pr > 0) * quo[row]) if affine else ((pr > 0) * z[row])
+                if mode == MODE_ALL and relu_or_maxpool == 2:
+                    ret[row] = z[row]
+        if post_mask:
+            ret = ret * (a > 0)
+        if post_scale_row >= 0:
+            ret = ret * bn[post_scale_row]
+        if z_out is not None:
+            z_out.copy_(ret.view_as(z_out))
+
+    def head_seed(self, Pn, W2, seed):
+        seed.copy_(torch.einsum('jc,jcd->jd', Pn, _rows(W2, Pn.shape[0])))
+
+    def normalize_bwd(self, gin, xn, nrm, gout):
+        J = gin.shape[0]
+        x, n = _rows(xn, J), _rows(nrm, J)
+        gout.copy_((gin - x * (x * gin).sum(1, keepdim=True)) / n.unsqueeze(1))
+
+    def maxpool_bwd(self, g, o, bn, out, pool_pad=1):
+        J = g.shape[0]
+        r1 = relu(_rows(o, J) * bn[0] + bn[1]).permute(0, 3, 1, 2)
+        _, idx = F.max_pool2d(r1, 3, 2, pool_pad, ceil_mode=(pool_pad == 0), return_indices=True)
+        zz = torch.zeros_like(r1).flatten(2).scatter_add_(2, idx.flatten(2), g.permute(0, 3, 1, 2).flatten(2))
+        out.copy_(zz.view_as(r1).permute(0, 2, 3, 1))
+
+    def subtree_score(self, gate, gneg, gate_ge0, score, arg):
+        m = (gate >= 0) if gate_ge0 else (gate < 0)
+        v = (m * (-gneg)).flatten()
+        score.fill_(float(v.max()))
+        arg.fill_(int(torch.argmax(v)))
 
     def bn_hook(self, g, o, xr, bn, y, kind, mode):
         """kind 0: BatchNorm backward (gamma+) + BatchNorm hook of a conv output; kind 1: relu(o)*sp + tp."""

@@ -1,0 +1,119 @@
+"""layerwise_ebp / layerwise_contrastive_ebp / weighted_subtree_ebp through the drop-in Whitebox API against the
+reference's outputs (tests/golden).  CPU: the host logic over the kernel emulation; GPU: the CUDA kernels."""
+import numpy as np
+import pytest
+import torch
+
+from emul_backend import EmulBackend
+from helpers import L101, L1111, golden, rel_err
+from xfr_b200 import synth, whitebox
+from xfr_b200.engine import StResnetEngine
+
+SUBTREE = (  # tag, ctor mode, subtree_mode, gating, do_max, ebp_version, classifier scale (1.0 = unit-norm rows)
+    ('ws_demo', 'affineonly_with_prior', 'all', True, False, 5, 1.0 / 2500.0),     # demo/test_whitebox.py:173-199
+    ('ws_eval', 'norelu', 'all', False, False, None, 1.0),                          # generate_whitebox_saliency.py:143
+    ('ws_norelu_max', 'norelu', 'norelu', True, True, None, 1.0 / 2500.0))
+
+
+class _EmulNet(whitebox.WhiteboxSTResnet):
+    """Test double: the same plugin class with the engine built on the torch emulation of the kernels."""
+
+    def _device(self):
+        return torch.device('cpu')
+
+    def engine(self, with_bias=False):
+        if self._engine is None or self._engine.with_bias != with_bias:
+            self._engine = StResnetEngine(self._sd, EmulBackend(), self._layers, with_bias=with_bias)
+        return self._engine
+
+
+def _net(layers, gpu):
+    sd = synth.stresnet_state_dict(0, layers, 2)
+    if gpu:
+        return whitebox.WhiteboxSTResnet({k: v.cuda() for k, v in sd.items()}, layers=layers)
+    return _EmulNet(sd, layers=layers)
+
+
+def _check_subtree(gpu):
+    G = golden(L1111)
+    probe = synth.smooth_probes(3, seed=1)[0:1]
+    xm, xn = torch.from_numpy(G['enc_mate']), torch.from_numpy(G['enc_nonmate'])
+    for tag, ctor_mode, sub_mode, gating, mx, ver, scale in SUBTREE:
+        wb = whitebox.Whitebox(_net(L1111, gpu), ebp_version=ver, ebp_subtree_mode=ctor_mode)
+        a = xm / torch.norm(xm) if scale == 1.0 else scale * xm
+        b = xn / torch.norm(xn) if scale == 1.0 else scale * xn
+        wb.net.set_triplet_classifier(a, b)
+        smap, P_img, P_sub, k_sub = wb.weighted_subtree_ebp(probe, 0, 1, topk=8, verbose=False, do_max_subtree=mx,
+                                                            do_mated_similarity_gating=gating, subtree_mode=sub_mode)
+        assert wb.ebp_subtree_mode() == sub_mode                           # the reference's side effect (whitebox.py:651)
+        assert len(P_img) == len(P_sub) == len(k_sub) == 8
+        # firings chained on one tensor tie exactly; np.argsort may order a tie differently, the maps are the same
+        assert sorted(P_sub) == pytest.approx(sorted(G[tag + '_scores']), rel=1e-3)
+        assert len(set(int(k) for k in k_sub) ^ set(int(k) for k in G[tag + '_k'])) <= 2
+        ref = G[tag + '_smap']
+        if ver is None:
+            assert smap.dtype == np.float32 and rel_err(smap, ref) < 2e-3
+        else:
+            d = np.abs(smap.astype(int) - ref.astype(int))          # 8-bit quantisation edges: a 1e-5 change can move a pixel
+            assert smap.dtype == np.uint8 and int((d > 2).sum()) <= 5 and d.max() <= 16
+
+
+def _check_layerwise(layers, gpu, tol):
+    G = golden(layers)
+    probe = synth.smooth_probes(3, seed=1)[0:1]
+    xm, xn = torch.from_numpy(G['enc_mate']), torch.from_numpy(G['enc_nonmate'])
+    for mode, tag in (('affineonly_with_prior', 'awp'), ('all', 'all'), ('norelu', 'norelu')):
+        wb = whitebox.Whitebox(_net(layers, gpu), ebp_subtree_mode=mode)
+        wb.net.set_triplet_classifier(xm / 2500.0, xn / 2500.0)
+        ks = list(zip(G['lw_k'], G['lw_el_%s' % tag]))
+        for i, (k, e) in list(enumerate(ks))[::(1 if layers == L1111 else 4)]:
+            got = wb.layerwise_ebp(probe, k_layer=int(k), k_element=int(e), mode='elementwise', k_poschannel=0, mwp=True)
+            assert got.shape == (112, 112)
+            assert rel_err(got, G['lw_%s' % tag][i]) < tol, (mode, k)
+        assert len(wb.P) == len(G['P_kinds']) and wb.P_layername == [str(s) for s in G['P_kinds']]
+        assert tuple(wb.P[3].shape[1:]) == (2048, 7, 7)                     # self.P entries look like the reference's [1,C,H,W]
+
+
+def test_weighted_subtree_emulated():
+    _check_subtree(False)
+
+
+def test_layerwise_emulated():
+    _check_layerwise(L1111, False, 2e-5)
+
+
+def test_layerwise_contrastive_modes_emulated():
+    """Every mode of the deprecated layerwise_contrastive_ebp runs and obeys its definition (whitebox.py:606-642):
+    'copy' with the contrastive difference of the LAST-but-one firing as prior reproduces... itself at that firing."""
+    wb = whitebox.Whitebox(_net(L1111, False))
+    G = golden(L1111)
+    wb.net.set_triplet_classifier(torch.from_numpy(G['enc_mate']) / 2500.0, torch.from_numpy(G['enc_nonmate']) / 2500.0)
+    probe = synth.smooth_probes(3, seed=1)[0:1]
+    k = 7        # (unnormalised non-mate MWPs dominate the mate ones below firing 8 on this synthetic triplet)
+    with pytest.warns(UserWarning):
+        base = wb.layerwise_contrastive_ebp(probe, 0, 1, k_layer=k, mode='copy', mwp=True)
+    assert base.shape == (112, 112) and np.isfinite(base).all() and base.max() > 0
+    prior_copy = wb.P[k].clone()
+    for mode in ('mean', 'product', 'argmax', 'argmax_product', 'percentile', 'percentile_argmax'):
+        with pytest.warns(UserWarning):
+            m = wb.layerwise_contrastive_ebp(probe, 0, 1, k_layer=k, mode=mode, percentile=20, mwp=True)
+        assert np.isfinite(m).all()
+        if 'argmax' in mode:
+            assert int((wb.P[k] > 0).sum()) <= 2                            # a single (tied) node seeds the sub-tree
+    with pytest.warns(UserWarning):
+        pm = wb.layerwise_contrastive_ebp(probe, 0, 1, k_layer=k, mode='percentile', percentile=0, mwp=True)
+    assert rel_err(pm, base) < 1e-6                                         # percentile 0 keeps everything == 'copy'
+    assert torch.equal(wb.P[k], prior_copy)
+    with pytest.raises(ValueError):
+        wb.layerwise_contrastive_ebp(probe, 0, 1, k_layer=k, mode='nope')
+
+
+@pytest.mark.gpu
+def test_weighted_subtree_gpu():
+    _check_subtree(True)
+
+
+@pytest.mark.gpu
+def test_layerwise_gpu():
+    _check_layerwise(L1111, True, 2e-3)
+    _check_layerwise(L101, True, 2e-2)

@@ -16,11 +16,14 @@ void set_error(const char* what, cudaError_t e) {
 cudaError_t launch_stem_fwd(const float*, const float*, const float*, const float*, float*, float*, int, int, cudaStream_t);
 cudaError_t launch_bn_hook(const float*, const float*, const float*, const float*, float*, size_t, size_t, int, int, int, float,
                            cudaStream_t);
+cudaError_t launch_normalize_bwd(const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
+cudaError_t launch_maxpool_bwd(const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
+cudaError_t launch_subtree_score(const float*, const float*, int, size_t, float*, long long*, cudaStream_t);
 cudaError_t launch_head_seed(const float*, const float*, int, int, int, int, float*, cudaStream_t);
 cudaError_t launch_subsample2(const float*, float*, int, int, int, int, cudaStream_t);
 cudaError_t launch_avgpool2(const float*, float*, int, int, int, int, cudaStream_t);
 cudaError_t launch_avgpool7(const float*, float*, int, int, cudaStream_t);
-cudaError_t launch_head_norm(const float*, int, float*, float*, float*, float*, int, cudaStream_t);
+cudaError_t launch_head_norm(const float*, int, float*, float*, float*, float*, float*, int, cudaStream_t);
 cudaError_t launch_head_bwd_a(const float*, const float*, int, const float*, const float*, const float*, float*, int, int,
                               int, float, cudaStream_t);
 cudaError_t launch_head_bwd_b(const float*, const float*, float*, int, int, int, int, float, cudaStream_t);
@@ -104,7 +107,7 @@ int xfrb_conv_dual(const float* inp, const float* Bf, const float* bias, const f
 }
 
 int xfrb_head_fwd(const float* u, const float* B1, const float* bias1, int tn, float* scratch, float* v, float* f1, float* f1p,
-                  float* xn, float* nrm, int N, int impl, void* stream) {
+                  float* xn, float* nrm, float* xmul, int N, int impl, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = launch_avgpool7(u, v, N, 2048, st);
     if (e != cudaSuccess) return finish("xfrb_head_fwd/avgpool", e);
@@ -118,7 +121,7 @@ int xfrb_head_fwd(const float* u, const float* B1, const float* bias1, int tn, f
     ep.out0 = scratch;
     e = run_gemm(v, B1, g, ep, impl, st, tn);
     if (e != cudaSuccess) return finish("xfrb_head_fwd/fc1", e);
-    return finish("xfrb_head_fwd/norm", launch_head_norm(scratch, tn, f1, f1p, xn, nrm, N, st));
+    return finish("xfrb_head_fwd/norm", launch_head_norm(scratch, tn, f1, f1p, xn, nrm, xmul, N, st));
 }
 
 int xfrb_head_bwd(const float* Pn, const float* W2, int C, const float* W1pT, const float* v, const float* f1p, const float* xn,
@@ -212,6 +215,37 @@ int xfrb_bn_hook(const float* g, const float* o, const float* xr, const float* b
     if (C % 4) return finish("xfrb_bn_hook", cudaErrorInvalidValue);
     return finish("xfrb_bn_hook", launch_bn_hook(g, o, xr, bn, y, (size_t)(kind == 1 ? N : J) * HW, (size_t)N * HW, C, kind, mode, eps,
                                                  (cudaStream_t)stream));
+}
+
+int xfrb_hook(const float* z_in, int up, int zc, const float* z_in2, int k2, int c2, float pre_scale, const float* s0, int c0,
+              const float* s1, const float* s2, int c2s, const float* bn, const float* prior, int prior_row, long long prior_elem,
+              float prior_val, float* P_out, float* z_out, int recipe, int affine, int relu_or_maxpool, int mode, int post_mask,
+              int post_scale_row, int J, int N, int H, int W, int C, float eps, void* stream) {
+    if (up < 1 || k2 < 1 || recipe < 0 || recipe > 5) return finish("xfrb_hook", cudaErrorInvalidValue);
+    HookArgs a;
+    a.z_in = z_in; a.up = up; a.zc = zc; a.z_in2 = z_in2; a.k2 = k2; a.c2 = c2; a.pre_scale = pre_scale;
+    a.s0 = s0; a.s1 = s1; a.s2 = s2; a.c0 = c0; a.c2s = c2s; a.bn = bn; a.prior = prior; a.P_out = P_out; a.z_out = z_out;
+    a.recipe = recipe; a.affine = affine; a.relu_or_maxpool = relu_or_maxpool; a.mode = mode; a.post_mask = post_mask;
+    a.post_scale_row = post_scale_row; a.J = J; a.N = N; a.H = H; a.W = W; a.C = C; a.eps = eps;
+    a.prior_row = prior_row; a.prior_elem = prior_elem; a.prior_val = prior_val;
+    return finish("xfrb_hook", launch_hook(a, (cudaStream_t)stream));
+}
+
+int xfrb_head_seed(const float* Pn, const float* W2, int Ccls, int D, int J, int N, float* seed, void* stream) {
+    return finish("xfrb_head_seed", launch_head_seed(Pn, W2, Ccls, D, J, N, seed, (cudaStream_t)stream));
+}
+
+int xfrb_normalize_bwd(const float* gin, const float* xn, const float* nrm, float* gout, int J, int N, int D, void* stream) {
+    if (D > 1024) return finish("xfrb_normalize_bwd", cudaErrorInvalidValue);
+    return finish("xfrb_normalize_bwd", launch_normalize_bwd(gin, xn, nrm, gout, J, N, D, (cudaStream_t)stream));
+}
+
+int xfrb_maxpool_bwd(const float* g, const float* o, const float* bn, float* out, int J, int N, int pool_pad, void* stream) {
+    return finish("xfrb_maxpool_bwd", launch_maxpool_bwd(g, o, bn, out, J, N, pool_pad, (cudaStream_t)stream));
+}
+
+int xfrb_subtree_score(const float* gate, const float* gneg, int gate_ge0, long long n, float* score, long long* arg, void* stream) {
+    return finish("xfrb_subtree_score", launch_subtree_score(gate, gneg, gate_ge0, (size_t)n, score, arg, (cudaStream_t)stream));
 }
 
 int xfrb_head_fwd_linear(const float* u, const float* Bfe, float* v, float* enc, int N, int C, int D, int impl, void* stream) {

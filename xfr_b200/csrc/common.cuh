@@ -7,6 +7,7 @@
 #define XFRB_MODE_AWP 0
 #define XFRB_MODE_ALL 1
 #define XFRB_MODE_AFFINEONLY 2
+#define XFRB_MODE_NONE 3        /* no hook fires: plain (true-gradient) backprop; used by weighted_subtree_ebp */
 
 namespace xfrb {
 
@@ -18,6 +19,7 @@ __device__ __forceinline__ float relu(float v) { return fmaxf(v, 0.f); }
 // One hook firing: zh = relu(z); p = a*zh; return p/(x+eps) | zh | z  depending on mode/kind.
 template <bool AFFINE>
 __device__ __forceinline__ float hook(float a, float x, float z, int mode, float eps) {
+    if (mode == XFRB_MODE_NONE) return z;
     float zh = fmaxf(z, 0.f);
     // p/(x+eps): x + eps >= 1e-16 is a normal positive float, so the 2-ulp reciprocal path (MUFU.RCP + FMUL) is safe;
     // an IEEE division costs ~10 issue slots per hook and the epilogues are issue-bound (profiles/r1_notes.md).
@@ -169,6 +171,25 @@ struct ConvGeom {
     int K;           // R*R*Cin
     int Nn;          // GEMM N (rows of B)
 };
+
+// arguments of the generic single-hook kernel (xfrb_hook): one _backward_ebp firing with optional prior and P recording
+struct HookArgs {
+    const float* z_in;  int up;            // incoming gradient [J,H/up,W/up,zc]; lands on pixels divisible by `up`
+    int zc;                                // channels of z_in (>= C: only the first C are read; ConcatChannels slice)
+    const float* z_in2; int k2, c2;        // optional addend [J,H/k2,W/k2,c2], replicated over k2 x k2 and divided (AvgPool bwd)
+    float pre_scale;                       // z *= pre_scale before the hook (Multiply backward)
+    const float* s0; const float* s1; const float* s2;   // recipe sources (saved tensors, sample = j % N)
+    int c0, c2s;                           // channel counts of s0 / s2 when narrower than C (zero beyond)
+    const float* bn;                       // [4][C] of the recipe's BatchNorm
+    const float* prior;                    // full prior tensor of row prior_row ([H*W*C]) or null
+    float* P_out;                          // records p (or, in MODE_NONE, the incoming gradient) [J,H,W,C]; may be null
+    float* z_out;                          // hook return value after the post ops [J,H,W,C]; may be null
+    int recipe, affine, relu_or_maxpool, mode, post_mask, post_scale_row;
+    int J, N, H, W, C;
+    float eps;
+    int prior_row; long long prior_elem; float prior_val;   // one-element prior (layerwise 'elementwise'); prior_row < 0: none
+};
+cudaError_t launch_hook(const HookArgs& a, cudaStream_t st);
 
 // arguments of the unfused block-boundary kernel (xfrb_join)
 struct JoinArgs {

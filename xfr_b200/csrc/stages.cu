@@ -160,8 +160,10 @@ __global__ void avgpool7_kernel(const float* __restrict__ u, float* __restrict__
 
 // scratch [N, 1024] (dual tile order, bias already added) -> f1, f1p, nrm, xn.   512 threads per row.
 __global__ void __launch_bounds__(512) head_norm_kernel(const float* __restrict__ scratch, int tn, float* __restrict__ f1,
-                                                        float* __restrict__ f1p, float* __restrict__ xn, float* __restrict__ nrm) {
+                                                        float* __restrict__ f1p, float* __restrict__ xn, float* __restrict__ nrm,
+                                                        float* __restrict__ xmul) {
     __shared__ float red[16];
+    __shared__ float red2[16];
     const int n = blockIdx.x, c = threadIdx.x;
     const int half = tn / 2;
     const int t = c / half, j = c % half;
@@ -169,15 +171,17 @@ __global__ void __launch_bounds__(512) head_norm_kernel(const float* __restrict_
     float p = scratch[(size_t)n * 1024 + t * tn + half + j];
     f1[(size_t)n * 512 + c] = a;
     f1p[(size_t)n * 512 + c] = p;
-    float s = a * a;
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((c & 31) == 0) red[c >> 5] = s;
+    float s = a * a, s2 = p * p;
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if ((c & 31) == 0) { red[c >> 5] = s; red2[c >> 5] = s2; }
     __syncthreads();
-    float tot = 0.f;
-    for (int i = 0; i < 16; ++i) tot += red[i];
+    float tot = 0.f, tot2 = 0.f;
+    for (int i = 0; i < 16; ++i) { tot += red[i]; tot2 += red2[i]; }
     float nn = fmaxf(sqrtf(tot), 1e-12f);      // F.normalize eps (resnet.py:250)
     if (c == 0) nrm[n] = nn;
     xn[(size_t)n * 512 + c] = __fdiv_rn(a, nn);
+    // X of the Multiply hook: relu(normalize(fc1 with relu(W) on relu(v)))  (positive pass, whitebox.py:327)
+    if (xmul != nullptr) xmul[(size_t)n * 512 + c] = fmaxf(__fdiv_rn(p, fmaxf(sqrtf(tot2), 1e-12f)), 0.f);
 }
 
 cudaError_t launch_avgpool7(const float* u, float* v, int N, int C, cudaStream_t st) {
@@ -185,8 +189,9 @@ cudaError_t launch_avgpool7(const float* u, float* v, int N, int C, cudaStream_t
     avgpool7_kernel<<<(total4 + 255) / 256, 256, 0, st>>>(u, v, C / 4, total4);
     return cudaGetLastError();
 }
-cudaError_t launch_head_norm(const float* scratch, int tn, float* f1, float* f1p, float* xn, float* nrm, int N, cudaStream_t st) {
-    head_norm_kernel<<<N, 512, 0, st>>>(scratch, tn, f1, f1p, xn, nrm);
+cudaError_t launch_head_norm(const float* scratch, int tn, float* f1, float* f1p, float* xn, float* nrm, float* xmul, int N,
+                             cudaStream_t st) {
+    head_norm_kernel<<<N, 512, 0, st>>>(scratch, tn, f1, f1p, xn, nrm, xmul);
     return cudaGetLastError();
 }
 
@@ -500,6 +505,187 @@ __global__ void head_seed_kernel(const float* __restrict__ Pn, const float* __re
 
 cudaError_t launch_head_seed(const float* Pn, const float* W2, int C, int D, int J, int N, float* seed, cudaStream_t st) {
     head_seed_kernel<<<J, 128, 0, st>>>(Pn, W2, C, D, N, seed);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ generic single hook (priors, P recording, true gradients)
+// One _backward_ebp firing (whitebox.py:381-430) as its own kernel: used by layerwise_ebp / layerwise_contrastive_ebp /
+// weighted_subtree_ebp, where a prior may replace p at one firing (whitebox.py:390-392, 570-577), every p is recorded
+// (self.P) and true gradients are needed (self.dA, whitebox.py:353-358).  (a, x) come from a recipe over saved tensors:
+//   0: a = x = relu(s0)                                   (block outputs / inputs, pooled tensors, vectors)
+//   1: a = relu(bn(s0)), x = relu(relu(s0)*sp + tp)       (ReLU hook at an inner activation)
+//   2: a = x = relu(bn(s0))                               (consumer Conv2d / MaxPool2d hook at an inner activation)
+//   3: a = relu(s0), x = s1                               (BatchNorm hook: s0 = o, s1 = xr)
+//   4: a = relu(s0), x = relu(relu(bn(s1)) + relu(s2))    (STR block ReLU hook: s0 = out, s1 = o3, s2 = residual)
+//   5: a = relu(s0), x = s1                               (materialised pair, e.g. the Multiply hook)
+__global__ void hook_kernel(HookArgs A, size_t total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % A.C);
+    size_t p = i / A.C;
+    const int w = (int)(p % A.W); p /= A.W;
+    const int h = (int)(p % A.H);
+    const int j = (int)(p / A.H);
+    const int n = j % A.N;
+    const size_t ms = ((size_t)n * A.H + h) * A.W + w;
+    float z = 0.f;
+    if (A.z_in != nullptr && h % A.up == 0 && w % A.up == 0) {
+        const int Hm = A.H / A.up, Wm = A.W / A.up;
+        z = A.z_in[(((size_t)j * Hm + h / A.up) * Wm + w / A.up) * A.zc + c];
+    }
+    if (A.z_in2 != nullptr && c < A.c2) {
+        const int Hr = A.H / A.k2, Wr = A.W / A.k2;
+        z = __fadd_rn(z, __fdiv_rn(A.z_in2[(((size_t)j * Hr + h / A.k2) * Wr + w / A.k2) * A.c2 + c], (float)(A.k2 * A.k2)));
+    }
+    z = __fmul_rn(z, A.pre_scale);
+    float a = 0.f, x = 0.f;
+    BnC b = {0.f, 0.f, 0.f, 0.f};
+    if (A.bn != nullptr) b = {A.bn[c], A.bn[A.C + c], A.bn[2 * A.C + c], A.bn[3 * A.C + c]};
+    const float v0 = (A.s0 != nullptr && c < A.c0) ? A.s0[ms * A.c0 + c] : 0.f;
+    switch (A.recipe) {
+        case 0: a = x = fmaxf(v0, 0.f); break;
+        case 1: a = bn_act(v0, b); x = fmaxf(__fadd_rn(__fmul_rn(fmaxf(v0, 0.f), b.sp), b.tp), 0.f); break;
+        case 2: a = x = bn_act(v0, b); break;
+        case 3: a = fmaxf(v0, 0.f); x = A.s1[ms * A.C + c]; break;
+        case 4: {
+            a = fmaxf(v0, 0.f);
+            float r = (A.s2 != nullptr && c < A.c2s) ? fmaxf(A.s2[ms * A.c2s + c], 0.f) : 0.f;
+            x = fmaxf(__fadd_rn(bn_act(A.s1[ms * A.C + c], b), r), 0.f);
+            break;
+        }
+        default: a = fmaxf(v0, 0.f); x = A.s1[ms * A.C + c]; break;
+    }
+    const size_t off = i;
+    float ret;
+    if (A.mode == XFRB_MODE_NONE) {
+        if (A.P_out != nullptr) A.P_out[off] = z;          // dA: the true gradient at this hooked tensor
+        ret = z;
+    } else {
+        const float zh = fmaxf(z, 0.f);
+        float pv = __fmul_rn(a, zh);
+        const bool has_prior = (j == A.prior_row);
+        float pr = 0.f;
+        if (has_prior) {
+            const size_t e = ((size_t)h * A.W + w) * A.C + c;
+            pr = A.prior != nullptr ? A.prior[e] : ((long long)e == A.prior_elem ? A.prior_val : 0.f);
+            pv = pr;                                           // p.data.copy_(p_prior)
+        }
+        if (A.P_out != nullptr) A.P_out[off] = pv;
+        const float quo = __fdividef(pv, __fadd_rn(x, A.eps));
+        if (A.mode == XFRB_MODE_ALL) ret = quo;
+        else if (A.mode == XFRB_MODE_AFFINEONLY) ret = A.affine ? quo : z;
+        else if (A.mode == XFRB_MODE_AWP) {
+            if (has_prior) ret = A.affine ? (pr > 0.f ? quo : 0.f) : (pr > 0.f ? z : 0.f);
+            else ret = A.affine ? quo : zh;
+        } else ret = z;
+        if (A.mode == XFRB_MODE_ALL && has_prior && A.relu_or_maxpool == 2) ret = z;    // 'norelu' (mode id ALL + flag 2)
+    }
+    if (A.post_mask) ret = a > 0.f ? ret : 0.f;
+    if (A.post_scale_row >= 0) ret = __fmul_rn(ret, A.bn[A.post_scale_row * A.C + c]);
+    if (A.z_out != nullptr) A.z_out[off] = ret;
+}
+
+cudaError_t launch_hook(const HookArgs& a, cudaStream_t st) {
+    size_t total = (size_t)a.J * a.H * a.W * a.C;
+    hook_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, total);
+    return cudaGetLastError();
+}
+
+// g = (g - xn*<xn,g>)/nrm per row: the Jacobian of F.normalize (resnet.py:250).  One block per row, D <= 1024.
+__global__ void normalize_bwd_kernel(const float* __restrict__ gin, const float* __restrict__ xn, const float* __restrict__ nrm,
+                                     float* __restrict__ gout, int N, int D) {
+    __shared__ float red[32];
+    __shared__ float bc;
+    const int j = blockIdx.x, n = j % N, d = threadIdx.x;
+    float x = d < D ? xn[(size_t)n * D + d] : 0.f, g = d < D ? gin[(size_t)j * D + d] : 0.f;
+    float s = x * g;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((d & 31) == 0) red[d >> 5] = s;
+    __syncthreads();
+    if (d == 0) {
+        float t = 0.f;
+        for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) t += red[i];
+        bc = t;
+    }
+    __syncthreads();
+    if (d < D) gout[(size_t)j * D + d] = __fdiv_rn(g - x * bc, nrm[n]);
+}
+cudaError_t launch_normalize_bwd(const float* gin, const float* xn, const float* nrm, float* gout, int J, int N, int D, cudaStream_t st) {
+    normalize_bwd_kernel<<<J, ((D + 31) / 32) * 32, 0, st>>>(gin, xn, nrm, gout, N, D);
+    return cudaGetLastError();
+}
+
+// MaxPool2d(3,2,pad) backward alone (gather form, first maximum wins): g [J,56,56,64] -> out [J,112,112,64]; r1 = relu(bn(o))
+__global__ void maxpool_bwd_kernel(const float* __restrict__ g, const float* __restrict__ o, const float* __restrict__ bn,
+                                   float* __restrict__ out, int N, int pad, size_t total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i & 63);
+    size_t p = i >> 6;
+    const int w = (int)(p % 112); p /= 112;
+    const int h = (int)(p % 112);
+    const int j = (int)(p / 112), n = j % N;
+    const float al = bn[c], be = bn[64 + c];
+    const float* ob = o + (size_t)n * 112 * 112 * 64 + c;
+    const float me = fmaxf(__fadd_rn(__fmul_rn(ob[((size_t)h * 112 + w) * 64], al), be), 0.f);
+    float z = 0.f;
+    for (int a = 0; a < 2; ++a) {
+        int ph = (h + pad) / 2 - a;
+        if (ph < 0 || ph >= 56 || 2 * ph - pad > h || h > 2 * ph - pad + 2) continue;
+        for (int b2 = 0; b2 < 2; ++b2) {
+            int pw = (w + pad) / 2 - b2;
+            if (pw < 0 || pw >= 56 || 2 * pw - pad > w || w > 2 * pw - pad + 2) continue;
+            bool win = true;
+            const int my = h - (2 * ph - pad), mx = w - (2 * pw - pad);
+            for (int r = 0; r < 3; ++r)
+                for (int s2 = 0; s2 < 3; ++s2) {
+                    int hh = 2 * ph - pad + r, ww = 2 * pw - pad + s2;
+                    if ((r == my && s2 == mx) || hh < 0 || hh >= 112 || ww < 0 || ww >= 112) continue;
+                    float rv = fmaxf(__fadd_rn(__fmul_rn(ob[((size_t)hh * 112 + ww) * 64], al), be), 0.f);
+                    bool before = (r < my) || (r == my && s2 < mx);
+                    win = win && (before ? (rv < me) : (rv <= me));
+                }
+            if (win) z = __fadd_rn(z, g[(((size_t)j * 56 + ph) * 56 + pw) * 64 + c]);
+        }
+    }
+    out[i] = z;
+}
+cudaError_t launch_maxpool_bwd(const float* g, const float* o, const float* bn, float* out, int J, int N, int pad, cudaStream_t st) {
+    size_t total = (size_t)J * 112 * 112 * 64;
+    maxpool_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, o, bn, out, N, pad, total);
+    return cudaGetLastError();
+}
+
+// per firing: score = max_e m(e) * (-gn[e]), arg = first argmax; m = (gm >= 0) (mated-similarity gating) or (gce < 0)
+// (whitebox.py:687-696).  One block per (firing, row); n elements.
+__global__ void __launch_bounds__(1024) subtree_score_kernel(const float* __restrict__ gate, const float* __restrict__ gneg, int gate_ge0,
+                                                             size_t n, float* __restrict__ score, long long* __restrict__ arg) {
+    __shared__ float sv[32];
+    __shared__ long long si[32];
+    float best = -INFINITY;
+    long long bi = 0x7fffffffffffffffLL;
+    for (size_t e = threadIdx.x; e < n; e += blockDim.x) {
+        const float m = gate_ge0 ? (gate[e] >= 0.f ? 1.f : 0.f) : (gate[e] < 0.f ? 1.f : 0.f);
+        const float v = __fmul_rn(m, -gneg[e]);
+        if (v > best || (v == best && (long long)e < bi)) { best = v; bi = (long long)e; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k)
+            if (sv[k] > best || (sv[k] == best && si[k] < bi)) { best = sv[k]; bi = si[k]; }
+        *score = best;
+        *arg = bi;
+    }
+}
+cudaError_t launch_subtree_score(const float* gate, const float* gneg, int gate_ge0, size_t n, float* score, long long* arg,
+                                 cudaStream_t st) {
+    subtree_score_kernel<<<1, 1024, 0, st>>>(gate, gneg, gate_ge0, n, score, arg);
     return cudaGetLastError();
 }
 

@@ -179,7 +179,8 @@ class StResnetEngine(_Engine):
         S['f1p'] = self.buf('f1p', N, 512)
         S['xn'] = self.buf('xn', N, 512)
         S['nrm'] = self.buf('nrm', N)
-        be.head_fwd(u, self.head, S['v'], S['f1'], S['f1p'], S['xn'], S['nrm'])
+        S['xmul'] = self.buf('xmul', N, 512)
+        be.head_fwd(u, self.head, S['v'], S['f1'], S['f1p'], S['xn'], S['nrm'], S['xmul'])
         self.saved = S
         return S['xn']
 

@@ -1,0 +1,135 @@
+"""Generic (one kernel per hook firing) backward sweep of the STR ResNet, for the parts of the reference API that need
+what the fused sweep never materialises: the MWP of EVERY firing (`Whitebox.P`, indexed by hook-firing order = the
+`k_layer` of reference whitebox.py:561-737), a prior that overrides p at one firing (whitebox.py:390-392), and the
+TRUE gradient at every hooked tensor (`self.dA`, whitebox.py:353-358, used by weighted_subtree_ebp).
+
+The schedule below is the firing order of SURVEY.md appendix A (validated against the reference hook for hook); every
+firing is one launch of the `xfrb_hook` kernel, convolutions are `xfrb_dgrad_plain` GEMMs.  Gradient rows may carry
+different priors: row j's prior sits at firing k_j, which is how weighted_subtree_ebp batches its per-layer sub-trees.
+"""
+import torch
+
+from .engine import MODE_IDS
+
+AFFINE = ('Conv', 'Linear', 'AvgPool', 'BatchNorm')       # substring test of reference whitebox.py:399,409
+MODE_NONE = 3
+
+
+class _FC(object):
+    """fc1 seen as a 1x1 'conv' by dgrad_plain."""
+
+    def __init__(self, B, cin):
+        self.Bd, self.cin, self.R = B, cin, 1
+
+    def signed_dgrad(self):
+        return self.Bd
+
+
+class GenericSweep(object):
+    def __init__(self, engine):
+        self.eng = engine
+        self.be = engine.be
+
+    # -------------------------------------------------------------------------------------------------
+    def run(self, Pn, W2, mode, priors=None, record=False, true_grad=False):
+        """One sweep over J = Pn.shape[0] gradient rows.
+        priors: {firing k: (row, elem, value) | (row, tensor)}; record: keep p of every firing (list of [J,H,W,C]
+        device tensors, NHWC; entry -1, the Conv2d hook on the image, is None: nothing reads it);
+        true_grad: no hooks, signed weights, true BatchNorm backward; the recorded tensors are then the gradients dA.
+        Returns (P list or None, names, P2 [J,112,112,64] = P[-2])."""
+        eng, be, S = self.eng, self.be, self.eng.saved
+        N, J = S['N'], Pn.shape[0]
+        self._k = 0
+        self._P = [] if record else None
+        self._names = []
+        self._priors = priors or {}
+        self._norelu = (mode == 'norelu')
+        m = MODE_NONE if true_grad else MODE_IDS[mode]
+        self._m = m
+        srow = 0 if true_grad else 2                     # BatchNorm backward: gamma/sigma (true) or gamma+/sigma
+        buf = eng.buf
+        head = eng.head
+
+        def dgrad(y, L, out):
+            be.dgrad_plain(y, L, out, signed=true_grad)
+            return out
+
+        # ---- head: fc2 (un-hooked triplet rows) -> x50 -> Multiply hook -> normalize' -> fc1 -> Linear hook -> AvgPool'
+        seed = buf('gs_seed', J, 1, 1, 512)
+        be.head_seed(Pn, W2, seed.view(J, 512))
+        z = self.fire('Multiply', 5, seed, (J, 1, 1, 512), s0=S['xn'], s1=S['xmul'], pre_scale=50.0, out='gs_mul')
+        zn = buf('gs_nb', J, 1, 1, 512)
+        be.normalize_bwd(z.view(J, 512), S['xn'], S['nrm'], zn.view(J, 512))
+        W1 = head.W1T_signed() if true_grad else head.W1pT
+        z = dgrad(zn, _FC(W1, 2048), buf('gs_fc1', J, 1, 1, 2048))
+        z = self.fire('Linear', 0, z, (J, 1, 1, 2048), s0=S['v'], out='gs_lin')
+        nb = len(eng.blocks)
+        last = eng.blocks[-1]
+        # AvgPool2d(7) backward rides on the first hook of the last block (z_in2 with k2 = 7)
+        zin, zin_up, zin2, k2 = None, 1, z, 7
+        for i in range(nb - 1, -1, -1):
+            b, t = eng.blocks[i], S[i]
+            h, C = b.hw, b.cout
+            shp = (J, h, h, C)
+            nxt = eng.blocks[i + 1] if i + 1 < nb else None
+            res = t['res']
+            z = self.fire('ReLU', 4, zin, shp, s0=t['out'], s1=t['o3'], s2=res, bn=b.c3.bn, up=zin_up, z_in2=zin2, k2=k2, out='gs_a')
+            if nxt is None:
+                z = self.fire('AvgPool2d', 0, z, shp, s0=t['out'], post_mask=True, out='gs_g%d' % (i % 2))
+            else:
+                z = self.fire('Conv2d', 0, z, shp, s0=t['out'], out='gs_b')
+                z = self.fire('AvgPool2d' if nxt.has_ds else 'Add', 0, z, shp, s0=t['out'], post_mask=True, out='gs_g%d' % (i % 2))
+            g = z                                                            # gradient at the block output after ReLU backward
+            gres, gres_k = g, 1
+            if b.has_ds:
+                Cr = b.cin
+                zr = self.fire('Add', 0, g, shp, s0=res, out='gs_r1')            # slot 1 (residual) fires first
+                gres = self.fire('ConcatChannels', 0, zr, (J, h, h, Cr), s0=t['ap'], zc=C, out='gs_r2')
+                gres_k = b.stride
+            z = self.fire('Add', 0, g, shp, s0=res, post_scale_row=srow, bn=b.c3.bn, out='gs_a')   # slot 0: residual's (A, X)
+            y3 = self.fire('BatchNorm2d', 3, z, shp, s0=t['o3'], s1=t['xr3'], out='gs_y3')
+            z = dgrad(y3, b.c3, buf('gs_z2', J, h, h, b.planes))
+            shp2 = (J, h, h, b.planes)
+            z = self.fire('ReLU', 1, z, shp2, s0=t['o2'], bn=b.c2.bn, out='gs_c')
+            z = self.fire('Conv2d', 2, z, shp2, s0=t['o2'], bn=b.c2.bn, post_mask=True, post_scale_row=srow, out='gs_d')
+            y2 = self.fire('BatchNorm2d', 3, z, shp2, s0=t['o2'], s1=t['xr2'], out='gs_y2')
+            z = dgrad(y2, b.c2, buf('gs_z1', J, h, h, b.planes))
+            z = self.fire('ReLU', 1, z, shp2, s0=t['o1'], bn=b.c1.bn, out='gs_c')
+            z = self.fire('Conv2d', 2, z, shp2, s0=t['o1'], bn=b.c1.bn, post_mask=True, post_scale_row=srow, out='gs_d')
+            y1 = self.fire('BatchNorm2d', 3, z, shp2, s0=t['o1'], s1=t['xr1'], out='gs_y1')
+            zlo = dgrad(y1, b.c1, buf('gs_zlo', J, h, h, b.cin))
+            # the sum g_main + g_res is taken by the next firing: z_in (stride-2 scatter) + z_in2 (AvgPool backward)
+            zin, zin_up, zin2, k2 = zlo, b.stride, gres, gres_k
+        # ---- stem
+        shp = (J, 56, 56, 64)
+        z = self.fire('Conv2d', 0, zin, shp, s0=S['mp'], up=zin_up, z_in2=zin2, k2=k2, out='gs_a')     # layer1.0.conv1
+        z = self.fire('AvgPool2d', 0, z, shp, s0=S['mp'], out='gs_b')                                   # layer1.0 shortcut (k = 1)
+        zz = buf('gs_mp', J, 112, 112, 64)
+        be.maxpool_bwd(z, S['o_s'], eng.stem.bn, zz, eng.stem.pool_pad)
+        shp = (J, 112, 112, 64)
+        z = self.fire('ReLU', 1, zz, shp, s0=S['o_s'], bn=eng.stem.bn, out='gs_s1')
+        z = self.fire('MaxPool2d', 2, z, shp, s0=S['o_s'], bn=eng.stem.bn, post_mask=True, post_scale_row=srow, out='gs_s2')
+        P2 = buf('gs_P2', *shp)
+        self.fire('BatchNorm2d', 3, z, shp, s0=S['o_s'], s1=S['o_s'], out=None, P_force=P2)   # X only shapes the unused return
+        if self._P is not None:
+            self._P.append(None)                            # Conv2d hook on the image: never read by any output
+        self._names.append('Conv2d')
+        return self._P, self._names, P2
+
+    # -------------------------------------------------------------------------------------------------
+    def fire(self, kind, recipe, z_in, shape, out, P_force=None, **kw):
+        """Firing number self._k of the sweep."""
+        k = self._k
+        self._k += 1
+        self._names.append(kind)
+        affine = any(s in kind for s in AFFINE)
+        P_out = P_force
+        if self._P is not None:
+            if P_out is None:
+                P_out = torch.empty(shape, dtype=torch.float32, device=self.eng.device)
+            self._P.append(P_out)
+        z_out = self.eng.buf(out, *shape) if out is not None else None
+        flag = 2 if (self._norelu and ('MaxPool' in kind or 'ReLU' in kind)) else 0
+        self.be.hook(z_in, z_out, shape, recipe, affine, self._m, prior=self._priors.get(k), P_out=P_out,
+                     relu_or_maxpool=flag, N=self.eng.saved['N'], **kw)
+        return z_out

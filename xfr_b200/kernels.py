@@ -26,7 +26,7 @@ _SIGNATURES = {
     'xfrb_subsample2': [_P, _P, _I, _I, _I, _I, _P],
     'xfrb_avgpool2': [_P, _P, _I, _I, _I, _I, _P],
     'xfrb_conv_dual': [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
-    'xfrb_head_fwd': [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    'xfrb_head_fwd': [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     'xfrb_head_bwd': [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
     'xfrb_dgrad_mid': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     'xfrb_dgrad_plain': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -35,6 +35,12 @@ _SIGNATURES = {
     'xfrb_ds_res': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     'xfrb_stem_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
     'xfrb_bn_hook': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
+    'xfrb_hook': [_P, _I, _I, _P, _I, _I, _F, _P, _I, _P, _P, _I, _P, _P, _I, ctypes.c_longlong, _F, _P, _P, _I, _I, _I, _I, _I,
+                  _I, _I, _I, _I, _I, _I, _F, _P],
+    'xfrb_head_seed': [_P, _P, _I, _I, _I, _I, _P, _P],
+    'xfrb_normalize_bwd': [_P, _P, _P, _P, _I, _I, _I, _P],
+    'xfrb_maxpool_bwd': [_P, _P, _P, _P, _I, _I, _I, _P],
+    'xfrb_subtree_score': [_P, _P, _I, ctypes.c_longlong, _P, _P, _P],
     'xfrb_head_fwd_linear': [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     'xfrb_head_bwd_linear': [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
     'xfrb_contrast': [_P, _P, _P, _P, _I, _I, _I, _P],
@@ -128,11 +134,11 @@ class CudaBackend(object):
                                             0 if res is None else res.shape[-1], _ptr(o), _ptr(xr), _ptr(act),
                                             N, H, W, Cin, L.cout, L.R, L.tn, 1 if relu_act else 0, self.impl, self._st()))
 
-    def head_fwd(self, u, head, v, f1, f1p, xn, nrm):
+    def head_fwd(self, u, head, v, f1, f1p, xn, nrm, xmul=None):
         N = u.shape[0]
         scratch = self._tmp('head_fwd', N * 1024)
         self._check(self.lib.xfrb_head_fwd(_ptr(u), _ptr(head.B1), _ptr(head.bias1), head.tn, _ptr(scratch), _ptr(v),
-                                           _ptr(f1), _ptr(f1p), _ptr(xn), _ptr(nrm), N, self.impl, self._st()), 3)
+                                           _ptr(f1), _ptr(f1p), _ptr(xn), _ptr(nrm), _ptr(xmul), N, self.impl, self._st()), 3)
 
     # -------------------------------------------------------------- backward
     def head_bwd(self, Pn, W2, head, v, f1p, xn, nrm, mode, g_out, hooked_fc2=False):
@@ -180,6 +186,39 @@ class CudaBackend(object):
         zc = self._tmp('stem_zc', J * 56 * 56 * 64)
         self._check(self.lib.xfrb_stem_bwd(_ptr(zmain), _ptr(gres), _ptr(o), _ptr(mp), _ptr(bn), _ptr(zc), _ptr(P2),
                                            _ptr(chansum), _ptr(sums), J, o.shape[0], mode, self.eps, pool_pad, self._st()), 2)
+
+    # -------------------------------------------------------------- generic single-hook path
+    def hook(self, z_in, z_out, shape, recipe, affine, mode, s0=None, s1=None, s2=None, bn=None, up=1, zc=None, z_in2=None, k2=1,
+             pre_scale=1.0, prior=None, P_out=None, relu_or_maxpool=0, post_mask=False, post_scale_row=-1, N=None):
+        """One hook firing over [J,H,W,C] = shape; prior = None | (row, tensor) | (row, elem, val).  See include/xfrb.h."""
+        J, H, W, C = shape
+        pr_t, pr_row, pr_elem, pr_val = None, -1, 0, 0.0
+        if prior is not None:
+            if len(prior) == 2:
+                pr_row, pr_t = prior
+            else:
+                pr_row, pr_elem, pr_val = prior
+        Ns = N if N is not None else (s0.shape[0] if s0 is not None else J)
+        self._check(self.lib.xfrb_hook(_ptr(z_in), up, C if zc is None else zc, _ptr(z_in2), k2, 0 if z_in2 is None else z_in2.shape[-1],
+                                       float(pre_scale), _ptr(s0), C if s0 is None else s0.shape[-1], _ptr(s1), _ptr(s2),
+                                       0 if s2 is None else s2.shape[-1], _ptr(bn), _ptr(pr_t), int(pr_row), int(pr_elem),
+                                       float(pr_val), _ptr(P_out), _ptr(z_out), recipe, 1 if affine else 0, relu_or_maxpool, mode,
+                                       1 if post_mask else 0, post_scale_row, J, Ns, H, W, C, self.eps, self._st()))
+
+    def head_seed(self, Pn, W2, seed):
+        J, Ccls = Pn.shape
+        self._check(self.lib.xfrb_head_seed(_ptr(Pn), _ptr(W2), Ccls, W2.shape[-1], J, W2.shape[0], _ptr(seed), self._st()))
+
+    def normalize_bwd(self, gin, xn, nrm, gout):
+        J, D = gin.shape
+        self._check(self.lib.xfrb_normalize_bwd(_ptr(gin), _ptr(xn), _ptr(nrm), _ptr(gout), J, xn.shape[0], D, self._st()))
+
+    def maxpool_bwd(self, g, o, bn, out, pool_pad=1):
+        self._check(self.lib.xfrb_maxpool_bwd(_ptr(g), _ptr(o), _ptr(bn), _ptr(out), g.shape[0], o.shape[0], pool_pad, self._st()))
+
+    def subtree_score(self, gate, gneg, gate_ge0, score, arg):
+        self._check(self.lib.xfrb_subtree_score(_ptr(gate), _ptr(gneg), 1 if gate_ge0 else 0, gate.numel(), _ptr(score), _ptr(arg),
+                                                self._st()))
 
     # -------------------------------------------------------------- VGGFace2 ResNet-50-128d pieces
     def bn_hook(self, g, o, xr, bn, y, kind, mode):

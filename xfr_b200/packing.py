@@ -164,6 +164,14 @@ class Head(object):
         self.B1 = gemm_planes(B1, impl)
         self.W2 = sd['fc2.weight'].float().contiguous() if 'fc2.weight' in sd else None
         self.scale = 50.0
+        self.impl = impl
+        self._W1T_signed = None
+
+    def W1T_signed(self):
+        """[2048][512] signed fc1^T: the dgrad operand of the true-gradient sweeps (weighted_subtree_ebp)."""
+        if self._W1T_signed is None:
+            self._W1T_signed = gemm_planes(self.W1.t(), self.impl).to(self.W1.device)
+        return self._W1T_signed
 
     def to(self, device):
         for k in ('W1', 'b1', 'W1p', 'b1p', 'W1pT', 'W2', 'B1', 'bias1'):

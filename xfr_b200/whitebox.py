@@ -15,8 +15,8 @@ Status of the reference surface in this round:
   done   encode / classify / set_triplet_classifier / num_classes / preprocess / clear,
          ebp, contrastive_ebp, truncated_contrastive_ebp (all four ebp_subtree_mode values, ebp_version 6 post-processing),
          embeddings, ebp_subtree_mode, with_bias / ebp_version 11, ebp_version != 6 (uint8 + PIL blur on the host)
-  next   layerwise_ebp, layerwise_contrastive_ebp, weighted_subtree_ebp,
-         the hooked (non-triplet) fc2 head
+  done   layerwise_ebp, layerwise_contrastive_ebp, weighted_subtree_ebp on the STR ResNet plugin (xfr_b200/generic.py)
+  next   the hooked (non-triplet) fc2 head; layerwise operators for the ResNet-50-128d plugin; Light-CNN plugin
 """
 import numpy as np
 import torch
@@ -301,14 +301,194 @@ class Whitebox(nn.Module):
         assert(k_negchannel >= 0 and k_negchannel < self.net.num_classes())
         return self.contrastive_ebp_batch(img_probe, k_poschannel, k_negchannel, percentile=percentile)[0]
 
+    # ---------------------------------------------------------------- layerwise / sub-tree operators (generic sweep)
+    def _generic(self, img_probe):
+        """Forward once, return (GenericSweep, W2 rows).  STR ResNet only in this round."""
+        from .generic import GenericSweep
+        eng = self._engine()
+        if not isinstance(eng, StResnetEngine):
+            raise NotImplementedError('xfr_b200: layerwise / weighted-subtree EBP is implemented for the STR ResNet plugin')
+        if img_probe.shape[0] != 1:
+            raise ValueError('layerwise operators take one probe (as in the reference)')
+        eng.forward(self.net._nhwc(img_probe))
+        return GenericSweep(eng), self.net.triplet_rows(1)
+
+    @staticmethod
+    def _nchw_index_to_nhwc(e, shape):
+        """The reference indexes flattened [1,C,H,W] tensors (whitebox.py:575-577); device tensors here are [1,H,W,C]."""
+        _, H, W, C = shape
+        c, hw = divmod(int(e), H * W)
+        h, w = divmod(hw, W)
+        return (h * W + w) * C + c
+
+    def _set_P(self, P, names):
+        """Expose the recorded MWPs like the reference's self.P / self.P_layername: [1,C,H,W] views (vectors: [1,C])."""
+        self.P = [None if p is None else (p.permute(0, 3, 1, 2) if p.shape[1] * p.shape[2] > 1 else p.reshape(p.shape[0], -1)) for p in P]
+        self.P_layername = list(names)
+
+    def _finish_map(self, P2, mwp):
+        chansum = P2.sum(-1)                                      # [J,112,112] pool over channels (whitebox.py:499)
+        if mwp:
+            return chansum.cpu().numpy().astype(np.float32)
+        out = torch.empty_like(chansum)
+        self.net.engine(self._ebp_with_bias).be.saliency_post(chansum.contiguous(), out)
+        maps = out.cpu().numpy()
+        if self.convert_saliency_uint8:
+            maps = np.stack([self._mwp_to_saliency_uint8(m) for m in chansum.cpu().numpy()])
+        return maps
+
+    def _onehot(self, k, dev):
+        P0 = torch.zeros((1, self.net.num_classes()), device=dev)
+        P0[0][k] = 1.0
+        return P0
+
     def layerwise_ebp(self, img_probe, k_layer, mode='argmax', k_element=None, k_poschannel=0, mwp=True):
-        raise NotImplementedError('xfr_b200: layerwise_ebp is scheduled next (DESIGN.md)')
+        """whitebox.py:561-581: EBP restarted from one node (or the arg-max nodes) of firing k_layer."""
+        assert(k_poschannel >= 0 and k_poschannel < self.net.num_classes())
+        gs, W2 = self._generic(img_probe)
+        P0 = self._onehot(k_poschannel, W2.device)
+        P_mate, names, _ = gs.run(P0, W2, self._ebp_subtree_mode, record=True)
+        Pk = P_mate[k_layer]
+        if mode == 'argmax':
+            prior = (0, (Pk * (Pk == Pk.max())).reshape(-1).contiguous())
+        elif mode == 'elementwise':
+            assert(k_element is not None)
+            e = self._nchw_index_to_nhwc(k_element, Pk.shape)
+            prior = (0, e, float(Pk.reshape(-1)[e]))
+        else:
+            raise ValueError('invalid layerwise EBP mode "%s"' % mode)
+        P, names, P2 = gs.run(0.0 * P0, W2, self._ebp_subtree_mode, priors={int(k_layer): prior}, record=True)
+        self._set_P(P, names)
+        return self._finish_map(P2, mwp)[0]
 
-    def layerwise_contrastive_ebp(self, *a, **k):
-        raise NotImplementedError('xfr_b200: layerwise_contrastive_ebp is scheduled next (DESIGN.md)')
+    def layerwise_contrastive_ebp(self, img_probe, k_poschannel, k_negchannel, k_layer, mode='copy', percentile=80, k_element=None,
+                                  gradlayer=None, mwp=False):
+        """whitebox.py:584-644 (deprecated in the reference in favour of weighted_subtree_ebp, kept for the layer sweeps)."""
+        import warnings
+        warnings.warn("layerwise_contrastive_ebp is deprecated, use weighted_subtree_ebp instead")
+        assert(k_poschannel >= 0 and k_poschannel < self.net.num_classes())
+        assert(k_negchannel >= 0 and k_negchannel < self.net.num_classes())
+        gs, W2 = self._generic(img_probe)
+        dev = W2.device
+        Pn = torch.cat((self._onehot(k_poschannel, dev), self._onehot(k_negchannel, dev)))
+        P, names, _ = gs.run(Pn, W2, self._ebp_subtree_mode, record=True)         # mate and non-mate as two gradient rows
+        Pm, Pq = P[k_layer][0:1], P[k_layer][1:2]
+        C = torch.clamp_min(Pm - Pq, 0)
+        argmax_only = lambda t: t * (t == t.max())
+        if mode == 'copy':
+            prior = C
+        elif mode == 'mean':
+            prior = 0.5 * (Pm + C)
+        elif mode == 'product':
+            prior = torch.sqrt(Pm.double() * C.double()).float()
+        elif mode == 'argmax':
+            prior = argmax_only(C)
+        elif mode == 'argmax_product':
+            prior = argmax_only(torch.sqrt(Pm.double() * C.double()).float())
+        elif mode in ('percentile', 'percentile_argmax'):
+            assert(percentile >= 0 and percentile <= 100)
+            be = gs.be
+            thr = torch.empty(1, device=dev)
+            sums = Pm.double().sum().reshape(1)
+            be.trunc_threshold(Pm.reshape(1, 1, 1, -1).contiguous(), sums, 1, percentile, thr)
+            prior = (Pm >= thr) * C
+            if mode == 'percentile_argmax':
+                prior = argmax_only(prior)
+        elif mode == 'elementwise':
+            e = self._nchw_index_to_nhwc(k_element, Pm.shape)
+            prior = torch.zeros_like(C).reshape(-1)
+            prior[e] = C.reshape(-1)[e]
+        else:
+            raise ValueError('unknown contrastive ebp mode "%s"' % mode)
+        P0 = self._onehot(k_poschannel, dev)
+        P, names, P2 = gs.run(0.0 * P0, W2, self._ebp_subtree_mode, priors={int(k_layer): (0, prior.reshape(-1).contiguous())}, record=True)
+        self._set_P(P, names)
+        return self._finish_map(P2, mwp)[0]
 
-    def weighted_subtree_ebp(self, *a, **k):
-        raise NotImplementedError('xfr_b200: weighted_subtree_ebp is scheduled next (DESIGN.md)')
+    def weighted_subtree_ebp(self, img_probe, k_poschannel, k_negchannel, topk=1, verbose=True, do_max_subtree=False,
+                             do_mated_similarity_gating=True, subtree_mode='norelu', do_mwp_to_saliency=True, rows_per_sweep=48):
+        """whitebox.py:647-737.  One forward; the three true-gradient passes (cross-entropy, mate logit, non-mate logit)
+        are one 3-row sweep without hooks; the per-layer scores come from the xfrb_subtree_score kernel; the ~n one-element
+        sub-tree EBPs are batched as gradient rows (`rows_per_sweep` at a time) instead of 2n separate ebp() calls."""
+        self._ebp_subtree_mode = subtree_mode                                       # the reference's side effect (651)
+        gs, W2 = self._generic(img_probe)
+        eng, be, dev = gs.eng, gs.be, W2.device
+        # true gradients dA of: cross-entropy(y, 0), y[0], y[1]
+        y = (50.0 * eng.saved['xn'][0:1]) @ W2[0].t()                               # classify(): logits of the triplet head
+        sm = torch.softmax(y, dim=1)
+        Pn = torch.zeros(3, self.net.num_classes(), device=dev)
+        Pn[0] = sm[0]
+        Pn[0, 0] -= 1.0
+        Pn[1, 0] = 1.0
+        Pn[2, 1] = 1.0
+        dA, names, _ = gs.run(Pn, W2, subtree_mode, record=True, true_grad=True)
+        n_layers = len(dA)
+        score = torch.empty(n_layers - 1, device=dev)
+        arg = torch.empty(n_layers - 1, dtype=torch.int64, device=dev)
+        for k in range(0, n_layers - 1):                                            # not including image layer (684)
+            gate = dA[k][1] if do_mated_similarity_gating else dA[k][0]
+            be.subtree_score(gate.contiguous(), dA[k][2].contiguous(), do_mated_similarity_gating, score[k:k + 1], arg[k:k + 1])
+        P_subtree = [float(v) for v in score.cpu().numpy()]
+        P_subtree_idx = arg.cpu().numpy()
+        del dA
+        k_subtree = np.argsort(np.array(P_subtree))                                 # ascending, one per layer (697)
+        # layerwise EBP for every sub-tree: P_mate once, then one-element priors as batched gradient rows
+        P0 = self._onehot(k_poschannel, dev)
+        P_mate, names, _ = gs.run(P0, W2, subtree_mode, record=True)
+        seeds = [(int(k), int(P_subtree_idx[k]), float(P_mate[k].reshape(-1)[int(P_subtree_idx[k])])) for k in k_subtree]
+        del P_mate
+        P_img = []
+        for i in range(0, len(seeds), rows_per_sweep):
+            chunk = seeds[i:i + rows_per_sweep]
+            priors = {k: (r, e, v) for r, (k, e, v) in enumerate(chunk)}
+            Z = torch.zeros(len(chunk), self.net.num_classes(), device=dev)
+            _, _, P2 = gs.run(Z, W2, subtree_mode, priors=priors)
+            P_img += list(P2.sum(-1).cpu().numpy().astype(np.float32))             # layerwise_ebp(..., mwp=True) maps
+        self.P_layername = list(names)
+        if verbose:
+            for k in k_subtree:
+                print('[weighted_subtree_ebp][%d]: layername=%s, grad=%f' % (k, names[k], P_subtree[k]))
+        # merge (whitebox.py:705-737)
+        k_valid = [np.max(P) > 0 for P in P_img]
+        k_subtree_valid = [k for (k, v) in zip(k_subtree, k_valid) if v == True and k != 1][-topk:]     # noqa: E712
+        if len(k_subtree_valid) == 0:
+            raise RuntimeError(
+                'Failed to calculate valid subtrees. The ebp subtree mode '
+                '(%s) may not support by this type of network. You may want '
+                'to try the "affineonly_with_prior" ebp subtree mode.' %
+                self._ebp_subtree_mode
+            )
+        P_img_valid = [p for (p, k, v) in zip(P_img, k_subtree, k_valid) if v == True and k != 1][-topk:]   # noqa: E712
+        P_subtree_valid = [P_subtree[k] for k in k_subtree_valid]
+        norm = self._scale_normalized(P_subtree_valid)
+        P_subtree_valid_norm = norm if not np.sum(norm) == 0 else np.ones_like(P_subtree_valid)
+        stack = np.dstack([float(w) * np.array(P) * (1.0 / (np.max(P) + 1E-12)) for (w, P) in zip(P_subtree_valid_norm, P_img_valid)])
+        smap = np.max(stack, axis=2) if do_max_subtree else np.sum(stack, axis=2)
+        if self.convert_saliency_uint8:
+            smap = self._float32_to_uint8(smap)
+        else:
+            smap /= max(smap.sum(), self.eps)
+        return (
+            self._mwp_to_saliency(smap) if do_mwp_to_saliency else smap,
+            [self._mwp_to_saliency(P) if do_mwp_to_saliency else P for P in P_img_valid],
+            P_subtree_valid,
+            k_subtree_valid)
+
+    def _scale_normalized(self, img):
+        """whitebox.py:443-446"""
+        img = np.float32(img)
+        return (img - np.min(img)) / (self.eps + (np.max(img) - np.min(img)))
+
+    def _mwp_to_saliency(self, P, blur_radius=2):
+        """whitebox.py:448-460 on one host map (the batched operators use the xfrb_saliency_post kernel instead)."""
+        if self.convert_saliency_uint8:
+            return self._mwp_to_saliency_uint8(P, blur_radius)
+        t = torch.from_numpy(np.ascontiguousarray(P, dtype=np.float32)).unsqueeze(0)
+        be = self.net.engine(self._ebp_with_bias).be
+        dev = self.net._device()
+        out = torch.empty(t.shape, device=dev)
+        be.saliency_post(t.to(dev), out)
+        return out[0].cpu().numpy()
 
     def ebp_subtree_mode(self):
         return self._ebp_subtree_mode
