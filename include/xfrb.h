@@ -81,7 +81,9 @@ int xfrb_head_fwd(const float* u, const float* B1, const float* bias1, int tn, f
 
 /* Head: seed = Pn @ W2 (un-hooked per-sample triplet classifier, whitebox.py:93-96), x50,
  * Multiply hook, Jacobian of F.normalize, fc1 with relu(W) (W1pT [2048][512]), Linear hook,
- * AvgPool2d(7) backward.  Pn [J,C], W2 [N,C,512]; scratch [J,2560]; g_out [J,7,7,2048]. */
+ * AvgPool2d(7) backward.  Pn [J,C], W2 [N,C,512]; scratch [J,2560]; g_out [J,7,7,2048].
+ * W2 == NULL: Pn is already the [J,512] gradient at the fc2 input (the network's own hooked fc2: xfrb_head_seed with
+ * relu(fc2.weight) followed by the Linear hook through xfrb_hook, whitebox.py:371-374). */
 int xfrb_head_bwd(const float* Pn, const float* W2, int C, const float* W1pT,
                   const float* v, const float* f1p, const float* xn, const float* nrm,
                   float* scratch, float* g_out, int J, int N, int mode, float eps, int impl, void* stream);

@@ -114,9 +114,8 @@ class EmulBackend(object):
         g_out [J,7,7,2048] = gradient w.r.t. the last block output (after AvgPool backward)."""
         J = Pn.shape[0]
         xn_, v_, nrm_ = _rows(xn, J), _rows(v, J), _rows(nrm, J)
-        if hooked_fc2:
-            gr = Pn @ relu(W2)
-            gr = hook(True, relu(xn_ * head.scale), relu(head.scale * relu(xn_)), gr, mode, self.eps)
+        if W2 is None:
+            gr = Pn                       # already the gradient at the fc2 input (hooked fc2 head)
         else:
             gr = torch.einsum('jc,jcd->jd', Pn, _rows(W2, J))
         gr = gr * head.scale

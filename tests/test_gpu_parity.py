@@ -130,3 +130,19 @@ def test_full_size_properties():
     assert float((b - a[perm]).abs().max() / a.max()) < 1e-4
     c = eng.contrastive(x, W2.flip(1).contiguous(), k_pos=1, k_neg=0).clone()
     assert float((c - a).abs().max() / a.max()) < 1e-4
+
+
+def test_hooked_fc2_head_api():
+    """demo/test_whitebox.py:77-107 style: no triplet classifier, the network's own fc2 is the (hooked) classifier."""
+    from xfr_b200 import whitebox
+    G = golden(L101)
+    dev = torch.device('cuda:0')
+    sd = {k: v.to(dev) for k, v in synth.stresnet_state_dict(0, L101, 2).items()}
+    wb = whitebox.Whitebox(whitebox.WhiteboxSTResnet(sd))
+    _, _, imgs = golden_inputs(G)
+    P = torch.zeros((1, wb.net.num_classes()))
+    P[0][1] = 1.0
+    m = wb.ebp(imgs[0:1], P, mwp=True)
+    assert rel_err(m, G['ebp_mwp_awp_fc2head']) < 5e-3
+    c = wb.contrastive_ebp(imgs[0:1], k_poschannel=0, k_negchannel=1)
+    assert np.abs(c - G['cebp_awp_fc2head']).max() < 1e-4

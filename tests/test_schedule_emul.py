@@ -96,3 +96,25 @@ def test_truncated_and_with_bias(layers):
     m = engb.ebp(x[:1], P1, W2[:1], saliency=False).clone().numpy()
     assert rel_err(m[0], G['ebp_mwp_awp_withbias']) < 1e-5
     assert rel_err(m[0], G['ebp_mwp_awp_smooth']) > 1e-4        # with_bias really changes the map
+
+
+@pytest.mark.parametrize('layers', [L1111, L101])
+def test_hooked_fc2_head(layers):
+    """No set_triplet_classifier: the network's own fc2 takes part with relu(W) and adds a leading Linear firing."""
+    G = golden(layers)
+    sd = synth.stresnet_state_dict(0, layers, 2)
+    eng = StResnetEngine(sd, EmulBackend(), layers)
+    x, _, _ = golden_inputs(G)
+    W2 = sd['fc2.weight']
+    P1 = torch.zeros(1, 2)
+    P1[0, 1] = 1
+    m = eng.ebp(x[:1].contiguous(), P1, W2, hooked_fc2=True, saliency=False).clone().numpy()
+    assert rel_err(m[0], G['ebp_mwp_awp_fc2head']) < 1e-5
+    c = eng.contrastive(x[:1].contiguous(), W2, hooked_fc2=True, num_classes=2).clone().numpy()
+    assert np.abs(c[0] - G['cebp_awp_fc2head']).max() < 1e-4 and rel_err(c[0], G['cebp_awp_fc2head']) < (5e-4 if layers == L1111 else 5e-2)
+    if layers == L1111:
+        from xfr_b200.generic import GenericSweep
+        eng.forward(x[:1].contiguous())
+        P, names, P2 = GenericSweep(eng).run(P1, W2, 'affineonly_with_prior', record=True, hooked_fc2=True)
+        assert len(P) == len(G['P_kinds']) + 1 and names[0] == 'Linear'          # 379 vs 378 firings on the 101 (SURVEY fact 2)
+        assert rel_err(P2.sum(-1)[0].numpy(), G['ebp_mwp_awp_fc2head']) < 1e-5

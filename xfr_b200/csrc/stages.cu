@@ -218,7 +218,9 @@ __global__ void __launch_bounds__(512) head_bwd_a_kernel(const float* __restrict
         return bc;
     };
     float g = 0.f;
-    for (int c = 0; c < C; ++c) g = fmaf(Pn[(size_t)j * C + c], W2[((size_t)n * C + c) * 512 + d], g);
+    if (W2 == nullptr) g = Pn[(size_t)j * 512 + d];               // Pn already is the seed (hooked fc2 head, xfrb_head_seed + xfrb_hook)
+    else
+        for (int c = 0; c < C; ++c) g = fmaf(Pn[(size_t)j * C + c], W2[((size_t)n * C + c) * 512 + d], g);
     g = g * 50.f;                                                 // Multiply backward (resnet.py:160-165)
     float x = xn[(size_t)n * 512 + d];
     float xmul = 0.f;

@@ -185,6 +185,26 @@ class StResnetEngine(_Engine):
         return S['xn']
 
     # ------------------------------------------------------------ backward
+    def hooked_fc2_seed(self, Pn, W2, m, prior=None, P_out=None):
+        """The network's own fc2 takes part in EBP (no set_triplet_classifier): gradient Pn @ relu(W2) at the fc2 input,
+        then the Linear hook with a = relu(50*xn), x = relu(50*relu(xn)) (reference whitebox.py:371-374, 381-430;
+        SURVEY.md appendix A).  W2 [C,512] signed.  Returns the [J,512] gradient after the hook."""
+        S, J = self.saved, Pn.shape[0]
+        key = ('W2p', W2.data_ptr())
+        W2p = self._ws.get(key)
+        if W2p is None:
+            W2p = torch.clamp_min(W2, 0).unsqueeze(0).contiguous()
+            self._ws[key] = W2p
+        seed = self.buf('fc2_seed', J, 1, 1, 512)
+        self.be.head_seed(Pn, W2p, seed.view(J, 512))
+        a50 = self.buf('fc2_a', S['N'], 512)
+        x50 = self.buf('fc2_x', S['N'], 512)
+        torch.mul(S['xn'], 50.0, out=a50)                       # 512-float glue per probe
+        torch.mul(torch.clamp_min(S['xn'], 0), 50.0, out=x50)
+        out = self.buf('fc2_hooked', J, 1, 1, 512)
+        self.be.hook(seed, out, (J, 1, 1, 512), 5, True, m, s0=a50, s1=x50, prior=prior, P_out=P_out, N=S['N'])
+        return out.view(J, 512)
+
     def ebp_backward(self, Pn, W2, mode='affineonly_with_prior', hooked_fc2=False):
         """One excitation-backprop sweep over J = Pn.shape[0] gradient rows (J % N == 0).
         Pn [J,C] class priors; W2 [N,C,512] per-sample classifier rows (set_triplet_classifier,
@@ -198,7 +218,9 @@ class StResnetEngine(_Engine):
         nb = len(self.blocks)
         last = self.blocks[-1]
         g = self.buf('g_head', J, 7, 7, last.cout)
-        be.head_bwd(Pn, W2, self.head, S['v'], S['f1p'], S['xn'], S['nrm'], m, g, hooked_fc2)
+        if hooked_fc2:
+            Pn, W2 = self.hooked_fc2_seed(Pn, W2, m), None
+        be.head_bwd(Pn, W2, self.head, S['v'], S['f1p'], S['xn'], S['nrm'], m, g)
         # chain on the last block output (ReLU + AvgPool2d hooks) and the start of its main path
         t = S[nb - 1]
         gb = self.buf('g%d' % ((nb - 1) % 2), J, last.hw, last.hw, last.cout)

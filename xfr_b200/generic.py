@@ -31,7 +31,7 @@ class GenericSweep(object):
         self.be = engine.be
 
     # -------------------------------------------------------------------------------------------------
-    def run(self, Pn, W2, mode, priors=None, record=False, true_grad=False):
+    def run(self, Pn, W2, mode, priors=None, record=False, true_grad=False, hooked_fc2=False):
         """One sweep over J = Pn.shape[0] gradient rows.
         priors: {firing k: (row, elem, value) | (row, tensor)}; record: keep p of every firing (list of [J,H,W,C]
         device tensors, NHWC; entry -1, the Conv2d hook on the image, is None: nothing reads it);
@@ -55,8 +55,19 @@ class GenericSweep(object):
             return out
 
         # ---- head: fc2 (un-hooked triplet rows) -> x50 -> Multiply hook -> normalize' -> fc1 -> Linear hook -> AvgPool'
-        seed = buf('gs_seed', J, 1, 1, 512)
-        be.head_seed(Pn, W2, seed.view(J, 512))
+        if hooked_fc2:          # the network's own fc2: W+ and one more (leading) Linear firing
+            if true_grad:
+                raise NotImplementedError('true-gradient sweep with the hooked fc2 head')
+            k = self._k
+            self._k += 1
+            self._names.append('Linear')
+            P_out = torch.empty(J, 1, 1, 512, device=eng.device) if record else None
+            if record:
+                self._P.append(P_out)
+            seed = eng.hooked_fc2_seed(Pn, W2, m, prior=self._priors.get(k), P_out=P_out).view(J, 1, 1, 512)
+        else:
+            seed = buf('gs_seed', J, 1, 1, 512)
+            be.head_seed(Pn, W2, seed.view(J, 512))
         z = self.fire('Multiply', 5, seed, (J, 1, 1, 512), s0=S['xn'], s1=S['xmul'], pre_scale=50.0, out='gs_mul')
         zn = buf('gs_nb', J, 1, 1, 512)
         be.normalize_bwd(z.view(J, 512), S['xn'], S['nrm'], zn.view(J, 512))

@@ -142,8 +142,6 @@ class CudaBackend(object):
 
     # -------------------------------------------------------------- backward
     def head_bwd(self, Pn, W2, head, v, f1p, xn, nrm, mode, g_out, hooked_fc2=False):
-        if hooked_fc2:
-            raise NotImplementedError('hooked fc2 head (non-triplet classifier) is not on the CUDA path yet')
         J, C = Pn.shape
         N = v.shape[0]
         scratch = self._tmp('head_bwd', J * 2560)

@@ -16,7 +16,8 @@ Status of the reference surface in this round:
          ebp, contrastive_ebp, truncated_contrastive_ebp (all four ebp_subtree_mode values, ebp_version 6 post-processing),
          embeddings, ebp_subtree_mode, with_bias / ebp_version 11, ebp_version != 6 (uint8 + PIL blur on the host)
   done   layerwise_ebp, layerwise_contrastive_ebp, weighted_subtree_ebp on the STR ResNet plugin (xfr_b200/generic.py)
-  next   the hooked (non-triplet) fc2 head; layerwise operators for the ResNet-50-128d plugin; Light-CNN plugin
+  done   the hooked (non-triplet) fc2 head for ebp / contrastive_ebp (e.g. the 65,359-class STR head, blackbox.py:280-294)
+  next   layerwise operators for the ResNet-50-128d plugin; Light-CNN plugin
 """
 import numpy as np
 import torch
@@ -107,9 +108,13 @@ class WhiteboxSTResnet(WhiteboxNetwork):
         self._W2 = torch.stack((x_mates.detach().float(), x_nonmates.detach().float()), dim=1).contiguous()
         self._ncls = 2
 
+    def hooked(self):
+        """True when no triplet classifier was set: the network's own (hooked) fc2 is the classifier."""
+        return self._W2 is None
+
     def triplet_rows(self, n):
-        if self._W2 is None:
-            raise NotImplementedError('xfr_b200: the hooked fc2 head (no set_triplet_classifier) is not on the CUDA path yet')
+        if self._W2 is None:                      # the network's own fc2 [C,512]: takes part in EBP with relu(W)
+            return self._sd['fc2.weight'].to(self._device()).float().contiguous()
         W2 = self._W2.to(self._device())
         if W2.shape[0] == 1 and n > 1:
             W2 = W2.expand(n, -1, -1)
@@ -260,9 +265,10 @@ class Whitebox(nn.Module):
         Pn = Pn.to(W2.device, dtype=torch.float32)
         if Pn.shape[0] == 1 and N > 1:
             Pn = Pn.expand(N, -1)
+        hk = self.net.hooked()
         for i in range(0, N, _CHUNK):
-            m = eng.ebp(self.net._nhwc(x[i:i + _CHUNK]), Pn[i:i + _CHUNK].contiguous(), W2[i:i + _CHUNK].contiguous(),
-                        self._ebp_subtree_mode, saliency=not (mwp or self.convert_saliency_uint8))
+            m = eng.ebp(self.net._nhwc(x[i:i + _CHUNK]), Pn[i:i + _CHUNK].contiguous(), W2 if hk else W2[i:i + _CHUNK].contiguous(),
+                        self._ebp_subtree_mode, hooked_fc2=hk, saliency=not (mwp or self.convert_saliency_uint8))
             outs.append(m.cpu())
         maps = torch.cat(outs).numpy()
         if self.convert_saliency_uint8 and not mwp:
@@ -275,9 +281,11 @@ class Whitebox(nn.Module):
         N = x.shape[0]
         W2 = self.net.triplet_rows(N)
         res = out if out is not None else torch.empty(N, 112, 112)
+        hk = self.net.hooked()
         for i in range(0, N, _CHUNK):
-            m = eng.contrastive(self.net._nhwc(x[i:i + _CHUNK]), W2[i:i + _CHUNK].contiguous(), k_poschannel, k_negchannel,
-                                self._ebp_subtree_mode, percentile=percentile, saliency=not self.convert_saliency_uint8)
+            m = eng.contrastive(self.net._nhwc(x[i:i + _CHUNK]), W2 if hk else W2[i:i + _CHUNK].contiguous(), k_poschannel,
+                                k_negchannel, self._ebp_subtree_mode, hooked_fc2=hk, percentile=percentile,
+                                saliency=not self.convert_saliency_uint8, num_classes=self.net.num_classes())
             res[i:i + m.shape[0]].copy_(m, non_blocking=True)
         torch.cuda.current_stream(W2.device).synchronize()
         if self.convert_saliency_uint8:
