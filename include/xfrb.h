@@ -17,8 +17,10 @@
  *    the same N probes); row j reads the forward tensors of sample j % N;
  *  - `mode`: 0 = affineonly_with_prior, 1 = all (== norelu without a prior),
  *    2 = affineonly   (reference whitebox.py:397-430, no prior set);
- *  - `impl`: 0 = fp32 CUDA-core implicit GEMM, 1 = tcgen05 3xTF32 (fp32-equivalent),
- *    2 = tcgen05 single-pass TF32;
+ *  - `impl`: 0 = fp32 CUDA-core implicit GEMM; 1 = tcgen05 split-TF32: three passes (fp32-equivalent) wherever a
+ *    weight is signed (true forward), two passes (activation split exactly, relu(W) rounded to TF32) for the W+ GEMMs,
+ *    whose products are all non-negative; 2 = tcgen05 single-pass TF32; 3 = tcgen05 3xTF32 in every GEMM
+ *    (xfrb_dgrad_plain with signed weights - the true-gradient sweep of weighted_subtree_ebp - must be called with 3);
  *  - weight operands (`Bf`, `Bd`, `B1`, `W1pT`) are K-major [rows][K] fp32.  For impl 1 they hold TWO planes
  *    [2][rows][K]: hi = rna_tf32(W) and lo = W - hi (the host does the 3xTF32 split of the static operand once,
  *    xfr_b200/packing.py); for impl 2 one plane of rna_tf32(W); for impl 0 one plane of W;
@@ -39,6 +41,7 @@ extern "C" {
 #define XFRB_IMPL_FP32 0
 #define XFRB_IMPL_TF32X3 1
 #define XFRB_IMPL_TF32 2
+#define XFRB_IMPL_TF32X3_FULL 3
 
 int xfrb_version(void);
 const char* xfrb_last_error(void);

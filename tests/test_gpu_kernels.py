@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 # GEMM-backed stages accumulate in a different order than the CPU BLAS: a few 1e-6; everything else is
 # elementwise IEEE arithmetic and must agree to rounding of the reductions.
-TOL = {'fp32': 2e-5, 'tf32x3': 2e-4, 'tf32': 3e-2}
+TOL = {'fp32': 2e-5, 'tf32x3': 2e-4, 'tf32x3full': 2e-4, 'tf32': 3e-2}
 
 
 @pytest.mark.parametrize('impl', ['fp32', 'tf32x3'])
@@ -58,7 +58,9 @@ def _conv_case(be, J, H, C_in, C_out, R, seed=0):
     return float((got - want).abs().max() / want.abs().max())
 
 
-@pytest.mark.parametrize('impl,tol', [('fp32', 1e-5), ('tf32x3', 1e-4), ('tf32', 3e-3)])
+# 'tf32x3' runs dgrad_plain as a W+ GEMM (two passes: weights rounded to TF32, activations exact), so on the SIGNED random
+# operands of this test it carries the 2^-12 weight rounding; 'tf32x3full' (three passes) is the fp32-equivalent plan.
+@pytest.mark.parametrize('impl,tol', [('fp32', 1e-5), ('tf32x3', 5e-4), ('tf32x3full', 1e-4), ('tf32', 3e-3)])
 def test_gemm_shapes(impl, tol):
     """Every (spatial size, tap count, N width) family the ResNet-101 schedule launches, incl. ragged M tails."""
     from xfr_b200.kernels import CudaBackend

@@ -22,7 +22,7 @@ def _engine(layers, impl):
     return StResnetEngine(synth.stresnet_state_dict(0, layers, 2), be, layers, device=dev), dev
 
 
-@pytest.mark.parametrize('impl', ['fp32', 'tf32x3'])
+@pytest.mark.parametrize('impl', ['fp32', 'tf32x3', 'tf32x3full'])
 @pytest.mark.parametrize('mode,tag', MODES)
 def test_small_net_vs_reference(impl, mode, tag):
     G = golden(L1111)

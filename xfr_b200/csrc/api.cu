@@ -43,11 +43,17 @@ static int finish(const char* what, cudaError_t e) {
     return 0;
 }
 
+// positive_weights: the B operand is relu(W) and the A operand is non-negative (a W+ GEMM of excitation backprop): under
+// XFRB_IMPL_TF32X3 it runs the two-pass plan (see conv_tc.cu); signed GEMMs keep all three passes.
 static cudaError_t run_gemm(const float* A, const float* B, const ConvGeom& g, const EpiParams& ep, int impl, cudaStream_t st,
-                            int tn = 0) {
+                            int tn = 0, bool positive_weights = false) {
     if (impl == XFRB_IMPL_FP32) return launch_conv_simt(A, B, g, ep, st);
-    if (impl == XFRB_IMPL_TF32X3 || impl == XFRB_IMPL_TF32) return launch_conv_tc(A, B, g, ep, impl == XFRB_IMPL_TF32X3, tn, st);
-    return cudaErrorInvalidValue;
+    int split;
+    if (impl == XFRB_IMPL_TF32) split = 0;
+    else if (impl == XFRB_IMPL_TF32X3_FULL) split = 1;
+    else if (impl == XFRB_IMPL_TF32X3) split = ep.kind == EPI_FWD_DUAL ? 3 : (ep.kind == EPI_MID || ep.kind == EPI_JOIN || positive_weights) ? 2 : 1;
+    else return cudaErrorInvalidValue;
+    return launch_conv_tc(A, B, g, ep, split, tn, st);
 }
 
 }  // namespace xfrb
@@ -68,7 +74,7 @@ int xfrb_device_ok(void) {
 
 int xfrb_impl_available(int impl) {
     if (impl == XFRB_IMPL_FP32) return 1;
-    if (impl == XFRB_IMPL_TF32X3 || impl == XFRB_IMPL_TF32) return conv_tc_available() ? 1 : 0;
+    if (impl == XFRB_IMPL_TF32X3 || impl == XFRB_IMPL_TF32 || impl == XFRB_IMPL_TF32X3_FULL) return conv_tc_available() ? 1 : 0;
     return 0;
 }
 
@@ -140,7 +146,7 @@ int xfrb_head_bwd(const float* Pn, const float* W2, int C, const float* W1pT, co
     ep.M = ep.Ms = J;
     ep.C = 2048;
     ep.out0 = z;
-    e = run_gemm(scratch, W1pT, g, ep, impl, st);
+    e = run_gemm(scratch, W1pT, g, ep, impl, st, 0, true);
     if (e != cudaSuccess) return finish("xfrb_head_bwd/fc1", e);
     return finish("xfrb_head_bwd/b", launch_head_bwd_b(z, v, g_out, J, N, 2048, mode, eps, st));
 }
@@ -171,7 +177,7 @@ int xfrb_dgrad_plain(const float* y, const float* Bd, float* z_out, int J, int H
     ep.C = Cin;
     ep.out0 = z_out;
     ep.g_res = accumulate ? z_out : nullptr;
-    return finish("xfrb_dgrad_plain", run_gemm(y, Bd, g, ep, impl, (cudaStream_t)stream));
+    return finish("xfrb_dgrad_plain", run_gemm(y, Bd, g, ep, impl, (cudaStream_t)stream, 0, true));
 }
 
 int xfrb_dgrad_join(const float* y1, const float* Bd, const float* g_res, const float* out, const float* o3, const float* xr3,
@@ -275,7 +281,7 @@ int xfrb_head_bwd_linear(const float* Pn, const float* W2, int Ccls, const float
     ep.M = ep.Ms = J;
     ep.C = C;
     ep.out0 = z;
-    e = run_gemm(scratch, BfeT, g, ep, impl, st);
+    e = run_gemm(scratch, BfeT, g, ep, impl, st, 0, true);
     if (e != cudaSuccess) return finish("xfrb_head_bwd_linear/gemm", e);
     return finish("xfrb_head_bwd_linear/b", launch_head_bwd_b(z, v, g_out, J, N, C, mode, eps, st));
 }

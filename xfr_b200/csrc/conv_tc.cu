@@ -12,7 +12,15 @@
 //                                main loop of tile i+1); tcgen05.commit releases smem stages / publishes accumulators
 //   warps 2-5   operand split  - (3xTF32 only) rewrite the landed activation tile as hi = rna_tf32(x) in place and
 //                                lo = x - hi in a twin buffer (weights arrive pre-split from the host as two planes);
-//                                the issuer then runs hi*hi + lo*hi + hi*lo into the same accumulator
+//                                the issuer then runs hi*hi + lo*hi (+ hi*lo) into the same accumulator.
+//
+// SPLIT (pass plan of the GEMM):
+//   0  single TF32 pass
+//   1  full 3xTF32: A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (signed weights: cancellation amplifies weight rounding)
+//   2  W+ GEMMs (non-negative weights and activations, no cancellation): A_hi*B_hi + A_lo*B_hi only, i.e. the exact
+//      product with relu(W) rounded to TF32; the lo weight plane is never loaded.  Using the same rounded W+ for the X of
+//      the forward twin and for the dgrad keeps excitation backprop mass-conserving.
+//   3  dual forward pack [W rows | relu(W) rows]: A_hi*B_hi + A_lo*B_hi over the whole tile, A_hi*B_lo over the W half only
 //   warps 6-13  epilogue       - tcgen05.ld the accumulator (lane = pixel row), apply the fused EBP epilogue of
 //                                common.cuh against the saved tensors, store NHWC fp32 with 128-bit accesses
 #include "common.cuh"
@@ -33,6 +41,7 @@ struct TcGeom {
     int H, W, bh, bimg, tiles_per_img, Nimg;
     int n_m_tiles, n_n_tiles;
     int b_rows;         // rows of one plane of B (the lo plane of the 3xTF32 split starts at row b_rows)
+    int groups, tiles_per_group;   // gradient-row groups whose m-tiles are visited interleaved (1: natural order)
     uint32_t a_bytes;   // bytes one A load deposits (box volume * 4)
 };
 
@@ -116,21 +125,25 @@ __device__ __forceinline__ void tmem_ld_wait(float* v) {
 }
 
 // ------------------------------------------------------------------ kernel
-template <int BN, bool SPLIT3>
+template <int BN, int SPLIT>
 struct TcCfg {
     static constexpr uint32_t B_TILE_BYTES = BN * TC_BK * 4;
-    static constexpr uint32_t STAGE_BYTES = (A_TILE_BYTES + B_TILE_BYTES) * (SPLIT3 ? 2 : 1);
-    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;   // 3xTF32: 2 / 3 / 4 for BN = 256 / 128 / 64; TF32: 4 / 6 / 8
+    static constexpr uint32_t B_LO_BYTES = SPLIT == 1 ? B_TILE_BYTES : SPLIT == 3 ? B_TILE_BYTES / 2 : 0;
+    static constexpr uint32_t STAGE_BYTES = A_TILE_BYTES * (SPLIT ? 2 : 1) + B_TILE_BYTES + B_LO_BYTES;
+    static constexpr int STAGES_RAW = (192 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr uint32_t TMEM_COLS = 2 * BN;          // two accumulator stages (128 or 256: powers of two)
     static constexpr uint32_t PRM_BYTES = 2 * 6 * BN * 4;   // per accumulator stage: bn[4][BN] + bias_t[BN] + bias_p[BN]
     static constexpr uint32_t TR_BYTES = TC_EPI_WARPS * 2048;   // per epilogue warp: 32 rows x 16 columns transpose slab
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + PRM_BYTES + TR_BYTES;
 };
 
-template <int BN, bool SPLIT3, int KIND>
+template <int BN, int SPLIT, int KIND>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGeom g, const EpiParams ep) {
-    using Cfg = TcCfg<BN, SPLIT3>;
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmBlo, const TcGeom g, const EpiParams ep) {
+    using Cfg = TcCfg<BN, SPLIT>;
+    constexpr bool SPLIT3 = SPLIT != 0;          // the activation tile is split into (hi, lo)
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -149,7 +162,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto a_hi = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
     auto a_lo = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + A_TILE_BYTES; };                       // split only
     auto b_hi = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + (SPLIT3 ? 2 : 1) * A_TILE_BYTES; };
-    auto b_lo = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES; };   // split only
+    auto b_lo = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES; };   // SPLIT 1 / 3
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = g.n_m_tiles * g.n_n_tiles;
@@ -157,6 +170,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        if (SPLIT == 3) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -180,6 +194,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // tile -> coordinates
     auto tile_coords = [&](int tile, int& m0, int& mvalid, int& n_img0, int& h0, int& ncol0) {
         int mt = tile / g.n_n_tiles, nt = tile - mt * g.n_n_tiles;
+        // gradient-row groups (mate / non-mate rows of the same probes) read the same saved tensors: visit group 0's
+        // tile i, then group 1's tile i, ... so the second read of a saved tile hits L2 instead of HBM
+        if (g.groups > 1) mt = (mt % g.groups) * g.tiles_per_group + mt / g.groups;
         ncol0 = nt * BN;
         if (!g.a4d) {
             m0 = mt * TC_BM;
@@ -209,7 +226,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tile_coords(tile, m0, mvalid, n_img0, h0, ncol0);
                 for (int kb = 0; kb < g.num_k; ++kb) {
                     mbar_wait(empty_bar(s), ph ^ 1u);
-                    mbar_expect_tx(full_bar(s), g.a_bytes + (SPLIT3 ? 2 : 1) * Cfg::B_TILE_BYTES);
+                    mbar_expect_tx(full_bar(s), g.a_bytes + Cfg::B_TILE_BYTES + Cfg::B_LO_BYTES);
                     int tap = kb / g.kchunks;
                     int c0 = (kb - tap * g.kchunks) * TC_BK;
                     if (g.a4d) {
@@ -219,7 +236,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tma_load_2d(a_hi(s), &tmA, c0, m0, full_bar(s));
                     }
                     tma_load_2d(b_hi(s), &tmB, kb * TC_BK, ncol0, full_bar(s));
-                    if (SPLIT3) tma_load_2d(b_lo(s), &tmB, kb * TC_BK, g.b_rows + ncol0, full_bar(s));   // host-split lo plane
+                    if (SPLIT == 1) tma_load_2d(b_lo(s), &tmB, kb * TC_BK, g.b_rows + ncol0, full_bar(s));   // host-split lo plane
+                    if (SPLIT == 3) tma_load_2d(b_lo(s), &tmBlo, kb * TC_BK, g.b_rows + ncol0, full_bar(s));  // lo of the W half
                     if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
             }
@@ -227,6 +245,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        constexpr uint32_t idesc_half = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 4) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
         int s = 0;
         uint32_t ph = 0;
         int it = 0;
@@ -253,7 +272,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int k = 0; k < TC_BK / 8; ++k) {
                             const uint64_t koff = (uint64_t)((k * 32) >> 4);
                             tc_mma_tf32(tacc, dal + koff, dbh + koff, idesc, 1u);
-                            tc_mma_tf32(tacc, dah + koff, dbl + koff, idesc, 1u);
+                            if (SPLIT == 1) tc_mma_tf32(tacc, dah + koff, dbl + koff, idesc, 1u);
+                            if (SPLIT == 3) tc_mma_tf32(tacc, dah + koff, dbl + koff, idesc_half, 1u);   // columns [0, BN/2): the W half
                         }
                     }
                     tc_commit(empty_bar(s));                 // smem stage reusable once these MMAs retire
@@ -504,13 +524,14 @@ static bool encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t
 
 bool conv_tc_available() { return true; }
 
-template <int BN, bool SPLIT3, int KIND>
-static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGeom& g, const EpiParams& ep, cudaStream_t st) {
-    using Cfg = TcCfg<BN, SPLIT3>;
+template <int BN, int SPLIT, int KIND>
+static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo, const TcGeom& g,
+                              const EpiParams& ep, cudaStream_t st) {
+    using Cfg = TcCfg<BN, SPLIT>;
     static bool attr = false;
     static int sms = 0;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT3, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -519,13 +540,15 @@ static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, co
     }
     int total = g.n_m_tiles * g.n_n_tiles;
     int grid = total < sms ? total : sms;
-    conv_tc_kernel<BN, SPLIT3, KIND><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, g, ep);
+    conv_tc_kernel<BN, SPLIT, KIND><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmBlo, g, ep);
     return cudaGetLastError();
 }
 
-cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, const EpiParams& ep, int split3, int tn,
+cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, const EpiParams& ep, int split, int tn,
                            cudaStream_t st) {
-    if (cg.Cin % TC_BK != 0) return cudaErrorInvalidValue;
+    if (cg.Cin % TC_BK != 0 || split < 0 || split > 3) return cudaErrorInvalidValue;
+    if (split == 3 && ep.kind != EPI_FWD_DUAL) return cudaErrorInvalidValue;
+    if (split == 2 && ep.kind == EPI_FWD_DUAL) return cudaErrorInvalidValue;
     int BN;
     if (ep.kind == EPI_FWD_DUAL) {
         BN = tn;                                  // the dual pack fixes the tile width
@@ -546,7 +569,7 @@ cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, c
     g.b_rows = cg.Nn;
     const int HW = cg.H * cg.W;
     g.Nimg = ep.M / HW;
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmBlo;
     if (cg.R == 1) {
         g.a4d = 0;
         g.bh = g.bimg = g.tiles_per_img = 1;
@@ -582,26 +605,47 @@ cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, c
     }
     {
         // B is [planes][Nn][K]: plane 0 = rna_tf32(W) (or W itself for single-pass TF32), plane 1 = W - plane 0
-        cuuint64_t dims[2] = {(cuuint64_t)cg.K, (cuuint64_t)cg.Nn * (split3 ? 2 : 1)};
+        cuuint64_t dims[2] = {(cuuint64_t)cg.K, (cuuint64_t)cg.Nn * (split ? 2 : 1)};
         cuuint64_t strides[1] = {(cuuint64_t)cg.K * 4};
         cuuint32_t box[2] = {TC_BK, (cuuint32_t)BN};
         if (!encode(&tmB, B, 2, dims, strides, box)) return cudaErrorInvalidValue;
+        tmBlo = tmB;
+        if (split == 3) {
+            cuuint32_t box_half[2] = {TC_BK, (cuuint32_t)(BN / 2)};
+            if (!encode(&tmBlo, B, 2, dims, strides, box_half)) return cudaErrorInvalidValue;
+        }
     }
-#define XFRB_TC_DISPATCH(BN_, SP_)                                                                       \
+    // interleave the m-tiles of the gradient-row groups when every group is a whole number of tiles
+    g.groups = 1;
+    g.tiles_per_group = g.n_m_tiles;
+    if ((ep.kind == EPI_MID || ep.kind == EPI_JOIN) && ep.Ms > 0 && ep.M > ep.Ms && ep.M % ep.Ms == 0) {
+        int G = ep.M / ep.Ms;
+        if (g.n_m_tiles % G == 0 && (cg.R != 1 || ep.Ms % TC_BM == 0)) {
+            g.groups = G;
+            g.tiles_per_group = g.n_m_tiles / G;
+        }
+    }
+#define XFRB_TC_KINDS(BN_, SP_)                                                                          \
     switch (ep.kind) {                                                                                   \
-        case EPI_PLAIN: return launch_cfg<BN_, SP_, EPI_PLAIN>(tmA, tmB, g, ep, st);                      \
-        case EPI_FWD_DUAL: return launch_cfg<BN_, SP_, EPI_FWD_DUAL>(tmA, tmB, g, ep, st);                \
-        case EPI_MID: return launch_cfg<BN_, SP_, EPI_MID>(tmA, tmB, g, ep, st);                          \
-        case EPI_JOIN: return launch_cfg<BN_, SP_, EPI_JOIN>(tmA, tmB, g, ep, st);                        \
-        default: return cudaErrorInvalidValue;                                                           \
+        case EPI_PLAIN: return launch_cfg<BN_, SP_, EPI_PLAIN>(tmA, tmB, tmBlo, g, ep, st);               \
+        case EPI_MID: return launch_cfg<BN_, SP_, EPI_MID>(tmA, tmB, tmBlo, g, ep, st);                   \
+        case EPI_JOIN: return launch_cfg<BN_, SP_, EPI_JOIN>(tmA, tmB, tmBlo, g, ep, st);                 \
+        default: break;                                                                                  \
     }
-    if (BN == 256) {
-        if (split3) { XFRB_TC_DISPATCH(256, true) } else { XFRB_TC_DISPATCH(256, false) }
-    } else if (BN == 128) {
-        if (split3) { XFRB_TC_DISPATCH(128, true) } else { XFRB_TC_DISPATCH(128, false) }
-    } else {
-        if (split3) { XFRB_TC_DISPATCH(64, true) } else { XFRB_TC_DISPATCH(64, false) }
-    }
+#define XFRB_TC_DISPATCH(BN_)                                                                            \
+    if (ep.kind == EPI_FWD_DUAL) {                                                                       \
+        if (split == 0) return launch_cfg<BN_, 0, EPI_FWD_DUAL>(tmA, tmB, tmBlo, g, ep, st);              \
+        if (split == 1) return launch_cfg<BN_, 1, EPI_FWD_DUAL>(tmA, tmB, tmBlo, g, ep, st);              \
+        return launch_cfg<BN_, 3, EPI_FWD_DUAL>(tmA, tmB, tmBlo, g, ep, st);                              \
+    }                                                                                                    \
+    if (split == 0) { XFRB_TC_KINDS(BN_, 0) }                                                            \
+    else if (split == 1) { XFRB_TC_KINDS(BN_, 1) }                                                       \
+    else { XFRB_TC_KINDS(BN_, 2) }                                                                       \
+    return cudaErrorInvalidValue;
+    if (BN == 256) { XFRB_TC_DISPATCH(256) }
+    else if (BN == 128) { XFRB_TC_DISPATCH(128) }
+    else { XFRB_TC_DISPATCH(64) }
+#undef XFRB_TC_KINDS
 #undef XFRB_TC_DISPATCH
 }
 

@@ -13,8 +13,8 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libxfr_b200.so')
 
-IMPL_FP32, IMPL_TF32X3, IMPL_TF32 = 0, 1, 2
-IMPLS = {'fp32': IMPL_FP32, 'tf32x3': IMPL_TF32X3, 'tf32': IMPL_TF32}
+IMPL_FP32, IMPL_TF32X3, IMPL_TF32, IMPL_TF32X3_FULL = 0, 1, 2, 3
+IMPLS = {'fp32': IMPL_FP32, 'tf32x3': IMPL_TF32X3, 'tf32': IMPL_TF32, 'tf32x3full': IMPL_TF32X3_FULL}
 
 _P = ctypes.c_void_p
 _I = ctypes.c_int
@@ -157,8 +157,9 @@ class CudaBackend(object):
     def dgrad_plain(self, y, L, z_out, signed=False, accumulate=False):
         J, H, W, Cout = y.shape
         B = L.signed_dgrad() if signed else L.Bd
+        impl = IMPL_TF32X3_FULL if (signed and self.impl == IMPL_TF32X3) else self.impl     # signed weights: all three passes
         self._check(self.lib.xfrb_dgrad_plain(_ptr(y), _ptr(B), _ptr(z_out), J, H, W, L.cin, Cout, L.R,
-                                              1 if accumulate else 0, self.impl, self._st()))
+                                              1 if accumulate else 0, impl, self._st()))
 
     def dgrad_join(self, y1, L, g_res, out, o3, xr3, bn3, res, hooks, mode, g_out, y3_out):
         J, H, W, Cout = y1.shape

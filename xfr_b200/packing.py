@@ -29,14 +29,15 @@ def rna_tf32(t):
 
 def gemm_planes(B, impl):
     """Weight operand as the GEMM implementation wants it (include/xfrb.h):
-    'fp32' -> B ; 'tf32' -> rna_tf32(B) ; 'tf32x3' -> [2, rows, K] = (hi, lo) with hi + lo == B exactly."""
+    'fp32' -> B ; 'tf32' -> rna_tf32(B) ; 'tf32x3' / 'tf32x3full' -> [2, rows, K] = (hi, lo) with hi + lo == B exactly
+    (the two-pass W+ GEMMs of 'tf32x3' read only the hi plane)."""
     B = B.float().contiguous()
     if impl == 'fp32':
         return B
     hi = rna_tf32(B)
     if impl == 'tf32':
         return hi.contiguous()
-    if impl == 'tf32x3':
+    if impl in ('tf32x3', 'tf32x3full'):
         return torch.stack((hi, B - hi)).contiguous()
     raise ValueError(impl)
 
