@@ -87,3 +87,44 @@ def smooth_probes(n, seed=1):
     img = img.clamp(0, 255).round()
     mean = torch.tensor(MEAN_RGB, dtype=torch.float32).view(1, 3, 1, 1)
     return (img - mean).contiguous()
+
+
+# ---------------------------------------------------------------- Light-CNN-29v2 (reference lightcnn.py:216-275)
+LIGHTCNN_LAYERS = (1, 2, 3, 4)
+
+
+def lightcnn_convs(layers=LIGHTCNN_LAYERS):
+    """(prefix, cin, cout, k) of every mfm of network_29layers_v2 in forward order (the Conv2d has 2*cout outputs)."""
+    out = [('conv1', 1, 48, 5)]
+    for bi, (n, cin, cout) in enumerate(zip(layers, (48, 96, 192, 128), (96, 192, 128, 128)), start=1):
+        for i in range(n):
+            out.append(('block%d.%d.conv1' % (bi, i), cin, cin, 3))
+            out.append(('block%d.%d.conv2' % (bi, i), cin, cin, 3))
+        out.append(('group%d.conv_a' % bi, cin, cin, 1))
+        out.append(('group%d.conv' % bi, cin, cout, 3))
+    return out
+
+
+def lightcnn_state_dict(seed=0, num_classes=2, layers=LIGHTCNN_LAYERS):
+    """Seeded state_dict with the key layout of the reference network_29layers_v2 and torch's default
+    Conv2d / Linear initialisation statistics, U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weights and biases
+    (no Light-CNN weights are bundled with the reference)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for prefix, cin, cout, k in lightcnn_convs(layers):
+        bound = 1.0 / math.sqrt(cin * k * k)
+        sd[prefix + '.filter.weight'] = (torch.rand(2 * cout, cin, k, k, generator=g) * 2 - 1) * bound
+        sd[prefix + '.filter.bias'] = (torch.rand(2 * cout, generator=g) * 2 - 1) * bound
+    _linear(sd, 'fc', 256, 8 * 8 * 128, g)
+    _linear(sd, 'fc2', num_classes, 256, g, bias=False)
+    return sd
+
+
+def lightcnn_probes(n, seed=1, smooth=True):
+    """n synthetic Light-CNN inputs [n,1,128,128] in [0,1] (reference lightcnn.py:19-31: grayscale / 255)."""
+    g = torch.Generator().manual_seed(seed)
+    if smooth:
+        coarse = torch.rand(n, 1, 16, 16, generator=g) * 255.0
+        img = torch.nn.functional.interpolate(coarse, size=(128, 128), mode='bicubic', align_corners=False)
+        return (img.clamp(0, 255).round() / 255.0).contiguous()
+    return (torch.randint(0, 256, (n, 1, 128, 128), generator=g, dtype=torch.int32).float() / 255.0).contiguous()
