@@ -173,6 +173,7 @@ int xfrb_saliency_post(const float* mwp, float* out, int B, int H, int W, float 
  *   (a, x) from `recipe` over the saved tensors s0 [N,H,W,c0], s1 [N,H,W,C], s2 [N,H,W,c2s] and bn [4][C]
  *     0: a = x = relu(s0)   1: a = relu(bn(s0)), x = relu(relu(s0)*sp+tp)   2: a = x = relu(bn(s0))
  *     3: a = relu(s0), x = s1   4: a = relu(s0), x = relu(relu(bn(s1)) + relu(s2))   5: a = relu(s0), x = s1
+ *     6: a = relu(s0), x = relu(s1) + relu(s2)   7: a = relu(s0), x = relu(s1)      (Light-CNN: resblock output / Split input)
  *   p = a*relu(z), replaced for gradient row `prior_row` by the prior (a full tensor `prior` [H*W*C], or the single element
  *   prior_elem = prior_val); P_out <- p; return value per `mode` (`affine`: Conv/Linear/AvgPool/BatchNorm kinds;
  *   relu_or_maxpool = 2 marks ReLU/MaxPool kinds for the 'norelu' rule whitebox.py:418-419, passed with mode 1);
@@ -190,6 +191,36 @@ int xfrb_maxpool_bwd(const float* g, const float* o, const float* bn, float* out
 /* weighted_subtree_ebp layer score (whitebox.py:687-696): max / first argmax over n elements of m*(-gneg),
  * m = (gate >= 0) if gate_ge0 else (gate < 0) */
 int xfrb_subtree_score(const float* gate, const float* gneg, int gate_ge0, long long n, float* score, long long* arg, void* stream);
+
+/* ---- Light-CNN-29v2 (reference python/xfr/models/lightcnn.py:216-275, plugin whitebox.py:113-159) ----
+ * The net has no ReLU / BatchNorm: every `mfm` is Conv2d(in, 2*out) -> Split -> torch.max (lightcnn.py:48-62).  A conv output
+ * is stored as c [rows][2*Cp]: first Split half in columns [0,Cp), second in [Cp,2*Cp); Cp = `out` padded to the GEMM tile
+ * granularity (48 -> 64, 96 -> 128), padded columns are exact zeros.  The backward sweep is issued firing by firing through
+ * xfrb_hook (recipes 0, 3, 6, 7) with xfrb_dgrad_plain for the W+ transposed convs (xfr_b200/lightcnn.py). */
+
+/* out [N,H,W,Cout] = conv_B(inp [N,H,W,Cin]) + bias.  B [Cout][R*R*Cin] K-major ((r,s,ci) order, weight planes per `impl`),
+ * R = 1|3, stride 1, pad R/2; also the fc layer (H = W = 1).  positive = 1: B is relu(W) and inp >= 0 (two-pass plan under
+ * impl 1).  Replaces mfm.filter's forward (lightcnn.py:59) in the 'activation' / 'positive_activation' passes. */
+int xfrb_conv_bias(const float* inp, const float* B, const float* bias, float* out, int N, int H, int W, int Cin, int Cout, int R,
+                   int positive, int impl, void* stream);
+/* conv1 = Conv2d(1, 96, 5, 1, 2) (lightcnn.py:219): x [N,H,W] -> c [N,H,W,C2]; Wt [25][C2] tap-major in the padded column
+ * layout; cpos (may be NULL) = conv_relu(W)(relu(x)) + bpos, the positive-pass twin (X of the Split hook = P[-2]'s X). */
+int xfrb_lc_conv1(const float* x, const float* Wt, const float* b, const float* bpos, float* c, float* cpos, int N, int H, int W,
+                  int C2, void* stream);
+/* m = max(c[:, :Cp], c[:, Cp:]) [rows,Cp] (mfm.forward, lightcnn.py:58-62); y (may be NULL) = m + res (resblock Add,
+ * lightcnn.py:84-88); relu_out (may be NULL) = relu(y if y else m). */
+int xfrb_mfm_fwd(const float* c, const float* res, float* m, float* y, float* relu_out, long long rows, int Cp, void* stream);
+/* autograd of torch.max(a, b) + Split: g [rows,Cp], c [rows_saved,2*Cp] (row r reads r % rows_saved) -> z [rows,2*Cp];
+ * the larger branch takes g, exact ties take g/2 each. */
+int xfrb_mfm_bwd(const float* g, const float* c, float* z, long long rows, long long rows_saved, int Cp, void* stream);
+/* p = maxpool2(m) + avgpool2(m) (lightcnn.py:252-269); ppos (may be NULL) = the same on relu(m): the positive-pass value */
+int xfrb_pool2_fwd(const float* m, float* p, float* ppos, int N, int H, int W, int C, void* stream);
+/* its backward: gm [J,H,W,C] = MaxPool2d backward (first maximum wins, as torch) + AvgPool2d backward of g [J,H/2,W/2,C] */
+int xfrb_pool2_bwd(const float* g, const float* m, float* gm, int J, int N, int H, int W, int C, void* stream);
+/* out = relu(in), n floats (A operand of a positive-pass GEMM) */
+int xfrb_relu(const float* in, float* out, long long n, void* stream);
+/* chansum [J,HW] = sum_c P2 [J,HW,C]; sums [J] (double) = total per row  (whitebox.py:499, 524-525) */
+int xfrb_chansum(const float* P2, float* chansum, double* sums, int J, int HW, int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -251,6 +251,10 @@ class EmulBackend(object):
         elif recipe == 4:
             a = relu(v0)
             x = relu(relu(v1 * alpha + beta) + (relu(v2) if v2 is not None else 0))
+        elif recipe == 6:
+            a, x = relu(v0), relu(v1) + relu(v2)
+        elif recipe == 7:
+            a, x = relu(v0), relu(v1)
         else:
             a, x = relu(v0), v1
         if mode == 3:                                    # XFRB_MODE_NONE: true gradient, dA recording
@@ -387,3 +391,53 @@ class EmulBackend(object):
             img = np.maximum(0, img)
             img = img / max(img.sum(), self.eps)
             out[i].copy_(torch.from_numpy(img))
+
+    # ------------------------------------------------------------ Light-CNN-29v2 pieces (include/xfrb.h)
+    def conv_bias(self, inp, B, bias, out, R, positive=False):
+        out.view(-1, out.shape[-1]).copy_(im2col_nhwc(inp, R, R, R // 2) @ _w(B).t() + bias)
+
+    def lc_conv1(self, x, Wt, b, bpos, c, cpos=None):
+        C2 = Wt.shape[1]
+        w = Wt.t().reshape(C2, 1, 5, 5)
+        c.copy_(F.conv2d(x.unsqueeze(1), w, b, 1, 2).permute(0, 2, 3, 1))
+        if cpos is not None:
+            cpos.copy_(F.conv2d(relu(x).unsqueeze(1), relu(w), bpos, 1, 2).permute(0, 2, 3, 1))
+
+    def mfm_fwd(self, c, m, res=None, y=None, relu_out=None):
+        cp = m.shape[-1]
+        v = torch.max(c[..., :cp], c[..., cp:])
+        m.copy_(v)
+        if y is not None:
+            v = v + res
+            y.copy_(v)
+        if relu_out is not None:
+            relu_out.copy_(relu(v))
+
+    def mfm_bwd(self, g, c, z):
+        cp = g.shape[-1]
+        cc = _rows(c, g.shape[0])
+        a, b = cc[..., :cp], cc[..., cp:]
+        t = torch.where(a == b, g / 2, g)
+        z[..., :cp] = t.masked_fill(a < b, 0)
+        z[..., cp:] = t.masked_fill(b < a, 0)
+
+    def pool2_fwd(self, m, p, ppos=None):
+        f = lambda t: (F.max_pool2d(t.permute(0, 3, 1, 2), 2) + F.avg_pool2d(t.permute(0, 3, 1, 2), 2)).permute(0, 2, 3, 1)
+        p.copy_(f(m))
+        if ppos is not None:
+            ppos.copy_(f(relu(m)))
+
+    def pool2_bwd(self, g, m, gm):
+        mm = _rows(m, g.shape[0]).permute(0, 3, 1, 2).contiguous()
+        gg = g.permute(0, 3, 1, 2).contiguous()
+        _, idx = F.max_pool2d(mm, 2, return_indices=True)
+        out = torch.zeros_like(mm).flatten(2).scatter_add_(2, idx.flatten(2), gg.flatten(2)).view_as(mm)
+        out = out + F.interpolate(gg, scale_factor=2, mode='nearest') / 4.0
+        gm.copy_(out.permute(0, 2, 3, 1))
+
+    def relu(self, inp, out):
+        out.copy_(relu(inp))
+
+    def chansum(self, P2, chansum, sums):
+        chansum.copy_(P2.sum(-1))
+        sums.copy_(P2.double().sum(dim=(1, 2, 3)))

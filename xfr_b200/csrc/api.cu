@@ -34,6 +34,14 @@ cudaError_t launch_stem_bwd(const float*, const float*, const float*, const floa
 cudaError_t launch_contrast(const float*, const double*, const float*, float*, int, int, int, cudaStream_t);
 cudaError_t launch_trunc_threshold(const float*, const double*, float, float*, int, size_t, cudaStream_t);
 cudaError_t launch_saliency_post(const float*, float*, int, int, int, float, cudaStream_t);
+// lightcnn.cu
+cudaError_t launch_lc_conv1(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, cudaStream_t);
+cudaError_t launch_mfm_fwd(const float*, const float*, float*, float*, float*, size_t, int, cudaStream_t);
+cudaError_t launch_mfm_bwd(const float*, const float*, float*, size_t, size_t, int, cudaStream_t);
+cudaError_t launch_pool2_fwd(const float*, float*, float*, int, int, int, int, cudaStream_t);
+cudaError_t launch_pool2_bwd(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+cudaError_t launch_relu(const float*, float*, size_t, cudaStream_t);
+cudaError_t launch_chansum(const float*, float*, double*, int, int, int, cudaStream_t);
 
 static int finish(const char* what, cudaError_t e) {
     if (e != cudaSuccess) {
@@ -227,7 +235,7 @@ int xfrb_hook(const float* z_in, int up, int zc, const float* z_in2, int k2, int
               const float* s1, const float* s2, int c2s, const float* bn, const float* prior, int prior_row, long long prior_elem,
               float prior_val, float* P_out, float* z_out, int recipe, int affine, int relu_or_maxpool, int mode, int post_mask,
               int post_scale_row, int J, int N, int H, int W, int C, float eps, void* stream) {
-    if (up < 1 || k2 < 1 || recipe < 0 || recipe > 5) return finish("xfrb_hook", cudaErrorInvalidValue);
+    if (up < 1 || k2 < 1 || recipe < 0 || recipe > 7) return finish("xfrb_hook", cudaErrorInvalidValue);
     HookArgs a;
     a.z_in = z_in; a.up = up; a.zc = zc; a.z_in2 = z_in2; a.k2 = k2; a.c2 = c2; a.pre_scale = pre_scale;
     a.s0 = s0; a.s1 = s1; a.s2 = s2; a.c0 = c0; a.c2s = c2s; a.bn = bn; a.prior = prior; a.P_out = P_out; a.z_out = z_out;
@@ -298,6 +306,56 @@ int xfrb_trunc_threshold(const float* P2, const double* sums, float percentile, 
 int xfrb_saliency_post(const float* mwp, float* out, int B, int H, int W, float eps, void* stream) {
     if (H > 128 || W > 128) return finish("xfrb_saliency_post", cudaErrorInvalidValue);
     return finish("xfrb_saliency_post", launch_saliency_post(mwp, out, B, H, W, eps, (cudaStream_t)stream));
+}
+
+/* ---- Light-CNN-29v2 ---- */
+
+int xfrb_conv_bias(const float* inp, const float* B, const float* bias, float* out, int N, int H, int W, int Cin, int Cout, int R,
+                   int positive, int impl, void* stream) {
+    if (R != 1 && R != 3) return finish("xfrb_conv_bias", cudaErrorInvalidValue);
+    ConvGeom g{H, W, Cin, R, R * R * Cin, Cout};
+    EpiParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.kind = EPI_PLAIN;
+    ep.M = ep.Ms = N * H * W;
+    ep.C = Cout;
+    ep.bias = bias;
+    ep.out0 = out;
+    return finish("xfrb_conv_bias", run_gemm(inp, B, g, ep, impl, (cudaStream_t)stream, 0, positive != 0));
+}
+
+int xfrb_lc_conv1(const float* x, const float* Wt, const float* b, const float* bpos, float* c, float* cpos, int N, int H, int W,
+                  int C2, void* stream) {
+    return finish("xfrb_lc_conv1", launch_lc_conv1(x, Wt, b, bpos, c, cpos, N, H, W, C2, (cudaStream_t)stream));
+}
+
+int xfrb_mfm_fwd(const float* c, const float* res, float* m, float* y, float* relu_out, long long rows, int Cp, void* stream) {
+    if (Cp % 4 || (y != nullptr && res == nullptr)) return finish("xfrb_mfm_fwd", cudaErrorInvalidValue);
+    return finish("xfrb_mfm_fwd", launch_mfm_fwd(c, res, m, y, relu_out, (size_t)rows, Cp, (cudaStream_t)stream));
+}
+
+int xfrb_mfm_bwd(const float* g, const float* c, float* z, long long rows, long long rows_saved, int Cp, void* stream) {
+    if (Cp % 4 || rows_saved <= 0 || rows % rows_saved) return finish("xfrb_mfm_bwd", cudaErrorInvalidValue);
+    return finish("xfrb_mfm_bwd", launch_mfm_bwd(g, c, z, (size_t)rows, (size_t)rows_saved, Cp, (cudaStream_t)stream));
+}
+
+int xfrb_pool2_fwd(const float* m, float* p, float* ppos, int N, int H, int W, int C, void* stream) {
+    if ((H | W) & 1 || C % 4) return finish("xfrb_pool2_fwd", cudaErrorInvalidValue);
+    return finish("xfrb_pool2_fwd", launch_pool2_fwd(m, p, ppos, N, H, W, C, (cudaStream_t)stream));
+}
+
+int xfrb_pool2_bwd(const float* g, const float* m, float* gm, int J, int N, int H, int W, int C, void* stream) {
+    if ((H | W) & 1 || C % 4 || N <= 0 || J % N) return finish("xfrb_pool2_bwd", cudaErrorInvalidValue);
+    return finish("xfrb_pool2_bwd", launch_pool2_bwd(g, m, gm, J, N, H, W, C, (cudaStream_t)stream));
+}
+
+int xfrb_relu(const float* in, float* out, long long n, void* stream) {
+    if (n % 4) return finish("xfrb_relu", cudaErrorInvalidValue);
+    return finish("xfrb_relu", launch_relu(in, out, (size_t)n, (cudaStream_t)stream));
+}
+
+int xfrb_chansum(const float* P2, float* chansum, double* sums, int J, int HW, int C, void* stream) {
+    return finish("xfrb_chansum", launch_chansum(P2, chansum, sums, J, HW, C, (cudaStream_t)stream));
 }
 
 }  // extern "C"

@@ -520,6 +520,8 @@ cudaError_t launch_head_seed(const float* Pn, const float* W2, int C, int D, int
 //   3: a = relu(s0), x = s1                               (BatchNorm hook: s0 = o, s1 = xr)
 //   4: a = relu(s0), x = relu(relu(bn(s1)) + relu(s2))    (STR block ReLU hook: s0 = out, s1 = o3, s2 = residual)
 //   5: a = relu(s0), x = s1                               (materialised pair, e.g. the Multiply hook)
+//   6: a = relu(s0), x = relu(s1) + relu(s2)              (Light-CNN resblock output: s0 = out + res, s1 = out, s2 = res)
+//   7: a = relu(s0), x = relu(s1)                         (Light-CNN Split hook: s0 = conv output, s1 = its positive twin)
 __global__ void hook_kernel(HookArgs A, size_t total) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -555,6 +557,8 @@ __global__ void hook_kernel(HookArgs A, size_t total) {
             x = fmaxf(__fadd_rn(bn_act(A.s1[ms * A.C + c], b), r), 0.f);
             break;
         }
+        case 6: a = fmaxf(v0, 0.f); x = __fadd_rn(fmaxf(A.s1[ms * A.C + c], 0.f), fmaxf(A.s2[ms * A.C + c], 0.f)); break;
+        case 7: a = fmaxf(v0, 0.f); x = fmaxf(A.s1[ms * A.C + c], 0.f); break;
         default: a = fmaxf(v0, 0.f); x = A.s1[ms * A.C + c]; break;
     }
     const size_t off = i;

@@ -46,6 +46,14 @@ _SIGNATURES = {
     'xfrb_contrast': [_P, _P, _P, _P, _I, _I, _I, _P],
     'xfrb_trunc_threshold': [_P, _P, _F, _P, _I, ctypes.c_longlong, _P],
     'xfrb_saliency_post': [_P, _P, _I, _I, _I, _F, _P],
+    'xfrb_conv_bias': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'xfrb_lc_conv1': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    'xfrb_mfm_fwd': [_P, _P, _P, _P, _P, ctypes.c_longlong, _I, _P],
+    'xfrb_mfm_bwd': [_P, _P, _P, ctypes.c_longlong, ctypes.c_longlong, _I, _P],
+    'xfrb_pool2_fwd': [_P, _P, _P, _I, _I, _I, _I, _P],
+    'xfrb_pool2_bwd': [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    'xfrb_relu': [_P, _P, ctypes.c_longlong, _P],
+    'xfrb_chansum': [_P, _P, _P, _I, _I, _I, _P],
 }
 EXPORTS = ['xfrb_version', 'xfrb_last_error', 'xfrb_device_ok', 'xfrb_impl_available'] + sorted(_SIGNATURES)
 
@@ -249,3 +257,37 @@ class CudaBackend(object):
     def saliency_post(self, mwp, out):
         B, H, W = mwp.shape
         self._check(self.lib.xfrb_saliency_post(_ptr(mwp), _ptr(out), B, H, W, self.eps, self._st()))
+
+    # -------------------------------------------------------------- Light-CNN-29v2 pieces
+    def conv_bias(self, inp, B, bias, out, R, positive=False):
+        N, H, W, Cin = inp.shape
+        self._check(self.lib.xfrb_conv_bias(_ptr(inp), _ptr(B), _ptr(bias), _ptr(out), N, H, W, Cin, out.shape[-1], R,
+                                            1 if positive else 0, self.impl, self._st()))
+
+    def lc_conv1(self, x, Wt, b, bpos, c, cpos=None):
+        N, H, W = x.shape
+        self._check(self.lib.xfrb_lc_conv1(_ptr(x), _ptr(Wt), _ptr(b), _ptr(bpos), _ptr(c), _ptr(cpos), N, H, W, c.shape[-1],
+                                           self._st()))
+
+    def mfm_fwd(self, c, m, res=None, y=None, relu_out=None):
+        Cp = m.shape[-1]
+        self._check(self.lib.xfrb_mfm_fwd(_ptr(c), _ptr(res), _ptr(m), _ptr(y), _ptr(relu_out), m.numel() // Cp, Cp, self._st()))
+
+    def mfm_bwd(self, g, c, z):
+        Cp = g.shape[-1]
+        self._check(self.lib.xfrb_mfm_bwd(_ptr(g), _ptr(c), _ptr(z), g.numel() // Cp, c.numel() // (2 * Cp), Cp, self._st()))
+
+    def pool2_fwd(self, m, p, ppos=None):
+        N, H, W, C = m.shape
+        self._check(self.lib.xfrb_pool2_fwd(_ptr(m), _ptr(p), _ptr(ppos), N, H, W, C, self._st()))
+
+    def pool2_bwd(self, g, m, gm):
+        N, H, W, C = m.shape
+        self._check(self.lib.xfrb_pool2_bwd(_ptr(g), _ptr(m), _ptr(gm), g.shape[0], N, H, W, C, self._st()))
+
+    def relu(self, inp, out):
+        self._check(self.lib.xfrb_relu(_ptr(inp), _ptr(out), inp.numel(), self._st()))
+
+    def chansum(self, P2, chansum, sums):
+        J, H, W, C = P2.shape
+        self._check(self.lib.xfrb_chansum(_ptr(P2), _ptr(chansum), _ptr(sums), J, H * W, C, self._st()))

@@ -196,3 +196,90 @@ class LinearHead(object):
     def to(self, device):
         self.Bfe, self.BfeT = self.Bfe.to(device), self.BfeT.to(device)
         return self
+
+
+# ---------------------------------------------------------------- Light-CNN-29v2 (reference lightcnn.py:48-62, 216-275)
+def lc_pad(c):
+    """Channel count padded to the GEMM tile granularity (multiples of 64: 48 -> 64, 96 -> 128)."""
+    return ((c + 63) // 64) * 64
+
+
+def _mfm_padded(w, b):
+    """w [2C, cin, R, S], b [2C] -> zero-padded (w [2Cp, cin_p, R, S], b [2Cp]) with Split half h at rows [h*Cp, h*Cp + C)."""
+    c2, cin, R, S = w.shape
+    C = c2 // 2
+    cp, cin_p = lc_pad(C), (lc_pad(cin) if cin > 1 else 1)
+    wp = torch.zeros(2 * cp, cin_p, R, S)
+    bp = torch.zeros(2 * cp)
+    for h in (0, 1):
+        wp[h * cp:h * cp + C, :cin] = w[h * C:(h + 1) * C]
+        bp[h * cp:h * cp + C] = b[h * C:(h + 1) * C]
+    return wp, bp, C, cp, cin, cin_p
+
+
+class MfmConv(object):
+    """One mfm's Conv2d(in, 2*out, k, 1, k//2) packed for the forward GEMM (true and relu(W) twins) and the W+ dgrad."""
+
+    def __init__(self, sd, name, impl='fp32', with_bias=False):
+        w, b = sd[name + '.filter.weight'].float(), sd[name + '.filter.bias'].float()
+        wp, bp, self.c, self.cp, self.cin_real, self.cin = _mfm_padded(w, b)      # cin: padded width (GEMM N of the dgrad)
+        self.name, self.impl = name, impl
+        self.R = self.S = w.shape[-1]
+        flat = lambda t: t.permute(0, 2, 3, 1).reshape(t.shape[0], -1)            # [2Cp][(r,s,ci)]
+        self.Bf = gemm_planes(flat(wp), impl)
+        self.Bfp = gemm_planes(flat(torch.clamp_min(wp, 0)), impl)
+        self.bias = bp.contiguous()
+        self.bias_pos = (torch.clamp_min(bp, 0) if with_bias else bp).contiguous()
+        self.Bd = gemm_planes(pack_dgrad(wp, positive=True), impl)                  # [cin_p][R*S*2Cp]
+        self.Bd_signed = None
+        self._w = wp
+
+    def signed_dgrad(self):
+        if self.Bd_signed is None:
+            self.Bd_signed = gemm_planes(pack_dgrad(self._w, positive=False), self.impl).to(self.Bd.device)
+        return self.Bd_signed
+
+    def to(self, device):
+        for k in ('Bf', 'Bfp', 'bias', 'bias_pos', 'Bd'):
+            setattr(self, k, getattr(self, k).to(device))
+        return self
+
+
+class MfmStem(object):
+    """conv1 = mfm(1, 48, 5, 1, 2) (lightcnn.py:219): tap-major weights [25][2*Cp] for the direct kernel."""
+
+    def __init__(self, sd, name='conv1', with_bias=False):
+        w, b = sd[name + '.filter.weight'].float(), sd[name + '.filter.bias'].float()
+        wp, bp, self.c, self.cp, _, _ = _mfm_padded(w, b)
+        self.Wt = wp.reshape(2 * self.cp, 25).t().contiguous()
+        self.b = bp.contiguous()
+        self.bpos = (torch.clamp_min(bp, 0) if with_bias else bp).contiguous()
+
+    def to(self, device):
+        for k in ('Wt', 'b', 'bpos'):
+            setattr(self, k, getattr(self, k).to(device))
+        return self
+
+
+class LcHead(object):
+    """fc = Linear(8*8*128, 256) on the NCHW-flattened pool4 output (lightcnn.py:271-272); columns re-ordered to the
+    NHWC flattening used on the device.  fc2 (if present) is the network's own classifier [C,256]."""
+
+    def __init__(self, sd, impl='fp32', with_bias=False):
+        W = sd['fc.weight'].float()
+        b = sd['fc.bias'].float()
+        Wn = W.view(256, 128, 8, 8).permute(0, 2, 3, 1).reshape(256, 8192).contiguous()
+        self.Bfc = gemm_planes(Wn, impl)
+        self.Bfc_pos = gemm_planes(torch.clamp_min(Wn, 0), impl)
+        self.bfc = b.contiguous()
+        self.bfc_pos = (torch.clamp_min(b, 0) if with_bias else b).contiguous()
+        self.BfcT_pos = gemm_planes(torch.clamp_min(Wn, 0).t(), impl)              # [8192][256]: dgrad operand
+        self.BfcT_signed = gemm_planes(Wn.t(), impl)
+        self.W2 = sd['fc2.weight'].float().contiguous() if 'fc2.weight' in sd else None
+
+    def to(self, device):
+        for k in ('Bfc', 'Bfc_pos', 'bfc', 'bfc_pos', 'BfcT_pos', 'BfcT_signed', 'W2'):
+            v = getattr(self, k)
+            if v is not None:
+                setattr(self, k, v.to(device))
+        return self
