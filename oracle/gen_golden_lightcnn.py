@@ -91,6 +91,23 @@ def main(check):
     G['lw_k'] = np.array(ks)
     for k in ks:
         G['lw_elem_%d' % k] = wb.layerwise_ebp(probe, k_layer=k, mode='argmax', mwp=True)
+    # layerwise_ebp(mode='elementwise'): the reference indexes the flattened [1,C,H,W] MWP (whitebox.py:572-577)
+    wb.ebp(probe, P0)
+    el = [int(torch.argmax(wb.P[k].flatten())) for k in ks]
+    G['lw_el_idx'] = np.array(el)
+    for k, e in zip(ks, el):
+        G['lw_el_%d' % k] = wb.layerwise_ebp(probe, k_layer=k, mode='elementwise', k_element=e, mwp=True)
+    # weighted_subtree_ebp (whitebox.py:647-737) in two configurations
+    for tag, kw in (('a', dict(topk=8, do_max_subtree=False, do_mated_similarity_gating=True, subtree_mode='affineonly_with_prior')),
+                    ('b', dict(topk=4, do_max_subtree=True, do_mated_similarity_gating=False, subtree_mode='all'))):
+        wbs = Whitebox(WhiteboxLightCNN(ref_net()))
+        wbs.net.set_triplet_classifier(x_mate, x_non)
+        smap, P_img, P_sub, k_sub = wbs.weighted_subtree_ebp(probe, 0, 1, verbose=False, **kw)
+        G['ws_%s_smap' % tag] = smap
+        G['ws_%s_scores' % tag] = np.array(P_sub, dtype=np.float64)
+        G['ws_%s_k' % tag] = np.array(k_sub)
+        G['ws_%s_first' % tag] = P_img[-1]
+        print('weighted_subtree', tag, 'k', list(k_sub), 'scores', ['%.3g' % v for v in P_sub])
     out = os.path.join(ROOT, 'tests', 'golden', 'lightcnn29v2_seed0.npz')
     np.savez_compressed(out, **G)
     print('wrote', out, os.path.getsize(out) // 1024, 'KB')

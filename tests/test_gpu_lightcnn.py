@@ -126,3 +126,52 @@ def test_batch_512_properties():
         assert torch.allclose(a.sum(dim=(1, 2)), torch.ones(N, device=dev), atol=1e-4)
         one = eng.ebp(x[5:6].contiguous(), P1[5:6].contiguous(), W2[5:6].contiguous(), mode).clone()
         assert float((one[0] - a[5]).abs().max() / a[5].max()) < 1e-4
+
+
+def test_whitebox_api_vs_reference():
+    """The drop-in plugin classes used the way demo/test_whitebox.py / create_wbnet.py use the reference's."""
+    import PIL.Image
+    from xfr_b200 import whitebox
+    G, sd, imgs, _, _ = lc_setup()
+    dev = torch.device('cuda:0')
+    sdg = {k: v.to(dev) for k, v in sd.items()}
+    wb = whitebox.Whitebox(whitebox.WhiteboxLightCNN(sdg))
+    probe = imgs[0:1]                                           # [1,1,128,128] like net.preprocess() returns
+    assert wb.net.num_classes() == NUM_CLASSES
+    x_mate, x_non = wb.net.encode(imgs[1:2]), wb.net.encode(imgs[2:3])
+    assert rel_err(x_mate.cpu().numpy(), G['enc_mate']) < 1e-3
+    wb.net.set_triplet_classifier(x_mate, x_non)
+    assert wb.net.num_classes() == 2 and tuple(wb.net.classify(probe).shape) == (1, 2)
+    P = torch.zeros(1, 2)
+    P[0][0] = 1.0
+    e = wb.ebp(probe, P)
+    assert e.shape == (128, 128) and e.dtype == np.float32
+    assert rel_err(e, G['ebp_awp_smooth']) < 2e-2 and np.abs(e - G['ebp_awp_smooth']).max() < 1e-4
+    c = wb.contrastive_ebp(probe, k_poschannel=0, k_negchannel=1)
+    assert np.abs(c - G['cebp_awp_smooth']).max() < 1e-4 and rel_err(c, G['cebp_awp_smooth']) < 5e-2
+    t = wb.truncated_contrastive_ebp(probe, 0, 1, percentile=20)
+    assert np.abs(t - G['tcebp20_awp_smooth']).max() < 1e-4 and rel_err(t, G['tcebp20_awp_smooth']) < 5e-2
+    for k, el in zip(G['lw_k'], G['lw_el_idx']):
+        m = wb.layerwise_ebp(probe, k_layer=int(k), mode='argmax', mwp=True)
+        assert rel_err(m, G['lw_elem_%d' % k]) < 2e-2, k
+        m = wb.layerwise_ebp(probe, k_layer=int(k), mode='elementwise', k_element=int(el), mwp=True)
+        assert rel_err(m, G['lw_el_%d' % k]) < 2e-2, k
+    assert len(wb.P) == 87 and tuple(wb.P[-2].shape) == (1, 96, 128, 128) and tuple(wb.P[0].shape) == (1, 8192)
+    assert [n for n in wb.P_layername] == [str(n) for n in G['P_kinds']]
+    # weighted_subtree_ebp, two configurations (whitebox.py:647-737)
+    for tag, kw in (('a', dict(topk=8, do_max_subtree=False, do_mated_similarity_gating=True, subtree_mode='affineonly_with_prior')),
+                    ('b', dict(topk=4, do_max_subtree=True, do_mated_similarity_gating=False, subtree_mode='all'))):
+        wbs = whitebox.Whitebox(whitebox.WhiteboxLightCNN(sdg))
+        wbs.net.set_triplet_classifier(x_mate, x_non)
+        smap, P_img, P_sub, k_sub = wbs.weighted_subtree_ebp(probe, 0, 1, verbose=False, **kw)
+        assert wbs.ebp_subtree_mode() == kw['subtree_mode']
+        assert np.allclose(sorted(P_sub), sorted(G['ws_%s_scores' % tag]), rtol=2e-2)
+        if tag == 'a':                                            # 'b' has exact score ties: the order of equal layers is free
+            assert [int(k) for k in k_sub] == [int(k) for k in G['ws_a_k']]
+            assert rel_err(P_img[-1], G['ws_a_first']) < 5e-2
+        assert smap.shape == (128, 128) and np.abs(smap - G['ws_%s_smap' % tag]).max() < 1e-4
+        assert rel_err(smap, G['ws_%s_smap' % tag]) < 0.1, tag
+    # preprocess: PIL image -> [1,1,128,128] in [0,1]
+    im = PIL.Image.fromarray(np.random.RandomState(0).randint(0, 255, (300, 200, 3)).astype(np.uint8))
+    xp = wb.net.preprocess(im)
+    assert tuple(xp.shape) == (1, 1, 128, 128) and float(xp.min()) >= 0 and float(xp.max()) <= 1

@@ -184,6 +184,15 @@ class StResnetEngine(_Engine):
         self.saved = S
         return S['xn']
 
+    # ------------------------------------------------------------ generic (firing-by-firing) operators
+    def sweep(self):
+        from .generic import GenericSweep
+        return GenericSweep(self)
+
+    def logits(self, W2):
+        """classify() of the triplet head for probe 0: (50 * xn) @ W2^T  (resnet.py:252-258, whitebox.py:93-96)"""
+        return (50.0 * self.saved['xn'][0:1]) @ W2[0].t()
+
     # ------------------------------------------------------------ backward
     def hooked_fc2_seed(self, Pn, W2, m, prior=None, P_out=None):
         """The network's own fc2 takes part in EBP (no set_triplet_classifier): gradient Pn @ relu(W2) at the fc2 input,

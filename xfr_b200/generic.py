@@ -31,6 +31,21 @@ class GenericSweep(object):
         self.be = engine.be
 
     # -------------------------------------------------------------------------------------------------
+    @staticmethod
+    def elem_index(k, e, shape):
+        """The reference indexes flattened [1,C,H,W] tensors (whitebox.py:575-577); device tensors here are [1,H,W,C]."""
+        _, H, W, C = shape
+        c, hw = divmod(int(e), H * W)
+        h, w = divmod(hw, W)
+        return (h * W + w) * C + c
+
+    @staticmethod
+    def to_reference(k, p):
+        """Recorded MWP of firing k as the reference exposes it in self.P: [J,C,H,W] (vectors: [J,C])."""
+        if p is None:
+            return None
+        return p.permute(0, 3, 1, 2) if p.shape[1] * p.shape[2] > 1 else p.reshape(p.shape[0], -1)
+
     def run(self, Pn, W2, mode, priors=None, record=False, true_grad=False, hooked_fc2=False):
         """One sweep over J = Pn.shape[0] gradient rows.
         priors: {firing k: (row, elem, value) | (row, tensor)}; record: keep p of every firing (list of [J,H,W,C]

@@ -182,8 +182,10 @@ class LightCNNSweep(object):
         self._k = 0
         self._P = [] if record else None
         self._names = []
+        self._layout = []                            # per firing: (real channels, padded channels, is_split)
         self._priors = priors or {}
         self._norelu = (mode == 'norelu')
+        self._k_fcvec = -1
         self._m = m = MODE_NONE if true_grad else MODE_IDS[mode]
         need_x = (not true_grad) and mode in ('all', 'norelu')
         if need_x or (hooked_fc2 and not true_grad):
@@ -209,15 +211,16 @@ class LightCNNSweep(object):
         else:
             be.head_seed(Pn, W2, seed.view(J, 256))
         z = dgrad(seed, eng.fc_pack, buf('lc_gv', J, 1, 1, 8192)).view(J, 8, 8, 128)
+        self._k_fcvec = self._k
         z = self.fire('Linear', 3, z, (J, 8, 8, 128), s0=S['p4'], s1=S['p4pos'], out='lc_g8')
 
-        def pooled_site(mt, g_p, tag):
+        def pooled_site(mt, g_p, tag, rc):
             """hooks [MaxPool2d, AvgPool2d] on the tensor that feeds a pooled sum"""
             n_, h_, w_, c_ = mt.shape
             gm = buf('lc_pb' + tag, J, h_, w_, c_)
             be.pool2_bwd(g_p, mt, gm)
-            zz = self.fire('MaxPool2d', 0, gm, (J, h_, w_, c_), s0=mt, out='lc_pa' + tag)
-            return self.fire('AvgPool2d', 0, zz, (J, h_, w_, c_), s0=mt, out='lc_pb' + tag)
+            zz = self.fire('MaxPool2d', 0, gm, (J, h_, w_, c_), s0=mt, out='lc_pa' + tag, rc=rc)
+            return self.fire('AvgPool2d', 0, zz, (J, h_, w_, c_), s0=mt, out='lc_pb' + tag, rc=rc)
 
         def through_mfm(name, g_m, P_force=None):
             """gradient at an mfm output (its hooks applied) -> gradient at the mfm input (before its hooks)"""
@@ -227,12 +230,12 @@ class LightCNNSweep(object):
             be.mfm_bwd(g_m, st.c, zc)
             last = name == 'conv1'
             yc = self.fire('Split', 7, zc, (J, hw, hw, 2 * cp), s0=st.c, s1=st.cpos if st.cpos is not None else st.c,
-                           out=None if last else 'lc_yc', P_force=P_force)
+                           out=None if last else 'lc_yc', P_force=P_force, rc=st.L.c, split=True)
             if last:
                 return None
             return dgrad(yc, st.L, buf('lc_zu', J, hw, hw, st.L.cin))
 
-        z = pooled_site(S['pool4_in'], z, '4')
+        z = pooled_site(S['pool4_in'], z, '4', 128)
         stages = S['stages']
         for bi in range(len(stages), 0, -1):
             sg = stages[bi - 1]
@@ -240,14 +243,15 @@ class LightCNNSweep(object):
             z = through_mfm('group%d.conv' % bi, z)
             mga = sites['group%d.conv_a' % bi].m
             shp = (J, hw, hw, mga.shape[-1])
-            z = self.fire('Conv2d', 0, z, shp, s0=mga, out='lc_a')
+            rc = sites['group%d.conv_a' % bi].L.c       # real channel count of this stage's block tensors
+            z = self.fire('Conv2d', 0, z, shp, s0=mga, out='lc_a', rc=rc)
             z = through_mfm('group%d.conv_a' % bi, z)
             blocks = sg['blocks']
             z2 = None                                # residual-path gradient waiting to be summed at the next firing
             for i in range(len(blocks) - 1, -1, -1):
                 B = blocks[i]
                 shp = (J, hw, hw, B['y'].shape[-1])
-                yrec = dict(s0=B['y'], s1=B['out'], s2=B['res'])
+                yrec = dict(s0=B['y'], s1=B['out'], s2=B['res'], rc=rc)
                 gname = 'lc_gres%d' % (i % 2)          # Add backward: the same gradient goes to `out` and to `res`
                 if i + 1 < len(blocks):
                     z = self.fire('Conv2d', 6, z, shp, z_in2=z2, out='lc_a', **yrec)
@@ -256,15 +260,15 @@ class LightCNNSweep(object):
                     g_res = self.fire('Conv2d', 6, z, shp, z_in2=z2, out=gname, **yrec)
                 if i > 0:
                     pb = blocks[i - 1]
-                    rres, rrec = 6, dict(s0=pb['y'], s1=pb['out'], s2=pb['res'])
+                    rres, rrec = 6, dict(s0=pb['y'], s1=pb['out'], s2=pb['res'], rc=rc)
                 elif sg['pool_in'] is not None:
-                    rres, rrec = 3, dict(s0=sg['p'], s1=sg['ppos'])
+                    rres, rrec = 3, dict(s0=sg['p'], s1=sg['ppos'], rc=rc)
                 else:
-                    rres, rrec = 0, dict(s0=B['res'])                 # block4.0: the residual is group3's MFM output
+                    rres, rrec = 0, dict(s0=B['res'], rc=rc)          # block4.0: the residual is group3's MFM output
                 z = self.fire('Add', rres, g_res, shp, out='lc_a', **rrec)             # slot 0: the residual's (A, X)
                 z = through_mfm('block%d.%d.conv2' % (bi, i), z)
                 ma = sites['block%d.%d.conv1' % (bi, i)].m
-                z = self.fire('Conv2d', 0, z, shp, s0=ma, out='lc_a')
+                z = self.fire('Conv2d', 0, z, shp, s0=ma, out='lc_a', rc=rc)
                 z = through_mfm('block%d.%d.conv1' % (bi, i), z)
                 z2 = g_res
                 if i == 0:
@@ -272,18 +276,44 @@ class LightCNNSweep(object):
                     z = self.fire('Add', rres, z, shp, out='lc_b', **rrec)
                     z2 = None
             if sg['pool_in'] is not None:
-                z = pooled_site(sg['pool_in'], z, str(bi))
+                z = pooled_site(sg['pool_in'], z, str(bi), rc)
         P2 = buf('lc_P2', J, 128, 128, 2 * eng.stem.cp)
         through_mfm('conv1', z, P_force=P2)
         if self._P is not None:
             self._P.append(None)                     # Conv2d hook on the image: never read by any output
         self._names.append('Conv2d')
+        self._layout.append((1, 1, False))
         return self._P, self._names, P2
 
-    def fire(self, kind, recipe, z_in, shape, out, P_force=None, z_in2=None, **kw):
+    def elem_index(self, k, e, shape):
+        """flat index into the reference's [1,C,H,W] MWP of firing k -> flat index into the device tensor (NHWC, padded)"""
+        c_real, cp, split = self._layout[k]
+        _, H, W, Cdev = shape
+        c, hw = divmod(int(e), H * W)
+        h, w = divmod(hw, W)
+        if split and c >= c_real:
+            c = cp + (c - c_real)
+        return (h * W + w) * Cdev + c
+
+    def to_reference(self, k, p):
+        """Recorded MWP of firing k in the reference's layout: [J,C,H,W] without channel padding (fc vectors: [J,C])."""
+        if p is None:
+            return None
+        c_real, cp, split = self._layout[k]
+        if split:
+            p = torch.cat((p[..., :c_real], p[..., cp:cp + c_real]), -1)
+        else:
+            p = p[..., :c_real]
+        if k == self._k_fcvec:
+            return p.permute(0, 3, 1, 2).reshape(p.shape[0], -1)          # the Linear hook sees the NCHW-flattened vector
+        return p.permute(0, 3, 1, 2) if p.shape[1] * p.shape[2] > 1 else p.reshape(p.shape[0], -1)
+
+    def fire(self, kind, recipe, z_in, shape, out, P_force=None, z_in2=None, rc=None, split=False, **kw):
         k = self._k
         self._k += 1
         self._names.append(kind)
+        cdev = shape[-1]
+        self._layout.append((rc if rc is not None else (cdev // 2 if split else cdev), cdev // 2 if split else cdev, split))
         affine = any(s in kind for s in AFFINE)
         P_out = P_force
         if self._P is not None:

@@ -17,7 +17,8 @@ Status of the reference surface in this round:
          embeddings, ebp_subtree_mode, with_bias / ebp_version 11, ebp_version != 6 (uint8 + PIL blur on the host)
   done   layerwise_ebp, layerwise_contrastive_ebp, weighted_subtree_ebp on the STR ResNet plugin (xfr_b200/generic.py)
   done   the hooked (non-triplet) fc2 head for ebp / contrastive_ebp (e.g. the 65,359-class STR head, blackbox.py:280-294)
-  next   layerwise operators for the ResNet-50-128d plugin; Light-CNN plugin
+  done   Light-CNN-29v2 plugin (WhiteboxLightCNN): every operator above incl. layerwise / weighted-subtree (xfr_b200/lightcnn.py)
+  next   layerwise operators for the ResNet-50-128d plugin
 """
 import numpy as np
 import torch
@@ -25,6 +26,7 @@ import torch.nn as nn
 
 from . import synth
 from .engine import MODE_IDS, Resnet50_128Engine, StResnetEngine
+from .lightcnn import LightCNNEngine
 
 _CHUNK = 128    # probes per engine sweep (workspace = ~210 MB per probe)
 
@@ -197,6 +199,61 @@ class Whitebox_resnet50_128(WhiteboxSTResnet):
         return torch.from_numpy(x.transpose(2, 0, 1).astype(np.float32)).unsqueeze(0)
 
 
+class WhiteboxLightCNN(WhiteboxSTResnet):
+    """Light-CNN-29v2 plugin (reference whitebox.py:113-159).  `net` is the reference's
+    xfr.models.lightcnn.network_29layers_v2 module (lightcnn.py:216-275) or its state_dict.  The classifier is the
+    network's fc2 (hooked, W+ in the backward) until set_triplet_classifier replaces it by an un-hooked Linear(256, 2)
+    (whitebox.py:120-123).  Saliency maps are 128x128 (P[-2] is the first Split input, 96x128x128)."""
+
+    def __init__(self, net, impl='tf32x3'):
+        if isinstance(net, dict):
+            self._sd = net
+            self.net = _StateDictModule(net)
+        else:
+            self.net = net
+            self.net.eval()
+            self._sd = net.state_dict()
+        self._impl = impl
+        self._engine = None
+        self._W2 = None
+        self._ncls = int(self._sd['fc2.weight'].shape[0]) if 'fc2.weight' in self._sd else 0
+
+    def engine(self, with_bias=False):
+        if self._engine is None or self._engine.with_bias != with_bias:
+            from .kernels import CudaBackend
+            dev = self._device()
+            self._engine = LightCNNEngine(self._sd, CudaBackend(dev, impl=self._impl), device=dev, with_bias=with_bias)
+        return self._engine
+
+    def encode(self, x):
+        """whitebox.py:125-128: the 256-d fc output (`features` of net(x))."""
+        eng = self.engine()
+        return torch.cat([eng.forward(self._nhwc(x[i:i + _CHUNK])).clone() for i in range(0, x.shape[0], _CHUNK)])
+
+    def classify(self, x):
+        """whitebox.py:130-132: fc2(dropout(fc)) in eval mode; fc2 has no bias (lightcnn.py:228)."""
+        enc = self.encode(x)
+        if self._W2 is not None:
+            return torch.einsum('nd,ncd->nc', enc, self.triplet_rows(enc.shape[0]))
+        return enc @ self._sd['fc2.weight'].to(enc.device).t()
+
+    def preprocess(self, im):
+        """whitebox.py:137-139 / lightcnn.py:19-31: Resize(144) (shorter side, bilinear), CenterCrop(128), luminance in [0,1]
+        with skimage.color.rgb2gray's weights -> [1,1,128,128]."""
+        import PIL.Image
+        w, h = im.size
+        if w <= h:
+            nw, nh = 144, int(144 * h / w)
+        else:
+            nw, nh = int(144 * w / h), 144
+        im = im.resize((nw, nh), PIL.Image.BILINEAR)
+        l, t = int(round((nw - 128) / 2.0)), int(round((nh - 128) / 2.0))
+        a = np.array(im.crop((l, t, l + 128, t + 128)))
+        if a.ndim == 3:
+            a = (a[..., :3].astype(np.float64) / 255.0) @ np.array([0.2125, 0.7154, 0.0721])
+        return torch.from_numpy(np.asarray(a)).float().unsqueeze(0).unsqueeze(0)
+
+
 class _StateDictModule(nn.Module):
     def __init__(self, sd):
         super(_StateDictModule, self).__init__()
@@ -280,7 +337,7 @@ class Whitebox(nn.Module):
         eng = self._engine()
         N = x.shape[0]
         W2 = self.net.triplet_rows(N)
-        res = out if out is not None else torch.empty(N, 112, 112)
+        res = out if out is not None else torch.empty(N, eng.map_hw, eng.map_hw)
         hk = self.net.hooked()
         for i in range(0, N, _CHUNK):
             m = eng.contrastive(self.net._nhwc(x[i:i + _CHUNK]), W2 if hk else W2[i:i + _CHUNK].contiguous(), k_poschannel,
@@ -311,27 +368,19 @@ class Whitebox(nn.Module):
 
     # ---------------------------------------------------------------- layerwise / sub-tree operators (generic sweep)
     def _generic(self, img_probe):
-        """Forward once, return (GenericSweep, W2 rows).  STR ResNet only in this round."""
-        from .generic import GenericSweep
+        """Forward once, return (firing-by-firing sweep of the engine, W2 rows)."""
         eng = self._engine()
-        if not isinstance(eng, StResnetEngine):
-            raise NotImplementedError('xfr_b200: layerwise / weighted-subtree EBP is implemented for the STR ResNet plugin')
+        if not hasattr(eng, 'sweep'):
+            raise NotImplementedError('xfr_b200: layerwise / weighted-subtree EBP is implemented for the STR ResNet and '
+                                      'Light-CNN plugins')
         if img_probe.shape[0] != 1:
             raise ValueError('layerwise operators take one probe (as in the reference)')
         eng.forward(self.net._nhwc(img_probe))
-        return GenericSweep(eng), self.net.triplet_rows(1)
+        return eng.sweep(), self.net.triplet_rows(1)
 
-    @staticmethod
-    def _nchw_index_to_nhwc(e, shape):
-        """The reference indexes flattened [1,C,H,W] tensors (whitebox.py:575-577); device tensors here are [1,H,W,C]."""
-        _, H, W, C = shape
-        c, hw = divmod(int(e), H * W)
-        h, w = divmod(hw, W)
-        return (h * W + w) * C + c
-
-    def _set_P(self, P, names):
+    def _set_P(self, gs, P, names):
         """Expose the recorded MWPs like the reference's self.P / self.P_layername: [1,C,H,W] views (vectors: [1,C])."""
-        self.P = [None if p is None else (p.permute(0, 3, 1, 2) if p.shape[1] * p.shape[2] > 1 else p.reshape(p.shape[0], -1)) for p in P]
+        self.P = [gs.to_reference(k, p) for k, p in enumerate(P)]
         self.P_layername = list(names)
 
     def _finish_map(self, P2, mwp):
@@ -361,12 +410,12 @@ class Whitebox(nn.Module):
             prior = (0, (Pk * (Pk == Pk.max())).reshape(-1).contiguous())
         elif mode == 'elementwise':
             assert(k_element is not None)
-            e = self._nchw_index_to_nhwc(k_element, Pk.shape)
+            e = gs.elem_index(k_layer, k_element, Pk.shape)
             prior = (0, e, float(Pk.reshape(-1)[e]))
         else:
             raise ValueError('invalid layerwise EBP mode "%s"' % mode)
         P, names, P2 = gs.run(0.0 * P0, W2, self._ebp_subtree_mode, priors={int(k_layer): prior}, record=True)
-        self._set_P(P, names)
+        self._set_P(gs, P, names)
         return self._finish_map(P2, mwp)[0]
 
     def layerwise_contrastive_ebp(self, img_probe, k_poschannel, k_negchannel, k_layer, mode='copy', percentile=80, k_element=None,
@@ -403,14 +452,14 @@ class Whitebox(nn.Module):
             if mode == 'percentile_argmax':
                 prior = argmax_only(prior)
         elif mode == 'elementwise':
-            e = self._nchw_index_to_nhwc(k_element, Pm.shape)
+            e = gs.elem_index(k_layer, k_element, Pm.shape)
             prior = torch.zeros_like(C).reshape(-1)
             prior[e] = C.reshape(-1)[e]
         else:
             raise ValueError('unknown contrastive ebp mode "%s"' % mode)
         P0 = self._onehot(k_poschannel, dev)
         P, names, P2 = gs.run(0.0 * P0, W2, self._ebp_subtree_mode, priors={int(k_layer): (0, prior.reshape(-1).contiguous())}, record=True)
-        self._set_P(P, names)
+        self._set_P(gs, P, names)
         return self._finish_map(P2, mwp)[0]
 
     def weighted_subtree_ebp(self, img_probe, k_poschannel, k_negchannel, topk=1, verbose=True, do_max_subtree=False,
@@ -422,7 +471,7 @@ class Whitebox(nn.Module):
         gs, W2 = self._generic(img_probe)
         eng, be, dev = gs.eng, gs.be, W2.device
         # true gradients dA of: cross-entropy(y, 0), y[0], y[1]
-        y = (50.0 * eng.saved['xn'][0:1]) @ W2[0].t()                               # classify(): logits of the triplet head
+        y = eng.logits(W2)                                                          # classify(): logits of the triplet head
         sm = torch.softmax(y, dim=1)
         Pn = torch.zeros(3, self.net.num_classes(), device=dev)
         Pn[0] = sm[0]
