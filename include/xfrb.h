@@ -49,6 +49,9 @@ const char* xfrb_last_error(void);
 int xfrb_device_ok(void);
 /* 1 when GEMM implementation `impl` (XFRB_IMPL_*) is compiled into this library */
 int xfrb_impl_available(int impl);
+/* tcgen05 kernels as CTA pairs (cta_group::2, one 256-row tile per TPC) where a launch has enough tiles: off by default
+ * (XFRB_CTA2=1 in the environment enables); returns the previous setting.  Results are bit-identical either way. */
+int xfrb_set_cta_pairs(int on);
 
 /* ---- forward ("activation" + "positive_activation" passes, whitebox.py:490-493) ---- */
 

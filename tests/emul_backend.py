@@ -58,6 +58,12 @@ def _w(B):
     return B.sum(0) if B.dim() == 3 else B
 
 
+def _wpos(B):
+    """W+ operand as the split-TF32 plan of impl 'tf32x3' multiplies it (conv_tc.cu, SPLIT 2 / 3): activations exact,
+    relu(W) rounded to TF32 = the hi plane alone.  Single-plane packs (fp32 / tf32) are used as they are."""
+    return B[0] if B.dim() == 3 else B
+
+
 class EmulBackend(object):
     name = 'emul'
 
@@ -84,8 +90,8 @@ class EmulBackend(object):
     def conv_dual(self, inp, L, o, xr, act, res=None, relu_act=True):
         """o = conv(inp)+b ; xr = relu(conv_{W+}(inp)+b') ; act = relu(o*alpha+beta [+ res, zero-padded channels])."""
         A = im2col_nhwc(inp, L.R, L.S, L.R // 2)
-        D = A @ _w(L.Bf).t() + L.bias
-        t, p = unpack_dual_cols(D, L.tn)
+        t, _ = unpack_dual_cols(A @ _w(L.Bf).t() + L.bias, L.tn)
+        _, p = unpack_dual_cols(A @ _wpos(L.Bf).t() + L.bias, L.tn)
         o.view(-1, L.cout).copy_(t)
         xr.view(-1, L.cout).copy_(relu(p))
         a = t * L.bn[0] + L.bn[1]
@@ -122,7 +128,7 @@ class EmulBackend(object):
         Xmul = relu(F.normalize(_rows(f1p, J), p=2, dim=1))
         gr = hook(False, relu(xn_), Xmul, gr, mode, self.eps)
         gr = (gr - xn_ * (xn_ * gr).sum(1, keepdim=True)) / nrm_.unsqueeze(1)
-        gr = gr @ _w(head.W1pT).t()
+        gr = gr @ _wpos(head.W1pT).t()
         gr = hook(True, relu(v_), relu(v_), gr, mode, self.eps)     # X = relu(avgpool(relu(u))) = v since u >= 0
         g_out.copy_((gr / 49.0).view(J, 1, 1, -1).expand(-1, 7, 7, -1))
 
@@ -136,9 +142,9 @@ class EmulBackend(object):
         z = z * sp                                       # BatchNorm backward with gamma+
         return hook(True, relu(o), xr, z, mode, self.eps)  # BatchNorm hook
 
-    def _dgrad(self, y, Bd, R):
+    def _dgrad(self, y, Bd, R, signed=False):
         """y [J,H,W,Cout] -> [J*H*W, Cin]"""
-        return im2col_nhwc(y, R, R, R // 2) @ _w(Bd).t()
+        return im2col_nhwc(y, R, R, R // 2) @ (_w(Bd) if signed else _wpos(Bd)).t()
 
     def dgrad_mid(self, y, L, o, xr, bn, mode, y_out):
         """z = W+^T y (conv L), then the hook chain at the activation a = relu(bn(o)) that fed conv L."""
@@ -148,7 +154,7 @@ class EmulBackend(object):
                                                      _rows(xr, J).reshape(-1, L.cin), bn, mode))
 
     def dgrad_plain(self, y, L, z_out, signed=False, accumulate=False):
-        z = self._dgrad(y, L.signed_dgrad() if signed else L.Bd, L.R)
+        z = self._dgrad(y, L.signed_dgrad() if signed else L.Bd, L.R, signed)
         if accumulate:
             z = z + z_out.reshape(-1, L.cin)
         z_out.view(-1, L.cin).copy_(z)
@@ -335,7 +341,7 @@ class EmulBackend(object):
     def head_bwd_linear(self, Pn, W2, head, v, mode, g_out):
         J = Pn.shape[0]
         v_ = _rows(v, J)
-        gr = torch.einsum('jc,jcd->jd', Pn, _rows(W2, J)) @ _w(head.BfeT).t()
+        gr = torch.einsum('jc,jcd->jd', Pn, _rows(W2, J)) @ _wpos(head.BfeT).t()
         gr = hook(True, relu(v_), relu(v_), gr, mode, self.eps)
         g_out.copy_((gr / 49.0).view(J, 1, 1, -1).expand(-1, 7, 7, -1))
 
@@ -394,7 +400,7 @@ class EmulBackend(object):
 
     # ------------------------------------------------------------ Light-CNN-29v2 pieces (include/xfrb.h)
     def conv_bias(self, inp, B, bias, out, R, positive=False):
-        out.view(-1, out.shape[-1]).copy_(im2col_nhwc(inp, R, R, R // 2) @ _w(B).t() + bias)
+        out.view(-1, out.shape[-1]).copy_(im2col_nhwc(inp, R, R, R // 2) @ (_wpos(B) if positive else _w(B)).t() + bias)
 
     def lc_conv1(self, x, Wt, b, bpos, c, cpos=None):
         C2 = Wt.shape[1]

@@ -72,6 +72,8 @@ def test_gemm_shapes(impl, tol):
         (3, 56, 64, 64, 1), (3, 56, 64, 64, 3), (2, 56, 256, 64, 1), (3, 28, 128, 128, 3), (3, 28, 512, 128, 1),
         (5, 14, 256, 256, 3), (5, 14, 1024, 256, 1), (5, 7, 512, 512, 3), (3, 7, 2048, 512, 1), (7, 1, 2048, 512, 1),
         (1, 7, 512, 2048, 1), (300, 1, 128, 64, 1),
+        # enough tiles for the CTA-pair (cta_group::2) kernels, incl. an odd tile count (phantom half) and a ragged M tail
+        (13, 56, 256, 64, 1), (32, 28, 128, 128, 3), (40, 14, 1024, 256, 1), (160, 7, 512, 512, 3), (24, 56, 64, 64, 3),
     ]
     errs = {}
     for c in cases:
@@ -79,3 +81,27 @@ def test_gemm_shapes(impl, tol):
     print('\n'.join('%-28s %.3g' % (str(k), v) for k, v in errs.items()))
     bad = {k: v for k, v in errs.items() if not v < tol}
     assert not bad, bad
+
+
+def test_cta_pairs_match_single_cta():
+    """The cta_group::2 kernels accumulate in the same order as the single-CTA ones: a 16-probe ResNet-101 contrastive
+    sweep (every conv launch large enough to run as CTA pairs) is bit-identical with pairs on and off."""
+    from xfr_b200.engine import StResnetEngine
+    from xfr_b200.kernels import CudaBackend
+    from helpers import L101
+    dev = torch.device('cuda:0')
+    be = CudaBackend(dev, impl='tf32x3')
+    eng = StResnetEngine(synth.stresnet_state_dict(0, L101, 2), be, L101, device=dev)
+    N = 16
+    x = synth.synthetic_probes(N, seed=31).permute(0, 2, 3, 1).contiguous().to(dev)
+    g = torch.Generator().manual_seed(32)
+    W2 = (torch.randn(N, 2, 512, generator=g) * 0.02).to(dev)
+    prev = be.lib.xfrb_set_cta_pairs(1)
+    try:
+        a = eng.contrastive(x, W2, saliency=False).clone()
+        be.lib.xfrb_set_cta_pairs(0)
+        b = eng.contrastive(x, W2, saliency=False).clone()
+    finally:
+        be.lib.xfrb_set_cta_pairs(prev)
+    assert torch.isfinite(a).all() and float(a.abs().max()) > 0
+    assert torch.equal(a, b), float((a - b).abs().max() / b.abs().max())

@@ -39,11 +39,13 @@ def test_all_modes(mode, tag, impl):
     c = eng.contrastive(x, W2, mode=mode).clone().numpy()
     t = eng.contrastive(x, W2, mode=mode, percentile=20).clone().numpy()
     assert m.shape == (2, 128, 128)
+    # 'tf32x3' packs: the emulation multiplies relu(W) rounded to TF32 in the W+ GEMMs, as the product's two-pass plan does
+    tol = 1e-5 if impl == 'fp32' else 1e-3
     for i, pname in enumerate(('smooth', 'noise')):
-        assert rel_err(m[i], G['ebp_mwp_%s_%s' % (tag, pname)]) < 1e-5
-        assert rel_err(s[i], G['ebp_%s_%s' % (tag, pname)]) < 1e-5
-        assert rel_err(c[i], G['cebp_%s_%s' % (tag, pname)]) < 5e-4
-        assert rel_err(t[i], G['tcebp20_%s_%s' % (tag, pname)]) < 5e-4
+        assert rel_err(m[i], G['ebp_mwp_%s_%s' % (tag, pname)]) < tol
+        assert rel_err(s[i], G['ebp_%s_%s' % (tag, pname)]) < tol
+        assert rel_err(c[i], G['cebp_%s_%s' % (tag, pname)]) < 50 * tol
+        assert rel_err(t[i], G['tcebp20_%s_%s' % (tag, pname)]) < 50 * tol
 
 
 def test_recorded_P_and_hooked_fc2():

@@ -47,10 +47,12 @@ def test_schedule_emulation(mode, tag):
     s = eng.ebp(x, P1, W2, mode).clone().numpy()
     c = eng.contrastive(x, W2, mode=mode).clone().numpy()
     t = eng.contrastive(x, W2, mode=mode, percentile=20).clone().numpy()
+    # 'tf32x3' packs: the emulation multiplies relu(W) rounded to TF32 in the W+ GEMMs (the product's two-pass plan), which
+    # moves the real-weights maps by 2e-5 (EBP) / 1.5e-4 (contrastive) of their maximum
     for i, p in enumerate(('probe', 'demo')):
-        assert rel_err(s[i], G['ebp_%s_%s' % (tag, p)]) < 1e-5
-        assert rel_err(c[i], G['cebp_%s_%s' % (tag, p)]) < 1e-4
-        assert rel_err(t[i], G['tcebp20_%s_%s' % (tag, p)]) < 1e-4
+        assert rel_err(s[i], G['ebp_%s_%s' % (tag, p)]) < 1e-4
+        assert rel_err(c[i], G['cebp_%s_%s' % (tag, p)]) < 1e-3
+        assert rel_err(t[i], G['tcebp20_%s_%s' % (tag, p)]) < 1e-3
 
 
 @needs_weights

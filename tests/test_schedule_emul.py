@@ -57,10 +57,12 @@ def test_small_net(mode, tag, impl):
     m = eng.ebp(x, P1, W2, mode, saliency=False).clone().numpy()
     s = eng.ebp(x, P1, W2, mode).clone().numpy()
     c = eng.contrastive(x, W2, mode=mode).clone().numpy()
+    # 'tf32x3' packs: the emulation multiplies relu(W) rounded to TF32 in the W+ GEMMs, as the product's two-pass plan does
+    tol = 1e-5 if impl == 'fp32' else 1e-4
     for i, pname in enumerate(('smooth', 'noise')):
-        assert rel_err(m[i], G['ebp_mwp_%s_%s' % (tag, pname)]) < 1e-5
-        assert rel_err(s[i], G['ebp_%s_%s' % (tag, pname)]) < 1e-5
-        assert rel_err(c[i], G['cebp_%s_%s' % (tag, pname)]) < 5e-4
+        assert rel_err(m[i], G['ebp_mwp_%s_%s' % (tag, pname)]) < tol
+        assert rel_err(s[i], G['ebp_%s_%s' % (tag, pname)]) < tol
+        assert rel_err(c[i], G['cebp_%s_%s' % (tag, pname)]) < 50 * tol
 
 
 def test_resnet101_default_mode():

@@ -86,6 +86,8 @@ int xfrb_impl_available(int impl) {
     return 0;
 }
 
+int xfrb_set_cta_pairs(int on) { return conv_tc_set_cta2(on); }
+
 int xfrb_stem_fwd(const float* x, const float* W, const float* b, const float* bn, float* o, float* mp, int N, int pool_pad,
                   void* stream) {
     if (pool_pad != 0 && pool_pad != 1) return finish("xfrb_stem_fwd", cudaErrorInvalidValue);

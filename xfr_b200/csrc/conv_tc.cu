@@ -14,6 +14,13 @@
 //                                lo = x - hi in a twin buffer (weights arrive pre-split from the host as two planes);
 //                                the issuer then runs hi*hi + lo*hi (+ hi*lo) into the same accumulator.
 //
+// CTA2: the same kernel as a CTA PAIR (cluster of 2, tcgen05 cta_group::2).  One M = 256 x BN tile per pair: each CTA
+//   loads and splits its own 128 activation rows and HALF of the weight tile (BN/2 rows); the leader CTA issues
+//   tcgen05.mma.cta_group::2, whose tensor cores read each CTA's own A and both B halves, so the shared-memory operand
+//   traffic per SM per MMA drops from A + B to A + B/2 (the 3xTF32 main loop is shared-memory-bandwidth bound,
+//   profiles/r1_notes.md).  Peer -> leader signalling: remote mbarrier arrives (split done, accumulator drained);
+//   leader -> both: multicast tcgen05.commit.
+//
 // SPLIT (pass plan of the GEMM):
 //   0  single TF32 pass
 //   1  full 3xTF32: A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (signed weights: cancellation amplifies weight rounding)
@@ -26,6 +33,8 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace xfrb {
 
@@ -80,6 +89,53 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
         "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
         : "memory");
 }
+// ---- CTA-pair (cluster) variants
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+        "}\n" ::"r"(bar), "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAITC_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONEC_%=;\n\t"
+        "bra WAITC_%=;\n\t"
+        "DONEC_%=:\n\t"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit2(uint32_t bar) {      // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -125,9 +181,10 @@ __device__ __forceinline__ void tmem_ld_wait(float* v) {
 }
 
 // ------------------------------------------------------------------ kernel
-template <int BN, int SPLIT>
+template <int BN, int SPLIT, bool CTA2 = false>
 struct TcCfg {
-    static constexpr uint32_t B_TILE_BYTES = BN * TC_BK * 4;
+    static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;            // weight rows this CTA stages (a pair shares the tile)
+    static constexpr uint32_t B_TILE_BYTES = B_ROWS * TC_BK * 4;
     static constexpr uint32_t B_LO_BYTES = SPLIT == 1 ? B_TILE_BYTES : SPLIT == 3 ? B_TILE_BYTES / 2 : 0;
     static constexpr uint32_t STAGE_BYTES = A_TILE_BYTES * (SPLIT ? 2 : 1) + B_TILE_BYTES + B_LO_BYTES;
     static constexpr int STAGES_RAW = (192 * 1024) / STAGE_BYTES;
@@ -138,11 +195,16 @@ struct TcCfg {
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + PRM_BYTES + TR_BYTES;
 };
 
-template <int BN, int SPLIT, int KIND>
+template <int BN, int SPLIT, int KIND, bool CTA2>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBlo, const TcGeom g, const EpiParams ep) {
-    using Cfg = TcCfg<BN, SPLIT>;
+    using Cfg = TcCfg<BN, SPLIT, CTA2>;
+    static_assert(!CTA2 || SPLIT != 0, "the CTA-pair kernel signals the leader from the split warps");
+    const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const int worker = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // tile stream this CTA (pair) walks
+    const int nworkers = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     constexpr bool SPLIT3 = SPLIT != 0;          // the activation tile is split into (hi, lo)
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -165,7 +227,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto b_lo = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES; };   // SPLIT 1 / 3
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = g.n_m_tiles * g.n_n_tiles;
+    const int total_tiles = (CTA2 ? (g.n_m_tiles + 1) / 2 : g.n_m_tiles) * g.n_n_tiles;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -174,29 +236,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
-            mbar_init(split_bar(s), 4);
+            mbar_init(split_bar(s), CTA2 ? 8 : 4);               // pair: the peer's split warps arrive here too (leader's copy)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), TC_EPI_WARPS);
+            mbar_init(tempty_bar(a), CTA2 ? 2 * TC_EPI_WARPS : TC_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (CTA2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CTA2) cluster_sync_all();       // both CTAs' barriers are initialised before any remote arrive / multicast commit
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     // tile -> coordinates
     auto tile_coords = [&](int tile, int& m0, int& mvalid, int& n_img0, int& h0, int& ncol0) {
         int mt = tile / g.n_n_tiles, nt = tile - mt * g.n_n_tiles;
+        if (CTA2) mt = 2 * mt + (int)rank;             // the pair's tile is 256 rows: two consecutive m-tiles
+        const bool phantom = mt >= g.n_m_tiles;        // odd tile count: the last pair's second half loads zeros, stores nothing
         // gradient-row groups (mate / non-mate rows of the same probes) read the same saved tensors: visit group 0's
         // tile i, then group 1's tile i, ... so the second read of a saved tile hits L2 instead of HBM
-        if (g.groups > 1) mt = (mt % g.groups) * g.tiles_per_group + mt / g.groups;
+        if (g.groups > 1 && !phantom) mt = (mt % g.groups) * g.tiles_per_group + mt / g.groups;
         ncol0 = nt * BN;
         if (!g.a4d) {
             m0 = mt * TC_BM;
@@ -214,6 +284,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             m0 = (n_img0 * g.H + h0) * g.W;
             mvalid = min(g.bh, g.H - h0) * g.W;
         }
+        if (phantom) mvalid = 0;
     };
 
     if (warp == 0) {
@@ -221,7 +292,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = worker; tile < total_tiles; tile += nworkers) {
                 int m0, mvalid, n_img0, h0, ncol0;
                 tile_coords(tile, m0, mvalid, n_img0, h0, ncol0);
                 for (int kb = 0; kb < g.num_k; ++kb) {
@@ -235,49 +306,66 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     } else {
                         tma_load_2d(a_hi(s), &tmA, c0, m0, full_bar(s));
                     }
-                    tma_load_2d(b_hi(s), &tmB, kb * TC_BK, ncol0, full_bar(s));
-                    if (SPLIT == 1) tma_load_2d(b_lo(s), &tmB, kb * TC_BK, g.b_rows + ncol0, full_bar(s));   // host-split lo plane
-                    if (SPLIT == 3) tma_load_2d(b_lo(s), &tmBlo, kb * TC_BK, g.b_rows + ncol0, full_bar(s));  // lo of the W half
+                    const int brow = ncol0 + (CTA2 ? (int)rank * (BN / 2) : 0);        // pair: this CTA stages its half of the tile
+                    tma_load_2d(b_hi(s), &tmB, kb * TC_BK, brow, full_bar(s));
+                    if (SPLIT == 1) tma_load_2d(b_lo(s), &tmB, kb * TC_BK, g.b_rows + brow, full_bar(s));   // host-split lo plane
+                    if (SPLIT == 3)                                                                          // lo of the W half
+                        tma_load_2d(b_lo(s), &tmBlo, kb * TC_BK, g.b_rows + ncol0 + (CTA2 ? (int)rank * (BN / 4) : 0), full_bar(s));
                     if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-        constexpr uint32_t idesc_half = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 4) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        // ===================== MMA issuer (pair: the leader CTA only) =====================
+        constexpr uint32_t MM = CTA2 ? 2 * TC_BM : TC_BM;      // cta_group::2: M = 256, rows 128.. live in the peer's TMEM
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(MM >> 4) << 24);
+        constexpr uint32_t idesc_half = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 4) << 17) | ((uint32_t)(MM >> 4) << 24);
+        auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t id, uint32_t acc) {
+            if (CTA2) tc_mma_tf32_2(d, da, db, id, acc);
+            else tc_mma_tf32(d, da, db, id, acc);
+        };
         int s = 0;
         uint32_t ph = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        if (leader)
+        for (int tile = worker; tile < total_tiles; tile += nworkers, ++it) {
             const int a = it & 1;
             const uint32_t aph = (it >> 1) & 1;
-            if (lane == 0) mbar_wait(tempty_bar(a), aph ^ 1u);
+            if (lane == 0) {
+                if (CTA2) mbar_wait_cluster(tempty_bar(a), aph ^ 1u);
+                else mbar_wait(tempty_bar(a), aph ^ 1u);
+            }
             __syncwarp();
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(a * BN);
             for (int kb = 0; kb < g.num_k; ++kb) {
                 if (lane == 0) {
-                    mbar_wait(SPLIT3 ? split_bar(s) : full_bar(s), ph);
+                    if (CTA2) mbar_wait_cluster(split_bar(s), ph);
+                    else mbar_wait(SPLIT3 ? split_bar(s) : full_bar(s), ph);
                     tc_fence_after();
                     const uint64_t dah = make_desc(a_hi(s)), dbh = make_desc(b_hi(s));
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k) {
                         const uint64_t koff = (uint64_t)((k * 32) >> 4);
-                        tc_mma_tf32(tacc, dah + koff, dbh + koff, idesc, (kb | k) != 0 ? 1u : 0u);
+                        mma(tacc, dah + koff, dbh + koff, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     if (SPLIT3) {
                         const uint64_t dal = make_desc(a_lo(s)), dbl = make_desc(b_lo(s));
 #pragma unroll
                         for (int k = 0; k < TC_BK / 8; ++k) {
                             const uint64_t koff = (uint64_t)((k * 32) >> 4);
-                            tc_mma_tf32(tacc, dal + koff, dbh + koff, idesc, 1u);
-                            if (SPLIT == 1) tc_mma_tf32(tacc, dah + koff, dbl + koff, idesc, 1u);
-                            if (SPLIT == 3) tc_mma_tf32(tacc, dah + koff, dbl + koff, idesc_half, 1u);   // columns [0, BN/2): the W half
+                            mma(tacc, dal + koff, dbh + koff, idesc, 1u);
+                            if (SPLIT == 1) mma(tacc, dah + koff, dbl + koff, idesc, 1u);
+                            if (SPLIT == 3) mma(tacc, dah + koff, dbl + koff, idesc_half, 1u);   // columns [0, BN/2): the W half
                         }
                     }
-                    tc_commit(empty_bar(s));                 // smem stage reusable once these MMAs retire
-                    if (kb == g.num_k - 1) tc_commit(tfull_bar(a));
+                    if (CTA2) {
+                        tc_commit2(empty_bar(s));                // both CTAs' stage s
+                        if (kb == g.num_k - 1) tc_commit2(tfull_bar(a));
+                    } else {
+                        tc_commit(empty_bar(s));                 // smem stage reusable once these MMAs retire
+                        if (kb == g.num_k - 1) tc_commit(tfull_bar(a));
+                    }
                 }
                 __syncwarp();
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -289,7 +377,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int t = threadIdx.x - 64;    // 0..127
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = worker; tile < total_tiles; tile += nworkers) {
                 for (int kb = 0; kb < g.num_k; ++kb) {
                     mbar_wait(full_bar(s), ph);
                     // only the activation tile is split here; the weight tile arrives as (hi, lo) planes split on the host
@@ -310,7 +398,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(split_bar(s));
+                    if (lane == 0) {
+                        if (CTA2 && !leader) mbar_arrive_remote(split_bar(s), 0);     // the leader's MMA thread waits for both halves
+                        else mbar_arrive(split_bar(s));
+                    }
                     if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
             }
@@ -332,7 +423,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float4* tbuf = tr_s + ew * 128;
         constexpr int CH = (KIND == EPI_FWD_DUAL) ? BN / 2 : BN;      // channels per tile
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = worker; tile < total_tiles; tile += nworkers, ++it) {
             const int a = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             int m0, mvalid, n_img0, h0, ncol0;
@@ -482,15 +573,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(a));
+            if (lane == 0) {
+                if (CTA2 && !leader) mbar_arrive_remote(tempty_bar(a), 0);
+                else mbar_arrive(tempty_bar(a));
+            }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CTA2) cluster_sync_all();       // neither CTA may leave (or free TMEM) while its peer can still touch its smem / barriers
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS));
+        if (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS));
     }
 }
 
@@ -527,11 +623,11 @@ bool conv_tc_available() { return true; }
 template <int BN, int SPLIT, int KIND>
 static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo, const TcGeom& g,
                               const EpiParams& ep, cudaStream_t st) {
-    using Cfg = TcCfg<BN, SPLIT>;
+    using Cfg = TcCfg<BN, SPLIT, false>;
     static bool attr = false;
     static int sms = 0;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT, KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -540,8 +636,60 @@ static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, co
     }
     int total = g.n_m_tiles * g.n_n_tiles;
     int grid = total < sms ? total : sms;
-    conv_tc_kernel<BN, SPLIT, KIND><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmBlo, g, ep);
+    conv_tc_kernel<BN, SPLIT, KIND, false><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmBlo, g, ep);
     return cudaGetLastError();
+}
+
+// CTA-pair launch: clusters of 2, one pair per TPC, persistent over the 256-row pair tiles.
+template <int BN, int SPLIT, int KIND>
+static cudaError_t launch_cfg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo, const TcGeom& g,
+                               const EpiParams& ep, cudaStream_t st) {
+    using Cfg = TcCfg<BN, SPLIT, true>;
+    auto kern = conv_tc_kernel<BN, SPLIT, KIND, true>;
+    static int max_clusters = -1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (max_clusters < 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cfg.gridDim = dim3((unsigned)(sms & ~1));
+        int n = 0;
+        e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+        if (e != cudaSuccess) return e;
+        max_clusters = n < sms / 2 ? n : sms / 2;
+        if (max_clusters < 1) return cudaErrorLaunchOutOfResources;
+    }
+    int pairs = ((g.n_m_tiles + 1) / 2) * g.n_n_tiles;
+    int clusters = pairs < max_clusters ? pairs : max_clusters;
+    cfg.gridDim = dim3((unsigned)(2 * clusters));
+    return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmBlo, g, ep);
+}
+
+static int g_cta2 = -1;      // -1: from the environment (XFRB_CTA2=1 enables), else 0 / 1
+static bool cta2_enabled() {
+    if (g_cta2 < 0) {
+        const char* e = getenv("XFRB_CTA2");
+        g_cta2 = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return g_cta2 != 0;
+}
+int conv_tc_set_cta2(int on) {
+    int prev = cta2_enabled() ? 1 : 0;
+    g_cta2 = on ? 1 : 0;
+    return prev;
 }
 
 cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, const EpiParams& ep, int split, int tn,
@@ -603,15 +751,17 @@ cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, c
         cuuint32_t box[4] = {TC_BK, (cuuint32_t)cg.W, (cuuint32_t)g.bh, (cuuint32_t)g.bimg};
         if (!encode(&tmA, A, 4, dims, strides, box)) return cudaErrorInvalidValue;
     }
+    // CTA pairs (cta_group::2) for the split-TF32 plans of the product path when there are enough pair tiles for every TPC
+    const bool cta2 = (split == 2 || split == 3) && cta2_enabled() && ((g.n_m_tiles + 1) / 2) * g.n_n_tiles >= 74;
     {
         // B is [planes][Nn][K]: plane 0 = rna_tf32(W) (or W itself for single-pass TF32), plane 1 = W - plane 0
         cuuint64_t dims[2] = {(cuuint64_t)cg.K, (cuuint64_t)cg.Nn * (split ? 2 : 1)};
         cuuint64_t strides[1] = {(cuuint64_t)cg.K * 4};
-        cuuint32_t box[2] = {TC_BK, (cuuint32_t)BN};
+        cuuint32_t box[2] = {TC_BK, (cuuint32_t)(cta2 ? BN / 2 : BN)};     // a CTA pair stages half of the tile per CTA
         if (!encode(&tmB, B, 2, dims, strides, box)) return cudaErrorInvalidValue;
         tmBlo = tmB;
         if (split == 3) {
-            cuuint32_t box_half[2] = {TC_BK, (cuuint32_t)(BN / 2)};
+            cuuint32_t box_half[2] = {TC_BK, (cuuint32_t)(cta2 ? BN / 4 : BN / 2)};
             if (!encode(&tmBlo, B, 2, dims, strides, box_half)) return cudaErrorInvalidValue;
         }
     }
@@ -625,6 +775,20 @@ cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, c
             g.tiles_per_group = g.n_m_tiles / G;
         }
     }
+#define XFRB_TC_PAIR(BN_)                                                                                \
+    switch (ep.kind) {                                                                                   \
+        case EPI_FWD_DUAL: return launch_cfg2<BN_, 3, EPI_FWD_DUAL>(tmA, tmB, tmBlo, g, ep, st);          \
+        case EPI_PLAIN: return launch_cfg2<BN_, 2, EPI_PLAIN>(tmA, tmB, tmBlo, g, ep, st);                \
+        case EPI_MID: return launch_cfg2<BN_, 2, EPI_MID>(tmA, tmB, tmBlo, g, ep, st);                    \
+        case EPI_JOIN: return launch_cfg2<BN_, 2, EPI_JOIN>(tmA, tmB, tmBlo, g, ep, st);                  \
+        default: return cudaErrorInvalidValue;                                                           \
+    }
+    if (cta2) {
+        if (BN == 256) { XFRB_TC_PAIR(256) }
+        else if (BN == 128) { XFRB_TC_PAIR(128) }
+        else { XFRB_TC_PAIR(64) }
+    }
+#undef XFRB_TC_PAIR
 #define XFRB_TC_KINDS(BN_, SP_)                                                                          \
     switch (ep.kind) {                                                                                   \
         case EPI_PLAIN: return launch_cfg<BN_, SP_, EPI_PLAIN>(tmA, tmB, tmBlo, g, ep, st);               \
