@@ -10,9 +10,10 @@
 //   warp 1      MMA issuer     - one lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) with the
 //                                accumulator in TMEM (two accumulator stages so the epilogue of tile i overlaps the
 //                                main loop of tile i+1); tcgen05.commit releases smem stages / publishes accumulators
-//   warps 2-5   operand split  - (3xTF32 only) rewrite the landed activation tile as hi = rna_tf32(x) in place and
-//                                lo = x - hi in a twin buffer (weights arrive pre-split from the host as two planes);
-//                                the issuer then runs hi*hi + lo*hi (+ hi*lo) into the same accumulator.
+//   warps 2-5   operand split  - (split plans only) lo = x - trunc_tf32(x) of the landed activation tile into a twin
+//                                buffer; the raw tile itself is the hi operand (the tensor core truncates fp32 to TF32);
+//                                weights arrive pre-split from the host as two planes.  The issuer runs hi*hi as soon
+//                                as the TMA data lands and lo*hi (+ hi*lo) one k-block later, into the same accumulator.
 //
 // CTA2: the same kernel as a CTA PAIR (cluster of 2, tcgen05 cta_group::2).  One M = 256 x BN tile per pair: each CTA
 //   loads and splits its own 128 activation rows and HALF of the weight tile (BN/2 rows); the leader CTA issues
@@ -338,10 +339,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(a * BN);
+            // The hi pass of a k-block needs only the TMA data (the tensor core truncates the raw fp32 activations to TF32
+            // itself), so it is issued as soon as the stage lands and runs while the split warps produce the lo tile.
             for (int kb = 0; kb < g.num_k; ++kb) {
                 if (lane == 0) {
-                    if (CTA2) mbar_wait_cluster(split_bar(s), ph);
-                    else mbar_wait(SPLIT3 ? split_bar(s) : full_bar(s), ph);
+                    if (CTA2) mbar_wait_cluster(split_bar(s), ph);            // implies both CTAs' TMA data landed
+                    else mbar_wait(full_bar(s), ph);
                     tc_fence_after();
                     const uint64_t dah = make_desc(a_hi(s)), dbh = make_desc(b_hi(s));
 #pragma unroll
@@ -350,6 +353,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         mma(tacc, dah + koff, dbh + koff, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     if (SPLIT3) {
+                        if (!CTA2) {
+                            mbar_wait(split_bar(s), ph);
+                            tc_fence_after();
+                        }
                         const uint64_t dal = make_desc(a_lo(s)), dbl = make_desc(b_lo(s));
 #pragma unroll
                         for (int k = 0; k < TC_BK / 8; ++k) {
@@ -386,14 +393,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     constexpr int NV = A_TILE_BYTES / 16;
 #pragma unroll 4
                     for (int i = t; i < NV; i += 128) {
-                        float4 v = hi[i];
-                        float4 h, l;
+                        // tcgen05 kind::tf32 reads only the top 19 bits of an fp32 operand (measured: tools_trunc_probe.py), so
+                        // the raw tile IS the hi operand, hi = trunc(x).  x - trunc(x) is exact in fp32 but carries up to 13
+                        // significant bits: it is rounded to nearest TF32 here so that the hardware truncation of the lo
+                        // operand loses nothing more and the residual (<= 2^-21 |x|) stays unbiased.
+                        const float4 v = hi[i];
+                        float4 l;
                         uint32_t u;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u); l.x = v.x - h.x;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y)); h.y = __uint_as_float(u); l.y = v.y - h.y;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u); l.z = v.z - h.z;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u); l.w = v.w - h.w;
-                        hi[i] = h;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u))); l.x = __uint_as_float(u);
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u))); l.y = __uint_as_float(u);
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u))); l.z = __uint_as_float(u);
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u))); l.w = __uint_as_float(u);
                         lo[i] = l;
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
