@@ -57,9 +57,10 @@ int xfrb_set_cta_pairs(int on);
 
 /* STR ResNet stem: o = conv7x7/2(x)+b  [N,112,112,64];  mp = maxpool3x3/2(relu(bn(o))) [N,56,56,64]
  * (reference resnet.py:225-228).  W is [147][64] ((r,s,ci) major), x is [N,224,224,3].  pool_pad = 1 (STR net) or 0
- * (VGGFace2 ResNet-50: MaxPool2d(3,2,0,ceil_mode=True), resnet50_128.py:16; windows clipped at the border). */
+ * (VGGFace2 ResNet-50: MaxPool2d(3,2,0,ceil_mode=True), resnet50_128.py:16; windows clipped at the border).
+ * mp_arg (may be NULL) [N,56,56,64] bytes: window position r*3+s of the first maximum, consumed by xfrb_stem_bwd. */
 int xfrb_stem_fwd(const float* x, const float* W, const float* b, const float* bn,
-                  float* o, float* mp, int N, int pool_pad, void* stream);
+                  float* o, float* mp, unsigned char* mp_arg, int N, int pool_pad, void* stream);
 
 /* u[N,H,W,C] -> out[N,H/2,W/2,C]: even pixels (input of a stride-2 1x1 conv, resnet.py:116) */
 int xfrb_subsample2(const float* u, float* out, int N, int H, int W, int C, void* stream);
@@ -134,9 +135,9 @@ int xfrb_ds_res(const float* g, const float* ap, float* gres_lo,
 /* Stem: hooks on the max-pool output, MaxPool backward (first maximum wins, as torch),
  * ReLU / MaxPool2d hooks, ReLU + BatchNorm backward, BatchNorm hook:
  *   P2 = P[-2] = relu(o)*relu(z) [J,112,112,64]; chansum [J,112,112]; sums [J] (double).
- * zc is scratch [J,56,56,64]. */
+ * zc is scratch [J,56,56,64].  mp_arg: the arg-max bytes of xfrb_stem_fwd, or NULL to re-derive them from o. */
 int xfrb_stem_bwd(const float* zmain, const float* gres, const float* o, const float* mp, const float* bn,
-                  float* zc, float* P2, float* chansum, double* sums,
+                  float* zc, float* P2, float* chansum, double* sums, const unsigned char* mp_arg,
                   int J, int N, int mode, float eps, int pool_pad, void* stream);
 
 /* ---- VGGFace2 ResNet-50-128d pieces (reference models/resnet50_128_pytorch/resnet50_128.py, whitebox.py:210-258) ---- */

@@ -72,7 +72,7 @@ class EmulBackend(object):
         self.impl_name = impl_name      # which weight packing the engine should build (the arithmetic here is fp32)
 
     # ------------------------------------------------------------ forward
-    def stem_fwd(self, x, stem, o, mp):
+    def stem_fwd(self, x, stem, o, mp, mp_arg=None):
         """x [N,224,224,3]; o = conv7x7/2(x)+b [N,112,112,64]; mp = maxpool3x3/2(relu(bn(o)))."""
         w = stem.W.view(7, 7, 3, stem.cout).permute(3, 2, 0, 1)
         oo = F.conv2d(x.permute(0, 3, 1, 2), w, stem.b, 2, 3)
@@ -345,7 +345,7 @@ class EmulBackend(object):
         gr = hook(True, relu(v_), relu(v_), gr, mode, self.eps)
         g_out.copy_((gr / 49.0).view(J, 1, 1, -1).expand(-1, 7, 7, -1))
 
-    def stem_bwd(self, zmain, gres, o, mp, bn, mode, P2, chansum, sums, pool_pad=1):
+    def stem_bwd(self, zmain, gres, o, mp, bn, mode, P2, chansum, sums, pool_pad=1, mp_arg=None):
         """Chain at the max-pool output (Conv2d + AvgPool2d(k=1) hooks, both affine), MaxPool
         backward, ReLU / MaxPool2d hooks, ReLU + BN backward, BN hook -> P[-2] = relu(o)*relu(z)."""
         J = zmain.shape[0]

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace xfrb {
 
@@ -13,7 +14,8 @@ void set_error(const char* what, cudaError_t e) {
 }
 
 // forward declarations of the stage launchers (stages.cu)
-cudaError_t launch_stem_fwd(const float*, const float*, const float*, const float*, float*, float*, int, int, cudaStream_t);
+cudaError_t launch_stem_fwd(const float*, const float*, const float*, const float*, float*, float*, unsigned char*, int, int,
+                            cudaStream_t);
 cudaError_t launch_bn_hook(const float*, const float*, const float*, const float*, float*, size_t, size_t, int, int, int, float,
                            cudaStream_t);
 cudaError_t launch_normalize_bwd(const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
@@ -30,7 +32,7 @@ cudaError_t launch_head_bwd_b(const float*, const float*, float*, int, int, int,
 cudaError_t launch_join(const JoinArgs&, cudaStream_t);
 cudaError_t launch_ds_res(const float*, const float*, float*, int, int, int, int, int, int, int, float, cudaStream_t);
 cudaError_t launch_stem_bwd(const float*, const float*, const float*, const float*, const float*, float*, float*, float*,
-                            double*, int, int, int, float, int, cudaStream_t);
+                            double*, const unsigned char*, int, int, int, float, int, cudaStream_t);
 cudaError_t launch_contrast(const float*, const double*, const float*, float*, int, int, int, cudaStream_t);
 cudaError_t launch_trunc_threshold(const float*, const double*, float, float*, int, size_t, cudaStream_t);
 cudaError_t launch_saliency_post(const float*, float*, int, int, int, float, cudaStream_t);
@@ -88,10 +90,10 @@ int xfrb_impl_available(int impl) {
 
 int xfrb_set_cta_pairs(int on) { return conv_tc_set_cta2(on); }
 
-int xfrb_stem_fwd(const float* x, const float* W, const float* b, const float* bn, float* o, float* mp, int N, int pool_pad,
-                  void* stream) {
+int xfrb_stem_fwd(const float* x, const float* W, const float* b, const float* bn, float* o, float* mp, unsigned char* mp_arg,
+                  int N, int pool_pad, void* stream) {
     if (pool_pad != 0 && pool_pad != 1) return finish("xfrb_stem_fwd", cudaErrorInvalidValue);
-    return finish("xfrb_stem_fwd", launch_stem_fwd(x, W, b, bn, o, mp, N, pool_pad, (cudaStream_t)stream));
+    return finish("xfrb_stem_fwd", launch_stem_fwd(x, W, b, bn, o, mp, mp_arg, N, pool_pad, (cudaStream_t)stream));
 }
 
 int xfrb_subsample2(const float* u, float* out, int N, int H, int W, int C, void* stream) {
@@ -202,7 +204,9 @@ int xfrb_dgrad_join(const float* y1, const float* Bd, const float* g_res, const 
     ep.mode = mode; ep.hooks = hooks; ep.eps = eps;
     ep.bn = bn3; ep.o = o3; ep.xr = xr3; ep.outp = out; ep.g_res = g_res; ep.res = res; ep.res_c = res_c;
     ep.out0 = g_out; ep.out1 = y3_out;
-    return finish("xfrb_dgrad_join", run_gemm(y1, Bd, g, ep, impl, (cudaStream_t)stream));
+    static int tn_cap = -1;
+    if (tn_cap < 0) { const char* e = getenv("XFRB_JOIN_BN"); tn_cap = e ? atoi(e) : 0; }
+    return finish("xfrb_dgrad_join", run_gemm(y1, Bd, g, ep, impl, (cudaStream_t)stream, tn_cap));
 }
 
 int xfrb_join(const float* zmain, int up, const float* gres_lo, int gres_c, int k, const float* out, const float* o3,
@@ -220,10 +224,12 @@ int xfrb_ds_res(const float* g, const float* ap, float* gres_lo, int J, int N, i
 }
 
 int xfrb_stem_bwd(const float* zmain, const float* gres, const float* o, const float* mp, const float* bn, float* zc, float* P2,
-                  float* chansum, double* sums, int J, int N, int mode, float eps, int pool_pad, void* stream) {
+                  float* chansum, double* sums, const unsigned char* mp_arg, int J, int N, int mode, float eps, int pool_pad,
+                  void* stream) {
     if (pool_pad != 0 && pool_pad != 1) return finish("xfrb_stem_bwd", cudaErrorInvalidValue);
     return finish("xfrb_stem_bwd",
-                  launch_stem_bwd(zmain, gres, o, mp, bn, zc, P2, chansum, sums, J, N, mode, eps, pool_pad, (cudaStream_t)stream));
+                  launch_stem_bwd(zmain, gres, o, mp, bn, zc, P2, chansum, sums, mp_arg, J, N, mode, eps, pool_pad,
+                                  (cudaStream_t)stream));
 }
 
 int xfrb_bn_hook(const float* g, const float* o, const float* xr, const float* bn, float* y, int J, int N, int HW, int C, int kind,

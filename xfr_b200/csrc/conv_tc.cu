@@ -2,7 +2,8 @@
 //
 //   D[m, n] = sum_k A[m, k] * B[n, k]      A: NHWC activations (R x R taps, stride 1, zero pad), B: K-major weights
 //
-// One persistent CTA per SM, 448 threads, warp-specialised:
+// One persistent CTA per SM, 512 threads in four warpgroups, warp-specialised (setmaxnreg moves the registers the
+// producer warpgroups do not need to the epilogue warpgroups, whose loads are double-buffered in registers):
 //   warp 0      TMA producer   - cp.async.bulk.tensor loads of the A tile (128 pixel rows x 32 channels; for 3x3 convs a
 //                                4-D box (32ch, W, bh rows, bn images) shifted by the tap, out-of-bounds rows/columns
 //                                zero-filled by the TMA unit = the conv padding) and of the B tile (BN x 32), both
@@ -10,7 +11,7 @@
 //   warp 1      MMA issuer     - one lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) with the
 //                                accumulator in TMEM (two accumulator stages so the epilogue of tile i overlaps the
 //                                main loop of tile i+1); tcgen05.commit releases smem stages / publishes accumulators
-//   warps 2-5   operand split  - (split plans only) lo = x - trunc_tf32(x) of the landed activation tile into a twin
+//   warps 4-7   operand split  - (split plans only) lo = x - trunc_tf32(x) of the landed activation tile into a twin
 //                                buffer; the raw tile itself is the hi operand (the tensor core truncates fp32 to TF32);
 //                                weights arrive pre-split from the host as two planes.  The issuer runs hi*hi as soon
 //                                as the TMA data lands and lo*hi (+ hi*lo) one k-block later, into the same accumulator.
@@ -29,8 +30,9 @@
 //      product with relu(W) rounded to TF32; the lo weight plane is never loaded.  Using the same rounded W+ for the X of
 //      the forward twin and for the dgrad keeps excitation backprop mass-conserving.
 //   3  dual forward pack [W rows | relu(W) rows]: A_hi*B_hi + A_lo*B_hi over the whole tile, A_hi*B_lo over the W half only
-//   warps 6-13  epilogue       - tcgen05.ld the accumulator (lane = pixel row), apply the fused EBP epilogue of
-//                                common.cuh against the saved tensors, store NHWC fp32 with 128-bit accesses
+//   warps 8-15  epilogue       - tcgen05.ld the accumulator (lane = pixel row), apply the fused EBP epilogue of
+//                                common.cuh against the saved tensors, store NHWC fp32 with 128-bit accesses; the
+//                                global loads of slab j+1 are in flight while slab j is computed
 #include "common.cuh"
 #include <cuda.h>
 #include <stdio.h>
@@ -42,7 +44,12 @@ namespace xfrb {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                       // 32 fp32 = one 128-byte swizzle row
 constexpr int TC_EPI_WARPS = 8;                  // two warps per TMEM lane quarter, alternating 16-column chunks
-constexpr int TC_THREADS = (6 + TC_EPI_WARPS) * 32;   // 448
+constexpr int TC_FIRST_SPLIT_WARP = 4;           // warpgroup 0: TMA, MMA, 2 idle; warpgroup 1: split; warpgroups 2-3: epilogue
+constexpr int TC_FIRST_EPI_WARP = 8;
+constexpr int TC_THREADS = (TC_FIRST_EPI_WARP + TC_EPI_WARPS) * 32;   // 512
+// register budget per role (setmaxnreg, whole warpgroups): 256 x 56 + 256 x 200 = 65536
+constexpr int TC_REGS_PRODUCER = 56;
+constexpr int TC_REGS_EPILOGUE = 200;
 constexpr uint32_t A_TILE_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 
 struct TcGeom {
@@ -196,7 +203,9 @@ struct TcCfg {
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + PRM_BYTES + TR_BYTES;
 };
 
-template <int BN, int SPLIT, int KIND, bool CTA2>
+// MODE: the ebp_subtree_mode id of the MID / JOIN hook chains as a compile-time constant (the chains are ~2x cheaper once
+// the mode branches fold away: tools_epi_probe.py), or -1 to read it from EpiParams at run time.
+template <int BN, int SPLIT, int KIND, bool CTA2, int MODE = -1>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBlo, const TcGeom g, const EpiParams ep) {
@@ -288,6 +297,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (phantom) mvalid = 0;
     };
 
+    if (warp < TC_FIRST_SPLIT_WARP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_PRODUCER));      // whole warpgroup 0
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
@@ -378,10 +389,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
         }
-    } else if (warp < 6) {
+    }
+    } else if (warp < TC_FIRST_EPI_WARP) {
         // ===================== operand split (3xTF32) =====================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_PRODUCER));  // whole warpgroup 1
         if (SPLIT3) {
-            const int t = threadIdx.x - 64;    // 0..127
+            const int t = threadIdx.x - TC_FIRST_SPLIT_WARP * 32;    // 0..127
             int s = 0;
             uint32_t ph = 0;
             for (int tile = worker; tile < total_tiles; tile += nworkers) {
@@ -424,14 +437,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // access of the epilogue is then a 64-byte row segment per 4 lanes (8 rows per request instead of 32), and all
         // loads of a slab are issued before the accumulator is waited for.  The two warps of a TMEM lane quarter
         // alternate slabs; per-channel constants are staged in smem once per tile.
-        const int ew = warp - 6;                       // 0..7
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPILOGUE));  // warpgroups 2 and 3
+        const int ew = warp - TC_FIRST_EPI_WARP;       // 0..7
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
         const int half = ew >> 2;                      // which slabs of the tile this warp owns
-        const int et = threadIdx.x - 6 * 32;           // 0..255
+        const int et = threadIdx.x - TC_FIRST_EPI_WARP * 32;   // 0..255
         const int cgl = lane & 3;                      // my 4-channel group inside the slab
         const int rsub = lane >> 2;                    // my row inside each group of 8 rows
         float4* tbuf = tr_s + ew * 128;
         constexpr int CH = (KIND == EPI_FWD_DUAL) ? BN / 2 : BN;      // channels per tile
+        constexpr int NL = (KIND == EPI_JOIN) ? 4 : (KIND == EPI_MID) ? 2 : 1;     // tensors loaded per output element
+        struct Loads { float4 v[NL][4]; };             // one slab's global loads: [tensor][row group]
         int it = 0;
         for (int tile = worker; tile < total_tiles; tile += nworkers, ++it) {
             const int a = it & 1;
@@ -455,10 +471,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else if (KIND == EPI_PLAIN) {
                 for (int i = et; i < BN; i += TC_EPI_WARPS * 32) prm[4 * BN + i] = ep.bias ? __ldg(ep.bias + ncol0 + i) : 0.f;
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
-            mbar_wait(tfull_bar(a), aph);
-            tc_fence_after();
-            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
             // rows this thread finishes (coalesced orientation)
             int mrow[4], msav[4];
             bool vrow[4];
@@ -469,34 +481,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mrow[i] = m0 + r;
                 msav[i] = (KIND == EPI_MID || KIND == EPI_JOIN) ? mrow[i] % ep.Ms : mrow[i];
             }
-#pragma unroll 1
-            for (int j = half * 16; j < CH; j += 32) {
+            // ---- every global load of slab j (issued one slab ahead of its use)
+            const int mode = MODE >= 0 ? MODE : ep.mode;
+            const int dbg = ep.hooks >> 8;              // profiling switches (tools_epi_probe.py): 1 no loads, 2 no stores, 4 no math
+            auto issue_loads = [&](int j, Loads& L) {
+                const int c = cbase + j + 4 * cgl;
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                    for (int t = 0; t < NL; ++t) L.v[t][i] = z4;
+                    if (!vrow[i] || (dbg & 1)) continue;
+                    if (KIND == EPI_FWD_DUAL) {
+                        if (ep.res != nullptr && c < ep.res_c) L.v[0][i] = __ldg(reinterpret_cast<const float4*>(ep.res + (size_t)mrow[i] * ep.res_c + c));
+                    } else if (KIND == EPI_PLAIN) {
+                        if (ep.g_res != nullptr) L.v[0][i] = *reinterpret_cast<const float4*>(ep.g_res + (size_t)mrow[i] * ep.C + c);
+                    } else {
+                        const size_t offs = (size_t)msav[i] * ep.C + c;
+                        L.v[0][i] = __ldg(reinterpret_cast<const float4*>(ep.o + offs));
+                        L.v[1][i] = __ldg(reinterpret_cast<const float4*>(ep.xr + offs));
+                        if (KIND == EPI_JOIN) {
+                            L.v[2][i] = __ldg(reinterpret_cast<const float4*>(ep.outp + offs));
+                            L.v[3][i] = __ldg(reinterpret_cast<const float4*>(ep.g_res + (size_t)mrow[i] * ep.C + c));
+                        }
+                    }
+                }
+            };
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
+            // ---- accumulator slab j -> epilogue math -> stores
+            auto process = [&](int j, const Loads& L) {
                 const int c = cbase + j + 4 * cgl;
                 float vt[16], vp[16];
                 tmem_ld16(tacc + j, vt);
                 if (KIND == EPI_FWD_DUAL) tmem_ld16(tacc + CH + j, vp);
-                // ---- issue every global load of this slab before touching the accumulator
-                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                float4 l0[4], l1[4], l2[4], l3[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    l0[i] = l1[i] = l2[i] = l3[i] = z4;
-                    if (!vrow[i]) continue;
-                    if (KIND == EPI_FWD_DUAL) {
-                        if (ep.res != nullptr && c < ep.res_c) l0[i] = __ldg(reinterpret_cast<const float4*>(ep.res + (size_t)mrow[i] * ep.res_c + c));
-                    } else if (KIND == EPI_PLAIN) {
-                        if (ep.g_res != nullptr) l0[i] = *reinterpret_cast<const float4*>(ep.g_res + (size_t)mrow[i] * ep.C + c);
-                    } else if (KIND == EPI_MID || KIND == EPI_JOIN) {
-                        const size_t offs = (size_t)msav[i] * ep.C + c;
-                        l0[i] = __ldg(reinterpret_cast<const float4*>(ep.o + offs));
-                        l1[i] = __ldg(reinterpret_cast<const float4*>(ep.xr + offs));
-                        if (KIND == EPI_JOIN) {
-                            l2[i] = __ldg(reinterpret_cast<const float4*>(ep.outp + offs));
-                            l3[i] = __ldg(reinterpret_cast<const float4*>(ep.g_res + (size_t)mrow[i] * ep.C + c));
-                        }
-                    }
-                }
-                // ---- transpose the accumulator slab(s): row-per-lane -> channel-group-per-lane
+                // transpose the accumulator slab(s): row-per-lane -> channel-group-per-lane
                 float4 at[4], apv[4];
                 tmem_ld_wait(vt);
 #pragma unroll
@@ -522,7 +540,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     __syncwarp();
                 }
-                // ---- per-channel constants of my 4 channels
+                // per-channel constants of my 4 channels
                 const int pj = j + 4 * cgl;
                 BnC b[4];
                 float bt[4] = {0.f, 0.f, 0.f, 0.f}, bp[4] = {0.f, 0.f, 0.f, 0.f};
@@ -544,8 +562,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (!vrow[i]) continue;
                     const size_t off = (size_t)mrow[i] * ep.C + c;
                     const float av[4] = {at[i].x, at[i].y, at[i].z, at[i].w};
-                    const float la[4] = {l0[i].x, l0[i].y, l0[i].z, l0[i].w};
-                    const float lb[4] = {l1[i].x, l1[i].y, l1[i].z, l1[i].w};
+                    const float la[4] = {L.v[0][i].x, L.v[0][i].y, L.v[0][i].z, L.v[0][i].w};
                     float r0[4], r1[4], r2[4];
                     if (KIND == EPI_PLAIN) {
 #pragma unroll
@@ -560,19 +577,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (!(ep.hooks & 1)) r2[e] = fmaxf(r2[e], 0.f);
                         }
                     } else if (KIND == EPI_MID) {
+                        const float lb[4] = {L.v[NL > 1 ? 1 : 0][i].x, L.v[NL > 1 ? 1 : 0][i].y, L.v[NL > 1 ? 1 : 0][i].z, L.v[NL > 1 ? 1 : 0][i].w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) r0[e] = mid_chain(av[e], la[e], lb[e], b[e], ep.mode, ep.eps);
+                        for (int e = 0; e < 4; ++e) r0[e] = mid_chain(av[e], la[e], lb[e], b[e], mode, ep.eps);
                     } else {
-                        const float lc[4] = {l2[i].x, l2[i].y, l2[i].z, l2[i].w};
-                        const float ld[4] = {l3[i].x, l3[i].y, l3[i].z, l3[i].w};
+                        const float4 v1 = L.v[NL > 1 ? 1 : 0][i], v2 = L.v[NL > 2 ? 2 : 0][i], v3 = L.v[NL > 3 ? 3 : 0][i];
+                        const float lb[4] = {v1.x, v1.y, v1.z, v1.w};
+                        const float lc[4] = {v2.x, v2.y, v2.z, v2.w};
+                        const float ld[4] = {v3.x, v3.y, v3.z, v3.w};
                         float rr[4] = {0.f, 0.f, 0.f, 0.f};
-                        if (ep.mode == XFRB_MODE_ALL && ep.res != nullptr && c < ep.res_c) {
+                        if (mode == XFRB_MODE_ALL && ep.res != nullptr && c < ep.res_c) {
                             const float4 t = __ldg(reinterpret_cast<const float4*>(ep.res + (size_t)msav[i] * ep.res_c + c));
                             rr[0] = t.x; rr[1] = t.y; rr[2] = t.z; rr[3] = t.w;
                         }
+                        if (dbg & 4) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            join_chain(__fadd_rn(av[e], ld[e]), lc[e], la[e], lb[e], rr[e], b[e], ep.hooks, ep.mode, ep.eps, r0[e], r1[e]);
+                            for (int e = 0; e < 4; ++e) { r0[e] = av[e] + ld[e]; r1[e] = lc[e] + la[e] + lb[e]; }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                join_chain(__fadd_rn(av[e], ld[e]), lc[e], la[e], lb[e], rr[e], b[e], ep.hooks & 255, mode, ep.eps, r0[e], r1[e]);
+                        }
+                    }
+                    if (dbg & 2) {
+                        if (r0[0] + r0[1] + r0[2] + r0[3] + r1[0] + r1[1] + r1[2] + r1[3] != 1.2345e-30f) continue;    // keep the math alive
                     }
                     *reinterpret_cast<float4*>(ep.out0 + off) = make_float4(r0[0], r0[1], r0[2], r0[3]);
                     if (KIND == EPI_FWD_DUAL || KIND == EPI_JOIN)
@@ -580,6 +608,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (KIND == EPI_FWD_DUAL)
                         *reinterpret_cast<float4*>(ep.out2 + off) = make_float4(r2[0], r2[1], r2[2], r2[3]);
                 }
+            };
+            // the first slab's loads go out before the accumulator is waited for; afterwards slab j+1 is always in flight
+            Loads La, Lb;
+            const int j0 = half * 16;
+            issue_loads(j0, La);
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");      // constants staged
+            mbar_wait(tfull_bar(a), aph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int j = j0; j < CH; j += 64) {
+                const bool more1 = j + 32 < CH, more2 = j + 64 < CH;
+                if (more1) issue_loads(j + 32, Lb);
+                process(j, La);
+                if (more2) issue_loads(j + 64, La);
+                if (more1) process(j + 32, Lb);
             }
             tc_fence_before();
             __syncwarp();
@@ -630,14 +673,14 @@ static bool encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t
 
 bool conv_tc_available() { return true; }
 
-template <int BN, int SPLIT, int KIND>
+template <int BN, int SPLIT, int KIND, int MODE = -1>
 static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo, const TcGeom& g,
                               const EpiParams& ep, cudaStream_t st) {
     using Cfg = TcCfg<BN, SPLIT, false>;
     static bool attr = false;
     static int sms = 0;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT, KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT, KIND, false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -646,7 +689,7 @@ static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, co
     }
     int total = g.n_m_tiles * g.n_n_tiles;
     int grid = total < sms ? total : sms;
-    conv_tc_kernel<BN, SPLIT, KIND, false><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmBlo, g, ep);
+    conv_tc_kernel<BN, SPLIT, KIND, false, MODE><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmBlo, g, ep);
     return cudaGetLastError();
 }
 
@@ -814,7 +857,16 @@ cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, c
     }                                                                                                    \
     if (split == 0) { XFRB_TC_KINDS(BN_, 0) }                                                            \
     else if (split == 1) { XFRB_TC_KINDS(BN_, 1) }                                                       \
-    else { XFRB_TC_KINDS(BN_, 2) }                                                                       \
+    else {                                                                                               \
+        /* the product plan: hook chains specialised per ebp_subtree_mode */                             \
+        if (ep.kind == EPI_MID && ep.mode == 0) return launch_cfg<BN_, 2, EPI_MID, 0>(tmA, tmB, tmBlo, g, ep, st);    \
+        if (ep.kind == EPI_MID && ep.mode == 1) return launch_cfg<BN_, 2, EPI_MID, 1>(tmA, tmB, tmBlo, g, ep, st);    \
+        if (ep.kind == EPI_MID && ep.mode == 2) return launch_cfg<BN_, 2, EPI_MID, 2>(tmA, tmB, tmBlo, g, ep, st);    \
+        if (ep.kind == EPI_JOIN && ep.mode == 0) return launch_cfg<BN_, 2, EPI_JOIN, 0>(tmA, tmB, tmBlo, g, ep, st);  \
+        if (ep.kind == EPI_JOIN && ep.mode == 1) return launch_cfg<BN_, 2, EPI_JOIN, 1>(tmA, tmB, tmBlo, g, ep, st);  \
+        if (ep.kind == EPI_JOIN && ep.mode == 2) return launch_cfg<BN_, 2, EPI_JOIN, 2>(tmA, tmB, tmBlo, g, ep, st);  \
+        XFRB_TC_KINDS(BN_, 2)                                                                            \
+    }                                                                                                    \
     return cudaErrorInvalidValue;
     if (BN == 256) { XFRB_TC_DISPATCH(256) }
     else if (BN == 128) { XFRB_TC_DISPATCH(128) }

@@ -8,14 +8,16 @@ namespace xfrb {
 
 // ------------------------------------------------------------------ stem forward
 // o[n,oh,ow,co] = sum_{r,s,ci} x[n,2oh+r-3,2ow+s-3,ci] * W[(r,s,ci),co] + b[co]      (resnet.py:177,225)
-// block = 8x8 output pixels x 64 channels; 256 threads = 64 pixels x 4 channel groups of 16.
-constexpr int ST_T = 8;                   // output tile edge
-constexpr int ST_P = ST_T * 2 + 5;        // input patch edge (21)
-__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ W,
-                                                        const float* __restrict__ b, float* __restrict__ o, int N) {
+// block = 16x16 output pixels x 64 channels; 256 threads = 64 quads of 4 consecutive pixels x 4 channel groups of 16:
+// 64 accumulators per thread, 8 FMAs per shared-memory load (the 8x8-pixel / 16-accumulator version was LSU-bound at 12 %
+// of the FMA peak and re-read the 37 KB of weights once per 64 pixels).
+constexpr int ST_T = 16;                  // output tile edge
+constexpr int ST_P = ST_T * 2 + 5;        // input patch edge (37)
+__global__ void __launch_bounds__(256, 2) stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                           const float* __restrict__ b, float* __restrict__ o, int N) {
     extern __shared__ __align__(16) float sm[];
     float* sW = sm;                       // [147][64]
-    float* sx = sm + 147 * 64;            // [21][21][3]
+    float* sx = sm + 147 * 64;            // [37][37][3]
     const int tid = threadIdx.x;
     const int n = blockIdx.z, oh0 = blockIdx.y * ST_T, ow0 = blockIdx.x * ST_T;
     for (int i = tid; i < 147 * 64 / 4; i += 256) reinterpret_cast<float4*>(sW)[i] = __ldg(reinterpret_cast<const float4*>(W) + i);
@@ -29,39 +31,51 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
         sx[i] = v;
     }
     __syncthreads();
-    const int pix = tid >> 2, cg = tid & 3;
-    const int py = pix >> 3, px = pix & 7;
-    float acc[16];
+    const int quad = tid >> 2, cg = tid & 3;
+    const int py = quad >> 2, px0 = (quad & 3) * 4;
+    float acc[4][16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[p][j] = 0.f;
     for (int r = 0; r < 7; ++r) {
-        const float* xr = sx + ((py * 2 + r) * ST_P + px * 2) * 3;
+        const float* xr = sx + ((py * 2 + r) * ST_P + px0 * 2) * 3;
         const float* wr = sW + (r * 21) * 64 + cg * 16;
-#pragma unroll
+#pragma unroll 7
         for (int sc = 0; sc < 21; ++sc) {
-            float xv = xr[sc];
+            const float xv[4] = {xr[sc], xr[sc + 6], xr[sc + 12], xr[sc + 18]};     // pixels 2 columns (6 floats) apart
             const float4* w4 = reinterpret_cast<const float4*>(wr + sc * 64);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                float4 w = w4[q];
-                acc[q * 4 + 0] = fmaf(xv, w.x, acc[q * 4 + 0]);
-                acc[q * 4 + 1] = fmaf(xv, w.y, acc[q * 4 + 1]);
-                acc[q * 4 + 2] = fmaf(xv, w.z, acc[q * 4 + 2]);
-                acc[q * 4 + 3] = fmaf(xv, w.w, acc[q * 4 + 3]);
+                const float4 w = w4[q];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    acc[p][q * 4 + 0] = fmaf(xv[p], w.x, acc[p][q * 4 + 0]);
+                    acc[p][q * 4 + 1] = fmaf(xv[p], w.y, acc[p][q * 4 + 1]);
+                    acc[p][q * 4 + 2] = fmaf(xv[p], w.z, acc[p][q * 4 + 2]);
+                    acc[p][q * 4 + 3] = fmaf(xv[p], w.w, acc[p][q * 4 + 3]);
+                }
             }
         }
     }
-    float* op = o + (((size_t)n * 112 + oh0 + py) * 112 + ow0 + px) * 64 + cg * 16;
+    float4 bb[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        float4 bb = __ldg(reinterpret_cast<const float4*>(b + cg * 16) + q);
-        st4(op + q * 4, make_float4(acc[q * 4] + bb.x, acc[q * 4 + 1] + bb.y, acc[q * 4 + 2] + bb.z, acc[q * 4 + 3] + bb.w));
+    for (int q = 0; q < 4; ++q) bb[q] = __ldg(reinterpret_cast<const float4*>(b + cg * 16) + q);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        float* op = o + (((size_t)n * 112 + oh0 + py) * 112 + ow0 + px0 + p) * 64 + cg * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            st4(op + q * 4, make_float4(acc[p][q * 4] + bb[q].x, acc[p][q * 4 + 1] + bb[q].y, acc[p][q * 4 + 2] + bb[q].z,
+                                        acc[p][q * 4 + 3] + bb[q].w));
     }
 }
 
 // mp = maxpool3x3/2 pad 1 of relu(bn(o))   (resnet.py:226-228)
-__global__ void stem_pool_kernel(const float* __restrict__ o, const float* __restrict__ bn, float* __restrict__ mp, int total4,
-                                 int pad) {
+// arg (may be null): position r*3+s of the FIRST maximum of each window (torch's scan order), one byte per pooled element -
+// what MaxPool2d backward routes by, recorded here so the backward sweep does not re-derive it per gradient row.
+__global__ void stem_pool_kernel(const float* __restrict__ o, const float* __restrict__ bn, float* __restrict__ mp,
+                                 unsigned char* __restrict__ arg, int total4, int pad) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
     int c = (i & 15) * 4;
@@ -70,7 +84,9 @@ __global__ void stem_pool_kernel(const float* __restrict__ o, const float* __res
     int ph = p % 56;
     int n = p / 56;
     float4 al = ld4(bn + c), be = ld4(bn + 64 + c);
-    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    unsigned char am[4] = {0, 0, 0, 0};
+    const float alv[4] = {al.x, al.y, al.z, al.w}, bev[4] = {be.x, be.y, be.z, be.w};
     for (int r = 0; r < 3; ++r) {
         int h = ph * 2 - pad + r;
         if (h < 0 || h >= 112) continue;
@@ -78,17 +94,20 @@ __global__ void stem_pool_kernel(const float* __restrict__ o, const float* __res
             int w = pw * 2 - pad + s;
             if (w < 0 || w >= 112) continue;
             float4 v = ld4(o + (((size_t)n * 112 + h) * 112 + w) * 64 + c);
-            m.x = fmaxf(m.x, fmaxf(__fadd_rn(__fmul_rn(v.x, al.x), be.x), 0.f));
-            m.y = fmaxf(m.y, fmaxf(__fadd_rn(__fmul_rn(v.y, al.y), be.y), 0.f));
-            m.z = fmaxf(m.z, fmaxf(__fadd_rn(__fmul_rn(v.z, al.z), be.z), 0.f));
-            m.w = fmaxf(m.w, fmaxf(__fadd_rn(__fmul_rn(v.w, al.w), be.w), 0.f));
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float rv = fmaxf(__fadd_rn(__fmul_rn(vv[q], alv[q]), bev[q]), 0.f);
+                if (rv > m[q]) { m[q] = rv; am[q] = (unsigned char)(r * 3 + s); }
+            }
         }
     }
-    st4(mp + (size_t)i * 4, m);
+    st4(mp + (size_t)i * 4, make_float4(m[0], m[1], m[2], m[3]));
+    if (arg != nullptr) reinterpret_cast<uchar4*>(arg)[i] = make_uchar4(am[0], am[1], am[2], am[3]);
 }
 
-cudaError_t launch_stem_fwd(const float* x, const float* W, const float* b, const float* bn, float* o, float* mp, int N,
-                            int pool_pad, cudaStream_t st) {
+cudaError_t launch_stem_fwd(const float* x, const float* W, const float* b, const float* bn, float* o, float* mp,
+                            unsigned char* mp_arg, int N, int pool_pad, cudaStream_t st) {
     size_t smem = (147 * 64 + ST_P * ST_P * 3) * sizeof(float);
     static bool attr = false;
     if (!attr) {
@@ -97,7 +116,7 @@ cudaError_t launch_stem_fwd(const float* x, const float* W, const float* b, cons
     }
     stem_conv_kernel<<<dim3(112 / ST_T, 112 / ST_T, N), 256, smem, st>>>(x, W, b, o, N);
     int total4 = N * 56 * 56 * 16;
-    stem_pool_kernel<<<(total4 + 255) / 256, 256, 0, st>>>(o, bn, mp, total4, pool_pad);
+    stem_pool_kernel<<<(total4 + 255) / 256, 256, 0, st>>>(o, bn, mp, mp_arg, total4, pool_pad);
     return cudaGetLastError();
 }
 
@@ -365,6 +384,7 @@ __global__ void stem_bwd_a_kernel(const float* __restrict__ zmain, const float* 
 __global__ void __launch_bounds__(256) stem_bwd_b_kernel(const float* __restrict__ zc, const float* __restrict__ o,
                                                          const float* __restrict__ bn, float* __restrict__ P2,
                                                          float* __restrict__ chansum, double* __restrict__ sums,
+                                                         const unsigned char* __restrict__ mp_arg,
                                                          int N, int mode, float eps, int pad) {
     // grid: (112*112*16/256, J)
     __shared__ double red[8];
@@ -398,6 +418,11 @@ __global__ void __launch_bounds__(256) stem_bwd_b_kernel(const float* __restrict
             if (pw < 0 || pw >= 56 || 2 * pw - pad > w || w > 2 * pw - pad + 2) continue;
             bool win[4] = {true, true, true, true};
             const int my = h - (2 * ph - pad), mx = w - (2 * pw - pad);     // my position inside the window
+            if (mp_arg != nullptr) {        // the forward pass recorded which position won each window
+                const uchar4 am = __ldg(reinterpret_cast<const uchar4*>(mp_arg) + (((size_t)n * 56 + ph) * 56 + pw) * 16 + (c >> 2));
+                const int me_idx = my * 3 + mx;
+                win[0] = am.x == me_idx; win[1] = am.y == me_idx; win[2] = am.z == me_idx; win[3] = am.w == me_idx;
+            } else
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -450,12 +475,12 @@ __global__ void __launch_bounds__(256) stem_bwd_b_kernel(const float* __restrict
 }
 
 cudaError_t launch_stem_bwd(const float* zmain, const float* gres, const float* o, const float* mp, const float* bn,
-                            float* zc, float* P2, float* chansum, double* sums, int J, int N, int mode, float eps,
-                            int pool_pad, cudaStream_t st) {
+                            float* zc, float* P2, float* chansum, double* sums, const unsigned char* mp_arg, int J, int N,
+                            int mode, float eps, int pool_pad, cudaStream_t st) {
     size_t per4 = (size_t)56 * 56 * 16, total4 = per4 * J;
     cudaMemsetAsync(sums, 0, sizeof(double) * J, st);
     stem_bwd_a_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(zmain, gres, mp, zc, per4, N, mode, eps, total4);
-    stem_bwd_b_kernel<<<dim3(112 * 112 * 16 / 256, J), 256, 0, st>>>(zc, o, bn, P2, chansum, sums, N, mode, eps, pool_pad);
+    stem_bwd_b_kernel<<<dim3(112 * 112 * 16 / 256, J), 256, 0, st>>>(zc, o, bn, P2, chansum, sums, mp_arg, N, mode, eps, pool_pad);
     return cudaGetLastError();
 }
 

@@ -142,7 +142,8 @@ class StResnetEngine(_Engine):
         S = {'N': N}
         S['o_s'] = self.buf('o_s', N, 112, 112, 64)
         S['mp'] = self.buf('mp', N, 56, 56, 64)
-        be.stem_fwd(x_nhwc, self.stem, S['o_s'], S['mp'])
+        S['mp_arg'] = self.buf('mp_arg', N, 56, 56, 64, dtype=torch.uint8)      # which window position won each max-pool
+        be.stem_fwd(x_nhwc, self.stem, S['o_s'], S['mp'], S['mp_arg'])
         u = S['mp']
         for i, b in enumerate(self.blocks):
             h = b.hw
@@ -257,7 +258,7 @@ class StResnetEngine(_Engine):
                 P2 = self.buf('P2', J, 112, 112, 64)
                 chansum = self.buf('chansum', J, 112, 112)
                 sums = self.buf('sums', J, dtype=torch.float64)
-                be.stem_bwd(zlo, gres, S['o_s'], S['mp'], self.stem.bn, m, P2, chansum, sums)
+                be.stem_bwd(zlo, gres, S['o_s'], S['mp'], self.stem.bn, m, P2, chansum, sums, mp_arg=S['mp_arg'])
                 return P2, chansum, sums
             p, tp = self.blocks[i - 1], S[i - 1]
             hp = b.hw_in
@@ -306,7 +307,8 @@ class Resnet50_128Engine(_Engine):
         S = {'N': N}
         S['o_s'] = self.buf('o_s', N, 112, 112, 64)
         S['mp'] = self.buf('mp', N, 56, 56, 64)
-        be.stem_fwd(x_nhwc, self.stem, S['o_s'], S['mp'])
+        S['mp_arg'] = self.buf('mp_arg', N, 56, 56, 64, dtype=torch.uint8)      # which window position won each max-pool
+        be.stem_fwd(x_nhwc, self.stem, S['o_s'], S['mp'], S['mp_arg'])
         u = S['mp']
         for i, b in enumerate(self.blocks):
             h = b.hw
@@ -391,7 +393,7 @@ class Resnet50_128Engine(_Engine):
                 P2 = self.buf('P2', J, 112, 112, 64)
                 chansum = self.buf('chansum', J, 112, 112)
                 sums = self.buf('sums', J, dtype=torch.float64)
-                be.stem_bwd(zlo, None, S['o_s'], S['mp'], self.stem.bn, m, P2, chansum, sums, 0)
+                be.stem_bwd(zlo, None, S['o_s'], S['mp'], self.stem.bn, m, P2, chansum, sums, 0, mp_arg=S['mp_arg'])
                 return P2, chansum, sums
             p, tp = self.blocks[i - 1], S[i - 1]
             hp = b.hw_in

@@ -22,7 +22,7 @@ _F = ctypes.c_float
 
 # name -> argtypes, in the order of include/xfrb.h
 _SIGNATURES = {
-    'xfrb_stem_fwd': [_P, _P, _P, _P, _P, _P, _I, _I, _P],
+    'xfrb_stem_fwd': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     'xfrb_subsample2': [_P, _P, _I, _I, _I, _I, _P],
     'xfrb_avgpool2': [_P, _P, _I, _I, _I, _I, _P],
     'xfrb_conv_dual': [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -33,7 +33,7 @@ _SIGNATURES = {
     'xfrb_dgrad_join': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     'xfrb_join': [_P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     'xfrb_ds_res': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
-    'xfrb_stem_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
+    'xfrb_stem_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
     'xfrb_bn_hook': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     'xfrb_hook': [_P, _I, _I, _P, _I, _I, _F, _P, _I, _P, _P, _I, _P, _P, _I, ctypes.c_longlong, _F, _P, _P, _I, _I, _I, _I, _I,
                   _I, _I, _I, _I, _I, _I, _F, _P],
@@ -126,8 +126,8 @@ class CudaBackend(object):
         return t
 
     # -------------------------------------------------------------- forward
-    def stem_fwd(self, x, stem, o, mp):
-        self._check(self.lib.xfrb_stem_fwd(_ptr(x), _ptr(stem.W), _ptr(stem.b), _ptr(stem.bn), _ptr(o), _ptr(mp),
+    def stem_fwd(self, x, stem, o, mp, mp_arg=None):
+        self._check(self.lib.xfrb_stem_fwd(_ptr(x), _ptr(stem.W), _ptr(stem.b), _ptr(stem.bn), _ptr(o), _ptr(mp), _ptr(mp_arg),
                                            x.shape[0], stem.pool_pad, self._st()), 2)
 
     def subsample2(self, u, out):
@@ -190,11 +190,11 @@ class CudaBackend(object):
         self._check(self.lib.xfrb_ds_res(_ptr(g), _ptr(ap), _ptr(gres_lo), J, ap.shape[0], H, W, C, ap.shape[-1], mode,
                                          self.eps, self._st()))
 
-    def stem_bwd(self, zmain, gres, o, mp, bn, mode, P2, chansum, sums, pool_pad=1):
+    def stem_bwd(self, zmain, gres, o, mp, bn, mode, P2, chansum, sums, pool_pad=1, mp_arg=None):
         J = zmain.shape[0]
         zc = self._tmp('stem_zc', J * 56 * 56 * 64)
         self._check(self.lib.xfrb_stem_bwd(_ptr(zmain), _ptr(gres), _ptr(o), _ptr(mp), _ptr(bn), _ptr(zc), _ptr(P2),
-                                           _ptr(chansum), _ptr(sums), J, o.shape[0], mode, self.eps, pool_pad, self._st()), 2)
+                                           _ptr(chansum), _ptr(sums), _ptr(mp_arg), J, o.shape[0], mode, self.eps, pool_pad, self._st()), 2)
 
     # -------------------------------------------------------------- generic single-hook path
     def hook(self, z_in, z_out, shape, recipe, affine, mode, s0=None, s1=None, s2=None, bn=None, up=1, zc=None, z_in2=None, k2=1,
