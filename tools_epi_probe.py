@@ -5,7 +5,8 @@ sys.path.insert(0, '.')
 from xfr_b200.kernels import CudaBackend
 from xfr_b200.packing import gemm_planes
 be = CudaBackend('cuda:0', impl='tf32x3')
-J, N, H, Cin, Cout = 256, 128, 14, 1024, 256
+import os
+J, N, H, Cin, Cout = 256, 128, 14, 1024, int(os.environ.get("PROBE_K", "256"))
 g = torch.Generator().manual_seed(0)
 dev = 'cuda'
 y1 = torch.rand(J, H, H, Cout, generator=g).to(dev)

@@ -189,14 +189,17 @@ __device__ __forceinline__ void tmem_ld_wait(float* v) {
 }
 
 // ------------------------------------------------------------------ kernel
-template <int BN, int SPLIT, bool CTA2 = false>
+// KIND only matters for the stage count: the JOIN kernels (K = Cout of a 1x1 conv, 2-8 k-blocks per tile) are bound by
+// their epilogue's global loads, which like a large L1: two stages leave ~70 KB more of the unified L1/shared memory to it.
+template <int BN, int SPLIT, bool CTA2 = false, int KIND = EPI_PLAIN>
 struct TcCfg {
     static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;            // weight rows this CTA stages (a pair shares the tile)
     static constexpr uint32_t B_TILE_BYTES = B_ROWS * TC_BK * 4;
     static constexpr uint32_t B_LO_BYTES = SPLIT == 1 ? B_TILE_BYTES : SPLIT == 3 ? B_TILE_BYTES / 2 : 0;
     static constexpr uint32_t STAGE_BYTES = A_TILE_BYTES * (SPLIT ? 2 : 1) + B_TILE_BYTES + B_LO_BYTES;
     static constexpr int STAGES_RAW = (192 * 1024) / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int STAGES_CAP = (KIND == EPI_JOIN && SPLIT == 2) ? 2 : 8;
+    static constexpr int STAGES = STAGES_RAW > STAGES_CAP ? STAGES_CAP : STAGES_RAW;
     static constexpr uint32_t TMEM_COLS = 2 * BN;          // two accumulator stages (128 or 256: powers of two)
     static constexpr uint32_t PRM_BYTES = 2 * 6 * BN * 4;   // per accumulator stage: bn[4][BN] + bias_t[BN] + bias_p[BN]
     static constexpr uint32_t TR_BYTES = TC_EPI_WARPS * 2048;   // per epilogue warp: 32 rows x 16 columns transpose slab
@@ -209,7 +212,7 @@ template <int BN, int SPLIT, int KIND, bool CTA2, int MODE = -1>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBlo, const TcGeom g, const EpiParams ep) {
-    using Cfg = TcCfg<BN, SPLIT, CTA2>;
+    using Cfg = TcCfg<BN, SPLIT, CTA2, KIND>;
     static_assert(!CTA2 || SPLIT != 0, "the CTA-pair kernel signals the leader from the split warps");
     const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
@@ -448,6 +451,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr int CH = (KIND == EPI_FWD_DUAL) ? BN / 2 : BN;      // channels per tile
         constexpr int NL = (KIND == EPI_JOIN) ? 4 : (KIND == EPI_MID) ? 2 : 1;     // tensors loaded per output element
         struct Loads { float4 v[NL][4]; };             // one slab's global loads: [tensor][row group]
+        struct Acc { float vt[16]; float vp[KIND == EPI_FWD_DUAL ? 16 : 1]; };   // one slab of the accumulator(s), row per lane
+        constexpr bool ACC_PREFETCH = KIND != EPI_JOIN;    // JOIN's 2 x 16 prefetched float4 loads leave no registers for it
         int it = 0;
         for (int tile = worker; tile < total_tiles; tile += nworkers, ++it) {
             const int a = it & 1;
@@ -498,6 +503,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (ep.g_res != nullptr) L.v[0][i] = *reinterpret_cast<const float4*>(ep.g_res + (size_t)mrow[i] * ep.C + c);
                     } else {
                         const size_t offs = (size_t)msav[i] * ep.C + c;
+                        // plain cached loads: L1 allocation merges the two 64-byte halves of a line that the two warps of a
+                        // lane quarter read (ld.global.cs / L1::no_allocate measured 35-50 % slower here)
                         L.v[0][i] = __ldg(reinterpret_cast<const float4*>(ep.o + offs));
                         L.v[1][i] = __ldg(reinterpret_cast<const float4*>(ep.xr + offs));
                         if (KIND == EPI_JOIN) {
@@ -508,15 +515,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             };
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
-            // ---- accumulator slab j -> epilogue math -> stores
-            auto process = [&](int j, const Loads& L) {
+            // ---- accumulator slab j (requested from TMEM one slab ahead) -> epilogue math -> stores
+            auto request_acc = [&](int j, Acc& V) {
+                tmem_ld16(tacc + j, V.vt);
+                if (KIND == EPI_FWD_DUAL) tmem_ld16(tacc + CH + j, V.vp);
+            };
+            auto process = [&](int j, const Loads& L, Acc& V, int jn, Acc& Vn) {
                 const int c = cbase + j + 4 * cgl;
-                float vt[16], vp[16];
-                tmem_ld16(tacc + j, vt);
-                if (KIND == EPI_FWD_DUAL) tmem_ld16(tacc + CH + j, vp);
+                float* vt = V.vt;
+                float* vp = V.vp;
                 // transpose the accumulator slab(s): row-per-lane -> channel-group-per-lane
                 float4 at[4], apv[4];
+                if (!ACC_PREFETCH) request_acc(j, V);
                 tmem_ld_wait(vt);
+                if (KIND == EPI_FWD_DUAL) tmem_ld_wait(vp);
+                if (ACC_PREFETCH && jn < CH) request_acc(jn, Vn);      // the next slab's TMEM read overlaps this slab's math
 #pragma unroll
                 for (int g4 = 0; g4 < 4; ++g4)
                     tbuf[lane * 4 + (g4 ^ ((lane >> 1) & 3))] = make_float4(vt[4 * g4], vt[4 * g4 + 1], vt[4 * g4 + 2], vt[4 * g4 + 3]);
@@ -528,7 +541,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 __syncwarp();
                 if (KIND == EPI_FWD_DUAL) {
-                    tmem_ld_wait(vp);
 #pragma unroll
                     for (int g4 = 0; g4 < 4; ++g4)
                         tbuf[lane * 4 + (g4 ^ ((lane >> 1) & 3))] = make_float4(vp[4 * g4], vp[4 * g4 + 1], vp[4 * g4 + 2], vp[4 * g4 + 3]);
@@ -611,18 +623,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             };
             // the first slab's loads go out before the accumulator is waited for; afterwards slab j+1 is always in flight
             Loads La, Lb;
+            Acc Va, Vb;
             const int j0 = half * 16;
             issue_loads(j0, La);
             asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");      // constants staged
             mbar_wait(tfull_bar(a), aph);
             tc_fence_after();
+            if (ACC_PREFETCH) request_acc(j0, Va);
 #pragma unroll 1
             for (int j = j0; j < CH; j += 64) {
                 const bool more1 = j + 32 < CH, more2 = j + 64 < CH;
                 if (more1) issue_loads(j + 32, Lb);
-                process(j, La);
+                process(j, La, Va, j + 32, ACC_PREFETCH ? Vb : Va);
                 if (more2) issue_loads(j + 64, La);
-                if (more1) process(j + 32, Lb);
+                if (more1) process(j + 32, Lb, ACC_PREFETCH ? Vb : Va, j + 64, Va);
             }
             tc_fence_before();
             __syncwarp();
@@ -676,7 +690,7 @@ bool conv_tc_available() { return true; }
 template <int BN, int SPLIT, int KIND, int MODE = -1>
 static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo, const TcGeom& g,
                               const EpiParams& ep, cudaStream_t st) {
-    using Cfg = TcCfg<BN, SPLIT, false>;
+    using Cfg = TcCfg<BN, SPLIT, false, KIND>;
     static bool attr = false;
     static int sms = 0;
     if (!attr) {
@@ -697,7 +711,7 @@ static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, co
 template <int BN, int SPLIT, int KIND>
 static cudaError_t launch_cfg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo, const TcGeom& g,
                                const EpiParams& ep, cudaStream_t st) {
-    using Cfg = TcCfg<BN, SPLIT, true>;
+    using Cfg = TcCfg<BN, SPLIT, true, KIND>;
     auto kern = conv_tc_kernel<BN, SPLIT, KIND, true>;
     static int max_clusters = -1;
     cudaLaunchConfig_t cfg;
