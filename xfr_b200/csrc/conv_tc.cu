@@ -196,14 +196,26 @@ struct TcCfg {
     static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;            // weight rows this CTA stages (a pair shares the tile)
     static constexpr uint32_t B_TILE_BYTES = B_ROWS * TC_BK * 4;
     static constexpr uint32_t B_LO_BYTES = SPLIT == 1 ? B_TILE_BYTES : SPLIT == 3 ? B_TILE_BYTES / 2 : 0;
-    static constexpr uint32_t STAGE_BYTES = A_TILE_BYTES * (SPLIT ? 2 : 1) + B_TILE_BYTES + B_LO_BYTES;
-    static constexpr int STAGES_RAW = (192 * 1024) / STAGE_BYTES;
-    static constexpr int STAGES_CAP = (KIND == EPI_JOIN && SPLIT == 2) ? 2 : 8;
-    static constexpr int STAGES = STAGES_RAW > STAGES_CAP ? STAGES_CAP : STAGES_RAW;
+    // Two independent rings: activations (raw + lo tile) and weights (hi + lo planes).  Activation tiles are unique to the
+    // CTA and partly come from HBM; weight tiles are re-read by every CTA and sit in L2 - so the activation ring gets the
+    // depth (FWD dual tiles: 3 + 2 where one coupled ring held 2; W+ dgrads: 4 + 2 instead of 3).  A CTA pair keeps one
+    // coupled ring (its leader learns that the peer's data landed from the peer's split warps).
+    static constexpr uint32_t A_BYTES = A_TILE_BYTES * (SPLIT ? 2 : 1);
+    static constexpr uint32_t B_BYTES = B_TILE_BYTES + B_LO_BYTES;
+    static constexpr uint32_t RING_BUDGET = 192 * 1024;
+    static constexpr bool SPLITRING = !CTA2;
+    static constexpr bool SHORT = (KIND == EPI_JOIN && SPLIT == 2);      // epilogue-bound: leave the memory to L1
+    static constexpr int COUPLED_RAW = RING_BUDGET / (A_BYTES + B_BYTES);
+    static constexpr int COUPLED = SHORT ? 2 : (COUPLED_RAW > 8 ? 8 : COUPLED_RAW);
+    static constexpr int NB_PICK = B_BYTES >= 32 * 1024 ? 2 : (B_BYTES >= 16 * 1024 ? 3 : 4);
+    static constexpr int NB = SPLITRING ? (SHORT ? 2 : NB_PICK) : COUPLED;
+    static constexpr int NA_RAW = (RING_BUDGET - NB * B_BYTES) / A_BYTES;
+    static constexpr int NA = SPLITRING ? (SHORT ? 2 : (NA_RAW > 6 ? 6 : NA_RAW)) : COUPLED;
+    static constexpr uint32_t RING_BYTES = NA * A_BYTES + NB * B_BYTES;
     static constexpr uint32_t TMEM_COLS = 2 * BN;          // two accumulator stages (128 or 256: powers of two)
     static constexpr uint32_t PRM_BYTES = 2 * 6 * BN * 4;   // per accumulator stage: bn[4][BN] + bias_t[BN] + bias_p[BN]
     static constexpr uint32_t TR_BYTES = TC_EPI_WARPS * 2048;   // per epilogue warp: 32 rows x 16 columns transpose slab
-    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + PRM_BYTES + TR_BYTES;
+    static constexpr uint32_t SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + PRM_BYTES + TR_BYTES;
 };
 
 // MODE: the ebp_subtree_mode id of the MID / JOIN hook chains as a compile-time constant (the chains are ~2x cheaper once
@@ -219,25 +231,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int worker = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // tile stream this CTA (pair) walks
     const int nworkers = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     constexpr bool SPLIT3 = SPLIT != 0;          // the activation tile is split into (hi, lo)
-    constexpr int STAGES = Cfg::STAGES;
+    constexpr int NA = Cfg::NA, NB = Cfg::NB;
+    constexpr bool SPLITRING = Cfg::SPLITRING;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     // barrier block lives after the stages
-    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    auto split_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-    auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + a); };
-    auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + 2 + a); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8 * (3 * STAGES + 4));
-    float* prm_s = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 256);   // [2][6][BN]
-    float4* tr_s = reinterpret_cast<float4*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 256 + Cfg::PRM_BYTES);
+    const uint32_t bar_base = smem_base + Cfg::RING_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };                       // activation ring (coupled ring: both)
+    auto empty_bar = [&](int s) { return bar_base + 8u * (NA + s); };
+    auto split_bar = [&](int s) { return bar_base + 8u * (2 * NA + s); };
+    auto fullb_bar = [&](int s) { return bar_base + 8u * (3 * NA + s); };            // weight ring
+    auto emptyb_bar = [&](int s) { return bar_base + 8u * (3 * NA + NB + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * NA + 2 * NB + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * NA + 2 * NB + 2 + a); };
+    static_assert(8 * (3 * NA + 2 * NB + 4) + 4 <= 256, "barrier block");
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + Cfg::RING_BYTES + 8 * (3 * NA + 2 * NB + 4));
+    float* prm_s = reinterpret_cast<float*>(smem_gen + Cfg::RING_BYTES + 256);   // [2][6][BN]
+    float4* tr_s = reinterpret_cast<float4*>(smem_gen + Cfg::RING_BYTES + 256 + Cfg::PRM_BYTES);
 
-    auto a_hi = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
-    auto a_lo = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + A_TILE_BYTES; };                       // split only
-    auto b_hi = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + (SPLIT3 ? 2 : 1) * A_TILE_BYTES; };
-    auto b_lo = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES; };   // SPLIT 1 / 3
+    auto a_hi = [&](int s) { return smem_base + s * Cfg::A_BYTES; };
+    auto a_lo = [&](int s) { return smem_base + s * Cfg::A_BYTES + A_TILE_BYTES; };                           // split only
+    auto b_hi = [&](int s) { return smem_base + NA * Cfg::A_BYTES + s * Cfg::B_BYTES; };
+    auto b_lo = [&](int s) { return smem_base + NA * Cfg::A_BYTES + s * Cfg::B_BYTES + Cfg::B_TILE_BYTES; };   // SPLIT 1 / 3
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = (CTA2 ? (g.n_m_tiles + 1) / 2 : g.n_m_tiles) * g.n_n_tiles;
@@ -246,10 +262,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         if (SPLIT == 3) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < NA; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
             mbar_init(split_bar(s), CTA2 ? 8 : 4);               // pair: the peer's split warps arrive here too (leader's copy)
+        }
+        for (int s = 0; s < NB; ++s) {
+            mbar_init(fullb_bar(s), 1);
+            mbar_init(emptyb_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
@@ -312,7 +332,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tile_coords(tile, m0, mvalid, n_img0, h0, ncol0);
                 for (int kb = 0; kb < g.num_k; ++kb) {
                     mbar_wait(empty_bar(s), ph ^ 1u);
-                    mbar_expect_tx(full_bar(s), g.a_bytes + Cfg::B_TILE_BYTES + Cfg::B_LO_BYTES);
+                    mbar_expect_tx(full_bar(s), g.a_bytes + (SPLITRING ? 0u : Cfg::B_BYTES));
                     int tap = kb / g.kchunks;
                     int c0 = (kb - tap * g.kchunks) * TC_BK;
                     if (g.a4d) {
@@ -321,12 +341,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     } else {
                         tma_load_2d(a_hi(s), &tmA, c0, m0, full_bar(s));
                     }
-                    const int brow = ncol0 + (CTA2 ? (int)rank * (BN / 2) : 0);        // pair: this CTA stages its half of the tile
-                    tma_load_2d(b_hi(s), &tmB, kb * TC_BK, brow, full_bar(s));
-                    if (SPLIT == 1) tma_load_2d(b_lo(s), &tmB, kb * TC_BK, g.b_rows + brow, full_bar(s));   // host-split lo plane
-                    if (SPLIT == 3)                                                                          // lo of the W half
-                        tma_load_2d(b_lo(s), &tmBlo, kb * TC_BK, g.b_rows + ncol0 + (CTA2 ? (int)rank * (BN / 4) : 0), full_bar(s));
-                    if (++s == STAGES) { s = 0; ph ^= 1u; }
+                    if (!SPLITRING) {                                                   // coupled ring (CTA pair)
+                        const int brow = ncol0 + (CTA2 ? (int)rank * (BN / 2) : 0);    // pair: this CTA stages its half of the tile
+                        tma_load_2d(b_hi(s), &tmB, kb * TC_BK, brow, full_bar(s));
+                        if (SPLIT == 1) tma_load_2d(b_lo(s), &tmB, kb * TC_BK, g.b_rows + brow, full_bar(s));
+                        if (SPLIT == 3)
+                            tma_load_2d(b_lo(s), &tmBlo, kb * TC_BK, g.b_rows + ncol0 + (CTA2 ? (int)rank * (BN / 4) : 0), full_bar(s));
+                    }
+                    if (++s == NA) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== TMA producer of the weight ring =====================
+        if (SPLITRING && lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = worker; tile < total_tiles; tile += nworkers) {
+                const int ncol0 = (tile % g.n_n_tiles) * BN;
+                for (int kb = 0; kb < g.num_k; ++kb) {
+                    mbar_wait(emptyb_bar(s), ph ^ 1u);
+                    mbar_expect_tx(fullb_bar(s), Cfg::B_BYTES);
+                    tma_load_2d(b_hi(s), &tmB, kb * TC_BK, ncol0, fullb_bar(s));
+                    if (SPLIT == 1) tma_load_2d(b_lo(s), &tmB, kb * TC_BK, g.b_rows + ncol0, fullb_bar(s));   // host-split lo plane
+                    if (SPLIT == 3) tma_load_2d(b_lo(s), &tmBlo, kb * TC_BK, g.b_rows + ncol0, fullb_bar(s));  // lo of the W half
+                    if (++s == NB) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -339,8 +378,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (CTA2) tc_mma_tf32_2(d, da, db, id, acc);
             else tc_mma_tf32(d, da, db, id, acc);
         };
-        int s = 0;
-        uint32_t ph = 0;
+        int s = 0, sb = 0;
+        uint32_t ph = 0, phb = 0;
         int it = 0;
         if (leader)
         for (int tile = worker; tile < total_tiles; tile += nworkers, ++it) {
@@ -359,8 +398,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (lane == 0) {
                     if (CTA2) mbar_wait_cluster(split_bar(s), ph);            // implies both CTAs' TMA data landed
                     else mbar_wait(full_bar(s), ph);
+                    if (SPLITRING) mbar_wait(fullb_bar(sb), phb);
                     tc_fence_after();
-                    const uint64_t dah = make_desc(a_hi(s)), dbh = make_desc(b_hi(s));
+                    const int bs = SPLITRING ? sb : s;
+                    const uint64_t dah = make_desc(a_hi(s)), dbh = make_desc(b_hi(bs));
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k) {
                         const uint64_t koff = (uint64_t)((k * 32) >> 4);
@@ -371,7 +412,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             mbar_wait(split_bar(s), ph);
                             tc_fence_after();
                         }
-                        const uint64_t dal = make_desc(a_lo(s)), dbl = make_desc(b_lo(s));
+                        const uint64_t dal = make_desc(a_lo(s)), dbl = make_desc(b_lo(bs));
 #pragma unroll
                         for (int k = 0; k < TC_BK / 8; ++k) {
                             const uint64_t koff = (uint64_t)((k * 32) >> 4);
@@ -384,12 +425,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tc_commit2(empty_bar(s));                // both CTAs' stage s
                         if (kb == g.num_k - 1) tc_commit2(tfull_bar(a));
                     } else {
-                        tc_commit(empty_bar(s));                 // smem stage reusable once these MMAs retire
+                        tc_commit(empty_bar(s));                 // smem stages reusable once these MMAs retire
+                        if (SPLITRING) tc_commit(emptyb_bar(sb));
                         if (kb == g.num_k - 1) tc_commit(tfull_bar(a));
                     }
                 }
                 __syncwarp();
-                if (++s == STAGES) { s = 0; ph ^= 1u; }
+                if (++s == NA) { s = 0; ph ^= 1u; }
+                if (++sb == NB) { sb = 0; phb ^= 1u; }
             }
         }
     }
@@ -404,8 +447,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int kb = 0; kb < g.num_k; ++kb) {
                     mbar_wait(full_bar(s), ph);
                     // only the activation tile is split here; the weight tile arrives as (hi, lo) planes split on the host
-                    float4* hi = reinterpret_cast<float4*>(smem_gen + s * Cfg::STAGE_BYTES);
-                    float4* lo = reinterpret_cast<float4*>(smem_gen + s * Cfg::STAGE_BYTES + A_TILE_BYTES);
+                    float4* hi = reinterpret_cast<float4*>(smem_gen + s * Cfg::A_BYTES);
+                    float4* lo = reinterpret_cast<float4*>(smem_gen + s * Cfg::A_BYTES + A_TILE_BYTES);
                     constexpr int NV = A_TILE_BYTES / 16;
 #pragma unroll 4
                     for (int i = t; i < NV; i += 128) {
@@ -428,7 +471,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (CTA2 && !leader) mbar_arrive_remote(split_bar(s), 0);     // the leader's MMA thread waits for both halves
                         else mbar_arrive(split_bar(s));
                     }
-                    if (++s == STAGES) { s = 0; ph ^= 1u; }
+                    if (++s == NA) { s = 0; ph ^= 1u; }
                 }
             }
         }
