@@ -67,6 +67,74 @@ class ClockSampler(threading.Thread):
         return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.rows[0][1]), 'reasons': reasons, 'samples': len(sm)}
 
 
+# DRAM bytes of one layer3 launch of each kernel family from `ncu --set full` (profiles/r1_ncu_full_{bwd,fwd}_g.csv)
+NCU_TRAFFIC = {'dgrad_join': 946e6, 'dgrad_mid': 127e6, 'conv_dual': 387e6}
+
+
+def kernel_families(eng, step_fn):
+    """One extra (untimed) step with CUDA events around every GEMM-backed launch: per kernel family the launch count,
+    average device time, algorithmic bytes / flops per launch and what that is of the HBM / tensor peak."""
+    be = eng.be
+    rec = []
+
+    def rows(t):
+        return t.numel() // t.shape[-1]
+
+    def meta(name, a):
+        if name == 'dgrad_join':      # y1, L, g_res, out, o3, xr3, bn3, res, hooks, mode, g_out, y3_out
+            M, K, C, Ms = rows(a[0]), a[0].shape[-1], a[10].shape[-1], rows(a[3])
+            return 4.0 * (3 * Ms * C + 3 * M * C + M * K), 2.0 * M * C * K * a[1].R ** 2
+        if name == 'dgrad_mid':       # y, L, o, xr, bn, mode, y_out
+            M, K, C, Ms = rows(a[0]), a[0].shape[-1], a[6].shape[-1], rows(a[2])
+            return 4.0 * (2 * Ms * C + M * C + M * K), 2.0 * M * C * K * a[1].R ** 2
+        if name == 'conv_dual':       # inp, L, o, xr, act, res
+            M, K, C = rows(a[0]), a[0].shape[-1], a[2].shape[-1]
+            return 4.0 * (M * K + 3 * M * C + (M * C if len(a) > 5 and a[5] is not None else 0)), 2.0 * 2 * M * C * K * a[1].R ** 2
+        return 0.0, 0.0
+    saved = {}
+    for name in ('dgrad_join', 'dgrad_mid', 'conv_dual'):
+        orig = getattr(be, name)
+        saved[name] = orig
+
+        def wrapped(*a, _orig=orig, _name=name, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _orig(*a, **k)
+            e1.record()
+            rec.append((_name, e0, e1) + meta(_name, a))
+        setattr(be, name, wrapped)
+    try:
+        step_fn(False)
+        torch.cuda.synchronize()
+    finally:
+        for name in saved:
+            delattr(be, name)
+    hbm, _ = measured_peaks()
+    tf32_peak = 0.5 * tensor_peak()
+    out = []
+    label = {'dgrad_join': 'W+ dgrad + JOIN hook chain (conv_tc_kernel<BN,2,JOIN>)', 'dgrad_mid': 'W+ dgrad + MID hook chain (conv_tc_kernel<BN,2,MID>)',
+             'conv_dual': 'forward dual conv: o, xr, act (conv_tc_kernel<BN,3,FWD_DUAL>)'}
+    passes = {'dgrad_join': 2.0, 'dgrad_mid': 2.0, 'conv_dual': 2.5}
+    for name in ('dgrad_join', 'dgrad_mid', 'conv_dual'):
+        rr = [r for r in rec if r[0] == name]
+        if not rr:
+            continue
+        t = sum(r[1].elapsed_time(r[2]) for r in rr) * 1e-3
+        by, fl = sum(r[3] for r in rr), sum(r[4] for r in rr)
+        out.append({'kernel': label[name], 'launches': len(rr), 'avg_us': 1e6 * t / len(rr),
+                    'alg_bytes_per_launch': by / len(rr), 'achieved_gbs': by / t / 1e9, 'hbm_frac': by / t / 1e9 / hbm,
+                    'useful_tflops': fl / t / 1e12, 'issued_tf32_tflops': passes[name] * fl / t / 1e12,
+                    'tf32_frac': passes[name] * fl / t / 1e12 / tf32_peak, 'ncu_dram_bytes_layer3_launch': NCU_TRAFFIC[name]})
+    return out
+
+
+def tensor_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return float(json.load(open(p)).get('bf16_tflops', 1650.0))
+    return 1650.0
+
+
 def cpu_port(n_triplets, threads):
     """The reference algorithm restated on the CPU (oracle port, torch CPU fp32), batch 1 like the reference."""
     from oracle import stresnet_oracle as O      # cpu_baseline leg only
@@ -225,6 +293,7 @@ def main():
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.summary()
+    families = kernel_families(eng, step_resident) if rank == 0 else []      # after the timed regions: events around launches
 
     if world > 1:
         lt = torch.tensor([float(launches), bwd_ms], device=dev)
@@ -249,10 +318,14 @@ def main():
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches),
         'clocks': clocks,
-        'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
+        'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                     'traffic': NCU_TRAFFIC['dgrad_join'],
+                     'traffic_note': 'DRAM read+write of one layer3 JOIN launch (ncu --set full, profiles/r1_ncu_full_bwd_g.csv); '
+                                     'its algorithmic bytes are 976e6',
                      'kernel': 'EBP backward sweep (conv_tc_kernel dgrad + fused hook epilogues, join/stem kernels)',
                      'peak_source': peak_src, 'bwd_ms_per_step': bwd_ms / args.steps,
-                     'tensor_tflops_whole_step': FLOP_PER_MAP * B * args.steps / (ms / 1e3) / 1e12 / 1.0},
+                     'tensor_tflops_whole_step': FLOP_PER_MAP * B * args.steps / (ms / 1e3) / 1e12 / 1.0,
+                     'kernels': families},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count()

@@ -178,6 +178,8 @@ int xfrb_saliency_post(const float* mwp, float* out, int B, int H, int W, float 
  *     0: a = x = relu(s0)   1: a = relu(bn(s0)), x = relu(relu(s0)*sp+tp)   2: a = x = relu(bn(s0))
  *     3: a = relu(s0), x = s1   4: a = relu(s0), x = relu(relu(bn(s1)) + relu(s2))   5: a = relu(s0), x = s1
  *     6: a = relu(s0), x = relu(s1) + relu(s2)   7: a = relu(s0), x = relu(s1)      (Light-CNN: resblock output / Split input)
+ *     8: a = relu(s0), x = relu(relu(s1)*sp + tp + s2)                              (VGGFace2 ResNet-50 block ReLU hook)
+ *   pre_scale_row >= 0: z *= bn[pre_scale_row][c] before the hook (the BatchNorm backward that precedes a BatchNorm hook);
  *   p = a*relu(z), replaced for gradient row `prior_row` by the prior (a full tensor `prior` [H*W*C], or the single element
  *   prior_elem = prior_val); P_out <- p; return value per `mode` (`affine`: Conv/Linear/AvgPool/BatchNorm kinds;
  *   relu_or_maxpool = 2 marks ReLU/MaxPool kinds for the 'norelu' rule whitebox.py:418-419, passed with mode 1);
@@ -185,7 +187,7 @@ int xfrb_saliency_post(const float* mwp, float* out, int B, int H, int W, float 
 int xfrb_hook(const float* z_in, int up, int zc, const float* z_in2, int k2, int c2, float pre_scale, const float* s0, int c0,
               const float* s1, const float* s2, int c2s, const float* bn, const float* prior, int prior_row, long long prior_elem,
               float prior_val, float* P_out, float* z_out, int recipe, int affine, int relu_or_maxpool, int mode, int post_mask,
-              int post_scale_row, int J, int N, int H, int W, int C, float eps, void* stream);
+              int post_scale_row, int pre_scale_row, int J, int N, int H, int W, int C, float eps, void* stream);
 /* seed[j,:] = Pn[j,:] @ W2[j % N]  (Pn [J,Ccls], W2 [N,Ccls,D]) */
 int xfrb_head_seed(const float* Pn, const float* W2, int Ccls, int D, int J, int N, float* seed, void* stream);
 /* Jacobian of F.normalize (resnet.py:250): gout = (gin - xn*<xn,gin>)/nrm, rows of length D <= 1024 */

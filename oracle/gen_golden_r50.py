@@ -83,6 +83,22 @@ def main():
         print(mode, 'cebp max %.6e argmax %d | tcebp max %.6e | ebp max %.6e argmax %d' % (
             G['cebp_%s_probe' % tag].max(), G['cebp_%s_probe' % tag].argmax(), G['tcebp20_%s_probe' % tag].max(),
             G['ebp_%s_probe' % tag].max(), G['ebp_%s_probe' % tag].argmax()))
+    # layerwise_ebp (whitebox.py:561-581) and weighted_subtree_ebp (647-737) on the real triplet, default mode
+    wb = Whitebox(Whitebox_resnet50_128(net))
+    wb.net.set_triplet_classifier(x_mate, x_non)
+    ks = (0, 3, 10, 45, 80, 120, 150, 155)
+    G['lw_k'] = np.array(ks)
+    wb.ebp(X['probe'], P0)
+    G['lw_el_idx'] = np.array([int(torch.argmax(wb.P[k].flatten())) for k in ks])
+    for k, e in zip(ks, G['lw_el_idx']):
+        G['lw_argmax_%d' % k] = wb.layerwise_ebp(X['probe'], k_layer=k, mode='argmax', mwp=True)
+        G['lw_el_%d' % k] = wb.layerwise_ebp(X['probe'], k_layer=k, mode='elementwise', k_element=int(e), mwp=True)
+    wbs = Whitebox(Whitebox_resnet50_128(net))
+    wbs.net.set_triplet_classifier(x_mate, x_non)
+    smap, P_img, P_sub, k_sub = wbs.weighted_subtree_ebp(X['probe'], 0, 1, topk=16, verbose=False, do_max_subtree=False,
+                                                         do_mated_similarity_gating=True, subtree_mode='affineonly_with_prior')
+    G['ws_smap'], G['ws_scores'], G['ws_k'], G['ws_first'] = smap, np.array(P_sub, dtype=np.float64), np.array(k_sub), P_img[-1]
+    print('weighted_subtree k', list(k_sub), 'scores', ['%.3g' % v for v in P_sub])
     out = os.path.join(ROOT, 'tests', 'golden', 'resnet50_128_real.npz')
     np.savez_compressed(out, **G)
     print('wrote', out, os.path.getsize(out) // 1024, 'KB')

@@ -228,7 +228,8 @@ class EmulBackend(object):
 
     # ------------------------------------------------------------ generic single-hook path
     def hook(self, z_in, z_out, shape, recipe, affine, mode, s0=None, s1=None, s2=None, bn=None, up=1, zc=None, z_in2=None, k2=1,
-             pre_scale=1.0, prior=None, P_out=None, relu_or_maxpool=0, post_mask=False, post_scale_row=-1, N=None):
+             pre_scale=1.0, prior=None, P_out=None, relu_or_maxpool=0, post_mask=False, post_scale_row=-1, N=None,
+             pre_scale_row=-1):
         """One _backward_ebp firing with optional prior / recording (reference whitebox.py:381-430); include/xfrb.h xfrb_hook."""
         J, H, W, C = shape
         z = torch.zeros(J, H, W, C)
@@ -238,6 +239,8 @@ class EmulBackend(object):
             c2 = z_in2.shape[-1]
             z[..., :c2] += z_in2.reshape(J, H // k2, W // k2, c2).repeat_interleave(k2, 1).repeat_interleave(k2, 2) / float(k2 * k2)
         z = z * pre_scale
+        if pre_scale_row >= 0:
+            z = z * bn[pre_scale_row]
 
         def src(t, width=C):
             if t is None:
@@ -261,6 +264,8 @@ class EmulBackend(object):
             a, x = relu(v0), relu(v1) + relu(v2)
         elif recipe == 7:
             a, x = relu(v0), relu(v1)
+        elif recipe == 8:
+            a, x = relu(v0), relu(relu(v1) * sp + tp + (v2 if v2 is not None else 0))
         else:
             a, x = relu(v0), v1
         if mode == 3:                                    # XFRB_MODE_NONE: true gradient, dA recording

@@ -104,3 +104,61 @@ def test_gpu_real_weights_real_triplet_vs_reference(impl):
     for k, (a, r) in report.items():
         assert a < 1e-4, (k, a)
         assert r < rel_tol, (k, r)
+
+
+@needs_weights
+@pytest.mark.parametrize('mode,tag', (('affineonly_with_prior', 'awp'), ('all', 'all')))
+def test_generic_sweep_emulation(mode, tag):
+    """The firing-by-firing sweep (xfr_b200.generic.R50Sweep) on the emulated kernel set: all 158 recorded MWPs and the
+    layerwise priors reproduce the reference (whitebox.py:561-581)."""
+    sd, G, X = R50
+    eng = Resnet50_128Engine(sd, EmulBackend())
+    x = X['probe'].permute(0, 2, 3, 1).contiguous()
+    W2 = torch.from_numpy(np.concatenate((G['enc_mate'], G['enc_nonmate']))).float().unsqueeze(0)
+    P1 = torch.zeros(1, 2)
+    P1[0, 0] = 1
+    eng.forward(x)
+    gs = eng.sweep()
+    P, names, P2 = gs.run(P1, W2, mode, record=True)
+    assert names == [str(k) for k in G['P_kinds']] and len(P) == 158
+    sums = np.array([float(p.double().sum()) for p in P[:-1]])
+    gsum = G['Psum_%s_probe' % tag][:-1]
+    assert np.max(np.abs(sums - gsum) / (np.abs(gsum) + 1e-30)) < 2e-5
+    assert rel_err(P2.sum(-1)[0].numpy(), G['ebp_mwp_%s_probe' % tag]) < 1e-5
+    if tag == 'awp':
+        Pm = [None if p is None else p.clone() for p in P]
+        ks = [int(k) for k in G['lw_k']]
+        priors = {k: (r, (Pm[k] * (Pm[k] == Pm[k].max())).reshape(-1).contiguous()) for r, k in enumerate(ks)}
+        _, _, P2 = gs.run(torch.zeros(len(ks), 2), W2, mode, priors=priors)
+        maps = P2.sum(-1).numpy()
+        for r, k in enumerate(ks):
+            assert rel_err(maps[r], G['lw_argmax_%d' % k]) < 2e-5, k
+        for k, e in zip(ks, G['lw_el_idx']):
+            ed = gs.elem_index(k, int(e), Pm[k].shape)
+            _, _, P2 = gs.run(torch.zeros(1, 2), W2, mode, priors={k: (0, ed, float(Pm[k].reshape(-1)[ed]))})
+            assert rel_err(P2.sum(-1)[0].numpy(), G['lw_el_%d' % k]) < 2e-5, k
+
+
+@needs_weights
+@pytest.mark.gpu
+def test_gpu_layerwise_and_weighted_subtree_vs_reference():
+    """layerwise_ebp / weighted_subtree_ebp of the ResNet-50-128d plugin on the real weights and triplet."""
+    from xfr_b200 import whitebox
+    sd, G, X = R50
+    dev = torch.device('cuda:0')
+    sdd = {k: v.to(dev) for k, v in sd.items()}
+    wb = whitebox.Whitebox(whitebox.Whitebox_resnet50_128(sdd))
+    x_mate, x_non = wb.net.encode(X['mate']), wb.net.encode(X['nonmate'])
+    wb.net.set_triplet_classifier(x_mate, x_non)
+    for k, e in zip(G['lw_k'], G['lw_el_idx']):
+        m = wb.layerwise_ebp(X['probe'], k_layer=int(k), mode='argmax', mwp=True)
+        assert rel_err(m, G['lw_argmax_%d' % k]) < 1e-2, k
+        m = wb.layerwise_ebp(X['probe'], k_layer=int(k), mode='elementwise', k_element=int(e), mwp=True)
+        assert rel_err(m, G['lw_el_%d' % k]) < 1e-2, k
+    assert len(wb.P) == 158 and [str(n) for n in wb.P_layername] == [str(n) for n in G['P_kinds']]
+    smap, P_img, P_sub, k_sub = wb.weighted_subtree_ebp(X['probe'], 0, 1, topk=16, verbose=False, do_max_subtree=False,
+                                                        do_mated_similarity_gating=True, subtree_mode='affineonly_with_prior')
+    assert [int(k) for k in k_sub] == [int(k) for k in G['ws_k']]
+    assert np.allclose(P_sub, G['ws_scores'], rtol=1e-2)
+    assert rel_err(P_img[-1], G['ws_first']) < 2e-2
+    assert np.abs(smap - G['ws_smap']).max() < 1e-4 and rel_err(smap, G['ws_smap']) < 5e-2

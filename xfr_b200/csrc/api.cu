@@ -242,14 +242,16 @@ int xfrb_bn_hook(const float* g, const float* o, const float* xr, const float* b
 int xfrb_hook(const float* z_in, int up, int zc, const float* z_in2, int k2, int c2, float pre_scale, const float* s0, int c0,
               const float* s1, const float* s2, int c2s, const float* bn, const float* prior, int prior_row, long long prior_elem,
               float prior_val, float* P_out, float* z_out, int recipe, int affine, int relu_or_maxpool, int mode, int post_mask,
-              int post_scale_row, int J, int N, int H, int W, int C, float eps, void* stream) {
-    if (up < 1 || k2 < 1 || recipe < 0 || recipe > 7) return finish("xfrb_hook", cudaErrorInvalidValue);
+              int post_scale_row, int pre_scale_row, int J, int N, int H, int W, int C, float eps, void* stream) {
+    if (up < 1 || k2 < 1 || recipe < 0 || recipe > 8 || ((post_scale_row >= 0 || pre_scale_row >= 0) && bn == nullptr))
+        return finish("xfrb_hook", cudaErrorInvalidValue);
     HookArgs a;
     a.z_in = z_in; a.up = up; a.zc = zc; a.z_in2 = z_in2; a.k2 = k2; a.c2 = c2; a.pre_scale = pre_scale;
     a.s0 = s0; a.s1 = s1; a.s2 = s2; a.c0 = c0; a.c2s = c2s; a.bn = bn; a.prior = prior; a.P_out = P_out; a.z_out = z_out;
     a.recipe = recipe; a.affine = affine; a.relu_or_maxpool = relu_or_maxpool; a.mode = mode; a.post_mask = post_mask;
     a.post_scale_row = post_scale_row; a.J = J; a.N = N; a.H = H; a.W = W; a.C = C; a.eps = eps;
     a.prior_row = prior_row; a.prior_elem = prior_elem; a.prior_val = prior_val;
+    a.pre_scale_row = pre_scale_row;
     return finish("xfrb_hook", launch_hook(a, (cudaStream_t)stream));
 }
 

@@ -188,6 +188,7 @@ struct HookArgs {
     int J, N, H, W, C;
     float eps;
     int prior_row; long long prior_elem; float prior_val;   // one-element prior (layerwise 'elementwise'); prior_row < 0: none
+    int pre_scale_row;                     // >= 0: z *= bn[pre_scale_row][c] before the hook (BatchNorm backward)
 };
 cudaError_t launch_hook(const HookArgs& a, cudaStream_t st);
 

@@ -547,6 +547,7 @@ cudaError_t launch_head_seed(const float* Pn, const float* W2, int C, int D, int
 //   5: a = relu(s0), x = s1                               (materialised pair, e.g. the Multiply hook)
 //   6: a = relu(s0), x = relu(s1) + relu(s2)              (Light-CNN resblock output: s0 = out + res, s1 = out, s2 = res)
 //   7: a = relu(s0), x = relu(s1)                         (Light-CNN Split hook: s0 = conv output, s1 = its positive twin)
+//   8: a = relu(s0), x = relu(relu(s1)*sp + tp + s2)      (VGGFace2 ResNet-50 block ReLU: s0 = out, s1 = o3, s2 = positive shortcut)
 __global__ void hook_kernel(HookArgs A, size_t total) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -567,6 +568,7 @@ __global__ void hook_kernel(HookArgs A, size_t total) {
         z = __fadd_rn(z, __fdiv_rn(A.z_in2[(((size_t)j * Hr + h / A.k2) * Wr + w / A.k2) * A.c2 + c], (float)(A.k2 * A.k2)));
     }
     z = __fmul_rn(z, A.pre_scale);
+    if (A.pre_scale_row >= 0) z = __fmul_rn(z, A.bn[A.pre_scale_row * A.C + c]);        // BatchNorm backward ahead of its hook
     float a = 0.f, x = 0.f;
     BnC b = {0.f, 0.f, 0.f, 0.f};
     if (A.bn != nullptr) b = {A.bn[c], A.bn[A.C + c], A.bn[2 * A.C + c], A.bn[3 * A.C + c]};
@@ -584,6 +586,12 @@ __global__ void hook_kernel(HookArgs A, size_t total) {
         }
         case 6: a = fmaxf(v0, 0.f); x = __fadd_rn(fmaxf(A.s1[ms * A.C + c], 0.f), fmaxf(A.s2[ms * A.C + c], 0.f)); break;
         case 7: a = fmaxf(v0, 0.f); x = fmaxf(A.s1[ms * A.C + c], 0.f); break;
+        case 8: {
+            a = fmaxf(v0, 0.f);
+            const float r = (A.s2 != nullptr && c < A.c2s) ? A.s2[ms * A.c2s + c] : 0.f;
+            x = fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(fmaxf(A.s1[ms * A.C + c], 0.f), b.sp), b.tp), r), 0.f);
+            break;
+        }
         default: a = fmaxf(v0, 0.f); x = A.s1[ms * A.C + c]; break;
     }
     const size_t off = i;

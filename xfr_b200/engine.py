@@ -342,6 +342,14 @@ class Resnet50_128Engine(_Engine):
         self.saved = S
         return S['enc']
 
+    def sweep(self):
+        from .generic import R50Sweep
+        return R50Sweep(self)
+
+    def logits(self, W2):
+        """classify() for probe 0 (whitebox.py:226-230): fc1(net(x)[0]) with the wrapper's un-hooked rows"""
+        return self.saved['enc'][0:1] @ W2[0].t()
+
     def _xres(self, i, m):
         """Positive-pass value of block i's shortcut operand (only read in mode 'all'): identity blocks -> the block
         input; projection blocks -> BN+(relu(op))."""

@@ -159,3 +159,88 @@ class GenericSweep(object):
         self.be.hook(z_in, z_out, shape, recipe, affine, self._m, prior=self._priors.get(k), P_out=P_out,
                      relu_or_maxpool=flag, N=self.eng.saved['N'], **kw)
         return z_out
+
+
+class R50Sweep(GenericSweep):
+    """The same firing-by-firing sweep for the VGGFace2 ResNet-50-128d (reference resnet50_128.py, plugin whitebox.py:210-258):
+    158 firings in triplet mode.  Differences from the STR net: the residual sum is a function (no Add
+    hooks; the block ReLU's X sums positive-pass values), projection shortcuts are conv + BatchNorm whose hook fires before
+    the main path's, un-hooked fc1 head on the wrapper, 1x1 feat_extract conv after the 7x7 average pool."""
+
+    def run(self, Pn, W2, mode, priors=None, record=False, true_grad=False, hooked_fc2=False):
+        assert not hooked_fc2, 'the VGGFace2 plugin has no hooked classifier (whitebox.py:216)'
+        eng, be, S = self.eng, self.be, self.eng.saved
+        N, J = S['N'], Pn.shape[0]
+        self._k = 0
+        self._P = [] if record else None
+        self._names = []
+        self._priors = priors or {}
+        self._norelu = (mode == 'norelu')
+        m = MODE_NONE if true_grad else MODE_IDS[mode]
+        self._m = m
+        srow = 0 if true_grad else 2                     # BatchNorm backward: gamma/sigma (true) or gamma+/sigma
+        need_x = (not true_grad) and mode in ('all', 'norelu')
+        buf, head = eng.buf, eng.head
+        D, C = head.dim, head.cin
+
+        def dgrad(y, L, out, accumulate=False):
+            be.dgrad_plain(y, L, out, signed=true_grad, accumulate=accumulate)
+            return out
+
+        seed = buf('gs_seed', J, 1, 1, D)
+        be.head_seed(Pn, W2, seed.view(J, D))
+        fe = _FC(head.BfeT_signed() if true_grad else head.BfeT, C)
+        z = dgrad(seed, fe, buf('gs_fe', J, 1, 1, C))
+        z = self.fire('Conv2d', 0, z, (J, 1, 1, C), s0=S['v'], out='gs_lin')            # feat_extract input: x = a = avgpool7(out)
+        nb = len(eng.blocks)
+        zin, zin_up, zin2, k2 = None, 1, z, 7                                            # AvgPool2d(7) backward rides on the next firing
+        for i in range(nb - 1, -1, -1):
+            b, t = eng.blocks[i], S[i]
+            h, Co = b.hw, b.cout
+            shp = (J, h, h, Co)
+            nxt = eng.blocks[i + 1] if i + 1 < nb else None
+            xres = eng._xres(i, MODE_IDS['all']) if need_x else t['u']      # positive-pass shortcut (only X of the ReLU hook reads it)
+            if b.proj and not need_x:
+                xres = None
+            z = self.fire('ReLU', 8, zin, shp, s0=t['out'], s1=t['o3'], s2=xres, bn=b.c3.bn, up=zin_up, z_in2=zin2, k2=k2, out='gs_a')
+            if nxt is None:
+                g = self.fire('AvgPool2d', 0, z, shp, s0=t['out'], post_mask=True, out='gs_g%d' % (i % 2))
+            elif nxt.proj:
+                z = self.fire('Conv2d', 0, z, shp, s0=t['out'], out='gs_b')
+                g = self.fire('Conv2d', 0, z, shp, s0=t['out'], post_mask=True, out='gs_g%d' % (i % 2))
+            else:
+                g = self.fire('Conv2d', 0, z, shp, s0=t['out'], post_mask=True, out='gs_g%d' % (i % 2))
+            zlo = buf('gs_zlo', J, h, h, b.cin)
+            if b.proj:       # proj_bn's hook fires before the main path's (it was created later: autograd order)
+                yp = self.fire('BatchNorm2d', 3, g, shp, s0=t['op'], s1=t['xrp'], bn=b.cp.bn, pre_scale_row=srow, out='gs_yp')
+                dgrad(yp, b.cp, zlo)
+            y3 = self.fire('BatchNorm2d', 3, g, shp, s0=t['o3'], s1=t['xr3'], bn=b.c3.bn, pre_scale_row=srow, out='gs_y3')
+            z = dgrad(y3, b.c3, buf('gs_z2', J, h, h, b.planes))
+            shp2 = (J, h, h, b.planes)
+            z = self.fire('ReLU', 1, z, shp2, s0=t['o2'], bn=b.c2.bn, out='gs_c')
+            z = self.fire('Conv2d', 2, z, shp2, s0=t['o2'], bn=b.c2.bn, post_mask=True, post_scale_row=srow, out='gs_d')
+            y2 = self.fire('BatchNorm2d', 3, z, shp2, s0=t['o2'], s1=t['xr2'], out='gs_y2')
+            z = dgrad(y2, b.c2, buf('gs_z1', J, h, h, b.planes))
+            z = self.fire('ReLU', 1, z, shp2, s0=t['o1'], bn=b.c1.bn, out='gs_c')
+            z = self.fire('Conv2d', 2, z, shp2, s0=t['o1'], bn=b.c1.bn, post_mask=True, post_scale_row=srow, out='gs_d')
+            y1 = self.fire('BatchNorm2d', 3, z, shp2, s0=t['o1'], s1=t['xr1'], out='gs_y1')
+            dgrad(y1, b.c1, zlo, accumulate=b.proj)
+            if b.proj:
+                zin, zin_up, zin2, k2 = zlo, b.stride, None, 1          # both dgrads landed on the (sub-sampled) block input
+            else:
+                zin, zin_up, zin2, k2 = zlo, 1, g, 1                    # identity shortcut: the block-output gradient itself
+        # ---- stem: conv2_1's reduce and proj Conv2d hooks on the max-pool output, then as the STR net (pool pad 0, ceil)
+        shp = (J, 56, 56, 64)
+        z = self.fire('Conv2d', 0, zin, shp, s0=S['mp'], up=zin_up, z_in2=zin2, k2=k2, out='gs_a')
+        z = self.fire('Conv2d', 0, z, shp, s0=S['mp'], out='gs_b')
+        zz = buf('gs_mp', J, 112, 112, 64)
+        be.maxpool_bwd(z, S['o_s'], eng.stem.bn, zz, eng.stem.pool_pad)
+        shp = (J, 112, 112, 64)
+        z = self.fire('ReLU', 1, zz, shp, s0=S['o_s'], bn=eng.stem.bn, out='gs_s1')
+        z = self.fire('MaxPool2d', 2, z, shp, s0=S['o_s'], bn=eng.stem.bn, post_mask=True, post_scale_row=srow, out='gs_s2')
+        P2 = buf('gs_P2', *shp)
+        self.fire('BatchNorm2d', 3, z, shp, s0=S['o_s'], s1=S['o_s'], out=None, P_force=P2)
+        if self._P is not None:
+            self._P.append(None)
+        self._names.append('Conv2d')
+        return self._P, self._names, P2

@@ -195,6 +195,13 @@ class LinearHead(object):
         W = w.reshape(self.dim, self.cin)
         self.Bfe = gemm_planes(W, impl)                                   # [D][C]
         self.BfeT = gemm_planes(torch.clamp_min(W, 0).t(), impl)          # [C][D]: relu(W)^T, the dgrad operand
+        self._W, self._impl, self._BfeT_signed = W, impl, None
+
+    def BfeT_signed(self):
+        """[C][D] signed feat_extract^T: the dgrad operand of the true-gradient sweeps (weighted_subtree_ebp)."""
+        if self._BfeT_signed is None:
+            self._BfeT_signed = gemm_planes(self._W.t(), self._impl).to(self.BfeT.device)
+        return self._BfeT_signed
 
     def to(self, device):
         self.Bfe, self.BfeT = self.Bfe.to(device), self.BfeT.to(device)
