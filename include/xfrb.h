@@ -112,7 +112,9 @@ int xfrb_dgrad_plain(const float* y, const float* Bd, float* z_out,
  * output `out` (ReLU; Conv2d; then `hooks & 3`: 1 none, 2 Add(non-affine), 3 a second affine hook; `hooks & 4`: the
  * residual sum is torch.add, not a module - no Add hook, other X for the block ReLU: VGGFace2 ResNet-50),
  * ReLU backward -> g_out; then Add slot-0 hook (residual's (A,X): the late-binding closure of
- * whitebox.py:379-432), BatchNorm backward, BatchNorm hook -> y3_out.  All [.,H,W,C], C = Cin. */
+ * whitebox.py:379-432), BatchNorm backward, BatchNorm hook -> y3_out.  All [.,H,W,C], C = Cin.
+ * Bits 8-10 of `hooks` are profiling switches of the tcgen05 epilogue (1: no global loads, 2: no stores, 4: no hook math;
+ * tools/epi_probe.py) and must be 0 in production calls. */
 int xfrb_dgrad_join(const float* y1, const float* Bd, const float* g_res,
                     const float* out, const float* o3, const float* xr3, const float* bn3,
                     const float* res, int res_c, float* g_out, float* y3_out,

@@ -29,7 +29,7 @@ def test_vs_reference(impl, mode, tag):
     x, W2 = x.to(dev), W2.to(dev)
     fc = eng.forward(imgs.permute(0, 2, 3, 1).contiguous().to(dev))
     # tcgen05 accumulates fp32 with round-toward-zero: K/8 accumulation steps per pass shrink every sum by ~3e-8 each
-    # (tools_bias_probe.py: -7.7e-6 at K = 512), a uniform scale over 29 layers that the normalised maps do not see
+    # (tools/bias_probe.py: -7.7e-6 at K = 512), a uniform scale over 29 layers that the normalised maps do not see
     assert rel_err(fc[1:2].cpu().numpy(), G['enc_mate']) < (1e-4 if impl == 'fp32' else 3e-4)
     P1 = torch.zeros(2, 2, device=dev)
     P1[:, 0] = 1

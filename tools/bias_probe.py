@@ -1,6 +1,6 @@
 """GPU probe: signed mean relative error of the split-TF32 GEMM plans on all-positive operands (bias detector)."""
 import sys, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from xfr_b200.kernels import CudaBackend
 from xfr_b200.packing import gemm_planes
 g = torch.Generator().manual_seed(0)

@@ -1,7 +1,7 @@
 """GPU probe: time the fused dgrad + JOIN epilogue kernel at the ResNet-101 layer3 shape with parts of the epilogue
 switched off (debug bits in `hooks` >> 8: 1 no global loads, 2 no stores, 4 no hook math)."""
 import sys, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from xfr_b200.kernels import CudaBackend
 from xfr_b200.packing import gemm_planes
 be = CudaBackend('cuda:0', impl='tf32x3')

@@ -1,6 +1,6 @@
 """Scratch timing helper for gpurun sessions (not the contract bench)."""
 import sys, time, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from xfr_b200 import synth
 from xfr_b200.engine import StResnetEngine
 from xfr_b200.kernels import CudaBackend

@@ -1,5 +1,5 @@
 import sys, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from xfr_b200.kernels import CudaBackend
 be = CudaBackend('cuda:0', impl='tf32')
 vals = [1 + 2**-11, 1 + 2**-11 + 2**-20, 1 + 2**-12, 1 + 2**-10 - 2**-22, -(1 + 2**-11), -(1 + 2**-11 + 2**-20), 1 + 3 * 2**-11, 1 + 3*2**-11 - 2**-21]

@@ -204,9 +204,7 @@ int xfrb_dgrad_join(const float* y1, const float* Bd, const float* g_res, const 
     ep.mode = mode; ep.hooks = hooks; ep.eps = eps;
     ep.bn = bn3; ep.o = o3; ep.xr = xr3; ep.outp = out; ep.g_res = g_res; ep.res = res; ep.res_c = res_c;
     ep.out0 = g_out; ep.out1 = y3_out;
-    static int tn_cap = -1;
-    if (tn_cap < 0) { const char* e = getenv("XFRB_JOIN_BN"); tn_cap = e ? atoi(e) : 0; }
-    return finish("xfrb_dgrad_join", run_gemm(y1, Bd, g, ep, impl, (cudaStream_t)stream, tn_cap));
+    return finish("xfrb_dgrad_join", run_gemm(y1, Bd, g, ep, impl, (cudaStream_t)stream));
 }
 
 int xfrb_join(const float* zmain, int up, const float* gres_lo, int gres_c, int k, const float* out, const float* o3,

@@ -219,7 +219,7 @@ struct TcCfg {
 };
 
 // MODE: the ebp_subtree_mode id of the MID / JOIN hook chains as a compile-time constant (the chains are ~2x cheaper once
-// the mode branches fold away: tools_epi_probe.py), or -1 to read it from EpiParams at run time.
+// the mode branches fold away: tools/epi_probe.py), or -1 to read it from EpiParams at run time.
 template <int BN, int SPLIT, int KIND, bool CTA2, int MODE = -1>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -452,7 +452,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     constexpr int NV = A_TILE_BYTES / 16;
 #pragma unroll 4
                     for (int i = t; i < NV; i += 128) {
-                        // tcgen05 kind::tf32 reads only the top 19 bits of an fp32 operand (measured: tools_trunc_probe.py), so
+                        // tcgen05 kind::tf32 reads only the top 19 bits of an fp32 operand (measured: tools/trunc_probe.py), so
                         // the raw tile IS the hi operand, hi = trunc(x).  x - trunc(x) is exact in fp32 but carries up to 13
                         // significant bits: it is rounded to nearest TF32 here so that the hardware truncation of the lo
                         // operand loses nothing more and the residual (<= 2^-21 |x|) stays unbiased.
@@ -531,7 +531,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             // ---- every global load of slab j (issued one slab ahead of its use)
             const int mode = MODE >= 0 ? MODE : ep.mode;
-            const int dbg = ep.hooks >> 8;              // profiling switches (tools_epi_probe.py): 1 no loads, 2 no stores, 4 no math
+            const int dbg = ep.hooks >> 8;              // profiling switches (tools/epi_probe.py): 1 no loads, 2 no stores, 4 no math
             auto issue_loads = [&](int j, Loads& L) {
                 const int c = cbase + j + 4 * cgl;
                 const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);

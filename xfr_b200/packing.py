@@ -44,9 +44,6 @@ def gemm_planes(B, impl):
 
 def dual_tile_width(cout, impl):
     """Tile width of the forward dual pack: the tcgen05 kernel runs N = 256 tiles when the layer is wide enough."""
-    import os
-    if os.environ.get('XFRB_DUAL_TN') == '128':         # experiment switch
-        return 128
     return 256 if (impl != 'fp32' and cout % 128 == 0) else 128
 
 
