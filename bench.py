@@ -104,7 +104,7 @@ def kernel_families(eng, step_fn):
             rec.append((_name, e0, e1) + meta(_name, a))
         setattr(be, name, wrapped)
     try:
-        step_fn(False)
+        step_fn(False, gather=False)          # rank 0 only: no collective in here
         torch.cuda.synchronize()
     finally:
         for name in saved:
@@ -240,7 +240,7 @@ def main():
     ev = lambda: torch.cuda.Event(enable_timing=True)
     bwd_events = []
 
-    def step_resident(record):
+    def step_resident(record, gather=True):
         for i in range(0, B, args.chunk):
             xs, ws = x_dev[i:i + args.chunk], W2[i:i + args.chunk].contiguous()
             n = xs.shape[0]
@@ -255,7 +255,7 @@ def main():
             mwp = eng.buf('cmwp', n, 112, 112)
             eng.be.contrast(P2, sums, n, mwp)
             eng.be.saliency_post(mwp, maps_dev[i:i + n])
-        if world > 1:
+        if world > 1 and gather:
             gather_maps(maps_dev, world * B, dst=0)          # the only collective on the data path (NCCL gather)
 
     def step_e2e():
