@@ -199,6 +199,29 @@ class Whitebox_resnet50_128(WhiteboxSTResnet):
         return torch.from_numpy(x.transpose(2, 0, 1).astype(np.float32)).unsqueeze(0)
 
 
+class Whitebox_senet50_256(Whitebox_resnet50_128):
+    """VGGFace2 SENet-50-256d plugin (reference whitebox.py:163-208).  Its squeeze-and-excitation gates are Sigmoid modules,
+    for which the reference's own EBP hooks raise ValueError ('... is a special case ... and is not yet supported',
+    whitebox.py:404-405, 413-414, 421-422): no excitation-backprop operator of the reference runs on this net, so there is
+    no hot path to accelerate.  The class exists so that code which names it imports; preprocess() is the reference's
+    (identical to the ResNet-50-128d plugin's, whitebox.py:185-208)."""
+
+    def __init__(self, net, impl='tf32x3'):
+        self.net = net
+        self._sd = {}
+        self._impl = impl
+        self._engine = None
+        self._W2 = None
+        self._ncls = 2
+
+    def engine(self, with_bias=False):
+        raise ValueError('Whitebox_senet50_256: Sigmoid layers are a special case of excitation backprop that the reference '
+                         'does not support either (whitebox.py:404); no EBP operator is available for this network')
+
+    def encode(self, x):
+        raise NotImplementedError('Whitebox_senet50_256.encode: the SENet forward is not part of the B200 hot path')
+
+
 class WhiteboxLightCNN(WhiteboxSTResnet):
     """Light-CNN-29v2 plugin (reference whitebox.py:113-159).  `net` is the reference's
     xfr.models.lightcnn.network_29layers_v2 module (lightcnn.py:216-275) or its state_dict.  The classifier is the
@@ -553,10 +576,45 @@ class Whitebox(nn.Module):
     def encode(self, x):
         return self.net.encode(x)
 
+    def convert_from_numpy(self, img):
+        """whitebox.py:787-806: float RGB image (HxWx3) in [0,1] or uint8 image -> network input tensor via net.preprocess.
+        The reference resamples to 224x224 with skimage.transform.resize (absent here, and the identity for the 224x224
+        images of the inpainting-game flow); other sizes go through PIL's bilinear resize."""
+        import PIL.Image
+        img = np.asarray(img)
+        if img.dtype == np.uint8:
+            img = img.astype(np.float32) / 255
+        if img.max() > 1 + 1e-6 and img.min() > 0 - 1e-6:
+            img = img / 255
+        if img.max() > 1 + 1e-6 or img.min() < 0 - 1e-6:
+            raise ValueError('convert_from_numpy: image range outside [0, 1] / [0, 255] (the reference drops into pdb here)')
+        im8 = (img * 255).astype(np.uint8)
+        pil = PIL.Image.fromarray(im8).convert('RGB')
+        if pil.size != (224, 224):
+            pil = pil.resize((224, 224), PIL.Image.BILINEAR)
+        return self.net.preprocess(pil)
+
+    def preprocess_loader(self, images, returnImageIndex=False, repeats=1):
+        """whitebox.py:808-824 for in-memory HxWx3 arrays: yields (displayable image, [C,H,W] tensor, file name = None).
+        (File lists / DataFrames go through xfr.utils.image_loader in the reference - host glue outside this package.)"""
+        for i, im in enumerate(images):
+            if not isinstance(im, np.ndarray):
+                raise NotImplementedError('preprocess_loader: only in-memory numpy images are handled here')
+            assert im.ndim == 3 and im.shape[2] == 3
+            imT = self.convert_from_numpy(im)
+            base = (im, imT[0]) + ((i,) if returnImageIndex else ()) + (None,)
+            if repeats == 1:
+                yield base
+            else:
+                for r in range(repeats):
+                    yield base + (r,)
+
     def embeddings(self, images, norm=True):
-        """whitebox.py:747-785 for tensors / arrays already in network format."""
+        """whitebox.py:747-785: tensors / arrays already in network format ([C,H,W]), or HxWx3 numpy images."""
         if isinstance(images[0], torch.Tensor):
             imagesT = torch.stack(list(images)) if not isinstance(images, torch.Tensor) else images
+        elif isinstance(images[0], np.ndarray) and images[0].ndim == 3 and images[0].shape[0] not in (1, 3):
+            imagesT = torch.stack([self.convert_from_numpy(im)[0] for im in images])
         else:
             imagesT = torch.stack([torch.from_numpy(np.asarray(im)).float() for im in images])
         embeds = self.encode(imagesT).detach().cpu().numpy()
