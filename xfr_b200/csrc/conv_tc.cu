@@ -55,7 +55,7 @@ constexpr uint32_t A_TILE_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 struct TcGeom {
     int a4d;            // 0: A is a 2-D [M, C] matrix (1x1 conv / linear); 1: 4-D NHWC box loads (3x3)
     int R, Cin, kchunks, num_k;
-    int H, W, bh, bimg, tiles_per_img, Nimg;
+    int H, W, bh, bimg, tiles_per_img, Nimg;    // 4-D box: bimg images x bh rows; tiles_per_img = row strips per image group
     int n_m_tiles, n_n_tiles;
     int b_rows;         // rows of one plane of B (the lo plane of the 3xTF32 split starts at row b_rows)
     int groups, tiles_per_group;   // gradient-row groups whose m-tiles are visited interleaved (1: natural order)
@@ -306,16 +306,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mvalid = min(TC_BM, ep.M - m0);
             n_img0 = 0;
             h0 = 0;
-        } else if (g.bimg > 1) {
-            n_img0 = mt * g.bimg;
-            h0 = 0;
-            m0 = n_img0 * g.H * g.W;
-            mvalid = min(g.bimg, g.Nimg - n_img0) * g.H * g.W;
         } else {
-            n_img0 = mt / g.tiles_per_img;
-            h0 = (mt - n_img0 * g.tiles_per_img) * g.bh;
+            // 4-D box: bimg images x bh image rows x W pixels; tile mt = (image group, row strip).  Rows of the tile are NOT
+            // contiguous in the [N*H*W, C] matrix when bimg > 1 and bh < H: the epilogue maps them one by one (row_of).
+            const int gi = mt / g.tiles_per_img;
+            n_img0 = gi * g.bimg;
+            h0 = (mt - gi * g.tiles_per_img) * g.bh;
             m0 = (n_img0 * g.H + h0) * g.W;
-            mvalid = min(g.bh, g.H - h0) * g.W;
+            mvalid = TC_BM;
         }
         if (phantom) mvalid = 0;
     };
@@ -525,8 +523,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int r = q * 32 + 8 * i + rsub;
-                vrow[i] = r < mvalid;
-                mrow[i] = m0 + r;
+                if (!g.a4d) {
+                    vrow[i] = r < mvalid;
+                    mrow[i] = m0 + r;
+                } else {                                   // row r of the box -> (image, image row, pixel)
+                    const int strip = g.bh * g.W;
+                    const int bi = r / strip, rem = r - bi * strip;
+                    const int hh = h0 + rem / g.W, img = n_img0 + bi;
+                    vrow[i] = mvalid > 0 && bi < g.bimg && img < g.Nimg && hh < g.H;
+                    mrow[i] = (img * g.H + hh) * g.W + (rem % g.W);
+                }
                 msav[i] = (KIND == EPI_MID || KIND == EPI_JOIN) ? mrow[i] % ep.Ms : mrow[i];
             }
             // ---- every global load of slab j (issued one slab ahead of its use)
@@ -840,20 +846,24 @@ cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, c
     } else {
         g.a4d = 1;
         if (cg.W > 128) return cudaErrorInvalidValue;
-        if (HW <= 64) {                         // several whole images per tile (7x7 maps)
-            g.bimg = TC_BM / HW;
-            g.bh = cg.H;
-            g.tiles_per_img = 1;
-            g.n_m_tiles = (g.Nimg + g.bimg - 1) / g.bimg;
-        } else {
-            g.bimg = 1;
-            g.bh = TC_BM / cg.W;
-            if (g.bh > cg.H) g.bh = cg.H;
-            // prefer a row count that divides H (no ragged last tile) when it costs nothing
-            for (int b = g.bh; b >= 1; --b)
-                if (cg.H % b == 0 && (cg.H / b) == (cg.H + g.bh - 1) / g.bh) { g.bh = b; break; }
-            g.tiles_per_img = (cg.H + g.bh - 1) / g.bh;
-            g.n_m_tiles = g.Nimg * g.tiles_per_img;
+        {
+            // Box = bimg images x bh image rows x W pixels <= 128 GEMM rows.  Pick the (bh, bimg) that wastes the fewest of
+            // the 128 rows, counting the ragged last strip and the ragged last image group: 14x14 maps go from 7 rows of one
+            // image (98 of 128 rows = 77 %) to 1 row of 9 images (126 rows, 97 %), 7x7 maps to 1 row of 18 images (93 %).
+            double best = -1.0;
+            int lim = TC_BM / cg.W;
+            if (lim > cg.H) lim = cg.H;
+            for (int bh = lim; bh >= 1; --bh) {         // ties keep the larger strip (more contiguous rows per image)
+                int bimg = TC_BM / (bh * cg.W);
+                if (bimg > g.Nimg) bimg = g.Nimg;
+                if (bimg > 256) bimg = 256;
+                if (bimg < 1) continue;
+                const int th = (cg.H + bh - 1) / bh, ng = (g.Nimg + bimg - 1) / bimg;
+                const double eff = ((double)cg.H / (th * bh)) * ((double)(bh * cg.W * bimg) / TC_BM) * ((double)g.Nimg / (ng * bimg));
+                if (eff > best + 1e-9) { best = eff; g.bh = bh; g.bimg = bimg; }
+            }
+            g.tiles_per_img = (cg.H + g.bh - 1) / g.bh;             // row strips per image group
+            g.n_m_tiles = ((g.Nimg + g.bimg - 1) / g.bimg) * g.tiles_per_img;
         }
         g.a_bytes = (uint32_t)(TC_BK * cg.W * g.bh * g.bimg * 4);
         cuuint64_t dims[4] = {(cuuint64_t)cg.Cin, (cuuint64_t)cg.W, (cuuint64_t)cg.H, (cuuint64_t)g.Nimg};
