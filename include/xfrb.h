@@ -52,6 +52,10 @@ int xfrb_impl_available(int impl);
 /* tcgen05 kernels as CTA pairs (cta_group::2, one 256-row tile per TPC) where a launch has enough tiles: off by default
  * (XFRB_CTA2=1 in the environment enables); returns the previous setting.  Results are bit-identical either way. */
 int xfrb_set_cta_pairs(int on);
+/* tcgen05 kernels as clusters of two CTAs that TMA-multicast the weight tiles to each other (half the weight traffic out of
+ * L2 per CTA; MMAs, TMEM and epilogue stay private): on by default where a launch has enough tiles (XFRB_MC=0 disables);
+ * returns the previous setting.  Results are bit-identical either way. */
+int xfrb_set_multicast_pairs(int on);
 
 /* ---- forward ("activation" + "positive_activation" passes, whitebox.py:490-493) ---- */
 

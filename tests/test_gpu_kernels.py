@@ -96,12 +96,17 @@ def test_cta_pairs_match_single_cta():
     x = synth.synthetic_probes(N, seed=31).permute(0, 2, 3, 1).contiguous().to(dev)
     g = torch.Generator().manual_seed(32)
     W2 = (torch.randn(N, 2, 512, generator=g) * 0.02).to(dev)
+    prev_mc = be.lib.xfrb_set_multicast_pairs(0)
     prev = be.lib.xfrb_set_cta_pairs(1)
     try:
         a = eng.contrastive(x, W2, saliency=False).clone()
         be.lib.xfrb_set_cta_pairs(0)
-        b = eng.contrastive(x, W2, saliency=False).clone()
+        b = eng.contrastive(x, W2, saliency=False).clone()               # single-CTA kernels
+        be.lib.xfrb_set_multicast_pairs(1)
+        c = eng.contrastive(x, W2, saliency=False).clone()               # multicast pairs (the default)
     finally:
         be.lib.xfrb_set_cta_pairs(prev)
+        be.lib.xfrb_set_multicast_pairs(prev_mc)
     assert torch.isfinite(a).all() and float(a.abs().max()) > 0
     assert torch.equal(a, b), float((a - b).abs().max() / b.abs().max())
+    assert torch.equal(c, b), float((c - b).abs().max() / b.abs().max())

@@ -89,6 +89,7 @@ int xfrb_impl_available(int impl) {
 }
 
 int xfrb_set_cta_pairs(int on) { return conv_tc_set_cta2(on); }
+int xfrb_set_multicast_pairs(int on) { return conv_tc_set_mc(on); }
 
 int xfrb_stem_fwd(const float* x, const float* W, const float* b, const float* bn, float* o, float* mp, unsigned char* mp_arg,
                   int N, int pool_pad, void* stream) {

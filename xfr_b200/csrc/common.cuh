@@ -205,6 +205,7 @@ struct JoinArgs {
 cudaError_t launch_conv_simt(const float* A, const float* B, const ConvGeom& g, const EpiParams& ep, cudaStream_t st);
 bool conv_tc_available();
 int conv_tc_set_cta2(int on);     // CTA-pair (cta_group::2) kernels on/off; returns the previous setting
+int conv_tc_set_mc(int on);       // multicast-pair kernels (shared weight loads) on/off; returns the previous setting
 // B: [planes][Nn][K] with the 3xTF32 (hi, lo) planes when split != 0 (pass plans 0-3: conv_tc.cu); tn: dual-pack tile
 // width (FWD_DUAL) or a cap on BN
 cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& g, const EpiParams& ep, int split, int tn,

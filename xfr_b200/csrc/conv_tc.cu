@@ -2,7 +2,7 @@
 //
 //   D[m, n] = sum_k A[m, k] * B[n, k]      A: NHWC activations (R x R taps, stride 1, zero pad), B: K-major weights
 //
-// One persistent CTA per SM, 512 threads in four warpgroups, warp-specialised (setmaxnreg moves the registers the
+// One persistent CTA per SM, 512 threads in four warpgroups (640 / five for the JOIN kernels), warp-specialised (setmaxnreg moves the registers the
 // producer warpgroups do not need to the epilogue warpgroups, whose loads are double-buffered in registers):
 //   warp 0      TMA producer   - cp.async.bulk.tensor loads of the A tile (128 pixel rows x 32 channels; for 3x3 convs a
 //                                4-D box (32ch, W, bh rows, bn images) shifted by the tap, out-of-bounds rows/columns
@@ -16,7 +16,13 @@
 //                                weights arrive pre-split from the host as two planes.  The issuer runs hi*hi as soon
 //                                as the TMA data lands and lo*hi (+ hi*lo) one k-block later, into the same accumulator.
 //
-// CTA2: the same kernel as a CTA PAIR (cluster of 2, tcgen05 cta_group::2).  One M = 256 x BN tile per pair: each CTA
+// PAIR = 2 (the product default): a cluster of two CTAs that work on two consecutive m-tiles of the SAME n-tile and share the
+//   weight traffic: each CTA's weight producer loads HALF of the weight tile and TMA-multicasts it into both CTAs' rings
+//   (the weight ring's empty barriers collect both CTAs' tcgen05.commit through a multicast commit).  Everything else -
+//   activation ring, split, MMA (cta_group::1, M = 128), TMEM, epilogue - stays private to the CTA.  Why: the weight tiles are
+//   2/3 of the L2 -> SM traffic (a 3x3 W+ dgrad launch moves 0.9 GB of activations and 1.8 GB of re-read weights at ~7.5 TB/s,
+//   which is what bounds the main loop), and the remote signalling sits on the EMPTY path, which has the ring depth as slack.
+// PAIR = 1 / CTA2: the same kernel as a CTA PAIR (cluster of 2, tcgen05 cta_group::2).  One M = 256 x BN tile per pair: each CTA
 //   loads and splits its own 128 activation rows and HALF of the weight tile (BN/2 rows); the leader CTA issues
 //   tcgen05.mma.cta_group::2, whose tensor cores read each CTA's own A and both B halves, so the shared-memory operand
 //   traffic per SM per MMA drops from A + B to A + B/2 (the 3xTF32 main loop is shared-memory-bandwidth bound,
@@ -30,7 +36,7 @@
 //      product with relu(W) rounded to TF32; the lo weight plane is never loaded.  Using the same rounded W+ for the X of
 //      the forward twin and for the dgrad keeps excitation backprop mass-conserving.
 //   3  dual forward pack [W rows | relu(W) rows]: A_hi*B_hi + A_lo*B_hi over the whole tile, A_hi*B_lo over the W half only
-//   warps 8-15  epilogue       - tcgen05.ld the accumulator (lane = pixel row), apply the fused EBP epilogue of
+//   warps 8-15 (8-19)  epilogue       - tcgen05.ld the accumulator (lane = pixel row), apply the fused EBP epilogue of
 //                                common.cuh against the saved tensors, store NHWC fp32 with 128-bit accesses; the
 //                                global loads of slab j+1 are in flight while slab j is computed
 #include "common.cuh"
@@ -43,13 +49,8 @@ namespace xfrb {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                       // 32 fp32 = one 128-byte swizzle row
-constexpr int TC_EPI_WARPS = 8;                  // two warps per TMEM lane quarter, alternating 16-column chunks
-constexpr int TC_FIRST_SPLIT_WARP = 4;           // warpgroup 0: TMA, MMA, 2 idle; warpgroup 1: split; warpgroups 2-3: epilogue
-constexpr int TC_FIRST_EPI_WARP = 8;
-constexpr int TC_THREADS = (TC_FIRST_EPI_WARP + TC_EPI_WARPS) * 32;   // 512
-// register budget per role (setmaxnreg, whole warpgroups): 256 x 56 + 256 x 200 = 65536
-constexpr int TC_REGS_PRODUCER = 56;
-constexpr int TC_REGS_EPILOGUE = 200;
+constexpr int TC_FIRST_SPLIT_WARP = 4;           // warpgroup 0: TMA (activations), MMA, TMA (weights), idle; warpgroup 1: split
+constexpr int TC_FIRST_EPI_WARP = 8;             // warpgroups 2.. : epilogue (8 or 12 warps, TcCfg)
 constexpr uint32_t A_TILE_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 
 struct TcGeom {
@@ -129,6 +130,18 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         "}\n" ::"r"(bar), "r"(parity)
         : "memory");
 }
+// TMA load whose box lands at the same smem offset in every CTA of `mask` and signals each one's barrier at `bar`'s offset
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+        "l"(tm), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar) {    // cta_group::1 commit arriving on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
 __device__ __forceinline__ void tc_commit2(uint32_t bar) {      // arrives on `bar` in BOTH CTAs of the pair
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                  "h"((uint16_t)3)
@@ -191,9 +204,10 @@ __device__ __forceinline__ void tmem_ld_wait(float* v) {
 // ------------------------------------------------------------------ kernel
 // KIND only matters for the stage count: the JOIN kernels (K = Cout of a 1x1 conv, 2-8 k-blocks per tile) are bound by
 // their epilogue's global loads, which like a large L1: two stages leave ~70 KB more of the unified L1/shared memory to it.
-template <int BN, int SPLIT, bool CTA2 = false, int KIND = EPI_PLAIN>
+template <int BN, int SPLIT, int PAIR = 0, int KIND = EPI_PLAIN>
 struct TcCfg {
-    static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;            // weight rows this CTA stages (a pair shares the tile)
+    static constexpr bool CTA2 = PAIR == 1;
+    static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;            // weight rows this CTA stages (a cta_group::2 pair shares the tile)
     static constexpr uint32_t B_TILE_BYTES = B_ROWS * TC_BK * 4;
     static constexpr uint32_t B_LO_BYTES = SPLIT == 1 ? B_TILE_BYTES : SPLIT == 3 ? B_TILE_BYTES / 2 : 0;
     // Two independent rings: activations (raw + lo tile) and weights (hi + lo planes).  Activation tiles are unique to the
@@ -213,25 +227,45 @@ struct TcCfg {
     static constexpr int NA = SPLITRING ? (SHORT ? 2 : (NA_RAW > 6 ? 6 : NA_RAW)) : COUPLED;
     static constexpr uint32_t RING_BYTES = NA * A_BYTES + NB * B_BYTES;
     static constexpr uint32_t TMEM_COLS = 2 * BN;          // two accumulator stages (128 or 256: powers of two)
-    static constexpr uint32_t PRM_BYTES = 2 * 6 * BN * 4;   // per accumulator stage: bn[4][BN] + bias_t[BN] + bias_p[BN]
-    static constexpr uint32_t TR_BYTES = TC_EPI_WARPS * 2048;   // per epilogue warp: 32 rows x 16 columns transpose slab
+    // per-channel constants staged per accumulator stage: rows bn[0..3] (alpha, beta, sp, tp), bias_t, bias_p, PRM_LD wide
+    static constexpr int PRM_LD = KIND == EPI_FWD_DUAL ? BN / 2 : BN;
+    static constexpr int PRM_ROWS = KIND == EPI_FWD_DUAL ? 6 : (KIND == EPI_PLAIN ? 1 : 4);       // PLAIN: the bias row alone
+    static constexpr int BIAS_ROW = KIND == EPI_PLAIN ? 0 : 4;
+    static constexpr uint32_t PRM_BYTES = 2 * PRM_ROWS * PRM_LD * 4;
+    // Epilogue warps: two per TMEM lane quarter, or three for the JOIN kernels, whose epilogue (4 tensor reads, 2 writes, the
+    // longest hook chain) is what bounds them: 707 -> 615 us per launch with 12 warps; the others lose 6 % to the smaller
+    // register budget.  setmaxnreg moves registers between whole warpgroups inside the pool the CTA was LAUNCHED with
+    // (threads x the most __launch_bounds__ allows; asking for more blocks setmaxnreg.inc forever).
+    static constexpr int EPI_WARPS = KIND == EPI_JOIN ? 12 : 8;
+    static constexpr int THREADS = (TC_FIRST_EPI_WARP + EPI_WARPS) * 32;                  // 512 / 640
+    static constexpr int REGS_LAUNCH = (65536 / THREADS) / 8 * 8;                          // 128 / 96
+    static constexpr int REGS_PRODUCER = EPI_WARPS == 12 ? 48 : 56;
+    static constexpr int REGS_EPILOGUE = EPI_WARPS == 12 ? 128 : 200;
+    static_assert(TC_FIRST_EPI_WARP * 32 * REGS_PRODUCER + EPI_WARPS * 32 * REGS_EPILOGUE <= THREADS * REGS_LAUNCH,
+                  "setmaxnreg budgets exceed the CTA's register pool");
+    static constexpr uint32_t TR_BYTES = EPI_WARPS * 2048;      // per epilogue warp: 32 rows x 16 columns transpose slab
     static constexpr uint32_t SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + PRM_BYTES + TR_BYTES;
+    static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory a CTA can opt into");
 };
 
 // MODE: the ebp_subtree_mode id of the MID / JOIN hook chains as a compile-time constant (the chains are ~2x cheaper once
 // the mode branches fold away: tools/epi_probe.py), or -1 to read it from EpiParams at run time.
-template <int BN, int SPLIT, int KIND, bool CTA2, int MODE = -1>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int BN, int SPLIT, int KIND, int PAIR, int MODE = -1>
+__global__ void __launch_bounds__((TcCfg<BN, SPLIT, PAIR, KIND>::THREADS), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBlo, const TcGeom g, const EpiParams ep) {
-    using Cfg = TcCfg<BN, SPLIT, CTA2, KIND>;
+    using Cfg = TcCfg<BN, SPLIT, PAIR, KIND>;
+    constexpr bool CTA2 = PAIR == 1;             // cta_group::2 pair: one M = 256 MMA, the leader issues
+    constexpr bool MC = PAIR == 2;               // multicast pair: private M = 128 MMAs, shared weight loads
+    constexpr bool CLUSTERED = PAIR != 0;
     static_assert(!CTA2 || SPLIT != 0, "the CTA-pair kernel signals the leader from the split warps");
-    const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
-    const bool leader = rank == 0;
-    const int worker = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // tile stream this CTA (pair) walks
-    const int nworkers = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const uint32_t rank = CLUSTERED ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0 || MC;         // who issues MMAs: every CTA of a multicast pair
+    const int worker = CLUSTERED ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;     // tile stream this CTA (pair) walks
+    const int nworkers = CLUSTERED ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     constexpr bool SPLIT3 = SPLIT != 0;          // the activation tile is split into (hi, lo)
     constexpr int NA = Cfg::NA, NB = Cfg::NB;
+    constexpr int EW = Cfg::EPI_WARPS;
     constexpr bool SPLITRING = Cfg::SPLITRING;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -256,7 +290,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto b_lo = [&](int s) { return smem_base + NA * Cfg::A_BYTES + s * Cfg::B_BYTES + Cfg::B_TILE_BYTES; };   // SPLIT 1 / 3
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = (CTA2 ? (g.n_m_tiles + 1) / 2 : g.n_m_tiles) * g.n_n_tiles;
+    const int total_tiles = (CLUSTERED ? (g.n_m_tiles + 1) / 2 : g.n_m_tiles) * g.n_n_tiles;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -269,11 +303,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int s = 0; s < NB; ++s) {
             mbar_init(fullb_bar(s), 1);
-            mbar_init(emptyb_bar(s), 1);
+            mbar_init(emptyb_bar(s), MC ? 2 : 1);                // multicast pair: both CTAs' MMAs must have released the stage
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), CTA2 ? 2 * TC_EPI_WARPS : TC_EPI_WARPS);
+            mbar_init(tempty_bar(a), CTA2 ? 2 * EW : EW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -287,7 +321,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     }
     tc_fence_before();
-    if (CTA2) cluster_sync_all();       // both CTAs' barriers are initialised before any remote arrive / multicast commit
+    if (CLUSTERED) cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
@@ -295,7 +329,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // tile -> coordinates
     auto tile_coords = [&](int tile, int& m0, int& mvalid, int& n_img0, int& h0, int& ncol0) {
         int mt = tile / g.n_n_tiles, nt = tile - mt * g.n_n_tiles;
-        if (CTA2) mt = 2 * mt + (int)rank;             // the pair's tile is 256 rows: two consecutive m-tiles
+        if (CLUSTERED) mt = 2 * mt + (int)rank;        // the pair's tile is 256 rows: two consecutive m-tiles
         const bool phantom = mt >= g.n_m_tiles;        // odd tile count: the last pair's second half loads zeros, stores nothing
         // gradient-row groups (mate / non-mate rows of the same probes) read the same saved tensors: visit group 0's
         // tile i, then group 1's tile i, ... so the second read of a saved tile hits L2 instead of HBM
@@ -319,7 +353,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     };
 
     if (warp < TC_FIRST_SPLIT_WARP) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_PRODUCER));      // whole warpgroup 0
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_PRODUCER));      // whole warpgroup 0
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
@@ -358,11 +392,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int tile = worker; tile < total_tiles; tile += nworkers) {
                 const int ncol0 = (tile % g.n_n_tiles) * BN;
                 for (int kb = 0; kb < g.num_k; ++kb) {
-                    mbar_wait(emptyb_bar(s), ph ^ 1u);
-                    mbar_expect_tx(fullb_bar(s), Cfg::B_BYTES);
-                    tma_load_2d(b_hi(s), &tmB, kb * TC_BK, ncol0, fullb_bar(s));
-                    if (SPLIT == 1) tma_load_2d(b_lo(s), &tmB, kb * TC_BK, g.b_rows + ncol0, fullb_bar(s));   // host-split lo plane
-                    if (SPLIT == 3) tma_load_2d(b_lo(s), &tmBlo, kb * TC_BK, g.b_rows + ncol0, fullb_bar(s));  // lo of the W half
+                    if (MC) mbar_wait_cluster(emptyb_bar(s), ph ^ 1u);      // released by both CTAs (the peer writes into this stage too)
+                    else mbar_wait(emptyb_bar(s), ph ^ 1u);
+                    mbar_expect_tx(fullb_bar(s), Cfg::B_BYTES);             // both halves land here: mine and the peer's multicast
+                    if (MC) {
+                        // my half of every plane, multicast into both CTAs at the half's own offset
+                        constexpr uint32_t HALF = Cfg::B_TILE_BYTES / 2;
+                        const int r0 = (int)rank * (BN / 2);
+                        tma_load_2d_mc(b_hi(s) + rank * HALF, &tmB, kb * TC_BK, ncol0 + r0, fullb_bar(s), 3);
+                        if (SPLIT == 1) tma_load_2d_mc(b_lo(s) + rank * HALF, &tmB, kb * TC_BK, g.b_rows + ncol0 + r0, fullb_bar(s), 3);
+                        if (SPLIT == 3)
+                            tma_load_2d_mc(b_lo(s) + rank * (HALF / 2), &tmBlo, kb * TC_BK, g.b_rows + ncol0 + (int)rank * (BN / 4), fullb_bar(s), 3);
+                    } else {
+                        tma_load_2d(b_hi(s), &tmB, kb * TC_BK, ncol0, fullb_bar(s));
+                        if (SPLIT == 1) tma_load_2d(b_lo(s), &tmB, kb * TC_BK, g.b_rows + ncol0, fullb_bar(s));   // host-split lo plane
+                        if (SPLIT == 3) tma_load_2d(b_lo(s), &tmBlo, kb * TC_BK, g.b_rows + ncol0, fullb_bar(s));  // lo of the W half
+                    }
                     if (++s == NB) { s = 0; ph ^= 1u; }
                 }
             }
@@ -424,7 +469,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (kb == g.num_k - 1) tc_commit2(tfull_bar(a));
                     } else {
                         tc_commit(empty_bar(s));                 // smem stages reusable once these MMAs retire
-                        if (SPLITRING) tc_commit(emptyb_bar(sb));
+                        if (SPLITRING) {
+                            if (MC) tc_commit_mc(emptyb_bar(sb));    // the peer's weight producer waits for this CTA too
+                            else tc_commit(emptyb_bar(sb));
+                        }
                         if (kb == g.num_k - 1) tc_commit(tfull_bar(a));
                     }
                 }
@@ -436,7 +484,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     } else if (warp < TC_FIRST_EPI_WARP) {
         // ===================== operand split (3xTF32) =====================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_PRODUCER));  // whole warpgroup 1
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_PRODUCER));  // whole warpgroup 1
         if (SPLIT3) {
             const int t = threadIdx.x - TC_FIRST_SPLIT_WARP * 32;    // 0..127
             int s = 0;
@@ -481,10 +529,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // access of the epilogue is then a 64-byte row segment per 4 lanes (8 rows per request instead of 32), and all
         // loads of a slab are issued before the accumulator is waited for.  The two warps of a TMEM lane quarter
         // alternate slabs; per-channel constants are staged in smem once per tile.
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPILOGUE));  // warpgroups 2 and 3
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_EPILOGUE));  // the epilogue warpgroups
         const int ew = warp - TC_FIRST_EPI_WARP;       // 0..7
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
-        const int half = ew >> 2;                      // which slabs of the tile this warp owns
+        const int part = ew >> 2;                      // which slabs of the tile this warp owns: part, part + 3, ...
         const int et = threadIdx.x - TC_FIRST_EPI_WARP * 32;   // 0..255
         const int cgl = lane & 3;                      // my 4-channel group inside the slab
         const int rsub = lane >> 2;                    // my row inside each group of 8 rows
@@ -493,7 +541,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr int NL = (KIND == EPI_JOIN) ? 4 : (KIND == EPI_MID) ? 2 : 1;     // tensors loaded per output element
         struct Loads { float4 v[NL][4]; };             // one slab's global loads: [tensor][row group]
         struct Acc { float vt[16]; float vp[KIND == EPI_FWD_DUAL ? 16 : 1]; };   // one slab of the accumulator(s), row per lane
-        constexpr bool ACC_PREFETCH = KIND != EPI_JOIN;    // JOIN's 2 x 16 prefetched float4 loads leave no registers for it
+        constexpr bool ACC_PREFETCH = false;               // TMEM slab prefetch measured +-0 and costs 16-32 registers of the 136
+        constexpr bool LOAD_AHEAD = KIND != EPI_JOIN;      // other kinds keep the next slab's global loads in flight
+        constexpr int SLAB_STRIDE = 16 * (EW / 4);         // columns between two slabs of the same warp
         int it = 0;
         for (int tile = worker; tile < total_tiles; tile += nworkers, ++it) {
             const int a = it & 1;
@@ -501,21 +551,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int m0, mvalid, n_img0, h0, ncol0;
             tile_coords(tile, m0, mvalid, n_img0, h0, ncol0);
             const int cbase = (KIND == EPI_FWD_DUAL) ? (ncol0 / BN) * (BN / 2) : ncol0;
-            float* prm = prm_s + a * 6 * BN;
+            constexpr int PLD = Cfg::PRM_LD;
+            float* prm = prm_s + a * Cfg::PRM_ROWS * PLD;
             // stage the per-channel constants of this tile: rows 0-3 bn (alpha, beta, sp, tp), 4 bias_t, 5 bias_p
             if (KIND != EPI_PLAIN) {
-                for (int i = et; i < 4 * CH; i += TC_EPI_WARPS * 32) {
+                for (int i = et; i < 4 * CH; i += EW * 32) {
                     int r = i / CH, j = i - r * CH;
-                    prm[r * BN + j] = __ldg(ep.bn + (size_t)r * ep.C + cbase + j);
+                    prm[r * PLD + j] = __ldg(ep.bn + (size_t)r * ep.C + cbase + j);
                 }
             }
             if (KIND == EPI_FWD_DUAL) {
-                for (int i = et; i < BN; i += TC_EPI_WARPS * 32) {
+                for (int i = et; i < BN; i += EW * 32) {
                     int r = i / CH, j = i - r * CH;            // r = 0: true bias, 1: positive twin
-                    prm[(4 + r) * BN + j] = __ldg(ep.bias + ncol0 + r * CH + j);
+                    prm[(4 + r) * PLD + j] = __ldg(ep.bias + ncol0 + r * CH + j);
                 }
             } else if (KIND == EPI_PLAIN) {
-                for (int i = et; i < BN; i += TC_EPI_WARPS * 32) prm[4 * BN + i] = ep.bias ? __ldg(ep.bias + ncol0 + i) : 0.f;
+                for (int i = et; i < BN; i += EW * 32) prm[Cfg::BIAS_ROW * PLD + i] = ep.bias ? __ldg(ep.bias + ncol0 + i) : 0.f;
             }
             // rows this thread finishes (coalesced orientation)
             int mrow[4], msav[4];
@@ -606,16 +657,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 BnC b[4];
                 float bt[4] = {0.f, 0.f, 0.f, 0.f}, bp[4] = {0.f, 0.f, 0.f, 0.f};
                 if (KIND != EPI_PLAIN) {
-                    const float4 al = *reinterpret_cast<const float4*>(prm + pj), be = *reinterpret_cast<const float4*>(prm + BN + pj);
-                    const float4 sp = *reinterpret_cast<const float4*>(prm + 2 * BN + pj), tp = *reinterpret_cast<const float4*>(prm + 3 * BN + pj);
+                    const float4 al = *reinterpret_cast<const float4*>(prm + pj), be = *reinterpret_cast<const float4*>(prm + PLD + pj);
+                    const float4 sp = *reinterpret_cast<const float4*>(prm + 2 * PLD + pj), tp = *reinterpret_cast<const float4*>(prm + 3 * PLD + pj);
                     b[0] = {al.x, be.x, sp.x, tp.x}; b[1] = {al.y, be.y, sp.y, tp.y}; b[2] = {al.z, be.z, sp.z, tp.z}; b[3] = {al.w, be.w, sp.w, tp.w};
                 }
                 if (KIND == EPI_PLAIN || KIND == EPI_FWD_DUAL) {
-                    const float4 t = *reinterpret_cast<const float4*>(prm + 4 * BN + pj);
+                    const float4 t = *reinterpret_cast<const float4*>(prm + Cfg::BIAS_ROW * PLD + pj);
                     bt[0] = t.x; bt[1] = t.y; bt[2] = t.z; bt[3] = t.w;
                 }
                 if (KIND == EPI_FWD_DUAL) {
-                    const float4 t = *reinterpret_cast<const float4*>(prm + 5 * BN + pj);
+                    const float4 t = *reinterpret_cast<const float4*>(prm + 5 * PLD + pj);
                     bp[0] = t.x; bp[1] = t.y; bp[2] = t.z; bp[3] = t.w;
                 }
 #pragma unroll
@@ -640,7 +691,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     } else if (KIND == EPI_MID) {
                         const float lb[4] = {L.v[NL > 1 ? 1 : 0][i].x, L.v[NL > 1 ? 1 : 0][i].y, L.v[NL > 1 ? 1 : 0][i].z, L.v[NL > 1 ? 1 : 0][i].w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) r0[e] = mid_chain(av[e], la[e], lb[e], b[e], mode, ep.eps);
+                        for (int e = 0; e < 4; ++e) r0[e] = (dbg & 4) ? av[e] + la[e] + lb[e] : mid_chain(av[e], la[e], lb[e], b[e], mode, ep.eps);
                     } else {
                         const float4 v1 = L.v[NL > 1 ? 1 : 0][i], v2 = L.v[NL > 2 ? 2 : 0][i], v3 = L.v[NL > 3 ? 3 : 0][i];
                         const float lb[4] = {v1.x, v1.y, v1.z, v1.w};
@@ -660,8 +711,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 join_chain(__fadd_rn(av[e], ld[e]), lc[e], la[e], lb[e], rr[e], b[e], ep.hooks & 255, mode, ep.eps, r0[e], r1[e]);
                         }
                     }
-                    if (dbg & 2) {
-                        if (r0[0] + r0[1] + r0[2] + r0[3] + r1[0] + r1[1] + r1[2] + r1[3] != 1.2345e-30f) continue;    // keep the math alive
+                    if (dbg & 2) {      // keep the math alive without storing
+                        float chk = r0[0] + r0[1] + r0[2] + r0[3];
+                        if (KIND == EPI_FWD_DUAL || KIND == EPI_JOIN) chk += r1[0] + r1[1] + r1[2] + r1[3];
+                        if (KIND == EPI_FWD_DUAL) chk += r2[0] + r2[1] + r2[2] + r2[3];
+                        if (chk != 1.2345e-30f) continue;
                     }
                     *reinterpret_cast<float4*>(ep.out0 + off) = make_float4(r0[0], r0[1], r0[2], r0[3]);
                     if (KIND == EPI_FWD_DUAL || KIND == EPI_JOIN)
@@ -673,19 +727,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // the first slab's loads go out before the accumulator is waited for; afterwards slab j+1 is always in flight
             Loads La, Lb;
             Acc Va, Vb;
-            const int j0 = half * 16;
-            issue_loads(j0, La);
-            asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");      // constants staged
+            const int j0 = part * 16;
+            if (LOAD_AHEAD && j0 < CH) issue_loads(j0, La);
+            asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");      // constants staged
             mbar_wait(tfull_bar(a), aph);
             tc_fence_after();
-            if (ACC_PREFETCH) request_acc(j0, Va);
+            if (LOAD_AHEAD) {
+                if (ACC_PREFETCH && j0 < CH) request_acc(j0, Va);
 #pragma unroll 1
-            for (int j = j0; j < CH; j += 64) {
-                const bool more1 = j + 32 < CH, more2 = j + 64 < CH;
-                if (more1) issue_loads(j + 32, Lb);
-                process(j, La, Va, j + 32, ACC_PREFETCH ? Vb : Va);
-                if (more2) issue_loads(j + 64, La);
-                if (more1) process(j + 32, Lb, ACC_PREFETCH ? Vb : Va, j + 64, Va);
+                for (int j = j0; j < CH; j += 2 * SLAB_STRIDE) {
+                    const bool more1 = j + SLAB_STRIDE < CH, more2 = j + 2 * SLAB_STRIDE < CH;
+                    if (more1) issue_loads(j + SLAB_STRIDE, Lb);
+                    process(j, La, Va, j + SLAB_STRIDE, ACC_PREFETCH ? Vb : Va);
+                    if (more2) issue_loads(j + 2 * SLAB_STRIDE, La);
+                    if (more1) process(j + SLAB_STRIDE, Lb, ACC_PREFETCH ? Vb : Va, j + 2 * SLAB_STRIDE, Va);
+                }
+            } else {
+#pragma unroll 1
+                for (int j = j0; j < CH; j += SLAB_STRIDE) {
+                    issue_loads(j, La);
+                    process(j, La, Va, CH, Va);
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -697,7 +759,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 
     tc_fence_before();
-    if (CTA2) cluster_sync_all();       // neither CTA may leave (or free TMEM) while its peer can still touch its smem / barriers
+    if (CLUSTERED) cluster_sync_all();  // neither CTA may leave (or free TMEM) while its peer can still touch its smem / barriers
     else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
@@ -739,11 +801,11 @@ bool conv_tc_available() { return true; }
 template <int BN, int SPLIT, int KIND, int MODE = -1>
 static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo, const TcGeom& g,
                               const EpiParams& ep, cudaStream_t st) {
-    using Cfg = TcCfg<BN, SPLIT, false, KIND>;
+    using Cfg = TcCfg<BN, SPLIT, 0, KIND>;
     static bool attr = false;
     static int sms = 0;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT, KIND, false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT, KIND, 0, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -752,16 +814,16 @@ static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, co
     }
     int total = g.n_m_tiles * g.n_n_tiles;
     int grid = total < sms ? total : sms;
-    conv_tc_kernel<BN, SPLIT, KIND, false, MODE><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmBlo, g, ep);
+    conv_tc_kernel<BN, SPLIT, KIND, 0, MODE><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmBlo, g, ep);
     return cudaGetLastError();
 }
 
-// CTA-pair launch: clusters of 2, one pair per TPC, persistent over the 256-row pair tiles.
-template <int BN, int SPLIT, int KIND>
+// CTA-pair launch (PAIR 1: cta_group::2, PAIR 2: multicast weights): clusters of 2, persistent over the 256-row pair tiles.
+template <int BN, int SPLIT, int KIND, int PAIR = 1, int MODE = -1>
 static cudaError_t launch_cfg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo, const TcGeom& g,
                                const EpiParams& ep, cudaStream_t st) {
-    using Cfg = TcCfg<BN, SPLIT, true, KIND>;
-    auto kern = conv_tc_kernel<BN, SPLIT, KIND, true>;
+    using Cfg = TcCfg<BN, SPLIT, PAIR, KIND>;
+    auto kern = conv_tc_kernel<BN, SPLIT, KIND, PAIR, MODE>;
     static int max_clusters = -1;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -770,7 +832,7 @@ static cudaError_t launch_cfg2(const CUtensorMap& tmA, const CUtensorMap& tmB, c
     at[0].val.clusterDim.x = 2;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
-    cfg.blockDim = dim3(TC_THREADS);
+    cfg.blockDim = dim3(Cfg::THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = st;
     cfg.attrs = at;
@@ -794,6 +856,19 @@ static cudaError_t launch_cfg2(const CUtensorMap& tmA, const CUtensorMap& tmB, c
     return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmBlo, g, ep);
 }
 
+static int g_mc = -1;        // multicast pairs: -1 from the environment (XFRB_MC=0 disables), else 0 / 1
+static bool mc_enabled() {
+    if (g_mc < 0) {
+        const char* e = getenv("XFRB_MC");
+        g_mc = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return g_mc != 0;
+}
+int conv_tc_set_mc(int on) {
+    int prev = mc_enabled() ? 1 : 0;
+    g_mc = on ? 1 : 0;
+    return prev;
+}
 static int g_cta2 = -1;      // -1: from the environment (XFRB_CTA2=1 enables), else 0 / 1
 static bool cta2_enabled() {
     if (g_cta2 < 0) {
@@ -808,8 +883,14 @@ int conv_tc_set_cta2(int on) {
     return prev;
 }
 
-cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, const EpiParams& ep, int split, int tn,
+cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, const EpiParams& ep_in, int split, int tn,
                            cudaStream_t st) {
+    EpiParams ep = ep_in;
+    {   // profiling switches for every epilogue kind (tools/epi_probe.py uses the `hooks` bits of xfrb_dgrad_join directly)
+        static int dbg_env = -1;
+        if (dbg_env < 0) { const char* e = getenv("XFRB_DBG"); dbg_env = e ? atoi(e) : 0; }
+        if (dbg_env) ep.hooks |= dbg_env << 8;
+    }
     if (cg.Cin % TC_BK != 0 || split < 0 || split > 3) return cudaErrorInvalidValue;
     if (split == 3 && ep.kind != EPI_FWD_DUAL) return cudaErrorInvalidValue;
     if (split == 2 && ep.kind == EPI_FWD_DUAL) return cudaErrorInvalidValue;
@@ -872,16 +953,22 @@ cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, c
         if (!encode(&tmA, A, 4, dims, strides, box)) return cudaErrorInvalidValue;
     }
     // CTA pairs (cta_group::2) for the split-TF32 plans of the product path when there are enough pair tiles for every TPC
-    const bool cta2 = (split == 2 || split == 3) && cta2_enabled() && ((g.n_m_tiles + 1) / 2) * g.n_n_tiles >= 74;
+    const bool enough_pairs = ((g.n_m_tiles + 1) / 2) * g.n_n_tiles >= 74;
+    const bool cta2 = (split == 2 || split == 3) && cta2_enabled() && enough_pairs;
+    // multicast pairs: the product plans, for the default hook mode (other modes keep the single-CTA kernels whose hook chains
+    // are specialised per mode)
+    const bool mc = !cta2 && (split == 2 || split == 3) && mc_enabled() && enough_pairs &&
+                    (ep.kind == EPI_FWD_DUAL || ep.kind == EPI_PLAIN || ep.mode == 0);
+    const bool half_boxes = cta2 || mc;
     {
         // B is [planes][Nn][K]: plane 0 = rna_tf32(W) (or W itself for single-pass TF32), plane 1 = W - plane 0
         cuuint64_t dims[2] = {(cuuint64_t)cg.K, (cuuint64_t)cg.Nn * (split ? 2 : 1)};
         cuuint64_t strides[1] = {(cuuint64_t)cg.K * 4};
-        cuuint32_t box[2] = {TC_BK, (cuuint32_t)(cta2 ? BN / 2 : BN)};     // a CTA pair stages half of the tile per CTA
+        cuuint32_t box[2] = {TC_BK, (cuuint32_t)(half_boxes ? BN / 2 : BN)};     // a CTA pair loads half of the tile per CTA
         if (!encode(&tmB, B, 2, dims, strides, box)) return cudaErrorInvalidValue;
         tmBlo = tmB;
         if (split == 3) {
-            cuuint32_t box_half[2] = {TC_BK, (cuuint32_t)(cta2 ? BN / 4 : BN / 2)};
+            cuuint32_t box_half[2] = {TC_BK, (cuuint32_t)(half_boxes ? BN / 4 : BN / 2)};
             if (!encode(&tmBlo, B, 2, dims, strides, box_half)) return cudaErrorInvalidValue;
         }
     }
@@ -909,6 +996,20 @@ cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, c
         else { XFRB_TC_PAIR(64) }
     }
 #undef XFRB_TC_PAIR
+#define XFRB_TC_MC(BN_)                                                                                  \
+    switch (ep.kind) {                                                                                   \
+        case EPI_FWD_DUAL: return launch_cfg2<BN_, 3, EPI_FWD_DUAL, 2>(tmA, tmB, tmBlo, g, ep, st);       \
+        case EPI_PLAIN: return launch_cfg2<BN_, 2, EPI_PLAIN, 2>(tmA, tmB, tmBlo, g, ep, st);             \
+        case EPI_MID: return launch_cfg2<BN_, 2, EPI_MID, 2, 0>(tmA, tmB, tmBlo, g, ep, st);              \
+        case EPI_JOIN: return launch_cfg2<BN_, 2, EPI_JOIN, 2, 0>(tmA, tmB, tmBlo, g, ep, st);            \
+        default: return cudaErrorInvalidValue;                                                           \
+    }
+    if (mc) {
+        if (BN == 256) { XFRB_TC_MC(256) }
+        else if (BN == 128) { XFRB_TC_MC(128) }
+        else { XFRB_TC_MC(64) }
+    }
+#undef XFRB_TC_MC
 #define XFRB_TC_KINDS(BN_, SP_)                                                                          \
     switch (ep.kind) {                                                                                   \
         case EPI_PLAIN: return launch_cfg<BN_, SP_, EPI_PLAIN>(tmA, tmB, tmBlo, g, ep, st);               \

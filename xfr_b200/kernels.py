@@ -55,7 +55,7 @@ _SIGNATURES = {
     'xfrb_relu': [_P, _P, ctypes.c_longlong, _P],
     'xfrb_chansum': [_P, _P, _P, _I, _I, _I, _P],
 }
-EXPORTS = ['xfrb_version', 'xfrb_last_error', 'xfrb_device_ok', 'xfrb_impl_available', 'xfrb_set_cta_pairs'] + sorted(_SIGNATURES)
+EXPORTS = ['xfrb_version', 'xfrb_last_error', 'xfrb_device_ok', 'xfrb_impl_available', 'xfrb_set_cta_pairs', 'xfrb_set_multicast_pairs'] + sorted(_SIGNATURES)
 
 _lib = None
 
@@ -76,6 +76,8 @@ def load_library(path=LIB_PATH):
     lib.xfrb_impl_available.argtypes = [_I]
     lib.xfrb_set_cta_pairs.restype = _I
     lib.xfrb_set_cta_pairs.argtypes = [_I]
+    lib.xfrb_set_multicast_pairs.restype = _I
+    lib.xfrb_set_multicast_pairs.argtypes = [_I]
     for name, args in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = args
