@@ -53,7 +53,7 @@ int xfrb_impl_available(int impl);
  * (XFRB_CTA2=1 in the environment enables); returns the previous setting.  Results are bit-identical either way. */
 int xfrb_set_cta_pairs(int on);
 /* tcgen05 kernels as clusters of two CTAs that TMA-multicast the weight tiles to each other (half the weight traffic out of
- * L2 per CTA; MMAs, TMEM and epilogue stay private): on by default where a launch has enough tiles (XFRB_MC=0 disables);
+ * L2 per CTA; MMAs, TMEM and epilogue stay private): measured neutral, off by default (XFRB_MC=1 enables);
  * returns the previous setting.  Results are bit-identical either way. */
 int xfrb_set_multicast_pairs(int on);
 

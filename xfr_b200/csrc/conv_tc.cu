@@ -16,12 +16,13 @@
 //                                weights arrive pre-split from the host as two planes.  The issuer runs hi*hi as soon
 //                                as the TMA data lands and lo*hi (+ hi*lo) one k-block later, into the same accumulator.
 //
-// PAIR = 2 (the product default): a cluster of two CTAs that work on two consecutive m-tiles of the SAME n-tile and share the
-//   weight traffic: each CTA's weight producer loads HALF of the weight tile and TMA-multicasts it into both CTAs' rings
-//   (the weight ring's empty barriers collect both CTAs' tcgen05.commit through a multicast commit).  Everything else -
-//   activation ring, split, MMA (cta_group::1, M = 128), TMEM, epilogue - stays private to the CTA.  Why: the weight tiles are
-//   2/3 of the L2 -> SM traffic (a 3x3 W+ dgrad launch moves 0.9 GB of activations and 1.8 GB of re-read weights at ~7.5 TB/s,
-//   which is what bounds the main loop), and the remote signalling sits on the EMPTY path, which has the ring depth as slack.
+// PAIR = 2 (XFRB_MC=1): a cluster of two CTAs that work on two consecutive m-tiles of the SAME n-tile and share the weight
+//   traffic: each CTA's weight producer loads HALF of the weight tile and TMA-multicasts it into both CTAs' rings (the weight
+//   ring's empty barriers collect both CTAs' tcgen05.commit through a multicast commit).  Everything else - activation ring,
+//   split, MMA (cta_group::1, M = 128), TMEM, epilogue - stays private to the CTA, and the remote signalling sits on the EMPTY
+//   path, which has the ring depth as slack.  The weight tiles are 2/3 of the L2 -> SM traffic (a 3x3 W+ dgrad launch moves
+//   0.9 GB of activations and 1.8 GB of re-read weights, ~7.5 TB/s), yet halving them measured neutral (2,862 vs 2,847 maps/s):
+//   L2 -> SM bandwidth is not what bounds the main loop.  Bit-identical to the single-CTA kernels; off by default.
 // PAIR = 1 / CTA2: the same kernel as a CTA PAIR (cluster of 2, tcgen05 cta_group::2).  One M = 256 x BN tile per pair: each CTA
 //   loads and splits its own 128 activation rows and HALF of the weight tile (BN/2 rows); the leader CTA issues
 //   tcgen05.mma.cta_group::2, whose tensor cores read each CTA's own A and both B halves, so the shared-memory operand
@@ -856,11 +857,11 @@ static cudaError_t launch_cfg2(const CUtensorMap& tmA, const CUtensorMap& tmB, c
     return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmBlo, g, ep);
 }
 
-static int g_mc = -1;        // multicast pairs: -1 from the environment (XFRB_MC=0 disables), else 0 / 1
+static int g_mc = -1;        // multicast pairs: -1 from the environment (XFRB_MC=1 enables), else 0 / 1
 static bool mc_enabled() {
     if (g_mc < 0) {
         const char* e = getenv("XFRB_MC");
-        g_mc = (e != nullptr && e[0] == '0') ? 0 : 1;
+        g_mc = (e != nullptr && e[0] == '1') ? 1 : 0;
     }
     return g_mc != 0;
 }
