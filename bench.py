@@ -67,8 +67,9 @@ class ClockSampler(threading.Thread):
         return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.rows[0][1]), 'reasons': reasons, 'samples': len(sm)}
 
 
-# DRAM bytes of one layer3 launch of each kernel family from `ncu --set full` (profiles/r1_ncu_full_{bwd,fwd}_g.csv)
-NCU_TRAFFIC = {'dgrad_join': 946e6, 'dgrad_mid': 127e6, 'conv_dual': 387e6}
+# DRAM bytes of one layer3 launch (128-probe sweep) of each kernel family from `ncu --set full`
+# (profiles/r1_ncu_full_bwd_i_final.csv, r1_ncu_full_fwd_g.csv)
+NCU_TRAFFIC = {'dgrad_join': 952e6, 'dgrad_mid': 131e6, 'conv_dual': 387e6}
 
 
 def kernel_families(eng, step_fn):
@@ -320,7 +321,7 @@ def main():
         'clocks': clocks,
         'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
                      'traffic': NCU_TRAFFIC['dgrad_join'],
-                     'traffic_note': 'DRAM read+write of one layer3 JOIN launch (ncu --set full, profiles/r1_ncu_full_bwd_g.csv); '
+                     'traffic_note': 'DRAM read+write of one layer3 JOIN launch (ncu --set full, profiles/r1_ncu_full_bwd_i_final.csv); '
                                      'its algorithmic bytes are 976e6',
                      'kernel': 'EBP backward sweep (conv_tc_kernel dgrad + fused hook epilogues, join/stem kernels)',
                      'peak_source': peak_src, 'bwd_ms_per_step': bwd_ms / args.steps,
