@@ -49,8 +49,9 @@ const char* xfrb_last_error(void);
 int xfrb_device_ok(void);
 /* 1 when GEMM implementation `impl` (XFRB_IMPL_*) is compiled into this library */
 int xfrb_impl_available(int impl);
-/* tcgen05 kernels as CTA pairs (cta_group::2, one 256-row tile per TPC) where a launch has enough tiles: off by default
- * (XFRB_CTA2=1 in the environment enables); returns the previous setting.  Results are bit-identical either way. */
+/* tcgen05 kernels as CTA pairs (cta_group::2, one 256-row tile per TPC: each SM stages and reads half of the weight tile) for
+ * the forward dual conv and the MID dgrads where a launch has enough tiles: on by default (XFRB_CTA2=0 in the environment
+ * disables); returns the previous setting.  Results are bit-identical either way. */
 int xfrb_set_cta_pairs(int on);
 /* tcgen05 kernels as clusters of two CTAs that TMA-multicast the weight tiles to each other (half the weight traffic out of
  * L2 per CTA; MMAs, TMEM and epilogue stay private): measured neutral, off by default (XFRB_MC=1 enables);

@@ -23,7 +23,8 @@
 //   path, which has the ring depth as slack.  The weight tiles are 2/3 of the L2 -> SM traffic (a 3x3 W+ dgrad launch moves
 //   0.9 GB of activations and 1.8 GB of re-read weights, ~7.5 TB/s), yet halving them measured neutral (2,862 vs 2,847 maps/s):
 //   L2 -> SM bandwidth is not what bounds the main loop.  Bit-identical to the single-CTA kernels; off by default.
-// PAIR = 1 / CTA2: the same kernel as a CTA PAIR (cluster of 2, tcgen05 cta_group::2).  One M = 256 x BN tile per pair: each CTA
+// PAIR = 1 / CTA2 (default for the forward dual conv and the MID dgrads): the same kernel as a CTA PAIR (cluster of 2,
+//   tcgen05 cta_group::2).  One M = 256 x BN tile per pair: each CTA
 //   loads and splits its own 128 activation rows and HALF of the weight tile (BN/2 rows); the leader CTA issues
 //   tcgen05.mma.cta_group::2, whose tensor cores read each CTA's own A and both B halves, so the shared-memory operand
 //   traffic per SM per MMA drops from A + B to A + B/2 (the 3xTF32 main loop is shared-memory-bandwidth bound,
@@ -109,13 +110,15 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the barrier at the same smem offset in CTA `cta` of the cluster (release at cluster scope)
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster.  Plain forms, as CUTLASS's ClusterBarrier uses
+// them: with .release.cluster here and try_wait.acquire.cluster on the waiting side every k-block paid a cluster-scope fence
+// and the pair kernels ran 1.05-1.5x SLOWER than single CTAs; with the plain forms they run 1.1-1.15x faster.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
     asm volatile(
         "{\n\t"
         ".reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
         "}\n" ::"r"(bar), "r"(cta)
         : "memory");
 }
@@ -124,7 +127,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAITC_%=:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@p bra DONEC_%=;\n\t"
         "bra WAITC_%=;\n\t"
         "DONEC_%=:\n\t"
@@ -870,11 +873,11 @@ int conv_tc_set_mc(int on) {
     g_mc = on ? 1 : 0;
     return prev;
 }
-static int g_cta2 = -1;      // -1: from the environment (XFRB_CTA2=1 enables), else 0 / 1
+static int g_cta2 = -1;      // -1: from the environment (XFRB_CTA2=0 disables), else 0 / 1
 static bool cta2_enabled() {
     if (g_cta2 < 0) {
         const char* e = getenv("XFRB_CTA2");
-        g_cta2 = (e != nullptr && e[0] == '1') ? 1 : 0;
+        g_cta2 = (e != nullptr && e[0] == '0') ? 0 : 1;
     }
     return g_cta2 != 0;
 }
@@ -955,7 +958,11 @@ cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, c
     }
     // CTA pairs (cta_group::2) for the split-TF32 plans of the product path when there are enough pair tiles for every TPC
     const bool enough_pairs = ((g.n_m_tiles + 1) / 2) * g.n_n_tiles >= 74;
-    const bool cta2 = (split == 2 || split == 3) && cta2_enabled() && enough_pairs;
+    // cta_group::2 pairs for the main-loop-bound kinds of the product plans: the forward dual conv and the MID dgrads in the
+    // default hook mode (measured per launch: 331 -> 297 us and 370 -> 322 us).  The JOIN dgrads are epilogue-bound and lose
+    // (623 -> 776 us as pairs); other hook modes keep the single-CTA kernels specialised per mode.
+    const bool cta2 = cta2_enabled() && enough_pairs &&
+                      ((split == 3 && ep.kind == EPI_FWD_DUAL) || (split == 2 && ep.kind == EPI_MID && ep.mode == 0));
     // multicast pairs: the product plans, for the default hook mode (other modes keep the single-CTA kernels whose hook chains
     // are specialised per mode)
     const bool mc = !cta2 && (split == 2 || split == 3) && mc_enabled() && enough_pairs &&
@@ -985,10 +992,8 @@ cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, c
     }
 #define XFRB_TC_PAIR(BN_)                                                                                \
     switch (ep.kind) {                                                                                   \
-        case EPI_FWD_DUAL: return launch_cfg2<BN_, 3, EPI_FWD_DUAL>(tmA, tmB, tmBlo, g, ep, st);          \
-        case EPI_PLAIN: return launch_cfg2<BN_, 2, EPI_PLAIN>(tmA, tmB, tmBlo, g, ep, st);                \
-        case EPI_MID: return launch_cfg2<BN_, 2, EPI_MID>(tmA, tmB, tmBlo, g, ep, st);                    \
-        case EPI_JOIN: return launch_cfg2<BN_, 2, EPI_JOIN>(tmA, tmB, tmBlo, g, ep, st);                  \
+        case EPI_FWD_DUAL: return launch_cfg2<BN_, 3, EPI_FWD_DUAL, 1>(tmA, tmB, tmBlo, g, ep, st);       \
+        case EPI_MID: return launch_cfg2<BN_, 2, EPI_MID, 1, 0>(tmA, tmB, tmBlo, g, ep, st);              \
         default: return cudaErrorInvalidValue;                                                           \
     }
     if (cta2) {
