@@ -248,7 +248,8 @@ struct TcCfg {
     static_assert(TC_FIRST_EPI_WARP * 32 * REGS_PRODUCER + EPI_WARPS * 32 * REGS_EPILOGUE <= THREADS * REGS_LAUNCH,
                   "setmaxnreg budgets exceed the CTA's register pool");
     static constexpr uint32_t TR_BYTES = EPI_WARPS * 2048;      // per epilogue warp: 32 rows x 16 columns transpose slab
-    static constexpr uint32_t SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + PRM_BYTES + TR_BYTES;
+    static constexpr uint32_t BAR_BYTES = 512;
+    static constexpr uint32_t SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + BAR_BYTES + PRM_BYTES + TR_BYTES;
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory a CTA can opt into");
 };
 
@@ -283,10 +284,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto emptyb_bar = [&](int s) { return bar_base + 8u * (3 * NA + NB + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * NA + 2 * NB + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * NA + 2 * NB + 2 + a); };
-    static_assert(8 * (3 * NA + 2 * NB + 4) + 4 <= 256, "barrier block");
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + Cfg::RING_BYTES + 8 * (3 * NA + 2 * NB + 4));
-    float* prm_s = reinterpret_cast<float*>(smem_gen + Cfg::RING_BYTES + 256);   // [2][6][BN]
-    float4* tr_s = reinterpret_cast<float4*>(smem_gen + Cfg::RING_BYTES + 256 + Cfg::PRM_BYTES);
+    auto land_bar = [&](int s) { return bar_base + 8u * (3 * NA + 2 * NB + 4 + s); };   // CTA pair: "both CTAs' TMA data landed"
+    static_assert(8 * (4 * NA + 2 * NB + 4) + 4 <= Cfg::BAR_BYTES, "barrier block");
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + Cfg::RING_BYTES + 8 * (4 * NA + 2 * NB + 4));
+    float* prm_s = reinterpret_cast<float*>(smem_gen + Cfg::RING_BYTES + Cfg::BAR_BYTES);   // [2][rows][PRM_LD]
+    float4* tr_s = reinterpret_cast<float4*>(smem_gen + Cfg::RING_BYTES + Cfg::BAR_BYTES + Cfg::PRM_BYTES);
 
     auto a_hi = [&](int s) { return smem_base + s * Cfg::A_BYTES; };
     auto a_lo = [&](int s) { return smem_base + s * Cfg::A_BYTES + A_TILE_BYTES; };                           // split only
@@ -304,6 +306,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
             mbar_init(split_bar(s), CTA2 ? 8 : 4);               // pair: the peer's split warps arrive here too (leader's copy)
+            if (CTA2) mbar_init(land_bar(s), 8);
         }
         for (int s = 0; s < NB; ++s) {
             mbar_init(fullb_bar(s), 1);
@@ -443,7 +446,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // itself), so it is issued as soon as the stage lands and runs while the split warps produce the lo tile.
             for (int kb = 0; kb < g.num_k; ++kb) {
                 if (lane == 0) {
-                    if (CTA2) mbar_wait_cluster(split_bar(s), ph);            // implies both CTAs' TMA data landed
+                    if (CTA2) mbar_wait_cluster(land_bar(s), ph);             // both CTAs' split warps saw their TMA data land
                     else mbar_wait(full_bar(s), ph);
                     if (SPLITRING) mbar_wait(fullb_bar(sb), phb);
                     tc_fence_after();
@@ -455,10 +458,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         mma(tacc, dah + koff, dbh + koff, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     if (SPLIT3) {
-                        if (!CTA2) {
-                            mbar_wait(split_bar(s), ph);
-                            tc_fence_after();
-                        }
+                        if (CTA2) mbar_wait_cluster(split_bar(s), ph);
+                        else mbar_wait(split_bar(s), ph);
+                        tc_fence_after();
                         const uint64_t dal = make_desc(a_lo(s)), dbl = make_desc(b_lo(bs));
 #pragma unroll
                         for (int k = 0; k < TC_BK / 8; ++k) {
@@ -496,6 +498,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int tile = worker; tile < total_tiles; tile += nworkers) {
                 for (int kb = 0; kb < g.num_k; ++kb) {
                     mbar_wait(full_bar(s), ph);
+                    if (CTA2 && lane == 0) {           // tell the leader's MMA thread that this CTA's stage landed: its hi pass can go
+                        if (!leader) mbar_arrive_remote(land_bar(s), 0);
+                        else mbar_arrive(land_bar(s));
+                    }
                     // only the activation tile is split here; the weight tile arrives as (hi, lo) planes split on the host
                     float4* hi = reinterpret_cast<float4*>(smem_gen + s * Cfg::A_BYTES);
                     float4* lo = reinterpret_cast<float4*>(smem_gen + s * Cfg::A_BYTES + A_TILE_BYTES);
