@@ -19,6 +19,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if '--impl' in sys.argv and 'reference' in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is a CPU measurement on all host cores (rank 0 only)
+    for _k in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ.pop(_k, None)
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402

@@ -1,35 +1,26 @@
-// tcgen05 implicit-GEMM convolution for sm_100a (impl 1 = 3xTF32 "fp32-equivalent", impl 2 = single TF32).
+// tcgen05 implicit-GEMM convolution for sm_100a: the forward convs and the W+ transposed convs (dgrads) of the whitebox
+// sweep with the excitation-backprop hook chains fused into the epilogue.
 //
 //   D[m, n] = sum_k A[m, k] * B[n, k]      A: NHWC activations (R x R taps, stride 1, zero pad), B: K-major weights
 //
-// One persistent CTA per SM, 512 threads in four warpgroups (640 / five for the JOIN kernels), warp-specialised (setmaxnreg moves the registers the
-// producer warpgroups do not need to the epilogue warpgroups, whose loads are double-buffered in registers):
-//   warp 0      TMA producer   - cp.async.bulk.tensor loads of the A tile (128 pixel rows x 32 channels; for 3x3 convs a
-//                                4-D box (32ch, W, bh rows, bn images) shifted by the tap, out-of-bounds rows/columns
-//                                zero-filled by the TMA unit = the conv padding) and of the B tile (BN x 32), both
-//                                landing in 128B-swizzled shared memory, signalled through an mbarrier (complete_tx)
-//   warp 1      MMA issuer     - one lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) with the
-//                                accumulator in TMEM (two accumulator stages so the epilogue of tile i overlaps the
-//                                main loop of tile i+1); tcgen05.commit releases smem stages / publishes accumulators
-//   warps 4-7   operand split  - (split plans only) lo = x - trunc_tf32(x) of the landed activation tile into a twin
-//                                buffer; the raw tile itself is the hi operand (the tensor core truncates fp32 to TF32);
-//                                weights arrive pre-split from the host as two planes.  The issuer runs hi*hi as soon
-//                                as the TMA data lands and lo*hi (+ hi*lo) one k-block later, into the same accumulator.
-//
-// PAIR = 2 (XFRB_MC=1): a cluster of two CTAs that work on two consecutive m-tiles of the SAME n-tile and share the weight
-//   traffic: each CTA's weight producer loads HALF of the weight tile and TMA-multicasts it into both CTAs' rings (the weight
-//   ring's empty barriers collect both CTAs' tcgen05.commit through a multicast commit).  Everything else - activation ring,
-//   split, MMA (cta_group::1, M = 128), TMEM, epilogue - stays private to the CTA, and the remote signalling sits on the EMPTY
-//   path, which has the ring depth as slack.  The weight tiles are 2/3 of the L2 -> SM traffic (a 3x3 W+ dgrad launch moves
-//   0.9 GB of activations and 1.8 GB of re-read weights, ~7.5 TB/s), yet halving them measured neutral (2,862 vs 2,847 maps/s):
-//   L2 -> SM bandwidth is not what bounds the main loop.  Bit-identical to the single-CTA kernels; off by default.
-// PAIR = 1 / CTA2 (default for the forward dual conv and the MID dgrads): the same kernel as a CTA PAIR (cluster of 2,
-//   tcgen05 cta_group::2).  One M = 256 x BN tile per pair: each CTA
-//   loads and splits its own 128 activation rows and HALF of the weight tile (BN/2 rows); the leader CTA issues
-//   tcgen05.mma.cta_group::2, whose tensor cores read each CTA's own A and both B halves, so the shared-memory operand
-//   traffic per SM per MMA drops from A + B to A + B/2 (the 3xTF32 main loop is shared-memory-bandwidth bound,
-//   profiles/r1_notes.md).  Peer -> leader signalling: remote mbarrier arrives (split done, accumulator drained);
-//   leader -> both: multicast tcgen05.commit.
+// One persistent CTA per SM, warp-specialised in whole warpgroups so that setmaxnreg can move the registers the producers
+// do not need to the epilogue (512 threads; 640 for the JOIN kernels):
+//   warp 0      TMA producer, activation ring - cp.async.bulk.tensor loads of the A tile (128 pixel rows x 32 channels;
+//               for 3x3 convs a 4-D box (32 ch, W, bh image rows, bimg images) shifted by the tap, out-of-bounds rows /
+//               columns zero-filled by the TMA unit = the conv padding) into 128B-swizzled shared memory (mbarrier complete_tx)
+//   warp 2      TMA producer, weight ring - the B tile (BN x 32, hi plane and, where the plan needs it, the lo plane).  The
+//               two rings are independently deep: 3 + 2 stages for the forward dual tiles, 4 + 2 for the W+ dgrads
+//   warp 1      MMA issuer - one lane issues tcgen05.mma.kind::tf32 (M = 128, N = BN, K = 8) into TMEM; two accumulator
+//               stages so the epilogue of tile i overlaps the main loop of tile i+1; tcgen05.commit releases ring stages and
+//               publishes accumulators.  The hi pass of a k-block is issued as soon as its TMA data lands, the lo passes when
+//               the split warps are done
+//   warps 4-7   operand split - lo = rna_tf32(x - trunc_tf32(x)) of the landed activation tile into a twin buffer; the raw
+//               tile itself is the hi operand (tcgen05 truncates fp32 operands to TF32: tools/trunc_probe.py); weights arrive
+//               pre-split from the host as two planes
+//   warps 8-15  epilogue (8-19 for JOIN) - tcgen05.ld a 32-row x 16-column slab of the accumulator (lane = pixel row),
+//               transpose it through swizzled smem so that lanes own consecutive channels, apply the fused EBP epilogue of
+//               common.cuh against the saved tensors (their global loads are issued one slab ahead), store NHWC fp32 with
+//               128-bit accesses.  The hook mode is a template constant (MODE) in the product plans
 //
 // SPLIT (pass plan of the GEMM):
 //   0  single TF32 pass
@@ -38,9 +29,20 @@
 //      product with relu(W) rounded to TF32; the lo weight plane is never loaded.  Using the same rounded W+ for the X of
 //      the forward twin and for the dgrad keeps excitation backprop mass-conserving.
 //   3  dual forward pack [W rows | relu(W) rows]: A_hi*B_hi + A_lo*B_hi over the whole tile, A_hi*B_lo over the W half only
-//   warps 8-15 (8-19)  epilogue       - tcgen05.ld the accumulator (lane = pixel row), apply the fused EBP epilogue of
-//                                common.cuh against the saved tensors, store NHWC fp32 with 128-bit accesses; the
-//                                global loads of slab j+1 are in flight while slab j is computed
+//
+// PAIR (clusters of two CTAs working on two consecutive m-tiles of the same n-tile; all variants are bit-identical):
+//   0  single CTAs.
+//   1  cta_group::2 pair (CTA2; default for the forward dual conv and the MID dgrads): one M = 256 x BN tile per pair.
+//      Each CTA loads and splits its own 128 activation rows and stages HALF of the weight tile; the leader issues
+//      tcgen05.mma.cta_group::2, whose tensor cores read each CTA's own A and both B halves, so the shared-memory traffic
+//      per SM per k-block drops from 224 KB to 160 KB (forward dual) - the split-TF32 main loop is shared-memory-bandwidth
+//      bound (profiles/r1_notes.md).  Peer -> leader: remote mbarrier arrives (data landed, split done, accumulator
+//      drained); leader -> both: multicast tcgen05.commit.  The remote arrives and the leader's waits are the PLAIN forms:
+//      with .release.cluster / .acquire.cluster the same kernel was 1.05-1.5x slower than single CTAs.
+//   2  multicast pair (XFRB_MC=1): each CTA's weight producer loads HALF of the weight tile and TMA-multicasts it into both
+//      CTAs' rings (the weight ring's empty barriers collect both CTAs' commits through a multicast commit); MMAs, TMEM and
+//      epilogue stay private.  Halves the weight traffic out of L2 (2/3 of the ~7.5 TB/s L2 -> SM stream of a 3x3 dgrad) and
+//      measured neutral: L2 -> SM bandwidth is not what bounds the main loop.  Off by default.
 #include "common.cuh"
 #include <cuda.h>
 #include <stdio.h>
@@ -420,7 +422,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (pair: the leader CTA only) =====================
+        // ===================== MMA issuer (cta_group::2 pair: the leader CTA only) =====================
         constexpr uint32_t MM = CTA2 ? 2 * TC_BM : TC_BM;      // cta_group::2: M = 256, rows 128.. live in the peer's TMEM
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(MM >> 4) << 24);
         constexpr uint32_t idesc_half = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 4) << 17) | ((uint32_t)(MM >> 4) << 24);
@@ -540,10 +542,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // loads of a slab are issued before the accumulator is waited for.  The two warps of a TMEM lane quarter
         // alternate slabs; per-channel constants are staged in smem once per tile.
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_EPILOGUE));  // the epilogue warpgroups
-        const int ew = warp - TC_FIRST_EPI_WARP;       // 0..7
+        const int ew = warp - TC_FIRST_EPI_WARP;       // 0..EW-1
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
         const int part = ew >> 2;                      // which slabs of the tile this warp owns: part, part + 3, ...
-        const int et = threadIdx.x - TC_FIRST_EPI_WARP * 32;   // 0..255
+        const int et = threadIdx.x - TC_FIRST_EPI_WARP * 32;   // 0..32*EW-1
         const int cgl = lane & 3;                      // my 4-channel group inside the slab
         const int rsub = lane >> 2;                    // my row inside each group of 8 rows
         float4* tbuf = tr_s + ew * 128;
