@@ -57,6 +57,10 @@ int xfrb_set_cta_pairs(int on);
  * L2 per CTA; MMAs, TMEM and epilogue stay private): measured neutral, off by default (XFRB_MC=1 enables);
  * returns the previous setting.  Results are bit-identical either way. */
 int xfrb_set_multicast_pairs(int on);
+/* Host-only helper (no GPU needed): the 4-D TMA box the tcgen05 kernel uses for the activation tiles of a 3x3 conv over
+ * Nimg maps of H x W pixels - bimg images x bh image rows x W pixels <= 128 GEMM rows.  Returns the fraction of the 128 rows
+ * that carry pixels (-1 on bad arguments). */
+double xfrb_tile_geometry(int H, int W, int Nimg, int* bh, int* bimg);
 
 /* ---- forward ("activation" + "positive_activation" passes, whitebox.py:490-493) ---- */
 

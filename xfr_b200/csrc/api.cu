@@ -88,6 +88,10 @@ int xfrb_impl_available(int impl) {
     return 0;
 }
 
+double xfrb_tile_geometry(int H, int W, int Nimg, int* bh, int* bimg) {
+    if (H < 1 || W < 1 || W > 128 || Nimg < 1 || bh == nullptr || bimg == nullptr) return -1.0;
+    return conv_tc_tile_geometry(H, W, Nimg, bh, bimg);
+}
 int xfrb_set_cta_pairs(int on) { return conv_tc_set_cta2(on); }
 int xfrb_set_multicast_pairs(int on) { return conv_tc_set_mc(on); }
 

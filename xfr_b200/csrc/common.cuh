@@ -204,6 +204,7 @@ struct JoinArgs {
 
 cudaError_t launch_conv_simt(const float* A, const float* B, const ConvGeom& g, const EpiParams& ep, cudaStream_t st);
 bool conv_tc_available();
+double conv_tc_tile_geometry(int H, int W, int Nimg, int* bh, int* bimg);   // host: 4-D TMA box of a 3x3 conv (conv_tc.cu)
 int conv_tc_set_cta2(int on);     // CTA-pair (cta_group::2) kernels on/off; returns the previous setting
 int conv_tc_set_mc(int on);       // multicast-pair kernels (shared weight loads) on/off; returns the previous setting
 // B: [planes][Nn][K] with the 3xTF32 (hi, lo) planes when split != 0 (pass plans 0-3: conv_tc.cu); tn: dual-pack tile

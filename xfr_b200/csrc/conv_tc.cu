@@ -810,6 +810,28 @@ static bool encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t
 
 bool conv_tc_available() { return true; }
 
+// Box of a 3x3 conv's activation tile = bimg images x bh image rows x W pixels <= 128 GEMM rows.  Picks the (bh, bimg) that
+// wastes the fewest of the 128 rows, counting the ragged last strip and the ragged last image group: 14x14 maps go from 7 rows
+// of one image (98 of 128 rows = 77 %) to 1 row of 9 images (126 rows, 97 %), 7x7 maps to 1 row of 18 images (93 %).
+// Returns the fraction of useful rows.
+double conv_tc_tile_geometry(int H, int W, int Nimg, int* bh_out, int* bimg_out) {
+    double best = -1.0;
+    int lim = TC_BM / W;
+    if (lim > H) lim = H;
+    *bh_out = 1;
+    *bimg_out = 1;
+    for (int bh = lim; bh >= 1; --bh) {         // ties keep the larger strip (more contiguous rows per image)
+        int bimg = TC_BM / (bh * W);
+        if (bimg > Nimg) bimg = Nimg;
+        if (bimg > 256) bimg = 256;
+        if (bimg < 1) continue;
+        const int th = (H + bh - 1) / bh, ng = (Nimg + bimg - 1) / bimg;
+        const double eff = ((double)H / (th * bh)) * ((double)(bh * W * bimg) / TC_BM) * ((double)Nimg / (ng * bimg));
+        if (eff > best + 1e-9) { best = eff; *bh_out = bh; *bimg_out = bimg; }
+    }
+    return best;
+}
+
 template <int BN, int SPLIT, int KIND, int MODE = -1>
 static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo, const TcGeom& g,
                               const EpiParams& ep, cudaStream_t st) {
@@ -939,25 +961,9 @@ cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, c
     } else {
         g.a4d = 1;
         if (cg.W > 128) return cudaErrorInvalidValue;
-        {
-            // Box = bimg images x bh image rows x W pixels <= 128 GEMM rows.  Pick the (bh, bimg) that wastes the fewest of
-            // the 128 rows, counting the ragged last strip and the ragged last image group: 14x14 maps go from 7 rows of one
-            // image (98 of 128 rows = 77 %) to 1 row of 9 images (126 rows, 97 %), 7x7 maps to 1 row of 18 images (93 %).
-            double best = -1.0;
-            int lim = TC_BM / cg.W;
-            if (lim > cg.H) lim = cg.H;
-            for (int bh = lim; bh >= 1; --bh) {         // ties keep the larger strip (more contiguous rows per image)
-                int bimg = TC_BM / (bh * cg.W);
-                if (bimg > g.Nimg) bimg = g.Nimg;
-                if (bimg > 256) bimg = 256;
-                if (bimg < 1) continue;
-                const int th = (cg.H + bh - 1) / bh, ng = (g.Nimg + bimg - 1) / bimg;
-                const double eff = ((double)cg.H / (th * bh)) * ((double)(bh * cg.W * bimg) / TC_BM) * ((double)g.Nimg / (ng * bimg));
-                if (eff > best + 1e-9) { best = eff; g.bh = bh; g.bimg = bimg; }
-            }
-            g.tiles_per_img = (cg.H + g.bh - 1) / g.bh;             // row strips per image group
-            g.n_m_tiles = ((g.Nimg + g.bimg - 1) / g.bimg) * g.tiles_per_img;
-        }
+        conv_tc_tile_geometry(cg.H, cg.W, g.Nimg, &g.bh, &g.bimg);
+        g.tiles_per_img = (cg.H + g.bh - 1) / g.bh;             // row strips per image group
+        g.n_m_tiles = ((g.Nimg + g.bimg - 1) / g.bimg) * g.tiles_per_img;
         g.a_bytes = (uint32_t)(TC_BK * cg.W * g.bh * g.bimg * 4);
         cuuint64_t dims[4] = {(cuuint64_t)cg.Cin, (cuuint64_t)cg.W, (cuuint64_t)cg.H, (cuuint64_t)g.Nimg};
         cuuint64_t strides[3] = {(cuuint64_t)cg.Cin * 4, (cuuint64_t)cg.W * cg.Cin * 4, (cuuint64_t)HW * cg.Cin * 4};

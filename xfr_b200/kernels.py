@@ -55,7 +55,7 @@ _SIGNATURES = {
     'xfrb_relu': [_P, _P, ctypes.c_longlong, _P],
     'xfrb_chansum': [_P, _P, _P, _I, _I, _I, _P],
 }
-EXPORTS = ['xfrb_version', 'xfrb_last_error', 'xfrb_device_ok', 'xfrb_impl_available', 'xfrb_set_cta_pairs', 'xfrb_set_multicast_pairs'] + sorted(_SIGNATURES)
+EXPORTS = ['xfrb_version', 'xfrb_last_error', 'xfrb_device_ok', 'xfrb_impl_available', 'xfrb_set_cta_pairs', 'xfrb_set_multicast_pairs', 'xfrb_tile_geometry'] + sorted(_SIGNATURES)
 
 _lib = None
 
@@ -78,6 +78,8 @@ def load_library(path=LIB_PATH):
     lib.xfrb_set_cta_pairs.argtypes = [_I]
     lib.xfrb_set_multicast_pairs.restype = _I
     lib.xfrb_set_multicast_pairs.argtypes = [_I]
+    lib.xfrb_tile_geometry.restype = ctypes.c_double
+    lib.xfrb_tile_geometry.argtypes = [_I, _I, _I, ctypes.POINTER(_I), ctypes.POINTER(_I)]
     for name, args in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = args
