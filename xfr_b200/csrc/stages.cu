@@ -284,7 +284,64 @@ cudaError_t launch_head_bwd_b(const float* z, const float* v, float* g_out, int 
 
 // ------------------------------------------------------------------ unfused block boundary
 
-__global__ void join_kernel(JoinArgs a, size_t total4) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) join_kernel(JoinArgs a, size_t total4) {
+    // one thread = 4 channels of one pixel of one SAMPLE; it walks the gradient-row groups (mate, non-mate, ...) of that sample so
+    // that the saved tensors (out, o3, xr3, res) and the BatchNorm constants are read once, not once per group
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int C4 = a.C / 4;
+    int c = (int)(i % C4) * 4;
+    size_t p = i / C4;
+    int w = p % a.W; p /= a.W;
+    int h = p % a.H;
+    int n = (int)(p / a.H);
+    size_t ms = ((size_t)n * a.H + h) * a.W + w;
+    float4 uv = ld4(a.out + ms * a.C + c), ov = ld4(a.o3 + ms * a.C + c), xv = ld4(a.xr3 + ms * a.C + c);
+    float u[4] = {uv.x, uv.y, uv.z, uv.w}, o[4] = {ov.x, ov.y, ov.z, ov.w}, x[4] = {xv.x, xv.y, xv.z, xv.w};
+    float r[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a.mode == XFRB_MODE_ALL && a.res != nullptr && c < a.res_c) {
+        float4 rv = ld4(a.res + ms * a.res_c + c);
+        r[0] = rv.x; r[1] = rv.y; r[2] = rv.z; r[3] = rv.w;
+    }
+    float4 al = ld4(a.bn3 + c), be = ld4(a.bn3 + a.C + c), sp = ld4(a.bn3 + 2 * a.C + c), tp = ld4(a.bn3 + 3 * a.C + c);
+    BnC b[4] = {{al.x, be.x, sp.x, tp.x}, {al.y, be.y, sp.y, tp.y}, {al.z, be.z, sp.z, tp.z}, {al.w, be.w, sp.w, tp.w}};
+    const bool on_main = (h % a.up == 0 && w % a.up == 0);
+    const bool on_res = (a.gres_lo != nullptr && c < a.gres_c);
+    const int Hm = a.H / a.up, Wm = a.W / a.up, Hr = a.H / a.k, Wr = a.W / a.k;
+    const float kk = (float)(a.k * a.k);
+    // two gradient-row groups per trip: both groups' gradient loads are in flight before the first hook chain starts
+    for (int j0 = n; j0 < a.J; j0 += 2 * a.N) {
+        const int ng = (j0 + a.N < a.J) ? 2 : 1;
+        float z[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        float4 tm[2], tr[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int j = j0 + s * a.N;
+            if (s < ng && on_main) tm[s] = ld4(a.zmain + (((size_t)j * Hm + h / a.up) * Wm + w / a.up) * a.C + c);
+            if (s < ng && on_res) tr[s] = ld4(a.gres_lo + (((size_t)j * Hr + h / a.k) * Wr + w / a.k) * a.gres_c + c);
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (s >= ng) break;
+            const int j = j0 + s * a.N;
+            if (on_main) { z[s][0] = tm[s].x; z[s][1] = tm[s].y; z[s][2] = tm[s].z; z[s][3] = tm[s].w; }
+            if (on_res) {
+                z[s][0] = __fadd_rn(z[s][0], __fdiv_rn(tr[s].x, kk)); z[s][1] = __fadd_rn(z[s][1], __fdiv_rn(tr[s].y, kk));
+                z[s][2] = __fadd_rn(z[s][2], __fdiv_rn(tr[s].z, kk)); z[s][3] = __fadd_rn(z[s][3], __fdiv_rn(tr[s].w, kk));
+            }
+            float g[4], y3[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) join_chain(z[s][q], u[q], o[q], x[q], r[q], b[q], a.hooks, a.mode, a.eps, g[q], y3[q]);
+            const size_t off = ((((size_t)j * a.H + h) * a.W + w) * a.C + c) / 4;
+            reinterpret_cast<float4*>(a.g_out)[off] = make_float4(g[0], g[1], g[2], g[3]);
+            reinterpret_cast<float4*>(a.y3_out)[off] = make_float4(y3[0], y3[1], y3[2], y3[3]);
+        }
+    }
+}
+
+// A/B twin of join_kernel: one thread per (gradient row, pixel, 4 channels); saved tensors are re-read per gradient-row group
+__global__ void join_rows_kernel(JoinArgs a, size_t total4) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
     const int C4 = a.C / 4;
@@ -325,8 +382,17 @@ __global__ void join_kernel(JoinArgs a, size_t total4) {
 }
 
 cudaError_t launch_join(const JoinArgs& a, cudaStream_t st) {
-    size_t total4 = (size_t)a.J * a.H * a.W * (a.C / 4);
-    join_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(a, total4);
+    if (a.N <= 0 || a.J % a.N != 0) return cudaErrorInvalidValue;
+    static const int variant = [] { const char* e = getenv("XFRB_JOIN"); return e ? atoi(e) : 0; }();   // 1: per-row twin (A/B probe)
+    if (variant == 1) {
+        size_t total4 = (size_t)a.J * a.H * a.W * (a.C / 4);
+        join_rows_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(a, total4);
+        return cudaGetLastError();
+    }
+    size_t total4 = (size_t)a.N * a.H * a.W * (a.C / 4);
+    // occupancy decides this kernel (tools/join_probe.py, 128 probes x 2 groups, four boundaries of a ResNet-101 sweep): 104 registers
+    // (2 CTAs per SM) 2,393 us, 80 (3) 1,846 us, 64 (4, a few spilled words) 1,667 us; the per-row twin (46 registers) 2,024 us
+    join_kernel<4><<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(a, total4);
     return cudaGetLastError();
 }
 
