@@ -179,6 +179,15 @@ int xfrb_trunc_threshold(const float* P2, const double* sums, float percentile, 
 /* skimage.filters.gaussian(sigma=2) -> max(0,.) -> /max(sum,eps)  (whitebox.py:455-460); [B,H,W], H,W <= 128 */
 int xfrb_saliency_post(const float* mwp, float* out, int B, int H, int W, float eps, void* stream);
 
+/* Inpainting-game blends (python/xfr/inpainting_game/inpainting_game.py:110-132, consumed by Whitebox.embeddings,
+ * whitebox.py:747-785): out[k,h,w,c] = fp32((1 - m) * orig[c,h,w] + m * inp[c,h,w]), evaluated in double, with
+ * m = (value[h,w] > thr[k]) (inpainting_game.py:66; `masks` = NULL) or m = masks[k,h,w] (blurred masks, lines 69-78).
+ * orig / inp [C,H,W] double (network format, as the reference's astype(np.float64)), value [H,W] / thr [K] / masks [K,H,W]
+ * double, out [K,H,W,C] fp32 (NHWC: the forward sweep's input).  mask_f32 != 0: the masks were float32 numbers (numpy then
+ * evaluates 1 - m in float32).  C = 1 or 3, H*W % 4 == 0, K <= 65535. */
+int xfrb_twin_blends(const double* orig, const double* inp, const double* value, const double* thr, const double* masks, float* out,
+                     int K, int C, int H, int W, int mask_f32, void* stream);
+
 /* ---- generic single-hook path: priors, P recording, true gradients (whitebox.py:561-737) ---- */
 
 #define XFRB_MODE_NONE 3   /* no hook fires (plain backprop); P_out then records the incoming gradient (self.dA) */

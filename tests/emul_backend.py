@@ -403,6 +403,14 @@ class EmulBackend(object):
             img = img / max(img.sum(), self.eps)
             out[i].copy_(torch.from_numpy(img))
 
+    def twin_blends(self, orig, inp, value, thr, masks, out, mask_f32=False):
+        """xfrb_twin_blends: float64 blend of two CHW images under K masks, rounded once to fp32, written NHWC."""
+        m = masks if masks is not None else (value.unsqueeze(0) > thr.view(-1, 1, 1)).double()          # [K,H,W]
+        m = m.unsqueeze(1)
+        w = (1.0 - m.float()).double() if mask_f32 else 1.0 - m
+        b = w * orig.double().unsqueeze(0) + m * inp.double().unsqueeze(0)                                 # [K,C,H,W]
+        out.copy_(b.float().permute(0, 2, 3, 1))
+
     # ------------------------------------------------------------ Light-CNN-29v2 pieces (include/xfrb.h)
     def conv_bias(self, inp, B, bias, out, R, positive=False):
         out.view(-1, out.shape[-1]).copy_(im2col_nhwc(inp, R, R, R // 2) @ (_wpos(B) if positive else _w(B)).t() + bias)

@@ -36,6 +36,8 @@ cudaError_t launch_stem_bwd(const float*, const float*, const float*, const floa
 cudaError_t launch_contrast(const float*, const double*, const float*, float*, int, int, int, cudaStream_t);
 cudaError_t launch_trunc_threshold(const float*, const double*, float, float*, int, size_t, cudaStream_t);
 cudaError_t launch_saliency_post(const float*, float*, int, int, int, float, cudaStream_t);
+cudaError_t launch_twin_blends(const double*, const double*, const double*, const double*, const double*, float*, int, int, int, int,
+                               int, cudaStream_t);
 // lightcnn.cu
 cudaError_t launch_lc_conv1(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, cudaStream_t);
 cudaError_t launch_mfm_fwd(const float*, const float*, float*, float*, float*, size_t, int, cudaStream_t);
@@ -319,6 +321,11 @@ int xfrb_trunc_threshold(const float* P2, const double* sums, float percentile, 
 int xfrb_saliency_post(const float* mwp, float* out, int B, int H, int W, float eps, void* stream) {
     if (H > 128 || W > 128) return finish("xfrb_saliency_post", cudaErrorInvalidValue);
     return finish("xfrb_saliency_post", launch_saliency_post(mwp, out, B, H, W, eps, (cudaStream_t)stream));
+}
+
+int xfrb_twin_blends(const double* orig, const double* inp, const double* value, const double* thr, const double* masks, float* out,
+                     int K, int C, int H, int W, int mask_f32, void* stream) {
+    return finish("xfrb_twin_blends", launch_twin_blends(orig, inp, value, thr, masks, out, K, C, H, W, mask_f32, (cudaStream_t)stream));
 }
 
 /* ---- Light-CNN-29v2 ---- */

@@ -946,4 +946,62 @@ cudaError_t launch_saliency_post(const float* mwp, float* out, int B, int H, int
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ inpainting-game blends
+// blend[k,h,w,c] = (1 - m) * orig[c,h,w] + m * inp[c,h,w] evaluated in double and rounded once to fp32 - the float64 blends of
+// inpainting_game.py:124-132 followed by the .float() of Whitebox.embeddings (whitebox.py:762) - with m = (value[h,w] > thr[k])
+// (inpainting_game.py:66: the K masks are never materialised) or, when `masks` is given, the explicit (blurred) mask
+// m = masks[k,h,w].  One thread = 4 consecutive pixels of one blend: both images (double, CHW = the reference's network format,
+// 1.2 MB each: L2-resident across the K blends) are read as two double2 per channel plane and the blend is written NHWC, C float4
+// per thread, ready for the stem kernel.
+template <int C>
+__global__ void __launch_bounds__(256) twin_blend_kernel(const double* __restrict__ orig, const double* __restrict__ inp,
+                                                         const double* __restrict__ value, const double* __restrict__ thr,
+                                                         const double* __restrict__ masks, float* __restrict__ out, int HW4, int mask_f32) {
+    const int i = blockIdx.x * 256 + threadIdx.x;        // pixel quad inside the image
+    if (i >= HW4) return;
+    const int k = blockIdx.y;
+    const size_t HW = (size_t)HW4 * 4;
+    double m[4];
+    if (masks != nullptr) {
+        const double2* mp = reinterpret_cast<const double2*>(masks + (size_t)k * HW) + (size_t)i * 2;
+        const double2 a = mp[0], b = mp[1];
+        m[0] = a.x; m[1] = a.y; m[2] = b.x; m[3] = b.y;
+    } else {
+        const double t = thr[k];
+        const double2* vp = reinterpret_cast<const double2*>(value) + (size_t)i * 2;
+        const double2 a = __ldg(vp), b = __ldg(vp + 1);
+        m[0] = a.x > t ? 1.0 : 0.0; m[1] = a.y > t ? 1.0 : 0.0; m[2] = b.x > t ? 1.0 : 0.0; m[3] = b.y > t ? 1.0 : 0.0;
+    }
+    // numpy evaluates `1.0 - masks` in the masks' own dtype: float32 masks (a float32 saliency map, blurred) round it to fp32
+    double w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[q] = mask_f32 ? (double)__fsub_rn(1.0f, (float)m[q]) : __dsub_rn(1.0, m[q]);
+    float f[4 * C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const double2* op = reinterpret_cast<const double2*>(orig + (size_t)c * HW) + (size_t)i * 2;
+        const double2* pp = reinterpret_cast<const double2*>(inp + (size_t)c * HW) + (size_t)i * 2;
+        const double2 o0 = __ldg(op), o1 = __ldg(op + 1), p0 = __ldg(pp), p1 = __ldg(pp + 1);
+        const double ov[4] = {o0.x, o0.y, o1.x, o1.y}, pv[4] = {p0.x, p0.y, p1.x, p1.y};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            f[q * C + c] = __double2float_rn(__dadd_rn(__dmul_rn(w[q], ov[q]), __dmul_rn(m[q], pv[q])));
+    }
+    float4* dst = reinterpret_cast<float4*>(out + ((size_t)k * HW + (size_t)i * 4) * C);
+#pragma unroll
+    for (int c = 0; c < C; ++c) dst[c] = make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
+}
+
+cudaError_t launch_twin_blends(const double* orig, const double* inp, const double* value, const double* thr, const double* masks,
+                               float* out, int K, int C, int H, int W, int mask_f32, cudaStream_t st) {
+    const size_t HW = (size_t)H * W;
+    if (K <= 0 || K > 65535 || HW % 4 != 0 || (masks == nullptr && (value == nullptr || thr == nullptr))) return cudaErrorInvalidValue;
+    const int HW4 = (int)(HW / 4);
+    dim3 grid((unsigned)((HW4 + 255) / 256), (unsigned)K);
+    if (C == 3) twin_blend_kernel<3><<<grid, 256, 0, st>>>(orig, inp, value, thr, masks, out, HW4, mask_f32);
+    else if (C == 1) twin_blend_kernel<1><<<grid, 256, 0, st>>>(orig, inp, value, thr, masks, out, HW4, mask_f32);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
 }  // namespace xfrb

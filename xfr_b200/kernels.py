@@ -46,6 +46,7 @@ _SIGNATURES = {
     'xfrb_contrast': [_P, _P, _P, _P, _I, _I, _I, _P],
     'xfrb_trunc_threshold': [_P, _P, _F, _P, _I, ctypes.c_longlong, _P],
     'xfrb_saliency_post': [_P, _P, _I, _I, _I, _F, _P],
+    'xfrb_twin_blends': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     'xfrb_conv_bias': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'xfrb_lc_conv1': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     'xfrb_mfm_fwd': [_P, _P, _P, _P, _P, ctypes.c_longlong, _I, _P],
@@ -264,6 +265,16 @@ class CudaBackend(object):
     def saliency_post(self, mwp, out):
         B, H, W = mwp.shape
         self._check(self.lib.xfrb_saliency_post(_ptr(mwp), _ptr(out), B, H, W, self.eps, self._st()))
+
+    def twin_blends(self, orig, inp, value, thr, masks, out, mask_f32=False):
+        """orig / inp [C,H,W], value [H,W] + thr [K] (or masks [K,H,W]), all float64 -> out [K,H,W,C] fp32 blends."""
+        K, H, W, C = out.shape
+        assert orig.shape == inp.shape == (C, H, W) and out.dtype == torch.float32 and out.is_contiguous()
+        for t in (orig, inp, value, thr, masks):
+            assert t is None or (t.dtype == torch.float64 and t.is_contiguous())
+        assert (masks is not None and masks.shape == (K, H, W)) or (value.shape == (H, W) and thr.shape == (K,))
+        self._check(self.lib.xfrb_twin_blends(_ptr(orig), _ptr(inp), _ptr(value), _ptr(thr), _ptr(masks), _ptr(out), K, C, H, W,
+                                              1 if mask_f32 else 0, self._st()))
 
     # -------------------------------------------------------------- Light-CNN-29v2 pieces
     def conv_bias(self, inp, B, bias, out, R, positive=False):

@@ -132,6 +132,15 @@ class WhiteboxSTResnet(WhiteboxNetwork):
             out.append(50.0 * eng.forward(self._nhwc(x[i:i + _CHUNK])).clone())
         return torch.cat(out)
 
+    _ENC_SCALE = 50.0      # encode() = 50 * L2-normalised fc1 (whitebox.py:98-100); the other two plugins return the raw feature
+
+    def encode_nhwc(self, x_nhwc):
+        """encode() for probes that are already on the device in the engine's NHWC layout (xfr_b200/inpaintgame.py)."""
+        eng = self.engine()
+        out = [eng.forward(x_nhwc[i:i + _CHUNK]).clone() for i in range(0, x_nhwc.shape[0], _CHUNK)]
+        enc = torch.cat(out)
+        return enc * self._ENC_SCALE if self._ENC_SCALE != 1.0 else enc
+
     def classify(self, x):
         enc = self.encode(x)
         if self._W2 is not None:
@@ -151,6 +160,8 @@ class Whitebox_resnet50_128(WhiteboxSTResnet):
     """VGGFace2 ResNet-50-128d plugin (reference whitebox.py:210-258): 128-d encoding = feat_extract output, classifier =
     an un-hooked Linear(128, 2) held by the wrapper (whitebox.py:216-230).  `net` is the reference's
     resnet50_128.Resnet50_128 module or its state_dict."""
+
+    _ENC_SCALE = 1.0
 
     def __init__(self, net, impl='tf32x3'):
         if isinstance(net, dict):
@@ -227,6 +238,7 @@ class WhiteboxLightCNN(WhiteboxSTResnet):
     xfr.models.lightcnn.network_29layers_v2 module (lightcnn.py:216-275) or its state_dict.  The classifier is the
     network's fc2 (hooked, W+ in the backward) until set_triplet_classifier replaces it by an un-hooked Linear(256, 2)
     (whitebox.py:120-123).  Saliency maps are 128x128 (P[-2] is the first Split input, 96x128x128)."""
+    _ENC_SCALE = 1.0
 
     def __init__(self, net, impl='tf32x3'):
         if isinstance(net, dict):
@@ -367,7 +379,8 @@ class Whitebox(nn.Module):
                                 k_negchannel, self._ebp_subtree_mode, hooked_fc2=hk, percentile=percentile,
                                 saliency=not self.convert_saliency_uint8, num_classes=self.net.num_classes())
             res[i:i + m.shape[0]].copy_(m, non_blocking=True)
-        torch.cuda.current_stream(W2.device).synchronize()
+        if W2.is_cuda:
+            torch.cuda.current_stream(W2.device).synchronize()
         if self.convert_saliency_uint8:
             return np.stack([self._mwp_to_saliency_uint8(m) for m in res.numpy()])
         return res if out is not None else res.numpy()
