@@ -284,8 +284,9 @@ cudaError_t launch_head_bwd_b(const float* z, const float* v, float* g_out, int 
 
 // ------------------------------------------------------------------ unfused block boundary
 
-template <int MINB>
+template <int MINB, int MODE>      // MODE >= 0: the hook mode as a compile-time constant (drops the BatchNorm constants it does not use)
 __global__ void __launch_bounds__(256, MINB) join_kernel(JoinArgs a, size_t total4) {
+    const int mode = MODE >= 0 ? MODE : a.mode;
     // one thread = 4 channels of one pixel of one SAMPLE; it walks the gradient-row groups (mate, non-mate, ...) of that sample so
     // that the saved tensors (out, o3, xr3, res) and the BatchNorm constants are read once, not once per group
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(256, MINB) join_kernel(JoinArgs a, size_t tota
     float4 uv = ld4(a.out + ms * a.C + c), ov = ld4(a.o3 + ms * a.C + c), xv = ld4(a.xr3 + ms * a.C + c);
     float u[4] = {uv.x, uv.y, uv.z, uv.w}, o[4] = {ov.x, ov.y, ov.z, ov.w}, x[4] = {xv.x, xv.y, xv.z, xv.w};
     float r[4] = {0.f, 0.f, 0.f, 0.f};
-    if (a.mode == XFRB_MODE_ALL && a.res != nullptr && c < a.res_c) {
+    if (mode == XFRB_MODE_ALL && a.res != nullptr && c < a.res_c) {
         float4 rv = ld4(a.res + ms * a.res_c + c);
         r[0] = rv.x; r[1] = rv.y; r[2] = rv.z; r[3] = rv.w;
     }
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(256, MINB) join_kernel(JoinArgs a, size_t tota
             }
             float g[4], y3[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) join_chain(z[s][q], u[q], o[q], x[q], r[q], b[q], a.hooks, a.mode, a.eps, g[q], y3[q]);
+            for (int q = 0; q < 4; ++q) join_chain(z[s][q], u[q], o[q], x[q], r[q], b[q], a.hooks, mode, a.eps, g[q], y3[q]);
             const size_t off = ((((size_t)j * a.H + h) * a.W + w) * a.C + c) / 4;
             reinterpret_cast<float4*>(a.g_out)[off] = make_float4(g[0], g[1], g[2], g[3]);
             reinterpret_cast<float4*>(a.y3_out)[off] = make_float4(y3[0], y3[1], y3[2], y3[3]);
@@ -383,16 +384,25 @@ __global__ void join_rows_kernel(JoinArgs a, size_t total4) {
 
 cudaError_t launch_join(const JoinArgs& a, cudaStream_t st) {
     if (a.N <= 0 || a.J % a.N != 0) return cudaErrorInvalidValue;
-    static const int variant = [] { const char* e = getenv("XFRB_JOIN"); return e ? atoi(e) : 0; }();   // 1: per-row twin (A/B probe)
+    static const int variant = [] { const char* e = getenv("XFRB_JOIN"); return e ? atoi(e) : 0; }();   // A/B probe: 1 per-row twin, 2 runtime hook mode, 5 / 6 min CTAs per SM
     if (variant == 1) {
         size_t total4 = (size_t)a.J * a.H * a.W * (a.C / 4);
         join_rows_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(a, total4);
         return cudaGetLastError();
     }
     size_t total4 = (size_t)a.N * a.H * a.W * (a.C / 4);
-    // occupancy decides this kernel (tools/join_probe.py, 128 probes x 2 groups, four boundaries of a ResNet-101 sweep): 104 registers
-    // (2 CTAs per SM) 2,393 us, 80 (3) 1,846 us, 64 (4, a few spilled words) 1,667 us; the per-row twin (46 registers) 2,024 us
-    join_kernel<4><<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(a, total4);
+    // occupancy decides this kernel (tools/join_probe.py, 128 probes x 2 groups, the four boundaries of a ResNet-101 sweep, all variants
+    // bit-identical): per-row twin (46 registers) 2,024 us; per sample with a runtime hook mode: 104 registers (2 CTAs per SM) 2,393 us,
+    // 80 (3) 1,846 us, 64 (4) 1,667 us; hook mode as a template constant (fewer BatchNorm constants live): 4 CTAs 1,416 us (default),
+    // 5 CTAs 1,364 us, 6 CTAs (192 B spilled) 1,451 us
+    const unsigned grid = (unsigned)((total4 + 255) / 256);
+    if (variant == 2) join_kernel<4, -1><<<grid, 256, 0, st>>>(a, total4);                   // A/B probe: runtime hook mode
+    else if (variant == 5 && a.mode == XFRB_MODE_AWP) join_kernel<5, XFRB_MODE_AWP><<<grid, 256, 0, st>>>(a, total4);
+    else if (variant == 6 && a.mode == XFRB_MODE_AWP) join_kernel<6, XFRB_MODE_AWP><<<grid, 256, 0, st>>>(a, total4);
+    else if (a.mode == XFRB_MODE_AWP) join_kernel<4, XFRB_MODE_AWP><<<grid, 256, 0, st>>>(a, total4);
+    else if (a.mode == XFRB_MODE_ALL) join_kernel<4, XFRB_MODE_ALL><<<grid, 256, 0, st>>>(a, total4);
+    else if (a.mode == XFRB_MODE_AFFINEONLY) join_kernel<4, XFRB_MODE_AFFINEONLY><<<grid, 256, 0, st>>>(a, total4);
+    else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 
