@@ -65,6 +65,42 @@ def test_batch_matches_per_job_gpu():
     _check_batch_matches_per_job(True, 5e-3)
 
 
+def _shard_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    wb = whitebox.Whitebox(_net(L1111, False))
+    jobs = _jobs()                                             # 3 jobs over 2 ranks: shards of 2 and 1
+    got = IG.run_contrastive_triplet_ebp_sharded(wb, jobs, truncate_percent=None)
+    if rank == 0:
+        want = IG.run_contrastive_triplet_ebp_batch(wb, jobs)
+        q.put((got.shape, float(np.abs(got - want).max() / want.max())))
+    else:
+        assert got is None
+    dist.destroy_process_group()
+
+
+def test_sharded_jobs_world2_gloo():
+    """SURVEY 8e for the front end: contiguous job shards, one gather of maps, job order preserved (ragged shards)."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    shape, err = q.get(timeout=10)
+    assert shape == (3, 112, 112) and err < 1e-4      # torch CPU GEMMs block a 2-probe and a 3-probe batch differently
+
+
 def test_mean_encodings_and_errors():
     wb = whitebox.Whitebox(_net(L1111, False))
     im = _images(4, seed=5)

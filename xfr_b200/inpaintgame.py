@@ -78,6 +78,27 @@ def run_contrastive_triplet_ebp_batch(wb, jobs, truncate_percent=None, device=No
     return wb.contrastive_ebp_batch(probes, 0, 1, percentile=truncate_percent)
 
 
+def run_contrastive_triplet_ebp_sharded(wb, jobs, truncate_percent=None, device=None, dst=0):
+    """Multi-GPU form of the batch (the reference farms jobs out one process per GPU,
+    eval/generate_inpaintinggame_wb_saliency_maps_multigpu.py:191-231): one process per GPU under torchrun, rank r sweeps
+    the contiguous slice shard_range(len(jobs), r, world) of the jobs and the only collective is the gather of the finished
+    maps to rank `dst`.  Returns the [N, h, w] maps in job order on `dst`, None on the other ranks."""
+    import torch.distributed as dist
+    from .shard import gather_maps, shard_range
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return run_contrastive_triplet_ebp_batch(wb, jobs, truncate_percent, device)
+    lo, hi = shard_range(len(jobs), dist.get_rank(), dist.get_world_size())
+    hw = wb.net.engine().map_hw
+    if hi > lo:
+        local = torch.from_numpy(np.ascontiguousarray(run_contrastive_triplet_ebp_batch(wb, jobs[lo:hi], truncate_percent, device)))
+    else:
+        local = torch.empty(0, hw, hw, dtype=torch.uint8 if wb.convert_saliency_uint8 else torch.float32)
+    if dist.get_backend() == 'nccl':
+        local = local.to(wb.net._device())
+    out = gather_maps(local, len(jobs), dst=dst)
+    return None if out is None else out.cpu().numpy()
+
+
 def run_contrastive_triplet_ebp(wb, im_mates, im_nonmates, probe_im, net_name=None, ebp_version=None, truncate_percent=None,
                                 device=None):
     """generate_whitebox_saliency.py:81-118 (same arguments; net_name / ebp_version are unused there too)."""
