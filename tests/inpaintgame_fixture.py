@@ -1,6 +1,7 @@
 """Seeded inputs of the inpainting-game scoring goldens (TEST INFRASTRUCTURE): shared by oracle/gen_golden_inpaintgame.py,
 which feeds them to the reference, and tests/test_inpaintgame.py, which feeds them to this package."""
 import numpy as np
+import torch
 
 from xfr_b200 import synth
 
@@ -20,3 +21,16 @@ def scoring_fixture():
     sparse[blob < 0.2] = 0
     sparse /= sparse.sum()
     return {'orig': imgs[0], 'inp': imgs[1], 'smap': smap, 'smap_sparse': sparse}
+
+
+def images(n, seed):
+    """n smooth 224x224x3 uint8 images (the inpainting-game images are 224x224 PNGs)."""
+    x = synth.smooth_probes(n, seed=seed) + torch.tensor(synth.MEAN_RGB).view(1, 3, 1, 1)
+    return [np.ascontiguousarray(im.permute(1, 2, 0).numpy().astype(np.uint8)) for im in x]
+
+
+def jobs():
+    """Three (im_mates, im_nonmates, probe_im) jobs, ragged: 3 mates / 1 non-mate, 1 mate / 2 non-mates, 1 / 1 with a probe
+    that is also job 0's mate."""
+    im = images(9, seed=11)
+    return [(im[0:3], im[3:4], im[4]), (im[5:6], im[6:8], im[8]), (im[2:3], im[7:8], im[0])]

@@ -1,7 +1,8 @@
-"""the batched inpainting-game front end (xfr_b200/inpaintgame.py) against the reference's
-per-job flow (python/xfr/inpainting_game/generate_whitebox_saliency.py:81-118, 122-205, 207-215) restated on the batch-1
-Whitebox API, whose own parity with the reference the golden tests establish.  CPU: host logic over the kernel emulation;
-GPU: the CUDA kernels."""
+"""the inpainting-game front end and scoring (xfr_b200/inpaintgame.py) against what the
+reference's own functions return (tests/golden/inpaintgame_seed0.npz: oracle/gen_golden_inpaintgame.py ran
+python/xfr/inpainting_game/generate_whitebox_saliency.py:81-215 and inpainting_game.py:12-146 on the seeded inputs of
+tests/inpaintgame_fixture.py), and against the reference's per-job flow restated on the batch-1 Whitebox API.
+CPU: host logic over the kernel emulation; GPU: the CUDA kernels."""
 import os
 
 import numpy as np
@@ -9,21 +10,10 @@ import pytest
 import torch
 
 from helpers import L1111, rel_err
+from inpaintgame_fixture import images as _images, jobs as _jobs
 from test_layerwise_subtree import _net
 from xfr_b200 import inpaintgame as IG
 from xfr_b200 import synth, whitebox
-
-
-def _images(n, seed):
-    """n smooth 224x224x3 uint8 images (the inpainting-game images are 224x224 PNGs)."""
-    x = synth.smooth_probes(n, seed=seed) + torch.tensor(synth.MEAN_RGB).view(1, 3, 1, 1)
-    return [np.ascontiguousarray(im.permute(1, 2, 0).numpy().astype(np.uint8)) for im in x]
-
-
-def _jobs():
-    im = _images(9, seed=11)
-    # ragged: 3 mates / 1 non-mate, 1 mate / 2 non-mates, 1 / 1 with a probe that is also job 0's mate
-    return [(im[0:3], im[3:4], im[4]), (im[5:6], im[6:8], im[8]), (im[2:3], im[7:8], im[0])]
 
 
 def _reference_flow(wb, im_mates, im_nonmates, probe_im, truncate_percent):
@@ -53,6 +43,38 @@ def _check_batch_matches_per_job(gpu, tol):
         one = IG.run_contrastive_triplet_ebp(wb, *jobs[1], net_name='resnetv4_pytorch', ebp_version=6, truncate_percent=pct)
         assert rel_err(one, want[1]) < tol
     assert rel_err(got[0], got[2]) > 0.1            # different triplets give different maps: rows were not mixed up
+
+
+def _check_jobs_vs_reference(gpu, tol_c, tol):
+    """The batched front end against the outputs of the reference's own run_contrastive_triplet_ebp /
+    run_weighted_subtree_triplet_ebp / mean_ebp (batch 1, one fresh reference Whitebox per call)."""
+    G = _gold()
+    jobs = _jobs()
+    wb = whitebox.Whitebox(_net(L1111, gpu))
+    for pct, tag in ((None, ''), (20, '_pct20')):
+        got = IG.run_contrastive_triplet_ebp_batch(wb, jobs, truncate_percent=pct)
+        for i in range(3):
+            ref = G['job%d_contrastive%s' % (i, tag)]
+            assert got[i].shape == ref.shape == (112, 112) and float(np.abs(got[i] - ref).max()) < 1e-4     # the north-star bar
+            assert rel_err(got[i], ref) < tol_c, (i, pct)
+    im = _images(4, seed=21)
+    wb = whitebox.Whitebox(_net(L1111, gpu))
+    assert rel_err(IG.mean_ebp(wb, im[3]), G['mean_ebp']) < tol
+    for ctor_mode, sub_mode, ver, key in (('norelu', 'all', 6, 'ws_eval_smap'),                       # the eval flow's settings
+                                          ('affineonly_with_prior', 'affineonly_with_prior', 7, 'ws_v7_smap')):   # + max, gating
+        wb = whitebox.Whitebox(_net(L1111, gpu), ebp_subtree_mode=ctor_mode)
+        got = IG.run_weighted_subtree_triplet_ebp(wb, im[0:2], im[2:3], im[3], net_name='resnetv4_pytorch',
+                                                  subtree_mode_weighted=sub_mode, ebp_version=ver, device=None, topk=4)
+        assert got.shape == (112, 112) and np.isfinite(got).all() and abs(float(got.sum()) - 1.0) < 1e-3
+        assert rel_err(got, G[key]) < tol
+
+
+def test_jobs_vs_reference_emulated():
+    _check_jobs_vs_reference(False, 1e-3, 2e-3)
+
+
+# On the GPU the same outputs are pinned transitively: test_batch_matches_per_job_gpu ties the batched front end to the per-job flow
+# on the CUDA kernels, tests/test_gpu_parity.py ties that flow to the reference's outputs.
 
 
 def test_batch_matches_per_job_emulated():
