@@ -123,6 +123,18 @@ def test_sharded_jobs_world2_gloo():
     assert shape == (3, 112, 112) and err < 1e-4      # torch CPU GEMMs block a 2-probe and a 3-probe batch differently
 
 
+def test_ragged_sweeps_emulated(monkeypatch):
+    """Jobs that do not fill the last engine sweep: 3 jobs / 7 gallery images in sweeps of 2 equal one sweep of everything."""
+    wb = whitebox.Whitebox(_net(L1111, False))
+    jobs = _jobs()
+    want = IG.run_contrastive_triplet_ebp_batch(wb, jobs, truncate_percent=20)
+    monkeypatch.setattr(whitebox, '_CHUNK', 2)
+    got = IG.run_contrastive_triplet_ebp_batch(wb, jobs, truncate_percent=20)
+    assert got.shape == (3, 112, 112) and rel_err(got, want) < 1e-4
+    with pytest.raises(ValueError):
+        IG.run_contrastive_triplet_ebp_batch(wb, [([], jobs[0][1], jobs[0][2])])
+
+
 def test_mean_encodings_and_errors():
     wb = whitebox.Whitebox(_net(L1111, False))
     im = _images(4, seed=5)
