@@ -74,7 +74,13 @@ def test_jobs_vs_reference_emulated():
 
 
 # On the GPU the same outputs are pinned transitively: test_batch_matches_per_job_gpu ties the batched front end to the per-job flow
-# on the CUDA kernels, tests/test_gpu_parity.py ties that flow to the reference's outputs.
+# on the CUDA kernels, tests/test_gpu_parity.py ties that flow to the reference's outputs.  The direct comparison below was written
+# after the round's GPU budget was spent and has not run on a B200 yet: non-strict xfail until it has (XPASS = it holds).
+@pytest.mark.gpu
+@pytest.mark.xfail(reason='not yet run on a B200 (added after the GPU budget of round 1 was spent)', strict=False)
+def test_jobs_vs_reference_gpu():
+    # tolerances of tests/test_gpu_parity.py: contrastive maps are cancellation-amplified (split-TF32 vs fp32), 1e-4 max-abs is the bar
+    _check_jobs_vs_reference(True, 5e-2, 1e-2)
 
 
 def test_batch_matches_per_job_emulated():

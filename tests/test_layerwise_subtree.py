@@ -82,6 +82,56 @@ def test_layerwise_emulated():
     _check_layerwise(L1111, False, 2e-5)
 
 
+def _check_layer_sweep(gpu, tol):
+    """BASELINE configs[2]: the percentile layer sweep of one triplet against the reference's own layerwise_contrastive_ebp run
+    firing by firing (tests/golden/layersweep1111_seed0.npz, oracle/gen_golden_layersweep.py)."""
+    import os
+    from helpers import GOLD
+    G, R = golden(L1111), np.load(os.path.join(GOLD, 'layersweep1111_seed0.npz'))
+    n = int(R['n_firings'])
+    wb = whitebox.Whitebox(_net(L1111, gpu))
+    wb.net.set_triplet_classifier(torch.from_numpy(G['enc_mate']) / 2500.0, torch.from_numpy(G['enc_nonmate']) / 2500.0)
+    probe = synth.smooth_probes(3, seed=1)[0:1]
+    maps = wb.layerwise_contrastive_ebp_sweep(probe, 0, 1, list(range(n)), mode='percentile', percentile=20, rows_per_sweep=16)
+    assert maps.shape == (n, 112, 112) and maps.dtype == np.float32
+    assert wb.P_layername == [str(s).split('(')[0] for s in R['names']]          # module kinds in firing order
+    live = R['map_max'] > 0
+    assert live.sum() == 15 and not live[n - 1]
+    for k in range(n):
+        if not live[k]:
+            assert not maps[k].any(), k                                    # non-affine firings / empty contrast: all-zero map
+        else:
+            assert abs(float(maps[k].astype(np.float64).sum()) - R['map_sum'][k]) < 1e-4
+            assert abs(float(maps[k].max()) / R['map_max'][k] - 1.0) < tol, k
+    for k, ref in zip(R['full_k'], R['full']):
+        if live[k]:
+            assert rel_err(maps[k], ref) < tol and np.abs(maps[k] - ref).max() < 1e-4, k
+    # the batched sweep is the per-layer operator, layer by layer
+    for k in (3, 29, -2):
+        with pytest.warns(UserWarning):
+            one = wb.layerwise_contrastive_ebp(probe, 0, 1, k_layer=k, mode='percentile', percentile=20)
+        assert rel_err(maps[k % n], one) < 1e-6
+    sub = wb.layerwise_contrastive_ebp_sweep(probe, 0, 1, [29, 3, 29, n - 1], mode='copy', mwp=True)      # order, repeats, last firing
+    assert sub.shape == (4, 112, 112) and np.array_equal(sub[0], sub[2]) and not sub[3].any() and sub[1].max() > 0
+    with pytest.raises(ValueError):
+        wb.layerwise_contrastive_ebp_sweep(probe, 0, 1, [3], mode='elementwise')
+    with pytest.warns(UserWarning):
+        assert not wb.layerwise_contrastive_ebp(probe, 0, 1, k_layer=n - 1, mode='percentile', percentile=20).any()
+    assert not wb.layerwise_ebp(probe, k_layer=-1, mode='argmax').any()
+
+
+def test_layer_sweep_emulated():
+    _check_layer_sweep(False, 2e-3)
+
+
+# Written after the round's GPU budget was spent: the sweep composes kernels the other GPU tests cover (row-indexed tensor
+# priors, P recording), but this test itself has not run on a B200 yet - non-strict xfail until it has (XPASS = it holds).
+@pytest.mark.gpu
+@pytest.mark.xfail(reason='not yet run on a B200 (added after the GPU budget of round 1 was spent)', strict=False)
+def test_layer_sweep_gpu():
+    _check_layer_sweep(True, 2e-2)
+
+
 def test_layerwise_contrastive_modes_emulated():
     """Every mode of the deprecated layerwise_contrastive_ebp runs and obeys its definition (whitebox.py:606-642):
     'copy' with the contrastive difference of the LAST-but-one firing as prior reproduces... itself at that firing."""

@@ -430,6 +430,12 @@ class Whitebox(nn.Module):
             maps = np.stack([self._mwp_to_saliency_uint8(m) for m in chansum.cpu().numpy()])
         return maps
 
+    def _zero_map(self, mwp):
+        """A prior at the last firing (the Conv2d hook on the image, not recorded) cannot reach P[-2]: the reference's third
+        pass starts from a zero seed and returns an all-zero map."""
+        hw = self.net.engine(self._ebp_with_bias).map_hw
+        return np.zeros((hw, hw), dtype=np.uint8 if (self.convert_saliency_uint8 and not mwp) else np.float32)
+
     def _onehot(self, k, dev):
         P0 = torch.zeros((1, self.net.num_classes()), device=dev)
         P0[0][k] = 1.0
@@ -441,6 +447,9 @@ class Whitebox(nn.Module):
         gs, W2 = self._generic(img_probe)
         P0 = self._onehot(k_poschannel, W2.device)
         P_mate, names, _ = gs.run(P0, W2, self._ebp_subtree_mode, record=True)
+        k_layer = int(k_layer) % len(P_mate)                    # the reference indexes Python lists: negative k_layer counts from the image
+        if P_mate[k_layer] is None:
+            return self._zero_map(mwp)
         Pk = P_mate[k_layer]
         if mode == 'argmax':
             prior = (0, (Pk * (Pk == Pk.max())).reshape(-1).contiguous())
@@ -454,18 +463,9 @@ class Whitebox(nn.Module):
         self._set_P(gs, P, names)
         return self._finish_map(P2, mwp)[0]
 
-    def layerwise_contrastive_ebp(self, img_probe, k_poschannel, k_negchannel, k_layer, mode='copy', percentile=80, k_element=None,
-                                  gradlayer=None, mwp=False):
-        """whitebox.py:584-644 (deprecated in the reference in favour of weighted_subtree_ebp, kept for the layer sweeps)."""
-        import warnings
-        warnings.warn("layerwise_contrastive_ebp is deprecated, use weighted_subtree_ebp instead")
-        assert(k_poschannel >= 0 and k_poschannel < self.net.num_classes())
-        assert(k_negchannel >= 0 and k_negchannel < self.net.num_classes())
-        gs, W2 = self._generic(img_probe)
-        dev = W2.device
-        Pn = torch.cat((self._onehot(k_poschannel, dev), self._onehot(k_negchannel, dev)))
-        P, names, _ = gs.run(Pn, W2, self._ebp_subtree_mode, record=True)         # mate and non-mate as two gradient rows
-        Pm, Pq = P[k_layer][0:1], P[k_layer][1:2]
+    def _contrastive_prior(self, gs, Pm, Pq, k_layer, mode, percentile, k_element):
+        """The prior of whitebox.py:603-636 at one firing from the mate / non-mate MWPs recorded there ([1,...] each)."""
+        dev = Pm.device
         C = torch.clamp_min(Pm - Pq, 0)
         argmax_only = lambda t: t * (t == t.max())
         if mode == 'copy':
@@ -493,6 +493,55 @@ class Whitebox(nn.Module):
             prior[e] = C.reshape(-1)[e]
         else:
             raise ValueError('unknown contrastive ebp mode "%s"' % mode)
+        return prior
+
+    def layerwise_contrastive_ebp_sweep(self, img_probe, k_poschannel, k_negchannel, k_layers, mode='percentile', percentile=20,
+                                        mwp=False, rows_per_sweep=48):
+        """Batched extension for layer sweeps (BASELINE.json configs[2]): layerwise_contrastive_ebp(..., k_layer=k) for every k in
+        k_layers of ONE probe -> [len(k_layers), h, w] maps.  The reference runs three ebp() per (probe, layer); the mate /
+        non-mate MWPs are the same for every layer, so they are recorded once (one 2-row sweep) and the per-layer third passes,
+        each with its prior at a different firing, are batched as gradient rows (`rows_per_sweep` at a time)."""
+        assert(k_poschannel >= 0 and k_poschannel < self.net.num_classes())
+        assert(k_negchannel >= 0 and k_negchannel < self.net.num_classes())
+        if mode == 'elementwise':
+            raise ValueError('layerwise_contrastive_ebp_sweep: mode "elementwise" needs a per-layer k_element; call '
+                             'layerwise_contrastive_ebp per layer')
+        gs, W2 = self._generic(img_probe)
+        dev = W2.device
+        Pn = torch.cat((self._onehot(k_poschannel, dev), self._onehot(k_negchannel, dev)))
+        P, names, _ = gs.run(Pn, W2, self._ebp_subtree_mode, record=True)
+        k_layers = [int(k) % len(P) for k in k_layers]                 # negative indices as Python lists take them
+        # the last firing (the Conv2d hook on the image) is not recorded: a prior there cannot reach P[-2], the map is all zero
+        priors = {k: self._contrastive_prior(gs, P[k][0:1], P[k][1:2], k, mode, percentile, None).reshape(-1).contiguous()
+                  for k in set(k_layers) if P[k] is not None}
+        zero = self._zero_map(mwp)
+        del P
+        self.P_layername = list(names)
+        todo = sorted(priors)                                             # one gradient row per distinct firing
+        maps = {}
+        for i in range(0, len(todo), rows_per_sweep):
+            chunk = todo[i:i + rows_per_sweep]
+            Z = torch.zeros(len(chunk), self.net.num_classes(), device=dev)
+            _, _, P2 = gs.run(Z, W2, self._ebp_subtree_mode, priors={k: (r, priors[k]) for r, k in enumerate(chunk)})
+            for k, m in zip(chunk, self._finish_map(P2, mwp)):
+                maps[k] = m
+        return np.stack([maps.get(k, zero) for k in k_layers])
+
+    def layerwise_contrastive_ebp(self, img_probe, k_poschannel, k_negchannel, k_layer, mode='copy', percentile=80, k_element=None,
+                                  gradlayer=None, mwp=False):
+        """whitebox.py:584-644 (deprecated in the reference in favour of weighted_subtree_ebp, kept for the layer sweeps)."""
+        import warnings
+        warnings.warn("layerwise_contrastive_ebp is deprecated, use weighted_subtree_ebp instead")
+        assert(k_poschannel >= 0 and k_poschannel < self.net.num_classes())
+        assert(k_negchannel >= 0 and k_negchannel < self.net.num_classes())
+        gs, W2 = self._generic(img_probe)
+        dev = W2.device
+        Pn = torch.cat((self._onehot(k_poschannel, dev), self._onehot(k_negchannel, dev)))
+        P, names, _ = gs.run(Pn, W2, self._ebp_subtree_mode, record=True)         # mate and non-mate as two gradient rows
+        k_layer = int(k_layer) % len(P)
+        if P[k_layer] is None:
+            return self._zero_map(mwp)
+        prior = self._contrastive_prior(gs, P[k_layer][0:1], P[k_layer][1:2], k_layer, mode, percentile, k_element)
         P0 = self._onehot(k_poschannel, dev)
         P, names, P2 = gs.run(0.0 * P0, W2, self._ebp_subtree_mode, priors={int(k_layer): (0, prior.reshape(-1).contiguous())}, record=True)
         self._set_P(gs, P, names)
