@@ -55,6 +55,17 @@ def main():
         if k % 4 == 1 or k == n - 2:
             full_k.append(k)
             full.append(m)
+    # the other modes of the operator (whitebox.py:606-642) at two live firings, layerwise_ebp's default 'argmax' mode
+    # (whitebox.py:561-581) and other truncation percentiles of truncated_contrastive_ebp (whitebox.py:529-558)
+    for mode in ('copy', 'mean', 'product', 'argmax', 'argmax_product', 'percentile_argmax'):
+        for k in (7, 29):
+            G['lc_%s_%d' % (mode, k)] = np.asarray(wb.layerwise_contrastive_ebp(probe, 0, 1, k_layer=k, mode=mode, percentile=20),
+                                                   dtype=np.float32)
+    for k in (3, 15, 29, 46, -2):
+        G['lw_argmax_%d' % (k % n)] = np.asarray(wb.layerwise_ebp(probe, k_layer=k, mode='argmax', k_poschannel=0, mwp=True),
+                                                 dtype=np.float32)
+    for pct in (0, 50, 80, 100):
+        G['trunc_pct%d' % pct] = np.asarray(wb.truncated_contrastive_ebp(probe, 0, 1, percentile=pct), dtype=np.float32)
     G.update(map_sum=np.array(sums), map_max=np.array(maxs), map_argmax=np.array(args), full_k=np.array(full_k),
              full=np.stack(full))
     out = os.path.join(ROOT, 'tests', 'golden', 'layersweep1111_seed0.npz')

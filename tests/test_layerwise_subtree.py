@@ -120,6 +120,37 @@ def _check_layer_sweep(gpu, tol):
     assert not wb.layerwise_ebp(probe, k_layer=-1, mode='argmax').any()
 
 
+def _check_other_modes(gpu, tol):
+    """The remaining modes of layerwise_contrastive_ebp, layerwise_ebp's default 'argmax' mode and other truncation percentiles
+    against the reference's own outputs (same golden file)."""
+    import os
+    from helpers import GOLD
+    G, R = golden(L1111), np.load(os.path.join(GOLD, 'layersweep1111_seed0.npz'))
+    wb = whitebox.Whitebox(_net(L1111, gpu))
+    wb.net.set_triplet_classifier(torch.from_numpy(G['enc_mate']) / 2500.0, torch.from_numpy(G['enc_nonmate']) / 2500.0)
+    probe = synth.smooth_probes(3, seed=1)[0:1]
+    for mode in ('copy', 'mean', 'product', 'argmax', 'argmax_product', 'percentile_argmax'):
+        for k in (7, 29):
+            with pytest.warns(UserWarning):
+                m = wb.layerwise_contrastive_ebp(probe, 0, 1, k_layer=k, mode=mode, percentile=20)
+            assert rel_err(m, R['lc_%s_%d' % (mode, k)]) < tol, (mode, k)
+        sweep = wb.layerwise_contrastive_ebp_sweep(probe, 0, 1, [7, 29], mode=mode, percentile=20)
+        assert rel_err(sweep[1], R['lc_%s_29' % mode]) < tol and rel_err(sweep[0], R['lc_%s_7' % mode]) < tol
+    for k in (3, 15, 29, 46, 57):
+        m = wb.layerwise_ebp(probe, k_layer=k, mode='argmax', k_poschannel=0, mwp=True)
+        assert rel_err(m, R['lw_argmax_%d' % k]) < tol, k
+    assert rel_err(wb.layerwise_ebp(probe, k_layer=-2), R['lw_argmax_57']) < tol                    # defaults: argmax, mwp
+    for pct in (0, 50, 80, 100):
+        t = wb.truncated_contrastive_ebp(probe, 0, 1, percentile=pct)
+        ref = R['trunc_pct%d' % pct]
+        assert np.abs(t - ref).max() < 1e-4
+        assert rel_err(t, ref) < 10 * tol if ref.max() > 0 else not t.any(), pct
+
+
+def test_other_modes_emulated():
+    _check_other_modes(False, 2e-3)
+
+
 def test_layer_sweep_emulated():
     _check_layer_sweep(False, 2e-3)
 
