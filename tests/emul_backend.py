@@ -67,9 +67,12 @@ def _wpos(B):
 class EmulBackend(object):
     name = 'emul'
 
-    def __init__(self, eps=EPS, impl_name='fp32'):
+    def __init__(self, eps=EPS, impl_name='fp32', bwd_single_pass=False):
         self.eps = eps
         self.impl_name = impl_name      # which weight packing the engine should build (the arithmetic here is fp32)
+        # kernels.HYBRID_IMPLS['tf32x3b1']: the W+ dgrads as ONE TF32 pass - the tensor core truncates the fp32 activation
+        # operand to TF32 (tools/trunc_probe.py) and multiplies the hi weight plane
+        self.bwd_single_pass = bwd_single_pass
 
     # ------------------------------------------------------------ forward
     def stem_fwd(self, x, stem, o, mp, mp_arg=None):
@@ -144,6 +147,8 @@ class EmulBackend(object):
 
     def _dgrad(self, y, Bd, R, signed=False):
         """y [J,H,W,Cout] -> [J*H*W, Cin]"""
+        if self.bwd_single_pass and not signed:
+            y = (y.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
         return im2col_nhwc(y, R, R, R // 2) @ (_w(Bd) if signed else _wpos(Bd)).t()
 
     def dgrad_mid(self, y, L, o, xr, bn, mode, y_out):

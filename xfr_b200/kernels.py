@@ -15,6 +15,10 @@ LIB_PATH = os.path.join(HERE, 'libxfr_b200.so')
 
 IMPL_FP32, IMPL_TF32X3, IMPL_TF32, IMPL_TF32X3_FULL = 0, 1, 2, 3
 IMPLS = {'fp32': IMPL_FP32, 'tf32x3': IMPL_TF32X3, 'tf32': IMPL_TF32, 'tf32x3full': IMPL_TF32X3_FULL}
+# Hybrid plans: name -> (forward / signed GEMMs, W+ dgrads of the EBP backward).  'tf32x3b1' keeps the split-TF32 forward (signed
+# weights decide the ReLU masks) and runs the W+ dgrads - sums of non-negative products, no cancellation - as ONE TF32 pass over
+# plane 0 (= rna_tf32(W+)) of the same weight packs.  Opt-in: its parity has to be measured on a B200 before it may become a default.
+HYBRID_IMPLS = {'tf32x3b1': ('tf32x3', 'tf32')}
 
 _P = ctypes.c_void_p
 _I = ctypes.c_int
@@ -106,10 +110,15 @@ class CudaBackend(object):
             if not self.lib.xfrb_device_ok():
                 raise RuntimeError('xfr_b200: kernels are built for sm_100a only; device is %s'
                                    % torch.cuda.get_device_name(self.device))
+        bwd = None
+        if isinstance(impl, str) and impl in HYBRID_IMPLS:
+            impl, bwd = HYBRID_IMPLS[impl]
         self.impl = IMPLS[impl] if isinstance(impl, str) else int(impl)
-        self.impl_name = {v: k for k, v in IMPLS.items()}[self.impl]
-        if not self.lib.xfrb_impl_available(self.impl):
-            raise NotImplementedError('xfr_b200: GEMM implementation %r is not compiled into %s' % (impl, LIB_PATH))
+        self.impl_name = {v: k for k, v in IMPLS.items()}[self.impl]      # also names the weight packing the engine builds
+        self.bwd_impl = self.impl if bwd is None else IMPLS[bwd]          # W+ dgrads of the EBP backward (MID / JOIN / plain)
+        for i in (self.impl, self.bwd_impl):
+            if not self.lib.xfrb_impl_available(i):
+                raise NotImplementedError('xfr_b200: GEMM implementation %r is not compiled into %s' % (impl, LIB_PATH))
         self.eps = float(eps)
         self._scratch = {}
         self.launches = 0
@@ -167,12 +176,12 @@ class CudaBackend(object):
     def dgrad_mid(self, y, L, o, xr, bn, mode, y_out):
         J, H, W, Cout = y.shape
         self._check(self.lib.xfrb_dgrad_mid(_ptr(y), _ptr(L.Bd), _ptr(o), _ptr(xr), _ptr(bn), _ptr(y_out), J,
-                                            o.shape[0], H, W, L.cin, Cout, L.R, mode, self.eps, self.impl, self._st()))
+                                            o.shape[0], H, W, L.cin, Cout, L.R, mode, self.eps, self.bwd_impl, self._st()))
 
     def dgrad_plain(self, y, L, z_out, signed=False, accumulate=False):
         J, H, W, Cout = y.shape
         B = L.signed_dgrad() if signed else L.Bd
-        impl = IMPL_TF32X3_FULL if (signed and self.impl == IMPL_TF32X3) else self.impl     # signed weights: all three passes
+        impl = (IMPL_TF32X3_FULL if self.impl == IMPL_TF32X3 else self.impl) if signed else self.bwd_impl   # signed: all three passes
         self._check(self.lib.xfrb_dgrad_plain(_ptr(y), _ptr(B), _ptr(z_out), J, H, W, L.cin, Cout, L.R,
                                               1 if accumulate else 0, impl, self._st()))
 
@@ -181,7 +190,7 @@ class CudaBackend(object):
         self._check(self.lib.xfrb_dgrad_join(_ptr(y1), _ptr(L.Bd), _ptr(g_res), _ptr(out), _ptr(o3), _ptr(xr3),
                                              _ptr(bn3), _ptr(res), 0 if res is None else res.shape[-1], _ptr(g_out),
                                              _ptr(y3_out), J, out.shape[0], H, W, L.cin, Cout, hooks, mode, self.eps,
-                                             self.impl, self._st()))
+                                             self.bwd_impl, self._st()))
 
     def join(self, zmain, up, gres_lo, k, out, o3, xr3, bn3, res, hooks, mode, g_out, y3_out):
         J, H, W, C = g_out.shape
