@@ -203,8 +203,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=256, help='triplets per GPU per step')
     ap.add_argument('--chunk', type=int, default=256, help='probes per engine sweep (256: 64 GB workspace, +4 %% over 128)')
-    ap.add_argument('--gemm', default='tf32x3', choices=['tf32x3', 'tf32x3full', 'tf32', 'fp32', 'tf32x3b1'],
-                    help="tf32x3 (default): the parity-grade plan; tf32x3b1: opt-in hybrid, one TF32 pass in the W+ dgrads (kernels.HYBRID_IMPLS)")
+    ap.add_argument('--gemm', default='tf32x3', choices=['tf32x3', 'tf32x3full', 'tf32', 'fp32', 'tf32x2f', 'tf32x3b1'],
+                    help="tf32x3 (default): the parity-grade plan; tf32x2f / tf32x3b1: opt-in hybrids (kernels.HYBRID_IMPLS)")
     ap.add_argument('--mode', default='affineonly_with_prior')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -316,6 +316,7 @@ def main():
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': {'tf32x3': 'f32 (split-TF32 tcgen05: 3 passes on signed weights, 2 on W+; fp32 accumulate)',
                   'tf32x3full': 'f32 (3xTF32 tcgen05 in every GEMM, fp32 accumulate)', 'tf32': 'tf32', 'fp32': 'f32',
+                  'tf32x2f': 'f32 (opt-in hybrid: two-pass split-TF32 forward with TF32-rounded weights, default W+ dgrads; fp32 accumulate)',
                   'tf32x3b1': 'f32 forward (split-TF32 tcgen05) / tf32 single-pass W+ dgrads (opt-in hybrid, not the parity-grade default)'}[args.gemm], 'data': 'synthetic',
         'config': {'workload': 'contrastive triplet EBP, ResNet-101, batch %d synthetic 224x224 per GPU (BASELINE configs[1])' % B,
                    'mode': args.mode, 'ebp_version': 6, 'chunk': args.chunk, 'gemm': args.gemm,

@@ -42,6 +42,8 @@ extern "C" {
 #define XFRB_IMPL_TF32X3 1
 #define XFRB_IMPL_TF32 2
 #define XFRB_IMPL_TF32X3_FULL 3
+#define XFRB_IMPL_TF32X2 4   /* two passes in every GEMM: activations exact (hi + lo), weights rounded to TF32 (plane 0 of the
+                              two-plane packs).  Opt-in (kernels.HYBRID_IMPLS 'tf32x2f' uses it for xfrb_conv_dual only) */
 
 int xfrb_version(void);
 const char* xfrb_last_error(void);

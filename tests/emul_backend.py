@@ -67,12 +67,14 @@ def _wpos(B):
 class EmulBackend(object):
     name = 'emul'
 
-    def __init__(self, eps=EPS, impl_name='fp32', bwd_single_pass=False):
+    def __init__(self, eps=EPS, impl_name='fp32', bwd_single_pass=False, fwd_two_pass=False):
         self.eps = eps
         self.impl_name = impl_name      # which weight packing the engine should build (the arithmetic here is fp32)
         # kernels.HYBRID_IMPLS['tf32x3b1']: the W+ dgrads as ONE TF32 pass - the tensor core truncates the fp32 activation
         # operand to TF32 (tools/trunc_probe.py) and multiplies the hi weight plane
         self.bwd_single_pass = bwd_single_pass
+        # kernels.HYBRID_IMPLS['tf32x2f']: the forward dual convs multiply the hi plane of the signed weights too (two passes)
+        self.fwd_two_pass = fwd_two_pass
 
     # ------------------------------------------------------------ forward
     def stem_fwd(self, x, stem, o, mp, mp_arg=None):
@@ -93,7 +95,7 @@ class EmulBackend(object):
     def conv_dual(self, inp, L, o, xr, act, res=None, relu_act=True):
         """o = conv(inp)+b ; xr = relu(conv_{W+}(inp)+b') ; act = relu(o*alpha+beta [+ res, zero-padded channels])."""
         A = im2col_nhwc(inp, L.R, L.S, L.R // 2)
-        t, _ = unpack_dual_cols(A @ _w(L.Bf).t() + L.bias, L.tn)
+        t, _ = unpack_dual_cols(A @ (_wpos(L.Bf) if self.fwd_two_pass else _w(L.Bf)).t() + L.bias, L.tn)
         _, p = unpack_dual_cols(A @ _wpos(L.Bf).t() + L.bias, L.tn)
         o.view(-1, L.cout).copy_(t)
         xr.view(-1, L.cout).copy_(relu(p))

@@ -1,5 +1,7 @@
 """GPU: end-to-end parity of the CUDA path with the reference's own outputs (tests/golden, produced by
 oracle/gen_golden.py from the unmodified reference) and with the oracle on fresh seeded inputs."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -146,3 +148,27 @@ def test_hooked_fc2_head_api():
     assert rel_err(m, G['ebp_mwp_awp_fc2head']) < 5e-3
     c = wb.contrastive_ebp(imgs[0:1], k_poschannel=0, k_negchannel=1)
     assert np.abs(c - G['cebp_awp_fc2head']).max() < 1e-4
+
+
+# Opt-in plan kernels.HYBRID_IMPLS['tf32x2f'] (two-pass forward dual convs: signed weights rounded to TF32).  Estimated on the kernel
+# emulation only (tools/hybrid_parity_emul.py: <= 6e-6 max-abs, contrastive parity unchanged); written after the round's GPU budget
+# was spent, so this has not run on a B200 yet - skipped unless XFRB_RUN_UNVERIFIED=1 until it has (a kernel
+# instantiation that never ran must not be able to hang the suite).
+@pytest.mark.skipif(not os.environ.get('XFRB_RUN_UNVERIFIED'), reason='not yet run on a B200 (added after the GPU budget of round 1 '
+                    'was spent): set XFRB_RUN_UNVERIFIED=1 to run it, under a timeout')
+@pytest.mark.parametrize('layers', [L1111, L101])
+def test_two_pass_forward_plan_vs_reference(layers):
+    G = golden(layers)
+    eng, dev = _engine(layers, 'tf32x2f')
+    x, W2, _ = golden_inputs(G)
+    x, W2 = x.to(dev), W2.to(dev)
+    P1 = torch.zeros(2, 2, device=dev)
+    P1[:, 0] = 1
+    s = eng.ebp(x, P1, W2).cpu().numpy()
+    c = eng.contrastive(x, W2).cpu().numpy()
+    t = eng.contrastive(x, W2, percentile=20).cpu().numpy()
+    for i, pname in enumerate(('smooth', 'noise')):
+        assert rel_err(s[i], G['ebp_awp_%s' % pname]) < 1e-2                     # emulation: 3e-3
+        for got, key in ((c, 'cebp_awp_%s'), (t, 'tcebp20_awp_%s')):
+            assert np.abs(got[i] - G[key % pname]).max() < 1e-4                   # north-star bar (emulation: 6e-6)
+            assert rel_err(got[i], G[key % pname]) < 5e-2

@@ -75,9 +75,10 @@ def test_jobs_vs_reference_emulated():
 
 # On the GPU the same outputs are pinned transitively: test_batch_matches_per_job_gpu ties the batched front end to the per-job flow
 # on the CUDA kernels, tests/test_gpu_parity.py ties that flow to the reference's outputs.  The direct comparison below was written
-# after the round's GPU budget was spent and has not run on a B200 yet: non-strict xfail until it has (XPASS = it holds).
+# after the round's GPU budget was spent and has not run on a B200 yet: skipped unless XFRB_RUN_UNVERIFIED=1 until it has.
 @pytest.mark.gpu
-@pytest.mark.xfail(reason='not yet run on a B200 (added after the GPU budget of round 1 was spent)', strict=False)
+@pytest.mark.skipif(not os.environ.get('XFRB_RUN_UNVERIFIED'), reason='not yet run on a B200 (added after the GPU budget of round 1 '
+                    'was spent): set XFRB_RUN_UNVERIFIED=1 to run it, under a timeout')
 def test_jobs_vs_reference_gpu():
     # tolerances of tests/test_gpu_parity.py: contrastive maps are cancellation-amplified (split-TF32 vs fp32), 1e-4 max-abs is the bar
     _check_jobs_vs_reference(True, 5e-2, 1e-2)

@@ -1,5 +1,7 @@
 """layerwise_ebp / layerwise_contrastive_ebp / weighted_subtree_ebp through the drop-in Whitebox API against the
 reference's outputs (tests/golden).  CPU: the host logic over the kernel emulation; GPU: the CUDA kernels."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -156,9 +158,10 @@ def test_layer_sweep_emulated():
 
 
 # Written after the round's GPU budget was spent: the sweep composes kernels the other GPU tests cover (row-indexed tensor
-# priors, P recording), but this test itself has not run on a B200 yet - non-strict xfail until it has (XPASS = it holds).
+# priors, P recording), but this test itself has not run on a B200 yet - skipped unless XFRB_RUN_UNVERIFIED=1 until it has.
 @pytest.mark.gpu
-@pytest.mark.xfail(reason='not yet run on a B200 (added after the GPU budget of round 1 was spent)', strict=False)
+@pytest.mark.skipif(not os.environ.get('XFRB_RUN_UNVERIFIED'), reason='not yet run on a B200 (added after the GPU budget of round 1 '
+                    'was spent): set XFRB_RUN_UNVERIFIED=1 to run it, under a timeout')
 def test_layer_sweep_gpu():
     _check_layer_sweep(True, 2e-2)
 

@@ -1,7 +1,8 @@
-"""CPU estimate of what the opt-in hybrid plan 'tf32x3b1' (kernels.HYBRID_IMPLS: split-TF32 forward, ONE TF32 pass in the
-W+ dgrads of the EBP backward) costs in parity, before GPU time is spent on it: the torch emulation of the kernel set
-(tests/emul_backend.py) with the dgrads' activation operand truncated to TF32 and the hi weight plane, against the
-reference's outputs (tests/golden).  Prints max-abs and max-abs / max(ref) per map for both plans."""
+"""CPU estimate of what the opt-in hybrid plans of kernels.HYBRID_IMPLS cost in parity, before GPU time is spent on them: the
+torch emulation of the kernel set (tests/emul_backend.py) against the reference's outputs (tests/golden).
+  'tf32x2f'   two-pass forward dual convs: the signed weights rounded to TF32 (hi plane), activations exact
+  'tf32x3b1'  ONE TF32 pass in the W+ dgrads: activation operand truncated to TF32 (as the tensor core does), hi weight plane
+Prints max-abs and max-abs / max(ref) per map for the default and both plans."""
 import os
 import sys
 
@@ -20,8 +21,8 @@ for layers in (L1111, L101):
     x, W2, _ = golden_inputs(G)
     P1 = torch.zeros(2, 2)
     P1[:, 0] = 1
-    for single in (False, True):
-        eng = StResnetEngine(synth.stresnet_state_dict(0, layers, 2), EmulBackend(impl_name='tf32x3', bwd_single_pass=single), layers)
+    for plan, kw in (('tf32x3 (default)', {}), ('tf32x2f', {'fwd_two_pass': True}), ('tf32x3b1', {'bwd_single_pass': True})):
+        eng = StResnetEngine(synth.stresnet_state_dict(0, layers, 2), EmulBackend(impl_name='tf32x3', **kw), layers)
         s = eng.ebp(x, P1, W2).clone().numpy()
         c = eng.contrastive(x, W2).clone().numpy()
         t = eng.contrastive(x, W2, percentile=20).clone().numpy()
@@ -31,6 +32,6 @@ for layers in (L1111, L101):
                 if key % p in G.files:
                     ref = G[key % p]
                     rows.append('%s/%s max-abs %.2e rel %.2e' % (name, p, np.abs(got[i] - ref).max(), rel_err(got[i], ref)))
-        print('layers %s  W+ dgrads %s:' % (layers, 'ONE TF32 pass (tf32x3b1)' if single else 'two passes (tf32x3, default)'))
+        print('layers %s  plan %s:' % (layers, plan))
         for r in rows:
             print('    ' + r)

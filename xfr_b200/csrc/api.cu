@@ -63,6 +63,7 @@ static cudaError_t run_gemm(const float* A, const float* B, const ConvGeom& g, c
     int split;
     if (impl == XFRB_IMPL_TF32) split = 0;
     else if (impl == XFRB_IMPL_TF32X3_FULL) split = 1;
+    else if (impl == XFRB_IMPL_TF32X2) split = 2;
     else if (impl == XFRB_IMPL_TF32X3) split = ep.kind == EPI_FWD_DUAL ? 3 : (ep.kind == EPI_MID || ep.kind == EPI_JOIN || positive_weights) ? 2 : 1;
     else return cudaErrorInvalidValue;
     return launch_conv_tc(A, B, g, ep, split, tn, st);
@@ -86,7 +87,8 @@ int xfrb_device_ok(void) {
 
 int xfrb_impl_available(int impl) {
     if (impl == XFRB_IMPL_FP32) return 1;
-    if (impl == XFRB_IMPL_TF32X3 || impl == XFRB_IMPL_TF32 || impl == XFRB_IMPL_TF32X3_FULL) return conv_tc_available() ? 1 : 0;
+    if (impl == XFRB_IMPL_TF32X3 || impl == XFRB_IMPL_TF32 || impl == XFRB_IMPL_TF32X3_FULL || impl == XFRB_IMPL_TF32X2)
+        return conv_tc_available() ? 1 : 0;
     return 0;
 }
 

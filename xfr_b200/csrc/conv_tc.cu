@@ -28,6 +28,8 @@
 //   2  W+ GEMMs (non-negative weights and activations, no cancellation): A_hi*B_hi + A_lo*B_hi only, i.e. the exact
 //      product with relu(W) rounded to TF32; the lo weight plane is never loaded.  Using the same rounded W+ for the X of
 //      the forward twin and for the dgrad keeps excitation backprop mass-conserving.
+//      With the dual forward pack (opt-in plan XFRB_IMPL_TF32X2) the signed W half is rounded to TF32 as well: the forward is
+//      shared by the mate and the non-mate sweep, so its weight rounding cancels in the contrastive map (tools/hybrid_parity_emul.py).
 //   3  dual forward pack [W rows | relu(W) rows]: A_hi*B_hi + A_lo*B_hi over the whole tile, A_hi*B_lo over the W half only
 //
 // PAIR (clusters of two CTAs working on two consecutive m-tiles of the same n-tile; all variants are bit-identical):
@@ -1041,6 +1043,7 @@ cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, c
     if (ep.kind == EPI_FWD_DUAL) {                                                                       \
         if (split == 0) return launch_cfg<BN_, 0, EPI_FWD_DUAL>(tmA, tmB, tmBlo, g, ep, st);              \
         if (split == 1) return launch_cfg<BN_, 1, EPI_FWD_DUAL>(tmA, tmB, tmBlo, g, ep, st);              \
+        if (split == 2) return launch_cfg<BN_, 2, EPI_FWD_DUAL>(tmA, tmB, tmBlo, g, ep, st);              \
         return launch_cfg<BN_, 3, EPI_FWD_DUAL>(tmA, tmB, tmBlo, g, ep, st);                              \
     }                                                                                                    \
     if (split == 0) { XFRB_TC_KINDS(BN_, 0) }                                                            \
