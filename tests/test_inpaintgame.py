@@ -312,3 +312,33 @@ def test_twin_blends_kernel_bit_exact():
             be.twin_blends(up(o), up(p), None, None, up(mk), out[:4], mask_f32=(dt == np.float32))
             want = ((1.0 - mk[:, None]) * o[None] + mk[:, None] * p[None]).astype(np.float32)
             assert np.array_equal(out[:4].cpu().numpy(), want.transpose(0, 2, 3, 1)), (C, dt)
+
+
+def test_scoring_lightcnn_one_channel_emulated():
+    """The 1-channel path of the scoring (Light-CNN images are [1,128,128], inpainting_game.py:110-113): device blends + forward
+    sweep against the numpy expression of inpainting_game.py:124-146 evaluated blend by blend on the same plugin."""
+    from emul_backend import EmulBackend
+    from xfr_b200.lightcnn import LightCNNEngine
+
+    class _EmulLightCNN(whitebox.WhiteboxLightCNN):
+        def _device(self):
+            return torch.device('cpu')
+
+        def engine(self, with_bias=False):
+            if self._engine is None:
+                self._engine = LightCNNEngine(self._sd, EmulBackend(), with_bias=with_bias)
+            return self._engine
+
+    snet = whitebox.Whitebox(_EmulLightCNN(synth.lightcnn_state_dict(0, 2)))
+    rng = np.random.RandomState(5)
+    orig, inp = rng.rand(1, 128, 128).astype(np.float32), rng.rand(1, 128, 128).astype(np.float32)
+    smap = rng.rand(128, 128) ** 3
+    pct = np.array([0, 10, 35, 70, 100])
+    gal_o, gal_p = snet.embeddings([orig]), snet.embeddings([inp])
+    cls, pg, pr = IG.classified_as_inpainted_twin(snet, orig, inp, gal_o, gal_p, smap, 'percent-density', percentiles=pct, seed=4)
+    masks = IG.create_threshold_masks(smap, 'percent-density', percentiles=pct, seed=4)[:, np.newaxis]
+    blends = (1.0 - masks) * orig.astype(np.float64)[np.newaxis] + masks * inp.astype(np.float64)[np.newaxis]
+    emb = snet.embeddings(blends)
+    emb = emb / np.linalg.norm(emb, axis=1, keepdims=True)
+    assert np.abs(pr - np.linalg.norm(emb - gal_o, axis=1)).max() < 1e-6 and np.abs(pg - np.linalg.norm(emb - gal_p, axis=1)).max() < 1e-6
+    assert not cls[0] and cls[-1] and pr[0] < 1e-6 and pg[-1] < 1e-6           # 0 %: the original probe; 100 %: the inpainted twin
