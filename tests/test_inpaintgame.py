@@ -342,3 +342,28 @@ def test_scoring_lightcnn_one_channel_emulated():
     emb = emb / np.linalg.norm(emb, axis=1, keepdims=True)
     assert np.abs(pr - np.linalg.norm(emb - gal_o, axis=1)).max() < 1e-6 and np.abs(pg - np.linalg.norm(emb - gal_p, axis=1)).max() < 1e-6
     assert not cls[0] and cls[-1] and pr[0] < 1e-6 and pg[-1] < 1e-6           # 0 %: the original probe; 100 %: the inpainted twin
+
+
+def test_scoring_batch_matches_per_job_emulated(monkeypatch):
+    """classified_as_inpainted_twin_batch == classified_as_inpainted_twin job by job (blends of several jobs in one sweep,
+    sweeps cut across jobs)."""
+    from inpaintgame_fixture import scoring_fixture
+    F, G = scoring_fixture(), _gold()
+    snet = whitebox.Whitebox(_net(L1111, False))
+    pct = np.array([0, 20, 50, 80, 100])
+    rng = np.random.RandomState(9)
+    smap2 = (F['smap'] * (0.5 + rng.rand(224, 224))).astype(np.float32)
+    jobs = [(F['orig'], F['inp'], G['gal_orig'], G['gal_inp'], F['smap']),
+            (F['inp'], F['orig'], G['gal_inp'], G['gal_orig'], smap2),
+            (torch.from_numpy(F['orig']), F['inp'], G['gal_orig'], G['gal_inp'], smap2)]
+    want = [IG.classified_as_inpainted_twin(snet, j[0], j[1], j[2], j[3], j[4], 'percent-density', percentiles=pct, seed=s)
+            for j, s in zip(jobs, (0, 1, 2))]
+    monkeypatch.setattr(whitebox, '_CHUNK', 4)                    # 15 blends in sweeps of 4: sweeps straddle the jobs
+    got = IG.classified_as_inpainted_twin_batch(snet, jobs, 'percent-density', percentiles=pct, seed=[0, 1, 2])
+    assert len(got) == 3
+    for (c0, g0, r0), (c1, g1, r1) in zip(want, got):
+        assert np.array_equal(c0, c1) and np.abs(g0 - g1).max() < 1e-6 and np.abs(r0 - r1).max() < 1e-6
+    assert IG.classified_as_inpainted_twin_batch(snet, [], 'percent-density', percentiles=pct) == []
+    with pytest.raises(ValueError):
+        IG.classified_as_inpainted_twin_batch(snet, jobs[:1] + [(np.zeros((1, 128, 128)),) * 2 + jobs[0][2:4] + (np.ones((128, 128)),)],
+                                              'percent-density', percentiles=pct)

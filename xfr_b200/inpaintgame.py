@@ -236,23 +236,32 @@ def _network_format(imT):
     return np.ascontiguousarray(a, dtype=np.float64)         # inpainting_game.py:124-125
 
 
-def twin_blend_embeddings(snet, original_imT, inpaint_imT, value=None, thr=None, masks=None, mask_f32=False):
-    """Device side of the scoring: K blends -> forward sweep -> [K, D] embeddings, normalised as Whitebox.embeddings does
-    (whitebox.py:779-783).  snet: xfr_b200.whitebox.Whitebox."""
+def _twin_blends_into(snet, blends, original_imT, inpaint_imT, value=None, thr=None, masks=None, mask_f32=False):
+    """Enqueue xfrb_twin_blends for one job into `blends` [K,H,W,C] (a slice of the sweep's input buffer)."""
     net = snet.net
-    eng = net.engine()
     dev = net._device()
     o, p = _network_format(original_imT), _network_format(inpaint_imT)
     if o.shape != p.shape:
         raise ValueError('original / inpainted image shapes differ: %s vs %s' % (o.shape, p.shape))
-    C, H, W = o.shape
+    if tuple(blends.shape[1:]) != (o.shape[1], o.shape[2], o.shape[0]):
+        raise ValueError('images of one batch must share their shape: %s vs blends %s' % (o.shape, tuple(blends.shape)))
     up = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
-    K = (masks if masks is not None else thr).shape[0]
-    blends = torch.empty(K, H, W, C, device=dev, dtype=torch.float32)
-    eng.be.twin_blends(up(o), up(p), up(value), up(thr), up(masks), blends, mask_f32)
-    embeds = net.encode_nhwc(blends).detach().cpu().numpy()
+    net.engine().be.twin_blends(up(o), up(p), up(value), up(thr), up(masks), blends, mask_f32)
+
+
+def _normalised(embeds):
     flat = embeds.reshape((embeds.shape[0], -1))
     return (flat / np.linalg.norm(flat, axis=1, keepdims=True)).reshape(embeds.shape)
+
+
+def twin_blend_embeddings(snet, original_imT, inpaint_imT, value=None, thr=None, masks=None, mask_f32=False):
+    """Device side of the scoring: K blends -> forward sweep -> [K, D] embeddings, normalised as Whitebox.embeddings does
+    (whitebox.py:779-783).  snet: xfr_b200.whitebox.Whitebox."""
+    C, H, W = _network_format(original_imT).shape
+    K = (masks if masks is not None else thr).shape[0]
+    blends = torch.empty(K, H, W, C, device=snet.net._device(), dtype=torch.float32)
+    _twin_blends_into(snet, blends, original_imT, inpaint_imT, value, thr, masks, mask_f32)
+    return _normalised(snet.net.encode_nhwc(blends).detach().cpu().numpy())
 
 
 def classified_as_inpainted_twin(snet, original_imT, inpaint_imT, original_gal_embed, inpaint_gal_embed, saliency_map,
@@ -284,3 +293,32 @@ def classified_as_inpainted_twin(snet, original_imT, inpaint_imT, original_gal_e
     cm = masks[:, np.newaxis] if o.shape[0] == 1 else np.repeat(masks[:, np.newaxis], 3, axis=1)      # dtype kept: see mask_f32
     blends = (1.0 - cm) * o[np.newaxis] + cm * p[np.newaxis]
     return classified_as_twin, pg_dist, pr_dist, blends, masks
+
+
+def classified_as_inpainted_twin_batch(snet, jobs, mask_threshold_method, include_zero_elements=True, percentiles=None,
+                                       thresholds=None, seed=None):
+    """Batched scoring: jobs = [(original_imT, inpaint_imT, original_gal_embed, inpaint_gal_embed, saliency_map), ...] with the
+    arguments of classified_as_inpainted_twin (hard masks; `seed` one value or one per job).  The K blends of every job go into
+    ONE device buffer and through the forward sweep together (full engine sweeps instead of one K-blend sweep per job); one
+    device-to-host copy of the [J*K, D] embeddings.  Returns [(classified_as_twin, pg_dist, pr_dist), ...] in job order."""
+    if not jobs:
+        return []
+    seeds = list(seed) if isinstance(seed, (list, tuple, np.ndarray)) else [seed] * len(jobs)
+    maps = [mask_value_map(j[4], mask_threshold_method, percentiles, thresholds, sd, include_zero_elements=include_zero_elements)
+            for j, sd in zip(jobs, seeds)]
+    K = maps[0][1].shape[0]
+    C, H, W = _network_format(jobs[0][0]).shape
+    blends = torch.empty(len(jobs) * K, H, W, C, device=snet.net._device(), dtype=torch.float32)
+    for i, (j, (value, thr)) in enumerate(zip(jobs, maps)):
+        _twin_blends_into(snet, blends[i * K:(i + 1) * K], j[0], j[1], value, thr)
+    embeds = snet.net.encode_nhwc(blends).detach().cpu().numpy()
+    out = []
+    for i, j in enumerate(jobs):
+        e = _normalised(embeds[i * K:(i + 1) * K])
+        e = e / np.linalg.norm(e, axis=1, keepdims=True)
+        pr_dist = np.linalg.norm(e - j[2], axis=1)
+        pg_dist = np.linalg.norm(e - j[3], axis=1)
+        cls = pg_dist < pr_dist
+        assert not cls[0]
+        out.append((cls, pg_dist, pr_dist))
+    return out
