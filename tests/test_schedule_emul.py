@@ -120,3 +120,26 @@ def test_hooked_fc2_head(layers):
         P, names, P2 = GenericSweep(eng).run(P1, W2, 'affineonly_with_prior', record=True, hooked_fc2=True)
         assert len(P) == len(G['P_kinds']) + 1 and names[0] == 'Linear'          # 379 vs 378 firings on the 101
         assert rel_err(P2.sum(-1)[0].numpy(), G['ebp_mwp_awp_fc2head']) < 1e-5
+
+
+@pytest.mark.parametrize('layers', [L1111, L101])
+def test_opt_in_plans_emulated(layers):
+    """The parity estimates DESIGN.md section 8 quotes for the opt-in plans of kernels.HYBRID_IMPLS, on the kernel emulation:
+    'tf32x2f' (signed forward weights rounded to TF32) keeps every map far inside the 1e-4 bar; 'tf32x3b1' (one TF32 pass in the
+    W+ dgrads) does not on the ill-conditioned ResNet-101 golden triplet."""
+    G = golden(layers)
+    x, W2, _ = golden_inputs(G)
+    sd = synth.stresnet_state_dict(0, layers, 2)
+    P1 = torch.zeros(2, 2)
+    P1[:, 0] = 1
+    eng = StResnetEngine(sd, EmulBackend(impl_name='tf32x3', fwd_two_pass=True), layers)
+    s = eng.ebp(x, P1, W2).clone().numpy()
+    c = eng.contrastive(x, W2).clone().numpy()
+    t = eng.contrastive(x, W2, percentile=20).clone().numpy()
+    for i, p in enumerate(('smooth', 'noise')):
+        assert rel_err(s[i], G['ebp_awp_%s' % p]) < 5e-3
+        assert np.abs(c[i] - G['cebp_awp_%s' % p]).max() < 1e-5 and np.abs(t[i] - G['tcebp20_awp_%s' % p]).max() < 1e-5
+    if layers == L101:
+        eng = StResnetEngine(sd, EmulBackend(impl_name='tf32x3', bwd_single_pass=True), layers)
+        c = eng.contrastive(x, W2).clone().numpy()
+        assert np.abs(c[0] - G['cebp_awp_smooth']).max() > 1e-4          # why that plan stays opt-in
