@@ -21,6 +21,8 @@
  *    weight is signed (true forward), two passes (activation split exactly, relu(W) rounded to TF32) for the W+ GEMMs,
  *    whose products are all non-negative; 2 = tcgen05 single-pass TF32; 3 = tcgen05 3xTF32 in every GEMM
  *    (xfrb_dgrad_plain with signed weights - the true-gradient sweep of weighted_subtree_ebp - must be called with 3);
+ *    4 = opt-in: two passes in every GEMM kind, the weight operand rounded to TF32 even where it is signed (XFRB_IMPL_TF32X2;
+ *    the host's 'tf32x2f' plan passes it to xfrb_conv_dual only);
  *  - weight operands (`Bf`, `Bd`, `B1`, `W1pT`) are K-major [rows][K] fp32.  For impl 1 they hold TWO planes
  *    [2][rows][K]: hi = rna_tf32(W) and lo = W - hi (the host does the 3xTF32 split of the static operand once,
  *    xfr_b200/packing.py); for impl 2 one plane of rna_tf32(W); for impl 0 one plane of W;
