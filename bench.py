@@ -337,7 +337,7 @@ def main():
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count()
-        n = 4
+        n = 40                                   # ~10 s of host work at the ~4 maps/s measured on the GPU box's 16 cores
         out['cpu_baseline'] = {'value': cpu_port(n, cores), 'unit': 'maps/s', 'cores': cores, 'kind': 'port',
                                'sample': '%d triplets of the same workload, batch 1, torch CPU fp32 restatement (oracle/)' % n}
     if rank == 0:
