@@ -367,3 +367,28 @@ def test_scoring_batch_matches_per_job_emulated(monkeypatch):
     with pytest.raises(ValueError):
         IG.classified_as_inpainted_twin_batch(snet, jobs[:1] + [(np.zeros((1, 128, 128)),) * 2 + jobs[0][2:4] + (np.ones((128, 128)),)],
                                               'percent-density', percentiles=pct)
+
+
+def test_front_end_lightcnn_emulated():
+    """The batched front end through the Light-CNN plugin (grayscale 128x128 network input, 128x128 maps, 256-d encodings)."""
+    from emul_backend import EmulBackend
+    from xfr_b200.lightcnn import LightCNNEngine
+
+    class _EmulLightCNN(whitebox.WhiteboxLightCNN):
+        def _device(self):
+            return torch.device('cpu')
+
+        def engine(self, with_bias=False):
+            if self._engine is None:
+                self._engine = LightCNNEngine(self._sd, EmulBackend(), with_bias=with_bias)
+            return self._engine
+
+    wb = whitebox.Whitebox(_EmulLightCNN(synth.lightcnn_state_dict(0, 2)))
+    jobs = _jobs()[:2]
+    got = IG.run_contrastive_triplet_ebp_batch(wb, jobs)
+    assert got.shape == (2, 128, 128) and got.dtype == np.float32
+    for j, g in zip(jobs, got):
+        want = _reference_flow(wb, *j, truncate_percent=None)
+        assert rel_err(g, want) < 1e-4 and abs(float(g.sum()) - 1.0) < 1e-3
+    rows = IG.mean_encodings(wb, [jobs[0][0]])
+    assert rows.shape == (1, 256)
