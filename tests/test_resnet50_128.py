@@ -162,3 +162,45 @@ def test_gpu_layerwise_and_weighted_subtree_vs_reference():
     assert np.allclose(P_sub, G['ws_scores'], rtol=1e-2)
     assert rel_err(P_img[-1], G['ws_first']) < 2e-2
     assert np.abs(smap - G['ws_smap']).max() < 1e-4 and rel_err(smap, G['ws_smap']) < 5e-2
+
+
+@needs_weights
+def test_inpaintgame_rows_emulated():
+    """SURVEY 8(f) rows 1 and 3 through the ResNet-50-128d plugin (un-normalised 128-d encodings, head on the wrapper) with the
+    REAL weights: batched front end == per-job flow, scoring == the numpy expression of inpainting_game.py:124-146."""
+    from xfr_b200 import inpaintgame as IG
+    from xfr_b200 import whitebox
+
+    class _EmulR50(whitebox.Whitebox_resnet50_128):
+        def _device(self):
+            return torch.device('cpu')
+
+        def engine(self, with_bias=False):
+            if self._engine is None:
+                self._engine = Resnet50_128Engine(self._sd, EmulBackend(), with_bias=with_bias)
+            return self._engine
+
+    sd, G, X = R50
+    wb = whitebox.Whitebox(_EmulR50(sd))
+    crops = {k: G['crop_' + k] for k in ('probe', 'mate', 'nonmate', 'demo')}           # 224x224x3 uint8
+    jobs = [([crops['mate']], [crops['nonmate']], crops['probe']), ([crops['mate'], crops['probe']], [crops['nonmate']], crops['demo'])]
+    got = IG.run_contrastive_triplet_ebp_batch(wb, jobs)
+    assert got.shape == (2, 112, 112)
+    # job 0 is the golden triplet up to the classifier scale: unit-norm rows / 2500 instead of the raw encodings
+    xm, xn = wb.encode(X['mate']), wb.encode(X['nonmate'])
+    wb.net.set_triplet_classifier((xm / torch.norm(xm)) / 2500.0, (xn / torch.norm(xn)) / 2500.0)
+    want = wb.contrastive_ebp(X['probe'], 0, 1)
+    assert rel_err(got[0], want) < 1e-4 and int(got[0].argmax()) == int(want.argmax())
+    # scoring: the probe turned into the non-mate, five percentiles
+    orig, inp = X['probe'][0].numpy(), X['nonmate'][0].numpy()
+    rng = np.random.RandomState(3)
+    smap = (got[0].repeat(2, 0).repeat(2, 1) + 1e-7 * rng.rand(224, 224)).astype(np.float32)
+    pct = np.array([0, 25, 50, 75, 100])
+    gal_o, gal_p = wb.embeddings([orig]), wb.embeddings([inp])
+    cls, pg, pr = IG.classified_as_inpainted_twin(wb, orig, inp, gal_o, gal_p, smap, 'percent-density', percentiles=pct, seed=0)
+    masks = IG.create_threshold_masks(smap, 'percent-density', percentiles=pct, seed=0)[:, np.newaxis]
+    blends = (1.0 - masks) * orig.astype(np.float64)[np.newaxis] + masks * inp.astype(np.float64)[np.newaxis]
+    emb = wb.embeddings(blends)
+    emb = emb / np.linalg.norm(emb, axis=1, keepdims=True)
+    assert np.abs(pr - np.linalg.norm(emb - gal_o, axis=1)).max() < 1e-5 and np.abs(pg - np.linalg.norm(emb - gal_p, axis=1)).max() < 1e-5
+    assert not cls[0] and cls[-1] and np.all(np.diff(pg) <= 1e-3)        # the more salient pixels go, the closer to the twin
