@@ -1,0 +1,1 @@
+"""Import shim (TEST INFRASTRUCTURE ONLY): see skimage/__init__.py."""

@@ -1,3 +1,4 @@
+"""Import shim (TEST INFRASTRUCTURE ONLY): see skimage/__init__.py."""
 import numpy as np
 
 
