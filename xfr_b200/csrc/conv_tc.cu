@@ -929,7 +929,6 @@ cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, c
     }
     if (cg.Cin % TC_BK != 0 || split < 0 || split > 3) return cudaErrorInvalidValue;
     if (split == 3 && ep.kind != EPI_FWD_DUAL) return cudaErrorInvalidValue;
-    if (split == 2 && ep.kind == EPI_FWD_DUAL) return cudaErrorInvalidValue;
     int BN;
     if (ep.kind == EPI_FWD_DUAL) {
         BN = tn;                                  // the dual pack fixes the tile width
@@ -978,10 +977,11 @@ cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, c
     // default hook mode (measured per launch: 331 -> 297 us and 370 -> 322 us).  The JOIN dgrads are epilogue-bound and lose
     // (623 -> 776 us as pairs); other hook modes keep the single-CTA kernels specialised per mode.
     const bool cta2 = cta2_enabled() && enough_pairs &&
-                      ((split == 3 && ep.kind == EPI_FWD_DUAL) || (split == 2 && ep.kind == EPI_MID && ep.mode == 0));
+                      (((split == 3 || split == 2) && ep.kind == EPI_FWD_DUAL) || (split == 2 && ep.kind == EPI_MID && ep.mode == 0));
     // multicast pairs: the product plans, for the default hook mode (other modes keep the single-CTA kernels whose hook chains
     // are specialised per mode)
     const bool mc = !cta2 && (split == 2 || split == 3) && mc_enabled() && enough_pairs &&
+                    !(split == 2 && ep.kind == EPI_FWD_DUAL) &&            // the two-pass forward plan has no multicast variant
                     (ep.kind == EPI_FWD_DUAL || ep.kind == EPI_PLAIN || ep.mode == 0);
     const bool half_boxes = cta2 || mc;
     {
@@ -1008,7 +1008,9 @@ cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& cg, c
     }
 #define XFRB_TC_PAIR(BN_)                                                                                \
     switch (ep.kind) {                                                                                   \
-        case EPI_FWD_DUAL: return launch_cfg2<BN_, 3, EPI_FWD_DUAL, 1>(tmA, tmB, tmBlo, g, ep, st);       \
+        case EPI_FWD_DUAL:                                                                               \
+            if (split == 2) return launch_cfg2<BN_, 2, EPI_FWD_DUAL, 1>(tmA, tmB, tmBlo, g, ep, st);      \
+            return launch_cfg2<BN_, 3, EPI_FWD_DUAL, 1>(tmA, tmB, tmBlo, g, ep, st);                      \
         case EPI_MID: return launch_cfg2<BN_, 2, EPI_MID, 1, 0>(tmA, tmB, tmBlo, g, ep, st);              \
         default: return cudaErrorInvalidValue;                                                           \
     }
