@@ -8,6 +8,8 @@ keep their names and arguments and a *_batch twin feeds N jobs through one sweep
     all mate / non-mate images of all jobs -> ONE batched encode -> per-job mean, L2-normalise (lines 57-69)
     -> Whitebox.net.set_triplet_classifiers(rows) -> Whitebox.contrastive_ebp_batch(probes)
 
+run_contrastive_triplet_ebp_sharded spreads the jobs over the ranks of a torchrun job (contiguous shards, one gather of maps).
+
 File discovery (the CSV / directory walk of generate_wb_smaps, lines 222-290) and the PNG overlay stay host glue of the
 caller: they are image I/O, not arithmetic.
 
@@ -16,6 +18,7 @@ signature.  The host turns the saliency map into ONE float64 value map + K thres
 sort and the cumulative sum of 50,176 doubles); the K (= 101) blends are built on the device by xfrb_twin_blends straight
 into the forward sweep's NHWC input (the reference materialises 101 float64 masks and 122 MB of float64 blends on the
 host), swept by the same conv kernels as the saliency path, and only the K x D embeddings come back.
+classified_as_inpainted_twin_batch puts the blends of several jobs through full engine sweeps.
 """
 import os
 
