@@ -106,7 +106,7 @@ def kernel_families(eng, step_fn):
             e0.record()
             _orig(*a, **k)
             e1.record()
-            rec.append((_name, e0, e1) + meta(_name, a))
+            rec.append((_name, e0, e1) + meta(_name, a) + (list(a[0].shape) + [a[1].cin, a[1].cout, a[1].R],))
         setattr(be, name, wrapped)
     try:
         step_fn(False, gather=False)          # rank 0 only: no collective in here
@@ -116,6 +116,11 @@ def kernel_families(eng, step_fn):
             delattr(be, name)
     hbm, _ = measured_peaks()
     tf32_peak = 0.5 * tensor_peak()
+    dump = os.environ.get('XFRB_BENCH_LAUNCHES')          # per-launch rows (name, A shape, us, bytes, flops) for roofline studies
+    if dump:
+        with open(dump, 'w') as f:
+            for r in rec:
+                f.write(json.dumps({'k': r[0], 'us': 1e3 * r[1].elapsed_time(r[2]), 'bytes': r[3], 'flops': r[4], 'shape': r[5]}) + '\n')
     out = []
     label = {'dgrad_join': 'W+ dgrad + JOIN hook chain (conv_tc_kernel<BN,2,JOIN>)', 'dgrad_mid': 'W+ dgrad + MID hook chain (conv_tc_kernel<BN,2,MID>)',
              'conv_dual': 'forward dual conv: o, xr, act (conv_tc_kernel<BN,3,FWD_DUAL>)'}
@@ -154,6 +159,36 @@ def cpu_port(n_triplets, threads):
     for i in range(1, n_triplets + 1):
         O.contrastive_ebp(sd, x[i:i + 1], W2[i:i + 1])
     return n_triplets / (time.time() - t0)
+
+
+def gpu_library_baseline(dev, n_triplets=64, batch=16, allow_tf32=False):
+    """SURVEY.md section 2a "the Blackwell kernel to beat": stock PyTorch eager (cuDNN / cuBLAS library kernels) running the
+    same algorithm - the oracle restatement, batched, one shared forward + mate / non-mate sweeps - on the same B200.
+    fp32 with TF32 off is the parity-grade setting; allow_tf32 shows what the library does with single-pass TF32.
+    Outside every timed region of the product; the host-side Gaussian post-filter is left out (it favours this arm)."""
+    from oracle import stresnet_oracle as O      # comparator leg only
+    from xfr_b200 import synth
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = bool(allow_tf32)
+    try:
+        sd = {k: v.to(dev) for k, v in synth.stresnet_state_dict(0).items()}
+        x = synth.synthetic_probes(batch, seed=1).to(dev)
+        g = torch.Generator().manual_seed(5)
+        W2 = (torch.randn(batch, 2, 512, generator=g) * 0.02).to(dev)
+        O.contrastive_mwp(sd, x, W2)                 # warm-up (cuDNN autotune, allocator)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(max(1, n_triplets // batch)):
+            O.contrastive_mwp(sd, x, W2)
+        e1.record()
+        torch.cuda.synchronize()
+        n = max(1, n_triplets // batch) * batch
+        return {'value': n / (e0.elapsed_time(e1) * 1e-3), 'unit': 'maps/s', 'kind': 'torch %s eager (cuDNN/cuBLAS), oracle restatement batched' % torch.__version__,
+                'batch': batch, 'triplets': n, 'precision': 'tf32 (library single pass)' if allow_tf32 else 'fp32 (TF32 off)'}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        torch.cuda.empty_cache()
 
 
 def run_reference(args, rank):
@@ -203,7 +238,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=256, help='triplets per GPU per step')
     ap.add_argument('--chunk', type=int, default=256, help='probes per engine sweep (256: 64 GB workspace, +4 %% over 128)')
-    ap.add_argument('--gemm', default='tf32x3', choices=['tf32x3', 'tf32x3full', 'tf32', 'fp32', 'tf32x2f', 'tf32x3b1'],
+    ap.add_argument('--gemm', default='tf32x3', choices=['tf32x3', 'tf32x3full', 'tf32', 'fp32', 'tf32x2f', 'tf32x3b1', 'bf16x2'],
                     help="tf32x3 (default): the parity-grade plan; tf32x2f / tf32x3b1: opt-in hybrids (kernels.HYBRID_IMPLS)")
     ap.add_argument('--mode', default='affineonly_with_prior')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
@@ -317,6 +352,7 @@ def main():
         'dtype': {'tf32x3': 'f32 (split-TF32 tcgen05: 3 passes on signed weights, 2 on W+; fp32 accumulate)',
                   'tf32x3full': 'f32 (3xTF32 tcgen05 in every GEMM, fp32 accumulate)', 'tf32': 'tf32', 'fp32': 'f32',
                   'tf32x2f': 'f32 (opt-in hybrid: two-pass split-TF32 forward with TF32-rounded weights, default W+ dgrads; fp32 accumulate)',
+                  'bf16x2': 'bf16 terms on tcgen05 kind::f16 (activations / gradients 2 terms = 16 bits, relu(W) 1, signed W 2), fp32 accumulate and fp32 epilogues',
                   'tf32x3b1': 'f32 forward (split-TF32 tcgen05) / tf32 single-pass W+ dgrads (opt-in hybrid, not the parity-grade default)'}[args.gemm], 'data': 'synthetic',
         'config': {'workload': 'contrastive triplet EBP, ResNet-101, batch %d synthetic 224x224 per GPU (BASELINE configs[1])' % B,
                    'mode': args.mode, 'ebp_version': 6, 'chunk': args.chunk, 'gemm': args.gemm,

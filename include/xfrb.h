@@ -46,6 +46,13 @@ extern "C" {
 #define XFRB_IMPL_TF32X3_FULL 3
 #define XFRB_IMPL_TF32X2 4   /* two passes in every GEMM: activations exact (hi + lo), weights rounded to TF32 (plane 0 of the
                               two-plane packs).  Opt-in (kernels.HYBRID_IMPLS 'tf32x2f' uses it for xfrb_conv_dual only) */
+#define XFRB_IMPL_BF16X2 5   /* the bf16x2 plan of the fused sweep (xfrb_conv_dual, xfrb_dgrad_mid / _join / _plain): tcgen05
+                              kind::f16 with bf16 terms - activations / gradients 2 terms, relu(W) 1 term, signed W 2 terms.
+                              The activation operand (`inp`, `y`, `y1`) and every output that feeds the next GEMM (`act`,
+                              `y_out`, `y3_out`) are then PAIR tensors: each row of C values is stored as [C bf16 hi | C bf16 lo]
+                              (hi = bf16(x), lo = bf16(x - hi); the same 4*C bytes per row as fp32; xfrb_to_pair converts).
+                              Weight operands are bf16 K-major: `Bd` one plane of relu(W) [rows][K]; `Bf` two planes
+                              [2][rows][K] (hi, lo) of the dual pack.  Channel counts of the A operand must be multiples of 64 */
 
 int xfrb_version(void);
 const char* xfrb_last_error(void);
@@ -75,6 +82,10 @@ double xfrb_tile_geometry(int H, int W, int Nimg, int* bh, int* bimg);
 int xfrb_stem_fwd(const float* x, const float* W, const float* b, const float* bn,
                   float* o, float* mp, unsigned char* mp_arg, int N, int pool_pad, void* stream);
 
+/* fp32 [rows,C] -> pair tensor [rows][C bf16 hi | C bf16 lo] (inverse = 0), or back to fp32 hi + lo (inverse = 1); C % 4 == 0.
+ * The bf16x2 plan's GEMM operand format (XFRB_IMPL_BF16X2); used where a non-GEMM kernel produces a GEMM input. */
+int xfrb_to_pair(const float* in, float* out, long long rows, int C, int inverse, void* stream);
+
 /* u[N,H,W,C] -> out[N,H/2,W/2,C]: even pixels (input of a stride-2 1x1 conv, resnet.py:116) */
 int xfrb_subsample2(const float* u, float* out, int N, int H, int W, int C, void* stream);
 /* u[N,H,W,C] -> out[N,H/2,W/2,C]: AvgPool2d(2,2) of the shortcut (resnet.py:211) */
@@ -85,9 +96,11 @@ int xfrb_avgpool2(const float* u, float* out, int N, int H, int W, int C, void* 
  *   xr  = relu(conv_relu(W)(inp) + b')        [N,H,W,Cout]   (X of the BatchNorm hook)
  *   act = relu(o*alpha + beta + res)          [N,H,W,Cout]   (res: [N,H,W,res_c], zero beyond res_c; may be NULL)
  * Bf/bias: dual pack of xfr_b200/packing.py (tile width tn).  R = 1 or 3, stride 1, pad R/2.
- * relu_act = 0 emits act = o*alpha + beta + res without the ReLU (conv + BN projection shortcut, resnet50_128.py:185-187). */
+ * relu_act = 0 emits act = o*alpha + beta + res without the ReLU (conv + BN projection shortcut, resnet50_128.py:185-187).
+ * impl XFRB_IMPL_BF16X2: inp and act are pair tensors (act may be NULL) and act_f32 (may be NULL) receives act in fp32 as
+ * well (block outputs are read again by epilogues: residual, hooks); every other impl: act_f32 must be NULL. */
 int xfrb_conv_dual(const float* inp, const float* Bf, const float* bias, const float* bn,
-                   const float* res, int res_c, float* o, float* xr, float* act,
+                   const float* res, int res_c, float* o, float* xr, float* act, float* act_f32,
                    int N, int H, int W, int Cin, int Cout, int R, int tn, int relu_act, int impl, void* stream);
 
 /* avgpool7 -> fc1 (+ the W+ twin) -> L2 normalise (resnet.py:235-252).
@@ -136,11 +149,12 @@ int xfrb_dgrad_join(const float* y1, const float* Bd, const float* g_res,
 
 /* Same boundary without the GEMM (head -> last block, and below a downsample block):
  * z[j,h,w,c] = zmain[j,h/up,w/up,c] on pixels divisible by `up` (else 0)
- *            + gres_lo[j,h/k,w/k,c]/(k*k) for c < gres_c   (AvgPool2d(k) backward). */
+ *            + gres_lo[j,h/k,w/k,c]/(k*k) for c < gres_c   (AvgPool2d(k) backward).
+ * y3_pair != 0: y3_out is written as a pair tensor (the A operand of the next dgrad under XFRB_IMPL_BF16X2). */
 int xfrb_join(const float* zmain, int up, const float* gres_lo, int gres_c, int k,
               const float* out, const float* o3, const float* xr3, const float* bn3,
               const float* res, int res_c, float* g_out, float* y3_out,
-              int J, int N, int H, int W, int C, int hooks, int mode, float eps, void* stream);
+              int J, int N, int H, int W, int C, int hooks, int mode, float eps, int y3_pair, void* stream);
 
 /* Shortcut branch of a downsample block up to AvgPool backward: Add slot-1 hook, channel
  * slice, ConcatChannels hook (resnet.py:152-157).  g [J,H,W,C], ap [N,H,W,Cr] -> gres_lo [J,H,W,Cr]. */

@@ -301,14 +301,14 @@ def mwp_to_saliency_uint8(P, eps=1e-16, blur_radius=2):
 def ebp(sd, x, Pn, fc2=None, mwp=False, **kw):
     """Whitebox.ebp (whitebox.py:482-504) -> [N,112,112] float32."""
     P, _ = ebp_mwp(sd, x, Pn, fc2, stop_at_stem=True, **kw)
-    m = P[-2].sum(1).numpy().astype(np.float32)
+    m = P[-2].sum(1).cpu().numpy().astype(np.float32)
     if mwp:
         return m
     return np.stack([mwp_to_saliency(mi, kw.get('eps', 1e-16)) for mi in m])
 
 
-def _onehot(n, c, k):
-    p = torch.zeros(n, c)
+def _onehot(n, c, k, device=None):
+    p = torch.zeros(n, c, device=device)
     p[:, k] = 1.0
     return p
 
@@ -318,8 +318,8 @@ def contrastive_mwp(sd, x, fc2, k_pos=0, k_neg=1, percentile=None, num_classes=2
     (whitebox.py:506-527, 529-558).  Normalisation and percentile mask are per sample."""
     N = x.shape[0]
     T = forward(sd, x, kw.get('layers', LAYERS101))
-    Pm, _ = ebp_mwp(sd, x, _onehot(N, num_classes, k_pos), fc2, T=T, stop_at_stem=True, **kw)
-    Pn, _ = ebp_mwp(sd, x, _onehot(N, num_classes, k_neg), fc2, T=T, stop_at_stem=True, **kw)
+    Pm, _ = ebp_mwp(sd, x, _onehot(N, num_classes, k_pos, x.device), fc2, T=T, stop_at_stem=True, **kw)
+    Pn, _ = ebp_mwp(sd, x, _onehot(N, num_classes, k_neg, x.device), fc2, T=T, stop_at_stem=True, **kw)
     pm, pn = Pm[-2], Pn[-2]
     mm = pm / pm.sum(dim=(1, 2, 3), keepdim=True)
     mn = pn / pn.sum(dim=(1, 2, 3), keepdim=True)
@@ -333,8 +333,8 @@ def contrastive_mwp(sd, x, fc2, k_pos=0, k_neg=1, percentile=None, num_classes=2
             mask[idx] = (cs >= (percentile / 100.0) * cs[-1]).float()
             mask = mask.view_as(mm[i])
             out.append(_relu(mask * mm[i] - mask * mn[i]).sum(0))
-        return torch.stack(out).numpy().astype(np.float32)
-    return _relu(mm - mn).sum(1).numpy().astype(np.float32)
+        return torch.stack(out).cpu().numpy().astype(np.float32)
+    return _relu(mm - mn).sum(1).cpu().numpy().astype(np.float32)
 
 
 def contrastive_ebp(sd, x, fc2, k_pos=0, k_neg=1, percentile=None, **kw):

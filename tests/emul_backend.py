@@ -11,7 +11,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from xfr_b200.packing import unpack_dual_cols
+from xfr_b200.packing import from_pair, to_pair, unpack_dual_cols
 
 MODE_AWP, MODE_ALL, MODE_AFFINEONLY = 0, 1, 2
 EPS = 1e-16
@@ -55,21 +55,27 @@ def im2col_nhwc(x, R, S, pad):
 
 def _w(B):
     """Weight operand -> plain matrix: the 3xTF32 pack is two planes (hi, lo) with hi + lo == W exactly."""
+    B = B.float()
     return B.sum(0) if B.dim() == 3 else B
 
 
 def _wpos(B):
     """W+ operand as the split-TF32 plan of impl 'tf32x3' multiplies it (conv_tc.cu, SPLIT 2 / 3): activations exact,
     relu(W) rounded to TF32 = the hi plane alone.  Single-plane packs (fp32 / tf32) are used as they are."""
+    B = B.float()
     return B[0] if B.dim() == 3 else B
 
 
 class EmulBackend(object):
     name = 'emul'
 
-    def __init__(self, eps=EPS, impl_name='fp32', bwd_single_pass=False, fwd_two_pass=False):
+    def __init__(self, eps=EPS, impl_name='fp32', bwd_single_pass=False, fwd_two_pass=False, pairs=False):
         self.eps = eps
         self.impl_name = impl_name      # which weight packing the engine should build (the arithmetic here is fp32)
+        # kernels.HYBRID_IMPLS['bf16x2']: GEMM operands of the fused sweep are pair tensors (bf16 hi | lo rows, 16 significant
+        # bits), relu(W) one bf16 term, signed W two; fp32 accumulation.  Pair tensors are bit-exact images of the device format.
+        self.pairs = pairs
+        self.conv_pack = 'bf16x2' if pairs else impl_name
         # kernels.HYBRID_IMPLS['tf32x3b1']: the W+ dgrads as ONE TF32 pass - the tensor core truncates the fp32 activation
         # operand to TF32 (tools/trunc_probe.py) and multiplies the hi weight plane
         self.bwd_single_pass = bwd_single_pass
@@ -92,8 +98,13 @@ class EmulBackend(object):
     def avgpool2(self, u, out):
         out.copy_(F.avg_pool2d(u.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1))
 
-    def conv_dual(self, inp, L, o, xr, act, res=None, relu_act=True):
+    def to_pair(self, x, out, inverse=False):
+        out.copy_(from_pair(x) if inverse else to_pair(x))
+
+    def conv_dual(self, inp, L, o, xr, act, res=None, relu_act=True, act_f32=None):
         """o = conv(inp)+b ; xr = relu(conv_{W+}(inp)+b') ; act = relu(o*alpha+beta [+ res, zero-padded channels])."""
+        if self.pairs:
+            inp = from_pair(inp)
         A = im2col_nhwc(inp, L.R, L.S, L.R // 2)
         t, _ = unpack_dual_cols(A @ (_wpos(L.Bf) if self.fwd_two_pass else _w(L.Bf)).t() + L.bias, L.tn)
         _, p = unpack_dual_cols(A @ _wpos(L.Bf).t() + L.bias, L.tn)
@@ -103,7 +114,14 @@ class EmulBackend(object):
         if res is not None:
             rc = res.shape[-1]
             a[:, :rc] += res.reshape(-1, rc)
-        act.view(-1, L.cout).copy_(relu(a) if relu_act else a)
+        a = relu(a) if relu_act else a
+        if self.pairs:
+            if act is not None:
+                act.view(-1, L.cout).copy_(to_pair(a))
+            if act_f32 is not None:
+                act_f32.view(-1, L.cout).copy_(a)
+        else:
+            act.view(-1, L.cout).copy_(a)
 
     def head_fwd(self, u, head, v, f1, f1p, xn, nrm, xmul=None):
         """v = avgpool7(u); (f1 | f1p) = one dual GEMM v @ [W1 ; relu(W1)]^T + (b | b'); xn = f1/|f1|."""
@@ -156,12 +174,16 @@ class EmulBackend(object):
     def dgrad_mid(self, y, L, o, xr, bn, mode, y_out):
         """z = W+^T y (conv L), then the hook chain at the activation a = relu(bn(o)) that fed conv L."""
         J = y.shape[0]
-        z = self._dgrad(y, L.Bd, L.R)
-        y_out.view(-1, L.cin).copy_(self._mid_chain(z, _rows(o, J).reshape(-1, L.cin),
-                                                     _rows(xr, J).reshape(-1, L.cin), bn, mode))
+        z = self._dgrad(from_pair(y) if self.pairs else y, L.Bd, L.R)
+        r = self._mid_chain(z, _rows(o, J).reshape(-1, L.cin), _rows(xr, J).reshape(-1, L.cin), bn, mode)
+        y_out.view(-1, L.cin).copy_(to_pair(r) if self.pairs else r)
 
-    def dgrad_plain(self, y, L, z_out, signed=False, accumulate=False):
-        z = self._dgrad(y, L.signed_dgrad() if signed else L.Bd, L.R, signed)
+    def dgrad_plain(self, y, L, z_out, signed=False, accumulate=False, pair=False):
+        if pair:
+            y, B = from_pair(y), L.Bd
+        else:
+            B = L.signed_dgrad() if signed else (L.Bd32() if getattr(L, 'pair_pack', False) else L.Bd)
+        z = self._dgrad(y, B, L.R, signed)
         if accumulate:
             z = z + z_out.reshape(-1, L.cin)
         z_out.view(-1, L.cin).copy_(z)
@@ -197,16 +219,16 @@ class EmulBackend(object):
         """z = W+^T y1 (1x1 conv L, stride 1) + g_res, then the join chain."""
         J = y1.shape[0]
         C = L.cin
-        z = self._dgrad(y1, L.Bd, 1) + g_res.reshape(-1, C)
+        z = self._dgrad(from_pair(y1) if self.pairs else y1, L.Bd, 1) + g_res.reshape(-1, C)
         r = None if res is None else _rows(res, J)
         if r is not None:
             r = (F.pad(r, (0, C - r.shape[-1])) if r.shape[-1] < C else r).reshape(-1, C)
         g, y3 = self._join_chain(z, _rows(out, J).reshape(-1, C), _rows(o3, J).reshape(-1, C),
                                  _rows(xr3, J).reshape(-1, C), bn3, r, hooks, mode)
         g_out.view(-1, C).copy_(g)
-        y3_out.view(-1, C).copy_(y3)
+        y3_out.view(-1, C).copy_(to_pair(y3) if self.pairs else y3)
 
-    def join(self, zmain, up, gres_lo, k, out, o3, xr3, bn3, res, hooks, mode, g_out, y3_out):
+    def join(self, zmain, up, gres_lo, k, out, o3, xr3, bn3, res, hooks, mode, g_out, y3_out, y3_pair=False):
         """Unfused block boundary: z[j,h,w,c] = zmain (at stride `up`: even pixels only) +
         avgpool_k backward of gres_lo (first Cr channels), then the join chain."""
         J, H, W, C = g_out.shape
@@ -222,7 +244,7 @@ class EmulBackend(object):
                                  _rows(xr3, J).reshape(-1, C), bn3, None if r is None else r.reshape(-1, C),
                                  hooks, mode)
         g_out.view(-1, C).copy_(g)
-        y3_out.view(-1, C).copy_(y3)
+        y3_out.view(-1, C).copy_(to_pair(y3) if y3_pair else y3)
 
     def ds_res(self, g, ap, mode, gres_lo):
         """Residual branch of a downsample block, up to (not including) AvgPool backward:

@@ -23,6 +23,7 @@ cudaError_t launch_maxpool_bwd(const float*, const float*, const float*, float*,
 cudaError_t launch_subtree_score(const float*, const float*, int, size_t, float*, long long*, cudaStream_t);
 cudaError_t launch_head_seed(const float*, const float*, int, int, int, int, float*, cudaStream_t);
 cudaError_t launch_subsample2(const float*, float*, int, int, int, int, cudaStream_t);
+cudaError_t launch_to_pair(const float*, float*, size_t, int, int, cudaStream_t);
 cudaError_t launch_avgpool2(const float*, float*, int, int, int, int, cudaStream_t);
 cudaError_t launch_avgpool7(const float*, float*, int, int, cudaStream_t);
 cudaError_t launch_head_norm(const float*, int, float*, float*, float*, float*, float*, int, cudaStream_t);
@@ -60,6 +61,7 @@ static int finish(const char* what, cudaError_t e) {
 static cudaError_t run_gemm(const float* A, const float* B, const ConvGeom& g, const EpiParams& ep, int impl, cudaStream_t st,
                             int tn = 0, bool positive_weights = false) {
     if (impl == XFRB_IMPL_FP32) return launch_conv_simt(A, B, g, ep, st);
+    if (impl == XFRB_IMPL_BF16X2) return launch_conv_tc_pair(A, B, g, ep, tn, st);     // A: pair tensor, B: bf16 planes
     int split;
     if (impl == XFRB_IMPL_TF32) split = 0;
     else if (impl == XFRB_IMPL_TF32X3_FULL) split = 1;
@@ -87,7 +89,8 @@ int xfrb_device_ok(void) {
 
 int xfrb_impl_available(int impl) {
     if (impl == XFRB_IMPL_FP32) return 1;
-    if (impl == XFRB_IMPL_TF32X3 || impl == XFRB_IMPL_TF32 || impl == XFRB_IMPL_TF32X3_FULL || impl == XFRB_IMPL_TF32X2)
+    if (impl == XFRB_IMPL_TF32X3 || impl == XFRB_IMPL_TF32 || impl == XFRB_IMPL_TF32X3_FULL || impl == XFRB_IMPL_TF32X2 ||
+        impl == XFRB_IMPL_BF16X2)
         return conv_tc_available() ? 1 : 0;
     return 0;
 }
@@ -115,11 +118,16 @@ int xfrb_avgpool2(const float* u, float* out, int N, int H, int W, int C, void* 
     return finish("xfrb_avgpool2", launch_avgpool2(u, out, N, H, W, C, (cudaStream_t)stream));
 }
 
+int xfrb_to_pair(const float* in, float* out, long long rows, int C, int inverse, void* stream) {
+    if (C % 4 || rows < 0) return finish("xfrb_to_pair", cudaErrorInvalidValue);
+    return finish("xfrb_to_pair", launch_to_pair(in, out, (size_t)rows, C, inverse, (cudaStream_t)stream));
+}
+
 int xfrb_conv_dual(const float* inp, const float* Bf, const float* bias, const float* bn, const float* res, int res_c,
-                   float* o, float* xr, float* act, int N, int H, int W, int Cin, int Cout, int R, int tn, int relu_act, int impl,
-                   void* stream) {
+                   float* o, float* xr, float* act, float* act_f32, int N, int H, int W, int Cin, int Cout, int R, int tn,
+                   int relu_act, int impl, void* stream) {
     if ((R != 1 && R != 3) || (tn != 128 && tn != 256) || (impl == XFRB_IMPL_FP32 && tn != 128) || (2 * Cout) % tn ||
-        (res && res_c % 4))
+        (res && res_c % 4) || (impl != XFRB_IMPL_BF16X2 && (act_f32 != nullptr || act == nullptr)))
         return finish("xfrb_conv_dual", cudaErrorInvalidValue);
     ConvGeom g{H, W, Cin, R, R * R * Cin, 2 * Cout};
     EpiParams ep;
@@ -129,7 +137,7 @@ int xfrb_conv_dual(const float* inp, const float* Bf, const float* bias, const f
     ep.C = Cout;
     ep.bias = bias; ep.bn = bn; ep.res = res; ep.res_c = res_c;
     ep.hooks = relu_act ? 0 : 1;
-    ep.out0 = o; ep.out1 = xr; ep.out2 = act;
+    ep.out0 = o; ep.out1 = xr; ep.out2 = act; ep.out3 = act_f32;
     return finish("xfrb_conv_dual", run_gemm(inp, Bf, g, ep, impl, (cudaStream_t)stream, tn));
 }
 
@@ -218,9 +226,9 @@ int xfrb_dgrad_join(const float* y1, const float* Bd, const float* g_res, const 
 
 int xfrb_join(const float* zmain, int up, const float* gres_lo, int gres_c, int k, const float* out, const float* o3,
               const float* xr3, const float* bn3, const float* res, int res_c, float* g_out, float* y3_out, int J, int N, int H,
-              int W, int C, int hooks, int mode, float eps, void* stream) {
+              int W, int C, int hooks, int mode, float eps, int y3_pair, void* stream) {
     if (C % 4 || (gres_lo && gres_c % 4) || (res && res_c % 4) || up < 1 || k < 1) return finish("xfrb_join", cudaErrorInvalidValue);
-    JoinArgs a{zmain, up, gres_lo, gres_c, k, out, o3, xr3, bn3, res, res_c, g_out, y3_out, J, N, H, W, C, hooks, mode, eps};
+    JoinArgs a{zmain, up, gres_lo, gres_c, k, out, o3, xr3, bn3, res, res_c, g_out, y3_out, J, N, H, W, C, hooks, mode, eps, y3_pair};
     return finish("xfrb_join", launch_join(a, (cudaStream_t)stream));
 }
 

@@ -1,6 +1,7 @@
 // Shared device helpers: the excitation-backprop hook algebra used by every epilogue.
 // Mirrors reference python/xfr/models/whitebox.py:381-430 (_backward_ebp, no prior set).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -10,6 +11,15 @@
 #define XFRB_MODE_NONE 3        /* no hook fires: plain (true-gradient) backprop; used by weighted_subtree_ebp */
 
 namespace xfrb {
+
+// cudaFuncSetAttribute / occupancy answers are per DEVICE: "done once" caches are indexed by the current device ordinal
+// (one process may drive several GPUs, e.g. the reference's multi-GPU eval driver with one Whitebox per cuda:%d).
+constexpr int XFRB_MAX_DEV = 64;
+inline int current_device_slot() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d >= 0 && d < XFRB_MAX_DEV) ? d : 0;
+}
 
 void set_error(const char* what, cudaError_t e);
 int check_launch(const char* what);
@@ -76,6 +86,33 @@ __device__ __forceinline__ void join_chain(float z, float out, float o3, float x
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// ---------------- "pair" tensors of the bf16x2 plan ----------------
+// A tensor whose rows of C fp32 values x are stored as [C bf16 hi | C bf16 lo] with hi = bf16(x), lo = bf16(x - hi): the same
+// 4*C bytes per row, 16 significant bits, and both halves are ready-made tcgen05 kind::f16 operands (one TMA box each).
+__device__ __forceinline__ uint32_t bf16x2_bits(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);           // .x (low 16 bits, lower address) = a
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void st_pair4(float* t, size_t row, int C, int c, const float v[4]) {
+    float hf[4], lf[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        hf[e] = __bfloat162float(__float2bfloat16_rn(v[e]));
+        lf[e] = v[e] - hf[e];                                  // exact in fp32
+    }
+    uint8_t* p = reinterpret_cast<uint8_t*>(t) + row * (size_t)C * 4;
+    *reinterpret_cast<uint2*>(p + 2 * c) = make_uint2(bf16x2_bits(hf[0], hf[1]), bf16x2_bits(hf[2], hf[3]));
+    *reinterpret_cast<uint2*>(p + 2 * (size_t)C + 2 * c) = make_uint2(bf16x2_bits(lf[0], lf[1]), bf16x2_bits(lf[2], lf[3]));
+}
+__device__ __forceinline__ void ld_pair4(const float* t, size_t row, int C, int c, float v[4]) {
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(t) + row * (size_t)C * 4;
+    const uint2 h = *reinterpret_cast<const uint2*>(p + 2 * c), l = *reinterpret_cast<const uint2*>(p + 2 * (size_t)C + 2 * c);
+    v[0] = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+    v[1] = __uint_as_float(h.x & 0xFFFF0000u) + __uint_as_float(l.x & 0xFFFF0000u);
+    v[2] = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+    v[3] = __uint_as_float(h.y & 0xFFFF0000u) + __uint_as_float(l.y & 0xFFFF0000u);
+}
+
 // ---------------- epilogue parameter block shared by the SIMT and tcgen05 GEMMs ----------------
 enum EpiKind { EPI_PLAIN = 0, EPI_FWD_DUAL = 1, EPI_MID = 2, EPI_JOIN = 3 };
 
@@ -97,6 +134,7 @@ struct EpiParams {
     float* out0;         // PLAIN: z ; FWD_DUAL: o ; MID: y_out ; JOIN: g_out
     float* out1;         // FWD_DUAL: xr ; JOIN: y3_out
     float* out2;         // FWD_DUAL: act
+    float* out3;         // FWD_DUAL, bf16x2 plan: optional fp32 copy of act (act itself is then a bf16 pair tensor)
 };
 
 // 4 consecutive channels (c..c+3) of one row.  acc = true/only accumulator, accp = positive twin (FWD_DUAL).
@@ -200,6 +238,7 @@ struct JoinArgs {
     const float* res; int res_c;
     float* g_out; float* y3_out;
     int J, N, H, W, C, hooks, mode; float eps;
+    int y3_pair;                           // bf16x2 plan: y3_out is a pair tensor
 };
 
 cudaError_t launch_conv_simt(const float* A, const float* B, const ConvGeom& g, const EpiParams& ep, cudaStream_t st);
@@ -211,5 +250,10 @@ int conv_tc_set_mc(int on);       // multicast-pair kernels (shared weight loads
 // width (FWD_DUAL) or a cap on BN
 cudaError_t launch_conv_tc(const float* A, const float* B, const ConvGeom& g, const EpiParams& ep, int split, int tn,
                            cudaStream_t st);
+bool conv_tc_cta2_enabled();
+// bf16x2 plan (conv_tc_pair.cu): A is a pair tensor [M][Cin bf16 hi | Cin bf16 lo]; B bf16 [planes][Nn][K]: one plane of
+// relu(W) for the W+ GEMMs (MID / JOIN / PLAIN), (hi, lo) planes of the dual pack for FWD_DUAL (the lo plane is read for the
+// W half of each tile only).  Outputs that feed the next GEMM (act / y_out / y3_out) are written as pair tensors.
+cudaError_t launch_conv_tc_pair(const float* A, const void* B, const ConvGeom& g, const EpiParams& ep, int tn, cudaStream_t st);
 
 }  // namespace xfrb

@@ -109,10 +109,11 @@ __global__ void stem_pool_kernel(const float* __restrict__ o, const float* __res
 cudaError_t launch_stem_fwd(const float* x, const float* W, const float* b, const float* bn, float* o, float* mp,
                             unsigned char* mp_arg, int N, int pool_pad, cudaStream_t st) {
     size_t smem = (147 * 64 + ST_P * ST_P * 3) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[XFRB_MAX_DEV] = {};
+    const int dev = current_device_slot();
+    if (!attr[dev]) {
         cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
+        attr[dev] = true;
     }
     stem_conv_kernel<<<dim3(112 / ST_T, 112 / ST_T, N), 256, smem, st>>>(x, W, b, o, N);
     int total4 = N * 56 * 56 * 16;
@@ -149,6 +150,31 @@ __global__ void avgpool2_kernel(const float* __restrict__ u, float* __restrict__
     r.z = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.z, b1.z), c0.z), c1.z), 4.f);
     r.w = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.w, b1.w), c0.w), c1.w), 4.f);
     reinterpret_cast<float4*>(out)[i] = r;
+}
+
+// ------------------------------------------------------------------ pair tensors (bf16x2 plan, common.cuh)
+__global__ void to_pair_kernel(const float* __restrict__ in, float* __restrict__ out, int C, size_t total4) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int C4 = C / 4;
+    const float4 t = __ldg(reinterpret_cast<const float4*>(in) + i);
+    const float v[4] = {t.x, t.y, t.z, t.w};
+    st_pair4(out, i / C4, C, (int)(i % C4) * 4, v);
+}
+__global__ void from_pair_kernel(const float* __restrict__ in, float* __restrict__ out, int C, size_t total4) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int C4 = C / 4;
+    float v[4];
+    ld_pair4(in, i / C4, C, (int)(i % C4) * 4, v);
+    reinterpret_cast<float4*>(out)[i] = make_float4(v[0], v[1], v[2], v[3]);
+}
+cudaError_t launch_to_pair(const float* in, float* out, size_t rows, int C, int inverse, cudaStream_t st) {
+    size_t total4 = rows * (size_t)(C / 4);
+    if (total4 == 0) return cudaSuccess;
+    if (inverse) from_pair_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(in, out, C, total4);
+    else to_pair_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(in, out, C, total4);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_subsample2(const float* u, float* out, int N, int H, int W, int C, cudaStream_t st) {
@@ -334,9 +360,11 @@ __global__ void __launch_bounds__(256, MINB) join_kernel(JoinArgs a, size_t tota
             float g[4], y3[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) join_chain(z[s][q], u[q], o[q], x[q], r[q], b[q], a.hooks, mode, a.eps, g[q], y3[q]);
-            const size_t off = ((((size_t)j * a.H + h) * a.W + w) * a.C + c) / 4;
+            const size_t row = ((size_t)j * a.H + h) * a.W + w;
+            const size_t off = (row * a.C + c) / 4;
             reinterpret_cast<float4*>(a.g_out)[off] = make_float4(g[0], g[1], g[2], g[3]);
-            reinterpret_cast<float4*>(a.y3_out)[off] = make_float4(y3[0], y3[1], y3[2], y3[3]);
+            if (a.y3_pair) st_pair4(a.y3_out, row, a.C, c, y3);      // bf16x2 plan: y3 is the A operand of the next dgrad
+            else reinterpret_cast<float4*>(a.y3_out)[off] = make_float4(y3[0], y3[1], y3[2], y3[3]);
         }
     }
 }
@@ -379,7 +407,8 @@ __global__ void join_rows_kernel(JoinArgs a, size_t total4) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) join_chain(z[q], u[q], o[q], x[q], r[q], b[q], a.hooks, a.mode, a.eps, g[q], y3[q]);
     reinterpret_cast<float4*>(a.g_out)[i] = make_float4(g[0], g[1], g[2], g[3]);
-    reinterpret_cast<float4*>(a.y3_out)[i] = make_float4(y3[0], y3[1], y3[2], y3[3]);
+    if (a.y3_pair) st_pair4(a.y3_out, i / C4, a.C, c, y3);
+    else reinterpret_cast<float4*>(a.y3_out)[i] = make_float4(y3[0], y3[1], y3[2], y3[3]);
 }
 
 cudaError_t launch_join(const JoinArgs& a, cudaStream_t st) {
@@ -947,10 +976,11 @@ __global__ void __launch_bounds__(512) saliency_post_kernel(const float* __restr
 
 cudaError_t launch_saliency_post(const float* mwp, float* out, int B, int H, int W, float eps, cudaStream_t st) {
     size_t smem = (size_t)2 * H * W * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[XFRB_MAX_DEV] = {};
+    const int dev = current_device_slot();
+    if (!attr[dev]) {
         cudaFuncSetAttribute(saliency_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 128 * 4);
-        attr = true;
+        attr[dev] = true;
     }
     saliency_post_kernel<<<B, 512, smem, st>>>(mwp, out, H, W, eps);
     return cudaGetLastError();

@@ -43,20 +43,28 @@ class _Engine(object):
         self.with_bias = with_bias
         self.eps = eps
         self._ws = {}
-        return getattr(backend, 'impl_name', 'fp32')     # decides the weight planes / tile widths of the packs
+        # bf16x2 plan: the GEMM operands of the fused sweep (block inputs, inner activations, y1 / y2 / y3) are PAIR tensors -
+        # rows of [C bf16 hi | C bf16 lo], the same bytes as fp32 (include/xfrb.h XFRB_IMPL_BF16X2) - written by the producing
+        # kernel; block outputs are kept in fp32 as well (residuals and hook chains read them)
+        self.pairs = bool(getattr(backend, 'pairs', False))
+        impl = getattr(backend, 'impl_name', 'fp32')     # decides the weight planes / tile widths of the packs
+        self.conv_impl = getattr(backend, 'conv_pack', impl)
+        return impl
 
     # ------------------------------------------------------------ workspace
     def buf(self, name, *shape, **kw):
-        """Named buffer, allocated once per (name, shape): static addresses for graph capture."""
-        key = (name,) + tuple(shape)
+        """Named buffer [rows, ...]: one allocation per (name, trailing shape) with a row CAPACITY - a smaller batch (the
+        ragged last chunk, a different job count) is a view of the same storage instead of a second complete workspace
+        (~210 MB per probe); addresses stay static while the capacity is not exceeded (graph capture)."""
+        key = (name,) + tuple(shape[1:])
         t = self._ws.get(key)
-        if t is None:
+        if t is None or t.shape[0] < shape[0]:
             t = torch.empty(shape, dtype=kw.get('dtype', torch.float32), device=self.device)
             self._ws[key] = t
-        return t
+        return t if t.shape[0] == shape[0] else t[:shape[0]]
 
     def workspace_bytes(self):
-        return sum(t.numel() * t.element_size() for t in self._ws.values())
+        return sum(t.numel() * t.element_size() for t in self._ws.values() if torch.is_tensor(t))
 
     # ------------------------------------------------------------ composed operators
     def _onehot(self, J, C, cols):
@@ -96,6 +104,21 @@ class _Engine(object):
         self.be.saliency_post(mwp, out)
         return out
 
+    def fc2_rows(self, W2, signed=False):
+        """The network's own (hooked) fc2 [C,D] as the [1,C,D] operand of head_seed: relu(W) for excitation backprop
+        (whitebox.py:371-374), the signed weights for the true-gradient sweeps.  Cached per (storage, version): an in-place
+        update of fc2 or a recycled address must not return a stale relu(W)."""
+        if signed:
+            return W2.unsqueeze(0).contiguous()
+        key = ('W2p', W2.data_ptr(), W2._version, tuple(W2.shape))
+        W2p = self._ws.get(key)
+        if W2p is None:
+            for k in [k for k in self._ws if isinstance(k, tuple) and k and k[0] == 'W2p']:
+                del self._ws[k]
+            W2p = torch.clamp_min(W2, 0).unsqueeze(0).contiguous()
+            self._ws[key] = W2p
+        return W2p
+
     def priors_contrastive(self, N, C, k_pos, k_neg):
         key = ('prior', N, C, k_pos, k_neg)
         P = self._ws.get(key)
@@ -126,9 +149,9 @@ class StResnetEngine(_Engine):
                 b.hw_in = hw
                 hw = hw // b.stride
                 b.hw = hw
-                b.c1 = packing.ConvBN(sd, b.name + '.conv1', b.name + '.bn1', impl, with_bias).to(self.device)
-                b.c2 = packing.ConvBN(sd, b.name + '.conv2', b.name + '.bn2', impl, with_bias).to(self.device)
-                b.c3 = packing.ConvBN(sd, b.name + '.conv3', b.name + '.bn3', impl, with_bias).to(self.device)
+                b.c1 = packing.ConvBN(sd, b.name + '.conv1', b.name + '.bn1', self.conv_impl, with_bias).to(self.device)
+                b.c2 = packing.ConvBN(sd, b.name + '.conv2', b.name + '.bn2', self.conv_impl, with_bias).to(self.device)
+                b.c3 = packing.ConvBN(sd, b.name + '.conv3', b.name + '.bn3', self.conv_impl, with_bias).to(self.device)
                 self.blocks.append(b)
                 inplanes = planes * 4
         self.enc_dim = 512
@@ -145,6 +168,11 @@ class StResnetEngine(_Engine):
         S['mp_arg'] = self.buf('mp_arg', N, 56, 56, 64, dtype=torch.uint8)      # which window position won each max-pool
         be.stem_fwd(x_nhwc, self.stem, S['o_s'], S['mp'], S['mp_arg'])
         u = S['mp']
+        pairs = self.pairs
+        upair = None                        # pair twin of u: the A operand of the next block's conv1
+        if pairs:
+            upair = self.buf('mp_pair', N, 56, 56, 64)
+            be.to_pair(u, upair)
         for i, b in enumerate(self.blocks):
             h = b.hw
             t = {}
@@ -155,12 +183,15 @@ class StResnetEngine(_Engine):
                     t['us'] = self.buf('us%d' % i, N, h, h, b.cin)
                     be.subsample2(u, t['us'])
                     cin1 = t['us']
+                    if pairs:
+                        cin1 = self.buf('us_pair', N, h, h, b.cin)
+                        be.to_pair(t['us'], cin1)
                 else:
                     t['ap'] = u
-                    cin1 = u
+                    cin1 = upair if pairs else u
                 res = t['ap']
             else:
-                cin1 = u
+                cin1 = upair if pairs else u
                 res = u
             for k, c in (('1', b.planes), ('2', b.planes), ('3', b.cout)):
                 t['o' + k] = self.buf('o%s_%d' % (k, i), N, h, h, c)
@@ -172,7 +203,11 @@ class StResnetEngine(_Engine):
             t['res'] = res
             be.conv_dual(cin1, b.c1, t['o1'], t['xr1'], a1)
             be.conv_dual(a1, b.c2, t['o2'], t['xr2'], a2)
-            be.conv_dual(a2, b.c3, t['o3'], t['xr3'], t['out'], res)
+            if pairs:
+                upair = self.buf('out_pair%d' % (i % 2), N, h, h, b.cout)
+                be.conv_dual(a2, b.c3, t['o3'], t['xr3'], upair, res, act_f32=t['out'])
+            else:
+                be.conv_dual(a2, b.c3, t['o3'], t['xr3'], t['out'], res)
             S[i] = t
             u = t['out']
         S['v'] = self.buf('v', N, 2048)
@@ -195,16 +230,17 @@ class StResnetEngine(_Engine):
         return (50.0 * self.saved['xn'][0:1]) @ W2[0].t()
 
     # ------------------------------------------------------------ backward
-    def hooked_fc2_seed(self, Pn, W2, m, prior=None, P_out=None):
+    def hooked_logits(self, W2):
+        """classify() with the network's own fc2 [C,512] for probe 0, without its bias (resnet.py:252-258)"""
+        return (50.0 * self.saved['xn'][0:1]) @ W2.t()
+
+    def hooked_fc2_seed(self, Pn, W2, m, prior=None, P_out=None, signed=False):
         """The network's own fc2 takes part in EBP (no set_triplet_classifier): gradient Pn @ relu(W2) at the fc2 input,
         then the Linear hook with a = relu(50*xn), x = relu(50*relu(xn)) (reference whitebox.py:371-374, 381-430;
-        SURVEY.md appendix A).  W2 [C,512] signed.  Returns the [J,512] gradient after the hook."""
+        SURVEY.md appendix A).  W2 [C,512] signed.  Returns the [J,512] gradient after the hook.  signed: the true-gradient
+        sweep (m = MODE_NONE): Pn @ W2, the hook only records."""
         S, J = self.saved, Pn.shape[0]
-        key = ('W2p', W2.data_ptr())
-        W2p = self._ws.get(key)
-        if W2p is None:
-            W2p = torch.clamp_min(W2, 0).unsqueeze(0).contiguous()
-            self._ws[key] = W2p
+        W2p = self.fc2_rows(W2, signed)
         seed = self.buf('fc2_seed', J, 1, 1, 512)
         self.be.head_seed(Pn, W2p, seed.view(J, 512))
         a50 = self.buf('fc2_a', S['N'], 512)
@@ -235,7 +271,9 @@ class StResnetEngine(_Engine):
         t = S[nb - 1]
         gb = self.buf('g%d' % ((nb - 1) % 2), J, last.hw, last.hw, last.cout)
         y3 = self.buf('y3', J, last.hw, last.hw, last.cout)
-        be.join(g, 1, None, 1, t['out'], t['o3'], t['xr3'], last.c3.bn, t['res'], 1, m, gb, y3)
+        pk = dict(y3_pair=True) if self.pairs else {}           # pairs: y1 / y2 / y3 are pair tensors, the g's stay fp32
+        pp = dict(pair=True) if self.pairs else {}
+        be.join(g, 1, None, 1, t['out'], t['o3'], t['xr3'], last.c3.bn, t['res'], 1, m, gb, y3, **pk)
         for i in range(nb - 1, -1, -1):
             b, t = self.blocks[i], S[i]
             h = b.hw
@@ -251,7 +289,7 @@ class StResnetEngine(_Engine):
                 gb = gp
                 continue
             zlo = self.buf('zlo', J, h, h, b.cin)
-            be.dgrad_plain(y1, b.c1, zlo)
+            be.dgrad_plain(y1, b.c1, zlo, **pp)
             gres = self.buf('gres', J, h, h, b.cin)
             be.ds_res(gb, t['ap'], m, gres)
             if i == 0:
@@ -265,7 +303,7 @@ class StResnetEngine(_Engine):
             gp = self.buf('g%d' % ((i - 1) % 2), J, hp, hp, b.cin)
             y3 = self.buf('y3', J, hp, hp, b.cin)
             be.join(zlo, b.stride, gres, b.stride, tp['out'], tp['o3'], tp['xr3'], p.c3.bn, tp['res'], 3, m,
-                    gp, y3)
+                    gp, y3, **pk)
             gb = gp
 
 
@@ -293,7 +331,7 @@ class Resnet50_128Engine(_Engine):
                 b.hw_in = hw
                 hw = hw // b.stride
                 b.hw = hw
-                mk = lambda c: packing.ConvBN(sd, b.name + c, b.name + c + '_bn', impl, with_bias).to(self.device)
+                mk = lambda c: packing.ConvBN(sd, b.name + c, b.name + c + '_bn', self.conv_impl, with_bias).to(self.device)
                 b.c1, b.c2, b.c3 = mk('_1x1_reduce'), mk('_3x3'), mk('_1x1_increase')
                 b.cp = mk('_1x1_proj') if b.proj else None
                 self.blocks.append(b)
@@ -310,13 +348,22 @@ class Resnet50_128Engine(_Engine):
         S['mp_arg'] = self.buf('mp_arg', N, 56, 56, 64, dtype=torch.uint8)      # which window position won each max-pool
         be.stem_fwd(x_nhwc, self.stem, S['o_s'], S['mp'], S['mp_arg'])
         u = S['mp']
+        pairs = self.pairs
+        upair = None
+        if pairs:
+            upair = self.buf('mp_pair', N, 56, 56, 64)
+            be.to_pair(u, upair)
         for i, b in enumerate(self.blocks):
             h = b.hw
             t = {'u': u}
-            cin1 = u
+            cin1 = upair if pairs else u
             if b.stride == 2:
                 cin1 = self.buf('us%d' % i, N, h, h, b.cin)
                 be.subsample2(u, cin1)
+                if pairs:
+                    us = cin1
+                    cin1 = self.buf('us_pair', N, h, h, b.cin)
+                    be.to_pair(us, cin1)
             for k, c in (('1', b.planes), ('2', b.planes), ('3', b.cout)):
                 t['o' + k] = self.buf('o%s_%d' % (k, i), N, h, h, c)
                 t['xr' + k] = self.buf('xr%s_%d' % (k, i), N, h, h, c)
@@ -329,11 +376,18 @@ class Resnet50_128Engine(_Engine):
                 t['op'] = self.buf('op%d' % i, N, h, h, b.cout)
                 t['xrp'] = self.buf('xrp%d' % i, N, h, h, b.cout)
                 res = self.buf('resp', N, h, h, b.cout)
-                be.conv_dual(cin1, b.cp, t['op'], t['xrp'], res, relu_act=False)     # res = bn_p(conv_p(u)), no ReLU
+                if pairs:       # res is read as a residual only: fp32, no pair twin
+                    be.conv_dual(cin1, b.cp, t['op'], t['xrp'], None, relu_act=False, act_f32=res)
+                else:
+                    be.conv_dual(cin1, b.cp, t['op'], t['xrp'], res, relu_act=False)     # res = bn_p(conv_p(u)), no ReLU
             else:
                 res = u
             t['res'] = res if not b.proj else None          # identity: the X of the shortcut operand is u itself
-            be.conv_dual(a2, b.c3, t['o3'], t['xr3'], t['out'], res)
+            if pairs:
+                upair = self.buf('out_pair%d' % (i % 2), N, h, h, b.cout)
+                be.conv_dual(a2, b.c3, t['o3'], t['xr3'], upair, res, act_f32=t['out'])
+            else:
+                be.conv_dual(a2, b.c3, t['o3'], t['xr3'], t['out'], res)
             S[i] = t
             u = t['out']
         S['v'] = self.buf('v', N, u.shape[-1])
@@ -376,7 +430,9 @@ class Resnet50_128Engine(_Engine):
         t = S[nb - 1]
         gb = self.buf('g%d' % ((nb - 1) % 2), J, last.hw, last.hw, last.cout)
         y3 = self.buf('y3', J, last.hw, last.hw, last.cout)
-        be.join(g, 1, None, 1, t['out'], t['o3'], t['xr3'], last.c3.bn, self._xres(nb - 1, m), 1 | 4, m, gb, y3)
+        pk = dict(y3_pair=True) if self.pairs else {}
+        pp = dict(pair=True) if self.pairs else {}
+        be.join(g, 1, None, 1, t['out'], t['o3'], t['xr3'], last.c3.bn, self._xres(nb - 1, m), 1 | 4, m, gb, y3, **pk)
         for i in range(nb - 1, -1, -1):
             b, t = self.blocks[i], S[i]
             h = b.hw
@@ -393,10 +449,14 @@ class Resnet50_128Engine(_Engine):
                 continue
             # projection block: both dgrads land on the (sub-sampled) block input
             zlo = self.buf('zlo', J, h, h, b.cin)
-            be.dgrad_plain(y1, b.c1, zlo)
+            be.dgrad_plain(y1, b.c1, zlo, **pp)
             yp = self.buf('yp', J, h, h, b.cout)
             be.bn_hook(gb, t['op'], t['xrp'], b.cp.bn, yp, 0, m)          # BN backward (gamma+) + BatchNorm hook of proj_bn
-            be.dgrad_plain(yp, b.cp, zlo, accumulate=True)
+            if self.pairs:
+                ypp = self.buf('yp_pair', J, h, h, b.cout)
+                be.to_pair(yp, ypp)
+                yp = ypp
+            be.dgrad_plain(yp, b.cp, zlo, accumulate=True, **pp)
             if i == 0:
                 P2 = self.buf('P2', J, 112, 112, 64)
                 chansum = self.buf('chansum', J, 112, 112)
@@ -407,5 +467,5 @@ class Resnet50_128Engine(_Engine):
             hp = b.hw_in
             gp = self.buf('g%d' % ((i - 1) % 2), J, hp, hp, b.cin)
             y3 = self.buf('y3', J, hp, hp, b.cin)
-            be.join(zlo, b.stride, None, 1, tp['out'], tp['o3'], tp['xr3'], p.c3.bn, self._xres(i - 1, m), 3 | 4, m, gp, y3)
+            be.join(zlo, b.stride, None, 1, tp['out'], tp['o3'], tp['xr3'], p.c3.bn, self._xres(i - 1, m), 3 | 4, m, gp, y3, **pk)
             gb = gp

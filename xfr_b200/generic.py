@@ -71,15 +71,13 @@ class GenericSweep(object):
 
         # ---- head: fc2 (un-hooked triplet rows) -> x50 -> Multiply hook -> normalize' -> fc1 -> Linear hook -> AvgPool'
         if hooked_fc2:          # the network's own fc2: W+ and one more (leading) Linear firing
-            if true_grad:
-                raise NotImplementedError('true-gradient sweep with the hooked fc2 head')
             k = self._k
             self._k += 1
             self._names.append('Linear')
             P_out = torch.empty(J, 1, 1, 512, device=eng.device) if record else None
             if record:
                 self._P.append(P_out)
-            seed = eng.hooked_fc2_seed(Pn, W2, m, prior=self._priors.get(k), P_out=P_out).view(J, 1, 1, 512)
+            seed = eng.hooked_fc2_seed(Pn, W2, m, prior=self._priors.get(k), P_out=P_out, signed=true_grad).view(J, 1, 1, 512)
         else:
             seed = buf('gs_seed', J, 1, 1, 512)
             be.head_seed(Pn, W2, seed.view(J, 512))

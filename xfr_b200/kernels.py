@@ -13,7 +13,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libxfr_b200.so')
 
-IMPL_FP32, IMPL_TF32X3, IMPL_TF32, IMPL_TF32X3_FULL, IMPL_TF32X2 = 0, 1, 2, 3, 4
+IMPL_FP32, IMPL_TF32X3, IMPL_TF32, IMPL_TF32X3_FULL, IMPL_TF32X2, IMPL_BF16X2 = 0, 1, 2, 3, 4, 5
 IMPLS = {'fp32': IMPL_FP32, 'tf32x3': IMPL_TF32X3, 'tf32': IMPL_TF32, 'tf32x3full': IMPL_TF32X3_FULL}
 # Opt-in hybrid plans on the 'tf32x3' weight packs: name -> (base plan, plan of the forward dual convs, plan of the W+ dgrads).
 #  'tf32x2f': the forward dual convs run TWO passes (activations exact as hi + lo, the signed weights rounded to TF32 like the W+
@@ -21,7 +21,11 @@ IMPLS = {'fp32': IMPL_FP32, 'tf32x3': IMPL_TF32X3, 'tf32': IMPL_TF32, 'tf32x3ful
 #             the contrastive map: on the kernel emulation the ResNet-101 golden triplet keeps 1.7e-6 max-abs (default 1.4e-6), single
 #             EBP maps move to <= 3e-3 of their maximum (4e-7 max-abs; bar 1e-4).  Not yet run on a B200.
 #  'tf32x3b1': the W+ dgrads as ONE TF32 pass.  NOT parity-grade: 4.5e-4 max-abs on the same triplet.
-HYBRID_IMPLS = {'tf32x2f': ('tf32x3', IMPL_TF32X2, None), 'tf32x3b1': ('tf32x3', None, IMPL_TF32)}
+#  'bf16x2': the fused sweep on tcgen05 kind::f16 with bf16 terms (activations 2, relu(W) 1, signed W 2: XFRB_IMPL_BF16X2); GEMM
+#             operands travel as pair tensors written by the producing epilogue.  Head GEMMs and the firing-by-firing sweeps
+#             (layerwise / weighted-subtree operators) stay on the split-TF32 kernels with fp32 activations.
+HYBRID_IMPLS = {'tf32x2f': ('tf32x3', IMPL_TF32X2, None), 'tf32x3b1': ('tf32x3', None, IMPL_TF32),
+                'bf16x2': ('tf32x3', IMPL_BF16X2, IMPL_BF16X2)}
 
 _P = ctypes.c_void_p
 _I = ctypes.c_int
@@ -32,13 +36,14 @@ _SIGNATURES = {
     'xfrb_stem_fwd': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     'xfrb_subsample2': [_P, _P, _I, _I, _I, _I, _P],
     'xfrb_avgpool2': [_P, _P, _I, _I, _I, _I, _P],
-    'xfrb_conv_dual': [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'xfrb_to_pair': [_P, _P, ctypes.c_longlong, _I, _I, _P],
+    'xfrb_conv_dual': [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'xfrb_head_fwd': [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     'xfrb_head_bwd': [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
     'xfrb_dgrad_mid': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     'xfrb_dgrad_plain': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'xfrb_dgrad_join': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
-    'xfrb_join': [_P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
+    'xfrb_join': [_P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     'xfrb_ds_res': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     'xfrb_stem_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
     'xfrb_bn_hook': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
@@ -100,19 +105,40 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+class _DeviceLib(object):
+    """The library's entry points with `device` made current around every call.  The C side launches on the stream it is
+    handed and never calls cudaSetDevice, so a caller that passes torch.device('cuda:1') without torch.cuda.set_device - as
+    the reference's multi-GPU driver does (eval/generate_inpaintinggame_wb_saliency_maps_multigpu.py:48) - would otherwise
+    launch on a foreign device's stream."""
+
+    def __init__(self, lib, device):
+        self._lib = lib
+        self._idx = device.index if device.index is not None else torch.cuda.current_device()
+
+    def __getattr__(self, name):
+        fn, idx = getattr(self._lib, name), self._idx
+
+        def call(*a):
+            if torch.cuda.current_device() == idx:
+                return fn(*a)
+            with torch.cuda.device(idx):
+                return fn(*a)
+        setattr(self, name, call)
+        return call
+
+
 class CudaBackend(object):
     """Kernel set of the engine on one B200.  Method names/arguments mirror tests/emul_backend.py."""
     name = 'cuda'
 
     def __init__(self, device, impl='fp32', eps=1e-16):
-        self.lib = load_library()
         self.device = torch.device(device)
         if self.device.type != 'cuda' or not torch.cuda.is_available():
             raise RuntimeError('xfr_b200: a CUDA device is required (no CPU fallback)')
-        with torch.cuda.device(self.device):
-            if not self.lib.xfrb_device_ok():
-                raise RuntimeError('xfr_b200: kernels are built for sm_100a only; device is %s'
-                                   % torch.cuda.get_device_name(self.device))
+        self.lib = _DeviceLib(load_library(), self.device)
+        if not self.lib.xfrb_device_ok():
+            raise RuntimeError('xfr_b200: kernels are built for sm_100a only; device is %s'
+                               % torch.cuda.get_device_name(self.device))
         fwd = bwd = None
         self.plan = impl if isinstance(impl, str) else None
         if isinstance(impl, str) and impl in HYBRID_IMPLS:
@@ -124,6 +150,8 @@ class CudaBackend(object):
         for i in (self.impl, self.fwd_impl, self.bwd_impl):
             if not self.lib.xfrb_impl_available(i):
                 raise NotImplementedError('xfr_b200: GEMM implementation %r is not compiled into %s' % (impl, LIB_PATH))
+        self.pairs = self.fwd_impl == IMPL_BF16X2      # GEMM operands of the fused sweep are pair tensors (include/xfrb.h)
+        self.conv_pack = 'bf16x2' if self.pairs else self.impl_name     # weight packing of the block convs (packing.ConvBN)
         self.eps = float(eps)
         self._scratch = {}
         self.launches = 0
@@ -157,10 +185,16 @@ class CudaBackend(object):
         N, H, W, C = u.shape
         self._check(self.lib.xfrb_avgpool2(_ptr(u), _ptr(out), N, H, W, C, self._st()))
 
-    def conv_dual(self, inp, L, o, xr, act, res=None, relu_act=True):
+    def to_pair(self, x, out, inverse=False):
+        """fp32 [..., C] -> pair tensor (or back): the GEMM operand format of the bf16x2 plan"""
+        C = x.shape[-1]
+        self._check(self.lib.xfrb_to_pair(_ptr(x), _ptr(out), x.numel() // C, C, 1 if inverse else 0, self._st()))
+
+    def conv_dual(self, inp, L, o, xr, act, res=None, relu_act=True, act_f32=None):
+        """pairs: inp / act are pair tensors, act_f32 an optional fp32 copy of act (act itself may then be None)"""
         N, H, W, Cin = inp.shape
         self._check(self.lib.xfrb_conv_dual(_ptr(inp), _ptr(L.Bf), _ptr(L.bias), _ptr(L.bn), _ptr(res),
-                                            0 if res is None else res.shape[-1], _ptr(o), _ptr(xr), _ptr(act),
+                                            0 if res is None else res.shape[-1], _ptr(o), _ptr(xr), _ptr(act), _ptr(act_f32),
                                             N, H, W, Cin, L.cout, L.R, L.tn, 1 if relu_act else 0, self.fwd_impl, self._st()))
 
     def head_fwd(self, u, head, v, f1, f1p, xn, nrm, xmul=None):
@@ -183,10 +217,16 @@ class CudaBackend(object):
         self._check(self.lib.xfrb_dgrad_mid(_ptr(y), _ptr(L.Bd), _ptr(o), _ptr(xr), _ptr(bn), _ptr(y_out), J,
                                             o.shape[0], H, W, L.cin, Cout, L.R, mode, self.eps, self.bwd_impl, self._st()))
 
-    def dgrad_plain(self, y, L, z_out, signed=False, accumulate=False):
+    def dgrad_plain(self, y, L, z_out, signed=False, accumulate=False, pair=False):
+        """pair: y is a pair tensor (fused sweep of the bf16x2 plan); otherwise fp32 activations on the split-TF32 kernels"""
         J, H, W, Cout = y.shape
-        B = L.signed_dgrad() if signed else L.Bd
-        impl = (IMPL_TF32X3_FULL if self.impl == IMPL_TF32X3 else self.impl) if signed else self.bwd_impl   # signed: all three passes
+        if pair:
+            assert self.pairs and not signed
+            B, impl = L.Bd, self.bwd_impl
+        else:
+            B = L.signed_dgrad() if signed else (L.Bd32() if getattr(L, 'pair_pack', False) else L.Bd)
+            impl = (IMPL_TF32X3_FULL if self.impl == IMPL_TF32X3 else self.impl) if signed else \
+                (self.impl if self.pairs else self.bwd_impl)              # signed: all three passes
         self._check(self.lib.xfrb_dgrad_plain(_ptr(y), _ptr(B), _ptr(z_out), J, H, W, L.cin, Cout, L.R,
                                               1 if accumulate else 0, impl, self._st()))
 
@@ -197,12 +237,12 @@ class CudaBackend(object):
                                              _ptr(y3_out), J, out.shape[0], H, W, L.cin, Cout, hooks, mode, self.eps,
                                              self.bwd_impl, self._st()))
 
-    def join(self, zmain, up, gres_lo, k, out, o3, xr3, bn3, res, hooks, mode, g_out, y3_out):
+    def join(self, zmain, up, gres_lo, k, out, o3, xr3, bn3, res, hooks, mode, g_out, y3_out, y3_pair=False):
         J, H, W, C = g_out.shape
         self._check(self.lib.xfrb_join(_ptr(zmain), up, _ptr(gres_lo), 0 if gres_lo is None else gres_lo.shape[-1], k,
                                        _ptr(out), _ptr(o3), _ptr(xr3), _ptr(bn3), _ptr(res),
                                        0 if res is None else res.shape[-1], _ptr(g_out), _ptr(y3_out), J, out.shape[0],
-                                       H, W, C, hooks, mode, self.eps, self._st()))
+                                       H, W, C, hooks, mode, self.eps, 1 if y3_pair else 0, self._st()))
 
     def ds_res(self, g, ap, mode, gres_lo):
         J, H, W, C = g.shape

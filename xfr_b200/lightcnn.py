@@ -156,6 +156,10 @@ class LightCNNEngine(_Engine):
         """classify() of the triplet head for probe 0 (whitebox.py:130-132): fc @ W2^T"""
         return self.saved['fc'][0:1] @ W2[0].t()
 
+    def hooked_logits(self, W2):
+        """classify() with the network's own fc2 [C,256] for probe 0 (no bias: lightcnn.py:228)"""
+        return self.saved['fc'][0:1] @ W2.t()
+
     def ebp_backward(self, Pn, W2, mode='affineonly_with_prior', hooked_fc2=False):
         """-> (P2 [J,128,128,2*64] = P[-2] in the padded Split layout, chansum [J,128,128], sums [J])"""
         _, _, P2 = self.sweep().run(Pn, W2, mode, hooked_fc2=hooked_fc2)
@@ -199,15 +203,10 @@ class LightCNNSweep(object):
         # ---- head: fc2 -> [Linear hook on fc] -> fc (W+) -> Linear hook on v
         seed = buf('lc_seed', J, 1, 1, 256)
         if hooked_fc2:
-            if true_grad:
-                raise NotImplementedError('true-gradient sweep with the hooked fc2 head')
-            W2p = eng._ws.get(('W2p', W2.data_ptr()))
-            if W2p is None:
-                W2p = torch.clamp_min(W2, 0).unsqueeze(0).contiguous()
-                eng._ws[('W2p', W2.data_ptr())] = W2p
+            W2p = eng.fc2_rows(W2, signed=true_grad)      # relu(W2) (whitebox.py:371-374); the signed rows for true gradients
             raw = buf('lc_seed_raw', J, 1, 1, 256)
             be.head_seed(Pn, W2p, raw.view(J, 256))
-            self.fire('Linear', 7, raw, (J, 1, 1, 256), s0=S['fc'], s1=S['fcpos'], out='lc_seed')
+            self.fire('Linear', 7, raw, (J, 1, 1, 256), s0=S['fc'], s1=S['fc'] if true_grad else S['fcpos'], out='lc_seed')
         else:
             be.head_seed(Pn, W2, seed.view(J, 256))
         z = dgrad(seed, eng.fc_pack, buf('lc_gv', J, 1, 1, 8192)).view(J, 8, 8, 128)

@@ -42,6 +42,32 @@ def gemm_planes(B, impl):
     raise ValueError(impl)
 
 
+def to_pair(x):
+    """fp32 [..., C] -> pair tensor of the bf16x2 plan (include/xfrb.h XFRB_IMPL_BF16X2): each row stored as
+    [C bf16 hi | C bf16 lo], hi = bf16(x), lo = bf16(x - hi), viewed as float32 [..., C] (the same bytes per row)."""
+    x = x.float().contiguous()
+    hi = x.bfloat16()
+    lo = (x - hi.float()).bfloat16()
+    return torch.cat((hi, lo), dim=-1).contiguous().view(torch.float32)
+
+
+def from_pair(p):
+    """pair tensor [..., C] (float32 view) -> fp32 hi + lo (exact: both terms lie inside one 24-bit window)"""
+    b = p.contiguous().view(torch.bfloat16)
+    C = b.shape[-1] // 2
+    return b[..., :C].float() + b[..., C:].float()
+
+
+def bf16_planes(B, two):
+    """Weight operand of the bf16x2 plan: one bf16 plane (relu(W): excitation backprop tolerates coarse W+, the same
+    rounded W+ is used for X and for the dgrad), or (hi, lo) bf16 planes [2, rows, K] for signed weights."""
+    B = B.float().contiguous()
+    hi = B.bfloat16()
+    if not two:
+        return hi.contiguous()
+    return torch.stack((hi, (B - hi.float()).bfloat16())).contiguous()
+
+
 def dual_tile_width(cout, impl):
     """Tile width of the forward dual pack: the tcgen05 kernel runs N = 256 tiles when the layer is wide enough."""
     return 256 if (impl != 'fp32' and cout % 128 == 0) else 128
@@ -110,16 +136,28 @@ class ConvBN(object):
         self.cout, self.cin, self.R, self.S = w.shape
         self.tn = dual_tile_width(self.cout, impl)
         Bf, self.bias = pack_dual_fwd(w, b, self.tn, with_bias)
-        self.Bf = gemm_planes(Bf, impl)
-        self.Bd = gemm_planes(pack_dgrad(w, positive=True), impl)
+        self.pair_pack = impl == 'bf16x2'       # Bf / Bd are bf16 operands of the pair-tensor GEMMs (fused sweep)
+        if self.pair_pack:
+            self.Bf = bf16_planes(Bf, two=True)
+            self.Bd = bf16_planes(pack_dgrad(w, positive=True), two=False)
+        else:
+            self.Bf = gemm_planes(Bf, impl)
+            self.Bd = gemm_planes(pack_dgrad(w, positive=True), impl)
         self.Bd_signed = None       # true-gradient passes (weighted subtree) pack this lazily
+        self._Bd32 = None           # bf16x2 plan: split-TF32 pack of relu(W) for the firing-by-firing sweeps (fp32 activations)
         self.bn = fold_bn(sd, bn, with_bias)
         self._w = w                 # kept for lazy packs only
 
     def signed_dgrad(self):
         if self.Bd_signed is None:
-            self.Bd_signed = gemm_planes(pack_dgrad(self._w, positive=False), self.impl).to(self.Bd.device)
+            impl = 'tf32x3' if self.pair_pack else self.impl
+            self.Bd_signed = gemm_planes(pack_dgrad(self._w, positive=False), impl).to(self.Bd.device)
         return self.Bd_signed
+
+    def Bd32(self):
+        if self._Bd32 is None:
+            self._Bd32 = gemm_planes(pack_dgrad(self._w, positive=True), 'tf32x3').to(self.Bd.device)
+        return self._Bd32
 
     def to(self, device):
         for k in ('Bf', 'bias', 'Bd', 'bn'):

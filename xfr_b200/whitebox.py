@@ -330,9 +330,19 @@ class Whitebox(nn.Module):
 
     # ---------------------------------------------------------------- helpers
     def _engine(self):
-        if self.eps != 1E-16 and abs(self.eps - self.net.engine().be.eps) > 0:
-            self.net.engine().be.eps = float(self.eps)
-        return self.net.engine(self._ebp_with_bias)
+        """The plugin's engine for this object's with_bias setting, with this object's eps (whitebox.py:267, 325-327): fetched
+        once, eps set unconditionally - several Whitebox objects may share one plugin."""
+        eng = self.net.engine(self._ebp_with_bias)
+        eng.be.eps = eng.eps = float(self.eps)
+        return eng
+
+    def _logits(self, eng, W2):
+        """classify() of probe 0 after eng.forward(): the un-hooked triplet rows, or the network's own fc2 (with its bias)."""
+        if not self.net.hooked():
+            return eng.logits(W2)
+        y = eng.hooked_logits(W2)
+        b2 = self.net._sd.get('fc2.bias')
+        return y if b2 is None else y + b2.to(y.device).float()
 
     def _float32_to_uint8(self, img):
         """whitebox.py:439-441"""
@@ -445,8 +455,9 @@ class Whitebox(nn.Module):
         """whitebox.py:561-581: EBP restarted from one node (or the arg-max nodes) of firing k_layer."""
         assert(k_poschannel >= 0 and k_poschannel < self.net.num_classes())
         gs, W2 = self._generic(img_probe)
+        hk = self.net.hooked()            # no triplet classifier: the network's own fc2 fires (and is indexed) first
         P0 = self._onehot(k_poschannel, W2.device)
-        P_mate, names, _ = gs.run(P0, W2, self._ebp_subtree_mode, record=True)
+        P_mate, names, _ = gs.run(P0, W2, self._ebp_subtree_mode, record=True, hooked_fc2=hk)
         k_layer = int(k_layer) % len(P_mate)                    # the reference indexes Python lists: negative k_layer counts from the image
         if P_mate[k_layer] is None:
             return self._zero_map(mwp)
@@ -459,7 +470,7 @@ class Whitebox(nn.Module):
             prior = (0, e, float(Pk.reshape(-1)[e]))
         else:
             raise ValueError('invalid layerwise EBP mode "%s"' % mode)
-        P, names, P2 = gs.run(0.0 * P0, W2, self._ebp_subtree_mode, priors={int(k_layer): prior}, record=True)
+        P, names, P2 = gs.run(0.0 * P0, W2, self._ebp_subtree_mode, priors={int(k_layer): prior}, record=True, hooked_fc2=hk)
         self._set_P(gs, P, names)
         return self._finish_map(P2, mwp)[0]
 
@@ -507,9 +518,10 @@ class Whitebox(nn.Module):
             raise ValueError('layerwise_contrastive_ebp_sweep: mode "elementwise" needs a per-layer k_element; call '
                              'layerwise_contrastive_ebp per layer')
         gs, W2 = self._generic(img_probe)
+        hk = self.net.hooked()            # no triplet classifier: the network's own fc2 fires (and is indexed) first
         dev = W2.device
         Pn = torch.cat((self._onehot(k_poschannel, dev), self._onehot(k_negchannel, dev)))
-        P, names, _ = gs.run(Pn, W2, self._ebp_subtree_mode, record=True)
+        P, names, _ = gs.run(Pn, W2, self._ebp_subtree_mode, record=True, hooked_fc2=hk)
         k_layers = [int(k) % len(P) for k in k_layers]                 # negative indices as Python lists take them
         # the last firing (the Conv2d hook on the image) is not recorded: a prior there cannot reach P[-2], the map is all zero
         priors = {k: self._contrastive_prior(gs, P[k][0:1], P[k][1:2], k, mode, percentile, None).reshape(-1).contiguous()
@@ -522,7 +534,7 @@ class Whitebox(nn.Module):
         for i in range(0, len(todo), rows_per_sweep):
             chunk = todo[i:i + rows_per_sweep]
             Z = torch.zeros(len(chunk), self.net.num_classes(), device=dev)
-            _, _, P2 = gs.run(Z, W2, self._ebp_subtree_mode, priors={k: (r, priors[k]) for r, k in enumerate(chunk)})
+            _, _, P2 = gs.run(Z, W2, self._ebp_subtree_mode, priors={k: (r, priors[k]) for r, k in enumerate(chunk)}, hooked_fc2=hk)
             for k, m in zip(chunk, self._finish_map(P2, mwp)):
                 maps[k] = m
         return np.stack([maps.get(k, zero) for k in k_layers])
@@ -535,15 +547,17 @@ class Whitebox(nn.Module):
         assert(k_poschannel >= 0 and k_poschannel < self.net.num_classes())
         assert(k_negchannel >= 0 and k_negchannel < self.net.num_classes())
         gs, W2 = self._generic(img_probe)
+        hk = self.net.hooked()            # no triplet classifier: the network's own fc2 fires (and is indexed) first
         dev = W2.device
         Pn = torch.cat((self._onehot(k_poschannel, dev), self._onehot(k_negchannel, dev)))
-        P, names, _ = gs.run(Pn, W2, self._ebp_subtree_mode, record=True)         # mate and non-mate as two gradient rows
+        P, names, _ = gs.run(Pn, W2, self._ebp_subtree_mode, record=True, hooked_fc2=hk)         # mate and non-mate as two gradient rows
         k_layer = int(k_layer) % len(P)
         if P[k_layer] is None:
             return self._zero_map(mwp)
         prior = self._contrastive_prior(gs, P[k_layer][0:1], P[k_layer][1:2], k_layer, mode, percentile, k_element)
         P0 = self._onehot(k_poschannel, dev)
-        P, names, P2 = gs.run(0.0 * P0, W2, self._ebp_subtree_mode, priors={int(k_layer): (0, prior.reshape(-1).contiguous())}, record=True)
+        P, names, P2 = gs.run(0.0 * P0, W2, self._ebp_subtree_mode, priors={int(k_layer): (0, prior.reshape(-1).contiguous())}, record=True,
+                                hooked_fc2=hk)
         self._set_P(gs, P, names)
         return self._finish_map(P2, mwp)[0]
 
@@ -554,16 +568,17 @@ class Whitebox(nn.Module):
         sub-tree EBPs are batched as gradient rows (`rows_per_sweep` at a time) instead of 2n separate ebp() calls."""
         self._ebp_subtree_mode = subtree_mode                                       # the reference's side effect (651)
         gs, W2 = self._generic(img_probe)
+        hk = self.net.hooked()            # no triplet classifier: the network's own fc2 fires (and is indexed) first
         eng, be, dev = gs.eng, gs.be, W2.device
         # true gradients dA of: cross-entropy(y, 0), y[0], y[1]
-        y = eng.logits(W2)                                                          # classify(): logits of the triplet head
+        y = self._logits(eng, W2)                                                        # classify(): logits of the triplet head
         sm = torch.softmax(y, dim=1)
         Pn = torch.zeros(3, self.net.num_classes(), device=dev)
         Pn[0] = sm[0]
         Pn[0, 0] -= 1.0
         Pn[1, 0] = 1.0
         Pn[2, 1] = 1.0
-        dA, names, _ = gs.run(Pn, W2, subtree_mode, record=True, true_grad=True)
+        dA, names, _ = gs.run(Pn, W2, subtree_mode, record=True, true_grad=True, hooked_fc2=hk)
         n_layers = len(dA)
         score = torch.empty(n_layers - 1, device=dev)
         arg = torch.empty(n_layers - 1, dtype=torch.int64, device=dev)
@@ -576,7 +591,7 @@ class Whitebox(nn.Module):
         k_subtree = np.argsort(np.array(P_subtree))                                 # ascending, one per layer (697)
         # layerwise EBP for every sub-tree: P_mate once, then one-element priors as batched gradient rows
         P0 = self._onehot(k_poschannel, dev)
-        P_mate, names, _ = gs.run(P0, W2, subtree_mode, record=True)
+        P_mate, names, _ = gs.run(P0, W2, subtree_mode, record=True, hooked_fc2=hk)
         seeds = [(int(k), int(P_subtree_idx[k]), float(P_mate[k].reshape(-1)[int(P_subtree_idx[k])])) for k in k_subtree]
         del P_mate
         P_img = []
@@ -584,7 +599,7 @@ class Whitebox(nn.Module):
             chunk = seeds[i:i + rows_per_sweep]
             priors = {k: (r, e, v) for r, (k, e, v) in enumerate(chunk)}
             Z = torch.zeros(len(chunk), self.net.num_classes(), device=dev)
-            _, _, P2 = gs.run(Z, W2, subtree_mode, priors=priors)
+            _, _, P2 = gs.run(Z, W2, subtree_mode, priors=priors, hooked_fc2=hk)
             P_img += list(P2.sum(-1).cpu().numpy().astype(np.float32))             # layerwise_ebp(..., mwp=True) maps
         self.P_layername = list(names)
         if verbose:
