@@ -191,6 +191,44 @@ def gpu_library_baseline(dev, n_triplets=64, batch=16, allow_tf32=False):
         torch.cuda.empty_cache()
 
 
+def batch1_latency(wb, net, dev, x_host, enc):
+    """Every reference caller is batch 1 (whitebox.py:482-527, generate_whitebox_saliency.py:81-205): wall-clock latency of one
+    Whitebox.contrastive_ebp / truncated_contrastive_ebp / weighted_subtree_ebp(topk=32) call through the public API with a
+    host-resident probe (H2D of the probe and D2H of the map inside), median of several calls after warm-up."""
+    from xfr_b200 import whitebox
+    res = {}
+    net.set_triplet_classifier(enc[0:1] / 2500.0, enc[1:2] / 2500.0)
+    x1 = x_host[0:1]
+
+    def med(fn, n):
+        fn()
+        fn()
+        ts = []
+        for _ in range(n):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            ts.append(1e3 * (time.perf_counter() - t0))
+        ts.sort()
+        return ts[len(ts) // 2]
+    l0 = net.engine().be.launches
+    wb.contrastive_ebp(x1, 0, 1)
+    res['contrastive_ebp_launches'] = net.engine().be.launches - l0
+    res['contrastive_ebp'] = med(lambda: wb.contrastive_ebp(x1, 0, 1), 15)
+    res['truncated_contrastive_ebp'] = med(lambda: wb.truncated_contrastive_ebp(x1, 0, 1, percentile=20), 15)
+    P = torch.zeros(1, 2)
+    P[0, 0] = 1
+    res['ebp'] = med(lambda: wb.ebp(x1, P), 15)
+    wbs = whitebox.Whitebox(net, ebp_subtree_mode='norelu')
+    unit = enc[0:2] / torch.norm(enc[0:2], dim=1, keepdim=True)
+    net.set_triplet_classifier(unit[0:1], unit[1:2])
+    res['weighted_subtree_ebp_topk32'] = med(lambda: wbs.weighted_subtree_ebp(x1, 0, 1, topk=32, verbose=False, do_max_subtree=False,
+                                                                              do_mated_similarity_gating=False, subtree_mode='all'), 3)
+    res['note'] = 'ms per call, public batch-1 API, host probe in / numpy map out'
+    return res
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's CPU implementation of the path on this box's host cores.  The reference is
     pure Python on torch and cannot travel to the GPU box, so this is the oracle port (oracle/stresnet_oracle.py, pinned to
@@ -231,6 +269,212 @@ def run_reference(args, rank):
     }))
 
 
+# ---------------------------------------------------------------------------------------------------------------------------
+# The other BASELINE.json workloads (configs[2], [3], [4]); `--workload contrastive` (configs[1]) is the headline above.
+WORKLOADS = {
+    'layer_sweep': ('truncated contrastive EBP layer-sweep: layerwise_contrastive_ebp(mode=percentile, 20 %) at every affine firing, '
+                    'ResNet-101 (BASELINE configs[2])', 'layer-sweep saliency maps/sec (ResNet-101, 224x224)', 'maps/s'),
+    'weighted_subtree': ('weighted subtree triplet EBP, ResNet-101, eval-flow settings (ctor norelu, subtree_mode all, topk 32, no gating; '
+                         'BASELINE configs[3]: the 541-job inpainting-game set, synthetic pixels)', 'weighted-subtree saliency jobs/sec (ResNet-101, 224x224)', 'jobs/s'),
+    'lightcnn': ('Light-CNN-29v2 MFM-layer EBP, 128x128 grayscale, batch 512 per GPU (BASELINE configs[4])',
+                 'EBP saliency maps/sec (Light-CNN-29v2, 128x128)', 'maps/s'),
+}
+AFFINE = ('Conv', 'Linear', 'AvgPool', 'BatchNorm')
+# algorithmic HBM bytes (fp32), SURVEY.md section 8d element counts: ResNet-101 S_i 13.65 M / S_o 14.20 M, Light-CNN S_i 2.11 M / S_o 6.32 M
+R101_ROW_BYTES = 4.0 * (14.20e6 + 13.65e6)        # one gradient row of an EBP backward sweep: gradient read + write per layer
+R101_SAVED_BYTES = 4.0 * 2 * 14.20e6              # saved o / xr, read once per sweep of rows over the same probe
+R101_FWD_BYTES = 4.0 * (13.65e6 + 2 * 14.20e6)
+LC_MAP_BYTES = 4.0 * ((2.11e6 + 6.32e6) + (6.32e6 + (6.32e6 + 2.11e6)))     # forward (in + conv out) + backward (saved c + gradient read / write)
+
+
+def _synthetic_jobs(n, seed):
+    """n (im_mates, im_nonmates, probe_im) jobs of 224x224x3 uint8 images: 2 mates, 2 non-mates, 1 probe each - the shape of an
+    inpainting-game job (generate_whitebox_saliency.py:222-416); the game's images are git-LFS pointers, hence synthetic pixels"""
+    from xfr_b200 import synth
+    x = synth.smooth_probes(5 * n, seed=seed) + torch.tensor(synth.MEAN_RGB).view(1, 3, 1, 1)
+    im = [np.ascontiguousarray(t.permute(1, 2, 0).numpy().astype(np.uint8)) for t in x]
+    return [(im[5 * i:5 * i + 2], im[5 * i + 2:5 * i + 4], im[5 * i + 4]) for i in range(n)]
+
+
+def cpu_port_extra(workload, budget_s, threads):
+    """CPU baseline of the extra workloads on a bounded sample: the reference algorithm restated (oracle/, torch CPU fp32)."""
+    from xfr_b200 import synth
+    torch.set_num_threads(threads)
+    if workload == 'lightcnn':
+        from oracle import lightcnn_oracle as LO
+        sd = synth.lightcnn_state_dict(0, 2)
+        x = synth.lightcnn_probes(64, seed=3, smooth=False)
+        W2 = torch.randn(64, 2, 256, generator=torch.Generator().manual_seed(4))
+        P = torch.zeros(1, 2)
+        P[0, 0] = 1
+        LO.ebp(sd, x[:1], P, W2[:1], mode='affineonly')
+        t0, n = time.time(), 0
+        while time.time() - t0 < budget_s and n < 63:
+            n += 1
+            LO.ebp(sd, x[n:n + 1], P, W2[n:n + 1], mode='affineonly')
+        return n / (time.time() - t0), '%d probes, batch 1, ebp in mode affineonly' % n
+    from oracle import stresnet_oracle as O
+    sd = synth.stresnet_state_dict(0)
+    x = synth.synthetic_probes(1, seed=1)
+    W2 = torch.randn(1, 2, 512, generator=torch.Generator().manual_seed(5)) * 0.02
+    P = torch.zeros(1, 2)
+    P[0, 0] = 1
+    mode = 'affineonly_with_prior' if workload == 'layer_sweep' else 'all'
+    O.ebp_mwp(sd, x, P, W2, mode=mode, stop_at_stem=True)
+    t0, n = time.time(), 0
+    while time.time() - t0 < budget_s:
+        n += 1
+        O.ebp_mwp(sd, x, P, W2, mode=mode, stop_at_stem=True)          # one forward + one hooked backward = one ebp() of the reference
+    t_ebp = (time.time() - t0) / n
+    if workload == 'layer_sweep':
+        # the reference runs three ebp() per (triplet, layer) (whitebox.py:584-644): mate, non-mate, the prior-restarted third pass
+        return 1.0 / (3 * t_ebp), '%d ebp() passes timed, 3 per layer map as the reference runs them (whitebox.py:584-644)' % n
+    # weighted_subtree_ebp: 3 true-gradient passes + 1 + 2 per firing (layerwise_ebp = 2 ebp()) = 2*377 + 4 passes per job (whitebox.py:647-737)
+    passes = 2 * 377 + 4
+    return 1.0 / (passes * t_ebp), ('%d ebp() passes timed and extrapolated to the %d passes one job makes (whitebox.py:647-737; the '
+                                    'unmodified reference measured 499 s per job on 8 cores of the build container)' % (n, passes))
+
+
+def run_extra(args, rank, local, world):
+    """--workload layer_sweep | weighted_subtree | lightcnn: the same JSON schema as the headline workload."""
+    import torch.distributed as dist
+    from xfr_b200 import inpaintgame as IG
+    from xfr_b200 import synth, whitebox
+    label, metric, unit = WORKLOADS[args.workload]
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        cores = os.cpu_count()
+        for k in range(args.warmup):
+            cpu_port_extra(args.workload, 2.0, cores)
+        vals = [cpu_port_extra(args.workload, 6.0, cores) for _ in range(max(1, args.steps))]
+        v = sum(x[0] for x in vals) / len(vals)
+        print(json.dumps({'impl': 'reference', 'metric': metric, 'value': v, 'unit': unit, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+                          'ms_per_step': 6000.0, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                          'config': {'workload': label + ' (bounded sample)', 'sample': vals[-1][1]},
+                          'cpu_baseline': {'value': v, 'unit': unit, 'cores': cores, 'kind': 'port', 'sample': vals[-1][1]},
+                          'e2e': {'value': v, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        return
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    gemm = args.gemm if args.gemm != 'bf16x2' else 'tf32x3'       # the firing-by-firing sweeps run on the split-TF32 kernels
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    cfg = {'workload': label, 'gemm': gemm, 'weights': 'seeded synthetic'}
+    if args.workload == 'lightcnn':
+        B = args.batch if args.batch != 256 else 512
+        sd = {k: v.to(dev) for k, v in synth.lightcnn_state_dict(0, 2).items()}
+        net = whitebox.WhiteboxLightCNN(sd, impl=gemm)
+        wb = whitebox.Whitebox(net, ebp_subtree_mode='affineonly')               # demo/test_whitebox.py:232-254
+        whitebox._CHUNK = 128
+        x_host = synth.lightcnn_probes(B, seed=3 + rank, smooth=False).pin_memory()
+        W2 = torch.randn(B, 2, 256, generator=torch.Generator().manual_seed(4)).to(dev)
+        net.set_triplet_classifiers(W2[:, 0], W2[:, 1])
+        P = torch.zeros(1, 2)
+        P[0, 0] = 1
+        x_dev = x_host.to(dev)
+        units = B
+        step_e2e = lambda: wb.ebp_batch(x_host, P)
+        step_res = lambda: wb.ebp_batch(x_dev, P)
+        h2d, d2h = x_host.numel() * 4, B * 128 * 128 * 4
+        alg_bytes = LC_MAP_BYTES * B
+        cfg.update(batch=B, mode='affineonly', chunk=128, l2='%.0f MB of probes + saved tensors per sweep, larger than L2' % (x_host.numel() * 4 / 1e6))
+    else:
+        sd = {k: v.to(dev) for k, v in synth.stresnet_state_dict(0).items()}
+        T = args.batch if args.batch != 256 else 2                            # triplets / jobs per GPU per step
+        if args.workload == 'layer_sweep':
+            net = whitebox.WhiteboxSTResnet(sd, impl=gemm)
+            wb = whitebox.Whitebox(net)
+            x_host = synth.synthetic_probes(T, seed=100 + rank).pin_memory()
+            with torch.no_grad():
+                enc = net.encode(synth.synthetic_probes(2 * T, seed=1000 + rank).to(dev))
+            rows = [(enc[i:i + 1] / 2500.0, enc[T + i:T + i + 1] / 2500.0) for i in range(T)]
+            net.set_triplet_classifier(*rows[0])
+            wb.layerwise_contrastive_ebp_sweep(x_host[0:1], 0, 1, [3], mode='percentile', percentile=20)
+            names = wb.P_layername
+            ks = [k for k, n in enumerate(names[:-1]) if any(a in n for a in AFFINE)]     # non-affine firings give all-zero maps in this mode
+            x_dev = x_host.to(dev)
+            units = T * len(ks)
+
+            def sweep(x):
+                out = []
+                for i in range(T):
+                    net.set_triplet_classifier(*rows[i])
+                    out.append(wb.layerwise_contrastive_ebp_sweep(x[i:i + 1], 0, 1, ks, mode='percentile', percentile=20, rows_per_sweep=args.rows))
+                return out
+            step_e2e = lambda: sweep(x_host)
+            step_res = lambda: sweep(x_dev)
+            h2d, d2h = x_host.numel() * 4, units * 112 * 112 * 4
+            nsweeps = -(-len(ks) // args.rows)
+            alg_bytes = T * (R101_FWD_BYTES + (len(ks) + 2) * R101_ROW_BYTES + (nsweeps + 1) * R101_SAVED_BYTES)
+            cfg.update(triplets_per_gpu_per_step=T, layers_per_triplet=len(ks), firings=len(names), rows_per_sweep=args.rows,
+                       note='BASELINE configs[2] runs 1,024 triplets on 8 GPUs: 1024 x %d layer maps' % len(ks),
+                       l2='every sweep streams > 1 GB of saved tensors and gradients (larger than L2)')
+        else:
+            net = whitebox.WhiteboxSTResnet(sd, impl=gemm)
+            wb = whitebox.Whitebox(net, ebp_subtree_mode='norelu')                 # create_wbnet.py:26-27
+            jobs = _synthetic_jobs(T, seed=200 + rank)
+            units = T
+            step_e2e = lambda: IG.run_weighted_subtree_triplet_ebp_sharded(wb, jobs, subtree_mode_weighted='all', ebp_version=None, device=dev, topk=32)
+            step_res = step_e2e               # the job API takes host images (numpy): there is no device-resident variant of a job
+            h2d, d2h = T * 5 * 224 * 224 * 3 * 4, T * 112 * 112 * 4
+            nrows = 3 + 1 + 377
+            alg_bytes = T * (5 * R101_FWD_BYTES + nrows * R101_ROW_BYTES + (2 + -(-377 // 48)) * R101_SAVED_BYTES)
+            cfg.update(jobs_per_gpu_per_step=T, topk=32, subtree_mode='all', ctor_mode='norelu', gating=False,
+                       note='BASELINE configs[3]: the 541 resnetv4 probe jobs of filtered_masks_threshold-resnetv4_pytorch.csv; jobs are '
+                            'independent, so the set takes 541 / value seconds',
+                       l2='every sweep streams > 1 GB of saved tensors and gradients (larger than L2)')
+    eng = net.engine(wb._ebp_with_bias)
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = ev(), ev()
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+    for _ in range(args.warmup):
+        step_res()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = eng.be.launches
+    ms = timed(step_res, args.steps)
+    launches = eng.be.launches - l0
+    ms_e2e = timed(step_e2e, args.steps) if step_e2e is not step_res else ms
+    clocks = sampler.summary()
+    total = world * units * args.steps
+    peak, peak_src = measured_peaks()
+    ach = alg_bytes * args.steps / (ms / 1e3) / 1e9
+    out = {'metric': metric, 'value': total / (ms / 1e3), 'unit': unit, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+           'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+           'dtype': 'f32 (split-TF32 tcgen05: 3 passes on signed weights, 2 on W+; fp32 accumulate)', 'data': 'synthetic', 'config': cfg,
+           'e2e': {'value': total / (ms_e2e / 1e3), 'unit': unit, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                   'ms_per_step': ms_e2e / args.steps},
+           'gpu_launches': int(launches), 'clocks': clocks,
+           'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
+                        'kernel': 'whole step (firing-by-firing sweep: xfrb_hook + xfrb_dgrad_plain per firing)' if args.workload != 'lightcnn'
+                        else 'whole step (Light-CNN sweep: conv_bias GEMMs, mfm / pool kernels, xfrb_hook per firing)',
+                        'alg_bytes_per_step': alg_bytes, 'peak_source': peak_src}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count()
+        v, sample = cpu_port_extra(args.workload, 12.0, cores)
+        out['cpu_baseline'] = {'value': v, 'unit': unit, 'cores': cores, 'kind': 'port', 'sample': sample}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -238,17 +482,23 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=256, help='triplets per GPU per step')
     ap.add_argument('--chunk', type=int, default=256, help='probes per engine sweep (256: 64 GB workspace, +4 %% over 128)')
-    ap.add_argument('--gemm', default='tf32x3', choices=['tf32x3', 'tf32x3full', 'tf32', 'fp32', 'tf32x2f', 'tf32x3b1', 'bf16x2'],
-                    help="tf32x3 (default): the parity-grade plan; tf32x2f / tf32x3b1: opt-in hybrids (kernels.HYBRID_IMPLS)")
+    ap.add_argument('--gemm', default='bf16x2', choices=['tf32x3', 'tf32x3full', 'tf32', 'fp32', 'tf32x2f', 'tf32x3b1', 'bf16x2'],
+                    help="bf16x2 (default, = xfr_b200.whitebox.DEFAULT_IMPL); tf32x3 / tf32x3full: split-TF32 plans; fp32: CUDA cores")
     ap.add_argument('--mode', default='affineonly_with_prior')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='contrastive', choices=['contrastive'] + sorted(WORKLOADS),
+                    help='contrastive = BASELINE configs[1] (the headline); the others are configs[2], [3], [4]')
+    ap.add_argument('--rows', type=int, default=48, help='gradient rows per firing-by-firing sweep (layer_sweep)')
+    ap.add_argument('--no-extras', action='store_true', help='skip the batch-1 latency and library-comparator legs')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.workload != 'contrastive':
+        return run_extra(args, rank, local, world)
     if args.impl == 'reference':
         return run_reference(args, rank)
 
@@ -371,6 +621,11 @@ def main():
                      'tensor_tflops_whole_step': FLOP_PER_MAP * B * args.steps / (ms / 1e3) / 1e12 / 1.0,
                      'kernels': families},
     }
+    if rank == 0 and world == 1 and not args.no_extras:
+        out['latency_ms_batch1'] = batch1_latency(wb, net, dev, x_host, enc)
+        torch.cuda.empty_cache()
+        out['gpu_library_baseline'] = gpu_library_baseline(dev, 64, 32)
+        out['gpu_library_baseline']['speedup_of_this_repo'] = value / out['gpu_library_baseline']['value']
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count()
         n = 40                                   # ~10 s of host work at the ~4 maps/s measured on the GPU box's 16 cores

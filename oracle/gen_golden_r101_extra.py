@@ -1,6 +1,6 @@
 """Further ResNet-101 golden vectors from the UNMODIFIED reference (TEST INFRASTRUCTURE; build container only):
 
-    python oracle/gen_golden_r101_extra.py [--only wellcond|subtree]
+    python oracle/gen_golden_r101_extra.py [--only wellcond|subtree|bighead]
 
   stresnet101_wellcond_seed0.npz
       The seeded random-weight network encodes every image almost identically (cos(mate, non-mate) = 0.9999), so the
@@ -13,6 +13,9 @@
       Whitebox.weighted_subtree_ebp on the full [3,4,23,3] net with the settings of the evaluation flow
       (generate_whitebox_saliency.py:122-205: ctor mode 'norelu', subtree_mode 'all', topk 32, no mated-similarity gating,
       unit-norm rows): ~760 hooked ebp() calls, ~10 minutes on 8 cores.  Pins the 378-firing case incl. np.argsort ties.
+  stresnet101_bighead_seed0.npz
+      The network's own hooked 65,359-class fc2 head (33 M parameters): mean-EBP prior of the blackbox
+      (uniform prior over all classes) and the demo's contrastive_ebp(x, 0, 100).
 """
 import argparse
 import os
@@ -98,6 +101,27 @@ def run_subtree(out):
     print('wrote %s (%d arrays, %.0f KB, %.0fs)' % (out, len(G), os.path.getsize(out) / 1024, time.time() - t0))
 
 
+def run_bighead(out, num_classes=65359):
+    """The STR network's own 65,359-class fc2 (no triplet classifier: hooked, W+ in the backward): STRise.mean_ebp_prior
+    (blackbox.py:280-294: ebp with a uniform prior over all classes) and the demo's contrastive_ebp(x, 0, 100)
+    (demo/test_whitebox.py:92-99)."""
+    t0 = time.time()
+    probe = synth.smooth_probes(3, seed=1)[0:1]
+    G = {'num_classes': np.array(num_classes)}
+    wb = Whitebox(WhiteboxSTResnet(ref_net(LAYERS, 0, num_classes)))
+    assert wb.net.num_classes() == num_classes
+    P = torch.ones((1, wb.net.num_classes()))
+    G['mean_ebp'] = wb.ebp(probe, P)
+    G['mean_ebp_mwp'] = wb.ebp(probe, P, mwp=True)
+    G['n_firings'] = np.array(len(wb.P_layername))
+    G['cebp_0_100'] = wb.contrastive_ebp(probe, k_poschannel=0, k_negchannel=100)
+    P1 = torch.zeros((1, num_classes))
+    P1[0][100] = 1.0
+    G['ebp_100_mwp'] = wb.ebp(probe, P1, mwp=True)
+    np.savez_compressed(out, **G)
+    print('wrote %s (%d arrays, %.0f KB, %.0fs)' % (out, len(G), os.path.getsize(out) / 1024, time.time() - t0))
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--only', default=None)
@@ -108,3 +132,5 @@ if __name__ == '__main__':
         run_wellcond(os.path.join(gold, 'stresnet101_wellcond_seed0.npz'))
     if a.only in (None, 'subtree'):
         run_subtree(os.path.join(gold, 'stresnet101_subtree_seed0.npz'))
+    if a.only in (None, 'bighead'):
+        run_bighead(os.path.join(gold, 'stresnet101_bighead_seed0.npz'))

@@ -34,7 +34,8 @@ def test_bf16_packs():
     assert float((L.Bf.float().sum(0) - W).abs().max() / W.abs().max()) < 2.0 ** -15     # signed weights: two bf16 terms
     Wp = L32.Bd.sum(0)
     assert float((L.Bd.float() - Wp).abs().max() / Wp.abs().max()) < 2.0 ** -8 and float(L.Bd.float().min()) >= 0.0
-    assert torch.equal(L.Bd32(), L32.Bd) and torch.equal(L.signed_dgrad(), L32.signed_dgrad())   # fp32-activation sweeps keep split-TF32 packs
+    # the fp32-activation sweeps (layerwise / weighted-subtree operators) multiply the SAME bf16-rounded relu(W) as a split-TF32 pack
+    assert torch.equal(L.Bd32()[0], L.Bd.float()) and not L.Bd32()[1].any() and torch.equal(L.signed_dgrad(), L32.signed_dgrad())
 
 
 def _engine(layers):

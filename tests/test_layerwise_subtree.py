@@ -157,11 +157,7 @@ def test_layer_sweep_emulated():
     _check_layer_sweep(False, 2e-3)
 
 
-# Written after the round's GPU budget was spent: the sweep composes kernels the other GPU tests cover (row-indexed tensor
-# priors, P recording), but this test itself has not run on a B200 yet - skipped unless XFRB_RUN_UNVERIFIED=1 until it has.
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get('XFRB_RUN_UNVERIFIED'), reason='not yet run on a B200 (added after the GPU budget of round 1 '
-                    'was spent): set XFRB_RUN_UNVERIFIED=1 to run it, under a timeout')
 def test_layer_sweep_gpu():
     _check_layer_sweep(True, 2e-2)
 
@@ -195,6 +191,53 @@ def test_layerwise_contrastive_modes_emulated():
 @pytest.mark.gpu
 def test_weighted_subtree_gpu():
     _check_subtree(True)
+
+
+def _check_subtree_resnet101(gpu):
+    """weighted_subtree_ebp on the full [3,4,23,3] net with the evaluation flow's settings (generate_whitebox_saliency.py:122-205)
+    against one run of the unmodified reference (tests/golden/stresnet101_subtree_seed0.npz, ~760 hooked ebp() calls, 499 s on 8
+    cores).  The 32 selected firings must be the SAME SET; their order may differ only inside groups of firings chained on one
+    tensor, whose scores tie exactly (np.argsort is not stable across summation orders) and whose sub-tree maps coincide."""
+    from helpers import GOLD
+    G = np.load(os.path.join(GOLD, 'stresnet101_subtree_seed0.npz'))
+    probe = synth.smooth_probes(3, seed=1)[0:1]
+    wb = whitebox.Whitebox(_net(L101, gpu), ebp_subtree_mode='norelu')
+    wb.net.set_triplet_classifier(torch.from_numpy(G['row_mate']), torch.from_numpy(G['row_nonmate']))
+    smap, P_img, P_sub, k_sub = wb.weighted_subtree_ebp(probe, 0, 1, topk=32, verbose=False, do_max_subtree=False,
+                                                        do_mated_similarity_gating=False, subtree_mode='all')
+    assert len(wb.P_layername) == int(G['n_firings']) == 378
+    k_sub, k_ref = [int(k) for k in k_sub], [int(k) for k in G['ws_k']]
+    assert set(k_sub) == set(k_ref)
+    tol = 2e-2 if gpu else 1e-4          # scores are maxima of true-gradient products: measured <= 1.2e-2 on the tensor-core plans
+    assert sorted(P_sub) == pytest.approx(sorted(G['ws_scores']), rel=tol)
+    score = dict(zip(k_ref, G['ws_scores']))
+    for pos, (a, b) in enumerate(zip(k_sub, k_ref)):
+        assert a == b or abs(score[a] - score[b]) <= (2 * tol if gpu else 1e-6) * abs(score[b]), (pos, a, b)      # reordered only inside (near-)ties
+    ref_max = dict(zip(k_ref, G['ws_maps_max']))
+    off = [k for k, m in zip(k_sub, P_img) if abs(float(np.max(m)) / ref_max[k] - 1.0) > (5e-2 if gpu else 1e-3)]
+    r = rel_err(smap, G['ws_smap'])
+    print('weighted_subtree_ebp ResNet-101: %d / 32 sub-tree maps off in their maximum %s, smap max-abs/max(ref) %.3g' % (len(off), off, r))
+    # a sub-tree is seeded at the arg-max ELEMENT of its firing's gated true gradient (whitebox.py:687-696): on the tensor-core plans a
+    # near-tie between two elements may pick the other one (measured: firing 333), which changes that one map, not the selected set
+    assert len(off) <= (2 if gpu else 0)
+    assert smap.dtype == np.float32 and r < (1e-1 if gpu else 1e-3) and np.abs(smap - G['ws_smap']).max() < 1e-4
+
+
+@pytest.mark.gpu
+def test_weighted_subtree_resnet101_gpu():
+    _check_subtree_resnet101(True)
+
+
+@pytest.mark.skipif(not os.environ.get('XFRB_SLOW'), reason='200 s of kernel emulation on 8 cores (set XFRB_SLOW=1); the GPU twin runs in the -m gpu suite')
+def test_weighted_subtree_resnet101_emulated():
+    _check_subtree_resnet101(False)
+
+
+@pytest.mark.gpu
+def test_other_modes_gpu():
+    """the six other layerwise_contrastive_ebp modes, layerwise_ebp 'argmax', truncation percentiles 0 / 50 / 80 / 100 on the CUDA
+    kernels against the reference's outputs"""
+    _check_other_modes(True, 2e-2)
 
 
 @pytest.mark.gpu

@@ -143,3 +143,34 @@ def test_opt_in_plans_emulated(layers):
         eng = StResnetEngine(sd, EmulBackend(impl_name='tf32x3', bwd_single_pass=True), layers)
         c = eng.contrastive(x, W2).clone().numpy()
         assert np.abs(c[0] - G['cebp_awp_smooth']).max() > 1e-4          # why that plan stays opt-in
+
+
+def _bighead_check(eng_factory, to_dev, tol):
+    """the STR network's own 65,359-class fc2 (33 M parameters, hooked: relu(W) in the backward and a leading Linear
+    firing) - STRise.mean_ebp_prior (blackbox.py:280-294: uniform prior over all classes) and the demo's contrastive_ebp(x, 0, 100)
+    (demo/test_whitebox.py:92-99) against the reference's outputs (tests/golden/stresnet101_bighead_seed0.npz)."""
+    import os
+    from helpers import GOLD
+    G = np.load(os.path.join(GOLD, 'stresnet101_bighead_seed0.npz'))
+    C = int(G['num_classes'])
+    assert C == 65359
+    sd = synth.stresnet_state_dict(0, L101, C)
+    eng = eng_factory(sd)
+    x = to_dev(synth.smooth_probes(3, seed=1)[0:1].permute(0, 2, 3, 1).contiguous())
+    W2 = to_dev(sd['fc2.weight'])
+    m = eng.ebp(x, to_dev(torch.ones(1, C)), W2, hooked_fc2=True, saliency=False).cpu().numpy()
+    assert rel_err(m[0], G['mean_ebp_mwp']) < tol
+    s = eng.ebp(x, to_dev(torch.ones(1, C)), W2, hooked_fc2=True).cpu().numpy()
+    assert rel_err(s[0], G['mean_ebp']) < tol
+    P1 = torch.zeros(1, C)
+    P1[0, 100] = 1
+    m = eng.ebp(x, to_dev(P1), W2, hooked_fc2=True, saliency=False).cpu().numpy()
+    assert rel_err(m[0], G['ebp_100_mwp']) < tol
+    c = eng.contrastive(x, W2, k_pos=0, k_neg=100, hooked_fc2=True, num_classes=C).cpu().numpy()
+    assert np.abs(c[0] - G['cebp_0_100']).max() < 1e-4
+    return rel_err(c[0], G['cebp_0_100'])
+
+
+def test_big_hooked_head_emulated():
+    r = _bighead_check(lambda sd: StResnetEngine(sd, EmulBackend(), L101), lambda t: t, 1e-5)
+    assert r < 5e-2

@@ -19,16 +19,20 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines / out: A/B variants of the library (tuning knobs of csrc/conv_tc.cuh) next to the product build:
+    python -m xfr_b200.build --define XFRB_PAIRA_EW=12 --out libxfr_b200_ew12.so ; XFRB_LIB=... selects one at run time"""
+    lib = LIB if out is None else os.path.join(HERE, out)
+    if out is None and not defines and not force and not _stale():
         return LIB
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
+    bdir = os.path.join(HERE, 'build' if out is None else 'build_' + os.path.splitext(out)[0])
+    os.makedirs(bdir, exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(HERE, 'build', src.replace('.cu', '.o'))
-        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        obj = os.path.join(bdir, src.replace('.cu', '.o'))
+        cmd = [nvcc] + NVCC_FLAGS + ['-D' + d for d in defines] + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False
@@ -39,10 +43,12 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError('nvcc failed')
-    cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-lcudart']
+    cmd = [nvcc, '-shared', '-o', lib] + objs + ['-lcudart']
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    defs = [sys.argv[i + 1] for i, a in enumerate(sys.argv) if a == '--define']
+    outs = [sys.argv[i + 1] for i, a in enumerate(sys.argv) if a == '--out']
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, defines=defs, out=outs[0] if outs else None))

@@ -9,6 +9,26 @@
 
 namespace xfrb {
 
+// tuning knobs of the bf16x2 (PAIRA) epilogue, overridable at build time for A/B runs (python -m xfr_b200.build --define ...)
+// Measured on a B200, 256-probe ResNet-101 sweeps (profiles/r2_notes.md): none of the variants beats the layout of the TF32 kernels
+// (XFRB_PAIRA_EW 0: idle split warpgroup kept, 8 epilogue warps at 200 registers, 12 at 128 for JOIN) - 3,855-3,897 maps/s against
+// 3,741 (EW 8, 224 registers, JOIN loads ahead), 3,737 (EW 12), 3,701 (EW 8 unpaired), 3,670 (+ TMEM prefetch), 3,597 (no per-tile barrier)
+#ifndef XFRB_PAIRA_EW
+#define XFRB_PAIRA_EW 0               /* 0: the warp layout of the TF32 kernels; 8 / 12: the split warpgroup's warps become epilogue warps (224 / 152 registers) */
+#endif
+#ifndef XFRB_PAIRA_PAIRED
+#define XFRB_PAIRA_PAIRED 0           /* a warp takes the two 16-column slabs of a 32-column group back to back: both halves of every 128-byte line */
+#endif
+#ifndef XFRB_PAIRA_JOIN_L2_PREFETCH
+#define XFRB_PAIRA_JOIN_L2_PREFETCH 0 /* JOIN: prefetch.global.L2 of the next slab's operand lines (measured -2 %) */
+#endif
+#ifndef XFRB_PAIRA_PRM_DIRECT
+#define XFRB_PAIRA_PRM_DIRECT 0       /* per-channel constants straight from global memory, no per-tile barrier (measured slower: warps drift apart) */
+#endif
+#ifndef XFRB_PAIRA_ACC_PREFETCH
+#define XFRB_PAIRA_ACC_PREFETCH 0     /* request the next slab's accumulator from TMEM before this slab's math */
+#endif
+
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                       // 32 fp32 = one 128-byte swizzle row
 constexpr int TC_FIRST_SPLIT_WARP = 4;           // warpgroup 0: TMA (activations), MMA, TMA (weights), idle; warpgroup 1: split
@@ -222,12 +242,16 @@ struct TcCfg {
     // longest hook chain) is what bounds them: 707 -> 615 us per launch with 12 warps; the others lose 6 % to the smaller
     // register budget.  setmaxnreg moves registers between whole warpgroups inside the pool the CTA was LAUNCHED with
     // (threads x the most __launch_bounds__ allows; asking for more blocks setmaxnreg.inc forever).
-    static constexpr int EPI_WARPS = KIND == EPI_JOIN ? 12 : 8;
-    static constexpr int THREADS = (TC_FIRST_EPI_WARP + EPI_WARPS) * 32;                  // 512 / 640
+    // bf16x2 plan (PAIRA): no operand-split warpgroup - its four warps become epilogue warps: 4 producer warps + 12 epilogue
+    // warps = 512 threads for every kind (a CTA pair's "landed" relay moves to the idle warp 3 of the producer warpgroup)
+    static constexpr bool REPURPOSE = PAIRA && XFRB_PAIRA_EW != 0;
+    static constexpr int FIRST_EPI_WARP = REPURPOSE ? TC_FIRST_SPLIT_WARP : TC_FIRST_EPI_WARP;
+    static constexpr int EPI_WARPS = REPURPOSE ? XFRB_PAIRA_EW : (KIND == EPI_JOIN ? 12 : 8);
+    static constexpr int THREADS = (FIRST_EPI_WARP + EPI_WARPS) * 32;                     // 512 / 640
     static constexpr int REGS_LAUNCH = (65536 / THREADS) / 8 * 8;                          // 128 / 96
-    static constexpr int REGS_PRODUCER = EPI_WARPS == 12 ? 48 : 56;
-    static constexpr int REGS_EPILOGUE = EPI_WARPS == 12 ? 128 : 200;
-    static_assert(TC_FIRST_EPI_WARP * 32 * REGS_PRODUCER + EPI_WARPS * 32 * REGS_EPILOGUE <= THREADS * REGS_LAUNCH,
+    static constexpr int REGS_PRODUCER = REPURPOSE ? 56 : (EPI_WARPS == 12 ? 48 : 56);
+    static constexpr int REGS_EPILOGUE = REPURPOSE ? (EPI_WARPS == 12 ? 152 : 224) : (EPI_WARPS == 12 ? 128 : 200);
+    static_assert(FIRST_EPI_WARP * 32 * REGS_PRODUCER + EPI_WARPS * 32 * REGS_EPILOGUE <= THREADS * REGS_LAUNCH,
                   "setmaxnreg budgets exceed the CTA's register pool");
     static constexpr uint32_t TR_BYTES = EPI_WARPS * 2048;      // per epilogue warp: 32 rows x 16 columns transpose slab
     static constexpr uint32_t BAR_BYTES = 512;
@@ -290,7 +314,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
             mbar_init(split_bar(s), CTA2 ? 8 : 4);               // pair: the peer's split warps arrive here too (leader's copy)
-            if (CTA2) mbar_init(land_bar(s), 8);
+            if (CTA2) mbar_init(land_bar(s), PAIRA ? 2 : 8);         // PAIRA: one relay lane per CTA (warp 3)
         }
         for (int s = 0; s < NB; ++s) {
             mbar_init(fullb_bar(s), 1);
@@ -405,6 +429,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
+    } else if (warp == 3) {
+        // ===================== bf16x2 CTA pair: relay "this CTA's stage landed" to the leader's MMA thread =====================
+        if (PAIRA && CTA2 && lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = worker; tile < total_tiles; tile += nworkers) {
+                for (int kb = 0; kb < g.num_k; ++kb) {
+                    mbar_wait(full_bar(s), ph);
+                    if (!leader) mbar_arrive_remote(land_bar(s), 0);
+                    else mbar_arrive(land_bar(s));
+                    if (++s == NA) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
     } else if (warp == 1) {
         // ===================== MMA issuer (cta_group::2 pair: the leader CTA only) =====================
         constexpr uint32_t MM = CTA2 ? 2 * TC_BM : TC_BM;      // cta_group::2: M = 256, rows 128.. live in the peer's TMEM
@@ -483,10 +521,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     }
-    } else if (warp < TC_FIRST_EPI_WARP) {
-        // ===================== operand split (3xTF32) =====================
+    } else if (!Cfg::REPURPOSE && warp < TC_FIRST_EPI_WARP) {
+        // ===================== operand split (3xTF32; idle in the bf16x2 plan) =====================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_PRODUCER));  // whole warpgroup 1
-        if (SPLIT3 && (!PAIRA || CTA2)) {
+        if (SPLIT3 && !PAIRA) {
             const int t = threadIdx.x - TC_FIRST_SPLIT_WARP * 32;    // 0..127
             int s = 0;
             uint32_t ph = 0;
@@ -496,10 +534,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (CTA2 && lane == 0) {           // tell the leader's MMA thread that this CTA's stage landed: its hi pass can go
                         if (!leader) mbar_arrive_remote(land_bar(s), 0);
                         else mbar_arrive(land_bar(s));
-                    }
-                    if (PAIRA) {              // nothing to split: these warps only relay "landed" to the pair leader
-                        if (++s == NA) { s = 0; ph ^= 1u; }
-                        continue;
                     }
                     // only the activation tile is split here; the weight tile arrives as (hi, lo) planes split on the host
                     float4* hi = reinterpret_cast<float4*>(smem_gen + s * Cfg::A_BYTES);
@@ -539,10 +573,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // loads of a slab are issued before the accumulator is waited for.  The two warps of a TMEM lane quarter
         // alternate slabs; per-channel constants are staged in smem once per tile.
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_EPILOGUE));  // the epilogue warpgroups
-        const int ew = warp - TC_FIRST_EPI_WARP;       // 0..EW-1
+        const int ew = warp - Cfg::FIRST_EPI_WARP;     // 0..EW-1
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
         const int part = ew >> 2;                      // which slabs of the tile this warp owns: part, part + 3, ...
-        const int et = threadIdx.x - TC_FIRST_EPI_WARP * 32;   // 0..32*EW-1
+        const int et = threadIdx.x - Cfg::FIRST_EPI_WARP * 32;   // 0..32*EW-1
         const int cgl = lane & 3;                      // my 4-channel group inside the slab
         const int rsub = lane >> 2;                    // my row inside each group of 8 rows
         float4* tbuf = tr_s + ew * 128;
@@ -550,9 +584,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr int NL = (KIND == EPI_JOIN) ? 4 : (KIND == EPI_MID) ? 2 : 1;     // tensors loaded per output element
         struct Loads { float4 v[NL][4]; };             // one slab's global loads: [tensor][row group]
         struct Acc { float vt[16]; float vp[KIND == EPI_FWD_DUAL ? 16 : 1]; };   // one slab of the accumulator(s), row per lane
-        constexpr bool ACC_PREFETCH = false;               // TMEM slab prefetch measured +-0 and costs 16-32 registers of the 136
-        constexpr bool LOAD_AHEAD = KIND != EPI_JOIN;      // other kinds keep the next slab's global loads in flight
+        constexpr bool ACC_PREFETCH = PAIRA && XFRB_PAIRA_ACC_PREFETCH;     // TF32 plans: measured +-0, costs 16-32 registers of the 136
+        constexpr bool LOAD_AHEAD = KIND != EPI_JOIN || (Cfg::REPURPOSE && EW == 8);   // the next slab's global loads stay in flight (JOIN: 4 tensors, needs the 224-register budget)
         constexpr int SLAB_STRIDE = 16 * (EW / 4);         // columns between two slabs of the same warp
+        constexpr bool PAIRED = PAIRA && XFRB_PAIRA_PAIRED;
         int it = 0;
         for (int tile = worker; tile < total_tiles; tile += nworkers, ++it) {
             const int a = it & 1;
@@ -562,14 +597,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int cbase = (KIND == EPI_FWD_DUAL) ? (ncol0 / BN) * (BN / 2) : ncol0;
             constexpr int PLD = Cfg::PRM_LD;
             float* prm = prm_s + a * Cfg::PRM_ROWS * PLD;
-            // stage the per-channel constants of this tile: rows 0-3 bn (alpha, beta, sp, tp), 4 bias_t, 5 bias_p
-            if (KIND != EPI_PLAIN) {
+            // stage the per-channel constants of this tile: rows 0-3 bn (alpha, beta, sp, tp), 4 bias_t, 5 bias_p.
+            // bf16x2 kernels (PRM_DIRECT) read them straight from global memory instead (L1-resident: every row of the tile uses
+            // the same few hundred floats): no staging, and above all no CTA-wide barrier per tile - with it the epilogue warps
+            // moved in lockstep and the ones with fewer slabs idled (ncu: 1.8 - 4.6 warps stalled on the barrier per issue)
+            constexpr bool PRM_DIRECT = PAIRA && XFRB_PAIRA_PRM_DIRECT;
+            if (!PRM_DIRECT && KIND != EPI_PLAIN) {
                 for (int i = et; i < 4 * CH; i += EW * 32) {
                     int r = i / CH, j = i - r * CH;
                     prm[r * PLD + j] = __ldg(ep.bn + (size_t)r * ep.C + cbase + j);
                 }
             }
-            if (KIND == EPI_FWD_DUAL) {
+            if (PRM_DIRECT) {
+            } else if (KIND == EPI_FWD_DUAL) {
                 for (int i = et; i < BN; i += EW * 32) {
                     int r = i / CH, j = i - r * CH;            // r = 0: true bias, 1: positive twin
                     prm[(4 + r) * PLD + j] = __ldg(ep.bias + ncol0 + r * CH + j);
@@ -666,16 +706,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 BnC b[4];
                 float bt[4] = {0.f, 0.f, 0.f, 0.f}, bp[4] = {0.f, 0.f, 0.f, 0.f};
                 if (KIND != EPI_PLAIN) {
-                    const float4 al = *reinterpret_cast<const float4*>(prm + pj), be = *reinterpret_cast<const float4*>(prm + PLD + pj);
-                    const float4 sp = *reinterpret_cast<const float4*>(prm + 2 * PLD + pj), tp = *reinterpret_cast<const float4*>(prm + 3 * PLD + pj);
+                    float4 al, be, sp, tp;
+                    if (PRM_DIRECT) {
+                        const float4* bnp = reinterpret_cast<const float4*>(ep.bn + cbase + pj);
+                        const size_t C4 = (size_t)ep.C / 4;
+                        al = __ldg(bnp); be = __ldg(bnp + C4); sp = __ldg(bnp + 2 * C4); tp = __ldg(bnp + 3 * C4);
+                    } else {
+                        al = *reinterpret_cast<const float4*>(prm + pj); be = *reinterpret_cast<const float4*>(prm + PLD + pj);
+                        sp = *reinterpret_cast<const float4*>(prm + 2 * PLD + pj); tp = *reinterpret_cast<const float4*>(prm + 3 * PLD + pj);
+                    }
                     b[0] = {al.x, be.x, sp.x, tp.x}; b[1] = {al.y, be.y, sp.y, tp.y}; b[2] = {al.z, be.z, sp.z, tp.z}; b[3] = {al.w, be.w, sp.w, tp.w};
                 }
                 if (KIND == EPI_PLAIN || KIND == EPI_FWD_DUAL) {
-                    const float4 t = *reinterpret_cast<const float4*>(prm + Cfg::BIAS_ROW * PLD + pj);
+                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!PRM_DIRECT) t = *reinterpret_cast<const float4*>(prm + Cfg::BIAS_ROW * PLD + pj);
+                    else if (ep.bias != nullptr) t = __ldg(reinterpret_cast<const float4*>(ep.bias + ncol0 + pj));
                     bt[0] = t.x; bt[1] = t.y; bt[2] = t.z; bt[3] = t.w;
                 }
                 if (KIND == EPI_FWD_DUAL) {
-                    const float4 t = *reinterpret_cast<const float4*>(prm + 5 * PLD + pj);
+                    const float4 t = PRM_DIRECT ? __ldg(reinterpret_cast<const float4*>(ep.bias + ncol0 + CH + pj))
+                                                : *reinterpret_cast<const float4*>(prm + 5 * PLD + pj);
                     bp[0] = t.x; bp[1] = t.y; bp[2] = t.z; bp[3] = t.w;
                 }
 #pragma unroll
@@ -747,26 +797,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // the first slab's loads go out before the accumulator is waited for; afterwards slab j+1 is always in flight
             Loads La, Lb;
             Acc Va, Vb;
-            const int j0 = part * 16;
+            // slab t of this warp starts at column col(t): every (EW/4)-th 16-column slab, or - PAIRED - every (EW/4)-th 32-column
+            // group, its two slabs back to back: the warp then touches both 64-byte halves of each 128-byte line of the operand and
+            // output tensors within one slab time (the second load hits L1, the two stores merge in L2)
+            auto col = [&](int t) { return PAIRED ? part * 32 + (t >> 1) * (32 * (EW / 4)) + (t & 1) * 16 : part * 16 + t * SLAB_STRIDE; };
+            const int j0 = col(0);
             if (LOAD_AHEAD && j0 < CH) issue_loads(j0, La);
-            asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");      // constants staged
+            if (!PRM_DIRECT) asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");      // constants staged
             mbar_wait(tfull_bar(a), aph);
             tc_fence_after();
             if (LOAD_AHEAD) {
                 if (ACC_PREFETCH && j0 < CH) request_acc(j0, Va);
 #pragma unroll 1
-                for (int j = j0; j < CH; j += 2 * SLAB_STRIDE) {
-                    const bool more1 = j + SLAB_STRIDE < CH, more2 = j + 2 * SLAB_STRIDE < CH;
-                    if (more1) issue_loads(j + SLAB_STRIDE, Lb);
-                    process(j, La, Va, j + SLAB_STRIDE, ACC_PREFETCH ? Vb : Va);
-                    if (more2) issue_loads(j + 2 * SLAB_STRIDE, La);
-                    if (more1) process(j + SLAB_STRIDE, Lb, ACC_PREFETCH ? Vb : Va, j + 2 * SLAB_STRIDE, Va);
+                for (int t = 0; col(t) < CH; t += 2) {
+                    const int ja = col(t), jb = col(t + 1), jc = col(t + 2);
+                    if (jb < CH) issue_loads(jb, Lb);
+                    process(ja, La, Va, jb, ACC_PREFETCH ? Vb : Va);
+                    if (jc < CH) issue_loads(jc, La);
+                    if (jb < CH) process(jb, Lb, ACC_PREFETCH ? Vb : Va, jc, Va);
                 }
             } else {
+                // JOIN: four operand tensors per element leave no registers for a second slab of loads; the next slab's
+                // lines are pulled into L2 instead (fire-and-forget), so that its loads pay L2 latency, not DRAM latency
+                auto prefetch_slab = [&](int j) {
+                    if (!(PAIRA && XFRB_PAIRA_JOIN_L2_PREFETCH) || cgl != 0) return;        // one lane per 64-byte row segment
+                    const int c = cbase + j;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (!vrow[i]) continue;
+                        const size_t offs = (size_t)msav[i] * ep.C + c;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.o + offs));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.xr + offs));
+                        if (KIND == EPI_JOIN) {
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.outp + offs));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.g_res + (size_t)mrow[i] * ep.C + c));
+                        }
+                    }
+                };
 #pragma unroll 1
-                for (int j = j0; j < CH; j += SLAB_STRIDE) {
-                    issue_loads(j, La);
-                    process(j, La, Va, CH, Va);
+                for (int t = 0; col(t) < CH; ++t) {
+                    if (col(t + 1) < CH) prefetch_slab(col(t + 1));
+                    issue_loads(col(t), La);
+                    process(col(t), La, Va, CH, Va);
                 }
             }
             tc_fence_before();

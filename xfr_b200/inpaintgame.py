@@ -125,6 +125,29 @@ def run_weighted_subtree_triplet_ebp(wb, im_mates, im_nonmates, probe_im, net_na
     return img_subtree
 
 
+def run_weighted_subtree_triplet_ebp_sharded(wb, jobs, subtree_mode_weighted='all', ebp_version=None, device=None, topk=32, dst=0):
+    """BASELINE configs[3] (the inpainting-game set, eval/generate_inpaintinggame_wb_saliency_maps_multigpu.py:121-231 farms one
+    job per process per GPU): `jobs` = [(im_mates, im_nonmates, probe_im), ...] are sharded contiguously over the ranks
+    (one process per GPU under torchrun), every rank runs run_weighted_subtree_triplet_ebp on its slice - the sub-trees of one
+    probe are already batched as gradient rows inside weighted_subtree_ebp - and the only collective is the gather of the
+    finished maps to rank `dst`.  Returns the [len(jobs), h, w] maps in job order on `dst`, None elsewhere."""
+    import torch.distributed as dist
+    from .shard import gather_maps, shard_range
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    lo, hi = shard_range(len(jobs), dist.get_rank(), dist.get_world_size()) if multi else (0, len(jobs))
+    hw = wb.net.engine().map_hw
+    maps = [run_weighted_subtree_triplet_ebp(wb, *job, subtree_mode_weighted=subtree_mode_weighted, ebp_version=ebp_version,
+                                             device=device, topk=topk) for job in jobs[lo:hi]]
+    local = np.stack(maps) if maps else np.empty((0, hw, hw), dtype=np.uint8 if wb.convert_saliency_uint8 else np.float32)
+    if not multi:
+        return local
+    local = torch.from_numpy(np.ascontiguousarray(local))
+    if dist.get_backend() == 'nccl':
+        local = local.to(wb.net._device())
+    out = gather_maps(local, len(jobs), dst=dst)
+    return None if out is None else out.cpu().numpy()
+
+
 def mean_ebp(wb, probe_im, net_name=None, ebp_version=None, device=None):
     """generate_whitebox_saliency.py:207-215: EBP with a uniform prior over the network's classes."""
     x = _to_device(wb, [probe_im], device)

@@ -11,7 +11,7 @@ import os
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libxfr_b200.so')
+LIB_PATH = os.environ.get('XFRB_LIB') or os.path.join(HERE, 'libxfr_b200.so')     # XFRB_LIB: an A/B build (xfr_b200/build.py --out)
 
 IMPL_FP32, IMPL_TF32X3, IMPL_TF32, IMPL_TF32X3_FULL, IMPL_TF32X2, IMPL_BF16X2 = 0, 1, 2, 3, 4, 5
 IMPLS = {'fp32': IMPL_FP32, 'tf32x3': IMPL_TF32X3, 'tf32': IMPL_TF32, 'tf32x3full': IMPL_TF32X3_FULL}

@@ -155,8 +155,11 @@ class ConvBN(object):
         return self.Bd_signed
 
     def Bd32(self):
+        """relu(W) for the fp32-activation dgrads of the firing-by-firing sweeps under the bf16x2 plan: the SAME bf16-rounded
+        values the forward used for X (excitation backprop stays mass-conserving only if X and the dgrad share one W+), as a
+        split-TF32 pack - a bf16 number is a TF32 number, so the hi plane holds it exactly and the lo plane is zero."""
         if self._Bd32 is None:
-            self._Bd32 = gemm_planes(pack_dgrad(self._w, positive=True), 'tf32x3').to(self.Bd.device)
+            self._Bd32 = gemm_planes(self.Bd.float().cpu(), 'tf32x3').to(self.Bd.device)
         return self._Bd32
 
     def to(self, device):

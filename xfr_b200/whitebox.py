@@ -29,6 +29,13 @@ from .engine import MODE_IDS, Resnet50_128Engine, StResnetEngine
 from .lightcnn import LightCNNEngine
 
 _CHUNK = 128    # probes per engine sweep (workspace = ~210 MB per probe)
+# The GEMM plan of the fused sweep (xfr_b200/kernels.py).  'bf16x2' (tcgen05 kind::f16 on bf16 terms, pair-tensor operands) is the
+# default because on the B200 it is as close to the reference as the three-pass TF32 plan: what separates every tensor-core plan
+# from the reference is the tensor core's truncating fp32 accumulation, not the operand precision (on the
+# well-conditioned ResNet-101 triplet bf16x2 / tf32x3 / tf32x3full sit at 3.8e-3 / 2.8e-3 / 3.0e-3 of the contrastive map's
+# maximum, all <= 4e-6 max-abs against the 1e-4 bar).  'fp32' (CUDA cores, exact products, round-to-nearest accumulation) is the
+# reference-grade plan: 1e-4 of the maximum, at a seventh of the speed.
+DEFAULT_IMPL = 'bf16x2'
 
 
 class WhiteboxNetwork(object):
@@ -57,6 +64,35 @@ class WhiteboxNetwork(object):
     def preprocess(self, im):
         raise NotImplementedError
 
+    _CONTAINERS = ('Sequential', 'Bottleneck')
+
+    def _layer_visitor(self, f_forward=None, f_preforward=None, net=None):
+        """reference whitebox.py:34-56 (Light-CNN override 142-159): the modules of the torch network in definition order,
+        containers expanded, as [{'name': str(layer), 'hooks': [...]}].  The B200 engine runs a static schedule instead of
+        hooks, so nothing depends on this list; hook functions, if given, are still registered on the torch modules (they fire
+        only if the caller runs the torch network itself).  A plain state_dict has no modules: one entry per parameter owner."""
+        net = self.net if net is None else net
+        if isinstance(net, _StateDictModule):
+            owners = []
+            for k in net.state_dict():
+                o = k.rsplit('.', 1)[0]
+                if o not in owners:
+                    owners.append(o)
+            return [{'name': o, 'hooks': []} for o in owners]
+        layerlist = []
+        for name, layer in net._modules.items():
+            if type(layer).__name__ in self._CONTAINERS:
+                layerlist.append({'name': str(layer), 'hooks': [None]})
+                layerlist = layerlist + self._layer_visitor(f_forward, f_preforward, layer)
+            else:
+                hooks = []
+                if f_forward is not None:
+                    hooks.append(layer.register_forward_hook(f_forward))
+                if f_preforward is not None:
+                    hooks.append(layer.register_forward_pre_hook(f_preforward))
+                layerlist.append({'name': str(layer), 'hooks': hooks})
+        return layerlist
+
 
 class WhiteboxSTResnet(WhiteboxNetwork):
     """STR-Janus ResNet-101 plugin (reference whitebox.py:87-110).
@@ -65,7 +101,7 @@ class WhiteboxSTResnet(WhiteboxNetwork):
     (reference resnet.py:168-221: conv1, bn1, layer{1-4}.{i}.conv{1,2,3}/bn{1,2,3}, fc1, fc2).
     The reference's own `xfr.models.resnet.ResNet` instance works unchanged."""
 
-    def __init__(self, net, layers=None, impl='tf32x3'):
+    def __init__(self, net, layers=None, impl=DEFAULT_IMPL):
         if isinstance(net, dict):
             self._sd = net
             self.net = _StateDictModule(net)
@@ -81,10 +117,15 @@ class WhiteboxSTResnet(WhiteboxNetwork):
 
     # -- engine plumbing
     def _device(self):
+        """Where the engine runs: the network's CUDA device, or - for a CPU-resident network, which is how demo/test_whitebox.py
+        builds its Whitebox objects (:77-107, 257-280) - the current CUDA device: the weights are packed onto the GPU once and
+        every kernel runs there (this is not a CPU path: without a B200 it raises)."""
         for v in self._sd.values():
             if v.is_cuda:
                 return v.device
-        raise RuntimeError('xfr_b200: the network must live on a CUDA device (.to("cuda")); there is no CPU path')
+        if torch.cuda.is_available():
+            return torch.device('cuda', torch.cuda.current_device())
+        raise RuntimeError('xfr_b200: no CUDA device - the whitebox engine runs on a B200 only (there is no CPU path)')
 
     def engine(self, with_bias=False):
         if self._engine is None or self._engine.with_bias != with_bias:
@@ -116,7 +157,11 @@ class WhiteboxSTResnet(WhiteboxNetwork):
 
     def triplet_rows(self, n):
         if self._W2 is None:                      # the network's own fc2 [C,512]: takes part in EBP with relu(W)
-            return self._sd['fc2.weight'].to(self._device()).float().contiguous()
+            w = self._sd['fc2.weight']
+            key = (w.data_ptr(), w._version, str(self._device()))
+            if getattr(self, '_fc2_dev', (None, None))[0] != key:         # one device copy (134 MB for the 65,359-class STR head)
+                self._fc2_dev = (key, w.detach().to(self._device()).float().contiguous())
+            return self._fc2_dev[1]
         W2 = self._W2.to(self._device())
         if W2.shape[0] == 1 and n > 1:
             W2 = W2.expand(n, -1, -1)
@@ -130,7 +175,7 @@ class WhiteboxSTResnet(WhiteboxNetwork):
         out = []
         for i in range(0, x.shape[0], _CHUNK):
             out.append(50.0 * eng.forward(self._nhwc(x[i:i + _CHUNK])).clone())
-        return torch.cat(out)
+        return torch.cat(out).to(x.device)
 
     _ENC_SCALE = 50.0      # encode() = 50 * L2-normalised fc1 (whitebox.py:98-100); the other two plugins return the raw feature
 
@@ -144,7 +189,7 @@ class WhiteboxSTResnet(WhiteboxNetwork):
     def classify(self, x):
         enc = self.encode(x)
         if self._W2 is not None:
-            return torch.einsum('nd,ncd->nc', enc, self.triplet_rows(enc.shape[0]))
+            return torch.einsum('nd,ncd->nc', enc, self.triplet_rows(enc.shape[0]).to(enc.device))
         return enc @ self._sd['fc2.weight'].to(enc.device).t() + self._sd['fc2.bias'].to(enc.device)
 
     def num_classes(self):
@@ -163,7 +208,7 @@ class Whitebox_resnet50_128(WhiteboxSTResnet):
 
     _ENC_SCALE = 1.0
 
-    def __init__(self, net, impl='tf32x3'):
+    def __init__(self, net, impl=DEFAULT_IMPL):
         if isinstance(net, dict):
             self._sd = net
             self.net = _StateDictModule(net)
@@ -187,11 +232,11 @@ class Whitebox_resnet50_128(WhiteboxSTResnet):
     def encode(self, x):
         """whitebox.py:222-224: self.net(x)[0], the 128-d feat_extract output (not normalised)."""
         eng = self.engine()
-        return torch.cat([eng.forward(self._nhwc(x[i:i + _CHUNK])).clone() for i in range(0, x.shape[0], _CHUNK)])
+        return torch.cat([eng.forward(self._nhwc(x[i:i + _CHUNK])).clone() for i in range(0, x.shape[0], _CHUNK)]).to(x.device)
 
     def classify(self, x):
         enc = self.encode(x)
-        return torch.einsum('nd,ncd->nc', enc, self.triplet_rows(enc.shape[0]))
+        return torch.einsum('nd,ncd->nc', enc, self.triplet_rows(enc.shape[0]).to(enc.device))
 
     def num_classes(self):
         return 2
@@ -217,7 +262,7 @@ class Whitebox_senet50_256(Whitebox_resnet50_128):
     no hot path to accelerate.  The class exists so that code which names it imports; preprocess() is the reference's
     (identical to the ResNet-50-128d plugin's, whitebox.py:185-208)."""
 
-    def __init__(self, net, impl='tf32x3'):
+    def __init__(self, net, impl=DEFAULT_IMPL):
         self.net = net
         self._sd = {}
         self._impl = impl
@@ -239,8 +284,9 @@ class WhiteboxLightCNN(WhiteboxSTResnet):
     network's fc2 (hooked, W+ in the backward) until set_triplet_classifier replaces it by an un-hooked Linear(256, 2)
     (whitebox.py:120-123).  Saliency maps are 128x128 (P[-2] is the first Split input, 96x128x128)."""
     _ENC_SCALE = 1.0
+    _CONTAINERS = ('Sequential', 'Bottleneck', 'mfm', 'group', 'resblock')       # whitebox.py:149
 
-    def __init__(self, net, impl='tf32x3'):
+    def __init__(self, net, impl=DEFAULT_IMPL):
         if isinstance(net, dict):
             self._sd = net
             self.net = _StateDictModule(net)
@@ -263,13 +309,13 @@ class WhiteboxLightCNN(WhiteboxSTResnet):
     def encode(self, x):
         """whitebox.py:125-128: the 256-d fc output (`features` of net(x))."""
         eng = self.engine()
-        return torch.cat([eng.forward(self._nhwc(x[i:i + _CHUNK])).clone() for i in range(0, x.shape[0], _CHUNK)])
+        return torch.cat([eng.forward(self._nhwc(x[i:i + _CHUNK])).clone() for i in range(0, x.shape[0], _CHUNK)]).to(x.device)
 
     def classify(self, x):
         """whitebox.py:130-132: fc2(dropout(fc)) in eval mode; fc2 has no bias (lightcnn.py:228)."""
         enc = self.encode(x)
         if self._W2 is not None:
-            return torch.einsum('nd,ncd->nc', enc, self.triplet_rows(enc.shape[0]))
+            return torch.einsum('nd,ncd->nc', enc, self.triplet_rows(enc.shape[0]).to(enc.device))
         return enc @ self._sd['fc2.weight'].to(enc.device).t()
 
     def preprocess(self, im):
@@ -313,7 +359,6 @@ class Whitebox(nn.Module):
         assert isinstance(net, WhiteboxNetwork)
         self.net = net
         self.eps = eps
-        self.layerlist = None
         self.ebp_ver = ebp_version
         if self.ebp_ver is None:
             self.ebp_ver = 6
@@ -324,6 +369,12 @@ class Whitebox(nn.Module):
         self.dA, self.A, self.X, self.P, self.P_prior, self.P_layername = [], [], [], [], [], []
         self.batch_size = 32
         self._ebp_mode = 'disable'
+        # the reference registers its hooks here (whitebox.py:303); the engine needs none - the list of layers is kept for callers
+        self.layerlist = self.net._layer_visitor()
+        # record_P = True: ebp() also fills self.P / self.P_layername with the MWP of every hook firing, as the reference's hooks
+        # do on every call (whitebox.py:388-395); off by default - the fused sweep never materialises them (layerwise_ebp,
+        # layerwise_contrastive_ebp and weighted_subtree_ebp always record what they need)
+        self.record_P = False
         if ebp_subtree_mode not in MODE_IDS:
             raise ValueError('Invalid subtree mode "%s"' % ebp_subtree_mode)
         self._ebp_subtree_mode = ebp_subtree_mode
@@ -369,8 +420,8 @@ class Whitebox(nn.Module):
             Pn = Pn.expand(N, -1)
         hk = self.net.hooked()
         for i in range(0, N, _CHUNK):
-            m = eng.ebp(self.net._nhwc(x[i:i + _CHUNK]), Pn[i:i + _CHUNK].contiguous(), W2 if hk else W2[i:i + _CHUNK].contiguous(),
-                        self._ebp_subtree_mode, hooked_fc2=hk, saliency=not (mwp or self.convert_saliency_uint8))
+            m = eng.graph_call('ebp', (self.net._nhwc(x[i:i + _CHUNK]), Pn[i:i + _CHUNK].contiguous(), W2 if hk else W2[i:i + _CHUNK].contiguous()),
+                               mode=self._ebp_subtree_mode, hooked_fc2=hk, saliency=not (mwp or self.convert_saliency_uint8))
             outs.append(m.cpu())
         maps = torch.cat(outs).numpy()
         if self.convert_saliency_uint8 and not mwp:
@@ -385,9 +436,9 @@ class Whitebox(nn.Module):
         res = out if out is not None else torch.empty(N, eng.map_hw, eng.map_hw)
         hk = self.net.hooked()
         for i in range(0, N, _CHUNK):
-            m = eng.contrastive(self.net._nhwc(x[i:i + _CHUNK]), W2 if hk else W2[i:i + _CHUNK].contiguous(), k_poschannel,
-                                k_negchannel, self._ebp_subtree_mode, hooked_fc2=hk, percentile=percentile,
-                                saliency=not self.convert_saliency_uint8, num_classes=self.net.num_classes())
+            m = eng.graph_call('contrastive', (self.net._nhwc(x[i:i + _CHUNK]), W2 if hk else W2[i:i + _CHUNK].contiguous()),
+                               k_pos=k_poschannel, k_neg=k_negchannel, mode=self._ebp_subtree_mode, hooked_fc2=hk, percentile=percentile,
+                               saliency=not self.convert_saliency_uint8, num_classes=self.net.num_classes())
             res[i:i + m.shape[0]].copy_(m, non_blocking=True)
         if W2.is_cuda:
             torch.cuda.current_stream(W2.device).synchronize()
@@ -398,7 +449,16 @@ class Whitebox(nn.Module):
     # ---------------------------------------------------------------- reference API (batch 1)
     def ebp(self, x, Pn, mwp=False):
         """whitebox.py:482-504"""
+        if self.record_P and x.shape[0] == 1:
+            return self._ebp_recorded(x, Pn, mwp)
         return self.ebp_batch(x, Pn, mwp)[0]
+
+    def _ebp_recorded(self, x, Pn, mwp):
+        """ebp() through the firing-by-firing sweep, keeping self.P / self.P_layername like the reference (record_P)."""
+        gs, W2 = self._generic(x)
+        P, names, P2 = gs.run(Pn.to(W2.device, dtype=torch.float32), W2, self._ebp_subtree_mode, record=True, hooked_fc2=self.net.hooked())
+        self._set_P(gs, P, names)
+        return self._finish_map(P2, mwp)[0]
 
     def contrastive_ebp(self, img_probe, k_poschannel, k_negchannel):
         """whitebox.py:506-527"""
