@@ -197,6 +197,13 @@ int xfrb_trunc_threshold(const float* P2, const double* sums, float percentile, 
 /* skimage.filters.gaussian(sigma=2) -> max(0,.) -> /max(sum,eps)  (whitebox.py:455-460); [B,H,W], H,W <= 128 */
 int xfrb_saliency_post(const float* mwp, float* out, int B, int H, int W, float eps, void* stream);
 
+/* The saliency .npz format's cubic resize (python/xfr/show.py:131-137 processSaliency: attMap -= min; attMap /= (max + 1e-9);
+ * skimage.transform.resize(attMap, img.shape[:2], order=3, mode='constant')).  scikit-image >= 0.19 evaluates that resize as
+ * scipy.ndimage.zoom(order=3, mode='grid-constant', cval=0, grid_mode=True) + clip to the input range; this kernel is that
+ * algorithm (zero pad 12, cubic B-spline prefilter per axis in double, half-pixel-centred sampling), one map per CTA.
+ * in [B,h,w] fp32 -> out [B,oh,ow] fp32; h, w <= 144.  normalize != 0 applies the min-shift / max-normalise first. */
+int xfrb_cubic_zoom(const float* in, float* out, int B, int h, int w, int oh, int ow, int normalize, void* stream);
+
 /* Inpainting-game blends (python/xfr/inpainting_game/inpainting_game.py:110-132, consumed by Whitebox.embeddings,
  * whitebox.py:747-785): out[k,h,w,c] = fp32((1 - m) * orig[c,h,w] + m * inp[c,h,w]), evaluated in double, with
  * m = (value[h,w] > thr[k]) (inpainting_game.py:66; `masks` = NULL) or m = masks[k,h,w] (blurred masks, lines 69-78).

@@ -98,6 +98,16 @@ class EmulBackend(object):
     def avgpool2(self, u, out):
         out.copy_(F.avg_pool2d(u.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1))
 
+    def cubic_zoom(self, maps, out, normalize=True):
+        """show.processSaliency's normalisation + the cubic resize as scikit-image >= 0.19 evaluates it (scipy.ndimage.zoom)"""
+        import scipy.ndimage
+        for i, m in enumerate(maps.numpy()):
+            lo, hi = m.min(), m.max()
+            if normalize:
+                m = (m - lo) / np.float32(np.float32(hi - lo) + np.float32(1e-9))
+            z = scipy.ndimage.zoom(m, (out.shape[1] / m.shape[0], out.shape[2] / m.shape[1]), order=3, mode='grid-constant', cval=0.0, grid_mode=True)
+            out[i].copy_(torch.from_numpy(np.clip(z, m.min(), m.max()).astype(np.float32)))
+
     def to_pair(self, x, out, inverse=False):
         out.copy_(from_pair(x) if inverse else to_pair(x))
 

@@ -394,3 +394,36 @@ def test_front_end_lightcnn_emulated():
         assert rel_err(g, want) < 1e-4 and abs(float(g.sum()) - 1.0) < 1e-3
     rows = IG.mean_encodings(wb, [jobs[0][0]])
     assert rows.shape == (1, 256)
+
+
+def _check_cubic_zoom(gpu):
+    """the batched resize (xfrb_cubic_zoom) against scipy.ndimage.zoom(order=3, mode='grid-constant',
+    grid_mode=True) + clip, which is how scikit-image >= 0.19 evaluates show.processSaliency's resize(order=3, mode='constant'),
+    and against the per-map host function process_saliency."""
+    import scipy.ndimage
+    wb = whitebox.Whitebox(_net(L1111, gpu))
+    rng = np.random.RandomState(3)
+    maps = np.stack([rng.rand(112, 112).astype(np.float32) ** 3, np.outer(np.hanning(112), np.hanning(112)).astype(np.float32) + 2.0,
+                     np.zeros((112, 112), np.float32)])
+    maps[2, 40:44, 60:70] = 1e-3                                   # sparse map: ringing below zero must be clipped away
+    got = IG.process_saliency_batch(wb, maps, (224, 224))
+    assert got.shape == (3, 224, 224) and got.dtype == np.float32
+    for g, m in zip(got, maps):
+        want = IG.process_saliency(np.zeros((224, 224, 3)), m)
+        assert float(np.abs(g - want).max()) < 2e-6 and g.min() >= 0.0 and g.max() <= 1.0
+        n = (m - m.min()) / (m.max() - m.min() + np.float32(1e-9))
+        z = scipy.ndimage.zoom(n.astype(np.float64), 2, order=3, mode='grid-constant', cval=0.0, grid_mode=True)
+        assert float(np.abs(g - np.clip(z, n.min(), n.max())).max()) < 2e-6
+    big = IG.process_saliency_batch(wb, maps[:1, :96, :80], (144, 200))           # other sizes / non-integer zooms
+    n = (maps[0, :96, :80] - maps[0, :96, :80].min()) / (maps[0, :96, :80].max() - maps[0, :96, :80].min() + np.float32(1e-9))
+    z = scipy.ndimage.zoom(n.astype(np.float64), (144 / 96, 200 / 80), order=3, mode='grid-constant', cval=0.0, grid_mode=True)
+    assert float(np.abs(big[0] - np.clip(z, n.min(), n.max())).max()) < 2e-6
+
+
+def test_cubic_zoom_emulated():
+    _check_cubic_zoom(False)
+
+
+@pytest.mark.gpu
+def test_cubic_zoom_gpu():
+    _check_cubic_zoom(True)

@@ -220,7 +220,9 @@ def _check_subtree_resnet101(gpu):
     # a sub-tree is seeded at the arg-max ELEMENT of its firing's gated true gradient (whitebox.py:687-696): on the tensor-core plans a
     # near-tie between two elements may pick the other one (measured: firing 333), which changes that one map, not the selected set
     assert len(off) <= (2 if gpu else 0)
-    assert smap.dtype == np.float32 and r < (1e-1 if gpu else 1e-3) and np.abs(smap - G['ws_smap']).max() < 1e-4
+    # (one re-seeded sub-tree of 32 moves the merged map by its weight: measured 0.11 of the maximum with firing 333 re-seeded)
+    assert smap.dtype == np.float32 and r < ((0.25 if off else 5e-2) if gpu else 1e-3)
+    assert np.abs(smap - G['ws_smap']).max() < (1e-3 if off else 1e-4)
 
 
 @pytest.mark.gpu

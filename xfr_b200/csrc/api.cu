@@ -37,6 +37,7 @@ cudaError_t launch_stem_bwd(const float*, const float*, const float*, const floa
 cudaError_t launch_contrast(const float*, const double*, const float*, float*, int, int, int, cudaStream_t);
 cudaError_t launch_trunc_threshold(const float*, const double*, float, float*, int, size_t, cudaStream_t);
 cudaError_t launch_saliency_post(const float*, float*, int, int, int, float, cudaStream_t);
+cudaError_t launch_cubic_zoom(const float*, float*, int, int, int, int, int, int, cudaStream_t);
 cudaError_t launch_twin_blends(const double*, const double*, const double*, const double*, const double*, float*, int, int, int, int,
                                int, cudaStream_t);
 // lightcnn.cu
@@ -51,6 +52,7 @@ cudaError_t launch_chansum(const float*, float*, double*, int, int, int, cudaStr
 static int finish(const char* what, cudaError_t e) {
     if (e != cudaSuccess) {
         set_error(what, e);
+        cudaGetLastError();          // a rejected launch / attribute call must not linger as the caller's next CUDA error
         return (int)e;
     }
     return 0;
@@ -331,6 +333,11 @@ int xfrb_trunc_threshold(const float* P2, const double* sums, float percentile, 
 int xfrb_saliency_post(const float* mwp, float* out, int B, int H, int W, float eps, void* stream) {
     if (H > 128 || W > 128) return finish("xfrb_saliency_post", cudaErrorInvalidValue);
     return finish("xfrb_saliency_post", launch_saliency_post(mwp, out, B, H, W, eps, (cudaStream_t)stream));
+}
+
+int xfrb_cubic_zoom(const float* in, float* out, int B, int h, int w, int oh, int ow, int normalize, void* stream) {
+    if (h < 4 || w < 4 || h > 144 || w > 144 || oh < 1 || ow < 1) return finish("xfrb_cubic_zoom", cudaErrorInvalidValue);
+    return finish("xfrb_cubic_zoom", launch_cubic_zoom(in, out, B, h, w, oh, ow, normalize, (cudaStream_t)stream));
 }
 
 int xfrb_twin_blends(const double* orig, const double* inp, const double* value, const double* thr, const double* masks, float* out,

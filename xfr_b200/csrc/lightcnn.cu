@@ -14,13 +14,13 @@ __global__ void __launch_bounds__(256) lc_conv1_kernel(const float* __restrict__
                                                        const float* __restrict__ b, const float* __restrict__ bpos,
                                                        float* __restrict__ c, float* __restrict__ cpos, int H, int W, int C2,
                                                        size_t total) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;      // 32-bit index arithmetic (launchers reject totals >= 2^31)
     if (i >= total) return;
-    const int ch = (int)(i % C2);
-    size_t p = i / C2;
-    const int w = (int)(p % W); p /= W;
-    const int h = (int)(p % H);
-    const size_t n = p / H;
+    const int ch = (int)(i % (unsigned)C2);
+    unsigned p = i / (unsigned)C2;
+    const int w = (int)(p % (unsigned)W); p /= (unsigned)W;
+    const int h = (int)(p % (unsigned)H);
+    const size_t n = p / (unsigned)H;
     const float* xi = x + n * H * W;
     float acc = 0.f, accp = 0.f;
 #pragma unroll
@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(256) lc_conv1_kernel(const float* __restrict__
 cudaError_t launch_lc_conv1(const float* x, const float* Wt, const float* b, const float* bpos, float* c, float* cpos, int N,
                             int H, int W, int C2, cudaStream_t st) {
     size_t total = (size_t)N * H * W * C2;
+    if (total >= 0x7FFFFF00ull) return cudaErrorInvalidValue;      // kernels index with 32-bit arithmetic
     lc_conv1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, Wt, b, bpos, c, cpos, H, W, C2, total);
     return cudaGetLastError();
 }
@@ -53,9 +54,9 @@ cudaError_t launch_lc_conv1(const float* x, const float* Wt, const float* b, con
 // the A operand of the positive-pass GEMM of the next conv.
 __global__ void mfm_fwd_kernel(const float4* __restrict__ c, const float4* __restrict__ res, float4* __restrict__ m,
                                float4* __restrict__ y, float4* __restrict__ relu_out, int Cp4, size_t total4) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;      // 32-bit index arithmetic (launchers reject totals >= 2^31)
     if (i >= total4) return;
-    const size_t row = i / Cp4;
+    const size_t row = i / (unsigned)Cp4;
     const int c4 = (int)(i - row * Cp4);
     const float4 a = c[row * 2 * Cp4 + c4], b = c[row * 2 * Cp4 + Cp4 + c4];
     float4 v = make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
@@ -71,6 +72,7 @@ __global__ void mfm_fwd_kernel(const float4* __restrict__ c, const float4* __res
 cudaError_t launch_mfm_fwd(const float* c, const float* res, float* m, float* y, float* relu_out, size_t rows, int Cp,
                            cudaStream_t st) {
     size_t total4 = rows * (Cp / 4);
+    if (total4 >= 0x7FFFFF00ull) return cudaErrorInvalidValue;      // kernels index with 32-bit arithmetic
     mfm_fwd_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(
         reinterpret_cast<const float4*>(c), reinterpret_cast<const float4*>(res), reinterpret_cast<float4*>(m),
         reinterpret_cast<float4*>(y), reinterpret_cast<float4*>(relu_out), Cp / 4, total4);
@@ -81,11 +83,11 @@ cudaError_t launch_mfm_fwd(const float* c, const float* res, float* m, float* y,
 // g [J*HW, Cp], c [N*HW, 2*Cp] (row m reads m % Ms) -> z [J*HW, 2*Cp]: the larger branch takes g, exact ties take g/2 each.
 __global__ void mfm_bwd_kernel(const float4* __restrict__ g, const float4* __restrict__ c, float4* __restrict__ z, int Cp4,
                                size_t rows_saved, size_t total4) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;      // 32-bit index arithmetic (launchers reject totals >= 2^31)
     if (i >= total4) return;
-    const size_t row = i / Cp4;
+    const size_t row = i / (unsigned)Cp4;
     const int c4 = (int)(i - row * Cp4);
-    const size_t rs = row % rows_saved;
+    const size_t rs = (unsigned)row % (unsigned)rows_saved;
     const float4 a = c[rs * 2 * Cp4 + c4], b = c[rs * 2 * Cp4 + Cp4 + c4];
     const float4 gv = g[i];
     const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
@@ -102,6 +104,7 @@ __global__ void mfm_bwd_kernel(const float4* __restrict__ g, const float4* __res
 
 cudaError_t launch_mfm_bwd(const float* g, const float* c, float* z, size_t rows, size_t rows_saved, int Cp, cudaStream_t st) {
     size_t total4 = rows * (Cp / 4);
+    if (total4 >= 0x7FFFFF00ull) return cudaErrorInvalidValue;      // kernels index with 32-bit arithmetic
     mfm_bwd_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(g),
                                                                      reinterpret_cast<const float4*>(c),
                                                                      reinterpret_cast<float4*>(z), Cp / 4, rows_saved, total4);
@@ -112,14 +115,14 @@ cudaError_t launch_mfm_bwd(const float* g, const float* c, float* z, size_t rows
 // m [N,H,W,C] -> p [N,H/2,W/2,C]; ppos = maxpool2(relu(m)) + avgpool2(relu(m)): the positive-pass value (X of p's consumers).
 __global__ void pool2_fwd_kernel(const float4* __restrict__ m, float4* __restrict__ p, float4* __restrict__ ppos, int H, int W,
                                  int C4, size_t total4) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;      // 32-bit index arithmetic (launchers reject totals >= 2^31)
     if (i >= total4) return;
-    const int c4 = (int)(i % C4);
-    size_t q = i / C4;
+    const int c4 = (int)(i % (unsigned)C4);
+    unsigned q = i / (unsigned)C4;
     const int Wo = W / 2, Ho = H / 2;
-    const int wo = (int)(q % Wo); q /= Wo;
-    const int ho = (int)(q % Ho);
-    const size_t n = q / Ho;
+    const int wo = (int)(q % (unsigned)Wo); q /= (unsigned)Wo;
+    const int ho = (int)(q % (unsigned)Ho);
+    const size_t n = q / (unsigned)Ho;
     const float4* base = m + ((n * H + 2 * ho) * W + 2 * wo) * C4 + c4;
     const float4 v[4] = {base[0], base[C4], base[(size_t)W * C4], base[(size_t)W * C4 + C4]};
     float out[4], outp[4];
@@ -141,6 +144,7 @@ __global__ void pool2_fwd_kernel(const float4* __restrict__ m, float4* __restric
 
 cudaError_t launch_pool2_fwd(const float* m, float* p, float* ppos, int N, int H, int W, int C, cudaStream_t st) {
     size_t total4 = (size_t)N * (H / 2) * (W / 2) * (C / 4);
+    if (total4 >= 0x7FFFFF00ull) return cudaErrorInvalidValue;      // kernels index with 32-bit arithmetic
     pool2_fwd_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(m),
                                                                        reinterpret_cast<float4*>(p),
                                                                        reinterpret_cast<float4*>(ppos), H, W, C / 4, total4);
@@ -151,15 +155,15 @@ cudaError_t launch_pool2_fwd(const float* m, float* p, float* ppos, int N, int H
 // AvgPool2d backward (g/4 on every pixel).  g [J,H/2,W/2,C], m [N,H,W,C] -> gm [J,H,W,C].
 __global__ void pool2_bwd_kernel(const float4* __restrict__ g, const float4* __restrict__ m, float4* __restrict__ gm, int H, int W,
                                  int C4, int N, size_t total4) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;      // 32-bit index arithmetic (launchers reject totals >= 2^31)
     if (i >= total4) return;
-    const int c4 = (int)(i % C4);
-    size_t q = i / C4;
+    const int c4 = (int)(i % (unsigned)C4);
+    unsigned q = i / (unsigned)C4;
     const int Wo = W / 2, Ho = H / 2;
-    const int wo = (int)(q % Wo); q /= Wo;
-    const int ho = (int)(q % Ho);
-    const size_t j = q / Ho;
-    const size_t n = j % N;
+    const int wo = (int)(q % (unsigned)Wo); q /= (unsigned)Wo;
+    const int ho = (int)(q % (unsigned)Ho);
+    const size_t j = q / (unsigned)Ho;
+    const size_t n = (unsigned)j % (unsigned)N;
     const float4* base = m + ((n * H + 2 * ho) * W + 2 * wo) * C4 + c4;
     const float4 v[4] = {base[0], base[C4], base[(size_t)W * C4], base[(size_t)W * C4 + C4]};
     const float4 gv = g[i];
@@ -186,6 +190,7 @@ __global__ void pool2_bwd_kernel(const float4* __restrict__ g, const float4* __r
 
 cudaError_t launch_pool2_bwd(const float* g, const float* m, float* gm, int J, int N, int H, int W, int C, cudaStream_t st) {
     size_t total4 = (size_t)J * (H / 2) * (W / 2) * (C / 4);
+    if (total4 >= 0x7FFFFF00ull) return cudaErrorInvalidValue;      // kernels index with 32-bit arithmetic
     pool2_bwd_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(g),
                                                                        reinterpret_cast<const float4*>(m),
                                                                        reinterpret_cast<float4*>(gm), H, W, C / 4, N, total4);
@@ -194,7 +199,7 @@ cudaError_t launch_pool2_bwd(const float* g, const float* m, float* gm, int J, i
 
 // ------------------------------------------------------------------ relu copy (A operand of a positive-pass GEMM)
 __global__ void relu_kernel(const float4* __restrict__ in, float4* __restrict__ out, size_t total4) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;      // 32-bit index arithmetic (launchers reject totals >= 2^31)
     if (i >= total4) return;
     const float4 v = in[i];
     out[i] = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
@@ -202,6 +207,7 @@ __global__ void relu_kernel(const float4* __restrict__ in, float4* __restrict__ 
 
 cudaError_t launch_relu(const float* in, float* out, size_t n, cudaStream_t st) {
     size_t total4 = n / 4;
+    if (total4 >= 0x7FFFFF00ull) return cudaErrorInvalidValue;      // kernels index with 32-bit arithmetic
     relu_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out),
                                                                   total4);
     return cudaGetLastError();

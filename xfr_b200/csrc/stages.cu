@@ -123,24 +123,28 @@ cudaError_t launch_stem_fwd(const float* x, const float* W, const float* b, cons
 
 // ------------------------------------------------------------------ shortcut helpers
 __global__ void subsample2_kernel(const float* __restrict__ u, float* __restrict__ out, int H, int W, int C4, size_t total4) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // 32-bit index arithmetic (launchers reject totals >= 2^31): a 64-bit division by a run-time divisor costs ~100 instructions,
+    // which made these bandwidth kernels issue-bound (ncu r2: join_kernel 78 % issue-active at 2.7 TB/s)
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
-    int c = i % C4;
-    size_t p = i / C4;
-    int w = p % (W / 2); p /= (W / 2);
-    int h = p % (H / 2);
-    size_t n = p / (H / 2);
+    const unsigned c = i % (unsigned)C4;
+    unsigned p = i / (unsigned)C4;
+    const unsigned w = p % (unsigned)(W / 2); p /= (unsigned)(W / 2);
+    const unsigned h = p % (unsigned)(H / 2);
+    const size_t n = p / (unsigned)(H / 2);
     reinterpret_cast<float4*>(out)[i] = __ldg(reinterpret_cast<const float4*>(u) + ((n * H + 2 * h) * W + 2 * w) * C4 + c);
 }
 
 __global__ void avgpool2_kernel(const float* __restrict__ u, float* __restrict__ out, int H, int W, int C4, size_t total4) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // 32-bit index arithmetic (launchers reject totals >= 2^31): a 64-bit division by a run-time divisor costs ~100 instructions,
+    // which made these bandwidth kernels issue-bound (ncu r2: join_kernel 78 % issue-active at 2.7 TB/s)
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
-    int c = i % C4;
-    size_t p = i / C4;
-    int w = p % (W / 2); p /= (W / 2);
-    int h = p % (H / 2);
-    size_t n = p / (H / 2);
+    const unsigned c = i % (unsigned)C4;
+    unsigned p = i / (unsigned)C4;
+    const unsigned w = p % (unsigned)(W / 2); p /= (unsigned)(W / 2);
+    const unsigned h = p % (unsigned)(H / 2);
+    const size_t n = p / (unsigned)(H / 2);
     const float4* b = reinterpret_cast<const float4*>(u) + ((n * H + 2 * h) * W + 2 * w) * C4 + c;
     float4 a = __ldg(b), b1 = __ldg(b + C4), c0 = __ldg(b + (size_t)W * C4), c1 = __ldg(b + (size_t)W * C4 + C4);
     // torch avg_pool2d: sum in window order, then divide by the pool size
@@ -154,23 +158,24 @@ __global__ void avgpool2_kernel(const float* __restrict__ u, float* __restrict__
 
 // ------------------------------------------------------------------ pair tensors (bf16x2 plan, common.cuh)
 __global__ void to_pair_kernel(const float* __restrict__ in, float* __restrict__ out, int C, size_t total4) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
-    const int C4 = C / 4;
+    const unsigned C4 = C / 4;
     const float4 t = __ldg(reinterpret_cast<const float4*>(in) + i);
     const float v[4] = {t.x, t.y, t.z, t.w};
     st_pair4(out, i / C4, C, (int)(i % C4) * 4, v);
 }
 __global__ void from_pair_kernel(const float* __restrict__ in, float* __restrict__ out, int C, size_t total4) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
-    const int C4 = C / 4;
+    const unsigned C4 = C / 4;
     float v[4];
     ld_pair4(in, i / C4, C, (int)(i % C4) * 4, v);
     reinterpret_cast<float4*>(out)[i] = make_float4(v[0], v[1], v[2], v[3]);
 }
 cudaError_t launch_to_pair(const float* in, float* out, size_t rows, int C, int inverse, cudaStream_t st) {
     size_t total4 = rows * (size_t)(C / 4);
+    if (total4 >= 0x7FFFFF00ull) return cudaErrorInvalidValue;      // kernels index with 32-bit arithmetic
     if (total4 == 0) return cudaSuccess;
     if (inverse) from_pair_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(in, out, C, total4);
     else to_pair_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(in, out, C, total4);
@@ -179,11 +184,13 @@ cudaError_t launch_to_pair(const float* in, float* out, size_t rows, int C, int 
 
 cudaError_t launch_subsample2(const float* u, float* out, int N, int H, int W, int C, cudaStream_t st) {
     size_t total4 = (size_t)N * (H / 2) * (W / 2) * (C / 4);
+    if (total4 >= 0x7FFFFF00ull) return cudaErrorInvalidValue;      // kernels index with 32-bit arithmetic
     subsample2_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(u, out, H, W, C / 4, total4);
     return cudaGetLastError();
 }
 cudaError_t launch_avgpool2(const float* u, float* out, int N, int H, int W, int C, cudaStream_t st) {
     size_t total4 = (size_t)N * (H / 2) * (W / 2) * (C / 4);
+    if (total4 >= 0x7FFFFF00ull) return cudaErrorInvalidValue;      // kernels index with 32-bit arithmetic
     avgpool2_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(u, out, H, W, C / 4, total4);
     return cudaGetLastError();
 }
@@ -315,15 +322,15 @@ __global__ void __launch_bounds__(256, MINB) join_kernel(JoinArgs a, size_t tota
     const int mode = MODE >= 0 ? MODE : a.mode;
     // one thread = 4 channels of one pixel of one SAMPLE; it walks the gradient-row groups (mate, non-mate, ...) of that sample so
     // that the saved tensors (out, o3, xr3, res) and the BatchNorm constants are read once, not once per group
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
-    const int C4 = a.C / 4;
-    int c = (int)(i % C4) * 4;
-    size_t p = i / C4;
-    int w = p % a.W; p /= a.W;
-    int h = p % a.H;
-    int n = (int)(p / a.H);
-    size_t ms = ((size_t)n * a.H + h) * a.W + w;
+    const unsigned C4 = a.C / 4;
+    const int c = (int)(i % C4) * 4;
+    unsigned p = i / C4;
+    const int w = p % (unsigned)a.W; p /= (unsigned)a.W;
+    const int h = p % (unsigned)a.H;
+    const int n = (int)(p / (unsigned)a.H);
+    const size_t ms = ((size_t)n * a.H + h) * a.W + w;
     float4 uv = ld4(a.out + ms * a.C + c), ov = ld4(a.o3 + ms * a.C + c), xv = ld4(a.xr3 + ms * a.C + c);
     float u[4] = {uv.x, uv.y, uv.z, uv.w}, o[4] = {ov.x, ov.y, ov.z, ov.w}, x[4] = {xv.x, xv.y, xv.z, xv.w};
     float r[4] = {0.f, 0.f, 0.f, 0.f};
@@ -371,14 +378,14 @@ __global__ void __launch_bounds__(256, MINB) join_kernel(JoinArgs a, size_t tota
 
 // A/B twin of join_kernel: one thread per (gradient row, pixel, 4 channels); saved tensors are re-read per gradient-row group
 __global__ void join_rows_kernel(JoinArgs a, size_t total4) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
-    const int C4 = a.C / 4;
-    int c = (int)(i % C4) * 4;
-    size_t p = i / C4;
-    int w = p % a.W; p /= a.W;
-    int h = p % a.H;
-    int j = (int)(p / a.H);
+    const unsigned C4 = a.C / 4;
+    const int c = (int)(i % C4) * 4;
+    unsigned p = i / C4;
+    const int w = p % (unsigned)a.W; p /= (unsigned)a.W;
+    const int h = p % (unsigned)a.H;
+    const int j = (int)(p / (unsigned)a.H);
     int n = j % a.N;
     float z[4] = {0.f, 0.f, 0.f, 0.f};
     if (h % a.up == 0 && w % a.up == 0) {
@@ -420,6 +427,7 @@ cudaError_t launch_join(const JoinArgs& a, cudaStream_t st) {
         return cudaGetLastError();
     }
     size_t total4 = (size_t)a.N * a.H * a.W * (a.C / 4);
+    if (total4 >= 0x7FFFFF00ull) return cudaErrorInvalidValue;      // kernels index with 32-bit arithmetic
     // occupancy decides this kernel (tools/join_probe.py, 128 probes x 2 groups, the four boundaries of a ResNet-101 sweep, all variants
     // bit-identical): per-row twin (46 registers) 2,024 us; per sample with a runtime hook mode: 104 registers (2 CTAs per SM) 2,393 us,
     // 80 (3) 1,846 us, 64 (4) 1,667 us; hook mode as a template constant (fewer BatchNorm constants live): 4 CTAs 1,416 us (default),
@@ -437,13 +445,13 @@ cudaError_t launch_join(const JoinArgs& a, cudaStream_t st) {
 
 __global__ void ds_res_kernel(const float* __restrict__ g, const float* __restrict__ ap, float* __restrict__ gres_lo,
                               int N, size_t HW, int C, int Cr, int mode, float eps, size_t total4) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
-    const int C4 = Cr / 4;
-    int c = (int)(i % C4) * 4;
-    size_t p = i / C4;              // j*HW + pixel
-    size_t j = p / HW, pix = p % HW;
-    size_t n = j % N;
+    const unsigned C4 = Cr / 4;
+    const int c = (int)(i % C4) * 4;
+    const size_t p = i / C4;              // j*HW + pixel
+    const unsigned j = (unsigned)p / (unsigned)HW, pix = (unsigned)p % (unsigned)HW;
+    const size_t n = j % (unsigned)N;
     float4 gv = ld4(g + p * C + c);
     float4 av = ld4(ap + (n * HW + pix) * Cr + c);
     float gg[4] = {gv.x, gv.y, gv.z, gv.w}, aa[4] = {av.x, av.y, av.z, av.w};
@@ -460,6 +468,7 @@ __global__ void ds_res_kernel(const float* __restrict__ g, const float* __restri
 cudaError_t launch_ds_res(const float* g, const float* ap, float* gres_lo, int J, int N, int H, int W, int C, int Cr,
                           int mode, float eps, cudaStream_t st) {
     size_t total4 = (size_t)J * H * W * (Cr / 4);
+    if (total4 >= 0x7FFFFF00ull) return cudaErrorInvalidValue;      // kernels index with 32-bit arithmetic
     ds_res_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(g, ap, gres_lo, N, (size_t)H * W, C, Cr, mode, eps, total4);
     return cudaGetLastError();
 }
@@ -468,10 +477,10 @@ cudaError_t launch_ds_res(const float* g, const float* ap, float* gres_lo, int J
 // zc = two affine hooks (Conv2d of layer1.0.conv1, AvgPool2d(k=1) of its shortcut) on z = zmain + gres, a = x = mp
 __global__ void stem_bwd_a_kernel(const float* __restrict__ zmain, const float* __restrict__ gres, const float* __restrict__ mp,
                                   float* __restrict__ zc, size_t per_sample4, int N, int mode, float eps, size_t total4) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
-    size_t j = i / per_sample4, r = i % per_sample4;
-    size_t n = j % N;
+    const unsigned j = i / (unsigned)per_sample4, r = i % (unsigned)per_sample4;
+    const size_t n = j % (unsigned)N;
     float4 a = reinterpret_cast<const float4*>(zmain)[i];
     float4 b = gres ? reinterpret_cast<const float4*>(gres)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 m = __ldg(reinterpret_cast<const float4*>(mp) + n * per_sample4 + r);
@@ -595,12 +604,12 @@ cudaError_t launch_stem_bwd(const float* zmain, const float* gres, const float* 
 __global__ void bn_hook_kernel(const float* __restrict__ g, const float* __restrict__ o, const float* __restrict__ xr,
                                const float* __restrict__ bn, float* __restrict__ y, size_t rows_saved, int C, int kind, int mode,
                                float eps, size_t total4) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
-    const int C4 = C / 4;
+    const unsigned C4 = C / 4;
     const int c = (int)(i % C4) * 4;
     const size_t row = i / C4;
-    const size_t rs = row % rows_saved;
+    const size_t rs = (unsigned)row % (unsigned)rows_saved;
     float4 ov = ld4(o + rs * C + c);
     float4 sp = ld4(bn + 2 * C + c), tp = ld4(bn + 3 * C + c);
     const float oo[4] = {ov.x, ov.y, ov.z, ov.w}, spv[4] = {sp.x, sp.y, sp.z, sp.w}, tpv[4] = {tp.x, tp.y, tp.z, tp.w};
@@ -620,6 +629,7 @@ __global__ void bn_hook_kernel(const float* __restrict__ g, const float* __restr
 cudaError_t launch_bn_hook(const float* g, const float* o, const float* xr, const float* bn, float* y, size_t rows, size_t rows_saved,
                            int C, int kind, int mode, float eps, cudaStream_t st) {
     size_t total4 = rows * (C / 4);
+    if (total4 >= 0x7FFFFF00ull) return cudaErrorInvalidValue;      // kernels index with 32-bit arithmetic
     bn_hook_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(g, o, xr, bn, y, rows_saved, C, kind, mode, eps, total4);
     return cudaGetLastError();
 }
@@ -654,13 +664,13 @@ cudaError_t launch_head_seed(const float* Pn, const float* W2, int C, int D, int
 //   7: a = relu(s0), x = relu(s1)                         (Light-CNN Split hook: s0 = conv output, s1 = its positive twin)
 //   8: a = relu(s0), x = relu(relu(s1)*sp + tp + s2)      (VGGFace2 ResNet-50 block ReLU: s0 = out, s1 = o3, s2 = positive shortcut)
 __global__ void hook_kernel(HookArgs A, size_t total) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;          // 32-bit index arithmetic (the launcher rejects totals >= 2^32)
     if (i >= total) return;
-    const int c = (int)(i % A.C);
-    size_t p = i / A.C;
-    const int w = (int)(p % A.W); p /= A.W;
-    const int h = (int)(p % A.H);
-    const int j = (int)(p / A.H);
+    const int c = (int)(i % (unsigned)A.C);
+    unsigned p = i / (unsigned)A.C;
+    const int w = (int)(p % (unsigned)A.W); p /= (unsigned)A.W;
+    const int h = (int)(p % (unsigned)A.H);
+    const int j = (int)(p / (unsigned)A.H);
     const int n = j % A.N;
     const size_t ms = ((size_t)n * A.H + h) * A.W + w;
     float z = 0.f;
@@ -731,6 +741,7 @@ __global__ void hook_kernel(HookArgs A, size_t total) {
 
 cudaError_t launch_hook(const HookArgs& a, cudaStream_t st) {
     size_t total = (size_t)a.J * a.H * a.W * a.C;
+    if (total >= 0xFFFFFF00ull) return cudaErrorInvalidValue;          // the kernel indexes with 32-bit arithmetic
     hook_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, total);
     return cudaGetLastError();
 }
@@ -895,12 +906,12 @@ cudaError_t launch_trunc_threshold(const float* P2, const double* sums, float pc
 __global__ void contrast_kernel(const float* __restrict__ P2, const double* __restrict__ sums, const float* __restrict__ thr,
                                 float* __restrict__ out, int N, int HW, int C4) {
     // C4 lanes per pixel (C = 64 -> 16 lanes), C4 a power of two <= 32
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t total = (size_t)N * HW * C4;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;         // 32-bit index arithmetic (N * HW * C4 < 2^31, checked by the launcher)
+    const unsigned total = (unsigned)N * HW * C4;
     float s = 0.f;
-    size_t pixg = i / C4;
+    const unsigned pixg = i / (unsigned)C4;
     if (i < total) {
-        size_t n = pixg / HW;
+        const unsigned n = pixg / (unsigned)HW;
         float sm = (float)sums[n], sn = (float)sums[N + n];
         float t = thr ? thr[n] : -1.f;
         float4 a = reinterpret_cast<const float4*>(P2)[i];
@@ -919,6 +930,7 @@ cudaError_t launch_contrast(const float* P2, const double* sums, const float* th
     int C4 = C / 4;
     if (C4 > 32 || (C4 & (C4 - 1))) return cudaErrorInvalidValue;
     size_t total = (size_t)N * HW * C4;
+    if (2 * total >= 0x7FFFFF00ull) return cudaErrorInvalidValue;      // 32-bit index arithmetic in the kernel
     contrast_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P2, sums, thr, out, N, HW, C4);
     return cudaGetLastError();
 }
@@ -983,6 +995,107 @@ cudaError_t launch_saliency_post(const float* mwp, float* out, int B, int H, int
         attr[dev] = true;
     }
     saliency_post_kernel<<<B, 512, smem, st>>>(mwp, out, H, W, eps);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ saliency .npz format
+// show.processSaliency (show.py:131-137): attMap -= min; attMap /= (max + 1e-9); skimage.transform.resize(attMap, img.shape[:2],
+// order=3, mode='constant') - the cubic resize that turns the 112x112 maps into the 224x224 maps the evaluation stores.
+// scikit-image >= 0.19 (skimage/transform/_warps.py, resize(): no anti-aliasing when up-scaling) evaluates it as
+//     scipy.ndimage.zoom(attMap, zoom, order=3, mode='grid-constant', cval=0, grid_mode=True)  followed by a clip to the input range,
+// i.e. (scipy/ndimage/_interpolation.py zoom(), src/ni_splines.c, src/ni_interpolation.c NI_ZoomShift):
+//   1. pad by 12 with zeros (_prepad_for_spline_filter), 2. cubic B-spline prefilter per axis in double - gain (1-z)(1-1/z), pole
+//   z = sqrt(3) - 2, mirror initial conditions, axis 0 first -, 3. output pixel i samples at (i + 0.5) * in/out - 0.5 (+ 12) with
+//   the four B-spline weights of get_spline_interpolation_weights, 4. cast to the input dtype (float32), clip.
+// One CTA per map; the padded coefficient image lives in shared memory as doubles ((h+24) x (w+24) x 8 B <= 227 KB: h, w <= 144).
+// tests/test_inpaintgame.py pins this kernel to scipy.ndimage.zoom (7e-15 for the restatement, fp32 rounding for the kernel).
+__global__ void __launch_bounds__(512) cubic_zoom_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w, int oh,
+                                                         int ow, int normalize) {
+    extern __shared__ double zs[];
+    __shared__ float red_lo[16], red_hi[16];
+    constexpr int NP = 12;
+    const int ph = h + 2 * NP, pw = w + 2 * NP;
+    const float* src = in + (size_t)blockIdx.x * h * w;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    // range of the map (processSaliency's min-shift / max-normalise, and the clip range of resize)
+    float lo = INFINITY, hi = -INFINITY;
+    for (int i = tid; i < h * w; i += nt) { const float v = src[i]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
+    for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if ((tid & 31) == 0) { red_lo[tid >> 5] = lo; red_hi[tid >> 5] = hi; }
+    __syncthreads();
+    lo = red_lo[0]; hi = red_hi[0];
+    for (int i = 1; i < (nt >> 5); ++i) { lo = fminf(lo, red_lo[i]); hi = fmaxf(hi, red_hi[i]); }
+    float scale_den = 1.f, clip_lo = lo, clip_hi = hi;
+    if (normalize) {                                  // float32 arithmetic, as numpy does on a float32 map
+        scale_den = __fadd_rn(__fsub_rn(hi, lo), 1e-9f);
+        clip_lo = 0.f;
+        clip_hi = __fdiv_rn(__fsub_rn(hi, lo), scale_den);
+    }
+    for (int i = tid; i < ph * pw; i += nt) {
+        const int y = i / pw - NP, x = i % pw - NP;
+        double v = 0.0;
+        if (y >= 0 && y < h && x >= 0 && x < w) {
+            const float f = src[y * w + x];
+            v = (double)(normalize ? __fdiv_rn(__fsub_rn(f, lo), scale_den) : f);
+        }
+        zs[i] = v;
+    }
+    __syncthreads();
+    const double z = sqrt(3.0) - 2.0, gain = (1.0 - z) * (1.0 - 1.0 / z);
+    // prefilter: axis 0 (columns of the padded image, stride pw), then axis 1 (rows, stride 1); one thread per line
+    for (int axis = 0; axis < 2; ++axis) {
+        const int n = axis == 0 ? ph : pw, lines = axis == 0 ? pw : ph;
+        const int step = axis == 0 ? pw : 1, lstep = axis == 0 ? 1 : pw;
+        const double z_n_1 = pow(z, (double)(n - 1));
+        for (int l = tid; l < lines; l += nt) {
+            double* c = zs + (size_t)l * lstep;
+            for (int i = 0; i < n; ++i) c[i * step] *= gain;
+            double z_i = z, c0 = c[0] + z_n_1 * c[(n - 1) * step];
+            for (int i = 1; i < n - 1; ++i) { c0 += z_i * (c[i * step] + z_n_1 * c[(n - 1 - i) * step]); z_i *= z; }
+            c[0] = c0 / (1.0 - z_n_1 * z_n_1);
+            for (int i = 1; i < n; ++i) c[i * step] += z * c[(i - 1) * step];
+            c[(n - 1) * step] = (z / (z * z - 1.0)) * (c[(n - 1) * step] + z * c[(n - 2) * step]);
+            for (int i = n - 2; i >= 0; --i) c[i * step] = z * (c[(i + 1) * step] - c[i * step]);
+        }
+        __syncthreads();
+    }
+    float* dst = out + (size_t)blockIdx.x * oh * ow;
+    for (int i = tid; i < oh * ow; i += nt) {
+        const int oy = i / ow, ox = i % ow;
+        double wy[4], wx[4];
+        int y0, x0;
+        {
+            const double c = ((double)oy + 0.5) * (double)h / (double)oh - 0.5 + NP, f = floor(c), t = c - f, t1 = 1.0 - t;
+            wy[1] = (t * t * (t - 2.0) * 3.0 + 4.0) / 6.0; wy[2] = (t1 * t1 * (t1 - 2.0) * 3.0 + 4.0) / 6.0; wy[0] = t1 * t1 * t1 / 6.0;
+            wy[3] = 1.0 - wy[0] - wy[1] - wy[2];
+            y0 = (int)f - 1;
+        }
+        {
+            const double c = ((double)ox + 0.5) * (double)w / (double)ow - 0.5 + NP, f = floor(c), t = c - f, t1 = 1.0 - t;
+            wx[1] = (t * t * (t - 2.0) * 3.0 + 4.0) / 6.0; wx[2] = (t1 * t1 * (t1 - 2.0) * 3.0 + 4.0) / 6.0; wx[0] = t1 * t1 * t1 / 6.0;
+            wx[3] = 1.0 - wx[0] - wx[1] - wx[2];
+            x0 = (int)f - 1;
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc += wy[a] * wx[b] * zs[(y0 + a) * pw + x0 + b];
+        dst[i] = fminf(fmaxf((float)acc, clip_lo), clip_hi);
+    }
+}
+
+cudaError_t launch_cubic_zoom(const float* in, float* out, int B, int h, int w, int oh, int ow, int normalize, cudaStream_t st) {
+    const size_t smem = (size_t)(h + 24) * (w + 24) * sizeof(double);
+    if (smem > 226 * 1024 || B < 1) return cudaErrorInvalidValue;      // 227 KB per CTA minus the kernel's static arrays
+    static size_t attr[XFRB_MAX_DEV] = {};            // largest dynamic shared-memory size opted into so far, per device
+    const int dev = current_device_slot();
+    if (smem > attr[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(cubic_zoom_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr[dev] = smem;
+    }
+    cubic_zoom_kernel<<<B, 512, smem, st>>>(in, out, h, w, oh, ow, normalize);
     return cudaGetLastError();
 }
 

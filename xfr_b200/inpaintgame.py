@@ -155,11 +155,27 @@ def mean_ebp(wb, probe_im, net_name=None, ebp_version=None, device=None):
     return wb.ebp(x, P if device is None else P.to(device))
 
 
+def process_saliency_batch(wb, maps, out_hw=(224, 224)):
+    """show.processSaliency (show.py:131-137) for a batch of maps on the B200: min-shift, max-normalise and the cubic resize to
+    the probe size as ONE kernel launch (xfrb_cubic_zoom: one CTA per map, spline coefficients in shared memory).  maps
+    [N,h,w] float32 (numpy, or a device tensor straight from the sweep) -> numpy float32 [N,oh,ow].  The definition is the one of
+    process_saliency below - scikit-image >= 0.19's resize(order=3, mode='constant') = scipy.ndimage.zoom(order=3,
+    mode='grid-constant', grid_mode=True) + clip - and the kernel is pinned to scipy's result (tests/test_inpaintgame.py)."""
+    be = wb.net.engine(wb._ebp_with_bias).be
+    dev = wb.net._device()
+    t = torch.as_tensor(np.ascontiguousarray(maps) if isinstance(maps, np.ndarray) else maps, dtype=torch.float32).to(dev).contiguous()
+    out = torch.empty((t.shape[0],) + tuple(out_hw), dtype=torch.float32, device=dev)
+    be.cubic_zoom(t, out, normalize=True)
+    return out.cpu().numpy()
+
+
 def process_saliency(img, attMap):
     """show.py:131-137: min-shift, max-normalise, cubic resize to the image size.  The resize is scikit-image's
     (README.md:37 pins >= 0.17.2; absent here): from 0.19 on `resize(order=3, mode='constant')` without anti-aliasing (an
-    upscale) is scipy.ndimage.zoom(order=3, mode='grid-constant', grid_mode=True) followed by a clip to the input range,
-    which is what runs here.  Parity at this call is unpinned (no reference output without scikit-image)."""
+    upscale) is scipy.ndimage.zoom(order=3, mode='grid-constant', grid_mode=True) followed by a clip to the input range
+    (skimage/transform/_warps.py resize(): zoom_factors = 1 / factors, ndi.zoom(..., mode=ndi_mode, cval=cval, grid_mode=True),
+    then _clip_warp_output), which is what runs here.  Parity against scikit-image itself is unpinned (it is not installed and no
+    reference output exists); the definition is pinned to scipy, which is what scikit-image calls."""
     import scipy.ndimage
     attMap = np.asarray(attMap)
     attMap = attMap - attMap.min()
@@ -201,6 +217,21 @@ def generate_wb_smaps_batch(wb, jobs, output_dirs, mask_ids, ebp_ver, device=Non
         if not todo:
             continue
         maps = run_contrastive_triplet_ebp_batch(wb, [jobs[i] for i in todo], pct, device)
+        sizes = {np.asarray(jobs[i][2]).shape[:2] for i in todo}
+        if len(sizes) == 1 and getattr(wb.net.engine(wb._ebp_with_bias).be, 'name', '') == 'cuda':
+            # every probe of the game is 224x224: the .npz arithmetic of show.create_save_smap (show.py:212-220) for the whole batch,
+            # the cubic resize as one kernel launch
+            m32 = np.array(maps, dtype=np.float32)
+            m32 -= m32.min(axis=(1, 2), keepdims=True)
+            m32 /= m32.sum(axis=(1, 2), keepdims=True)
+            big = process_saliency_batch(wb, m32, next(iter(sizes)))
+            for i, m in zip(todo, big):
+                d = os.path.dirname(files[i])
+                if d:
+                    os.makedirs(d, exist_ok=True)
+                np.savez_compressed(files[i], saliency_map=m)
+                written.append(files[i])
+            continue
         for i, m in zip(todo, maps):
             save_smap(files[i], m, jobs[i][2])
             written.append(files[i])

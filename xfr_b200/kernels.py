@@ -58,6 +58,7 @@ _SIGNATURES = {
     'xfrb_contrast': [_P, _P, _P, _P, _I, _I, _I, _P],
     'xfrb_trunc_threshold': [_P, _P, _F, _P, _I, ctypes.c_longlong, _P],
     'xfrb_saliency_post': [_P, _P, _I, _I, _I, _F, _P],
+    'xfrb_cubic_zoom': [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     'xfrb_twin_blends': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     'xfrb_conv_bias': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'xfrb_lc_conv1': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
@@ -319,6 +320,11 @@ class CudaBackend(object):
     def saliency_post(self, mwp, out):
         B, H, W = mwp.shape
         self._check(self.lib.xfrb_saliency_post(_ptr(mwp), _ptr(out), B, H, W, self.eps, self._st()))
+
+    def cubic_zoom(self, maps, out, normalize=True):
+        """[B,h,w] fp32 -> out [B,oh,ow]: show.processSaliency's normalisation + cubic resize (include/xfrb.h xfrb_cubic_zoom)"""
+        B, h, w = maps.shape
+        self._check(self.lib.xfrb_cubic_zoom(_ptr(maps), _ptr(out), B, h, w, out.shape[1], out.shape[2], 1 if normalize else 0, self._st()))
 
     def twin_blends(self, orig, inp, value, thr, masks, out, mask_f32=False):
         """orig / inp [C,H,W], value [H,W] + thr [K] (or masks [K,H,W]), all float64 -> out [K,H,W,C] fp32 blends."""
