@@ -71,12 +71,16 @@ class ClockSampler(threading.Thread):
         return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.rows[0][1]), 'reasons': reasons, 'samples': len(sm)}
 
 
-# DRAM bytes of one layer3 launch (128-probe sweep) of each kernel family from `ncu --set full`
-# (profiles/r1_ncu_full_bwd_i_final.csv, r1_ncu_full_fwd_g.csv)
-NCU_TRAFFIC = {'dgrad_join': 952e6, 'dgrad_mid': 131e6, 'conv_dual': 387e6}
+# DRAM bytes (read + write) of one layer3 launch (128-probe sweep) of each kernel family from `ncu --set full`, bf16x2 plan
+# (profiles/r2_ncu_full_bf16x2.csv: JOIN dgrad 574 + 378 MB, 3x3 MID dgrad 107 + 25 MB, conv3 forward 66 + 152 MB - the 126 MB L2
+# holds part of a launch's writes back past its end, so per-launch DRAM writes under-count)
+NCU_TRAFFIC = {'dgrad_join': 952e6, 'dgrad_mid': 132e6, 'conv_dual': 218e6}
+# tcgen05 issue peaks of this chip measured by tools/mma_peak.cu (profiles/r2_mma_peak.jsonl; operands resident in shared memory, M = 128
+# per CTA, N = 256): kind::tf32 1,116 TFLOP/s, kind::f16 (bf16 operands) 2,232 TFLOP/s at 1.84 GHz - TF32 is exactly half of bf16
+MMA_PEAK_TFLOPS = {'tf32': 1116.0, 'bf16': 2232.0}
 
 
-def kernel_families(eng, step_fn):
+def kernel_families(eng, step_fn, gemm='bf16x2'):
     """One extra (untimed) step with CUDA events around every GEMM-backed launch: per kernel family the launch count,
     average device time, algorithmic bytes / flops per launch and what that is of the HBM / tensor peak."""
     be = eng.be
@@ -115,16 +119,18 @@ def kernel_families(eng, step_fn):
         for name in saved:
             delattr(be, name)
     hbm, _ = measured_peaks()
-    tf32_peak = 0.5 * tensor_peak()
+    bf16 = gemm == 'bf16x2'
+    mma_peak = MMA_PEAK_TFLOPS['bf16' if bf16 else 'tf32']
     dump = os.environ.get('XFRB_BENCH_LAUNCHES')          # per-launch rows (name, A shape, us, bytes, flops) for roofline studies
     if dump:
         with open(dump, 'w') as f:
             for r in rec:
                 f.write(json.dumps({'k': r[0], 'us': 1e3 * r[1].elapsed_time(r[2]), 'bytes': r[3], 'flops': r[4], 'shape': r[5]}) + '\n')
     out = []
-    label = {'dgrad_join': 'W+ dgrad + JOIN hook chain (conv_tc_kernel<BN,2,JOIN>)', 'dgrad_mid': 'W+ dgrad + MID hook chain (conv_tc_kernel<BN,2,MID>)',
-             'conv_dual': 'forward dual conv: o, xr, act (conv_tc_kernel<BN,3,FWD_DUAL>)'}
-    passes = {'dgrad_join': 2.0, 'dgrad_mid': 2.0, 'conv_dual': 2.5}
+    sp = (4, 5) if bf16 else (2, 3)
+    label = {'dgrad_join': 'W+ dgrad + JOIN hook chain (conv_tc_kernel<BN,%d,JOIN>)' % sp[0], 'dgrad_mid': 'W+ dgrad + MID hook chain (conv_tc_kernel<BN,%d,MID>)' % sp[0],
+             'conv_dual': 'forward dual conv: o, xr, act (conv_tc_kernel<BN,%d,FWD_DUAL>)' % sp[1]}
+    passes = {'dgrad_join': 2.0, 'dgrad_mid': 2.0, 'conv_dual': 2.5}      # MMA passes per useful flop (bf16x2: bf16 passes; split-TF32: TF32 passes)
     for name in ('dgrad_join', 'dgrad_mid', 'conv_dual'):
         rr = [r for r in rec if r[0] == name]
         if not rr:
@@ -133,8 +139,8 @@ def kernel_families(eng, step_fn):
         by, fl = sum(r[3] for r in rr), sum(r[4] for r in rr)
         out.append({'kernel': label[name], 'launches': len(rr), 'avg_us': 1e6 * t / len(rr),
                     'alg_bytes_per_launch': by / len(rr), 'achieved_gbs': by / t / 1e9, 'hbm_frac': by / t / 1e9 / hbm,
-                    'useful_tflops': fl / t / 1e12, 'issued_tf32_tflops': passes[name] * fl / t / 1e12,
-                    'tf32_frac': passes[name] * fl / t / 1e12 / tf32_peak, 'ncu_dram_bytes_layer3_launch': NCU_TRAFFIC[name]})
+                    'useful_tflops': fl / t / 1e12, 'issued_mma_tflops': passes[name] * fl / t / 1e12, 'mma_kind': 'bf16' if bf16 else 'tf32',
+                    'mma_frac_of_measured_issue_peak': passes[name] * fl / t / 1e12 / mma_peak, 'ncu_dram_bytes_layer3_launch': NCU_TRAFFIC[name]})
     return out
 
 
@@ -584,7 +590,7 @@ def main():
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.summary()
-    families = kernel_families(eng, step_resident) if rank == 0 else []      # after the timed regions: events around launches
+    families = kernel_families(eng, step_resident, args.gemm) if rank == 0 else []      # after the timed regions: events around launches
 
     if world > 1:
         lt = torch.tensor([float(launches), bwd_ms], device=dev)
@@ -614,8 +620,9 @@ def main():
         'clocks': clocks,
         'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
                      'traffic': NCU_TRAFFIC['dgrad_join'],
-                     'traffic_note': 'DRAM read+write of one layer3 JOIN launch (ncu --set full, profiles/r1_ncu_full_bwd_i_final.csv); '
+                     'traffic_note': 'DRAM read+write of one layer3 JOIN launch at a 128-probe sweep (ncu --set full, profiles/r2_ncu_full_bf16x2.csv); '
                                      'its algorithmic bytes are 976e6',
+                     'mma_issue_peaks_measured_tflops': MMA_PEAK_TFLOPS,
                      'kernel': 'EBP backward sweep (conv_tc_kernel dgrad + fused hook epilogues, join/stem kernels)',
                      'peak_source': peak_src, 'bwd_ms_per_step': bwd_ms / args.steps,
                      'tensor_tflops_whole_step': FLOP_PER_MAP * B * args.steps / (ms / 1e3) / 1e12 / 1.0,
