@@ -12,12 +12,16 @@ namespace xfrb {
 // tuning knobs of the bf16x2 (PAIRA) epilogue, overridable at build time for A/B runs (python -m xfr_b200.build --define ...)
 // Measured on a B200, 256-probe ResNet-101 sweeps (profiles/r2_notes.md): none of the variants beats the layout of the TF32 kernels
 // (XFRB_PAIRA_EW 0: idle split warpgroup kept, 8 epilogue warps at 200 registers, 12 at 128 for JOIN) - 3,855-3,897 maps/s against
-// 3,741 (EW 8, 224 registers, JOIN loads ahead), 3,737 (EW 12), 3,701 (EW 8 unpaired), 3,670 (+ TMEM prefetch), 3,597 (no per-tile barrier)
+// 3,741 (EW 8, 224 registers, JOIN loads ahead), 3,737 (EW 12), 3,701 (EW 8 unpaired), 3,670 (+ TMEM prefetch), 3,597 (no per-tile barrier),
+// 3,747 vs 3,796 in the same call (JOIN operands staged by cp.async)
 #ifndef XFRB_PAIRA_EW
 #define XFRB_PAIRA_EW 0               /* 0: the warp layout of the TF32 kernels; 8 / 12: the split warpgroup's warps become epilogue warps (224 / 152 registers) */
 #endif
 #ifndef XFRB_PAIRA_PAIRED
 #define XFRB_PAIRA_PAIRED 0           /* a warp takes the two 16-column slabs of a 32-column group back to back: both halves of every 128-byte line */
+#endif
+#ifndef XFRB_PAIRA_JOIN_STAGE
+#define XFRB_PAIRA_JOIN_STAGE 0       /* JOIN: the next slab's four operand tensors are copied global -> shared by cp.async while this slab is computed (measured: 526 vs 486 us per layer3 launch - slower) */
 #endif
 #ifndef XFRB_PAIRA_JOIN_L2_PREFETCH
 #define XFRB_PAIRA_JOIN_L2_PREFETCH 0 /* JOIN: prefetch.global.L2 of the next slab's operand lines (measured -2 %) */
@@ -225,12 +229,18 @@ struct TcCfg {
     static constexpr uint32_t RING_BUDGET = 192 * 1024;
     static constexpr bool SPLITRING = !CTA2;
     static constexpr bool SHORT = (KIND == EPI_JOIN && (SPLIT == 2 || SPLIT == 4));      // epilogue-bound: leave the memory to L1
+    // bf16x2 JOIN: every epilogue warp owns an 8 KB staging buffer (4 operand tensors x 32 rows x 64 bytes) that cp.async fills with
+    // the NEXT slab's operands while the current slab is computed - the load latency that was a third of the kernel's stall samples
+    // (ncu r2: first use of a loaded operand) hides behind math and stores without a second set of 64 load registers.  The main-loop
+    // ring shrinks to ONE stage to make room: JOIN tiles have 1 - 8 k-blocks and their epilogue, not their main loop, is the bound.
+    static constexpr bool STAGE_LOADS = KIND == EPI_JOIN && PAIRA && XFRB_PAIRA_JOIN_STAGE;
+    static constexpr int SHORT_STAGES = STAGE_LOADS ? 1 : 2;
     static constexpr int COUPLED_RAW = RING_BUDGET / (A_BYTES + B_BYTES);
-    static constexpr int COUPLED = SHORT ? 2 : (COUPLED_RAW > 8 ? 8 : COUPLED_RAW);
+    static constexpr int COUPLED = SHORT ? SHORT_STAGES : (COUPLED_RAW > 8 ? 8 : COUPLED_RAW);
     static constexpr int NB_PICK = B_BYTES >= 32 * 1024 ? 2 : (B_BYTES >= 16 * 1024 ? 3 : 4);
-    static constexpr int NB = SPLITRING ? (SHORT ? 2 : NB_PICK) : COUPLED;
+    static constexpr int NB = SPLITRING ? (SHORT ? SHORT_STAGES : NB_PICK) : COUPLED;
     static constexpr int NA_RAW = (RING_BUDGET - NB * B_BYTES) / A_BYTES;
-    static constexpr int NA = SPLITRING ? (SHORT ? 2 : (NA_RAW > 6 ? 6 : NA_RAW)) : COUPLED;
+    static constexpr int NA = SPLITRING ? (SHORT ? SHORT_STAGES : (NA_RAW > 6 ? 6 : NA_RAW)) : COUPLED;
     static constexpr uint32_t RING_BYTES = NA * A_BYTES + NB * B_BYTES;
     static constexpr uint32_t TMEM_COLS = 2 * BN;          // two accumulator stages (128 or 256: powers of two)
     // per-channel constants staged per accumulator stage: rows bn[0..3] (alpha, beta, sp, tp), bias_t, bias_p, PRM_LD wide
@@ -255,7 +265,8 @@ struct TcCfg {
                   "setmaxnreg budgets exceed the CTA's register pool");
     static constexpr uint32_t TR_BYTES = EPI_WARPS * 2048;      // per epilogue warp: 32 rows x 16 columns transpose slab
     static constexpr uint32_t BAR_BYTES = 512;
-    static constexpr uint32_t SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + BAR_BYTES + PRM_BYTES + TR_BYTES;
+    static constexpr uint32_t LD_BYTES = STAGE_LOADS ? EPI_WARPS * 8192 : 0;
+    static constexpr uint32_t SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + BAR_BYTES + PRM_BYTES + TR_BYTES + LD_BYTES;
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory a CTA can opt into");
 };
 
@@ -580,6 +591,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int cgl = lane & 3;                      // my 4-channel group inside the slab
         const int rsub = lane >> 2;                    // my row inside each group of 8 rows
         float4* tbuf = tr_s + ew * 128;
+        uint8_t* ldbuf = smem_gen + Cfg::RING_BYTES + Cfg::BAR_BYTES + Cfg::PRM_BYTES + Cfg::TR_BYTES + (Cfg::STAGE_LOADS ? ew * 8192 : 0);
         constexpr int CH = (KIND == EPI_FWD_DUAL) ? BN / 2 : BN;      // channels per tile
         constexpr int NL = (KIND == EPI_JOIN) ? 4 : (KIND == EPI_MID) ? 2 : 1;     // tensors loaded per output element
         struct Loads { float4 v[NL][4]; };             // one slab's global loads: [tensor][row group]
@@ -801,8 +813,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // group, its two slabs back to back: the warp then touches both 64-byte halves of each 128-byte line of the operand and
             // output tensors within one slab time (the second load hits L1, the two stores merge in L2)
             auto col = [&](int t) { return PAIRED ? part * 32 + (t >> 1) * (32 * (EW / 4)) + (t & 1) * 16 : part * 16 + t * SLAB_STRIDE; };
+            // lane (rsub, cgl) copies, and later reads back, the same 16 bytes: [tensor][row 8i + rsub][cgl] - nothing crosses lanes
+            auto stage_slab = [&](int j) {
+                const int c = cbase + j + 4 * cgl;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t dst = smem_u32(ldbuf) + (uint32_t)((8 * i + rsub) * 64 + cgl * 16);
+                    const size_t offs = (size_t)msav[i] * ep.C + c;
+                    const uint32_t n = vrow[i] ? 16u : 0u;             // invalid rows: zero-fill, nothing is read
+                    const float* src[4] = {ep.o + offs, ep.xr + offs, ep.outp + offs, ep.g_res + (size_t)mrow[i] * ep.C + c};
+#pragma unroll
+                    for (int tz = 0; tz < 4; ++tz)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst + tz * 2048u), "l"(vrow[i] ? src[tz] : ep.o), "r"(n) : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            auto fetch_slab = [&](Loads& L) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int tz = 0; tz < NL; ++tz)
+                        L.v[tz][i] = *reinterpret_cast<const float4*>(ldbuf + tz * 2048 + (8 * i + rsub) * 64 + cgl * 16);
+            };
             const int j0 = col(0);
             if (LOAD_AHEAD && j0 < CH) issue_loads(j0, La);
+            if (Cfg::STAGE_LOADS && !(dbg & 1) && j0 < CH) stage_slab(j0);      // in flight while the main loop of this tile finishes
             if (!PRM_DIRECT) asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");      // constants staged
             mbar_wait(tfull_bar(a), aph);
             tc_fence_after();
@@ -834,11 +870,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 };
+                if (Cfg::STAGE_LOADS && !(dbg & 1)) {
+#pragma unroll 1
+                    for (int t = 0; col(t) < CH; ++t) {
+                        fetch_slab(La);
+                        if (col(t + 1) < CH) stage_slab(col(t + 1));
+                        process(col(t), La, Va, CH, Va);
+                    }
+                } else {
 #pragma unroll 1
                 for (int t = 0; col(t) < CH; ++t) {
                     if (col(t + 1) < CH) prefetch_slab(col(t + 1));
                     issue_loads(col(t), La);
                     process(col(t), La, Va, CH, Va);
+                }
                 }
             }
             tc_fence_before();
