@@ -228,11 +228,26 @@ int xfrb_twin_blends(const double* orig, const double* inp, const double* value,
  *   p = a*relu(z), replaced for gradient row `prior_row` by the prior (a full tensor `prior` [H*W*C], or the single element
  *   prior_elem = prior_val); P_out <- p; return value per `mode` (`affine`: Conv/Linear/AvgPool/BatchNorm kinds;
  *   relu_or_maxpool = 2 marks ReLU/MaxPool kinds for the 'norelu' rule whitebox.py:418-419, passed with mode 1);
- *   then optionally masked by (a > 0) and scaled by bn[post_scale_row][c] (ReLU / BatchNorm backward); -> z_out. */
+ *   then optionally masked by (a > 0) and scaled by bn[post_scale_row][c] (ReLU / BatchNorm backward); -> z_out.
+ *   prior_entry (device pointer to ONE XfrbPriorEntry, or NULL): the prior of this firing read from device memory instead of the
+ *   four prior arguments - a sweep captured into a CUDA graph is then replayed with other priors by rewriting the table, which is
+ *   how the layer sweeps and weighted_subtree_ebp (whitebox.py:584-737) run without per-launch host work; with it, probe_out
+ *   (device float, or NULL) receives p of element probe_elem of row probe_row (P_mate at the arg-max node, whitebox.py:699). */
+typedef struct XfrbPriorEntry {
+    int row;               /* gradient row that takes the prior at this firing, -1: none */
+    int probe_row;         /* -1: no probe */
+    long long elem;        /* one-element prior: flattened [H,W,C] index (when tensor == NULL) */
+    long long probe_elem;
+    const float* tensor;   /* full prior tensor [H*W*C] or NULL */
+    float val;
+    float pad_;
+    long long pad2_;
+} XfrbPriorEntry;          /* 48 bytes */
 int xfrb_hook(const float* z_in, int up, int zc, const float* z_in2, int k2, int c2, float pre_scale, const float* s0, int c0,
               const float* s1, const float* s2, int c2s, const float* bn, const float* prior, int prior_row, long long prior_elem,
               float prior_val, float* P_out, float* z_out, int recipe, int affine, int relu_or_maxpool, int mode, int post_mask,
-              int post_scale_row, int pre_scale_row, int J, int N, int H, int W, int C, float eps, void* stream);
+              int post_scale_row, int pre_scale_row, int J, int N, int H, int W, int C, float eps, const void* prior_entry,
+              float* probe_out, void* stream);
 /* seed[j,:] = Pn[j,:] @ W2[j % N]  (Pn [J,Ccls], W2 [N,Ccls,D]) */
 int xfrb_head_seed(const float* Pn, const float* W2, int Ccls, int D, int J, int N, float* seed, void* stream);
 /* Jacobian of F.normalize (resnet.py:250): gout = (gin - xn*<xn,gin>)/nrm, rows of length D <= 1024 */

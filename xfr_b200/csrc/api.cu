@@ -259,7 +259,8 @@ int xfrb_bn_hook(const float* g, const float* o, const float* xr, const float* b
 int xfrb_hook(const float* z_in, int up, int zc, const float* z_in2, int k2, int c2, float pre_scale, const float* s0, int c0,
               const float* s1, const float* s2, int c2s, const float* bn, const float* prior, int prior_row, long long prior_elem,
               float prior_val, float* P_out, float* z_out, int recipe, int affine, int relu_or_maxpool, int mode, int post_mask,
-              int post_scale_row, int pre_scale_row, int J, int N, int H, int W, int C, float eps, void* stream) {
+              int post_scale_row, int pre_scale_row, int J, int N, int H, int W, int C, float eps, const void* prior_entry,
+              float* probe_out, void* stream) {
     if (up < 1 || k2 < 1 || recipe < 0 || recipe > 8 || ((post_scale_row >= 0 || pre_scale_row >= 0) && bn == nullptr))
         return finish("xfrb_hook", cudaErrorInvalidValue);
     HookArgs a;
@@ -269,6 +270,8 @@ int xfrb_hook(const float* z_in, int up, int zc, const float* z_in2, int k2, int
     a.post_scale_row = post_scale_row; a.J = J; a.N = N; a.H = H; a.W = W; a.C = C; a.eps = eps;
     a.prior_row = prior_row; a.prior_elem = prior_elem; a.prior_val = prior_val;
     a.pre_scale_row = pre_scale_row;
+    a.ptab = static_cast<const PriorEntry*>(prior_entry); a.probe_out = probe_out;
+    static_assert(sizeof(PriorEntry) == sizeof(XfrbPriorEntry), "include/xfrb.h XfrbPriorEntry mirrors PriorEntry");
     return finish("xfrb_hook", launch_hook(a, (cudaStream_t)stream));
 }
 

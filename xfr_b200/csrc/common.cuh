@@ -210,6 +210,16 @@ struct ConvGeom {
     int Nn;          // GEMM N (rows of B)
 };
 
+struct PriorEntry {                        // 48 bytes, mirrored by xfr_b200/generic.py PRIOR_DTYPE
+    int row;                               // gradient row that takes the prior at this firing, -1: none
+    int probe_row;                         // -1: no probe
+    long long elem;                        // one-element prior: flattened [H,W,C] index (used when tensor == nullptr)
+    long long probe_elem;
+    const float* tensor;                   // full prior tensor [H*W*C] or nullptr
+    float val;
+    float pad_;
+    long long pad2_;
+};
 // arguments of the generic single-hook kernel (xfrb_hook): one _backward_ebp firing with optional prior and P recording
 struct HookArgs {
     const float* z_in;  int up;            // incoming gradient [J,H/up,W/up,zc]; lands on pixels divisible by `up`
@@ -227,6 +237,10 @@ struct HookArgs {
     float eps;
     int prior_row; long long prior_elem; float prior_val;   // one-element prior (layerwise 'elementwise'); prior_row < 0: none
     int pre_scale_row;                     // >= 0: z *= bn[pre_scale_row][c] before the hook (BatchNorm backward)
+    // device-resident prior of this firing (one PriorEntry, include/xfrb.h XfrbPriorEntry): when set it REPLACES prior / prior_row /
+    // prior_elem / prior_val above, so a captured CUDA graph of a sweep can be replayed with different priors
+    const PriorEntry* ptab;
+    float* probe_out;                      // with ptab: p of element ptab->probe_elem of row ptab->probe_row is also written here
 };
 cudaError_t launch_hook(const HookArgs& a, cudaStream_t st);
 

@@ -9,20 +9,28 @@ namespace xfrb {
 
 // ------------------------------------------------------------------ stem: Conv2d(1, 96, 5, 1, 2)
 // x [N,H,W] (one channel) -> c [N,H,W,C2] = conv_W(x) + b ; cpos (optional) = conv_relu(W)(relu(x)) + bpos.
-// Wt [25][C2] tap-major, so a warp's lanes read consecutive channels.  One thread per (pixel, channel).
+// Wt [25][C2] tap-major.  One thread = one pixel x 4 consecutive channels: the 25 window values sit in registers, the weights
+// come from shared memory as float4 (one copy per CTA), so a tap costs one shared load per 4 (or 8, with the twin) FMAs.  The
+// thread-per-(pixel, channel) form it replaces issued two global loads per FMA and ran 20x above its store bound (5.7 ms for 128
+// probes, profiles/r2_notes.md).  Same accumulation order (taps row-major, fmaf chain), so the results are bit-identical.
+template <bool TWIN>
 __global__ void __launch_bounds__(256) lc_conv1_kernel(const float* __restrict__ x, const float* __restrict__ Wt,
                                                        const float* __restrict__ b, const float* __restrict__ bpos,
                                                        float* __restrict__ c, float* __restrict__ cpos, int H, int W, int C2,
-                                                       size_t total) {
+                                                       unsigned total4) {
+    extern __shared__ float4 w_s[];                                 // [25][C2/4]
+    const int C4 = C2 / 4;
+    for (int k = threadIdx.x; k < 25 * C4; k += blockDim.x) w_s[k] = reinterpret_cast<const float4*>(Wt)[k];
+    __syncthreads();
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;      // 32-bit index arithmetic (launchers reject totals >= 2^31)
-    if (i >= total) return;
-    const int ch = (int)(i % (unsigned)C2);
-    unsigned p = i / (unsigned)C2;
+    if (i >= total4) return;
+    const int c4 = (int)(i % (unsigned)C4);
+    unsigned p = i / (unsigned)C4;
     const int w = (int)(p % (unsigned)W); p /= (unsigned)W;
     const int h = (int)(p % (unsigned)H);
     const size_t n = p / (unsigned)H;
     const float* xi = x + n * H * W;
-    float acc = 0.f, accp = 0.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, accp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int r = 0; r < 5; ++r) {
         const int hh = h + r - 2;
@@ -32,20 +40,32 @@ __global__ void __launch_bounds__(256) lc_conv1_kernel(const float* __restrict__
             const int ww = w + s - 2;
             if (ww < 0 || ww >= W) continue;
             const float xv = __ldg(xi + (size_t)hh * W + ww);
-            const float wv = __ldg(Wt + (r * 5 + s) * C2 + ch);
-            acc = fmaf(xv, wv, acc);
-            accp = fmaf(fmaxf(xv, 0.f), fmaxf(wv, 0.f), accp);
+            const float4 wv = w_s[(r * 5 + s) * C4 + c4];
+            const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                acc[q] = fmaf(xv, wq[q], acc[q]);
+                if (TWIN) accp[q] = fmaf(fmaxf(xv, 0.f), fmaxf(wq[q], 0.f), accp[q]);
+            }
         }
     }
-    c[i] = __fadd_rn(acc, b[ch]);
-    if (cpos != nullptr) cpos[i] = __fadd_rn(accp, bpos[ch]);
+    const float4 bv = reinterpret_cast<const float4*>(b)[c4];
+    reinterpret_cast<float4*>(c)[i] = make_float4(__fadd_rn(acc[0], bv.x), __fadd_rn(acc[1], bv.y), __fadd_rn(acc[2], bv.z), __fadd_rn(acc[3], bv.w));
+    if (TWIN) {
+        const float4 bq = reinterpret_cast<const float4*>(bpos)[c4];
+        reinterpret_cast<float4*>(cpos)[i] = make_float4(__fadd_rn(accp[0], bq.x), __fadd_rn(accp[1], bq.y), __fadd_rn(accp[2], bq.z), __fadd_rn(accp[3], bq.w));
+    }
 }
 
 cudaError_t launch_lc_conv1(const float* x, const float* Wt, const float* b, const float* bpos, float* c, float* cpos, int N,
                             int H, int W, int C2, cudaStream_t st) {
-    size_t total = (size_t)N * H * W * C2;
-    if (total >= 0x7FFFFF00ull) return cudaErrorInvalidValue;      // kernels index with 32-bit arithmetic
-    lc_conv1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, Wt, b, bpos, c, cpos, H, W, C2, total);
+    size_t total4 = (size_t)N * H * W * (C2 / 4);
+    if (C2 % 4 || total4 >= 0x7FFFFF00ull) return cudaErrorInvalidValue;      // float4 channels, 32-bit index arithmetic
+    const size_t smem = (size_t)25 * C2 * sizeof(float);
+    if (smem > 48 * 1024) return cudaErrorInvalidValue;
+    const unsigned grid = (unsigned)((total4 + 255) / 256);
+    if (cpos != nullptr) lc_conv1_kernel<true><<<grid, 256, smem, st>>>(x, Wt, b, bpos, c, cpos, H, W, C2, (unsigned)total4);
+    else lc_conv1_kernel<false><<<grid, 256, smem, st>>>(x, Wt, b, bpos, c, cpos, H, W, C2, (unsigned)total4);
     return cudaGetLastError();
 }
 

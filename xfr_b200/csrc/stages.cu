@@ -663,68 +663,49 @@ cudaError_t launch_head_seed(const float* Pn, const float* W2, int C, int D, int
 //   6: a = relu(s0), x = relu(s1) + relu(s2)              (Light-CNN resblock output: s0 = out + res, s1 = out, s2 = res)
 //   7: a = relu(s0), x = relu(s1)                         (Light-CNN Split hook: s0 = conv output, s1 = its positive twin)
 //   8: a = relu(s0), x = relu(relu(s1)*sp + tp + s2)      (VGGFace2 ResNet-50 block ReLU: s0 = out, s1 = o3, s2 = positive shortcut)
-__global__ void hook_kernel(HookArgs A, size_t total) {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;          // 32-bit index arithmetic (the launcher rejects totals >= 2^32)
-    if (i >= total) return;
-    const int c = (int)(i % (unsigned)A.C);
-    unsigned p = i / (unsigned)A.C;
-    const int w = (int)(p % (unsigned)A.W); p /= (unsigned)A.W;
-    const int h = (int)(p % (unsigned)A.H);
-    const int j = (int)(p / (unsigned)A.H);
-    const int n = j % A.N;
-    const size_t ms = ((size_t)n * A.H + h) * A.W + w;
-    float z = 0.f;
-    if (A.z_in != nullptr && h % A.up == 0 && w % A.up == 0) {
-        const int Hm = A.H / A.up, Wm = A.W / A.up;
-        z = A.z_in[(((size_t)j * Hm + h / A.up) * Wm + w / A.up) * A.zc + c];
+struct HookPrior { int row; long long elem; float val; const float* tensor; int probe_row; long long probe_elem; };
+
+// the prior of this firing: from the device table entry when there is one (graph replay), else from the launch arguments
+__device__ __forceinline__ HookPrior hook_prior(const HookArgs& A) {
+    HookPrior P;
+    if (A.ptab != nullptr) {
+        const PriorEntry e = *A.ptab;
+        P.row = e.row; P.elem = e.elem; P.val = e.val; P.tensor = e.tensor; P.probe_row = e.probe_row; P.probe_elem = e.probe_elem;
+    } else {
+        P.row = A.prior_row; P.elem = A.prior_elem; P.val = A.prior_val; P.tensor = A.prior; P.probe_row = -1; P.probe_elem = -1;
     }
-    if (A.z_in2 != nullptr && c < A.c2) {
-        const int Hr = A.H / A.k2, Wr = A.W / A.k2;
-        z = __fadd_rn(z, __fdiv_rn(A.z_in2[(((size_t)j * Hr + h / A.k2) * Wr + w / A.k2) * A.c2 + c], (float)(A.k2 * A.k2)));
-    }
-    z = __fmul_rn(z, A.pre_scale);
-    if (A.pre_scale_row >= 0) z = __fmul_rn(z, A.bn[A.pre_scale_row * A.C + c]);        // BatchNorm backward ahead of its hook
-    float a = 0.f, x = 0.f;
-    BnC b = {0.f, 0.f, 0.f, 0.f};
-    if (A.bn != nullptr) b = {A.bn[c], A.bn[A.C + c], A.bn[2 * A.C + c], A.bn[3 * A.C + c]};
-    const float v0 = (A.s0 != nullptr && c < A.c0) ? A.s0[ms * A.c0 + c] : 0.f;
-    switch (A.recipe) {
+    return P;
+}
+
+// (a, x) of one element from the recipe sources
+__device__ __forceinline__ void hook_ax(int recipe, float v0, float v1, float v2, const BnC& b, float& a, float& x) {
+    switch (recipe) {
         case 0: a = x = fmaxf(v0, 0.f); break;
         case 1: a = bn_act(v0, b); x = fmaxf(__fadd_rn(__fmul_rn(fmaxf(v0, 0.f), b.sp), b.tp), 0.f); break;
         case 2: a = x = bn_act(v0, b); break;
-        case 3: a = fmaxf(v0, 0.f); x = A.s1[ms * A.C + c]; break;
-        case 4: {
-            a = fmaxf(v0, 0.f);
-            float r = (A.s2 != nullptr && c < A.c2s) ? fmaxf(A.s2[ms * A.c2s + c], 0.f) : 0.f;
-            x = fmaxf(__fadd_rn(bn_act(A.s1[ms * A.C + c], b), r), 0.f);
-            break;
-        }
-        case 6: a = fmaxf(v0, 0.f); x = __fadd_rn(fmaxf(A.s1[ms * A.C + c], 0.f), fmaxf(A.s2[ms * A.C + c], 0.f)); break;
-        case 7: a = fmaxf(v0, 0.f); x = fmaxf(A.s1[ms * A.C + c], 0.f); break;
-        case 8: {
-            a = fmaxf(v0, 0.f);
-            const float r = (A.s2 != nullptr && c < A.c2s) ? A.s2[ms * A.c2s + c] : 0.f;
-            x = fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(fmaxf(A.s1[ms * A.C + c], 0.f), b.sp), b.tp), r), 0.f);
-            break;
-        }
-        default: a = fmaxf(v0, 0.f); x = A.s1[ms * A.C + c]; break;
+        case 4: a = fmaxf(v0, 0.f); x = fmaxf(__fadd_rn(bn_act(v1, b), fmaxf(v2, 0.f)), 0.f); break;
+        case 6: a = fmaxf(v0, 0.f); x = __fadd_rn(fmaxf(v1, 0.f), fmaxf(v2, 0.f)); break;
+        case 7: a = fmaxf(v0, 0.f); x = fmaxf(v1, 0.f); break;
+        case 8: a = fmaxf(v0, 0.f); x = fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(fmaxf(v1, 0.f), b.sp), b.tp), v2), 0.f); break;
+        default: a = fmaxf(v0, 0.f); x = v1; break;          // 3, 5
     }
-    const size_t off = i;
+}
+
+// the firing itself for one element: z (after the pre-scales) -> return value (after the post ops); pv = what P_out records
+__device__ __forceinline__ float hook_fire(const HookArgs& A, const HookPrior& P, bool has_prior, size_t e, int c, float z, float a,
+                                           float x, float& pv) {
     float ret;
     if (A.mode == XFRB_MODE_NONE) {
-        if (A.P_out != nullptr) A.P_out[off] = z;          // dA: the true gradient at this hooked tensor
+        pv = z;                                                // dA: the true gradient at this hooked tensor
         ret = z;
     } else {
         const float zh = fmaxf(z, 0.f);
-        float pv = __fmul_rn(a, zh);
-        const bool has_prior = (j == A.prior_row);
+        pv = __fmul_rn(a, zh);
         float pr = 0.f;
         if (has_prior) {
-            const size_t e = ((size_t)h * A.W + w) * A.C + c;
-            pr = A.prior != nullptr ? A.prior[e] : ((long long)e == A.prior_elem ? A.prior_val : 0.f);
+            pr = P.tensor != nullptr ? P.tensor[e] : ((long long)e == P.elem ? P.val : 0.f);
             pv = pr;                                           // p.data.copy_(p_prior)
         }
-        if (A.P_out != nullptr) A.P_out[off] = pv;
         const float quo = __fdividef(pv, __fadd_rn(x, A.eps));
         if (A.mode == XFRB_MODE_ALL) ret = quo;
         else if (A.mode == XFRB_MODE_AFFINEONLY) ret = A.affine ? quo : z;
@@ -736,13 +717,98 @@ __global__ void hook_kernel(HookArgs A, size_t total) {
     }
     if (A.post_mask) ret = a > 0.f ? ret : 0.f;
     if (A.post_scale_row >= 0) ret = __fmul_rn(ret, A.bn[A.post_scale_row * A.C + c]);
-    if (A.z_out != nullptr) A.z_out[off] = ret;
+    return ret;
+}
+
+// VEC = 4: one thread = 4 consecutive channels of one (row, pixel) - every channel count involved is a multiple of 4 and every
+// tensor 16-byte aligned (launch_hook checks) - so each tensor moves as float4 and the index arithmetic is paid once per four
+// elements (the scalar form ran at 1.4 TB/s of its streams, issue-bound: profiles/r2_notes.md).  VEC = 1: any shape.
+template <int VEC>
+__global__ void __launch_bounds__(256) hook_kernel(HookArgs A, size_t total) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;          // 32-bit index arithmetic (the launcher rejects totals >= 2^32)
+    if (i >= total) return;
+    const unsigned Cv = (unsigned)A.C / VEC;
+    const int c = (int)(i % Cv) * VEC;
+    unsigned p = i / Cv;
+    const int w = (int)(p % (unsigned)A.W); p /= (unsigned)A.W;
+    const int h = (int)(p % (unsigned)A.H);
+    const int j = (int)(p / (unsigned)A.H);
+    const int n = j % A.N;
+    const size_t ms = ((size_t)n * A.H + h) * A.W + w;
+    auto ldv = [&](const float* q, float* v) {
+        if constexpr (VEC == 4) { const float4 t = *reinterpret_cast<const float4*>(q); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+        else v[0] = *q;
+    };
+    auto stv = [&](float* q, const float* v) {
+        if constexpr (VEC == 4) *reinterpret_cast<float4*>(q) = make_float4(v[0], v[1], v[2], v[3]);
+        else *q = v[0];
+    };
+    float z[VEC], v0[VEC], v1[VEC], v2[VEC], t[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) z[q] = v0[q] = v1[q] = v2[q] = 0.f;
+    if (A.z_in != nullptr && h % A.up == 0 && w % A.up == 0) {
+        const int Hm = A.H / A.up, Wm = A.W / A.up;
+        ldv(A.z_in + (((size_t)j * Hm + h / A.up) * Wm + w / A.up) * A.zc + c, z);
+    }
+    if (A.z_in2 != nullptr && c < A.c2) {
+        const int Hr = A.H / A.k2, Wr = A.W / A.k2;
+        ldv(A.z_in2 + (((size_t)j * Hr + h / A.k2) * Wr + w / A.k2) * A.c2 + c, t);
+        const float kk = (float)(A.k2 * A.k2);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) z[q] = __fadd_rn(z[q], __fdiv_rn(t[q], kk));
+    }
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) z[q] = __fmul_rn(z[q], A.pre_scale);
+    if (A.pre_scale_row >= 0) {                                          // BatchNorm backward ahead of its hook
+        ldv(A.bn + A.pre_scale_row * A.C + c, t);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) z[q] = __fmul_rn(z[q], t[q]);
+    }
+    BnC b[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) b[q] = {0.f, 0.f, 0.f, 0.f};
+    if (A.bn != nullptr) {
+        float al[VEC], be[VEC], sp[VEC], tp[VEC];
+        ldv(A.bn + c, al); ldv(A.bn + A.C + c, be); ldv(A.bn + 2 * A.C + c, sp); ldv(A.bn + 3 * A.C + c, tp);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) b[q] = {al[q], be[q], sp[q], tp[q]};
+    }
+    const int rc = A.recipe;
+    if (A.s0 != nullptr && c < A.c0) ldv(A.s0 + ms * A.c0 + c, v0);
+    if (rc >= 3) ldv(A.s1 + ms * A.C + c, v1);                           // recipes 3 - 8 read s1 [N,H,W,C]
+    if ((rc == 4 || rc == 8) && A.s2 != nullptr && c < A.c2s) ldv(A.s2 + ms * A.c2s + c, v2);
+    if (rc == 6) ldv(A.s2 + ms * A.C + c, v2);
+    const HookPrior P = hook_prior(A);
+    const bool has_prior = (A.mode != XFRB_MODE_NONE) && (j == P.row);
+    const size_t e0 = ((size_t)h * A.W + w) * A.C + c;
+    float ret[VEC], pv[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+        float a, x;
+        hook_ax(rc, v0[q], v1[q], v2[q], b[q], a, x);
+        ret[q] = hook_fire(A, P, has_prior, e0 + q, c + q, z[q], a, x, pv[q]);
+    }
+    const size_t off = (size_t)i * VEC;
+    if (A.P_out != nullptr) stv(A.P_out + off, pv);
+    if (A.z_out != nullptr) stv(A.z_out + off, ret);
+    if (A.probe_out != nullptr && j == P.probe_row && P.probe_elem >= (long long)e0 && P.probe_elem < (long long)e0 + VEC)
+        *A.probe_out = pv[(int)(P.probe_elem - (long long)e0)];
 }
 
 cudaError_t launch_hook(const HookArgs& a, cudaStream_t st) {
     size_t total = (size_t)a.J * a.H * a.W * a.C;
     if (total >= 0xFFFFFF00ull) return cudaErrorInvalidValue;          // the kernel indexes with 32-bit arithmetic
-    hook_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, total);
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    const bool vec = a.C % 4 == 0 && a.zc % 4 == 0 && (a.s0 == nullptr || a.c0 % 4 == 0) && (a.z_in2 == nullptr || a.c2 % 4 == 0) &&
+                     (a.s2 == nullptr || a.c2s % 4 == 0 || a.recipe == 6) && al16(a.z_in) && al16(a.z_in2) && al16(a.s0) && al16(a.s1) &&
+                     al16(a.s2) && al16(a.bn) && al16(a.P_out) && al16(a.z_out);
+    static const int force_scalar = [] { const char* e = getenv("XFRB_HOOK_SCALAR"); return e ? atoi(e) : 0; }();   // A/B probe
+    if (vec && !force_scalar) {
+        total /= 4;
+        hook_kernel<4><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, total);
+    } else {
+        hook_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, total);
+    }
     return cudaGetLastError();
 }
 

@@ -67,7 +67,7 @@ class _Engine(object):
         return t if t.shape[0] == shape[0] else t[:shape[0]]
 
     # ------------------------------------------------------------ batch-1 latency: one CUDA graph per (operator, shapes, options)
-    def graph_call(self, op, tensors, **opts):
+    def graph_call(self, op, tensors, max_n=None, **opts):
         """Every caller of the reference is batch 1 (whitebox.py:482-527): a ResNet-101 sweep is ~225 launches, each with a
         ctypes call and two or three tensor-map encodes on the host, i.e. host-bound at ~9 ms per map.  For batches up to
         graph_max_n the whole sweep is therefore captured once into a CUDA graph (the workspace addresses are static, the tensor
@@ -76,11 +76,11 @@ class _Engine(object):
         impossible (CPU emulation backend, a capture already in progress)."""
         fn = getattr(self, op)
         x = tensors[0]
-        if (self.graph_max_n <= 0 or x.shape[0] > self.graph_max_n or not x.is_cuda or getattr(self.be, 'name', '') != 'cuda'
-                or torch.cuda.is_current_stream_capturing()):
+        if (self.graph_max_n <= 0 or x.shape[0] > (self.graph_max_n if max_n is None else max_n) or not x.is_cuda
+                or getattr(self.be, 'name', '') != 'cuda' or torch.cuda.is_current_stream_capturing()):
             return fn(*tensors, **opts)
         # tensors flagged static (the network's own fc2, 134 MB for the STR head) are baked in by address instead of copied
-        static = tuple(t.data_ptr() if t.dim() == 2 and t.shape[0] > 64 else None for t in tensors)
+        static = tuple(t.data_ptr() if t.dim() == 2 and t.shape[0] > 1024 else None for t in tensors)
         key = (op, tuple((tuple(t.shape), t.dtype) for t in tensors), static, tuple(sorted(opts.items())), float(self.be.eps))
         ent = self._graphs.get(key)
         if ent is None:                                   # first call: eager, allocates every buffer the sweep touches
@@ -95,17 +95,57 @@ class _Engine(object):
                     a.copy_(t)
             torch.cuda.current_stream(self.device).synchronize()
             g = torch.cuda.CUDAGraph()
+            l0 = getattr(self.be, 'launches', 0)
             with torch.cuda.graph(g):
                 out = fn(*ins, **opts)
             if key not in self._graphs:                   # the capture itself allocated (should not happen): stay eager
                 return fn(*tensors, **opts)
-            ent.update(graph=g, ins=ins, out=out)
+            ent.update(graph=g, ins=ins, out=out, launches=getattr(self.be, 'launches', 0) - l0)
+            self.be.launches = l0                         # nothing ran yet: the replay below counts them
         else:
             for a, t, p in zip(ent['ins'], tensors, static):
                 if p is None:
                     a.copy_(t, non_blocking=True)
         ent['graph'].replay()
+        self.be.launches += ent['launches']               # kernels of this library the replay enqueued
         return ent['out']
+
+    # ------------------------------------------------------------ firing-by-firing sweeps as replayable graphs
+    graph_generic_rows = 64           # gradient-row counts up to which generic_run is replayed from a captured graph (0: never)
+    prior_table_len = 512             # >= hook firings of any plugin's sweep (STR ResNet-101: 379, ResNet-50-128d: 158, Light-CNN: 88)
+
+    def prior_table(self, tag):
+        """A PriorTable of this engine, one per purpose: a captured graph holds its addresses."""
+        from .generic import PriorTable
+        key = ('ptab', tag)
+        t = self._ws.get(key)
+        if t is None:
+            t = self._ws[key] = PriorTable(self.prior_table_len, self.device)
+        return t
+
+    def generic_run(self, Pn, W2, mode='affineonly_with_prior', record=False, true_grad=False, hooked_fc2=False, ptab=None,
+                    gating=None, n_saved=None):
+        """One firing-by-firing sweep (generic.GenericSweep.run and its twins) as an operator graph_call can capture: the layer
+        sweeps and weighted_subtree_ebp repeat the same ~500 launches with nothing but the device-resident priors (ptab)
+        changing.  gating (None | bool): also score every firing of a 3-row true-gradient sweep (whitebox.py:684-696, rows =
+        cross-entropy / mate / non-mate; True: do_mated_similarity_gating).  n_saved only keys the graph table.
+        -> {'gs': the sweep object (layout of the recorded tensors), 'P', 'names', 'P2'[, 'score', 'arg']}"""
+        gs = self.sweep()
+        P, names, P2 = gs.run(Pn, W2, mode, record=record, true_grad=true_grad, hooked_fc2=hooked_fc2, ptab=ptab)
+        out = {'gs': gs, 'P': P, 'names': names, 'P2': P2}
+        if gating is not None:
+            n = len(P) - 1                                                   # not including the image layer
+            score = torch.empty(n, device=self.device)
+            arg = torch.empty(n, dtype=torch.int64, device=self.device)
+            for k in range(n):
+                gate = P[k][1] if gating else P[k][0]
+                self.be.subtree_score(gate.contiguous(), P[k][2].contiguous(), bool(gating), score[k:k + 1], arg[k:k + 1])
+            out['score'], out['arg'] = score, arg
+        return out
+
+    def generic_call(self, Pn, W2, **opts):
+        """generic_run through the graph table (CUDA backend) or directly (emulation backend, row counts above graph_generic_rows)"""
+        return self.graph_call('generic_run', (Pn.contiguous(), W2), max_n=self.graph_generic_rows, n_saved=self.saved['N'], **opts)
 
     def workspace_bytes(self):
         return sum(t.numel() * t.element_size() for t in self._ws.values() if torch.is_tensor(t))

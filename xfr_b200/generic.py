@@ -7,12 +7,107 @@ The schedule below is the firing order of SURVEY.md appendix A (validated agains
 firing is one launch of the `xfrb_hook` kernel, convolutions are `xfrb_dgrad_plain` GEMMs.  Gradient rows may carry
 different priors: row j's prior sits at firing k_j, which is how weighted_subtree_ebp batches its per-layer sub-trees.
 """
+import numpy as np
 import torch
 
 from .engine import MODE_IDS
 
 AFFINE = ('Conv', 'Linear', 'AvgPool', 'BatchNorm')       # substring test of reference whitebox.py:399,409
 MODE_NONE = 3
+
+# One entry per hook firing, mirrored by XfrbPriorEntry (include/xfrb.h) / PriorEntry (csrc/common.cuh): 48 bytes
+PRIOR_DTYPE = np.dtype([('row', '<i4'), ('probe_row', '<i4'), ('elem', '<i8'), ('probe_elem', '<i8'), ('tensor', '<u8'),
+                        ('val', '<f4'), ('pad', '<f4'), ('pad2', '<i8')])
+assert PRIOR_DTYPE.itemsize == 48
+
+
+class PriorRef(object):
+    """What CudaBackend.hook passes to xfrb_hook for firing k: the address of its table entry and of its probe slot."""
+    __slots__ = ('entry_ptr', 'probe_ptr')
+
+    def __init__(self, entry_ptr, probe_ptr):
+        self.entry_ptr, self.probe_ptr = entry_ptr, probe_ptr
+
+
+class PriorTable(object):
+    """The priors of ONE sweep as device data (entry k = hook firing k) instead of launch arguments, so that a sweep captured
+    into a CUDA graph is replayed with other priors by rewriting this table: the layer sweeps and weighted_subtree_ebp
+    (whitebox.py:584-737) issue the same ~500 launches per sweep with nothing but the priors changing.  An entry may also
+    carry a probe: p of one element of one row is written to probe[k] (P_mate at a sub-tree's arg-max node, whitebox.py:699,
+    without recording all of P).  On the CPU emulation backend the same table is resolved on the host."""
+
+    def __init__(self, n, device):
+        self.n = int(n)
+        self.device = torch.device(device)
+        self.host = np.zeros(self.n, PRIOR_DTYPE)
+        self.dev = torch.zeros(self.n * PRIOR_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
+        self.probe = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        self._stage = torch.zeros(self.n * PRIOR_DTYPE.itemsize, dtype=torch.uint8)
+        if self.device.type == 'cuda':
+            self._stage = self._stage.pin_memory()
+        self._keep = {}
+        self.clear()
+
+    def clear(self):
+        self.host[:] = 0
+        self.host['row'] = -1
+        self.host['probe_row'] = -1
+        self.host['probe_elem'] = -1
+        self._keep.clear()
+
+    def set_elem(self, k, row, elem, val):
+        e = self.host[k]
+        e['row'], e['elem'], e['val'], e['tensor'] = row, elem, val, 0
+
+    def set_tensor(self, k, row, tensor):
+        assert tensor.is_contiguous() and tensor.dtype == torch.float32 and tensor.device == self.device
+        self._keep[k] = tensor                                  # the entry holds a raw address
+        e = self.host[k]
+        e['row'], e['tensor'] = row, tensor.data_ptr()
+
+    def set_probe(self, k, row, elem):
+        e = self.host[k]
+        e['probe_row'], e['probe_elem'] = row, elem
+
+    def upload(self):
+        self._stage.copy_(torch.from_numpy(self.host.view(np.uint8)))
+        self.dev.copy_(self._stage, non_blocking=True)
+
+    def ref(self, k):
+        return PriorRef(self.dev.data_ptr() + PRIOR_DTYPE.itemsize * k, self.probe.data_ptr() + 4 * k)
+
+    def legacy(self, k):
+        """entry k as the (row, tensor) | (row, elem, val) | None argument of the host-resolved path"""
+        e = self.host[k]
+        if e['row'] < 0:
+            return None
+        if e['tensor']:
+            return (int(e['row']), self._keep[k])
+        return (int(e['row']), int(e['elem']), float(e['val']))
+
+
+class _PriorMixin(object):
+    """Where a firing's prior comes from: the {k: prior} dict of run(priors=...) or the PriorTable of run(ptab=...)."""
+    _ptab = None
+
+    def _prior_of(self, k):
+        """-> (prior argument of backend.hook, probe (row, elem) to resolve on the host or None)"""
+        t = self._ptab
+        if t is None:
+            return self._priors.get(k), None
+        assert k < t.n, 'PriorTable shorter than the sweep'
+        if getattr(self.be, 'name', '') == 'cuda':
+            return t.ref(k), None
+        e = t.host[k]
+        return t.legacy(k), ((int(e['probe_row']), int(e['probe_elem'])) if e['probe_row'] >= 0 else None)
+
+    def _hook(self, k, z_in, z_out, shape, recipe, affine, P_out=None, **kw):
+        prior, probe = self._prior_of(k)
+        if probe is not None and P_out is None:                  # host-resolved probe (emulation backend): needs p itself
+            P_out = torch.empty(shape, dtype=torch.float32, device=self.eng.device)
+        self.be.hook(z_in, z_out, shape, recipe, affine, self._m, prior=prior, P_out=P_out, **kw)
+        if probe is not None:
+            self._ptab.probe[k] = P_out[probe[0]].reshape(-1)[probe[1]]
 
 
 class _FC(object):
@@ -25,7 +120,7 @@ class _FC(object):
         return self.Bd
 
 
-class GenericSweep(object):
+class GenericSweep(_PriorMixin):
     def __init__(self, engine):
         self.eng = engine
         self.be = engine.be
@@ -46,9 +141,9 @@ class GenericSweep(object):
             return None
         return p.permute(0, 3, 1, 2) if p.shape[1] * p.shape[2] > 1 else p.reshape(p.shape[0], -1)
 
-    def run(self, Pn, W2, mode, priors=None, record=False, true_grad=False, hooked_fc2=False):
+    def run(self, Pn, W2, mode, priors=None, record=False, true_grad=False, hooked_fc2=False, ptab=None):
         """One sweep over J = Pn.shape[0] gradient rows.
-        priors: {firing k: (row, elem, value) | (row, tensor)}; record: keep p of every firing (list of [J,H,W,C]
+        priors: {firing k: (row, elem, value) | (row, tensor)}, or ptab: a PriorTable (device-resident, graph-replayable); record: keep p of every firing (list of [J,H,W,C]
         device tensors, NHWC; entry -1, the Conv2d hook on the image, is None: nothing reads it);
         true_grad: no hooks, signed weights, true BatchNorm backward; the recorded tensors are then the gradients dA.
         Returns (P list or None, names, P2 [J,112,112,64] = P[-2])."""
@@ -58,6 +153,7 @@ class GenericSweep(object):
         self._P = [] if record else None
         self._names = []
         self._priors = priors or {}
+        self._ptab = ptab
         self._norelu = (mode == 'norelu')
         m = MODE_NONE if true_grad else MODE_IDS[mode]
         self._m = m
@@ -77,7 +173,12 @@ class GenericSweep(object):
             P_out = torch.empty(J, 1, 1, 512, device=eng.device) if record else None
             if record:
                 self._P.append(P_out)
-            seed = eng.hooked_fc2_seed(Pn, W2, m, prior=self._priors.get(k), P_out=P_out, signed=true_grad).view(J, 1, 1, 512)
+            prior, probe = self._prior_of(k)
+            if probe is not None and P_out is None:          # host-resolved probe (emulation backend)
+                P_out = torch.empty(J, 1, 1, 512, device=eng.device)
+            seed = eng.hooked_fc2_seed(Pn, W2, m, prior=prior, P_out=P_out, signed=true_grad).view(J, 1, 1, 512)
+            if probe is not None:
+                self._ptab.probe[k] = P_out[probe[0]].reshape(-1)[probe[1]]
         else:
             seed = buf('gs_seed', J, 1, 1, 512)
             be.head_seed(Pn, W2, seed.view(J, 512))
@@ -154,8 +255,7 @@ class GenericSweep(object):
             self._P.append(P_out)
         z_out = self.eng.buf(out, *shape) if out is not None else None
         flag = 2 if (self._norelu and ('MaxPool' in kind or 'ReLU' in kind)) else 0
-        self.be.hook(z_in, z_out, shape, recipe, affine, self._m, prior=self._priors.get(k), P_out=P_out,
-                     relu_or_maxpool=flag, N=self.eng.saved['N'], **kw)
+        self._hook(k, z_in, z_out, shape, recipe, affine, P_out=P_out, relu_or_maxpool=flag, N=self.eng.saved['N'], **kw)
         return z_out
 
 
@@ -165,7 +265,7 @@ class R50Sweep(GenericSweep):
     hooks; the block ReLU's X sums positive-pass values), projection shortcuts are conv + BatchNorm whose hook fires before
     the main path's, un-hooked fc1 head on the wrapper, 1x1 feat_extract conv after the 7x7 average pool."""
 
-    def run(self, Pn, W2, mode, priors=None, record=False, true_grad=False, hooked_fc2=False):
+    def run(self, Pn, W2, mode, priors=None, record=False, true_grad=False, hooked_fc2=False, ptab=None):
         assert not hooked_fc2, 'the VGGFace2 plugin has no hooked classifier (whitebox.py:216)'
         eng, be, S = self.eng, self.be, self.eng.saved
         N, J = S['N'], Pn.shape[0]
@@ -173,6 +273,7 @@ class R50Sweep(GenericSweep):
         self._P = [] if record else None
         self._names = []
         self._priors = priors or {}
+        self._ptab = ptab
         self._norelu = (mode == 'norelu')
         m = MODE_NONE if true_grad else MODE_IDS[mode]
         self._m = m

@@ -48,7 +48,7 @@ _SIGNATURES = {
     'xfrb_stem_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
     'xfrb_bn_hook': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     'xfrb_hook': [_P, _I, _I, _P, _I, _I, _F, _P, _I, _P, _P, _I, _P, _P, _I, ctypes.c_longlong, _F, _P, _P, _I, _I, _I, _I, _I,
-                  _I, _I, _I, _I, _I, _I, _I, _F, _P],
+                  _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P],
     'xfrb_head_seed': [_P, _P, _I, _I, _I, _I, _P, _P],
     'xfrb_normalize_bwd': [_P, _P, _P, _P, _I, _I, _I, _P],
     'xfrb_maxpool_bwd': [_P, _P, _P, _P, _I, _I, _I, _P],
@@ -260,10 +260,14 @@ class CudaBackend(object):
     def hook(self, z_in, z_out, shape, recipe, affine, mode, s0=None, s1=None, s2=None, bn=None, up=1, zc=None, z_in2=None, k2=1,
              pre_scale=1.0, prior=None, P_out=None, relu_or_maxpool=0, post_mask=False, post_scale_row=-1, N=None,
              pre_scale_row=-1):
-        """One hook firing over [J,H,W,C] = shape; prior = None | (row, tensor) | (row, elem, val).  See include/xfrb.h."""
+        """One hook firing over [J,H,W,C] = shape; prior = None | (row, tensor) | (row, elem, val) | a generic.PriorRef (the prior
+        and an optional probe read from a device table entry: replayable from a captured graph).  See include/xfrb.h."""
         J, H, W, C = shape
         pr_t, pr_row, pr_elem, pr_val = None, -1, 0, 0.0
-        if prior is not None:
+        entry = probe = None
+        if prior is not None and hasattr(prior, 'entry_ptr'):
+            entry, probe = prior.entry_ptr, prior.probe_ptr
+        elif prior is not None:
             if len(prior) == 2:
                 pr_row, pr_t = prior
             else:
@@ -273,7 +277,8 @@ class CudaBackend(object):
                                        float(pre_scale), _ptr(s0), C if s0 is None else s0.shape[-1], _ptr(s1), _ptr(s2),
                                        0 if s2 is None else s2.shape[-1], _ptr(bn), _ptr(pr_t), int(pr_row), int(pr_elem),
                                        float(pr_val), _ptr(P_out), _ptr(z_out), recipe, 1 if affine else 0, relu_or_maxpool, mode,
-                                       1 if post_mask else 0, post_scale_row, pre_scale_row, J, Ns, H, W, C, self.eps, self._st()))
+                                       1 if post_mask else 0, post_scale_row, pre_scale_row, J, Ns, H, W, C, self.eps, entry, probe,
+                                       self._st()))
 
     def head_seed(self, Pn, W2, seed):
         J, Ccls = Pn.shape

@@ -21,6 +21,7 @@ import torch
 
 from . import packing
 from .engine import MODE_IDS, _Engine
+from .generic import _PriorMixin
 
 AFFINE = ('Conv', 'Linear', 'AvgPool', 'BatchNorm')
 MODE_NONE = 3
@@ -170,15 +171,16 @@ class LightCNNEngine(_Engine):
         return P2, chansum, sums
 
 
-class LightCNNSweep(object):
+class LightCNNSweep(_PriorMixin):
     """Firing-by-firing backward sweep; same interface as xfr_b200.generic.GenericSweep."""
 
     def __init__(self, engine):
         self.eng = engine
         self.be = engine.be
 
-    def run(self, Pn, W2, mode, priors=None, record=False, true_grad=False, hooked_fc2=False):
-        """priors: {firing k: (row, elem, value) | (row, tensor)} in the DEVICE layout (NHWC, padded Split columns);
+    def run(self, Pn, W2, mode, priors=None, record=False, true_grad=False, hooked_fc2=False, ptab=None):
+        """priors: {firing k: (row, elem, value) | (row, tensor)} in the DEVICE layout (NHWC, padded Split columns), or ptab: a
+        generic.PriorTable (device-resident, graph-replayable);
         record: keep p (true_grad: the incoming gradient dA) of every firing; returns (P list | None, names, P2)."""
         eng, be, S = self.eng, self.be, self.eng.saved
         N, J = S['N'], Pn.shape[0]
@@ -188,6 +190,7 @@ class LightCNNSweep(object):
         self._names = []
         self._layout = []                            # per firing: (real channels, padded channels, is_split)
         self._priors = priors or {}
+        self._ptab = ptab
         self._norelu = (mode == 'norelu')
         self._k_fcvec = -1
         self._m = m = MODE_NONE if true_grad else MODE_IDS[mode]
@@ -321,6 +324,6 @@ class LightCNNSweep(object):
             self._P.append(P_out)
         z_out = self.eng.buf(out, *shape) if out is not None else None
         flag = 2 if (self._norelu and ('MaxPool' in kind or 'ReLU' in kind)) else 0
-        self.be.hook(z_in, z_out, shape, recipe, affine, self._m, prior=self._priors.get(k), P_out=P_out,
-                     relu_or_maxpool=flag, N=self.eng.saved['N'], z_in2=z_in2, k2=1, **kw)
+        self._hook(k, z_in, z_out, shape, recipe, affine, P_out=P_out, relu_or_maxpool=flag, N=self.eng.saved['N'], z_in2=z_in2,
+                   k2=1, **kw)
         return z_out

@@ -446,6 +446,74 @@ class Whitebox(nn.Module):
             return np.stack([self._mwp_to_saliency_uint8(m) for m in res.numpy()])
         return res if out is not None else res.numpy()
 
+    def contrastive_ebp_stream(self, batches, k_poschannel=0, k_negchannel=1, outs=None, percentile=None):
+        """Streaming form of contrastive_ebp_batch for host-resident probes: `batches` is a sequence of [n,3,H,W] host tensors
+        (pinned memory makes the copies asynchronous), each swept against the classifier rows set for its n probes
+        (set_triplet_classifiers; an item may also be (x, x_mates, x_nonmates) with its own rows).  The host-to-device copy of
+        chunk i+1 runs on a copy stream while chunk i is swept, and the finished maps go back with an asynchronous copy, so the
+        copies stay off the critical path (3.4 ms of a 69 ms step at 256 probes otherwise).  Returns the list of [n,h,w] float32
+        maps (pinned host tensors, `outs` if given); results are identical to contrastive_ebp_batch."""
+        eng = self._engine()
+        dev = eng.device
+        if getattr(eng.be, 'name', '') != 'cuda' or self.convert_saliency_uint8:
+            res = []
+            for b, item in enumerate(batches):
+                x = item[0] if isinstance(item, (tuple, list)) else item
+                if isinstance(item, (tuple, list)):
+                    self.net.set_triplet_classifiers(item[1], item[2])
+                m = self.contrastive_ebp_batch(x, k_poschannel, k_negchannel, percentile=percentile)
+                m = torch.from_numpy(np.ascontiguousarray(m))
+                if outs is not None:
+                    outs[b].copy_(m)
+                    m = outs[b]
+                res.append(m)
+            return res
+        hk = self.net.hooked()
+        work, res = [], []
+        for b, item in enumerate(batches):
+            x = item[0] if isinstance(item, (tuple, list)) else item
+            if isinstance(item, (tuple, list)):
+                self.net.set_triplet_classifiers(item[1], item[2])
+            N = x.shape[0]
+            W2 = self.net.triplet_rows(N)
+            out = outs[b] if outs is not None else torch.empty(N, eng.map_hw, eng.map_hw).pin_memory()
+            res.append(out)
+            for i in range(0, N, _CHUNK):
+                work.append((x[i:i + _CHUNK], W2 if hk else W2[i:i + _CHUNK].contiguous(), out[i:i + _CHUNK]))
+        if not work:
+            return res
+        st = getattr(self, '_stream_state', None)
+        shape = (max(w[0].shape[0] for w in work),) + tuple(work[0][0].shape[1:])        # staging capacity: the largest chunk
+        if any(tuple(w[0].shape[1:]) != shape[1:] for w in work):
+            raise ValueError('contrastive_ebp_stream: every batch must have the same image shape')
+        if st is None or st['shape'][1:] != shape[1:] or st['shape'][0] < shape[0] or st['dev'] != dev:
+            st = self._stream_state = {'shape': shape, 'dev': dev, 'copy': torch.cuda.Stream(dev),
+                                       'stage': [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(2)],
+                                       'landed': [torch.cuda.Event() for _ in range(2)], 'free': [torch.cuda.Event() for _ in range(2)]}
+        main = torch.cuda.current_stream(dev)
+        for e in st['free']:
+            e.record(main)
+
+        def prefetch(i):
+            xs, s = work[i][0], i % 2
+            with torch.cuda.stream(st['copy']):
+                st['copy'].wait_event(st['free'][s])                   # the sweep that read this staging buffer is past its repack
+                st['stage'][s][:xs.shape[0]].copy_(xs, non_blocking=True)
+                st['landed'][s].record(st['copy'])
+        prefetch(0)
+        for i, (xs, ws, out) in enumerate(work):
+            s, n = i % 2, xs.shape[0]
+            main.wait_event(st['landed'][s])
+            x_nhwc = st['stage'][s][:n].permute(0, 2, 3, 1).contiguous()
+            st['free'][s].record(main)
+            if i + 1 < len(work):
+                prefetch(i + 1)
+            m = eng.graph_call('contrastive', (x_nhwc, ws), k_pos=k_poschannel, k_neg=k_negchannel, mode=self._ebp_subtree_mode,
+                               hooked_fc2=hk, percentile=percentile, saliency=True, num_classes=self.net.num_classes())
+            out.copy_(m, non_blocking=True)
+        main.synchronize()
+        return res
+
     # ---------------------------------------------------------------- reference API (batch 1)
     def ebp(self, x, Pn, mwp=False):
         """whitebox.py:482-504"""
@@ -580,22 +648,31 @@ class Whitebox(nn.Module):
         gs, W2 = self._generic(img_probe)
         hk = self.net.hooked()            # no triplet classifier: the network's own fc2 fires (and is indexed) first
         dev = W2.device
+        eng = gs.eng
         Pn = torch.cat((self._onehot(k_poschannel, dev), self._onehot(k_negchannel, dev)))
-        P, names, _ = gs.run(Pn, W2, self._ebp_subtree_mode, record=True, hooked_fc2=hk)
+        # every sweep below goes through the engine's graph table: the ~500 launches of a sweep are captured once and replayed,
+        # the per-layer priors travel in a device table (generic.PriorTable) instead of launch arguments
+        rec = eng.generic_call(Pn, W2, mode=self._ebp_subtree_mode, record=True, hooked_fc2=hk)
+        P, names = rec['P'], rec['names']
         k_layers = [int(k) % len(P) for k in k_layers]                 # negative indices as Python lists take them
         # the last firing (the Conv2d hook on the image) is not recorded: a prior there cannot reach P[-2], the map is all zero
         priors = {k: self._contrastive_prior(gs, P[k][0:1], P[k][1:2], k, mode, percentile, None).reshape(-1).contiguous()
                   for k in set(k_layers) if P[k] is not None}
         zero = self._zero_map(mwp)
-        del P
+        del P, rec
         self.P_layername = list(names)
         todo = sorted(priors)                                             # one gradient row per distinct firing
         maps = {}
-        for i in range(0, len(todo), rows_per_sweep):
-            chunk = todo[i:i + rows_per_sweep]
-            Z = torch.zeros(len(chunk), self.net.num_classes(), device=dev)
-            _, _, P2 = gs.run(Z, W2, self._ebp_subtree_mode, priors={k: (r, priors[k]) for r, k in enumerate(chunk)}, hooked_fc2=hk)
-            for k, m in zip(chunk, self._finish_map(P2, mwp)):
+        tab = eng.prior_table('rows')
+        Z = torch.zeros(min(rows_per_sweep, max(len(todo), 1)), self.net.num_classes(), device=dev)     # fixed row count: one graph
+        for i in range(0, len(todo), Z.shape[0]):
+            chunk = todo[i:i + Z.shape[0]]
+            tab.clear()
+            for r, k in enumerate(chunk):
+                tab.set_tensor(k, r, priors[k])
+            tab.upload()
+            P2 = eng.generic_call(Z, W2, mode=self._ebp_subtree_mode, hooked_fc2=hk, ptab=tab)['P2']
+            for k, m in zip(chunk, self._finish_map(P2[:len(chunk)], mwp)):
                 maps[k] = m
         return np.stack([maps.get(k, zero) for k in k_layers])
 
@@ -638,29 +715,39 @@ class Whitebox(nn.Module):
         Pn[0, 0] -= 1.0
         Pn[1, 0] = 1.0
         Pn[2, 1] = 1.0
-        dA, names, _ = gs.run(Pn, W2, subtree_mode, record=True, true_grad=True, hooked_fc2=hk)
-        n_layers = len(dA)
-        score = torch.empty(n_layers - 1, device=dev)
-        arg = torch.empty(n_layers - 1, dtype=torch.int64, device=dev)
-        for k in range(0, n_layers - 1):                                            # not including image layer (684)
-            gate = dA[k][1] if do_mated_similarity_gating else dA[k][0]
-            be.subtree_score(gate.contiguous(), dA[k][2].contiguous(), do_mated_similarity_gating, score[k:k + 1], arg[k:k + 1])
-        P_subtree = [float(v) for v in score.cpu().numpy()]
-        P_subtree_idx = arg.cpu().numpy()
-        del dA
+        # every sweep goes through the engine's graph table (captured once, replayed): the 3-row true-gradient sweep with the
+        # per-firing score / arg-max kernels (not including the image layer, 684), then P_mate with a probe at every arg-max
+        # node instead of a recording of all of P, then the one-element priors as batched gradient rows - priors and probes
+        # travel in device tables (generic.PriorTable), the only thing that changes between replays
+        tg = eng.generic_call(Pn, W2, mode=subtree_mode, record=True, true_grad=True, hooked_fc2=hk,
+                              gating=bool(do_mated_similarity_gating))
+        names = tg['names']
+        P_subtree = [float(v) for v in tg['score'].cpu().numpy()]
+        P_subtree_idx = tg['arg'].cpu().numpy()
+        n_layers = len(P_subtree) + 1
+        del tg
         k_subtree = np.argsort(np.array(P_subtree))                                 # ascending, one per layer (697)
         # layerwise EBP for every sub-tree: P_mate once, then one-element priors as batched gradient rows
         P0 = self._onehot(k_poschannel, dev)
-        P_mate, names, _ = gs.run(P0, W2, subtree_mode, record=True, hooked_fc2=hk)
-        seeds = [(int(k), int(P_subtree_idx[k]), float(P_mate[k].reshape(-1)[int(P_subtree_idx[k])])) for k in k_subtree]
-        del P_mate
+        probe = eng.prior_table('probe')
+        probe.clear()
+        for k in range(n_layers - 1):
+            probe.set_probe(k, 0, int(P_subtree_idx[k]))
+        probe.upload()
+        eng.generic_call(P0, W2, mode=subtree_mode, hooked_fc2=hk, ptab=probe)
+        p_at = probe.probe[:n_layers - 1].cpu().numpy()
+        seeds = [(int(k), int(P_subtree_idx[k]), float(p_at[k])) for k in k_subtree]
         P_img = []
-        for i in range(0, len(seeds), rows_per_sweep):
-            chunk = seeds[i:i + rows_per_sweep]
-            priors = {k: (r, e, v) for r, (k, e, v) in enumerate(chunk)}
-            Z = torch.zeros(len(chunk), self.net.num_classes(), device=dev)
-            _, _, P2 = gs.run(Z, W2, subtree_mode, priors=priors, hooked_fc2=hk)
-            P_img += list(P2.sum(-1).cpu().numpy().astype(np.float32))             # layerwise_ebp(..., mwp=True) maps
+        tab = eng.prior_table('rows')
+        Z = torch.zeros(min(rows_per_sweep, len(seeds)), self.net.num_classes(), device=dev)     # fixed row count: one graph
+        for i in range(0, len(seeds), Z.shape[0]):
+            chunk = seeds[i:i + Z.shape[0]]
+            tab.clear()
+            for r, (k, e, v) in enumerate(chunk):
+                tab.set_elem(k, r, e, v)
+            tab.upload()
+            P2 = eng.generic_call(Z, W2, mode=subtree_mode, hooked_fc2=hk, ptab=tab)['P2']
+            P_img += list(P2[:len(chunk)].sum(-1).cpu().numpy().astype(np.float32))             # layerwise_ebp(..., mwp=True) maps
         self.P_layername = list(names)
         if verbose:
             for k in k_subtree:
