@@ -555,10 +555,10 @@ def main():
         if world > 1 and gather:
             gather_maps(maps_dev, world * B, dst=0)          # the only collective on the data path (NCCL gather)
 
-    def step_e2e(steps=1):
+    def step_e2e(nsteps=1):
         # the public streaming call: every step copies its probes from pinned host memory (the copy of step i+1 overlaps the sweep
         # of step i on a copy stream) and its maps back to pinned host memory
-        wb.contrastive_ebp_stream([x_host] * steps, 0, 1, outs=[maps_host] * steps)
+        wb.contrastive_ebp_stream([x_host] * nsteps, 0, 1, outs=[maps_host] * nsteps)
         if world > 1:
             dist.barrier()
 
@@ -590,7 +590,7 @@ def main():
     bwd_ms = sum(a.elapsed_time(b) for a, b in bwd_events)
     for _ in range(2):
         step_e2e()
-    ms_e2e = timed(step_e2e, 1, steps=args.steps)
+    ms_e2e = timed(step_e2e, 1, nsteps=args.steps)
     clocks = sampler.summary()
     families = kernel_families(eng, step_resident, args.gemm) if rank == 0 else []      # after the timed regions: events around launches
 

@@ -232,7 +232,13 @@ int xfrb_twin_blends(const double* orig, const double* inp, const double* value,
  *   prior_entry (device pointer to ONE XfrbPriorEntry, or NULL): the prior of this firing read from device memory instead of the
  *   four prior arguments - a sweep captured into a CUDA graph is then replayed with other priors by rewriting the table, which is
  *   how the layer sweeps and weighted_subtree_ebp (whitebox.py:584-737) run without per-launch host work; with it, probe_out
- *   (device float, or NULL) receives p of element probe_elem of row probe_row (P_mate at the arg-max node, whitebox.py:699). */
+ *   (device float, or NULL) receives p of element probe_elem of row probe_row (P_mate at the arg-max node, whitebox.py:699).
+ *   chain: consecutive firings on the SAME [J,H,W,C] tensor can run as one launch - 1 appends this firing to the calling thread's
+ *   pending chain (nothing is launched), 2 appends it and launches the chain, 0 launches this firing alone; from the second link on
+ *   z_in / up / zc / z_in2 / k2 / c2 are ignored (the link takes its predecessor's return value from registers) and a NULL z_out
+ *   is simply not stored (at most XFRB_MAX_CHAIN = 6 links).  row_start ([J] device ints or NULL) with k = this firing's index
+ *   (those of the chain's first link count): gradient row j is skipped by every firing before row_start[j] and enters firing
+ *   row_start[j] with a zero gradient - the rows of a zero-seeded sweep whose priors sit at different firings. */
 typedef struct XfrbPriorEntry {
     int row;               /* gradient row that takes the prior at this firing, -1: none */
     int probe_row;         /* -1: no probe */
@@ -247,13 +253,15 @@ int xfrb_hook(const float* z_in, int up, int zc, const float* z_in2, int k2, int
               const float* s1, const float* s2, int c2s, const float* bn, const float* prior, int prior_row, long long prior_elem,
               float prior_val, float* P_out, float* z_out, int recipe, int affine, int relu_or_maxpool, int mode, int post_mask,
               int post_scale_row, int pre_scale_row, int J, int N, int H, int W, int C, float eps, const void* prior_entry,
-              float* probe_out, void* stream);
+              float* probe_out, int chain, const int* row_start, int k, void* stream);
 /* seed[j,:] = Pn[j,:] @ W2[j % N]  (Pn [J,Ccls], W2 [N,Ccls,D]) */
 int xfrb_head_seed(const float* Pn, const float* W2, int Ccls, int D, int J, int N, float* seed, void* stream);
 /* Jacobian of F.normalize (resnet.py:250): gout = (gin - xn*<xn,gin>)/nrm, rows of length D <= 1024 */
 int xfrb_normalize_bwd(const float* gin, const float* xn, const float* nrm, float* gout, int J, int N, int D, void* stream);
-/* MaxPool2d(3,2,pool_pad) backward alone: g [J,56,56,64] -> out [J,112,112,64]; arg-max recomputed from relu(bn(o)) */
-int xfrb_maxpool_bwd(const float* g, const float* o, const float* bn, float* out, int J, int N, int pool_pad, void* stream);
+/* MaxPool2d(3,2,pool_pad) backward alone: g [J,56,56,64] -> out [J,112,112,64]; arg-max from the bytes xfrb_stem_fwd recorded
+ * (mp_arg [N,56,56,64]) or, when mp_arg is NULL, recomputed from relu(bn(o)) */
+int xfrb_maxpool_bwd(const float* g, const float* o, const float* bn, float* out, const unsigned char* mp_arg, int J, int N, int pool_pad,
+                     void* stream);
 /* weighted_subtree_ebp layer score (whitebox.py:687-696): max / first argmax over n elements of m*(-gneg),
  * m = (gate >= 0) if gate_ge0 else (gate < 0) */
 int xfrb_subtree_score(const float* gate, const float* gneg, int gate_ge0, long long n, float* score, long long* arg, void* stream);

@@ -355,7 +355,7 @@ class EmulBackend(object):
         x, n = _rows(xn, J), _rows(nrm, J)
         gout.copy_((gin - x * (x * gin).sum(1, keepdim=True)) / n.unsqueeze(1))
 
-    def maxpool_bwd(self, g, o, bn, out, pool_pad=1):
+    def maxpool_bwd(self, g, o, bn, out, pool_pad=1, mp_arg=None):
         J = g.shape[0]
         r1 = relu(_rows(o, J) * bn[0] + bn[1]).permute(0, 3, 1, 2)
         _, idx = F.max_pool2d(r1, 3, 2, pool_pad, ceil_mode=(pool_pad == 0), return_indices=True)

@@ -15,6 +15,8 @@ AFFINE = ('Conv', 'Linear', 'AvgPool', 'BatchNorm')
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else 'layer_sweep'
     dev = torch.device('cuda:0')
+    if what == 'lightcnn':
+        return lightcnn(dev)
     sd = {k: v.to(dev) for k, v in synth.stresnet_state_dict(0).items()}
     net = whitebox.WhiteboxSTResnet(sd, impl='tf32x3')
     wb = whitebox.Whitebox(net, ebp_subtree_mode='affineonly_with_prior' if what == 'layer_sweep' else 'norelu')
@@ -75,6 +77,44 @@ def main():
     print('device time %.1f ms in %d kernels' % (total / 1e3, sum(v[0] for v in agg.values())))
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
         print('  %-70s %5d %9.1f us %5.1f %%' % (k, v[0], v[1], 100 * v[1] / total))
+
+
+def kernel_table(call):
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        call()
+        torch.cuda.synchronize()
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for e in prof.events():
+        if e.device_type == torch.autograd.DeviceType.CUDA:
+            a = agg[e.name[:70]]
+            a[0] += 1
+            a[1] += e.device_time
+    total = sum(v[1] for v in agg.values())
+    print('device time %.1f ms in %d kernels' % (total / 1e3, sum(v[0] for v in agg.values())))
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:16]:
+        print('  %-70s %5d %9.1f us %5.1f %%' % (k, v[0], v[1], 100 * v[1] / total))
+
+
+def lightcnn(dev):
+    sd = {k: v.to(dev) for k, v in synth.lightcnn_state_dict(0, 2).items()}
+    net = whitebox.WhiteboxLightCNN(sd, impl='tf32x3')
+    wb = whitebox.Whitebox(net, ebp_subtree_mode='affineonly')
+    B = 128
+    x = synth.lightcnn_probes(B, seed=3, smooth=False).to(dev)
+    W2 = torch.randn(B, 2, 256, generator=torch.Generator().manual_seed(4)).to(dev)
+    net.set_triplet_classifiers(W2[:, 0], W2[:, 1])
+    P = torch.zeros(1, 2)
+    P[0, 0] = 1
+    call = lambda: wb.ebp_batch(x, P)
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    call()
+    torch.cuda.synchronize()
+    print('lightcnn ebp, %d probes: %.1f ms per call' % (B, 1e3 * (time.perf_counter() - t0)))
+    kernel_table(call)
 
 
 if __name__ == '__main__':

@@ -19,7 +19,7 @@ cudaError_t launch_stem_fwd(const float*, const float*, const float*, const floa
 cudaError_t launch_bn_hook(const float*, const float*, const float*, const float*, float*, size_t, size_t, int, int, int, float,
                            cudaStream_t);
 cudaError_t launch_normalize_bwd(const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
-cudaError_t launch_maxpool_bwd(const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
+cudaError_t launch_maxpool_bwd(const float*, const float*, const float*, float*, const unsigned char*, int, int, int, cudaStream_t);
 cudaError_t launch_subtree_score(const float*, const float*, int, size_t, float*, long long*, cudaStream_t);
 cudaError_t launch_head_seed(const float*, const float*, int, int, int, int, float*, cudaStream_t);
 cudaError_t launch_subsample2(const float*, float*, int, int, int, int, cudaStream_t);
@@ -260,7 +260,10 @@ int xfrb_hook(const float* z_in, int up, int zc, const float* z_in2, int k2, int
               const float* s1, const float* s2, int c2s, const float* bn, const float* prior, int prior_row, long long prior_elem,
               float prior_val, float* P_out, float* z_out, int recipe, int affine, int relu_or_maxpool, int mode, int post_mask,
               int post_scale_row, int pre_scale_row, int J, int N, int H, int W, int C, float eps, const void* prior_entry,
-              float* probe_out, void* stream) {
+              float* probe_out, int chain, const int* row_start, int k, void* stream) {
+    static thread_local HookChain pending = {};      // links appended with chain = 1, launched by the call that passes chain = 2
+    if (chain == 0 && pending.n != 0) { pending.n = 0; return finish("xfrb_hook", cudaErrorInvalidValue); }   // an unfinished chain
+    if (chain < 0 || chain > 2 || pending.n >= XFRB_MAX_CHAIN) { pending.n = 0; return finish("xfrb_hook", cudaErrorInvalidValue); }
     if (up < 1 || k2 < 1 || recipe < 0 || recipe > 8 || ((post_scale_row >= 0 || pre_scale_row >= 0) && bn == nullptr))
         return finish("xfrb_hook", cudaErrorInvalidValue);
     HookArgs a;
@@ -272,7 +275,12 @@ int xfrb_hook(const float* z_in, int up, int zc, const float* z_in2, int k2, int
     a.pre_scale_row = pre_scale_row;
     a.ptab = static_cast<const PriorEntry*>(prior_entry); a.probe_out = probe_out;
     static_assert(sizeof(PriorEntry) == sizeof(XfrbPriorEntry), "include/xfrb.h XfrbPriorEntry mirrors PriorEntry");
-    return finish("xfrb_hook", launch_hook(a, (cudaStream_t)stream));
+    if (pending.n == 0) { pending.k0 = k; pending.row_start = row_start; }
+    pending.a[pending.n++] = a;
+    if (chain == 1) return 0;                        // deferred: nothing launched yet
+    HookChain ch = pending;
+    pending.n = 0;
+    return finish("xfrb_hook", launch_hook_chain(ch, (cudaStream_t)stream));
 }
 
 int xfrb_head_seed(const float* Pn, const float* W2, int Ccls, int D, int J, int N, float* seed, void* stream) {
@@ -284,8 +292,9 @@ int xfrb_normalize_bwd(const float* gin, const float* xn, const float* nrm, floa
     return finish("xfrb_normalize_bwd", launch_normalize_bwd(gin, xn, nrm, gout, J, N, D, (cudaStream_t)stream));
 }
 
-int xfrb_maxpool_bwd(const float* g, const float* o, const float* bn, float* out, int J, int N, int pool_pad, void* stream) {
-    return finish("xfrb_maxpool_bwd", launch_maxpool_bwd(g, o, bn, out, J, N, pool_pad, (cudaStream_t)stream));
+int xfrb_maxpool_bwd(const float* g, const float* o, const float* bn, float* out, const unsigned char* mp_arg, int J, int N, int pool_pad,
+                     void* stream) {
+    return finish("xfrb_maxpool_bwd", launch_maxpool_bwd(g, o, bn, out, mp_arg, J, N, pool_pad, (cudaStream_t)stream));
 }
 
 int xfrb_subtree_score(const float* gate, const float* gneg, int gate_ge0, long long n, float* score, long long* arg, void* stream) {

@@ -242,7 +242,15 @@ struct HookArgs {
     const PriorEntry* ptab;
     float* probe_out;                      // with ptab: p of element ptab->probe_elem of row ptab->probe_row is also written here
 };
+constexpr int XFRB_MAX_CHAIN = 6;
+struct HookChain {                         // consecutive firings on one [J,H,W,C] tensor fused into one launch (stages.cu hook_kernel)
+    HookArgs a[XFRB_MAX_CHAIN];
+    int n;
+    int k0;                                // firing index of link 0 (compared with row_start)
+    const int* row_start;                  // [J] or null: first firing each gradient row takes part in (zero-seeded prior sweeps)
+};
 cudaError_t launch_hook(const HookArgs& a, cudaStream_t st);
+cudaError_t launch_hook_chain(const HookChain& ch, cudaStream_t st);
 
 // arguments of the unfused block-boundary kernel (xfrb_join)
 struct JoinArgs {

@@ -351,6 +351,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch (conv_tc_pdl()): everything above - barrier set-up, TMEM allocation, tensor-map prefetch - may
+    // run while the previous kernel of the stream is still finishing on other SMs (a batch-1 sweep is ~230 kernels of a few tiles
+    // each); nothing below touches global memory before the previous kernel has completed and flushed.  No-ops in a normal launch.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // tile -> coordinates
     auto tile_coords = [&](int tile, int& m0, int& mvalid, int& n_img0, int& h0, int& ncol0) {
@@ -933,6 +938,12 @@ static bool encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t
     return r == CUDA_SUCCESS;
 }
 
+// XFRB_PDL=1: tcgen05 kernels are launched with programmatic stream serialization (see the griddepcontrol pair in the kernel)
+inline bool conv_tc_pdl() {
+    static const int on = [] { const char* e = getenv("XFRB_PDL"); return e ? atoi(e) : 0; }();
+    return on != 0;
+}
+
 template <int BN, int SPLIT, int KIND, int MODE = -1>
 static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo, const TcGeom& g,
                               const EpiParams& ep, cudaStream_t st) {
@@ -950,6 +961,20 @@ static cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, co
     const int sms = sms_of[slot];
     int total = g.n_m_tiles * g.n_n_tiles;
     int grid = total < sms ? total : sms;
+    if (conv_tc_pdl()) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(Cfg::THREADS);
+        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cfg.stream = st;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SPLIT, KIND, 0, MODE>, tmA, tmB, tmBlo, g, ep);
+    }
     conv_tc_kernel<BN, SPLIT, KIND, 0, MODE><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmBlo, g, ep);
     return cudaGetLastError();
 }
@@ -964,16 +989,18 @@ static cudaError_t launch_cfg2(const CUtensorMap& tmA, const CUtensorMap& tmB, c
     int& max_clusters = max_clusters_of[current_device_slot()];
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.blockDim = dim3(Cfg::THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = st;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = conv_tc_pdl() ? 2 : 1;
     if (max_clusters <= 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;

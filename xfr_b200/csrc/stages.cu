@@ -317,19 +317,34 @@ cudaError_t launch_head_bwd_b(const float* z, const float* v, float* g_out, int 
 
 // ------------------------------------------------------------------ unfused block boundary
 
-template <int MINB, int MODE>      // MODE >= 0: the hook mode as a compile-time constant (drops the BatchNorm constants it does not use)
-__global__ void __launch_bounds__(256, MINB) join_kernel(JoinArgs a, size_t total4) {
+// MODE >= 0: the hook mode as a compile-time constant (drops the BatchNorm constants it does not use).
+// FAST: `up`, `k` and C/4 are powers of two (every ResNet boundary: 1 or 2, 64 .. 512) - shifts and masks replace the runtime
+// integer divisions, a block handles a stretch of ONE image row (grid.x = row of the [N*H] sample rows, grid.y = stretch), and the
+// AvgPool backward's division by k*k is a multiplication by its exact reciprocal.  The form it replaces was issue-bound (ncu r2p:
+// 79 % issue-active at 3.1 TB/s, ~1,160 instructions per warp, about a third of them integer division); results are bit-identical.
+template <int MINB, int MODE, bool FAST>
+__global__ void __launch_bounds__(256, MINB) join_kernel(JoinArgs a, size_t total4, int c4_shift, int up_shift, int k_shift) {
     const int mode = MODE >= 0 ? MODE : a.mode;
     // one thread = 4 channels of one pixel of one SAMPLE; it walks the gradient-row groups (mate, non-mate, ...) of that sample so
     // that the saved tensors (out, o3, xr3, res) and the BatchNorm constants are read once, not once per group
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total4) return;
-    const unsigned C4 = a.C / 4;
-    const int c = (int)(i % C4) * 4;
-    unsigned p = i / C4;
-    const int w = p % (unsigned)a.W; p /= (unsigned)a.W;
-    const int h = p % (unsigned)a.H;
-    const int n = (int)(p / (unsigned)a.H);
+    int c, w, h, n;
+    if (FAST) {
+        const unsigned idx = blockIdx.y * blockDim.x + threadIdx.x;       // (w, c4) inside the image row
+        if (idx >= ((unsigned)a.W << c4_shift)) return;
+        c = (int)(idx & ((1u << c4_shift) - 1u)) * 4;
+        w = (int)(idx >> c4_shift);
+        n = (int)(blockIdx.x / (unsigned)a.H);                            // uniform per block
+        h = (int)(blockIdx.x - (unsigned)n * a.H);
+    } else {
+        const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= total4) return;
+        const unsigned C4 = a.C / 4;
+        c = (int)(i % C4) * 4;
+        unsigned p = i / C4;
+        w = p % (unsigned)a.W; p /= (unsigned)a.W;
+        h = p % (unsigned)a.H;
+        n = (int)(p / (unsigned)a.H);
+    }
     const size_t ms = ((size_t)n * a.H + h) * a.W + w;
     float4 uv = ld4(a.out + ms * a.C + c), ov = ld4(a.o3 + ms * a.C + c), xv = ld4(a.xr3 + ms * a.C + c);
     float u[4] = {uv.x, uv.y, uv.z, uv.w}, o[4] = {ov.x, ov.y, ov.z, ov.w}, x[4] = {xv.x, xv.y, xv.z, xv.w};
@@ -340,10 +355,14 @@ __global__ void __launch_bounds__(256, MINB) join_kernel(JoinArgs a, size_t tota
     }
     float4 al = ld4(a.bn3 + c), be = ld4(a.bn3 + a.C + c), sp = ld4(a.bn3 + 2 * a.C + c), tp = ld4(a.bn3 + 3 * a.C + c);
     BnC b[4] = {{al.x, be.x, sp.x, tp.x}, {al.y, be.y, sp.y, tp.y}, {al.z, be.z, sp.z, tp.z}, {al.w, be.w, sp.w, tp.w}};
-    const bool on_main = (h % a.up == 0 && w % a.up == 0);
+    const bool on_main = FAST ? (((h | w) & ((1 << up_shift) - 1)) == 0) : (h % a.up == 0 && w % a.up == 0);
     const bool on_res = (a.gres_lo != nullptr && c < a.gres_c);
-    const int Hm = a.H / a.up, Wm = a.W / a.up, Hr = a.H / a.k, Wr = a.W / a.k;
+    const int Hm = FAST ? a.H >> up_shift : a.H / a.up, Wm = FAST ? a.W >> up_shift : a.W / a.up;
+    const int Hr = FAST ? a.H >> k_shift : a.H / a.k, Wr = FAST ? a.W >> k_shift : a.W / a.k;
+    const int hm = FAST ? h >> up_shift : h / a.up, wm = FAST ? w >> up_shift : w / a.up;
+    const int hr = FAST ? h >> k_shift : h / a.k, wr = FAST ? w >> k_shift : w / a.k;
     const float kk = (float)(a.k * a.k);
+    const float rkk = 1.f / kk;                    // FAST: k*k is a power of two, x * (1/kk) == x / kk to the last bit
     // two gradient-row groups per trip: both groups' gradient loads are in flight before the first hook chain starts
     for (int j0 = n; j0 < a.J; j0 += 2 * a.N) {
         const int ng = (j0 + a.N < a.J) ? 2 : 1;
@@ -352,8 +371,8 @@ __global__ void __launch_bounds__(256, MINB) join_kernel(JoinArgs a, size_t tota
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             const int j = j0 + s * a.N;
-            if (s < ng && on_main) tm[s] = ld4(a.zmain + (((size_t)j * Hm + h / a.up) * Wm + w / a.up) * a.C + c);
-            if (s < ng && on_res) tr[s] = ld4(a.gres_lo + (((size_t)j * Hr + h / a.k) * Wr + w / a.k) * a.gres_c + c);
+            if (s < ng && on_main) tm[s] = ld4(a.zmain + (((size_t)j * Hm + hm) * Wm + wm) * a.C + c);
+            if (s < ng && on_res) tr[s] = ld4(a.gres_lo + (((size_t)j * Hr + hr) * Wr + wr) * a.gres_c + c);
         }
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
@@ -361,8 +380,13 @@ __global__ void __launch_bounds__(256, MINB) join_kernel(JoinArgs a, size_t tota
             const int j = j0 + s * a.N;
             if (on_main) { z[s][0] = tm[s].x; z[s][1] = tm[s].y; z[s][2] = tm[s].z; z[s][3] = tm[s].w; }
             if (on_res) {
-                z[s][0] = __fadd_rn(z[s][0], __fdiv_rn(tr[s].x, kk)); z[s][1] = __fadd_rn(z[s][1], __fdiv_rn(tr[s].y, kk));
-                z[s][2] = __fadd_rn(z[s][2], __fdiv_rn(tr[s].z, kk)); z[s][3] = __fadd_rn(z[s][3], __fdiv_rn(tr[s].w, kk));
+                if (FAST) {
+                    z[s][0] = __fadd_rn(z[s][0], __fmul_rn(tr[s].x, rkk)); z[s][1] = __fadd_rn(z[s][1], __fmul_rn(tr[s].y, rkk));
+                    z[s][2] = __fadd_rn(z[s][2], __fmul_rn(tr[s].z, rkk)); z[s][3] = __fadd_rn(z[s][3], __fmul_rn(tr[s].w, rkk));
+                } else {
+                    z[s][0] = __fadd_rn(z[s][0], __fdiv_rn(tr[s].x, kk)); z[s][1] = __fadd_rn(z[s][1], __fdiv_rn(tr[s].y, kk));
+                    z[s][2] = __fadd_rn(z[s][2], __fdiv_rn(tr[s].z, kk)); z[s][3] = __fadd_rn(z[s][3], __fdiv_rn(tr[s].w, kk));
+                }
             }
             float g[4], y3[4];
 #pragma unroll
@@ -432,13 +456,24 @@ cudaError_t launch_join(const JoinArgs& a, cudaStream_t st) {
     // bit-identical): per-row twin (46 registers) 2,024 us; per sample with a runtime hook mode: 104 registers (2 CTAs per SM) 2,393 us,
     // 80 (3) 1,846 us, 64 (4) 1,667 us; hook mode as a template constant (fewer BatchNorm constants live): 4 CTAs 1,416 us (default),
     // 5 CTAs 1,364 us, 6 CTAs (192 B spilled) 1,451 us
+    auto log2_of = [](int v) { int s = 0; while ((1 << s) < v) ++s; return (v > 0 && (1 << s) == v) ? s : -1; };
+    const int c4s = log2_of(a.C / 4), ups = log2_of(a.up), ks = log2_of(a.k);
+    const size_t rows = (size_t)a.N * a.H;
+    if (variant == 0 && c4s >= 0 && ups >= 0 && ks >= 0 && a.C % 4 == 0 && rows < 0x7FFFFFFFull) {
+        const dim3 grid((unsigned)rows, (unsigned)((((size_t)a.W << c4s) + 255) / 256));
+        if (a.mode == XFRB_MODE_AWP) join_kernel<4, XFRB_MODE_AWP, true><<<grid, 256, 0, st>>>(a, total4, c4s, ups, ks);
+        else if (a.mode == XFRB_MODE_ALL) join_kernel<4, XFRB_MODE_ALL, true><<<grid, 256, 0, st>>>(a, total4, c4s, ups, ks);
+        else if (a.mode == XFRB_MODE_AFFINEONLY) join_kernel<4, XFRB_MODE_AFFINEONLY, true><<<grid, 256, 0, st>>>(a, total4, c4s, ups, ks);
+        else return cudaErrorInvalidValue;
+        return cudaGetLastError();
+    }
     const unsigned grid = (unsigned)((total4 + 255) / 256);
-    if (variant == 2) join_kernel<4, -1><<<grid, 256, 0, st>>>(a, total4);                   // A/B probe: runtime hook mode
-    else if (variant == 5 && a.mode == XFRB_MODE_AWP) join_kernel<5, XFRB_MODE_AWP><<<grid, 256, 0, st>>>(a, total4);
-    else if (variant == 6 && a.mode == XFRB_MODE_AWP) join_kernel<6, XFRB_MODE_AWP><<<grid, 256, 0, st>>>(a, total4);
-    else if (a.mode == XFRB_MODE_AWP) join_kernel<4, XFRB_MODE_AWP><<<grid, 256, 0, st>>>(a, total4);
-    else if (a.mode == XFRB_MODE_ALL) join_kernel<4, XFRB_MODE_ALL><<<grid, 256, 0, st>>>(a, total4);
-    else if (a.mode == XFRB_MODE_AFFINEONLY) join_kernel<4, XFRB_MODE_AFFINEONLY><<<grid, 256, 0, st>>>(a, total4);
+    if (variant == 2) join_kernel<4, -1, false><<<grid, 256, 0, st>>>(a, total4, 0, 0, 0);                   // A/B probe: runtime hook mode
+    else if (variant == 5 && a.mode == XFRB_MODE_AWP) join_kernel<5, XFRB_MODE_AWP, false><<<grid, 256, 0, st>>>(a, total4, 0, 0, 0);
+    else if (variant == 6 && a.mode == XFRB_MODE_AWP) join_kernel<6, XFRB_MODE_AWP, false><<<grid, 256, 0, st>>>(a, total4, 0, 0, 0);
+    else if (a.mode == XFRB_MODE_AWP) join_kernel<4, XFRB_MODE_AWP, false><<<grid, 256, 0, st>>>(a, total4, 0, 0, 0);
+    else if (a.mode == XFRB_MODE_ALL) join_kernel<4, XFRB_MODE_ALL, false><<<grid, 256, 0, st>>>(a, total4, 0, 0, 0);
+    else if (a.mode == XFRB_MODE_AFFINEONLY) join_kernel<4, XFRB_MODE_AFFINEONLY, false><<<grid, 256, 0, st>>>(a, total4, 0, 0, 0);
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
@@ -522,6 +557,33 @@ __global__ void __launch_bounds__(256) stem_bwd_b_kernel(const float* __restrict
     // MaxPool2d(3, 2, pad) backward as a gather: pooled row ph covers input rows 2ph-pad..2ph-pad+2 (clipped: pad 1 for
     // the STR net, pad 0 + ceil_mode for VGGFace2); (h,w) receives the gradient of every window whose FIRST maximum
     // (row-major scan, as torch's CPU kernel) it is.
+    if (mp_arg != nullptr) {
+        // the forward pass recorded which position won each window: the (up to) four windows' arg-max bytes and gradients are
+        // loaded together, from clamped addresses, before any of them is used - the loop form below waited for each load in turn
+        // (ncu r2p: 7.9 warps stalled on the long scoreboard per issue, 1.9 TB/s).  Same additions in the same order.
+        uchar4 am[4];
+        float4 gz[4];
+        bool ok[4];
+        int me_idx[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int a = t >> 1, b2 = t & 1;
+            const int ph = (h + pad) / 2 - a, pw = (w + pad) / 2 - b2;
+            ok[t] = !(ph < 0 || ph >= 56 || 2 * ph - pad > h || h > 2 * ph - pad + 2) && !(pw < 0 || pw >= 56 || 2 * pw - pad > w || w > 2 * pw - pad + 2);
+            const int phc = ok[t] ? ph : 0, pwc = ok[t] ? pw : 0;
+            me_idx[t] = (h - (2 * phc - pad)) * 3 + (w - (2 * pwc - pad));
+            am[t] = __ldg(reinterpret_cast<const uchar4*>(mp_arg) + (((size_t)n * 56 + phc) * 56 + pwc) * 16 + (c >> 2));
+            gz[t] = ld4(zc + (((size_t)j * 56 + phc) * 56 + pwc) * 64 + c);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (!ok[t]) continue;
+            if (am[t].x == me_idx[t]) z[0] = __fadd_rn(z[0], gz[t].x);
+            if (am[t].y == me_idx[t]) z[1] = __fadd_rn(z[1], gz[t].y);
+            if (am[t].z == me_idx[t]) z[2] = __fadd_rn(z[2], gz[t].z);
+            if (am[t].w == me_idx[t]) z[3] = __fadd_rn(z[3], gz[t].w);
+        }
+    } else
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
         int ph = (h + pad) / 2 - a;
@@ -721,20 +783,36 @@ __device__ __forceinline__ float hook_fire(const HookArgs& A, const HookPrior& P
 }
 
 // VEC = 4: one thread = 4 consecutive channels of one (row, pixel) - every channel count involved is a multiple of 4 and every
-// tensor 16-byte aligned (launch_hook checks) - so each tensor moves as float4 and the index arithmetic is paid once per four
+// tensor 16-byte aligned (launch_hook_chain checks) - so each tensor moves as float4 and the index arithmetic is paid once per four
 // elements (the scalar form ran at 1.4 TB/s of its streams, issue-bound: profiles/r2_notes.md).  VEC = 1: any shape.
+//
+// CHAIN: ch.n consecutive firings on the same [J,H,W,C] tensor in one launch - link l + 1 takes link l's return value (after its post
+// ops) from registers instead of from memory; a link's z_out / P_out are stored only where they are non-null.  The sweeps of
+// generic.py / lightcnn.py fire 3 - 5 hooks in a row between two GEMMs (ReLU, Conv2d, Add, Add, BatchNorm2d on a block output):
+// as separate launches every one re-read and re-wrote the gradient tensor.
+//
+// Row skipping: with ch.row_start (zero-seeded prior sweeps) gradient row j is all zero until the firing that carries its prior,
+// row_start[j]: earlier firings load nothing for it and store zeros where a tensor is kept (the GEMMs in between may turn those
+// zeros into anything they like - rows never mix), and AT that firing the incoming gradient is taken as zero.
 template <int VEC>
-__global__ void __launch_bounds__(256) hook_kernel(HookArgs A, size_t total) {
+__global__ void __launch_bounds__(256) hook_kernel(HookChain ch, size_t total) {
+    const HookArgs& A0 = ch.a[0];
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;          // 32-bit index arithmetic (the launcher rejects totals >= 2^32)
     if (i >= total) return;
-    const unsigned Cv = (unsigned)A.C / VEC;
+    const unsigned Cv = (unsigned)A0.C / VEC;
     const int c = (int)(i % Cv) * VEC;
     unsigned p = i / Cv;
-    const int w = (int)(p % (unsigned)A.W); p /= (unsigned)A.W;
-    const int h = (int)(p % (unsigned)A.H);
-    const int j = (int)(p / (unsigned)A.H);
-    const int n = j % A.N;
-    const size_t ms = ((size_t)n * A.H + h) * A.W + w;
+    const int w = (int)(p % (unsigned)A0.W); p /= (unsigned)A0.W;
+    const int h = (int)(p % (unsigned)A0.H);
+    const int j = (int)(p / (unsigned)A0.H);
+    const int n = j % A0.N;
+    int first = 0;                                                       // first link this row takes part in
+    bool zero_in = false;
+    if (ch.row_start != nullptr) {
+        const int s0 = ch.row_start[j] - ch.k0;
+        if (s0 >= 0) { first = s0 < ch.n ? s0 : ch.n; zero_in = true; }
+    }
+    const size_t ms = ((size_t)n * A0.H + h) * A0.W + w;
     auto ldv = [&](const float* q, float* v) {
         if constexpr (VEC == 4) { const float4 t = *reinterpret_cast<const float4*>(q); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
         else v[0] = *q;
@@ -743,73 +821,104 @@ __global__ void __launch_bounds__(256) hook_kernel(HookArgs A, size_t total) {
         if constexpr (VEC == 4) *reinterpret_cast<float4*>(q) = make_float4(v[0], v[1], v[2], v[3]);
         else *q = v[0];
     };
-    float z[VEC], v0[VEC], v1[VEC], v2[VEC], t[VEC];
+    float z[VEC], t[VEC];
 #pragma unroll
-    for (int q = 0; q < VEC; ++q) z[q] = v0[q] = v1[q] = v2[q] = 0.f;
-    if (A.z_in != nullptr && h % A.up == 0 && w % A.up == 0) {
-        const int Hm = A.H / A.up, Wm = A.W / A.up;
-        ldv(A.z_in + (((size_t)j * Hm + h / A.up) * Wm + w / A.up) * A.zc + c, z);
+    for (int q = 0; q < VEC; ++q) z[q] = 0.f;
+    if (!zero_in) {                                                      // link 0's gather of the incoming gradient
+        if (A0.z_in != nullptr && h % A0.up == 0 && w % A0.up == 0) {
+            const int Hm = A0.H / A0.up, Wm = A0.W / A0.up;
+            ldv(A0.z_in + (((size_t)j * Hm + h / A0.up) * Wm + w / A0.up) * A0.zc + c, z);
+        }
+        if (A0.z_in2 != nullptr && c < A0.c2) {
+            const int Hr = A0.H / A0.k2, Wr = A0.W / A0.k2;
+            ldv(A0.z_in2 + (((size_t)j * Hr + h / A0.k2) * Wr + w / A0.k2) * A0.c2 + c, t);
+            const float kk = (float)(A0.k2 * A0.k2);
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) z[q] = __fadd_rn(z[q], __fdiv_rn(t[q], kk));
+        }
     }
-    if (A.z_in2 != nullptr && c < A.c2) {
-        const int Hr = A.H / A.k2, Wr = A.W / A.k2;
-        ldv(A.z_in2 + (((size_t)j * Hr + h / A.k2) * Wr + w / A.k2) * A.c2 + c, t);
-        const float kk = (float)(A.k2 * A.k2);
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) z[q] = __fadd_rn(z[q], __fdiv_rn(t[q], kk));
-    }
-#pragma unroll
-    for (int q = 0; q < VEC; ++q) z[q] = __fmul_rn(z[q], A.pre_scale);
-    if (A.pre_scale_row >= 0) {                                          // BatchNorm backward ahead of its hook
-        ldv(A.bn + A.pre_scale_row * A.C + c, t);
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) z[q] = __fmul_rn(z[q], t[q]);
-    }
-    BnC b[VEC];
-#pragma unroll
-    for (int q = 0; q < VEC; ++q) b[q] = {0.f, 0.f, 0.f, 0.f};
-    if (A.bn != nullptr) {
-        float al[VEC], be[VEC], sp[VEC], tp[VEC];
-        ldv(A.bn + c, al); ldv(A.bn + A.C + c, be); ldv(A.bn + 2 * A.C + c, sp); ldv(A.bn + 3 * A.C + c, tp);
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) b[q] = {al[q], be[q], sp[q], tp[q]};
-    }
-    const int rc = A.recipe;
-    if (A.s0 != nullptr && c < A.c0) ldv(A.s0 + ms * A.c0 + c, v0);
-    if (rc >= 3) ldv(A.s1 + ms * A.C + c, v1);                           // recipes 3 - 8 read s1 [N,H,W,C]
-    if ((rc == 4 || rc == 8) && A.s2 != nullptr && c < A.c2s) ldv(A.s2 + ms * A.c2s + c, v2);
-    if (rc == 6) ldv(A.s2 + ms * A.C + c, v2);
-    const HookPrior P = hook_prior(A);
-    const bool has_prior = (A.mode != XFRB_MODE_NONE) && (j == P.row);
-    const size_t e0 = ((size_t)h * A.W + w) * A.C + c;
-    float ret[VEC], pv[VEC];
-#pragma unroll
-    for (int q = 0; q < VEC; ++q) {
-        float a, x;
-        hook_ax(rc, v0[q], v1[q], v2[q], b[q], a, x);
-        ret[q] = hook_fire(A, P, has_prior, e0 + q, c + q, z[q], a, x, pv[q]);
-    }
+    const size_t e0 = ((size_t)h * A0.W + w) * A0.C + c;
     const size_t off = (size_t)i * VEC;
-    if (A.P_out != nullptr) stv(A.P_out + off, pv);
-    if (A.z_out != nullptr) stv(A.z_out + off, ret);
-    if (A.probe_out != nullptr && j == P.probe_row && P.probe_elem >= (long long)e0 && P.probe_elem < (long long)e0 + VEC)
-        *A.probe_out = pv[(int)(P.probe_elem - (long long)e0)];
+    // firings before the row's start: its gradient and p are zero there - the tensors that are kept (residual-path gradients are
+    // read again after the start) get their zeros, nothing is loaded
+    for (int l = 0; l < first; ++l) {
+        if (ch.a[l].P_out != nullptr) stv(ch.a[l].P_out + off, z);
+        if (ch.a[l].z_out != nullptr) stv(ch.a[l].z_out + off, z);
+    }
+    for (int l = first; l < ch.n; ++l) {
+        const HookArgs& A = ch.a[l];
+        if (!(zero_in && l == first)) {
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) z[q] = __fmul_rn(z[q], A.pre_scale);
+            if (A.pre_scale_row >= 0) {                                  // BatchNorm backward ahead of its hook
+                ldv(A.bn + A.pre_scale_row * A.C + c, t);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) z[q] = __fmul_rn(z[q], t[q]);
+            }
+        }
+        BnC b[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) b[q] = {0.f, 0.f, 0.f, 0.f};
+        if (A.bn != nullptr) {
+            float al[VEC], be[VEC], sp[VEC], tp[VEC];
+            ldv(A.bn + c, al); ldv(A.bn + A.C + c, be); ldv(A.bn + 2 * A.C + c, sp); ldv(A.bn + 3 * A.C + c, tp);
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) b[q] = {al[q], be[q], sp[q], tp[q]};
+        }
+        float v0[VEC], v1[VEC], v2[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) v0[q] = v1[q] = v2[q] = 0.f;
+        const int rc = A.recipe;
+        if (A.s0 != nullptr && c < A.c0) ldv(A.s0 + ms * A.c0 + c, v0);
+        if (rc >= 3) ldv(A.s1 + ms * A.C + c, v1);                       // recipes 3 - 8 read s1 [N,H,W,C]
+        if ((rc == 4 || rc == 8) && A.s2 != nullptr && c < A.c2s) ldv(A.s2 + ms * A.c2s + c, v2);
+        if (rc == 6) ldv(A.s2 + ms * A.C + c, v2);
+        const HookPrior P = hook_prior(A);
+        const bool has_prior = (A.mode != XFRB_MODE_NONE) && (j == P.row);
+        float pv[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+            float a, x;
+            hook_ax(rc, v0[q], v1[q], v2[q], b[q], a, x);
+            z[q] = hook_fire(A, P, has_prior, e0 + q, c + q, z[q], a, x, pv[q]);
+        }
+        if (A.P_out != nullptr) stv(A.P_out + off, pv);
+        if (A.z_out != nullptr) stv(A.z_out + off, z);
+        if (A.probe_out != nullptr && j == P.probe_row && P.probe_elem >= (long long)e0 && P.probe_elem < (long long)e0 + VEC)
+            *A.probe_out = pv[(int)(P.probe_elem - (long long)e0)];
+    }
 }
 
-cudaError_t launch_hook(const HookArgs& a, cudaStream_t st) {
-    size_t total = (size_t)a.J * a.H * a.W * a.C;
+cudaError_t launch_hook_chain(const HookChain& ch, cudaStream_t st) {
+    const HookArgs& a0 = ch.a[0];
+    if (ch.n < 1 || ch.n > XFRB_MAX_CHAIN) return cudaErrorInvalidValue;
+    size_t total = (size_t)a0.J * a0.H * a0.W * a0.C;
     if (total >= 0xFFFFFF00ull) return cudaErrorInvalidValue;          // the kernel indexes with 32-bit arithmetic
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    const bool vec = a.C % 4 == 0 && a.zc % 4 == 0 && (a.s0 == nullptr || a.c0 % 4 == 0) && (a.z_in2 == nullptr || a.c2 % 4 == 0) &&
-                     (a.s2 == nullptr || a.c2s % 4 == 0 || a.recipe == 6) && al16(a.z_in) && al16(a.z_in2) && al16(a.s0) && al16(a.s1) &&
-                     al16(a.s2) && al16(a.bn) && al16(a.P_out) && al16(a.z_out);
+    bool vec = a0.C % 4 == 0 && a0.zc % 4 == 0 && (a0.z_in2 == nullptr || a0.c2 % 4 == 0) && al16(a0.z_in) && al16(a0.z_in2);
+    for (int l = 0; l < ch.n; ++l) {
+        const HookArgs& a = ch.a[l];
+        if (a.J != a0.J || a.N != a0.N || a.H != a0.H || a.W != a0.W || a.C != a0.C) return cudaErrorInvalidValue;
+        vec = vec && (a.s0 == nullptr || a.c0 % 4 == 0) && (a.s2 == nullptr || a.c2s % 4 == 0 || a.recipe == 6) && al16(a.s0) && al16(a.s1) &&
+              al16(a.s2) && al16(a.bn) && al16(a.P_out) && al16(a.z_out);
+    }
     static const int force_scalar = [] { const char* e = getenv("XFRB_HOOK_SCALAR"); return e ? atoi(e) : 0; }();   // A/B probe
     if (vec && !force_scalar) {
         total /= 4;
-        hook_kernel<4><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, total);
+        hook_kernel<4><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ch, total);
     } else {
-        hook_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, total);
+        hook_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ch, total);
     }
     return cudaGetLastError();
+}
+
+cudaError_t launch_hook(const HookArgs& a, cudaStream_t st) {
+    HookChain ch;
+    ch.a[0] = a;
+    ch.n = 1;
+    ch.row_start = nullptr;
+    ch.k0 = 0;
+    return launch_hook_chain(ch, st);
 }
 
 // g = (g - xn*<xn,g>)/nrm per row: the Jacobian of F.normalize (resnet.py:250).  One block per row, D <= 1024.
@@ -871,42 +980,121 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ g, const float* __r
     }
     out[i] = z;
 }
-cudaError_t launch_maxpool_bwd(const float* g, const float* o, const float* bn, float* out, int J, int N, int pad, cudaStream_t st) {
+// the same gather from the window arg-max bytes the forward sweep recorded (stem_pool_kernel: 1 byte per pooled element, the
+// position 3*r + s of the first maximum): one thread = 4 channels, no window scans (the scan form: 845 us per 48-row launch)
+__global__ void __launch_bounds__(256) maxpool_bwd_arg_kernel(const float* __restrict__ g, const unsigned char* __restrict__ mp_arg,
+                                                              float* __restrict__ out, int N, int pad) {
+    // grid: (112*112*16/256, J)
+    const int j = blockIdx.y, n = j % N;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int c = (i & 15) * 4;
+    const int pix = i >> 4;
+    const int h = pix / 112, w = pix % 112;
+    uchar4 am[4];
+    float4 gz[4];
+    bool ok[4];
+    int me_idx[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int a = t >> 1, b2 = t & 1;
+        const int ph = (h + pad) / 2 - a, pw = (w + pad) / 2 - b2;
+        ok[t] = !(ph < 0 || ph >= 56 || 2 * ph - pad > h || h > 2 * ph - pad + 2) && !(pw < 0 || pw >= 56 || 2 * pw - pad > w || w > 2 * pw - pad + 2);
+        const int phc = ok[t] ? ph : 0, pwc = ok[t] ? pw : 0;
+        me_idx[t] = (h - (2 * phc - pad)) * 3 + (w - (2 * pwc - pad));
+        am[t] = __ldg(reinterpret_cast<const uchar4*>(mp_arg) + (((size_t)n * 56 + phc) * 56 + pwc) * 16 + (c >> 2));
+        gz[t] = ld4(g + (((size_t)j * 56 + phc) * 56 + pwc) * 64 + c);
+    }
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        if (!ok[t]) continue;
+        if (am[t].x == me_idx[t]) z[0] = __fadd_rn(z[0], gz[t].x);
+        if (am[t].y == me_idx[t]) z[1] = __fadd_rn(z[1], gz[t].y);
+        if (am[t].z == me_idx[t]) z[2] = __fadd_rn(z[2], gz[t].z);
+        if (am[t].w == me_idx[t]) z[3] = __fadd_rn(z[3], gz[t].w);
+    }
+    st4(out + ((size_t)j * 112 * 112 + pix) * 64 + c, make_float4(z[0], z[1], z[2], z[3]));
+}
+cudaError_t launch_maxpool_bwd(const float* g, const float* o, const float* bn, float* out, const unsigned char* mp_arg, int J, int N,
+                               int pad, cudaStream_t st) {
+    if (mp_arg != nullptr && J <= 65535) {
+        maxpool_bwd_arg_kernel<<<dim3(112 * 112 * 16 / 256, J), 256, 0, st>>>(g, mp_arg, out, N, pad);
+        return cudaGetLastError();
+    }
     size_t total = (size_t)J * 112 * 112 * 64;
     maxpool_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, o, bn, out, N, pad, total);
     return cudaGetLastError();
 }
 
+// Zero-initialised device scratch of the multi-block reductions below (one allocation per device, made on the first - eager - call:
+// cudaMalloc is not capturable; every user leaves it zeroed again, and the users of one device run on one stream).
+struct ReduceScratch {
+    unsigned long long key;            // subtree_score: running (value, ~index) maximum
+    unsigned int ticket;               // blocks of the current launch that have finished
+    unsigned int pad;
+};
+static void* device_scratch(int which, size_t bytes) {
+    static void* ptr[2][XFRB_MAX_DEV] = {};
+    void*& p = ptr[which][current_device_slot()];
+    if (p == nullptr) {
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { p = nullptr; return nullptr; }
+        cudaMemset(p, 0, bytes);
+    }
+    return p;
+}
+
 // per firing: score = max_e m(e) * (-gn[e]), arg = first argmax; m = (gm >= 0) (mated-similarity gating) or (gce < 0)
-// (whitebox.py:687-696).  One block per (firing, row); n elements.
-__global__ void __launch_bounds__(1024) subtree_score_kernel(const float* __restrict__ gate, const float* __restrict__ gneg, int gate_ge0,
-                                                             size_t n, float* __restrict__ score, long long* __restrict__ arg) {
-    __shared__ float sv[32];
-    __shared__ long long si[32];
-    float best = -INFINITY;
-    long long bi = 0x7fffffffffffffffLL;
-    for (size_t e = threadIdx.x; e < n; e += blockDim.x) {
-        const float m = gate_ge0 ? (gate[e] >= 0.f ? 1.f : 0.f) : (gate[e] < 0.f ? 1.f : 0.f);
-        const float v = __fmul_rn(m, -gneg[e]);
-        if (v > best || (v == best && (long long)e < bi)) { best = v; bi = (long long)e; }
+// (whitebox.py:687-696).  n elements, many blocks: every block folds its stretch into one 64-bit key - the value's bits made
+// monotonic in the high word, ~index in the low word, so that the largest key is the largest value at its FIRST position - and
+// atomicMax-es it into the scratch; the last block to finish decodes it.  (The one-block form took 91 us per firing on the
+// 56x56x256 tensors: 34 ms of a 243 ms weighted-subtree job, profiles/r2_notes.md.)
+__device__ __forceinline__ unsigned long long score_key(float v, unsigned int e) {
+    v = __fadd_rn(v, 0.f);                                              // -0 -> +0: the two compare equal, the first position wins
+    const unsigned int u = __float_as_uint(v);
+    const unsigned int ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)ord << 32) | (unsigned long long)(0xFFFFFFFFu - e);
+}
+__global__ void __launch_bounds__(256) subtree_score_kernel(const float* __restrict__ gate, const float* __restrict__ gneg, int gate_ge0,
+                                                            unsigned int n, float* __restrict__ score, long long* __restrict__ arg,
+                                                            ReduceScratch* __restrict__ sc) {
+    __shared__ unsigned long long sk[8];
+    unsigned long long best = 0ull;                                     // below every real key (ord >= 1 for any non-NaN value)
+    for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const float g = gate[e];
+        const float m = gate_ge0 ? (g >= 0.f ? 1.f : 0.f) : (g < 0.f ? 1.f : 0.f);
+        const unsigned long long k = score_key(__fmul_rn(m, -gneg[e]), e);
+        best = k > best ? k : best;
     }
     for (int o = 16; o > 0; o >>= 1) {
-        float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, best, o);
+        best = ok > best ? ok : best;
     }
-    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    if ((threadIdx.x & 31) == 0) sk[threadIdx.x >> 5] = best;
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int k = 1; k < (int)(blockDim.x >> 5); ++k)
-            if (sv[k] > best || (sv[k] == best && si[k] < bi)) { best = sv[k]; bi = si[k]; }
-        *score = best;
-        *arg = bi;
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) best = sk[k] > best ? sk[k] : best;
+        atomicMax(&sc->key, best);
+        __threadfence();
+        if (atomicAdd(&sc->ticket, 1u) == gridDim.x - 1) {              // last block: every key has been folded in
+            const unsigned long long k = atomicMax(&sc->key, 0ull);
+            const unsigned int ord = (unsigned int)(k >> 32);
+            const unsigned int u = (ord & 0x80000000u) ? (ord & 0x7FFFFFFFu) : ~ord;
+            *score = n ? __uint_as_float(u) : -INFINITY;
+            *arg = n ? (long long)(0xFFFFFFFFu - (unsigned int)(k & 0xFFFFFFFFull)) : 0x7fffffffffffffffLL;
+            sc->key = 0ull;
+            sc->ticket = 0u;
+            __threadfence();
+        }
     }
 }
 cudaError_t launch_subtree_score(const float* gate, const float* gneg, int gate_ge0, size_t n, float* score, long long* arg,
                                  cudaStream_t st) {
-    subtree_score_kernel<<<1, 1024, 0, st>>>(gate, gneg, gate_ge0, n, score, arg);
+    if (n >= 0xFFFFFFFFull) return cudaErrorInvalidValue;                // 32-bit positions in the key
+    ReduceScratch* sc = static_cast<ReduceScratch*>(device_scratch(0, sizeof(ReduceScratch)));
+    if (sc == nullptr) return cudaErrorMemoryAllocation;
+    unsigned grid = (unsigned)((n + 2047) / 2048);                       // >= 8 elements per thread
+    grid = grid < 1 ? 1 : (grid > 592 ? 592 : grid);
+    subtree_score_kernel<<<grid, 256, 0, st>>>(gate, gneg, gate_ge0, (unsigned int)n, score, arg, sc);
     return cudaGetLastError();
 }
 
@@ -960,44 +1148,160 @@ __global__ void __launch_bounds__(1024) trunc_threshold_kernel(const float* __re
     if (tid == 0) thr[n] = (pct <= 0.f) ? 0.f : __uint_as_float(s_prefix);
 }
 
+// Many blocks per sample (the layer sweeps call this with ONE sample per firing: one block took 296 us, a third of it thread 0
+// walking the 2,048 bins): one launch per radix level; every block histograms its stretch in shared memory, adds its non-empty
+// bins to the sample's global histogram, and the last block to finish (ticket) scans the bins in parallel, descends one level
+// and leaves histogram and ticket zeroed for the next launch.  State per sample: TruncState + 2,048 doubles of scratch.
+struct TruncState {
+    unsigned int prefix, ticket;
+    double below;
+};
+constexpr int TRUNC_MAX_SAMPLES = 1024;
+template <int LEVEL>
+__global__ void __launch_bounds__(1024) trunc_level_kernel(const float* __restrict__ P2, const double* __restrict__ sums, float pct,
+                                                           float* __restrict__ thr, size_t per_sample, TruncState* __restrict__ state,
+                                                           double* __restrict__ ghist_all) {
+    constexpr int SH = LEVEL == 0 ? 21 : (LEVEL == 1 ? 10 : 0);
+    constexpr int WIDTH = LEVEL == 2 ? 10 : 11;
+    constexpr int NB = 1 << WIDTH;
+    constexpr int HSH = SH + WIDTH;                     // bits above this level must equal the prefix
+    __shared__ double hist[2048];
+    __shared__ double wsum[32];
+    __shared__ int s_bin;
+    __shared__ bool s_last;
+    const int n = blockIdx.y, tid = threadIdx.x;
+    const float* p = P2 + (size_t)n * per_sample;
+    TruncState* stt = state + n;
+    double* ghist = ghist_all + (size_t)n * 2048;
+    for (int i = tid; i < NB; i += 1024) hist[i] = 0.0;
+    __syncthreads();
+    const unsigned int prefix = LEVEL == 0 ? 0u : stt->prefix;
+    for (size_t i = (size_t)blockIdx.x * 1024 + tid; i < per_sample / 4; i += (size_t)gridDim.x * 1024) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const unsigned int u = __float_as_uint(vv[e]);
+            if (vv[e] > 0.f && (LEVEL == 0 || (u >> HSH) == (prefix >> HSH))) atomicAdd(&hist[(u >> SH) & (NB - 1)], (double)vv[e]);
+        }
+    }
+    __syncthreads();
+    if (gridDim.x > 1) {
+        for (int i = tid; i < NB; i += 1024)
+            if (hist[i] != 0.0) atomicAdd(&ghist[i], hist[i]);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(&stt->ticket, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        for (int i = tid; i < NB; i += 1024) {
+            hist[i] = __ldcg(&ghist[i]);
+            ghist[i] = 0.0;                             // ready for the next level / the next call
+        }
+        __syncthreads();
+    }
+    // parallel form of: run = below; for b: if (run + hist[b] >= target) break; run += hist[b];   (thread t owns bins 2t, 2t + 1)
+    const double target = (double)(pct / 100.0f) * sums[n];
+    const double below = LEVEL == 0 ? 0.0 : stt->below;
+    const int b0 = 2 * tid, b1 = 2 * tid + 1;
+    const double h0 = b0 < NB ? hist[b0] : 0.0, h1 = b1 < NB ? hist[b1] : 0.0;
+    double inc = h0 + h1;
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((tid & 31) >= o) inc += t;
+    }
+    if ((tid & 31) == 31) wsum[tid >> 5] = inc;
+    if (tid == 0) s_bin = NB;
+    __syncthreads();
+    if (tid < 32) {
+        double w = wsum[tid];
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, w, o);
+            if (tid >= o) w += t;
+        }
+        wsum[tid] = w;                                   // inclusive over warps
+    }
+    __syncthreads();
+    const double excl0 = below + ((tid >> 5) ? wsum[(tid >> 5) - 1] : 0.0) + (inc - (h0 + h1));
+    const double excl1 = excl0 + h0;
+    if (b0 < NB && excl0 + h0 >= target) atomicMin(&s_bin, b0);
+    else if (b1 < NB && excl1 + h1 >= target) atomicMin(&s_bin, b1);
+    __syncthreads();
+    int b = s_bin;
+    const bool none = b == NB;                           // rounding: target marginally above the total - every bin is below
+    if (none) b = NB - 1;
+    if (b == b0 || b == b1) {
+        const unsigned int np = prefix | ((unsigned int)b << SH);
+        if (LEVEL == 2) {
+            thr[n] = (pct <= 0.f) ? 0.f : __uint_as_float(np);
+            stt->prefix = 0u;
+            stt->below = 0.0;
+        } else {
+            stt->prefix = np;
+            stt->below = (b == b0 ? excl0 : excl1) + (none ? (b == b0 ? h0 : h1) : 0.0);
+        }
+        stt->ticket = 0u;
+    }
+}
+
 cudaError_t launch_trunc_threshold(const float* P2, const double* sums, float pct, float* thr, int N, size_t per_sample,
                                    cudaStream_t st) {
     if (per_sample % 4) return cudaErrorInvalidValue;
-    trunc_threshold_kernel<<<N, 1024, 0, st>>>(P2, sums, pct, thr, per_sample);
+    static const int single = [] { const char* e = getenv("XFRB_TRUNC_SINGLE"); return e ? atoi(e) : 0; }();      // A/B probe: the one-block form
+    constexpr size_t BYTES = TRUNC_MAX_SAMPLES * (sizeof(TruncState) + 2048 * sizeof(double));
+    char* sc = (N <= TRUNC_MAX_SAMPLES && !single) ? static_cast<char*>(device_scratch(1, BYTES)) : nullptr;
+    if (sc == nullptr) {
+        trunc_threshold_kernel<<<N, 1024, 0, st>>>(P2, sums, pct, thr, per_sample);
+        return cudaGetLastError();
+    }
+    TruncState* state = reinterpret_cast<TruncState*>(sc + (size_t)TRUNC_MAX_SAMPLES * 2048 * sizeof(double));
+    double* ghist = reinterpret_cast<double*>(sc);
+    const size_t iters = (per_sample / 4 + 1023) / 1024;               // float4 trips of one block over the whole sample
+    int bps = (int)((iters + 3) / 4);                                   // >= 4 trips per block
+    const int cap = 296 / N > 1 ? 296 / N : 1;                          // about two blocks per SM over all samples
+    bps = bps < 1 ? 1 : (bps > cap ? cap : bps);
+    const dim3 grid((unsigned)bps, (unsigned)N);
+    trunc_level_kernel<0><<<grid, 1024, 0, st>>>(P2, sums, pct, thr, per_sample, state, ghist);
+    trunc_level_kernel<1><<<grid, 1024, 0, st>>>(P2, sums, pct, thr, per_sample, state, ghist);
+    trunc_level_kernel<2><<<grid, 1024, 0, st>>>(P2, sums, pct, thr, per_sample, state, ghist);
     return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ contrastive combine
 // out[n,pix] = sum_c relu(k*P2[n,pix,c]/S[n] - k*P2[N+n,pix,c]/S[N+n]),  k = (P2[n,pix,c] >= thr[n]) or 1    (whitebox.py:524-526, 556)
 __global__ void contrast_kernel(const float* __restrict__ P2, const double* __restrict__ sums, const float* __restrict__ thr,
-                                float* __restrict__ out, int N, int HW, int C4) {
-    // C4 lanes per pixel (C = 64 -> 16 lanes), C4 a power of two <= 32
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;         // 32-bit index arithmetic (N * HW * C4 < 2^31, checked by the launcher)
-    const unsigned total = (unsigned)N * HW * C4;
+                                float* __restrict__ out, int N, int HW, int c4_shift) {
+    // C/4 lanes per pixel (C = 64 -> 16 lanes), a power of two <= 32; grid.y = sample: no runtime integer division in the kernel
+    const int C4 = 1 << c4_shift;
+    const unsigned per = (unsigned)HW << c4_shift;                     // float4 groups per sample
+    const unsigned il = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned n = blockIdx.y;
     float s = 0.f;
-    const unsigned pixg = i / (unsigned)C4;
-    if (i < total) {
-        const unsigned n = pixg / (unsigned)HW;
-        float sm = (float)sums[n], sn = (float)sums[N + n];
-        float t = thr ? thr[n] : -1.f;
-        float4 a = reinterpret_cast<const float4*>(P2)[i];
-        float4 b = reinterpret_cast<const float4*>(P2)[i + (size_t)N * HW * C4];
+    if (il < per) {
+        const float sm = (float)sums[n], sn = (float)sums[N + n];
+        const float t = thr ? thr[n] : -1.f;
+        const size_t i = (size_t)n * per + il;
+        const float4 a = reinterpret_cast<const float4*>(P2)[i];
+        const float4 b = reinterpret_cast<const float4*>(P2)[i + (size_t)N * per];
         const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e)
             if (av[e] >= t) s += fmaxf(__fsub_rn(__fdiv_rn(av[e], sm), __fdiv_rn(bv[e], sn)), 0.f);
     }
     for (int o = C4 / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (i < total && (threadIdx.x % C4) == 0) out[pixg] = s;
+    if (il < per && (threadIdx.x & (C4 - 1)) == 0) out[(size_t)n * HW + (il >> c4_shift)] = s;
 }
 
 cudaError_t launch_contrast(const float* P2, const double* sums, const float* thr, float* out, int N, int HW, int C,
                             cudaStream_t st) {
     int C4 = C / 4;
-    if (C4 > 32 || (C4 & (C4 - 1))) return cudaErrorInvalidValue;
-    size_t total = (size_t)N * HW * C4;
-    if (2 * total >= 0x7FFFFF00ull) return cudaErrorInvalidValue;      // 32-bit index arithmetic in the kernel
-    contrast_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P2, sums, thr, out, N, HW, C4);
+    if (C4 > 32 || C4 < 1 || (C4 & (C4 - 1)) || N > 65535) return cudaErrorInvalidValue;
+    int sh = 0;
+    while ((1 << sh) < C4) ++sh;
+    const size_t per = (size_t)HW * C4;
+    if (per >= 0x7FFFFF00ull) return cudaErrorInvalidValue;      // 32-bit index arithmetic in the kernel
+    contrast_kernel<<<dim3((unsigned)((per + 255) / 256), (unsigned)N), 256, 0, st>>>(P2, sums, thr, out, N, HW, sh);
     return cudaGetLastError();
 }
 

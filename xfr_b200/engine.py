@@ -124,11 +124,12 @@ class _Engine(object):
         return t
 
     def generic_run(self, Pn, W2, mode='affineonly_with_prior', record=False, true_grad=False, hooked_fc2=False, ptab=None,
-                    gating=None, n_saved=None):
+                    gating=None, n_saved=None, zero_seed=None):
         """One firing-by-firing sweep (generic.GenericSweep.run and its twins) as an operator graph_call can capture: the layer
         sweeps and weighted_subtree_ebp repeat the same ~500 launches with nothing but the device-resident priors (ptab)
         changing.  gating (None | bool): also score every firing of a 3-row true-gradient sweep (whitebox.py:684-696, rows =
-        cross-entropy / mate / non-mate; True: do_mated_similarity_gating).  n_saved only keys the graph table.
+        cross-entropy / mate / non-mate; True: do_mated_similarity_gating).  n_saved / zero_seed only key the graph table (a
+        captured sweep holds the table's row-start pointer or none).
         -> {'gs': the sweep object (layout of the recorded tensors), 'P', 'names', 'P2'[, 'score', 'arg']}"""
         gs = self.sweep()
         P, names, P2 = gs.run(Pn, W2, mode, record=record, true_grad=true_grad, hooked_fc2=hooked_fc2, ptab=ptab)
@@ -145,6 +146,8 @@ class _Engine(object):
 
     def generic_call(self, Pn, W2, **opts):
         """generic_run through the graph table (CUDA backend) or directly (emulation backend, row counts above graph_generic_rows)"""
+        if opts.get('ptab') is not None:
+            opts['zero_seed'] = opts['ptab'].zero_seed
         return self.graph_call('generic_run', (Pn.contiguous(), W2), max_n=self.graph_generic_rows, n_saved=self.saved['N'], **opts)
 
     def workspace_bytes(self):

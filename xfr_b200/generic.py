@@ -29,6 +29,11 @@ class PriorRef(object):
         self.entry_ptr, self.probe_ptr = entry_ptr, probe_ptr
 
 
+MAX_ROWS = 64          # gradient rows a PriorTable describes (engine.graph_generic_rows)
+NEVER = 2 ** 31 - 1
+MAX_CHAIN = 6          # XFRB_MAX_CHAIN (csrc/common.cuh)
+
+
 class PriorTable(object):
     """The priors of ONE sweep as device data (entry k = hook firing k) instead of launch arguments, so that a sweep captured
     into a CUDA graph is replayed with other priors by rewriting this table: the layer sweeps and weighted_subtree_ebp
@@ -46,14 +51,22 @@ class PriorTable(object):
         if self.device.type == 'cuda':
             self._stage = self._stage.pin_memory()
         self._keep = {}
+        # zero-seeded sweeps (every gradient row starts from a zero class prior and comes to life at the firing that carries its
+        # prior): start[j] = that firing; the hook kernels skip row j before it and take its incoming gradient as zero there
+        self.zero_seed = False
+        self.start = torch.full((MAX_ROWS,), NEVER, dtype=torch.int32, device=self.device)
+        self._start_stage = torch.full((MAX_ROWS,), NEVER, dtype=torch.int32)
+        if self.device.type == 'cuda':
+            self._start_stage = self._start_stage.pin_memory()
         self.clear()
 
-    def clear(self):
+    def clear(self, zero_seed=False):
         self.host[:] = 0
         self.host['row'] = -1
         self.host['probe_row'] = -1
         self.host['probe_elem'] = -1
         self._keep.clear()
+        self.zero_seed = bool(zero_seed)
 
     def set_elem(self, k, row, elem, val):
         e = self.host[k]
@@ -72,6 +85,17 @@ class PriorTable(object):
     def upload(self):
         self._stage.copy_(torch.from_numpy(self.host.view(np.uint8)))
         self.dev.copy_(self._stage, non_blocking=True)
+        if self.zero_seed:
+            st = np.full(MAX_ROWS, NEVER, dtype=np.int32)
+            ks = np.nonzero(self.host['row'] >= 0)[0]
+            rows = self.host['row'][ks]
+            assert rows.max(initial=0) < MAX_ROWS and len(set(rows.tolist())) == len(rows), 'one prior per gradient row'
+            st[rows] = ks
+            self._start_stage.copy_(torch.from_numpy(st))
+            self.start.copy_(self._start_stage, non_blocking=True)
+
+    def start_ptr(self):
+        return self.start.data_ptr() if self.zero_seed else None
 
     def ref(self, k):
         return PriorRef(self.dev.data_ptr() + PRIOR_DTYPE.itemsize * k, self.probe.data_ptr() + 4 * k)
@@ -86,9 +110,32 @@ class PriorTable(object):
         return (int(e['row']), int(e['elem']), float(e['val']))
 
 
+class _FlushBE(object):
+    """The backend as the sweeps see it: any call other than hook() first launches the pending chain of firings."""
+
+    def __init__(self, sweep):
+        self._sweep, self._be = sweep, sweep.be
+
+    def __getattr__(self, name):
+        attr = getattr(self._be, name)
+        if not callable(attr) or name == 'hook':
+            return attr
+        sweep = self._sweep
+
+        def call(*a, **kw):
+            sweep._flush()
+            return attr(*a, **kw)
+        return call
+
+
 class _PriorMixin(object):
-    """Where a firing's prior comes from: the {k: prior} dict of run(priors=...) or the PriorTable of run(ptab=...)."""
+    """Where a firing's prior comes from - the {k: prior} dict of run(priors=...) or the PriorTable of run(ptab=...) - and how
+    firings reach the backend: on the CUDA backend consecutive firings on the same tensor are queued and launched as ONE
+    xfrb_hook chain (link l + 1 takes link l's return value from registers; an intermediate the sweep marked keep=False is
+    never written), everything else - the emulation backend, firings with launch-argument priors - goes out one by one."""
     _ptab = None
+    _pending = None
+    chain_hooks = True
 
     def _prior_of(self, k):
         """-> (prior argument of backend.hook, probe (row, elem) to resolve on the host or None)"""
@@ -101,13 +148,41 @@ class _PriorMixin(object):
         e = t.host[k]
         return t.legacy(k), ((int(e['probe_row']), int(e['probe_elem'])) if e['probe_row'] >= 0 else None)
 
-    def _hook(self, k, z_in, z_out, shape, recipe, affine, P_out=None, **kw):
+    def _hook(self, k, z_in, z_out, shape, recipe, affine, P_out=None, keep=True, **kw):
         prior, probe = self._prior_of(k)
-        if probe is not None and P_out is None:                  # host-resolved probe (emulation backend): needs p itself
-            P_out = torch.empty(shape, dtype=torch.float32, device=self.eng.device)
-        self.be.hook(z_in, z_out, shape, recipe, affine, self._m, prior=prior, P_out=P_out, **kw)
-        if probe is not None:
-            self._ptab.probe[k] = P_out[probe[0]].reshape(-1)[probe[1]]
+        if getattr(self.be, 'name', '') != 'cuda':
+            if probe is not None and P_out is None:              # host-resolved probe (emulation backend): needs p itself
+                P_out = torch.empty(shape, dtype=torch.float32, device=self.eng.device)
+            self.be.hook(z_in, z_out, shape, recipe, affine, self._m, prior=prior, P_out=P_out, **kw)
+            if probe is not None:
+                self._ptab.probe[k] = P_out[probe[0]].reshape(-1)[probe[1]]
+            return
+        if self._pending is None:
+            self._pending = []
+        pend = self._pending
+        legacy = prior is not None and not hasattr(prior, 'entry_ptr')       # a launch-argument prior: never chained
+        C = shape[-1]
+        vec = C % 4 == 0 and all(t is None or t.shape[-1] % 4 == 0 for t in (kw.get('s0'), kw.get('s2')))
+        ok = (self.chain_hooks and pend and not legacy and vec and len(pend) < MAX_CHAIN and z_in is not None
+              and pend[-1]['z_out'] is not None and pend[-1]['z_out'].data_ptr() == z_in.data_ptr()
+              and tuple(pend[-1]['shape']) == tuple(shape) and kw.get('up', 1) == 1 and kw.get('z_in2') is None
+              and kw.get('zc') in (None, C) and pend[-1]['chainable'])
+        if not ok:
+            self._flush()
+        pend.append(dict(k=k, z_in=z_in, z_out=z_out, shape=shape, recipe=recipe, affine=affine, prior=prior, P_out=P_out,
+                         keep=keep, kw=kw, chainable=vec and not legacy))
+
+    def _flush(self):
+        pend = self._pending
+        if not pend:
+            return
+        rs = self._ptab.start_ptr() if self._ptab is not None else None
+        n = len(pend)
+        for i, L in enumerate(pend):
+            last = i == n - 1
+            self.be.hook(L['z_in'], L['z_out'] if (last or L['keep']) else None, L['shape'], L['recipe'], L['affine'], self._m,
+                         prior=L['prior'], P_out=L['P_out'], chain=0 if n == 1 else (2 if last else 1), row_start=rs, k=L['k'], **L['kw'])
+        del pend[:]
 
 
 class _FC(object):
@@ -147,7 +222,7 @@ class GenericSweep(_PriorMixin):
         device tensors, NHWC; entry -1, the Conv2d hook on the image, is None: nothing reads it);
         true_grad: no hooks, signed weights, true BatchNorm backward; the recorded tensors are then the gradients dA.
         Returns (P list or None, names, P2 [J,112,112,64] = P[-2])."""
-        eng, be, S = self.eng, self.be, self.eng.saved
+        eng, be, S = self.eng, _FlushBE(self), self.eng.saved
         N, J = S['N'], Pn.shape[0]
         self._k = 0
         self._P = [] if record else None
@@ -198,52 +273,54 @@ class GenericSweep(_PriorMixin):
             shp = (J, h, h, C)
             nxt = eng.blocks[i + 1] if i + 1 < nb else None
             res = t['res']
-            z = self.fire('ReLU', 4, zin, shp, s0=t['out'], s1=t['o3'], s2=res, bn=b.c3.bn, up=zin_up, z_in2=zin2, k2=k2, out='gs_a')
+            z = self.fire('ReLU', 4, zin, shp, s0=t['out'], s1=t['o3'], s2=res, bn=b.c3.bn, up=zin_up, z_in2=zin2, k2=k2, out='gs_a', keep=False)
             if nxt is None:
                 z = self.fire('AvgPool2d', 0, z, shp, s0=t['out'], post_mask=True, out='gs_g%d' % (i % 2))
             else:
-                z = self.fire('Conv2d', 0, z, shp, s0=t['out'], out='gs_b')
+                z = self.fire('Conv2d', 0, z, shp, s0=t['out'], out='gs_b', keep=False)
                 z = self.fire('AvgPool2d' if nxt.has_ds else 'Add', 0, z, shp, s0=t['out'], post_mask=True, out='gs_g%d' % (i % 2))
             g = z                                                            # gradient at the block output after ReLU backward
             gres, gres_k = g, 1
             if b.has_ds:
                 Cr = b.cin
-                zr = self.fire('Add', 0, g, shp, s0=res, out='gs_r1')            # slot 1 (residual) fires first
+                zr = self.fire('Add', 0, g, shp, s0=res, out='gs_r1', keep=False)   # slot 1 (residual) fires first
                 gres = self.fire('ConcatChannels', 0, zr, (J, h, h, Cr), s0=t['ap'], zc=C, out='gs_r2')
                 gres_k = b.stride
-            z = self.fire('Add', 0, g, shp, s0=res, post_scale_row=srow, bn=b.c3.bn, out='gs_a')   # slot 0: residual's (A, X)
+            z = self.fire('Add', 0, g, shp, s0=res, post_scale_row=srow, bn=b.c3.bn, out='gs_a', keep=False)   # slot 0: residual's (A, X)
             y3 = self.fire('BatchNorm2d', 3, z, shp, s0=t['o3'], s1=t['xr3'], out='gs_y3')
             z = dgrad(y3, b.c3, buf('gs_z2', J, h, h, b.planes))
             shp2 = (J, h, h, b.planes)
-            z = self.fire('ReLU', 1, z, shp2, s0=t['o2'], bn=b.c2.bn, out='gs_c')
-            z = self.fire('Conv2d', 2, z, shp2, s0=t['o2'], bn=b.c2.bn, post_mask=True, post_scale_row=srow, out='gs_d')
+            z = self.fire('ReLU', 1, z, shp2, s0=t['o2'], bn=b.c2.bn, out='gs_c', keep=False)
+            z = self.fire('Conv2d', 2, z, shp2, s0=t['o2'], bn=b.c2.bn, post_mask=True, post_scale_row=srow, out='gs_d', keep=False)
             y2 = self.fire('BatchNorm2d', 3, z, shp2, s0=t['o2'], s1=t['xr2'], out='gs_y2')
             z = dgrad(y2, b.c2, buf('gs_z1', J, h, h, b.planes))
-            z = self.fire('ReLU', 1, z, shp2, s0=t['o1'], bn=b.c1.bn, out='gs_c')
-            z = self.fire('Conv2d', 2, z, shp2, s0=t['o1'], bn=b.c1.bn, post_mask=True, post_scale_row=srow, out='gs_d')
+            z = self.fire('ReLU', 1, z, shp2, s0=t['o1'], bn=b.c1.bn, out='gs_c', keep=False)
+            z = self.fire('Conv2d', 2, z, shp2, s0=t['o1'], bn=b.c1.bn, post_mask=True, post_scale_row=srow, out='gs_d', keep=False)
             y1 = self.fire('BatchNorm2d', 3, z, shp2, s0=t['o1'], s1=t['xr1'], out='gs_y1')
             zlo = dgrad(y1, b.c1, buf('gs_zlo', J, h, h, b.cin))
             # the sum g_main + g_res is taken by the next firing: z_in (stride-2 scatter) + z_in2 (AvgPool backward)
             zin, zin_up, zin2, k2 = zlo, b.stride, gres, gres_k
         # ---- stem
         shp = (J, 56, 56, 64)
-        z = self.fire('Conv2d', 0, zin, shp, s0=S['mp'], up=zin_up, z_in2=zin2, k2=k2, out='gs_a')     # layer1.0.conv1
+        z = self.fire('Conv2d', 0, zin, shp, s0=S['mp'], up=zin_up, z_in2=zin2, k2=k2, out='gs_a', keep=False)     # layer1.0.conv1
         z = self.fire('AvgPool2d', 0, z, shp, s0=S['mp'], out='gs_b')                                   # layer1.0 shortcut (k = 1)
         zz = buf('gs_mp', J, 112, 112, 64)
-        be.maxpool_bwd(z, S['o_s'], eng.stem.bn, zz, eng.stem.pool_pad)
+        be.maxpool_bwd(z, S['o_s'], eng.stem.bn, zz, eng.stem.pool_pad, mp_arg=S.get('mp_arg'))
         shp = (J, 112, 112, 64)
-        z = self.fire('ReLU', 1, zz, shp, s0=S['o_s'], bn=eng.stem.bn, out='gs_s1')
-        z = self.fire('MaxPool2d', 2, z, shp, s0=S['o_s'], bn=eng.stem.bn, post_mask=True, post_scale_row=srow, out='gs_s2')
+        z = self.fire('ReLU', 1, zz, shp, s0=S['o_s'], bn=eng.stem.bn, out='gs_s1', keep=False)
+        z = self.fire('MaxPool2d', 2, z, shp, s0=S['o_s'], bn=eng.stem.bn, post_mask=True, post_scale_row=srow, out='gs_s2', keep=False)
         P2 = buf('gs_P2', *shp)
         self.fire('BatchNorm2d', 3, z, shp, s0=S['o_s'], s1=S['o_s'], out=None, P_force=P2)   # X only shapes the unused return
         if self._P is not None:
             self._P.append(None)                            # Conv2d hook on the image: never read by any output
         self._names.append('Conv2d')
+        self._flush()
         return self._P, self._names, P2
 
     # -------------------------------------------------------------------------------------------------
-    def fire(self, kind, recipe, z_in, shape, out, P_force=None, **kw):
-        """Firing number self._k of the sweep."""
+    def fire(self, kind, recipe, z_in, shape, out, P_force=None, keep=True, **kw):
+        """Firing number self._k of the sweep.  keep=False: the return value is read by the NEXT firing only (a chained launch
+        then never stores it)."""
         k = self._k
         self._k += 1
         self._names.append(kind)
@@ -255,7 +332,7 @@ class GenericSweep(_PriorMixin):
             self._P.append(P_out)
         z_out = self.eng.buf(out, *shape) if out is not None else None
         flag = 2 if (self._norelu and ('MaxPool' in kind or 'ReLU' in kind)) else 0
-        self._hook(k, z_in, z_out, shape, recipe, affine, P_out=P_out, relu_or_maxpool=flag, N=self.eng.saved['N'], **kw)
+        self._hook(k, z_in, z_out, shape, recipe, affine, P_out=P_out, keep=keep, relu_or_maxpool=flag, N=self.eng.saved['N'], **kw)
         return z_out
 
 
@@ -267,7 +344,7 @@ class R50Sweep(GenericSweep):
 
     def run(self, Pn, W2, mode, priors=None, record=False, true_grad=False, hooked_fc2=False, ptab=None):
         assert not hooked_fc2, 'the VGGFace2 plugin has no hooked classifier (whitebox.py:216)'
-        eng, be, S = self.eng, self.be, self.eng.saved
+        eng, be, S = self.eng, _FlushBE(self), self.eng.saved
         N, J = S['N'], Pn.shape[0]
         self._k = 0
         self._P = [] if record else None
@@ -301,11 +378,11 @@ class R50Sweep(GenericSweep):
             xres = eng._xres(i, MODE_IDS['all']) if need_x else t['u']      # positive-pass shortcut (only X of the ReLU hook reads it)
             if b.proj and not need_x:
                 xres = None
-            z = self.fire('ReLU', 8, zin, shp, s0=t['out'], s1=t['o3'], s2=xres, bn=b.c3.bn, up=zin_up, z_in2=zin2, k2=k2, out='gs_a')
+            z = self.fire('ReLU', 8, zin, shp, s0=t['out'], s1=t['o3'], s2=xres, bn=b.c3.bn, up=zin_up, z_in2=zin2, k2=k2, out='gs_a', keep=False)
             if nxt is None:
                 g = self.fire('AvgPool2d', 0, z, shp, s0=t['out'], post_mask=True, out='gs_g%d' % (i % 2))
             elif nxt.proj:
-                z = self.fire('Conv2d', 0, z, shp, s0=t['out'], out='gs_b')
+                z = self.fire('Conv2d', 0, z, shp, s0=t['out'], out='gs_b', keep=False)
                 g = self.fire('Conv2d', 0, z, shp, s0=t['out'], post_mask=True, out='gs_g%d' % (i % 2))
             else:
                 g = self.fire('Conv2d', 0, z, shp, s0=t['out'], post_mask=True, out='gs_g%d' % (i % 2))
@@ -316,12 +393,12 @@ class R50Sweep(GenericSweep):
             y3 = self.fire('BatchNorm2d', 3, g, shp, s0=t['o3'], s1=t['xr3'], bn=b.c3.bn, pre_scale_row=srow, out='gs_y3')
             z = dgrad(y3, b.c3, buf('gs_z2', J, h, h, b.planes))
             shp2 = (J, h, h, b.planes)
-            z = self.fire('ReLU', 1, z, shp2, s0=t['o2'], bn=b.c2.bn, out='gs_c')
-            z = self.fire('Conv2d', 2, z, shp2, s0=t['o2'], bn=b.c2.bn, post_mask=True, post_scale_row=srow, out='gs_d')
+            z = self.fire('ReLU', 1, z, shp2, s0=t['o2'], bn=b.c2.bn, out='gs_c', keep=False)
+            z = self.fire('Conv2d', 2, z, shp2, s0=t['o2'], bn=b.c2.bn, post_mask=True, post_scale_row=srow, out='gs_d', keep=False)
             y2 = self.fire('BatchNorm2d', 3, z, shp2, s0=t['o2'], s1=t['xr2'], out='gs_y2')
             z = dgrad(y2, b.c2, buf('gs_z1', J, h, h, b.planes))
-            z = self.fire('ReLU', 1, z, shp2, s0=t['o1'], bn=b.c1.bn, out='gs_c')
-            z = self.fire('Conv2d', 2, z, shp2, s0=t['o1'], bn=b.c1.bn, post_mask=True, post_scale_row=srow, out='gs_d')
+            z = self.fire('ReLU', 1, z, shp2, s0=t['o1'], bn=b.c1.bn, out='gs_c', keep=False)
+            z = self.fire('Conv2d', 2, z, shp2, s0=t['o1'], bn=b.c1.bn, post_mask=True, post_scale_row=srow, out='gs_d', keep=False)
             y1 = self.fire('BatchNorm2d', 3, z, shp2, s0=t['o1'], s1=t['xr1'], out='gs_y1')
             dgrad(y1, b.c1, zlo, accumulate=b.proj)
             if b.proj:
@@ -330,16 +407,17 @@ class R50Sweep(GenericSweep):
                 zin, zin_up, zin2, k2 = zlo, 1, g, 1                    # identity shortcut: the block-output gradient itself
         # ---- stem: conv2_1's reduce and proj Conv2d hooks on the max-pool output, then as the STR net (pool pad 0, ceil)
         shp = (J, 56, 56, 64)
-        z = self.fire('Conv2d', 0, zin, shp, s0=S['mp'], up=zin_up, z_in2=zin2, k2=k2, out='gs_a')
+        z = self.fire('Conv2d', 0, zin, shp, s0=S['mp'], up=zin_up, z_in2=zin2, k2=k2, out='gs_a', keep=False)
         z = self.fire('Conv2d', 0, z, shp, s0=S['mp'], out='gs_b')
         zz = buf('gs_mp', J, 112, 112, 64)
-        be.maxpool_bwd(z, S['o_s'], eng.stem.bn, zz, eng.stem.pool_pad)
+        be.maxpool_bwd(z, S['o_s'], eng.stem.bn, zz, eng.stem.pool_pad, mp_arg=S.get('mp_arg'))
         shp = (J, 112, 112, 64)
-        z = self.fire('ReLU', 1, zz, shp, s0=S['o_s'], bn=eng.stem.bn, out='gs_s1')
-        z = self.fire('MaxPool2d', 2, z, shp, s0=S['o_s'], bn=eng.stem.bn, post_mask=True, post_scale_row=srow, out='gs_s2')
+        z = self.fire('ReLU', 1, zz, shp, s0=S['o_s'], bn=eng.stem.bn, out='gs_s1', keep=False)
+        z = self.fire('MaxPool2d', 2, z, shp, s0=S['o_s'], bn=eng.stem.bn, post_mask=True, post_scale_row=srow, out='gs_s2', keep=False)
         P2 = buf('gs_P2', *shp)
         self.fire('BatchNorm2d', 3, z, shp, s0=S['o_s'], s1=S['o_s'], out=None, P_force=P2)
         if self._P is not None:
             self._P.append(None)
         self._names.append('Conv2d')
+        self._flush()
         return self._P, self._names, P2

@@ -48,10 +48,10 @@ _SIGNATURES = {
     'xfrb_stem_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
     'xfrb_bn_hook': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     'xfrb_hook': [_P, _I, _I, _P, _I, _I, _F, _P, _I, _P, _P, _I, _P, _P, _I, ctypes.c_longlong, _F, _P, _P, _I, _I, _I, _I, _I,
-                  _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P],
+                  _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _I, _P, _I, _P],
     'xfrb_head_seed': [_P, _P, _I, _I, _I, _I, _P, _P],
     'xfrb_normalize_bwd': [_P, _P, _P, _P, _I, _I, _I, _P],
-    'xfrb_maxpool_bwd': [_P, _P, _P, _P, _I, _I, _I, _P],
+    'xfrb_maxpool_bwd': [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     'xfrb_subtree_score': [_P, _P, _I, ctypes.c_longlong, _P, _P, _P],
     'xfrb_head_fwd_linear': [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     'xfrb_head_bwd_linear': [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
@@ -259,9 +259,10 @@ class CudaBackend(object):
     # -------------------------------------------------------------- generic single-hook path
     def hook(self, z_in, z_out, shape, recipe, affine, mode, s0=None, s1=None, s2=None, bn=None, up=1, zc=None, z_in2=None, k2=1,
              pre_scale=1.0, prior=None, P_out=None, relu_or_maxpool=0, post_mask=False, post_scale_row=-1, N=None,
-             pre_scale_row=-1):
+             pre_scale_row=-1, chain=0, row_start=None, k=0):
         """One hook firing over [J,H,W,C] = shape; prior = None | (row, tensor) | (row, elem, val) | a generic.PriorRef (the prior
-        and an optional probe read from a device table entry: replayable from a captured graph).  See include/xfrb.h."""
+        and an optional probe read from a device table entry: replayable from a captured graph).  chain 1 / 2: append to / append
+        and launch the pending chain of firings on the same tensor; row_start + k: row skipping.  See include/xfrb.h."""
         J, H, W, C = shape
         pr_t, pr_row, pr_elem, pr_val = None, -1, 0, 0.0
         entry = probe = None
@@ -278,7 +279,7 @@ class CudaBackend(object):
                                        0 if s2 is None else s2.shape[-1], _ptr(bn), _ptr(pr_t), int(pr_row), int(pr_elem),
                                        float(pr_val), _ptr(P_out), _ptr(z_out), recipe, 1 if affine else 0, relu_or_maxpool, mode,
                                        1 if post_mask else 0, post_scale_row, pre_scale_row, J, Ns, H, W, C, self.eps, entry, probe,
-                                       self._st()))
+                                       int(chain), row_start, int(k), self._st()), 0 if chain == 1 else 1)
 
     def head_seed(self, Pn, W2, seed):
         J, Ccls = Pn.shape
@@ -288,8 +289,8 @@ class CudaBackend(object):
         J, D = gin.shape
         self._check(self.lib.xfrb_normalize_bwd(_ptr(gin), _ptr(xn), _ptr(nrm), _ptr(gout), J, xn.shape[0], D, self._st()))
 
-    def maxpool_bwd(self, g, o, bn, out, pool_pad=1):
-        self._check(self.lib.xfrb_maxpool_bwd(_ptr(g), _ptr(o), _ptr(bn), _ptr(out), g.shape[0], o.shape[0], pool_pad, self._st()))
+    def maxpool_bwd(self, g, o, bn, out, pool_pad=1, mp_arg=None):
+        self._check(self.lib.xfrb_maxpool_bwd(_ptr(g), _ptr(o), _ptr(bn), _ptr(out), _ptr(mp_arg), g.shape[0], o.shape[0], pool_pad, self._st()))
 
     def subtree_score(self, gate, gneg, gate_ge0, score, arg):
         self._check(self.lib.xfrb_subtree_score(_ptr(gate), _ptr(gneg), 1 if gate_ge0 else 0, gate.numel(), _ptr(score), _ptr(arg),

@@ -21,7 +21,7 @@ import torch
 
 from . import packing
 from .engine import MODE_IDS, _Engine
-from .generic import _PriorMixin
+from .generic import _FlushBE, _PriorMixin
 
 AFFINE = ('Conv', 'Linear', 'AvgPool', 'BatchNorm')
 MODE_NONE = 3
@@ -182,7 +182,7 @@ class LightCNNSweep(_PriorMixin):
         """priors: {firing k: (row, elem, value) | (row, tensor)} in the DEVICE layout (NHWC, padded Split columns), or ptab: a
         generic.PriorTable (device-resident, graph-replayable);
         record: keep p (true_grad: the incoming gradient dA) of every firing; returns (P list | None, names, P2)."""
-        eng, be, S = self.eng, self.be, self.eng.saved
+        eng, be, S = self.eng, _FlushBE(self), self.eng.saved
         N, J = S['N'], Pn.shape[0]
         assert J % N == 0
         self._k = 0
@@ -221,7 +221,7 @@ class LightCNNSweep(_PriorMixin):
             n_, h_, w_, c_ = mt.shape
             gm = buf('lc_pb' + tag, J, h_, w_, c_)
             be.pool2_bwd(g_p, mt, gm)
-            zz = self.fire('MaxPool2d', 0, gm, (J, h_, w_, c_), s0=mt, out='lc_pa' + tag, rc=rc)
+            zz = self.fire('MaxPool2d', 0, gm, (J, h_, w_, c_), s0=mt, out='lc_pa' + tag, rc=rc, keep=False)
             return self.fire('AvgPool2d', 0, zz, (J, h_, w_, c_), s0=mt, out='lc_pb' + tag, rc=rc)
 
         def through_mfm(name, g_m, P_force=None):
@@ -256,7 +256,7 @@ class LightCNNSweep(_PriorMixin):
                 yrec = dict(s0=B['y'], s1=B['out'], s2=B['res'], rc=rc)
                 gname = 'lc_gres%d' % (i % 2)          # Add backward: the same gradient goes to `out` and to `res`
                 if i + 1 < len(blocks):
-                    z = self.fire('Conv2d', 6, z, shp, z_in2=z2, out='lc_a', **yrec)
+                    z = self.fire('Conv2d', 6, z, shp, z_in2=z2, out='lc_a', keep=False, **yrec)
                     g_res = self.fire('Add', 6, z, shp, out=gname, **yrec)
                 else:
                     g_res = self.fire('Conv2d', 6, z, shp, z_in2=z2, out=gname, **yrec)
@@ -274,7 +274,7 @@ class LightCNNSweep(_PriorMixin):
                 z = through_mfm('block%d.%d.conv1' % (bi, i), z)
                 z2 = g_res
                 if i == 0:
-                    z = self.fire('Conv2d', rres, z, shp, z_in2=z2, out='lc_a', **rrec)
+                    z = self.fire('Conv2d', rres, z, shp, z_in2=z2, out='lc_a', keep=False, **rrec)
                     z = self.fire('Add', rres, z, shp, out='lc_b', **rrec)
                     z2 = None
             if sg['pool_in'] is not None:
@@ -285,6 +285,7 @@ class LightCNNSweep(_PriorMixin):
             self._P.append(None)                     # Conv2d hook on the image: never read by any output
         self._names.append('Conv2d')
         self._layout.append((1, 1, False))
+        self._flush()
         return self._P, self._names, P2
 
     def elem_index(self, k, e, shape):
@@ -310,7 +311,7 @@ class LightCNNSweep(_PriorMixin):
             return p.permute(0, 3, 1, 2).reshape(p.shape[0], -1)          # the Linear hook sees the NCHW-flattened vector
         return p.permute(0, 3, 1, 2) if p.shape[1] * p.shape[2] > 1 else p.reshape(p.shape[0], -1)
 
-    def fire(self, kind, recipe, z_in, shape, out, P_force=None, z_in2=None, rc=None, split=False, **kw):
+    def fire(self, kind, recipe, z_in, shape, out, P_force=None, z_in2=None, rc=None, split=False, keep=True, **kw):
         k = self._k
         self._k += 1
         self._names.append(kind)
@@ -324,6 +325,6 @@ class LightCNNSweep(_PriorMixin):
             self._P.append(P_out)
         z_out = self.eng.buf(out, *shape) if out is not None else None
         flag = 2 if (self._norelu and ('MaxPool' in kind or 'ReLU' in kind)) else 0
-        self._hook(k, z_in, z_out, shape, recipe, affine, P_out=P_out, relu_or_maxpool=flag, N=self.eng.saved['N'], z_in2=z_in2,
-                   k2=1, **kw)
+        self._hook(k, z_in, z_out, shape, recipe, affine, P_out=P_out, keep=keep, relu_or_maxpool=flag, N=self.eng.saved['N'],
+                   z_in2=z_in2, k2=1, **kw)
         return z_out

@@ -667,7 +667,7 @@ class Whitebox(nn.Module):
         Z = torch.zeros(min(rows_per_sweep, max(len(todo), 1)), self.net.num_classes(), device=dev)     # fixed row count: one graph
         for i in range(0, len(todo), Z.shape[0]):
             chunk = todo[i:i + Z.shape[0]]
-            tab.clear()
+            tab.clear(zero_seed=True)                                     # zero class priors: row r is all zero before its firing
             for r, k in enumerate(chunk):
                 tab.set_tensor(k, r, priors[k])
             tab.upload()
@@ -742,7 +742,7 @@ class Whitebox(nn.Module):
         Z = torch.zeros(min(rows_per_sweep, len(seeds)), self.net.num_classes(), device=dev)     # fixed row count: one graph
         for i in range(0, len(seeds), Z.shape[0]):
             chunk = seeds[i:i + Z.shape[0]]
-            tab.clear()
+            tab.clear(zero_seed=True)                                     # zero class priors: row r is all zero before its firing
             for r, (k, e, v) in enumerate(chunk):
                 tab.set_elem(k, r, e, v)
             tab.upload()
