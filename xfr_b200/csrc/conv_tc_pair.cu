@@ -69,7 +69,19 @@ cudaError_t launch_conv_tc_pair(const float* A, const void* B, const ConvGeom& c
         cuuint32_t box[4] = {BK, (cuuint32_t)cg.W, (cuuint32_t)g.bh, (cuuint32_t)g.bimg};
         if (!encode(&tmA, A, 4, dims, strides, box, true)) return cudaErrorInvalidValue;
     }
-    const bool enough_pairs = ((g.n_m_tiles + 1) / 2) * g.n_n_tiles >= 74;
+    // Small problems (batch-1 calls: a few hundred GEMM rows): a 256-wide tile leaves a handful of CTAs streaming the whole weight
+    // matrix through one SM each (26 - 42 us per launch, profiles/r2r_ncu_launches_batch1.csv) - narrower tiles spread the weight
+    // rows over more SMs.  The k-loop of an output element is unchanged, so the results are bit-identical.  The dual forward pack
+    // is tiled for its BN and keeps it.
+    static const int small_bn = [] { const char* e = getenv("XFRB_SMALL_BN"); return e ? atoi(e) : 1; }();
+    if (!dual && small_bn) {
+        while (BN > 64 && g.n_m_tiles * (cg.Nn / BN) < 64 && cg.Nn % (BN / 2) == 0) BN /= 2;
+        g.n_n_tiles = cg.Nn / BN;
+    }
+    // CTA pairs whenever there is at least one pair of m-tiles: measured faster at both ends - 256-probe sweeps and
+    // batch-1 calls (4.27 -> 4.05 ms per contrastive_ebp: each SM stages half of the weight tile); XFRB_PAIR_MIN=74 is the old rule
+    static const int pair_min = [] { const char* e = getenv("XFRB_PAIR_MIN"); return e ? atoi(e) : 1; }();
+    const bool enough_pairs = ((g.n_m_tiles + 1) / 2) * g.n_n_tiles >= pair_min;
     static const int pair_kinds = [] { const char* e = getenv("XFRB_PAIR_KINDS"); return e ? atoi(e) : 3; }();   // bit 0: forward, bit 1: MID
     const bool cta2 = conv_tc_cta2_enabled() && enough_pairs &&
                       ((dual && (pair_kinds & 1)) || (ep.kind == EPI_MID && ep.mode == 0 && (pair_kinds & 2)));

@@ -727,14 +727,18 @@ cudaError_t launch_head_seed(const float* Pn, const float* W2, int C, int D, int
 //   8: a = relu(s0), x = relu(relu(s1)*sp + tp + s2)      (VGGFace2 ResNet-50 block ReLU: s0 = out, s1 = o3, s2 = positive shortcut)
 struct HookPrior { int row; long long elem; float val; const float* tensor; int probe_row; long long probe_elem; };
 
-// the prior of this firing: from the device table entry when there is one (graph replay), else from the launch arguments
-__device__ __forceinline__ HookPrior hook_prior(const HookArgs& A) {
+// the prior of this firing: from the device table entry when there is one (graph replay), else from the launch arguments.  Only
+// the two row numbers are read by every thread; the rest is fetched by the threads of the rows they name.
+__device__ __forceinline__ HookPrior hook_prior(const HookArgs& A, int j) {
     HookPrior P;
+    P.elem = 0; P.val = 0.f; P.tensor = nullptr; P.probe_elem = -1;
     if (A.ptab != nullptr) {
-        const PriorEntry e = *A.ptab;
-        P.row = e.row; P.elem = e.elem; P.val = e.val; P.tensor = e.tensor; P.probe_row = e.probe_row; P.probe_elem = e.probe_elem;
+        P.row = A.ptab->row;
+        P.probe_row = A.probe_out != nullptr ? A.ptab->probe_row : -1;
+        if (j == P.row) { P.elem = A.ptab->elem; P.val = A.ptab->val; P.tensor = A.ptab->tensor; }
+        if (j == P.probe_row) P.probe_elem = A.ptab->probe_elem;
     } else {
-        P.row = A.prior_row; P.elem = A.prior_elem; P.val = A.prior_val; P.tensor = A.prior; P.probe_row = -1; P.probe_elem = -1;
+        P.row = A.prior_row; P.elem = A.prior_elem; P.val = A.prior_val; P.tensor = A.prior; P.probe_row = -1;
     }
     return P;
 }
@@ -754,10 +758,12 @@ __device__ __forceinline__ void hook_ax(int recipe, float v0, float v1, float v2
 }
 
 // the firing itself for one element: z (after the pre-scales) -> return value (after the post ops); pv = what P_out records
+template <int MODE>      // MODE >= 0: the hook mode as a compile-time constant, -1: A.mode
 __device__ __forceinline__ float hook_fire(const HookArgs& A, const HookPrior& P, bool has_prior, size_t e, int c, float z, float a,
                                            float x, float& pv) {
+    const int mode = MODE >= 0 ? MODE : A.mode;
     float ret;
-    if (A.mode == XFRB_MODE_NONE) {
+    if (mode == XFRB_MODE_NONE) {
         pv = z;                                                // dA: the true gradient at this hooked tensor
         ret = z;
     } else {
@@ -769,13 +775,13 @@ __device__ __forceinline__ float hook_fire(const HookArgs& A, const HookPrior& P
             pv = pr;                                           // p.data.copy_(p_prior)
         }
         const float quo = __fdividef(pv, __fadd_rn(x, A.eps));
-        if (A.mode == XFRB_MODE_ALL) ret = quo;
-        else if (A.mode == XFRB_MODE_AFFINEONLY) ret = A.affine ? quo : z;
-        else if (A.mode == XFRB_MODE_AWP) {
+        if (mode == XFRB_MODE_ALL) ret = quo;
+        else if (mode == XFRB_MODE_AFFINEONLY) ret = A.affine ? quo : z;
+        else if (mode == XFRB_MODE_AWP) {
             if (has_prior) ret = A.affine ? (pr > 0.f ? quo : 0.f) : (pr > 0.f ? z : 0.f);
             else ret = A.affine ? quo : zh;
         } else ret = z;
-        if (A.mode == XFRB_MODE_ALL && has_prior && A.relu_or_maxpool == 2) ret = z;    // 'norelu' (mode id ALL + flag 2)
+        if (mode == XFRB_MODE_ALL && has_prior && A.relu_or_maxpool == 2) ret = z;    // 'norelu' (mode id ALL + flag 2)
     }
     if (A.post_mask) ret = a > 0.f ? ret : 0.f;
     if (A.post_scale_row >= 0) ret = __fmul_rn(ret, A.bn[A.post_scale_row * A.C + c]);
@@ -794,17 +800,24 @@ __device__ __forceinline__ float hook_fire(const HookArgs& A, const HookPrior& P
 // Row skipping: with ch.row_start (zero-seeded prior sweeps) gradient row j is all zero until the firing that carries its prior,
 // row_start[j]: earlier firings load nothing for it and store zeros where a tensor is kept (the GEMMs in between may turn those
 // zeros into anything they like - rows never mix), and AT that firing the incoming gradient is taken as zero.
-template <int VEC>
-__global__ void __launch_bounds__(256) hook_kernel(HookChain ch, size_t total) {
+struct HookIdx {            // host-prepared index arithmetic: grid.y = gradient row, grid.x covers one row's H*W*C/VEC threads
+    unsigned per_row;       // H * W * (C / VEC)
+    int cv_shift;           // log2(C / VEC) or -1 (divide)
+    unsigned w_magic;       // ceil(2^32 / W) when floor(p / W) == umulhi(p, w_magic) for every pixel p of the tensor, else 0 (divide)
+    int up_shift;           // log2(up) or -1 (divide)
+};
+template <int VEC, int MODE>
+__global__ void __launch_bounds__(256) hook_kernel(HookChain ch, HookIdx ix) {
     const HookArgs& A0 = ch.a[0];
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;          // 32-bit index arithmetic (the launcher rejects totals >= 2^32)
-    if (i >= total) return;
+    const unsigned il = blockIdx.x * blockDim.x + threadIdx.x;         // position inside the gradient row
+    if (il >= ix.per_row) return;
+    const int j = blockIdx.y;
+    const unsigned i = (unsigned)j * ix.per_row + il;                   // 32-bit index arithmetic (the launcher rejects totals >= 2^32)
     const unsigned Cv = (unsigned)A0.C / VEC;
-    const int c = (int)(i % Cv) * VEC;
-    unsigned p = i / Cv;
-    const int w = (int)(p % (unsigned)A0.W); p /= (unsigned)A0.W;
-    const int h = (int)(p % (unsigned)A0.H);
-    const int j = (int)(p / (unsigned)A0.H);
+    const unsigned pix = ix.cv_shift >= 0 ? il >> ix.cv_shift : il / Cv;
+    const int c = (int)(il - pix * Cv) * VEC;
+    const int h = (int)(ix.w_magic ? __umulhi(pix, ix.w_magic) : pix / (unsigned)A0.W);
+    const int w = (int)(pix - (unsigned)h * (unsigned)A0.W);
     const int n = j % A0.N;
     int first = 0;                                                       // first link this row takes part in
     bool zero_in = false;
@@ -825,9 +838,12 @@ __global__ void __launch_bounds__(256) hook_kernel(HookChain ch, size_t total) {
 #pragma unroll
     for (int q = 0; q < VEC; ++q) z[q] = 0.f;
     if (!zero_in) {                                                      // link 0's gather of the incoming gradient
-        if (A0.z_in != nullptr && h % A0.up == 0 && w % A0.up == 0) {
-            const int Hm = A0.H / A0.up, Wm = A0.W / A0.up;
-            ldv(A0.z_in + (((size_t)j * Hm + h / A0.up) * Wm + w / A0.up) * A0.zc + c, z);
+        const int us = ix.up_shift;
+        const bool on = us >= 0 ? (((h | w) & ((1 << us) - 1)) == 0) : (h % A0.up == 0 && w % A0.up == 0);
+        if (A0.z_in != nullptr && on) {
+            const int Hm = us >= 0 ? A0.H >> us : A0.H / A0.up, Wm = us >= 0 ? A0.W >> us : A0.W / A0.up;
+            const int hm = us >= 0 ? h >> us : h / A0.up, wm = us >= 0 ? w >> us : w / A0.up;
+            ldv(A0.z_in + (((size_t)j * Hm + hm) * Wm + wm) * A0.zc + c, z);
         }
         if (A0.z_in2 != nullptr && c < A0.c2) {
             const int Hr = A0.H / A0.k2, Wr = A0.W / A0.k2;
@@ -873,14 +889,14 @@ __global__ void __launch_bounds__(256) hook_kernel(HookChain ch, size_t total) {
         if (rc >= 3) ldv(A.s1 + ms * A.C + c, v1);                       // recipes 3 - 8 read s1 [N,H,W,C]
         if ((rc == 4 || rc == 8) && A.s2 != nullptr && c < A.c2s) ldv(A.s2 + ms * A.c2s + c, v2);
         if (rc == 6) ldv(A.s2 + ms * A.C + c, v2);
-        const HookPrior P = hook_prior(A);
-        const bool has_prior = (A.mode != XFRB_MODE_NONE) && (j == P.row);
+        const HookPrior P = hook_prior(A, j);
+        const bool has_prior = ((MODE >= 0 ? MODE : A.mode) != XFRB_MODE_NONE) && (j == P.row);
         float pv[VEC];
 #pragma unroll
         for (int q = 0; q < VEC; ++q) {
             float a, x;
             hook_ax(rc, v0[q], v1[q], v2[q], b[q], a, x);
-            z[q] = hook_fire(A, P, has_prior, e0 + q, c + q, z[q], a, x, pv[q]);
+            z[q] = hook_fire<MODE>(A, P, has_prior, e0 + q, c + q, z[q], a, x, pv[q]);
         }
         if (A.P_out != nullptr) stv(A.P_out + off, pv);
         if (A.z_out != nullptr) stv(A.z_out + off, z);
@@ -892,8 +908,7 @@ __global__ void __launch_bounds__(256) hook_kernel(HookChain ch, size_t total) {
 cudaError_t launch_hook_chain(const HookChain& ch, cudaStream_t st) {
     const HookArgs& a0 = ch.a[0];
     if (ch.n < 1 || ch.n > XFRB_MAX_CHAIN) return cudaErrorInvalidValue;
-    size_t total = (size_t)a0.J * a0.H * a0.W * a0.C;
-    if (total >= 0xFFFFFF00ull) return cudaErrorInvalidValue;          // the kernel indexes with 32-bit arithmetic
+    if ((size_t)a0.J * a0.H * a0.W * a0.C >= 0xFFFFFF00ull) return cudaErrorInvalidValue;          // the kernel indexes with 32-bit arithmetic
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     bool vec = a0.C % 4 == 0 && a0.zc % 4 == 0 && (a0.z_in2 == nullptr || a0.c2 % 4 == 0) && al16(a0.z_in) && al16(a0.z_in2);
     for (int l = 0; l < ch.n; ++l) {
@@ -903,12 +918,39 @@ cudaError_t launch_hook_chain(const HookChain& ch, cudaStream_t st) {
               al16(a.s2) && al16(a.bn) && al16(a.P_out) && al16(a.z_out);
     }
     static const int force_scalar = [] { const char* e = getenv("XFRB_HOOK_SCALAR"); return e ? atoi(e) : 0; }();   // A/B probe
-    if (vec && !force_scalar) {
-        total /= 4;
-        hook_kernel<4><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ch, total);
-    } else {
-        hook_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ch, total);
+    if (a0.J > 65535) return cudaErrorInvalidValue;                     // grid.y = gradient row
+    const int V = (vec && !force_scalar) ? 4 : 1;
+    auto log2_of = [](unsigned v) { int sh = 0; while ((1u << sh) < v) ++sh; return (v > 0 && (1u << sh) == v) ? sh : -1; };
+    HookIdx ix;
+    const unsigned Cv = (unsigned)a0.C / V, npix = (unsigned)a0.H * a0.W;
+    ix.per_row = npix * Cv;
+    ix.cv_shift = log2_of(Cv);
+    ix.up_shift = log2_of((unsigned)a0.up);
+    ix.w_magic = 0;
+    if (npix <= 65536 && a0.W > 1 && a0.W <= 256) {                     // reciprocal verified on the host, once per width
+        static unsigned char known[257] = {};                            // 0: not checked, 1: exact for every p < 65536, 2: not exact
+        const unsigned m = (unsigned)((0x100000000ull + a0.W - 1) / a0.W);
+        if (known[a0.W] == 0) {
+            bool exact = true;
+            for (unsigned p = 0; p < 65536 && exact; ++p) exact = (unsigned)(((unsigned long long)p * m) >> 32) == p / (unsigned)a0.W;
+            known[a0.W] = exact ? 1 : 2;
+        }
+        if (known[a0.W] == 1) ix.w_magic = m;
     }
+    int mode = a0.mode;
+    for (int l = 1; l < ch.n; ++l)
+        if (ch.a[l].mode != mode) mode = -1;
+    const dim3 grid((ix.per_row + 255) / 256, (unsigned)a0.J);
+#define XFRB_HOOK_LAUNCH(V_)                                                                   \
+    switch (mode) {                                                                            \
+        case XFRB_MODE_AWP: hook_kernel<V_, XFRB_MODE_AWP><<<grid, 256, 0, st>>>(ch, ix); break;            \
+        case XFRB_MODE_ALL: hook_kernel<V_, XFRB_MODE_ALL><<<grid, 256, 0, st>>>(ch, ix); break;            \
+        case XFRB_MODE_AFFINEONLY: hook_kernel<V_, XFRB_MODE_AFFINEONLY><<<grid, 256, 0, st>>>(ch, ix); break; \
+        case XFRB_MODE_NONE: hook_kernel<V_, XFRB_MODE_NONE><<<grid, 256, 0, st>>>(ch, ix); break;          \
+        default: hook_kernel<V_, -1><<<grid, 256, 0, st>>>(ch, ix); break;                     \
+    }
+    if (V == 4) { XFRB_HOOK_LAUNCH(4) } else { XFRB_HOOK_LAUNCH(1) }
+#undef XFRB_HOOK_LAUNCH
     return cudaGetLastError();
 }
 

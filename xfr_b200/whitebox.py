@@ -419,11 +419,16 @@ class Whitebox(nn.Module):
         if Pn.shape[0] == 1 and N > 1:
             Pn = Pn.expand(N, -1)
         hk = self.net.hooked()
+        # the maps of every chunk go to ONE pinned host tensor with asynchronous copies (a pageable .cpu() per chunk cost 3 ms per
+        # 128 Light-CNN maps: 9 % of the sweep)
+        res = torch.empty(N, eng.map_hw, eng.map_hw, pin_memory=bool(W2.is_cuda))      # torch's caching host allocator: no cudaHostAlloc per call
         for i in range(0, N, _CHUNK):
             m = eng.graph_call('ebp', (self.net._nhwc(x[i:i + _CHUNK]), Pn[i:i + _CHUNK].contiguous(), W2 if hk else W2[i:i + _CHUNK].contiguous()),
                                mode=self._ebp_subtree_mode, hooked_fc2=hk, saliency=not (mwp or self.convert_saliency_uint8))
-            outs.append(m.cpu())
-        maps = torch.cat(outs).numpy()
+            res[i:i + m.shape[0]].copy_(m, non_blocking=True)
+        if W2.is_cuda:
+            torch.cuda.current_stream(W2.device).synchronize()
+        maps = res.numpy()
         if self.convert_saliency_uint8 and not mwp:
             maps = np.stack([self._mwp_to_saliency_uint8(m) for m in maps])
         return maps
