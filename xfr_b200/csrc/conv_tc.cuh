@@ -17,6 +17,9 @@ namespace xfrb {
 #ifndef XFRB_PAIRA_EW
 #define XFRB_PAIRA_EW 0               /* 0: the warp layout of the TF32 kernels; 8 / 12: the split warpgroup's warps become epilogue warps (224 / 152 registers) */
 #endif
+#ifndef XFRB_PAIRA_JOIN_EW16
+#define XFRB_PAIRA_JOIN_EW16 0        /* JOIN only: 16 epilogue warps (the split warpgroup joins in), 4 slabs each of a 256-wide tile instead of 6 / 5 / 5 over 12 */
+#endif
 #ifndef XFRB_PAIRA_PAIRED
 #define XFRB_PAIRA_PAIRED 0           /* a warp takes the two 16-column slabs of a 32-column group back to back: both halves of every 128-byte line */
 #endif
@@ -254,13 +257,14 @@ struct TcCfg {
     // (threads x the most __launch_bounds__ allows; asking for more blocks setmaxnreg.inc forever).
     // bf16x2 plan (PAIRA): no operand-split warpgroup - its four warps become epilogue warps: 4 producer warps + 12 epilogue
     // warps = 512 threads for every kind (a CTA pair's "landed" relay moves to the idle warp 3 of the producer warpgroup)
-    static constexpr bool REPURPOSE = PAIRA && XFRB_PAIRA_EW != 0;
+    static constexpr bool JOIN16 = PAIRA && KIND == EPI_JOIN && XFRB_PAIRA_JOIN_EW16 != 0;
+    static constexpr bool REPURPOSE = (PAIRA && XFRB_PAIRA_EW != 0) || JOIN16;
     static constexpr int FIRST_EPI_WARP = REPURPOSE ? TC_FIRST_SPLIT_WARP : TC_FIRST_EPI_WARP;
-    static constexpr int EPI_WARPS = REPURPOSE ? XFRB_PAIRA_EW : (KIND == EPI_JOIN ? 12 : 8);
+    static constexpr int EPI_WARPS = JOIN16 ? 16 : (REPURPOSE ? XFRB_PAIRA_EW : (KIND == EPI_JOIN ? 12 : 8));
     static constexpr int THREADS = (FIRST_EPI_WARP + EPI_WARPS) * 32;                     // 512 / 640
     static constexpr int REGS_LAUNCH = (65536 / THREADS) / 8 * 8;                          // 128 / 96
-    static constexpr int REGS_PRODUCER = REPURPOSE ? 56 : (EPI_WARPS == 12 ? 48 : 56);
-    static constexpr int REGS_EPILOGUE = REPURPOSE ? (EPI_WARPS == 12 ? 152 : 224) : (EPI_WARPS == 12 ? 128 : 200);
+    static constexpr int REGS_PRODUCER = JOIN16 ? 40 : (REPURPOSE ? 56 : (EPI_WARPS == 12 ? 48 : 56));
+    static constexpr int REGS_EPILOGUE = JOIN16 ? 104 : (REPURPOSE ? (EPI_WARPS == 12 ? 152 : 224) : (EPI_WARPS == 12 ? 128 : 200));
     static_assert(FIRST_EPI_WARP * 32 * REGS_PRODUCER + EPI_WARPS * 32 * REGS_EPILOGUE <= THREADS * REGS_LAUNCH,
                   "setmaxnreg budgets exceed the CTA's register pool");
     static constexpr uint32_t TR_BYTES = EPI_WARPS * 2048;      // per epilogue warp: 32 rows x 16 columns transpose slab
