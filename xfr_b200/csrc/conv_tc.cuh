@@ -18,7 +18,7 @@ namespace xfrb {
 #define XFRB_PAIRA_EW 0               /* 0: the warp layout of the TF32 kernels; 8 / 12: the split warpgroup's warps become epilogue warps (224 / 152 registers) */
 #endif
 #ifndef XFRB_PAIRA_JOIN_EW16
-#define XFRB_PAIRA_JOIN_EW16 0        /* JOIN only: 16 epilogue warps (the split warpgroup joins in), 4 slabs each of a 256-wide tile instead of 6 / 5 / 5 over 12 */
+#define XFRB_PAIRA_JOIN_EW16 0        /* JOIN only: 16 epilogue warps (the split warpgroup joins in), 4 slabs each of a 256-wide tile instead of 6 / 5 / 5 over 12: measured 551 vs 493 us per layer3 launch (104 registers per epilogue thread) - slower */
 #endif
 #ifndef XFRB_PAIRA_PAIRED
 #define XFRB_PAIRA_PAIRED 0           /* a warp takes the two 16-column slabs of a 32-column group back to back: both halves of every 128-byte line */
