@@ -365,7 +365,9 @@ def run_extra(args, rank, local, world):
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    gemm = args.gemm if args.gemm != 'bf16x2' else 'tf32x3'       # the firing-by-firing sweeps run on the split-TF32 kernels
+    # Light-CNN runs on the split-TF32 kernels; the ResNet-101 sweeps take the plan as given (default bf16x2: forward and W+ dgrads on
+    # pair tensors / kind::f16, true-gradient passes and the head on split-TF32)
+    gemm = 'tf32x3' if (args.workload == 'lightcnn' and args.gemm == 'bf16x2') else args.gemm
     ev = lambda: torch.cuda.Event(enable_timing=True)
     cfg = {'workload': label, 'gemm': gemm, 'weights': 'seeded synthetic'}
     if args.workload == 'lightcnn':
@@ -420,7 +422,11 @@ def run_extra(args, rank, local, world):
         else:
             net = whitebox.WhiteboxSTResnet(sd, impl=gemm)
             wb = whitebox.Whitebox(net, ebp_subtree_mode='norelu')                 # create_wbnet.py:26-27
-            jobs = _synthetic_jobs(T, seed=200 + rank)
+            # the GLOBAL job list, identical on every rank: the sharded driver gives rank r its contiguous slice of T jobs.  (Until the
+            # end of round 2 every rank built its OWN T jobs and handed them to the sharded driver, which then ran T jobs in total
+            # (one per rank on the first T ranks) while world * T were counted: the 8-GPU figures of this workload in profiles/r2m_*
+            # and r2w_bench8_weighted_subtree.json are inflated by the factor T = 2.)
+            jobs = _synthetic_jobs(world * T, seed=200)
             units = T
             step_e2e = lambda: IG.run_weighted_subtree_triplet_ebp_sharded(wb, jobs, subtree_mode_weighted='all', ebp_version=None, device=dev, topk=32)
             step_res = step_e2e               # the job API takes host images (numpy): there is no device-resident variant of a job
@@ -463,7 +469,9 @@ def run_extra(args, rank, local, world):
     ach = alg_bytes * args.steps / (ms / 1e3) / 1e9
     out = {'metric': metric, 'value': total / (ms / 1e3), 'unit': unit, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-           'dtype': 'f32 (split-TF32 tcgen05: 3 passes on signed weights, 2 on W+; fp32 accumulate)', 'data': 'synthetic', 'config': cfg,
+           'dtype': ('bf16 terms on tcgen05 kind::f16 (activations / gradients 2 terms, relu(W) 1, signed W 2) for the forward and the W+ dgrads, '
+                     'split-TF32 for the true-gradient passes and the head; fp32 accumulate and fp32 hook algebra') if gemm == 'bf16x2'
+           else 'f32 (split-TF32 tcgen05: 3 passes on signed weights, 2 on W+; fp32 accumulate)', 'data': 'synthetic', 'config': cfg,
            'e2e': {'value': total / (ms_e2e / 1e3), 'unit': unit, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                    'ms_per_step': ms_e2e / args.steps},
            'gpu_launches': int(launches), 'clocks': clocks,

@@ -238,7 +238,11 @@ int xfrb_twin_blends(const double* orig, const double* inp, const double* value,
  *   z_in / up / zc / z_in2 / k2 / c2 are ignored (the link takes its predecessor's return value from registers) and a NULL z_out
  *   is simply not stored (at most XFRB_MAX_CHAIN = 6 links).  row_start ([J] device ints or NULL) with k = this firing's index
  *   (those of the chain's first link count): gradient row j is skipped by every firing before row_start[j] and enters firing
- *   row_start[j] with a zero gradient - the rows of a zero-seeded sweep whose priors sit at different firings. */
+ *   row_start[j] with a zero gradient - the rows of a zero-seeded sweep whose priors sit at different firings.
+ *   mfm_c (or NULL; first link only): z_in is the gradient at a Light-CNN MFM OUTPUT [J,H,W,C/2] and mfm_c the saved Split input
+ *   [N,H,W,C]; the gradient is first routed to the larger half, ties half each (backward of torch.max + Split, lightcnn.py:48-62).
+ *   out_pair != 0: z_out is written as a pair tensor (rows of [C bf16 hi | C bf16 lo], XFRB_IMPL_BF16X2) - the A operand of the
+ *   kind::f16 dgrad that follows (xfrb_dgrad_plain with impl 5). */
 typedef struct XfrbPriorEntry {
     int row;               /* gradient row that takes the prior at this firing, -1: none */
     int probe_row;         /* -1: no probe */
@@ -253,7 +257,7 @@ int xfrb_hook(const float* z_in, int up, int zc, const float* z_in2, int k2, int
               const float* s1, const float* s2, int c2s, const float* bn, const float* prior, int prior_row, long long prior_elem,
               float prior_val, float* P_out, float* z_out, int recipe, int affine, int relu_or_maxpool, int mode, int post_mask,
               int post_scale_row, int pre_scale_row, int J, int N, int H, int W, int C, float eps, const void* prior_entry,
-              float* probe_out, int chain, const int* row_start, int k, void* stream);
+              float* probe_out, int chain, const int* row_start, int k, const float* mfm_c, int out_pair, void* stream);
 /* seed[j,:] = Pn[j,:] @ W2[j % N]  (Pn [J,Ccls], W2 [N,Ccls,D]) */
 int xfrb_head_seed(const float* Pn, const float* W2, int Ccls, int D, int J, int N, float* seed, void* stream);
 /* Jacobian of F.normalize (resnet.py:250): gout = (gin - xn*<xn,gin>)/nrm, rows of length D <= 1024 */

@@ -268,9 +268,13 @@ class EmulBackend(object):
     # ------------------------------------------------------------ generic single-hook path
     def hook(self, z_in, z_out, shape, recipe, affine, mode, s0=None, s1=None, s2=None, bn=None, up=1, zc=None, z_in2=None, k2=1,
              pre_scale=1.0, prior=None, P_out=None, relu_or_maxpool=0, post_mask=False, post_scale_row=-1, N=None,
-             pre_scale_row=-1):
+             pre_scale_row=-1, mfm_c=None, out_pair=False):
         """One _backward_ebp firing with optional prior / recording (reference whitebox.py:381-430); include/xfrb.h xfrb_hook."""
         J, H, W, C = shape
+        if mfm_c is not None:                            # the MFM backward fused into the Split firing
+            zc = torch.empty(J, H, W, C)
+            self.mfm_bwd(z_in, mfm_c, zc)
+            z_in = zc
         z = torch.zeros(J, H, W, C)
         if z_in is not None:
             z[:, ::up, ::up, :] += z_in.reshape(J, H // up, W // up, -1)[..., :C]
@@ -345,7 +349,7 @@ class EmulBackend(object):
         if post_scale_row >= 0:
             ret = ret * bn[post_scale_row]
         if z_out is not None:
-            z_out.copy_(ret.view_as(z_out))
+            z_out.copy_(to_pair(ret.reshape(-1, C)).view_as(z_out) if out_pair else ret.view_as(z_out))
 
     def head_seed(self, Pn, W2, seed):
         seed.copy_(torch.einsum('jc,jcd->jd', Pn, _rows(W2, Pn.shape[0])))

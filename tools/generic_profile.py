@@ -18,7 +18,7 @@ def main():
     if what == 'lightcnn':
         return lightcnn(dev)
     sd = {k: v.to(dev) for k, v in synth.stresnet_state_dict(0).items()}
-    net = whitebox.WhiteboxSTResnet(sd, impl='tf32x3')
+    net = whitebox.WhiteboxSTResnet(sd, impl=sys.argv[2] if len(sys.argv) > 2 else whitebox.DEFAULT_IMPL)
     wb = whitebox.Whitebox(net, ebp_subtree_mode='affineonly_with_prior' if what == 'layer_sweep' else 'norelu')
     x = synth.synthetic_probes(1, seed=100).to(dev)
     with torch.no_grad():

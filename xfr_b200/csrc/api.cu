@@ -260,7 +260,7 @@ int xfrb_hook(const float* z_in, int up, int zc, const float* z_in2, int k2, int
               const float* s1, const float* s2, int c2s, const float* bn, const float* prior, int prior_row, long long prior_elem,
               float prior_val, float* P_out, float* z_out, int recipe, int affine, int relu_or_maxpool, int mode, int post_mask,
               int post_scale_row, int pre_scale_row, int J, int N, int H, int W, int C, float eps, const void* prior_entry,
-              float* probe_out, int chain, const int* row_start, int k, void* stream) {
+              float* probe_out, int chain, const int* row_start, int k, const float* mfm_c, int out_pair, void* stream) {
     static thread_local HookChain pending = {};      // links appended with chain = 1, launched by the call that passes chain = 2
     if (chain == 0 && pending.n != 0) { pending.n = 0; return finish("xfrb_hook", cudaErrorInvalidValue); }   // an unfinished chain
     if (chain < 0 || chain > 2 || pending.n >= XFRB_MAX_CHAIN) { pending.n = 0; return finish("xfrb_hook", cudaErrorInvalidValue); }
@@ -273,7 +273,7 @@ int xfrb_hook(const float* z_in, int up, int zc, const float* z_in2, int k2, int
     a.post_scale_row = post_scale_row; a.J = J; a.N = N; a.H = H; a.W = W; a.C = C; a.eps = eps;
     a.prior_row = prior_row; a.prior_elem = prior_elem; a.prior_val = prior_val;
     a.pre_scale_row = pre_scale_row;
-    a.ptab = static_cast<const PriorEntry*>(prior_entry); a.probe_out = probe_out;
+    a.ptab = static_cast<const PriorEntry*>(prior_entry); a.probe_out = probe_out; a.mfm_c = mfm_c; a.out_pair = out_pair;
     static_assert(sizeof(PriorEntry) == sizeof(XfrbPriorEntry), "include/xfrb.h XfrbPriorEntry mirrors PriorEntry");
     if (pending.n == 0) { pending.k0 = k; pending.row_start = row_start; }
     pending.a[pending.n++] = a;

@@ -241,6 +241,10 @@ struct HookArgs {
     // prior_elem / prior_val above, so a captured CUDA graph of a sweep can be replayed with different priors
     const PriorEntry* ptab;
     float* probe_out;                      // with ptab: p of element ptab->probe_elem of row ptab->probe_row is also written here
+    // Light-CNN: z_in is the gradient at an MFM OUTPUT [J,H,W,C/2] and mfm_c the saved Split input [N,H,W,C]: the firing (a Split
+    // hook on c) first routes the gradient to the larger half (ties: half each) - the backward of torch.max + Split, lightcnn.py:48-62
+    const float* mfm_c;
+    int out_pair;                          // z_out is a pair tensor (bf16 hi | lo rows): the A operand of a kind::f16 dgrad (bf16x2 plan)
 };
 constexpr int XFRB_MAX_CHAIN = 6;
 struct HookChain {                         // consecutive firings on one [J,H,W,C] tensor fused into one launch (stages.cu hook_kernel)

@@ -837,7 +837,19 @@ __global__ void __launch_bounds__(256) hook_kernel(HookChain ch, HookIdx ix) {
     float z[VEC], t[VEC];
 #pragma unroll
     for (int q = 0; q < VEC; ++q) z[q] = 0.f;
-    if (!zero_in) {                                                      // link 0's gather of the incoming gradient
+    if (!zero_in && A0.mfm_c != nullptr) {                               // MFM backward fused into the Split firing (mfm_bwd_kernel)
+        const int Cp = A0.C / 2;
+        const int ch = c < Cp ? c : c - Cp;                              // a 4-channel group never straddles the halves (Cp % 4 == 0)
+        float g[VEC], a[VEC], b[VEC];
+        ldv(A0.z_in + (((size_t)j * A0.H + h) * A0.W + w) * Cp + ch, g);
+        ldv(A0.mfm_c + ms * A0.C + ch, a);
+        ldv(A0.mfm_c + ms * A0.C + Cp + ch, b);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+            const float tq = a[q] == b[q] ? __fmul_rn(g[q], 0.5f) : g[q];
+            z[q] = c < Cp ? (a[q] < b[q] ? 0.f : tq) : (b[q] < a[q] ? 0.f : tq);
+        }
+    } else if (!zero_in) {                                               // link 0's gather of the incoming gradient
         const int us = ix.up_shift;
         const bool on = us >= 0 ? (((h | w) & ((1 << us) - 1)) == 0) : (h % A0.up == 0 && w % A0.up == 0);
         if (A0.z_in != nullptr && on) {
@@ -857,7 +869,7 @@ __global__ void __launch_bounds__(256) hook_kernel(HookChain ch, HookIdx ix) {
     const size_t off = (size_t)i * VEC;
     // firings before the row's start: its gradient and p are zero there - the tensors that are kept (residual-path gradients are
     // read again after the start) get their zeros, nothing is loaded
-    for (int l = 0; l < first; ++l) {
+    for (int l = 0; l < first; ++l) {                                    // (a pair row of zeros is all zero bits as well)
         if (ch.a[l].P_out != nullptr) stv(ch.a[l].P_out + off, z);
         if (ch.a[l].z_out != nullptr) stv(ch.a[l].z_out + off, z);
     }
@@ -899,7 +911,12 @@ __global__ void __launch_bounds__(256) hook_kernel(HookChain ch, HookIdx ix) {
             z[q] = hook_fire<MODE>(A, P, has_prior, e0 + q, c + q, z[q], a, x, pv[q]);
         }
         if (A.P_out != nullptr) stv(A.P_out + off, pv);
-        if (A.z_out != nullptr) stv(A.z_out + off, z);
+        if (A.z_out != nullptr) {
+            if constexpr (VEC == 4) {
+                if (A.out_pair) st_pair4(A.z_out, ((size_t)j * A0.H + h) * A0.W + w, A0.C, c, z);
+                else stv(A.z_out + off, z);
+            } else stv(A.z_out + off, z);
+        }
         if (A.probe_out != nullptr && j == P.probe_row && P.probe_elem >= (long long)e0 && P.probe_elem < (long long)e0 + VEC)
             *A.probe_out = pv[(int)(P.probe_elem - (long long)e0)];
     }
@@ -910,7 +927,9 @@ cudaError_t launch_hook_chain(const HookChain& ch, cudaStream_t st) {
     if (ch.n < 1 || ch.n > XFRB_MAX_CHAIN) return cudaErrorInvalidValue;
     if ((size_t)a0.J * a0.H * a0.W * a0.C >= 0xFFFFFF00ull) return cudaErrorInvalidValue;          // the kernel indexes with 32-bit arithmetic
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    bool vec = a0.C % 4 == 0 && a0.zc % 4 == 0 && (a0.z_in2 == nullptr || a0.c2 % 4 == 0) && al16(a0.z_in) && al16(a0.z_in2);
+    if (a0.mfm_c != nullptr && (a0.z_in == nullptr || a0.z_in2 != nullptr || a0.up != 1 || a0.C % 2)) return cudaErrorInvalidValue;
+    bool vec = a0.C % 4 == 0 && a0.zc % 4 == 0 && (a0.z_in2 == nullptr || a0.c2 % 4 == 0) && al16(a0.z_in) && al16(a0.z_in2) &&
+               (a0.mfm_c == nullptr || (a0.C % 8 == 0 && al16(a0.mfm_c)));
     for (int l = 0; l < ch.n; ++l) {
         const HookArgs& a = ch.a[l];
         if (a.J != a0.J || a.N != a0.N || a.H != a0.H || a.W != a0.W || a.C != a0.C) return cudaErrorInvalidValue;
@@ -920,6 +939,8 @@ cudaError_t launch_hook_chain(const HookChain& ch, cudaStream_t st) {
     static const int force_scalar = [] { const char* e = getenv("XFRB_HOOK_SCALAR"); return e ? atoi(e) : 0; }();   // A/B probe
     if (a0.J > 65535) return cudaErrorInvalidValue;                     // grid.y = gradient row
     const int V = (vec && !force_scalar) ? 4 : 1;
+    for (int l = 0; l < ch.n; ++l)
+        if (ch.a[l].out_pair && V != 4) return cudaErrorInvalidValue;   // pair rows are written four channels at a time
     auto log2_of = [](unsigned v) { int sh = 0; while ((1u << sh) < v) ++sh; return (v > 0 && (1u << sh) == v) ? sh : -1; };
     HookIdx ix;
     const unsigned Cv = (unsigned)a0.C / V, npix = (unsigned)a0.H * a0.W;

@@ -196,6 +196,8 @@ class _FC(object):
 
 
 class GenericSweep(_PriorMixin):
+    pair_dgrads = True       # bf16x2 plan: pair-tensor dgrads in the W+ sweeps (False: fp32 activations on the split-TF32 kernels)
+
     def __init__(self, engine):
         self.eng = engine
         self.be = engine.be
@@ -236,8 +238,13 @@ class GenericSweep(_PriorMixin):
         buf = eng.buf
         head = eng.head
 
+        # bf16x2 plan: the W+ dgrads of the block convs run on the pair-tensor kernels (tcgen05 kind::f16, as in the fused sweep):
+        # the BatchNorm2d firing that feeds one writes its return value as a pair tensor.  True-gradient sweeps (signed weights,
+        # three TF32 passes) and the head's fc dgrad keep fp32 activations.
+        pairs = self._pairs = bool(getattr(self.be, 'pairs', False)) and not true_grad and self.pair_dgrads
+
         def dgrad(y, L, out):
-            be.dgrad_plain(y, L, out, signed=true_grad)
+            be.dgrad_plain(y, L, out, signed=true_grad, pair=pairs and getattr(L, 'pair_pack', False))
             return out
 
         # ---- head: fc2 (un-hooked triplet rows) -> x50 -> Multiply hook -> normalize' -> fc1 -> Linear hook -> AvgPool'
@@ -287,16 +294,16 @@ class GenericSweep(_PriorMixin):
                 gres = self.fire('ConcatChannels', 0, zr, (J, h, h, Cr), s0=t['ap'], zc=C, out='gs_r2')
                 gres_k = b.stride
             z = self.fire('Add', 0, g, shp, s0=res, post_scale_row=srow, bn=b.c3.bn, out='gs_a', keep=False)   # slot 0: residual's (A, X)
-            y3 = self.fire('BatchNorm2d', 3, z, shp, s0=t['o3'], s1=t['xr3'], out='gs_y3')
+            y3 = self.fire('BatchNorm2d', 3, z, shp, s0=t['o3'], s1=t['xr3'], out='gs_y3', out_pair=pairs)
             z = dgrad(y3, b.c3, buf('gs_z2', J, h, h, b.planes))
             shp2 = (J, h, h, b.planes)
             z = self.fire('ReLU', 1, z, shp2, s0=t['o2'], bn=b.c2.bn, out='gs_c', keep=False)
             z = self.fire('Conv2d', 2, z, shp2, s0=t['o2'], bn=b.c2.bn, post_mask=True, post_scale_row=srow, out='gs_d', keep=False)
-            y2 = self.fire('BatchNorm2d', 3, z, shp2, s0=t['o2'], s1=t['xr2'], out='gs_y2')
+            y2 = self.fire('BatchNorm2d', 3, z, shp2, s0=t['o2'], s1=t['xr2'], out='gs_y2', out_pair=pairs)
             z = dgrad(y2, b.c2, buf('gs_z1', J, h, h, b.planes))
             z = self.fire('ReLU', 1, z, shp2, s0=t['o1'], bn=b.c1.bn, out='gs_c', keep=False)
             z = self.fire('Conv2d', 2, z, shp2, s0=t['o1'], bn=b.c1.bn, post_mask=True, post_scale_row=srow, out='gs_d', keep=False)
-            y1 = self.fire('BatchNorm2d', 3, z, shp2, s0=t['o1'], s1=t['xr1'], out='gs_y1')
+            y1 = self.fire('BatchNorm2d', 3, z, shp2, s0=t['o1'], s1=t['xr1'], out='gs_y1', out_pair=pairs)
             zlo = dgrad(y1, b.c1, buf('gs_zlo', J, h, h, b.cin))
             # the sum g_main + g_res is taken by the next firing: z_in (stride-2 scatter) + z_in2 (AvgPool backward)
             zin, zin_up, zin2, k2 = zlo, b.stride, gres, gres_k
@@ -359,8 +366,10 @@ class R50Sweep(GenericSweep):
         buf, head = eng.buf, eng.head
         D, C = head.dim, head.cin
 
+        pairs = self._pairs = bool(getattr(self.be, 'pairs', False)) and not true_grad and self.pair_dgrads      # see GenericSweep.run
+
         def dgrad(y, L, out, accumulate=False):
-            be.dgrad_plain(y, L, out, signed=true_grad, accumulate=accumulate)
+            be.dgrad_plain(y, L, out, signed=true_grad, accumulate=accumulate, pair=pairs and getattr(L, 'pair_pack', False))
             return out
 
         seed = buf('gs_seed', J, 1, 1, D)
@@ -388,18 +397,18 @@ class R50Sweep(GenericSweep):
                 g = self.fire('Conv2d', 0, z, shp, s0=t['out'], post_mask=True, out='gs_g%d' % (i % 2))
             zlo = buf('gs_zlo', J, h, h, b.cin)
             if b.proj:       # proj_bn's hook fires before the main path's (it was created later: autograd order)
-                yp = self.fire('BatchNorm2d', 3, g, shp, s0=t['op'], s1=t['xrp'], bn=b.cp.bn, pre_scale_row=srow, out='gs_yp')
+                yp = self.fire('BatchNorm2d', 3, g, shp, s0=t['op'], s1=t['xrp'], bn=b.cp.bn, pre_scale_row=srow, out='gs_yp', out_pair=pairs)
                 dgrad(yp, b.cp, zlo)
-            y3 = self.fire('BatchNorm2d', 3, g, shp, s0=t['o3'], s1=t['xr3'], bn=b.c3.bn, pre_scale_row=srow, out='gs_y3')
+            y3 = self.fire('BatchNorm2d', 3, g, shp, s0=t['o3'], s1=t['xr3'], bn=b.c3.bn, pre_scale_row=srow, out='gs_y3', out_pair=pairs)
             z = dgrad(y3, b.c3, buf('gs_z2', J, h, h, b.planes))
             shp2 = (J, h, h, b.planes)
             z = self.fire('ReLU', 1, z, shp2, s0=t['o2'], bn=b.c2.bn, out='gs_c', keep=False)
             z = self.fire('Conv2d', 2, z, shp2, s0=t['o2'], bn=b.c2.bn, post_mask=True, post_scale_row=srow, out='gs_d', keep=False)
-            y2 = self.fire('BatchNorm2d', 3, z, shp2, s0=t['o2'], s1=t['xr2'], out='gs_y2')
+            y2 = self.fire('BatchNorm2d', 3, z, shp2, s0=t['o2'], s1=t['xr2'], out='gs_y2', out_pair=pairs)
             z = dgrad(y2, b.c2, buf('gs_z1', J, h, h, b.planes))
             z = self.fire('ReLU', 1, z, shp2, s0=t['o1'], bn=b.c1.bn, out='gs_c', keep=False)
             z = self.fire('Conv2d', 2, z, shp2, s0=t['o1'], bn=b.c1.bn, post_mask=True, post_scale_row=srow, out='gs_d', keep=False)
-            y1 = self.fire('BatchNorm2d', 3, z, shp2, s0=t['o1'], s1=t['xr1'], out='gs_y1')
+            y1 = self.fire('BatchNorm2d', 3, z, shp2, s0=t['o1'], s1=t['xr1'], out='gs_y1', out_pair=pairs)
             dgrad(y1, b.c1, zlo, accumulate=b.proj)
             if b.proj:
                 zin, zin_up, zin2, k2 = zlo, b.stride, None, 1          # both dgrads landed on the (sub-sampled) block input

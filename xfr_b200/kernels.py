@@ -48,7 +48,7 @@ _SIGNATURES = {
     'xfrb_stem_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
     'xfrb_bn_hook': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     'xfrb_hook': [_P, _I, _I, _P, _I, _I, _F, _P, _I, _P, _P, _I, _P, _P, _I, ctypes.c_longlong, _F, _P, _P, _I, _I, _I, _I, _I,
-                  _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _I, _P, _I, _P],
+                  _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _I, _P, _I, _P, _I, _P],
     'xfrb_head_seed': [_P, _P, _I, _I, _I, _I, _P, _P],
     'xfrb_normalize_bwd': [_P, _P, _P, _P, _I, _I, _I, _P],
     'xfrb_maxpool_bwd': [_P, _P, _P, _P, _P, _I, _I, _I, _P],
@@ -259,7 +259,7 @@ class CudaBackend(object):
     # -------------------------------------------------------------- generic single-hook path
     def hook(self, z_in, z_out, shape, recipe, affine, mode, s0=None, s1=None, s2=None, bn=None, up=1, zc=None, z_in2=None, k2=1,
              pre_scale=1.0, prior=None, P_out=None, relu_or_maxpool=0, post_mask=False, post_scale_row=-1, N=None,
-             pre_scale_row=-1, chain=0, row_start=None, k=0):
+             pre_scale_row=-1, chain=0, row_start=None, k=0, mfm_c=None, out_pair=False):
         """One hook firing over [J,H,W,C] = shape; prior = None | (row, tensor) | (row, elem, val) | a generic.PriorRef (the prior
         and an optional probe read from a device table entry: replayable from a captured graph).  chain 1 / 2: append to / append
         and launch the pending chain of firings on the same tensor; row_start + k: row skipping.  See include/xfrb.h."""
@@ -279,7 +279,8 @@ class CudaBackend(object):
                                        0 if s2 is None else s2.shape[-1], _ptr(bn), _ptr(pr_t), int(pr_row), int(pr_elem),
                                        float(pr_val), _ptr(P_out), _ptr(z_out), recipe, 1 if affine else 0, relu_or_maxpool, mode,
                                        1 if post_mask else 0, post_scale_row, pre_scale_row, J, Ns, H, W, C, self.eps, entry, probe,
-                                       int(chain), row_start, int(k), self._st()), 0 if chain == 1 else 1)
+                                       int(chain), row_start, int(k), _ptr(mfm_c), 1 if out_pair else 0, self._st()),
+                    0 if chain == 1 else 1)
 
     def head_seed(self, Pn, W2, seed):
         J, Ccls = Pn.shape

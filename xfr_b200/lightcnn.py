@@ -228,11 +228,11 @@ class LightCNNSweep(_PriorMixin):
             """gradient at an mfm output (its hooks applied) -> gradient at the mfm input (before its hooks)"""
             st = sites[name]
             hw, cp = st.hw, st.L.cp
-            zc = buf('lc_zc', J, hw, hw, 2 * cp)
-            be.mfm_bwd(g_m, st.c, zc)
             last = name == 'conv1'
-            yc = self.fire('Split', 7, zc, (J, hw, hw, 2 * cp), s0=st.c, s1=st.cpos if st.cpos is not None else st.c,
-                           out=None if last else 'lc_yc', P_force=P_force, rc=st.L.c, split=True)
+            # the MFM backward (route the gradient to the larger Split half) is the first thing the Split firing does: no [J,hw,hw,2cp]
+            # tensor is written and read back in between
+            yc = self.fire('Split', 7, g_m, (J, hw, hw, 2 * cp), s0=st.c, s1=st.cpos if st.cpos is not None else st.c,
+                           out=None if last else 'lc_yc', P_force=P_force, rc=st.L.c, split=True, mfm_c=st.c, zc=cp)
             if last:
                 return None
             return dgrad(yc, st.L, buf('lc_zu', J, hw, hw, st.L.cin))

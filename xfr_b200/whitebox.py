@@ -777,11 +777,10 @@ class Whitebox(nn.Module):
             smap = self._float32_to_uint8(smap)
         else:
             smap /= max(smap.sum(), self.eps)
-        return (
-            self._mwp_to_saliency(smap) if do_mwp_to_saliency else smap,
-            [self._mwp_to_saliency(P) if do_mwp_to_saliency else P for P in P_img_valid],
-            P_subtree_valid,
-            k_subtree_valid)
+        if do_mwp_to_saliency:                      # the merged map and the topk sub-tree maps through ONE post-filter call
+            sal = self._mwp_to_saliency_many([smap] + list(P_img_valid))
+            smap, P_img_valid = sal[0], sal[1:]
+        return (smap, P_img_valid, P_subtree_valid, k_subtree_valid)
 
     def _scale_normalized(self, img):
         """whitebox.py:443-446"""
@@ -798,6 +797,16 @@ class Whitebox(nn.Module):
         out = torch.empty(t.shape, device=dev)
         be.saliency_post(t.to(dev), out)
         return out[0].cpu().numpy()
+
+    def _mwp_to_saliency_many(self, maps, blur_radius=2):
+        """_mwp_to_saliency over a list of equally sized host maps: one copy in, one kernel, one copy out."""
+        if self.convert_saliency_uint8 or len(maps) == 0:
+            return [self._mwp_to_saliency(P, blur_radius) for P in maps]
+        t = torch.from_numpy(np.ascontiguousarray(np.stack(maps), dtype=np.float32))
+        dev = self.net._device()
+        out = torch.empty(t.shape, device=dev)
+        self.net.engine(self._ebp_with_bias).be.saliency_post(t.to(dev), out)
+        return list(out.cpu().numpy())
 
     def ebp_subtree_mode(self):
         return self._ebp_subtree_mode
