@@ -647,7 +647,11 @@ def main():
         cores = os.cpu_count()
         n = 40                                   # ~10 s of host work at the ~4 maps/s measured on the GPU box's 16 cores
         out['cpu_baseline'] = {'value': cpu_port(n, cores), 'unit': 'maps/s', 'cores': cores, 'kind': 'port',
-                               'sample': '%d triplets of the same workload, batch 1, torch CPU fp32 restatement (oracle/)' % n}
+                               'sample': '%d triplets of the same workload, batch 1, torch CPU fp32 restatement (oracle/)' % n,
+                               'note': 'the port shares one forward between the mate and the non-mate sweep (2 forwards + 2 backwards per map); the '
+                                       'unmodified reference (hook-based, 6 forwards + 2 backwards) measured 0.73 maps/s on 8 cores of the build '
+                                       'container (BASELINE.md section 2) and cannot travel to the GPU box',
+                               'reference_measured_maps_per_s_8_cores': 0.73}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

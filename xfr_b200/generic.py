@@ -51,6 +51,7 @@ class PriorTable(object):
         if self.device.type == 'cuda':
             self._stage = self._stage.pin_memory()
         self._keep = {}
+        self._copied = None
         # zero-seeded sweeps (every gradient row starts from a zero class prior and comes to life at the firing that carries its
         # prior): start[j] = that firing; the hook kernels skip row j before it and take its incoming gradient as zero there
         self.zero_seed = False
@@ -83,8 +84,16 @@ class PriorTable(object):
         e['probe_row'], e['probe_elem'] = row, elem
 
     def upload(self):
+        if self._copied is not None:
+            self._copied.synchronize()         # the previous upload's asynchronous copies have read the pinned staging buffers
         self._stage.copy_(torch.from_numpy(self.host.view(np.uint8)))
         self.dev.copy_(self._stage, non_blocking=True)
+        self._upload_start()
+        if self.device.type == 'cuda':
+            self._copied = torch.cuda.Event()
+            self._copied.record(torch.cuda.current_stream(self.device))
+
+    def _upload_start(self):
         if self.zero_seed:
             st = np.full(MAX_ROWS, NEVER, dtype=np.int32)
             ks = np.nonzero(self.host['row'] >= 0)[0]
