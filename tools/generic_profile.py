@@ -48,7 +48,7 @@ def main():
         setattr(obj, name, timed)
     wrap(eng, 'forward', 'forward')
     wrap(eng, 'generic_call', 'sweeps (graph replays)')
-    wrap(wb, '_contrastive_prior', 'priors')
+    wrap(eng, 'graph_fn', 'priors (graph replay)')
     wrap(wb, '_finish_map', 'finish maps')
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -59,10 +59,9 @@ def main():
     for k, v in phases.items():
         print('  %-28s %7.1f ms' % (k, v * 1e3))
     print('  %-28s %7.1f ms' % ('other (host)', (tot - sum(phases.values())) * 1e3))
-    for n in ('forward', 'generic_call'):
+    for n in ('forward', 'generic_call', 'graph_fn'):
         delattr(eng, n)
-    for n in ('_contrastive_prior', '_finish_map'):
-        delattr(wb, n)
+    delattr(wb, '_finish_map')
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         call()

@@ -73,6 +73,13 @@ cudaError_t launch_conv_tc_pair(const float* A, const void* B, const ConvGeom& c
     // matrix through one SM each (26 - 42 us per launch, profiles/r2r_ncu_launches_batch1.csv) - narrower tiles spread the weight
     // rows over more SMs.  The k-loop of an output element is unchanged, so the results are bit-identical.  The dual forward pack
     // is tiled for its BN and keeps it.
+    // The K >= 1,024 MID dgrads (conv3 dgrad of layer3 / layer4: 256 or 512 output columns) run on 128-wide tiles: twice the tiles -
+    // 10.6 rounds over the SMs instead of 5.3 run as 6 - each streaming the same A for half the MMA work: 174 -> 153 us per layer3
+    // launch (gpurun_out/r2ac).  Same k-loop per output element: bit-identical.  XFRB_MID_BN=256 restores the wide tiles.
+    static const int mid_bn = [] { const char* e = getenv("XFRB_MID_BN"); return e ? atoi(e) : 128; }();
+    if (mid_bn == 128 && ep.kind == EPI_MID && cg.R == 1 && cg.K >= 1024 && BN == 256) { BN = 128; g.n_n_tiles = cg.Nn / BN; }
+    static const int join_bn = [] { const char* e = getenv("XFRB_JOIN_BN"); return e ? atoi(e) : 0; }();      // A/B probe: JOIN dgrads on 128-wide tiles
+    if (join_bn == 128 && ep.kind == EPI_JOIN && BN == 256) { BN = 128; g.n_n_tiles = cg.Nn / BN; }
     static const int small_bn = [] { const char* e = getenv("XFRB_SMALL_BN"); return e ? atoi(e) : 1; }();
     if (!dual && small_bn) {
         while (BN > 64 && g.n_m_tiles * (cg.Nn / BN) < 64 && cg.Nn % (BN / 2) == 0) BN /= 2;

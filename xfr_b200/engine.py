@@ -150,6 +150,32 @@ class _Engine(object):
             opts['zero_seed'] = opts['ptab'].zero_seed
         return self.graph_call('generic_run', (Pn.contiguous(), W2), max_n=self.graph_generic_rows, n_saved=self.saved['N'], **opts)
 
+    def graph_fn(self, key, fn):
+        """fn() - device work on static addresses, no host synchronisation - through the graph table: eager the first time `key` is
+        seen, captured the second time, replayed afterwards (the returned tensors are then the captured ones, overwritten by every
+        replay).  Used for the ~2,000 small launches that turn the recorded MWPs of a layer sweep into its per-layer priors."""
+        if (self.graph_max_n <= 0 or self.device.type != 'cuda' or getattr(self.be, 'name', '') != 'cuda'
+                or torch.cuda.is_current_stream_capturing()):
+            return fn()
+        ent = self._graphs.get(key)
+        if ent is None:
+            out = fn()
+            self._graphs.setdefault(key, {'graph': None})
+            return out
+        if ent['graph'] is None:
+            torch.cuda.current_stream(self.device).synchronize()
+            g = torch.cuda.CUDAGraph()
+            l0 = getattr(self.be, 'launches', 0)
+            with torch.cuda.graph(g):
+                out = fn()
+            if key not in self._graphs:
+                return fn()
+            ent.update(graph=g, out=out, launches=getattr(self.be, 'launches', 0) - l0)
+            self.be.launches = l0
+        ent['graph'].replay()
+        self.be.launches += ent['launches']
+        return ent['out']
+
     def workspace_bytes(self):
         return sum(t.numel() * t.element_size() for t in self._ws.values() if torch.is_tensor(t))
 

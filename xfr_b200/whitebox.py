@@ -661,8 +661,12 @@ class Whitebox(nn.Module):
         P, names = rec['P'], rec['names']
         k_layers = [int(k) % len(P) for k in k_layers]                 # negative indices as Python lists take them
         # the last firing (the Conv2d hook on the image) is not recorded: a prior there cannot reach P[-2], the map is all zero
-        priors = {k: self._contrastive_prior(gs, P[k][0:1], P[k][1:2], k, mode, percentile, None).reshape(-1).contiguous()
-                  for k in set(k_layers) if P[k] is not None}
+        ks = tuple(sorted(k for k in set(k_layers) if P[k] is not None))
+
+        def make_priors():
+            return {k: self._contrastive_prior(gs, P[k][0:1], P[k][1:2], k, mode, percentile, None).reshape(-1).contiguous() for k in ks}
+        # ~10 small launches per layer: replayed as one graph once the recorded MWPs sit at static addresses (the record sweep's graph)
+        priors = eng.graph_fn(('layer_priors', mode, float(percentile), ks, tuple(P[k].data_ptr() for k in ks)), make_priors)
         zero = self._zero_map(mwp)
         del P, rec
         self.P_layername = list(names)
