@@ -30,7 +30,7 @@ def main():
         call = lambda: wb.layerwise_contrastive_ebp_sweep(x, 0, 1, ks, mode='percentile', percentile=20)
     else:
         call = lambda: wb.weighted_subtree_ebp(x, 0, 1, topk=32, verbose=False, do_mated_similarity_gating=False, subtree_mode='all')
-    for _ in range(3):
+    for _ in range(6):          # eager, capture, ... : the graphs of a call settle after a few calls (a grown workspace buffer drops them once)
         call()
     phases = collections.OrderedDict()
     eng = net.engine(wb._ebp_with_bias)
@@ -50,12 +50,13 @@ def main():
     wrap(eng, 'generic_call', 'sweeps (graph replays)')
     wrap(eng, 'graph_fn', 'priors (graph replay)')
     wrap(wb, '_finish_map', 'finish maps')
+    caps = eng.graph_captures
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     call()
     torch.cuda.synchronize()
     tot = time.perf_counter() - t0
-    print('%s: %.1f ms per call' % (what, tot * 1e3))
+    print('%s: %.1f ms per call (%d graph captures during it, %d before)' % (what, tot * 1e3, eng.graph_captures - caps, caps))
     for k, v in phases.items():
         print('  %-28s %7.1f ms' % (k, v * 1e3))
     print('  %-28s %7.1f ms' % ('other (host)', (tot - sum(phases.values())) * 1e3))

@@ -759,7 +759,7 @@ __device__ __forceinline__ void hook_ax(int recipe, float v0, float v1, float v2
 
 // the firing itself for one element: z (after the pre-scales) -> return value (after the post ops); pv = what P_out records
 template <int MODE>      // MODE >= 0: the hook mode as a compile-time constant, -1: A.mode
-__device__ __forceinline__ float hook_fire(const HookArgs& A, const HookPrior& P, bool has_prior, size_t e, int c, float z, float a,
+__device__ __forceinline__ float hook_fire(const HookArgs& A, const HookPrior& P, bool has_prior, size_t e, float pscale, float z, float a,
                                            float x, float& pv) {
     const int mode = MODE >= 0 ? MODE : A.mode;
     float ret;
@@ -784,7 +784,7 @@ __device__ __forceinline__ float hook_fire(const HookArgs& A, const HookPrior& P
         if (mode == XFRB_MODE_ALL && has_prior && A.relu_or_maxpool == 2) ret = z;    // 'norelu' (mode id ALL + flag 2)
     }
     if (A.post_mask) ret = a > 0.f ? ret : 0.f;
-    if (A.post_scale_row >= 0) ret = __fmul_rn(ret, A.bn[A.post_scale_row * A.C + c]);
+    if (A.post_scale_row >= 0) ret = __fmul_rn(ret, pscale);          // pscale = bn[post_scale_row][c]
     return ret;
 }
 
@@ -903,12 +903,15 @@ __global__ void __launch_bounds__(256) hook_kernel(HookChain ch, HookIdx ix) {
         if (rc == 6) ldv(A.s2 + ms * A.C + c, v2);
         const HookPrior P = hook_prior(A, j);
         const bool has_prior = ((MODE >= 0 ? MODE : A.mode) != XFRB_MODE_NONE) && (j == P.row);
-        float pv[VEC];
+        float pv[VEC], ps[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) ps[q] = 1.f;
+        if (A.post_scale_row >= 0) ldv(A.bn + A.post_scale_row * A.C + c, ps);
 #pragma unroll
         for (int q = 0; q < VEC; ++q) {
             float a, x;
             hook_ax(rc, v0[q], v1[q], v2[q], b[q], a, x);
-            z[q] = hook_fire<MODE>(A, P, has_prior, e0 + q, c + q, z[q], a, x, pv[q]);
+            z[q] = hook_fire<MODE>(A, P, has_prior, e0 + q, ps[q], z[q], a, x, pv[q]);
         }
         if (A.P_out != nullptr) stv(A.P_out + off, pv);
         if (A.z_out != nullptr) {
@@ -919,6 +922,119 @@ __global__ void __launch_bounds__(256) hook_kernel(HookChain ch, HookIdx ix) {
         }
         if (A.probe_out != nullptr && j == P.probe_row && P.probe_elem >= (long long)e0 && P.probe_elem < (long long)e0 + VEC)
             *A.probe_out = pv[(int)(P.probe_elem - (long long)e0)];
+    }
+}
+
+// Row walk: the sweeps of ONE probe (N = 1: layer sweeps, weighted_subtree_ebp) push up to 48 gradient rows through the same saved
+// tensors.  Here a thread owns 4 channels of one pixel and walks R gradient rows: (a, x), the BatchNorm constants and the pre / post
+// scales of every link are computed once and kept in registers (NL, the chain length, is a template constant so that they stay
+// there), and a row costs its gradient load, the hook arithmetic and its stores - about half of what the row-per-thread kernel
+// above spends per (row, link, element) (ncu r2u: that kernel is issue-bound at ~210 instructions per thread of a five-link chain).
+// Same operations on every element in the same order: bit-identical.
+template <int MODE, int NL, int R>
+__global__ void __launch_bounds__(256) hook_rows_kernel(HookChain ch, HookIdx ix) {
+    const HookArgs& A0 = ch.a[0];
+    const unsigned il = blockIdx.x * blockDim.x + threadIdx.x;         // position inside a gradient row
+    if (il >= ix.per_row) return;
+    const unsigned Cv = (unsigned)A0.C / 4;
+    const unsigned pix = ix.cv_shift >= 0 ? il >> ix.cv_shift : il / Cv;
+    const int c = (int)(il - pix * Cv) * 4;
+    const int h = (int)(ix.w_magic ? __umulhi(pix, ix.w_magic) : pix / (unsigned)A0.W);
+    const int w = (int)(pix - (unsigned)h * (unsigned)A0.W);
+    const size_t ms = pix;                                              // N == 1: the saved tensors of the one probe
+    auto ld4v = [&](const float* q, float* v) { const float4 t = *reinterpret_cast<const float4*>(q); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; };
+    auto st4v = [&](float* q, const float* v) { *reinterpret_cast<float4*>(q) = make_float4(v[0], v[1], v[2], v[3]); };
+    // ---- per link, once per thread
+    float a[NL][4], x[NL][4], ps[NL][4], pre[NL][4];
+    int prow[NL], qrow[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        const HookArgs& A = ch.a[l];
+        BnC b[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { b[q] = {0.f, 0.f, 0.f, 0.f}; ps[l][q] = 1.f; pre[l][q] = 1.f; }
+        if (A.bn != nullptr) {
+            float al[4], be[4], sp[4], tp[4];
+            ld4v(A.bn + c, al); ld4v(A.bn + A.C + c, be); ld4v(A.bn + 2 * A.C + c, sp); ld4v(A.bn + 3 * A.C + c, tp);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) b[q] = {al[q], be[q], sp[q], tp[q]};
+        }
+        if (A.post_scale_row >= 0) ld4v(A.bn + A.post_scale_row * A.C + c, ps[l]);
+        if (A.pre_scale_row >= 0) ld4v(A.bn + A.pre_scale_row * A.C + c, pre[l]);
+        float v0[4] = {0.f, 0.f, 0.f, 0.f}, v1[4] = {0.f, 0.f, 0.f, 0.f}, v2[4] = {0.f, 0.f, 0.f, 0.f};
+        const int rc = A.recipe;
+        if (A.s0 != nullptr && c < A.c0) ld4v(A.s0 + ms * A.c0 + c, v0);
+        if (rc >= 3) ld4v(A.s1 + ms * A.C + c, v1);
+        if ((rc == 4 || rc == 8) && A.s2 != nullptr && c < A.c2s) ld4v(A.s2 + ms * A.c2s + c, v2);
+        if (rc == 6) ld4v(A.s2 + ms * A.C + c, v2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) hook_ax(rc, v0[q], v1[q], v2[q], b[q], a[l][q], x[l][q]);
+        prow[l] = A.ptab != nullptr ? A.ptab->row : A.prior_row;
+        qrow[l] = (A.ptab != nullptr && A.probe_out != nullptr) ? A.ptab->probe_row : -1;
+    }
+    const int us = ix.up_shift;
+    const bool on = us >= 0 ? (((h | w) & ((1 << us) - 1)) == 0) : (h % A0.up == 0 && w % A0.up == 0);
+    const int Hm = us >= 0 ? A0.H >> us : A0.H / A0.up, Wm = us >= 0 ? A0.W >> us : A0.W / A0.up;
+    const int hm = us >= 0 ? h >> us : h / A0.up, wm = us >= 0 ? w >> us : w / A0.up;
+    const int Hr = A0.H / A0.k2, Wr = A0.W / A0.k2, hr = h / A0.k2, wr = w / A0.k2;
+    const float kk = (float)(A0.k2 * A0.k2);
+    const size_t e0 = ((size_t)h * A0.W + w) * A0.C + c;
+    // ---- the gradient rows
+    const int jend = min(A0.J, (int)(blockIdx.y + 1) * R);
+    for (int j = blockIdx.y * R; j < jend; ++j) {
+        int first = 0;
+        bool zero_in = false;
+        if (ch.row_start != nullptr) {
+            const int s0 = ch.row_start[j] - ch.k0;
+            if (s0 >= 0) { first = s0 < NL ? s0 : NL; zero_in = true; }
+        }
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        const size_t off = ((size_t)j * ix.per_row + il) * 4;
+        if (!zero_in) {
+            if (A0.z_in != nullptr && on) ld4v(A0.z_in + (((size_t)j * Hm + hm) * Wm + wm) * A0.zc + c, z);
+            if (A0.z_in2 != nullptr && c < A0.c2) {
+                float t[4];
+                ld4v(A0.z_in2 + (((size_t)j * Hr + hr) * Wr + wr) * A0.c2 + c, t);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) z[q] = __fadd_rn(z[q], __fdiv_rn(t[q], kk));
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            const HookArgs& A = ch.a[l];
+            if (l < first) {                                             // before the row's start: zeros where a tensor is kept
+                if (A.P_out != nullptr) st4v(A.P_out + off, z);
+                if (A.z_out != nullptr) st4v(A.z_out + off, z);
+                continue;
+            }
+            if (!(zero_in && l == first)) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) z[q] = __fmul_rn(z[q], A.pre_scale);
+                if (A.pre_scale_row >= 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) z[q] = __fmul_rn(z[q], pre[l][q]);
+                }
+            }
+            HookPrior P;
+            P.row = prow[l]; P.probe_row = qrow[l]; P.elem = 0; P.val = 0.f; P.tensor = nullptr; P.probe_elem = -1;
+            const bool has_prior = ((MODE >= 0 ? MODE : A.mode) != XFRB_MODE_NONE) && (j == P.row);
+            if (has_prior) {
+                if (A.ptab != nullptr) { P.elem = A.ptab->elem; P.val = A.ptab->val; P.tensor = A.ptab->tensor; }
+                else { P.elem = A.prior_elem; P.val = A.prior_val; P.tensor = A.prior; }
+            }
+            float pv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) z[q] = hook_fire<MODE>(A, P, has_prior, e0 + q, ps[l][q], z[q], a[l][q], x[l][q], pv[q]);
+            if (A.P_out != nullptr) st4v(A.P_out + off, pv);
+            if (A.z_out != nullptr) {
+                if (A.out_pair) st_pair4(A.z_out, (size_t)j * ((size_t)A0.H * A0.W) + pix, A0.C, c, z);
+                else st4v(A.z_out + off, z);
+            }
+            if (j == P.probe_row) {
+                const long long pe = A.ptab->probe_elem;
+                if (pe >= (long long)e0 && pe < (long long)e0 + 4) *A.probe_out = pv[(int)(pe - (long long)e0)];
+            }
+        }
     }
 }
 
@@ -961,6 +1077,22 @@ cudaError_t launch_hook_chain(const HookChain& ch, cudaStream_t st) {
     int mode = a0.mode;
     for (int l = 1; l < ch.n; ++l)
         if (ch.a[l].mode != mode) mode = -1;
+    // row walk (hook_rows_kernel): sweeps of one probe with enough gradient rows, vector path, a chain length it is instantiated for
+    static const int rows_on = [] { const char* e = getenv("XFRB_HOOK_ROWS"); return e ? atoi(e) : 1; }();       // A/B probe: 0 = off
+    if (rows_on && V == 4 && a0.N == 1 && a0.J >= 8 && a0.mfm_c == nullptr && mode >= 0 && (ch.n == 1 || ch.n == 2 || ch.n == 3 || ch.n == 5)) {
+        constexpr int R = 8;
+        const dim3 grid_r((ix.per_row + 255) / 256, (unsigned)((a0.J + R - 1) / R));
+#define XFRB_ROWS_MODE(NL_)                                                                                  \
+        switch (mode) {                                                                                      \
+            case XFRB_MODE_AWP: hook_rows_kernel<XFRB_MODE_AWP, NL_, R><<<grid_r, 256, 0, st>>>(ch, ix); break;            \
+            case XFRB_MODE_ALL: hook_rows_kernel<XFRB_MODE_ALL, NL_, R><<<grid_r, 256, 0, st>>>(ch, ix); break;            \
+            case XFRB_MODE_AFFINEONLY: hook_rows_kernel<XFRB_MODE_AFFINEONLY, NL_, R><<<grid_r, 256, 0, st>>>(ch, ix); break; \
+            default: hook_rows_kernel<XFRB_MODE_NONE, NL_, R><<<grid_r, 256, 0, st>>>(ch, ix); break;        \
+        }
+        if (ch.n == 1) { XFRB_ROWS_MODE(1) } else if (ch.n == 2) { XFRB_ROWS_MODE(2) } else if (ch.n == 3) { XFRB_ROWS_MODE(3) } else { XFRB_ROWS_MODE(5) }
+#undef XFRB_ROWS_MODE
+        return cudaGetLastError();
+    }
     const dim3 grid((ix.per_row + 255) / 256, (unsigned)a0.J);
 #define XFRB_HOOK_LAUNCH(V_)                                                                   \
     switch (mode) {                                                                            \

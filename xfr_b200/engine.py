@@ -44,6 +44,7 @@ class _Engine(object):
         self.eps = eps
         self._ws = {}
         self._graphs = {}             # CUDA graphs of small-batch sweeps (graph_call); dropped whenever a workspace buffer moves
+        self.graph_captures = 0       # captures made so far (a steady-state caller should see this stop growing)
         self.graph_max_n = 2          # batch sizes whose ebp / contrastive sweeps are replayed from a captured graph (0: never)
         # bf16x2 plan: the GEMM operands of the fused sweep (block inputs, inner activations, y1 / y2 / y3) are PAIR tensors -
         # rows of [C bf16 hi | C bf16 lo], the same bytes as fp32 (include/xfrb.h XFRB_IMPL_BF16X2) - written by the producing
@@ -102,6 +103,7 @@ class _Engine(object):
                 return fn(*tensors, **opts)
             ent.update(graph=g, ins=ins, out=out, launches=getattr(self.be, 'launches', 0) - l0)
             self.be.launches = l0                         # nothing ran yet: the replay below counts them
+            self.graph_captures += 1
         else:
             for a, t, p in zip(ent['ins'], tensors, static):
                 if p is None:
@@ -172,6 +174,7 @@ class _Engine(object):
                 return fn()
             ent.update(graph=g, out=out, launches=getattr(self.be, 'launches', 0) - l0)
             self.be.launches = l0
+            self.graph_captures += 1
         ent['graph'].replay()
         self.be.launches += ent['launches']
         return ent['out']
