@@ -490,9 +490,8 @@ def run_extra(args, rank, local, world):
 
 
 def main():
-    # stdout carries ONE JSON line: NCCL's version banner (NCCL_DEBUG=VERSION, as some boxes set it) would be a second one
-    if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
-        os.environ['NCCL_DEBUG'] = 'WARN'
+    # stdout carries ONE JSON line: whatever NCCL has to say (the boxes set NCCL_DEBUG=VERSION: a version banner) goes to stderr
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
