@@ -264,7 +264,7 @@ def run_reference(args, rank):
     tot = sum(t_steps)
     v = per_step * args.steps / tot
     sample = '%d triplets per step, batch 1, torch CPU fp32, %d threads' % (per_step, cores)
-    print(json.dumps({
+    emit(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'maps/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * tot / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -355,7 +355,7 @@ def run_extra(args, rank, local, world):
             cpu_port_extra(args.workload, 2.0, cores)
         vals = [cpu_port_extra(args.workload, 6.0, cores) for _ in range(max(1, args.steps))]
         v = sum(x[0] for x in vals) / len(vals)
-        print(json.dumps({'impl': 'reference', 'metric': metric, 'value': v, 'unit': unit, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        emit(json.dumps({'impl': 'reference', 'metric': metric, 'value': v, 'unit': unit, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
                           'ms_per_step': 6000.0, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                           'config': {'workload': label + ' (bounded sample)', 'sample': vals[-1][1]},
                           'cpu_baseline': {'value': v, 'unit': unit, 'cores': cores, 'kind': 'port', 'sample': vals[-1][1]},
@@ -484,14 +484,29 @@ def run_extra(args, rank, local, world):
         v, sample = cpu_port_extra(args.workload, 12.0, cores)
         out['cpu_baseline'] = {'value': v, 'unit': unit, 'cores': cores, 'kind': 'port', 'sample': sample}
     if rank == 0:
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The ONE line this program puts on its standard output."""
+    if _RESULT_FD is None:
+        print(line, flush=True)
+    else:
+        os.write(_RESULT_FD, (line + '\n').encode())
+
+
 def main():
-    # stdout carries ONE JSON line: whatever NCCL has to say (the boxes set NCCL_DEBUG=VERSION: a version banner) goes to stderr
-    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+    # stdout carries ONE JSON line.  Libraries write there too (the boxes set NCCL_DEBUG=VERSION: NCCL prints its version banner on
+    # stdout at communicator set-up), so file descriptor 1 is pointed at stderr for the run and the result goes to the saved one.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
@@ -655,7 +670,7 @@ def main():
                                        'container (BASELINE.md section 2) and cannot travel to the GPU box',
                                'reference_measured_maps_per_s_8_cores': 0.73}
     if rank == 0:
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
