@@ -21,6 +21,8 @@ Backward rows: the gradient batch holds J = G*N rows (G seed groups, e.g. mate a
 non-mate, over the same N probes); row j reads the saved tensors of sample j % N, so
 the two contrastive sweeps share one forward and run as one batch.
 """
+import os
+
 import torch
 
 from . import packing
@@ -45,7 +47,8 @@ class _Engine(object):
         self._ws = {}
         self._graphs = {}             # CUDA graphs of small-batch sweeps (graph_call); dropped whenever a workspace buffer moves
         self.graph_captures = 0       # captures made so far (a steady-state caller should see this stop growing)
-        self.graph_max_n = 2          # batch sizes whose ebp / contrastive sweeps are replayed from a captured graph (0: never)
+        # batch sizes whose ebp / contrastive sweeps are replayed from a captured graph (0: never; XFRB_GRAPH_MAX_N: A/B probe)
+        self.graph_max_n = int(os.environ.get('XFRB_GRAPH_MAX_N', '2'))
         # bf16x2 plan: the GEMM operands of the fused sweep (block inputs, inner activations, y1 / y2 / y3) are PAIR tensors -
         # rows of [C bf16 hi | C bf16 lo], the same bytes as fp32 (include/xfrb.h XFRB_IMPL_BF16X2) - written by the producing
         # kernel; block outputs are kept in fp32 as well (residuals and hook chains read them)
