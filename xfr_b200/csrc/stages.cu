@@ -650,12 +650,128 @@ __global__ void __launch_bounds__(256) stem_bwd_b_kernel(const float* __restrict
     }
 }
 
+// The same stage with one thread per 2x2 block of stem pixels x 4 channels (needs the arg-max bytes of the forward sweep).  The four
+// pixels of a quad (2i + dh, 2j + dw) only ever belong to the pooling windows ph in {i - 1 + PAD, i + PAD} x pw likewise: four
+// (arg byte, gradient) pairs are loaded for four pixels instead of nine, and with PAD a template constant which windows a pixel
+// belongs to, and its position inside each, are compile-time facts - the per-pixel kernel above spent a third of its ~380
+// instructions per thread evaluating them at run time (ncu r2ah: 61 % issue-active at 2.2 TB/s).  Same additions in the same order
+// (windows in (a, b2) order), same channel-sum tree: bit-identical.
+template <int PAD, int MODE>
+__global__ void __launch_bounds__(256) stem_bwd_quad_kernel(const float* __restrict__ zc, const float* __restrict__ o,
+                                                            const float* __restrict__ bn, float* __restrict__ P2,
+                                                            float* __restrict__ chansum, double* __restrict__ sums,
+                                                            const unsigned char* __restrict__ mp_arg, int N, float eps) {
+    // grid: (56*56*16/256, J)
+    __shared__ double red[8];
+    const int j = blockIdx.y, n = j % N;
+    const int t = blockIdx.x * 256 + threadIdx.x;      // < 56*56*16
+    const int c = (t & 15) * 4;
+    const int quad = t >> 4;
+    const int qi = quad / 56, qj = quad % 56;
+    float4 al = ld4(bn + c), be = ld4(bn + 64 + c), sp = ld4(bn + 128 + c), tp = ld4(bn + 192 + c);
+    const float alv[4] = {al.x, al.y, al.z, al.w}, bev[4] = {be.x, be.y, be.z, be.w};
+    const float spv[4] = {sp.x, sp.y, sp.z, sp.w}, tpv[4] = {tp.x, tp.y, tp.z, tp.w};
+    // the four candidate windows [wy][wx]: ph = qi - 1 + PAD + wy, pw = qj - 1 + PAD + wx
+    uchar4 am[2][2];
+    float4 gz[2][2];
+    bool ok[2][2];
+#pragma unroll
+    for (int wy = 0; wy < 2; ++wy)
+#pragma unroll
+        for (int wx = 0; wx < 2; ++wx) {
+            const int ph = qi - 1 + PAD + wy, pw = qj - 1 + PAD + wx;
+            ok[wy][wx] = ph >= 0 && ph < 56 && pw >= 0 && pw < 56;
+            const int phc = ok[wy][wx] ? ph : 0, pwc = ok[wy][wx] ? pw : 0;
+            am[wy][wx] = __ldg(reinterpret_cast<const uchar4*>(mp_arg) + (((size_t)n * 56 + phc) * 56 + pwc) * 16 + (c >> 2));
+            gz[wy][wx] = ld4(zc + (((size_t)j * 56 + phc) * 56 + pwc) * 64 + c);
+        }
+    const float* ob = o + (size_t)n * 112 * 112 * 64 + c;
+    float4 ov4[2][2];
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+        for (int dw = 0; dw < 2; ++dw) ov4[dh][dw] = ld4(ob + ((size_t)(2 * qi + dh) * 112 + (2 * qj + dw)) * 64);
+    double dsum = 0.0;
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+        for (int dw = 0; dw < 2; ++dw) {
+            const int pix = (2 * qi + dh) * 112 + (2 * qj + dw);
+            const float ov[4] = {ov4[dh][dw].x, ov4[dh][dw].y, ov4[dh][dw].z, ov4[dh][dw].w};
+            float z[4] = {0.f, 0.f, 0.f, 0.f};
+            // windows in the order of the per-pixel kernel: a = 0, 1 (ph = (h + PAD) / 2 - a), b2 = 0, 1
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                constexpr int dummy = 0; (void)dummy;
+                const int ky = (dh + PAD) / 2 - a;                         // ph = qi + ky
+                if (!(2 * ky - PAD <= dh && dh <= 2 * ky - PAD + 2)) continue;
+                const int wy = ky + 1 - PAD;                               // index into the loaded windows
+                if (wy < 0 || wy > 1) continue;
+                const int my = dh - 2 * ky + PAD;                          // row inside the window
+#pragma unroll
+                for (int b2 = 0; b2 < 2; ++b2) {
+                    const int kx = (dw + PAD) / 2 - b2;
+                    if (!(2 * kx - PAD <= dw && dw <= 2 * kx - PAD + 2)) continue;
+                    const int wx = kx + 1 - PAD;
+                    if (wx < 0 || wx > 1) continue;
+                    const int me_idx = my * 3 + (dw - 2 * kx + PAD);
+                    if (!ok[wy][wx]) continue;
+                    if (am[wy][wx].x == me_idx) z[0] = __fadd_rn(z[0], gz[wy][wx].x);
+                    if (am[wy][wx].y == me_idx) z[1] = __fadd_rn(z[1], gz[wy][wx].y);
+                    if (am[wy][wx].z == me_idx) z[2] = __fadd_rn(z[2], gz[wy][wx].z);
+                    if (am[wy][wx].w == me_idx) z[3] = __fadd_rn(z[3], gz[wy][wx].w);
+                }
+            }
+            float p[4];
+            float csum = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float r = fmaxf(__fadd_rn(__fmul_rn(ov[q], alv[q]), bev[q]), 0.f);
+                const float ro = fmaxf(ov[q], 0.f);
+                const float xrelu = fmaxf(__fadd_rn(__fmul_rn(ro, spv[q]), tpv[q]), 0.f);
+                float zz = hook<false>(r, xrelu, z[q], MODE, eps);   // ReLU hook
+                zz = hook<false>(r, r, zz, MODE, eps);               // MaxPool2d hook
+                zz = r > 0.f ? zz : 0.f;
+                zz = __fmul_rn(zz, spv[q]);
+                p[q] = __fmul_rn(ro, fmaxf(zz, 0.f));                // BatchNorm hook records P[-2]
+                csum += p[q];
+            }
+            st4(P2 + ((size_t)j * 112 * 112 + pix) * 64 + c, make_float4(p[0], p[1], p[2], p[3]));
+            for (int o2 = 8; o2 > 0; o2 >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o2);    // the 16 lanes that share a pixel
+            if ((threadIdx.x & 15) == 0) {
+                chansum[(size_t)j * 112 * 112 + pix] = csum;
+                dsum += (double)csum;
+            }
+        }
+    for (int o2 = 16; o2 > 0; o2 >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o2);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tsum = 0.0;
+        for (int k = 0; k < 8; ++k) tsum += red[k];
+        atomicAdd(sums + j, tsum);
+    }
+}
+
 cudaError_t launch_stem_bwd(const float* zmain, const float* gres, const float* o, const float* mp, const float* bn,
                             float* zc, float* P2, float* chansum, double* sums, const unsigned char* mp_arg, int J, int N,
                             int mode, float eps, int pool_pad, cudaStream_t st) {
     size_t per4 = (size_t)56 * 56 * 16, total4 = per4 * J;
     cudaMemsetAsync(sums, 0, sizeof(double) * J, st);
     stem_bwd_a_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(zmain, gres, mp, zc, per4, N, mode, eps, total4);
+    static const int quad = [] { const char* e = getenv("XFRB_STEM_QUAD"); return e ? atoi(e) : 1; }();       // A/B probe: 0 = the per-pixel kernel
+    if (quad && mp_arg != nullptr && (pool_pad == 0 || pool_pad == 1) && mode >= 0 && mode <= 2 && J <= 65535) {
+        const dim3 grid(56 * 56 * 16 / 256, J);
+#define XFRB_QUAD(PAD_)                                                                                                          \
+        switch (mode) {                                                                                                          \
+            case XFRB_MODE_AWP: stem_bwd_quad_kernel<PAD_, XFRB_MODE_AWP><<<grid, 256, 0, st>>>(zc, o, bn, P2, chansum, sums, mp_arg, N, eps); break;   \
+            case XFRB_MODE_ALL: stem_bwd_quad_kernel<PAD_, XFRB_MODE_ALL><<<grid, 256, 0, st>>>(zc, o, bn, P2, chansum, sums, mp_arg, N, eps); break;   \
+            default: stem_bwd_quad_kernel<PAD_, XFRB_MODE_AFFINEONLY><<<grid, 256, 0, st>>>(zc, o, bn, P2, chansum, sums, mp_arg, N, eps); break;     \
+        }
+        if (pool_pad == 1) { XFRB_QUAD(1) } else { XFRB_QUAD(0) }
+#undef XFRB_QUAD
+        return cudaGetLastError();
+    }
     stem_bwd_b_kernel<<<dim3(112 * 112 * 16 / 256, J), 256, 0, st>>>(zc, o, bn, P2, chansum, sums, mp_arg, N, mode, eps, pool_pad);
     return cudaGetLastError();
 }
