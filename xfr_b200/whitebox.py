@@ -29,6 +29,7 @@ from .engine import MODE_IDS, Resnet50_128Engine, StResnetEngine
 from .lightcnn import LightCNNEngine
 
 _CHUNK = 128    # probes per engine sweep (workspace = ~210 MB per probe)
+_MAX_ROWS = 64  # gradient rows of one firing-by-firing sweep (generic.MAX_ROWS)
 # The GEMM plan of the fused sweep (xfr_b200/kernels.py).  'bf16x2' (tcgen05 kind::f16 on bf16 terms, pair-tensor operands) is the
 # default because on the B200 it is as close to the reference as the three-pass TF32 plan: what separates every tensor-core plan
 # from the reference is the tensor core's truncating fp32 accumulation, not the operand precision (on the
@@ -673,6 +674,7 @@ class Whitebox(nn.Module):
         todo = sorted(priors)                                             # one gradient row per distinct firing
         maps = {}
         tab = eng.prior_table('rows')
+        rows_per_sweep = max(1, min(int(rows_per_sweep), _MAX_ROWS))                                    # a prior table describes up to 64 rows
         Z = torch.zeros(min(rows_per_sweep, max(len(todo), 1)), self.net.num_classes(), device=dev)     # fixed row count: one graph
         for i in range(0, len(todo), Z.shape[0]):
             chunk = todo[i:i + Z.shape[0]]
@@ -748,6 +750,7 @@ class Whitebox(nn.Module):
         seeds = [(int(k), int(P_subtree_idx[k]), float(p_at[k])) for k in k_subtree]
         P_img = []
         tab = eng.prior_table('rows')
+        rows_per_sweep = max(1, min(int(rows_per_sweep), _MAX_ROWS))                             # a prior table describes up to 64 rows
         Z = torch.zeros(min(rows_per_sweep, len(seeds)), self.net.num_classes(), device=dev)     # fixed row count: one graph
         for i in range(0, len(seeds), Z.shape[0]):
             chunk = seeds[i:i + Z.shape[0]]
